@@ -1,0 +1,286 @@
+// gmb_core.h — rank arithmetic on the 64-byte blocks and the per-k-mer search state machine.
+//
+// One "chain" (a CUDA thread in map_kernel.cu) owns one k-mer start at a time and walks the
+// bidirectional FM-index with the optimum-search-scheme bounds.  The recursion of the reference
+// (_optimalSearchSchemeGM/-ChildrenGM/-ExactGM, src/find2_index_approx.hpp:223-428, plus the by-value
+// iterator copies that act as its stack) is restated as an explicit state machine:
+//   * every loop iteration expands exactly ONE node: two rank-block reads (one if both interval
+//     ends fall into the same block) give the ranks of all four symbols at both ends, hence all
+//     children and every `smaller` of index_fm_stree.h:256-278 / index_bifm_stree.h:46-58 at once;
+//   * mismatching children are visited before the matching one, so the walk at error level e needs
+//     exactly one saved frame: at most E frames per chain, kept in shared memory;
+//   * a full-length node adds its interval size to the k-mer's count (countOccurrences,
+//     src/algo.hpp:48,191), saturating at the value type's maximum.
+// The same header is compiled for the host by the CPU tests (tests/hostsim) to debug the logic and to
+// count rank-block fetches without a GPU; the product library only instantiates it in device code.
+#pragma once
+#include "gmb_layout.h"
+
+namespace gmb {
+
+struct Ranks { uint32_t a, c, g, t, s; };
+
+struct BlockRegs {
+    uint32_t h[4];
+    uint64_t w[3][2];
+};
+
+GMB_HD uint32_t popc64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popcll(x);
+#else
+    return (uint32_t)__builtin_popcountll(x);
+#endif
+}
+
+GMB_HD BlockRegs load_block(const RankBlock* p)
+{
+    BlockRegs b;
+#if defined(__CUDA_ARCH__)
+    // one 64-byte block = two 256-bit read-only loads (LDG.E.256 on sm_100a)
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7, s0, s1, s2, s3, s4, s5, s6, s7;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                 : "l"(p));
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7)
+                 : "l"(reinterpret_cast<const char*>(p) + 32));
+    b.h[0] = r0; b.h[1] = r1; b.h[2] = r2; b.h[3] = r3;
+    b.w[0][0] = ((uint64_t)r5 << 32) | r4; b.w[0][1] = ((uint64_t)r7 << 32) | r6;
+    b.w[1][0] = ((uint64_t)s1 << 32) | s0; b.w[1][1] = ((uint64_t)s3 << 32) | s2;
+    b.w[2][0] = ((uint64_t)s5 << 32) | s4; b.w[2][1] = ((uint64_t)s7 << 32) | s6;
+#else
+    b.h[0] = p->cnt[0]; b.h[1] = p->cnt[1]; b.h[2] = p->cnt[2]; b.h[3] = p->sent;
+    for (int k = 0; k < 3; ++k) { b.w[k][0] = p->w[k][0]; b.w[k][1] = p->w[k][1]; }
+#endif
+    return b;
+}
+
+GMB_HD uint64_t low_mask(int bits)
+{
+    return bits <= 0 ? 0ull : (bits >= 64 ? ~0ull : ((1ull << bits) - 1ull));
+}
+
+// ranks of all symbols at BWT position i = blk*192 + r  (rank_c(i) = #c in bwt[0,i))
+GMB_HD Ranks block_rank(const BlockRegs& b, uint32_t r, uint32_t i, const uint32_t* sent_pos)
+{
+    uint32_t a = 0, c = 0, g = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        uint64_t m = low_mask((int)r - 64 * k);
+        uint64_t p0 = b.w[k][0], p1 = b.w[k][1];
+        a += popc64(~(p0 | p1) & m);
+        c += popc64(p0 & ~p1 & m);
+        g += popc64(~p0 & p1 & m);
+    }
+    uint32_t s_before = b.h[3] >> 8, s_in = b.h[3] & 0xffu, s = 0;
+    if (s_in) // rare: this block holds sentinel rows (stored as code 0)
+        for (uint32_t k = 0; k < s_in; ++k) s += sent_pos[s_before + k] < i;
+    Ranks R;
+    R.a = b.h[0] + a - s;
+    R.c = b.h[1] + c;
+    R.g = b.h[2] + g;
+    R.s = s_before + s;
+    R.t = i - R.a - R.c - R.g - R.s;
+    return R;
+}
+
+// ---- pattern -----------------------------------------------------------------------------------------
+template <int KW>
+struct Pattern {
+    uint64_t w[KW];
+    GMB_HD uint32_t at(uint32_t i) const
+    {
+        if (KW == 1) return (uint32_t)(w[0] >> (2 * i)) & 3u;
+        return (uint32_t)(w[i >> 5] >> (2 * (i & 31))) & 3u;
+    }
+};
+
+// 2-bit packed text (32 bases per uint64, base i in bits 2*(i&31)) -> the K bases starting at `pos`
+template <int KW>
+GMB_HD void load_pattern(Pattern<KW>& p, const uint64_t* text, uint64_t pos, uint32_t K)
+{
+    uint64_t wi = pos >> 5;
+    uint32_t sh = 2u * (uint32_t)(pos & 31);
+#pragma unroll
+    for (int k = 0; k < KW; ++k) {
+        if (32u * k >= K) { p.w[k] = 0; continue; }
+        uint64_t lo = text[wi + k], hi = text[wi + k + 1];
+        uint64_t v = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+        uint32_t left = K - 32u * k;
+        if (left < 32) v &= (1ull << (2 * left)) - 1ull;
+        p.w[k] = v;
+    }
+}
+
+// ---- search context ------------------------------------------------------------------------------------
+struct MapCtx {
+    const RankBlock* blk[2];  // [0]: BWT of T (extend left), [1]: BWT of T' (extend right)
+    const uint32_t* sent[2];
+    uint32_t C[4];
+    uint32_t n_bwt;
+    const uint32_t* steps;    // n_search * K packed steps (gmb_layout.h)
+    uint32_t K, n_search, n_strands, maxv;
+};
+
+template <int KW>
+struct Chain {
+    Pattern<KW> pat;
+    uint32_t lo_f, lo_r, size; // current node: [lo_f, lo_f+size) in SA(T), [lo_r, lo_r+size) in SA(T')
+    uint32_t acc;              // occurrences so far (saturating)
+    uint32_t t, e, s, strand;  // step, errors, search, strand of the current walk
+    uint32_t lvmask;           // error levels holding a frame with pending children
+};
+
+// frame words: 0..3 child lo in the active index, 4..7 child sizes, 8 = lo of child 0 in the other
+// index, 9 = t | pending << 8
+constexpr int kFrameWords = 10;
+
+template <int KW>
+GMB_HD void chain_start(Chain<KW>& st, const MapCtx& cx)
+{
+    st.lo_f = 0; st.lo_r = 0; st.size = cx.n_bwt;
+    st.t = 0; st.e = 0; st.lvmask = 0;
+}
+
+template <int KW>
+GMB_HD void chain_begin_kmer(Chain<KW>& st, const MapCtx& cx)
+{
+    st.acc = 0; st.s = 0; st.strand = 0;
+    chain_start(st, cx);
+}
+
+GMB_HD uint32_t sel4(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t c)
+{
+    return c == 0 ? v0 : (c == 1 ? v1 : (c == 2 ? v2 : v3));
+}
+
+GMB_HD uint32_t lowest_bit_index(uint32_t m)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffs((int)m) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(m);
+#endif
+}
+
+GMB_HD uint32_t highest_bit_index(uint32_t m)
+{
+#if defined(__CUDA_ARCH__)
+    return 31u - (uint32_t)__clz((int)m);
+#else
+    return 31u - (uint32_t)__builtin_clz(m);
+#endif
+}
+
+// One state-machine iteration.  Returns false when the k-mer is finished (st.acc is final).
+// `fetches` counts rank-block reads (the roofline's algorithmic unit), when non-null.
+template <int KW, class Frames>
+GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned long long* fetches)
+{
+    const uint32_t K = cx.K;
+    const uint32_t ent = cx.steps[st.s * K + st.t];
+    const uint32_t dir = step_dir(ent);
+    const uint32_t pos = step_pos(ent);
+    const uint32_t p = st.strand ? 3u - st.pat.at(K - 1 - pos) : st.pat.at(pos);
+
+    // ---- expand the node: ranks of all symbols at both interval ends of the active index ----------
+    const uint32_t x = dir ? st.lo_r : st.lo_f;
+    const uint32_t z = dir ? st.lo_f : st.lo_r;
+    const uint32_t y = x + st.size;
+    const RankBlock* B = cx.blk[dir];
+    const uint32_t* SP = cx.sent[dir];
+    const uint32_t bx = x / kBlockBases, by = y / kBlockBases;
+    BlockRegs rb = load_block(B + bx);
+    const Ranks R0 = block_rank(rb, x - bx * kBlockBases, x, SP);
+    if (by != bx) rb = load_block(B + by);
+    const Ranks R1 = block_rank(rb, y - by * kBlockBases, y, SP);
+    if (fetches) *fetches += 1u + (by != bx);
+
+    const uint32_t n0 = R1.a - R0.a, n1 = R1.c - R0.c, n2 = R1.g - R0.g, n3 = R1.t - R0.t;
+    const uint32_t l0 = cx.C[0] + R0.a, l1 = cx.C[1] + R0.c, l2 = cx.C[2] + R0.g, l3 = cx.C[3] + R0.t;
+    const uint32_t oth0 = z + (R1.s - R0.s);
+
+    // ---- admissible children (search-scheme bounds, find2_index_approx.hpp:388-389,254-258) -------
+    const uint32_t ub = step_ub(ent), lb = step_lb(ent), rem = step_rem(ent);
+    uint32_t ok = 0;
+    {
+        const uint32_t em = st.e + 1; // errors after a mismatching child
+        const bool mis_ok = em <= ub && em + rem >= lb;
+        const bool hit_ok = st.e <= ub && st.e + rem >= lb;
+        if (n0 && (p == 0 ? hit_ok : mis_ok)) ok |= 1u;
+        if (n1 && (p == 1 ? hit_ok : mis_ok)) ok |= 2u;
+        if (n2 && (p == 2 ? hit_ok : mis_ok)) ok |= 4u;
+        if (n3 && (p == 3 ? hit_ok : mis_ok)) ok |= 8u;
+    }
+
+    bool descend = false;
+    uint32_t c = 0, csize = 0, cact = 0, coth = 0, ce = 0, ct = 0, cdir = dir;
+
+    if (st.t + 1 == K) {
+        // children are full-length matches: count them (src/algo.hpp:48,191)
+        uint64_t sum = (uint64_t)st.acc + ((ok & 1u) ? n0 : 0u) + ((ok & 2u) ? n1 : 0u) +
+                       ((ok & 4u) ? n2 : 0u) + ((ok & 8u) ? n3 : 0u);
+        st.acc = sum < cx.maxv ? (uint32_t)sum : cx.maxv;
+    } else if (ok) {
+        const uint32_t mm = ok & ~(1u << p);
+        c = mm ? lowest_bit_index(mm) : p; // mismatching children first, the matching child last
+        const uint32_t pending = ok & ~(1u << c);
+        if (pending) {
+            const uint32_t lv = st.e;
+            fr.set(lv, 0, l0); fr.set(lv, 1, l1); fr.set(lv, 2, l2); fr.set(lv, 3, l3);
+            fr.set(lv, 4, n0); fr.set(lv, 5, n1); fr.set(lv, 6, n2); fr.set(lv, 7, n3);
+            fr.set(lv, 8, oth0);
+            fr.set(lv, 9, st.t | (pending << 8));
+            st.lvmask |= 1u << lv;
+        }
+        csize = sel4(n0, n1, n2, n3, c);
+        cact = sel4(l0, l1, l2, l3, c);
+        coth = oth0 + (c > 0 ? n0 : 0u) + (c > 1 ? n1 : 0u) + (c > 2 ? n2 : 0u);
+        ce = st.e + (c != p);
+        ct = st.t + 1;
+        descend = true;
+    }
+
+    if (!descend) {
+        // ---- backtrack: deepest error level that still has pending children ------------------------
+        if (st.lvmask == 0) {
+            // this search is exhausted: next search, next strand, or done
+            if (++st.s == cx.n_search) {
+                st.s = 0;
+                if (++st.strand == cx.n_strands) return false;
+            }
+            chain_start(st, cx);
+            return true;
+        }
+        const uint32_t lv = highest_bit_index(st.lvmask);
+        const uint32_t meta = fr.get(lv, 9);
+        const uint32_t tf = meta & 0xffu;
+        uint32_t pending = meta >> 8;
+        const uint32_t entf = cx.steps[st.s * K + tf];
+        const uint32_t posf = step_pos(entf);
+        const uint32_t pf = st.strand ? 3u - st.pat.at(K - 1 - posf) : st.pat.at(posf);
+        const uint32_t mm = pending & ~(1u << pf);
+        c = mm ? lowest_bit_index(mm) : pf;
+        pending &= ~(1u << c);
+        if (pending) fr.set(lv, 9, tf | (pending << 8));
+        else st.lvmask &= ~(1u << lv);
+        const uint32_t f0 = fr.get(lv, 4), f1 = fr.get(lv, 5), f2 = fr.get(lv, 6);
+        csize = fr.get(lv, 4 + c);
+        cact = fr.get(lv, c);
+        coth = fr.get(lv, 8) + (c > 0 ? f0 : 0u) + (c > 1 ? f1 : 0u) + (c > 2 ? f2 : 0u);
+        ce = lv + (c != pf);
+        ct = tf + 1;
+        cdir = step_dir(entf);
+    }
+
+    st.size = csize;
+    st.e = ce;
+    st.t = ct;
+    if (cdir) { st.lo_r = cact; st.lo_f = coth; }
+    else      { st.lo_f = cact; st.lo_r = coth; }
+    return true;
+}
+
+} // namespace gmb

@@ -1,0 +1,269 @@
+// gmb_host.cpp — step tables, host index builder, blob packing (no CUDA).
+#include "gmb_host.h"
+
+#include <algorithm>
+#include <cstring>
+
+#include "sais.hpp"
+
+namespace gmb {
+
+// ---------------------------------------------------------------------------------------------------
+// Optimum search schemes (Kianfar et al.) in the variant GenMap ships: pi / L / U per search.
+// Values: src/find2_index_approx.hpp:67-134 (they are the algorithm's specification).
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct SchemeDef {
+    uint8_t n_search, n_blocks;
+    uint8_t pi[7][6], lo[7][6], up[7][6];
+};
+const SchemeDef kSchemes[5] = {
+    {1, 1, {{1}}, {{0}}, {{0}}},
+    {2, 2, {{1, 2}, {2, 1}}, {{0, 0}, {0, 1}}, {{0, 1}, {0, 1}}},
+    {3, 4, {{1, 2, 3, 4}, {3, 2, 1, 4}, {4, 3, 2, 1}},
+           {{0, 0, 1, 1}, {0, 0, 0, 0}, {0, 0, 0, 2}},
+           {{0, 0, 2, 2}, {0, 1, 1, 2}, {0, 1, 2, 2}}},
+    {4, 5, {{1, 2, 3, 4, 5}, {2, 3, 4, 5, 1}, {3, 4, 5, 2, 1}, {5, 4, 3, 2, 1}},
+           {{0, 0, 0, 0, 3}, {0, 0, 0, 2, 2}, {0, 0, 1, 1, 1}, {0, 0, 0, 0, 0}},
+           {{0, 1, 2, 3, 3}, {0, 1, 2, 2, 3}, {0, 1, 1, 3, 3}, {0, 0, 3, 3, 3}}},
+    {7, 6, {{1, 2, 3, 4, 5, 6}, {3, 4, 5, 6, 2, 1}, {2, 3, 4, 5, 6, 1}, {3, 2, 4, 5, 6, 1},
+            {4, 3, 2, 5, 6, 1}, {4, 3, 2, 5, 6, 1}, {6, 5, 4, 3, 2, 1}},
+           {{0, 0, 0, 0, 0, 4}, {0, 0, 0, 1, 4, 4}, {0, 0, 0, 0, 0, 0}, {0, 1, 1, 1, 1, 1},
+            {0, 0, 2, 2, 2, 2}, {0, 1, 2, 2, 2, 2}, {0, 0, 0, 0, 3, 3}},
+           {{0, 2, 3, 3, 4, 4}, {0, 0, 1, 1, 4, 4}, {0, 2, 2, 3, 3, 4}, {0, 1, 2, 3, 3, 4},
+            {0, 0, 2, 3, 3, 4}, {0, 1, 2, 3, 3, 4}, {0, 0, 4, 4, 4, 4}}},
+};
+} // namespace
+
+bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err)
+{
+    if (E > kMaxE) { err = "E > 4 not yet supported."; return false; } // src/mappability.hpp:187
+    if (K < E + 2) { err = "K must be at least E + 2."; return false; } // undefined in the reference (rc 139)
+    if (K > kMaxK) { err = "K > 255 is not supported."; return false; }
+    const SchemeDef& sd = kSchemes[E];
+    const uint32_t nb = sd.n_blocks;
+    // block lengths over the whole k-mer: floor(K/nb), the first K mod nb blocks one longer (:164-176)
+    uint32_t len[6], begin[6];
+    for (uint32_t b = 0, o = 0; b < nb; ++b) {
+        len[b] = K / nb + (b < K % nb);
+        begin[b] = o;
+        o += len[b];
+    }
+    out.n_search = sd.n_search;
+    out.K = K;
+    for (uint32_t s = 0; s < sd.n_search; ++s) {
+        uint32_t* st = out.step + s * K;
+        uint32_t t = 0;
+        uint32_t l = begin[sd.pi[s][0] - 1], r = l; // consumed window [l, r)
+        for (uint32_t i = 0; i < nb; ++i) {
+            const uint32_t b = sd.pi[s][i] - 1u;
+            const bool right = (i == 0) || sd.pi[s][i] > sd.pi[s][i - 1]; // :273-285,321
+            for (uint32_t k = 0; k < len[b]; ++k, ++t) {
+                const uint32_t pos = right ? r++ : --l;
+                st[t] = pos | ((len[b] - 1 - k) << 8) | ((uint32_t)sd.up[s][i] << 16) |
+                        ((uint32_t)sd.lo[s][i] << 20) | ((right ? 1u : 0u) << 24);
+            }
+            if (right ? (r != begin[b] + len[b]) : (l != begin[b])) { err = "scheme is not contiguous"; return false; }
+        }
+        if (t != K || l != 0 || r != K) { err = "scheme does not cover the pattern"; return false; }
+        for (uint32_t a = 0; a < K; ++a) { // does a later step go the other way?
+            bool sw = false;
+            for (uint32_t b2 = a + 1; b2 < K; ++b2) sw |= step_dir(st[b2]) != step_dir(st[a]);
+            if (sw) st[a] |= 1u << 25;
+        }
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// blob layout
+// ---------------------------------------------------------------------------------------------------
+static uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+BlobPlan plan_blob(uint64_t n_text, uint32_t n_seq, bool with_sa)
+{
+    BlobPlan p;
+    std::memset(&p.h, 0, sizeof(p.h));
+    IndexHeader& h = p.h;
+    h.magic = kMagic;
+    h.version = kVersion;
+    h.sigma = 4;
+    h.n_text = n_text;
+    h.n_seq = n_seq;
+    h.n_bwt = n_text + n_seq;
+    h.n_blocks = (uint32_t)(h.n_bwt / kBlockBases + 1);
+    uint64_t o = align_up(sizeof(IndexHeader), 256);
+    h.off_fwd = o;        o = align_up(o + (uint64_t)h.n_blocks * sizeof(RankBlock), 256);
+    h.off_rev = o;        o = align_up(o + (uint64_t)h.n_blocks * sizeof(RankBlock), 256);
+    h.off_sent_fwd = o;   o = align_up(o + (uint64_t)n_seq * 4, 256);
+    h.off_sent_rev = o;   o = align_up(o + (uint64_t)n_seq * 4, 256);
+    h.off_text = o;       o = align_up(o + (n_text / 32 + 2) * 8, 256);
+    h.off_limits = o;     o = align_up(o + ((uint64_t)n_seq + 1) * 8, 256);
+    h.off_seq_start = o;  o = align_up(o + ((uint64_t)n_seq + 1) * 4, 256);
+    if (with_sa) { h.off_sa = o; o = align_up(o + h.n_bwt * 4, 256); }
+    h.total_bytes = o;
+    return p;
+}
+
+void pack_bwt_blocks(const uint8_t* bwt, uint64_t n, RankBlock* blocks, uint32_t n_blocks, uint32_t* sent_pos,
+                     uint32_t n_seq, uint64_t tot[4])
+{
+    uint64_t cnt[4] = {0, 0, 0, 0};
+    uint32_t n_sent = 0;
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        RankBlock& B = blocks[b];
+        std::memset(&B, 0, sizeof(B));
+        B.cnt[0] = (uint32_t)cnt[0];
+        B.cnt[1] = (uint32_t)cnt[1];
+        B.cnt[2] = (uint32_t)cnt[2];
+        const uint32_t sent_before = n_sent;
+        for (uint32_t k = 0; k < kBlockBases; ++k) {
+            const uint64_t i = (uint64_t)b * kBlockBases + k;
+            if (i >= n) break;
+            const uint8_t s = bwt[i];
+            if (s < 2) { // sentinel row: stored as code 0, listed on the side
+                if (n_sent < n_seq) sent_pos[n_sent] = (uint32_t)i;
+                ++n_sent;
+                continue;
+            }
+            const uint32_t c = s - 2u;
+            ++cnt[c];
+            B.w[k >> 6][0] |= (uint64_t)(c & 1u) << (k & 63);
+            B.w[k >> 6][1] |= (uint64_t)(c >> 1) << (k & 63);
+        }
+        B.sent = (sent_before << 8) | (n_sent - sent_before);
+    }
+    for (int c = 0; c < 4; ++c) tot[c] = cnt[c];
+}
+
+namespace {
+
+// T (or T') as SA-IS input: '#' = 0 (last symbol, unique smallest), '$' = 1, A,C,G,T = 2..5.
+// Order = the one the reference gets from divsufsort on ord+1 with 0 sentinels
+// (src/seqan_libdivsufsort.h:80-96): '$' < A, comparisons run through sentinels, shorter is smaller.
+void make_symbols(const uint8_t* codes, const uint64_t* limits, uint32_t n_seq, bool reversed, std::vector<uint8_t>& t)
+{
+    const uint64_t n = limits[n_seq] + n_seq;
+    t.resize(n);
+    uint64_t o = 0;
+    for (uint32_t s = 0; s < n_seq; ++s) {
+        const uint64_t b = limits[s], e = limits[s + 1];
+        if (!reversed) for (uint64_t k = b; k < e; ++k) t[o++] = (uint8_t)(codes[k] + 2);
+        else           for (uint64_t k = e; k > b; --k) t[o++] = (uint8_t)(codes[k - 1] + 2); // src/indexing.hpp:130
+        t[o++] = 1;
+    }
+    t[n - 1] = 0;
+}
+
+template <class Idx>
+void build_direction(const std::vector<uint8_t>& t, RankBlock* blocks, uint32_t n_blocks, uint32_t* sent_pos,
+                     uint32_t n_seq, uint64_t tot[4], uint32_t* sa_out)
+{
+    const uint64_t n = t.size();
+    std::vector<Idx> sa(n);
+    suffix_array<Idx>(t.data(), sa.data(), (Idx)n, (Idx)6);
+    std::vector<uint8_t> bwt(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t p = (uint64_t)sa[i];
+        bwt[i] = p ? t[p - 1] : t[n - 1]; // src/seqan_libdivsufsort.h:165-229
+        if (sa_out) sa_out[i] = (uint32_t)p;
+    }
+    pack_bwt_blocks(bwt.data(), n, blocks, n_blocks, sent_pos, n_seq, tot);
+}
+
+} // namespace
+
+bool build_index_host(const uint8_t* codes, const uint64_t* limits, uint32_t n_seq, bool with_sa, Blob& blob,
+                      std::string& err)
+{
+    if (n_seq == 0 || limits[n_seq] == 0) { err = "There is no non-empty sequence in the fasta file(s)."; return false; }
+    if (n_seq > kMaxSeq) { err = "too many sequences (limit 2^24 - 1)"; return false; }
+    const uint64_t n_text = limits[n_seq];
+    const uint64_t n = n_text + n_seq;
+    if (n >= 0xFFFFFFFFull) { err = "index too large: text + sentinels must stay below 2^32 - 1"; return false; }
+    for (uint32_t s = 0; s < n_seq; ++s)
+        if (limits[s + 1] <= limits[s]) { err = "empty sequence in input (skip empty records before indexing)"; return false; }
+    for (uint64_t i = 0; i < n_text; ++i)
+        if (codes[i] > 3) { err = "sequence contains N: Dna5 indices are not supported by the GPU path yet"; return false; }
+
+    BlobPlan plan = plan_blob(n_text, n_seq, with_sa);
+    blob.resize(plan.h.total_bytes);
+    uint8_t* base = blob.data();
+    IndexHeader& h = *reinterpret_cast<IndexHeader*>(base);
+    h = plan.h;
+
+    std::vector<uint8_t> t;
+    uint64_t tot[4];
+    for (int rev = 0; rev < 2; ++rev) {
+        make_symbols(codes, limits, n_seq, rev != 0, t);
+        RankBlock* blocks = reinterpret_cast<RankBlock*>(base + (rev ? h.off_rev : h.off_fwd));
+        uint32_t* sent = reinterpret_cast<uint32_t*>(base + (rev ? h.off_sent_rev : h.off_sent_fwd));
+        uint32_t* sa_out = (!rev && with_sa) ? reinterpret_cast<uint32_t*>(base + h.off_sa) : nullptr;
+        if (n < 0x7FFFFFF0ull) build_direction<int32_t>(t, blocks, h.n_blocks, sent, n_seq, tot, sa_out);
+        else                   build_direction<int64_t>(t, blocks, h.n_blocks, sent, n_seq, tot, sa_out);
+    }
+    // C array with the sentinels counted as smallest symbols (src/seqan_libdivsufsort.h:231-233)
+    h.C[0] = n_seq;
+    for (int c = 0; c < 4; ++c) h.C[c + 1] = h.C[c] + tot[c];
+
+    uint64_t* text = reinterpret_cast<uint64_t*>(base + h.off_text);
+    for (uint64_t i = 0; i < n_text; ++i) text[i >> 5] |= (uint64_t)codes[i] << (2 * (i & 31));
+    uint64_t* lim = reinterpret_cast<uint64_t*>(base + h.off_limits);
+    uint32_t* sst = reinterpret_cast<uint32_t*>(base + h.off_seq_start);
+    for (uint32_t s = 0; s <= n_seq; ++s) { lim[s] = limits[s]; sst[s] = (uint32_t)(limits[s] + s); }
+    return true;
+}
+
+void build_work_ranges(uint64_t text_len, uint32_t K, const uint64_t* chrom_cum, uint32_t n_chrom,
+                       const uint64_t* intervals, uint64_t n_intervals, uint64_t pos_begin, uint64_t pos_end,
+                       std::vector<WorkRange>& out)
+{
+    out.clear();
+    if (pos_end > text_len) pos_end = text_len;
+    std::vector<WorkRange> sel;
+    if (n_intervals) {
+        for (uint64_t k = 0; k < n_intervals; ++k) {
+            WorkRange r{intervals[2 * k], std::min(intervals[2 * k + 1], text_len)};
+            if (r.begin < r.end) sel.push_back(r);
+        }
+        std::sort(sel.begin(), sel.end(), [](const WorkRange& a, const WorkRange& b) { return a.begin < b.begin; });
+        std::vector<WorkRange> merged;
+        for (const WorkRange& r : sel) {
+            if (!merged.empty() && r.begin <= merged.back().end) merged.back().end = std::max(merged.back().end, r.end);
+            else merged.push_back(r);
+        }
+        sel.swap(merged);
+    } else {
+        sel.push_back(WorkRange{0, text_len});
+    }
+    size_t si = 0;
+    for (uint32_t c = 0; c < n_chrom; ++c) {
+        const uint64_t cb = chrom_cum[c], ce = chrom_cum[c + 1];
+        if (ce - cb < K) continue;
+        const uint64_t vb = std::max(cb, pos_begin), ve = std::min(ce - K + 1, pos_end);
+        if (vb >= ve) continue;
+        while (si < sel.size() && sel[si].end <= vb) ++si;
+        for (size_t k = si; k < sel.size() && sel[k].begin < ve; ++k) {
+            const uint64_t b = std::max(vb, sel[k].begin), e = std::min(ve, sel[k].end);
+            if (b < e) out.push_back(WorkRange{b, e});
+        }
+    }
+}
+
+bool validate_blob(const uint8_t* blob, uint64_t bytes, std::string& err)
+{
+    if (bytes < sizeof(IndexHeader)) { err = "index blob too small"; return false; }
+    IndexHeader h;
+    std::memcpy(&h, blob, sizeof(h));
+    if (h.magic != kMagic) { err = "not a genmap-b200 index (bad magic)"; return false; }
+    if (h.version != kVersion) { err = "index version mismatch: rebuild the index"; return false; }
+    if (h.sigma != 4) { err = "only Dna4 indices are supported"; return false; }
+    if (h.total_bytes > bytes) { err = "index blob truncated"; return false; }
+    if (h.n_bwt != h.n_text + h.n_seq || h.n_blocks != h.n_bwt / kBlockBases + 1) { err = "index header inconsistent"; return false; }
+    const uint64_t offs[] = {h.off_fwd, h.off_rev, h.off_sent_fwd, h.off_sent_rev, h.off_text, h.off_limits, h.off_seq_start, h.off_sa};
+    for (uint64_t o : offs)
+        if (o >= h.total_bytes || (o % 256) != 0) { err = "index header offsets out of range"; return false; }
+    return true;
+}
+
+} // namespace gmb

@@ -1,0 +1,53 @@
+// gmb_host.h — host-side pieces of the library that need no CUDA: search-scheme step tables, the host
+// index builder (SA-IS) and the blob packer shared with the GPU builder.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "gmb_layout.h"
+
+namespace gmb {
+
+// Flatten the optimum search scheme for E errors over a pattern of K characters into step tables
+// (scheme tables: src/find2_index_approx.hpp:67-134; block lengths :164-176; start/direction :149-162).
+// Returns false with `err` set if (K,E) is unsupported.
+bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err);
+
+// 256-byte aligned growable byte buffer for the index blob
+struct Blob {
+    std::vector<uint64_t> storage;
+    uint64_t bytes = 0;
+    uint8_t* data() { return reinterpret_cast<uint8_t*>(storage.data()); }
+    const uint8_t* data() const { return reinterpret_cast<const uint8_t*>(storage.data()); }
+    void resize(uint64_t n) { storage.assign((n + 7) / 8, 0); bytes = n; }
+};
+
+// section sizes/offsets for a text of n_text bases in n_seq sequences
+struct BlobPlan {
+    IndexHeader h;
+};
+BlobPlan plan_blob(uint64_t n_text, uint32_t n_seq, bool with_sa);
+
+// Pack one direction's BWT (symbols: 0/1 = sentinel, 2..5 = A,C,G,T) into rank blocks + sentinel list.
+// Returns per-base totals in tot[4].
+void pack_bwt_blocks(const uint8_t* bwt, uint64_t n, RankBlock* blocks, uint32_t n_blocks, uint32_t* sent_pos,
+                     uint32_t n_seq, uint64_t tot[4]);
+
+// Build the whole index on the host.  codes: 0..3 = ACGT (4 = N is rejected: Dna5 indices are not
+// supported by the GPU path yet); limits: n_seq+1 cumulative offsets.
+bool build_index_host(const uint8_t* codes, const uint64_t* limits, uint32_t n_seq, bool with_sa, Blob& blob,
+                      std::string& err);
+
+// Positions whose k-mer is actually searched: inside a sequence with at least K bases left
+// (everything else stays 0: resetLimits, src/algo.hpp:10-22), inside a selection interval if any
+// (src/algo.hpp:441-476), inside [pos_begin, pos_end) (multi-GPU sharding).  Sorted, disjoint.
+struct WorkRange { uint64_t begin, end; };
+void build_work_ranges(uint64_t text_len, uint32_t K, const uint64_t* chrom_cum, uint32_t n_chrom,
+                       const uint64_t* intervals, uint64_t n_intervals, uint64_t pos_begin, uint64_t pos_end,
+                       std::vector<WorkRange>& out);
+
+// sanity-check a blob (magic, version, offsets inside total_bytes)
+bool validate_blob(const uint8_t* blob, uint64_t bytes, std::string& err);
+
+} // namespace gmb

@@ -1,0 +1,90 @@
+// gmb_layout.h — the HBM-resident index layout and the per-(K,E) search step tables.
+//
+// Everything here is plain data shared by the host builder, the GPU builder and the kernels.
+// What it replaces in the reference: SeqAn's EPR rank dictionary (14-byte unaligned entries of 32
+// symbols + superblocks, SEQAN/index/index_fm_rank_dictionary_levels.h:197-209,484-491), the separate
+// sentinel bit-vector dictionary consulted whenever c == 'A' (index_fm_lf_table.h:468-491) and the
+// C array (`lf.sums`, src/seqan_libdivsufsort.h:231-233).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GMB_HD __host__ __device__ __forceinline__
+#else
+#define GMB_HD inline
+#endif
+
+namespace gmb {
+
+// ---- rank block: 64 bytes = one 2-sector DRAM access, 192 BWT symbols -----------------------------
+//   bytes  0..15 : cntA (sentinels NOT counted), cntC, cntG  = occurrences before this block
+//                  sent  = (#sentinels before this block) << 8 | (#sentinels inside this block)
+//   bytes 16..63 : 3 x { plane0 (low code bit) u64, plane1 (high code bit) u64 }, 64 symbols each
+// codes: A=0 C=1 G=2 T=3; a sentinel row is stored as code 0 and listed in `sent_pos`.
+// cntT is derived: T(i) = i - A(i) - C(i) - G(i) - $(i).
+constexpr uint32_t kBlockBases = 192;
+constexpr uint32_t kBlockBytes = 64;
+constexpr uint32_t kMaxSeq = (1u << 24) - 1; // sentinel counter has 24 bits
+constexpr uint32_t kMaxK = 255;              // step tables keep pattern offsets in 8 bits
+constexpr uint32_t kMaxE = 4;                // src/mappability.hpp:187
+constexpr uint32_t kMaxSearches = 7;         // src/find2_index_approx.hpp:121-131
+
+struct alignas(64) RankBlock {
+    uint32_t cnt[3];
+    uint32_t sent;
+    uint64_t w[3][2];
+};
+static_assert(sizeof(RankBlock) == 64, "rank block must be 64 bytes");
+
+// ---- on-disk / in-HBM blob --------------------------------------------------------------------------
+// One contiguous, 256-byte aligned blob; offsets are relative to its start so the same bytes serve as
+// file, pinned host copy and device copy (copied verbatim, broadcast verbatim).
+constexpr uint64_t kMagic = 0x3130584449424d47ULL; // "GMBIDX01"
+constexpr uint32_t kVersion = 2;
+
+struct IndexHeader {
+    uint64_t magic;
+    uint32_t version;
+    uint32_t sigma;          // 4 (Dna4). 5 (Dna5) is rejected by the GPU path for now.
+    uint64_t n_bwt;          // N = text length + one sentinel per sequence
+    uint64_t n_text;         // concatenated text length (no sentinels)
+    uint32_t n_seq;
+    uint32_t n_blocks;       // N / 192 + 1 per direction
+    uint64_t C[6];           // C[c] = #symbols smaller than base c in T (sentinels included); C[4] = N
+    uint64_t off_fwd;        // RankBlock[n_blocks]   BWT of T      (extend left,  reference: Fwd)
+    uint64_t off_rev;        // RankBlock[n_blocks]   BWT of T'     (extend right, reference: Rev)
+    uint64_t off_sent_fwd;   // uint32[n_seq]  sorted BWT rows holding a sentinel
+    uint64_t off_sent_rev;
+    uint64_t off_text;       // uint64[n_text/32 + 2]  2-bit packed concatenated text
+    uint64_t off_limits;     // uint64[n_seq + 1]      sequence limits in the concatenated text
+    uint64_t off_sa;         // uint32[n_bwt] FULL suffix array of T (0 = absent).  The reference samples
+                             // it every 10th text position (src/seqan_libdivsufsort.h:135) to save host
+                             // RAM; 4 bytes/row (12 GB at 3 Gbp) is affordable in 180 GB of HBM and
+                             // makes locate one read instead of an LF walk.  Only -ep / csv need it.
+    uint64_t off_seq_start;  // uint32[n_seq + 1] start of every sequence inside T (limits[i] + i)
+    uint64_t total_bytes;
+    uint64_t reserved[8];
+};
+static_assert(sizeof(IndexHeader) % 8 == 0, "header alignment");
+
+// ---- search step tables -----------------------------------------------------------------------------
+// A search of an optimum search scheme (pi, L, U over nb blocks; src/find2_index_approx.hpp:41-62) is
+// flattened into K steps.  Step t consumes pattern offset `pos` extending right (dir=1, BWT of T') or
+// left (dir=0, BWT of T); a child with e' errors is admissible iff e' <= ub and e' + rem >= lb, where
+// rem = characters of the current block still unread after this one.
+//   bits  0..7  pos      bits  8..15 rem      bits 16..19 ub     bits 20..23 lb    bit 24 dir
+//   bit 25 = the other strand's interval is still needed after this step (a direction switch follows)
+GMB_HD uint32_t step_pos(uint32_t s) { return s & 0xffu; }
+GMB_HD uint32_t step_rem(uint32_t s) { return (s >> 8) & 0xffu; }
+GMB_HD uint32_t step_ub(uint32_t s) { return (s >> 16) & 0xfu; }
+GMB_HD uint32_t step_lb(uint32_t s) { return (s >> 20) & 0xfu; }
+GMB_HD uint32_t step_dir(uint32_t s) { return (s >> 24) & 1u; }
+GMB_HD uint32_t step_sync(uint32_t s) { return (s >> 25) & 1u; }
+
+struct StepTables {
+    uint32_t n_search;
+    uint32_t K;
+    uint32_t step[kMaxSearches * (kMaxK + 1)]; // [search * K + t]
+};
+
+} // namespace gmb

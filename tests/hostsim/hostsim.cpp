@@ -1,0 +1,123 @@
+// hostsim.cpp — TEST INFRASTRUCTURE.  Compiles the kernel's search state machine (gmb_core.h) and the
+// host index builder for the CPU, so that `pytest -m "not gpu"` can check the logic against the oracle
+// and count rank-block fetches without a GPU.  It is never linked into libgenmap_b200.so and is not
+// reachable from the product API: the product path has no CPU fallback.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../genmap_b200/csrc/gmb_core.h"
+#include "../../genmap_b200/csrc/gmb_host.h"
+
+using namespace gmb;
+
+namespace {
+struct HostFrames {
+    uint32_t w[kMaxE][kFrameWords];
+    inline void set(uint32_t lv, uint32_t i, uint32_t v) { w[lv][i] = v; }
+    inline uint32_t get(uint32_t lv, uint32_t i) const { return w[lv][i]; }
+};
+
+template <int KW>
+void run_ranges(const MapCtx& cx, const uint64_t* text, uint64_t text_begin, const std::vector<WorkRange>& ranges,
+                int value_bits, void* out, unsigned long long* fetches)
+{
+    for (const WorkRange& r : ranges)
+        for (uint64_t j = r.begin; j < r.end; ++j) {
+            Chain<KW> st;
+            HostFrames fr;
+            load_pattern(st.pat, text, text_begin + j, cx.K);
+            chain_begin_kmer(st, cx);
+            while (chain_step(st, fr, cx, fetches)) {}
+            if (value_bits == 16) static_cast<uint16_t*>(out)[j] = (uint16_t)st.acc;
+            else static_cast<uint8_t*>(out)[j] = (uint8_t)st.acc;
+        }
+}
+} // namespace
+
+extern "C" {
+
+int hs_build(const uint8_t* codes, const uint64_t* limits, uint32_t n_seq, int with_sa, void** blob_out, uint64_t* bytes)
+{
+    Blob b;
+    std::string err;
+    if (!build_index_host(codes, limits, n_seq, with_sa != 0, b, err)) return -1;
+    void* p = std::malloc(b.bytes);
+    std::memcpy(p, b.data(), b.bytes);
+    *blob_out = p;
+    *bytes = b.bytes;
+    return 0;
+}
+
+void hs_free(void* p) { std::free(p); }
+
+// decode one direction's rank blocks back to symbols (0 = sentinel, 1..4 = A,C,G,T)
+void hs_export_bwt(const void* blob, int rev, uint8_t* out)
+{
+    const uint8_t* base = static_cast<const uint8_t*>(blob);
+    const IndexHeader& h = *reinterpret_cast<const IndexHeader*>(base);
+    const RankBlock* B = reinterpret_cast<const RankBlock*>(base + (rev ? h.off_rev : h.off_fwd));
+    const uint32_t* sent = reinterpret_cast<const uint32_t*>(base + (rev ? h.off_sent_rev : h.off_sent_fwd));
+    for (uint64_t i = 0; i < h.n_bwt; ++i) {
+        const RankBlock& b = B[i / kBlockBases];
+        const uint32_t k = (uint32_t)(i % kBlockBases);
+        out[i] = (uint8_t)(1 + (((b.w[k >> 6][0] >> (k & 63)) & 1) | (((b.w[k >> 6][1] >> (k & 63)) & 1) << 1)));
+    }
+    for (uint32_t s = 0; s < h.n_seq; ++s) out[sent[s]] = 0;
+}
+
+int hs_export_sa(const void* blob, uint32_t* out)
+{
+    const uint8_t* base = static_cast<const uint8_t*>(blob);
+    const IndexHeader& h = *reinterpret_cast<const IndexHeader*>(base);
+    if (!h.off_sa) return -1;
+    std::memcpy(out, base + h.off_sa, h.n_bwt * 4);
+    return 0;
+}
+
+int hs_step_tables(uint32_t K, uint32_t E, uint32_t* n_search, uint32_t* steps)
+{
+    StepTables* t = new StepTables;
+    std::string err;
+    bool ok = build_step_tables(K, E, *t, err);
+    if (ok) { *n_search = t->n_search; std::memcpy(steps, t->step, sizeof(uint32_t) * t->n_search * K); }
+    delete t;
+    return ok ? 0 : -1;
+}
+
+int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bits, uint64_t text_begin,
+           uint64_t text_len, const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t* intervals,
+           uint64_t n_intervals, uint64_t pos_begin, uint64_t pos_end, void* out, unsigned long long* fetches)
+{
+    const uint8_t* base = static_cast<const uint8_t*>(blob);
+    std::string err;
+    const IndexHeader& h = *reinterpret_cast<const IndexHeader*>(base);
+    StepTables* tabs = new StepTables;
+    if (!build_step_tables(K, E, *tabs, err)) { delete tabs; return -2; }
+    MapCtx cx;
+    cx.blk[0] = reinterpret_cast<const RankBlock*>(base + h.off_fwd);
+    cx.blk[1] = reinterpret_cast<const RankBlock*>(base + h.off_rev);
+    cx.sent[0] = reinterpret_cast<const uint32_t*>(base + h.off_sent_fwd);
+    cx.sent[1] = reinterpret_cast<const uint32_t*>(base + h.off_sent_rev);
+    for (int c = 0; c < 4; ++c) cx.C[c] = (uint32_t)h.C[c];
+    cx.n_bwt = (uint32_t)h.n_bwt;
+    cx.steps = tabs->step;
+    cx.K = K; cx.n_search = tabs->n_search; cx.n_strands = revcompl ? 2 : 1;
+    cx.maxv = value_bits == 16 ? 65535u : 255u;
+    std::memset(out, 0, text_len * (value_bits / 8));
+    std::vector<WorkRange> ranges;
+    build_work_ranges(text_len, K, chrom_cum, n_chrom, intervals, n_intervals, pos_begin, pos_end, ranges);
+    const uint64_t* text = reinterpret_cast<const uint64_t*>(base + h.off_text);
+    unsigned long long f = 0;
+    if (K <= 32) run_ranges<1>(cx, text, text_begin, ranges, value_bits, out, &f);
+    else if (K <= 64) run_ranges<2>(cx, text, text_begin, ranges, value_bits, out, &f);
+    else if (K <= 128) run_ranges<4>(cx, text, text_begin, ranges, value_bits, out, &f);
+    else run_ranges<8>(cx, text, text_begin, ranges, value_bits, out, &f);
+    if (fetches) *fetches = f;
+    delete tabs;
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,86 @@
+"""CPU checks of the product's host code and of the kernel's search state machine compiled for the host
+(tests/hostsim): index builder vs the oracle's naive suffix sort, counts vs the oracle / brute force."""
+import numpy as np
+import pytest
+
+import gmtest as T
+
+
+@pytest.mark.parametrize("seed,nchr,length", [(1, 1, 400), (2, 3, 1500), (3, 5, 77), (4, 2, 20000)])
+def test_index_builder_matches_oracle_suffix_sort(seed, nchr, length):
+    seqs = T.repeat_rich(seed, nchr, length)
+    orc, hs = T.Oracle(seqs), T.HostSim(seqs, with_sa=True)
+    for rev in (False, True):
+        a, b = orc.bwt(rev), hs.bwt(rev)
+        assert np.array_equal(np.minimum(a, 5), b), "BWT differs (rev=%s)" % rev
+    assert np.array_equal(orc.sa().astype(np.uint32), hs.sa())
+
+
+def test_index_builder_degenerate_texts():
+    for seqs in ([np.zeros(500, np.uint8)], [np.tile(np.array([0, 1], np.uint8), 300)] * 3,
+                 [np.array([2], np.uint8), np.array([2], np.uint8)], [np.full(193, 3, np.uint8), np.full(191, 3, np.uint8)]):
+        orc, hs = T.Oracle(seqs), T.HostSim(seqs, with_sa=True)
+        for rev in (False, True):
+            assert np.array_equal(orc.bwt(rev), hs.bwt(rev))
+        assert np.array_equal(orc.sa().astype(np.uint32), hs.sa())
+
+
+@pytest.mark.parametrize("K,E", [(30, 0), (30, 1), (30, 2), (21, 3), (16, 4), (50, 2), (12, 2), (9, 1), (8, 0),
+                                 (33, 1), (64, 2), (65, 1), (2, 0), (3, 1), (4, 2), (5, 3), (6, 4), (130, 3)])
+def test_state_machine_matches_oracle(K, E):
+    seqs = T.repeat_rich(7, 3, 3000)
+    orc, hs = T.Oracle(seqs), T.HostSim(seqs)
+    for rc in (True, False):
+        want = orc.map(K, E, revcompl=rc)
+        got = hs.map(K, E, revcompl=rc)
+        assert np.array_equal(got, want), (K, E, rc, np.nonzero(got != want)[0][:10])
+
+
+def test_state_machine_saturation_and_palindromes():
+    seqs = [np.tile(np.array([0, 1, 2, 3], dtype=np.uint8), 2000)]
+    orc, hs = T.Oracle(seqs), T.HostSim(seqs)
+    for bits in (8, 16):
+        want = orc.map(8, 0, value_bits=bits)
+        assert np.array_equal(hs.map(8, 0, value_bits=bits), want)
+        assert want.max() == (255 if bits == 8 else 3998)
+    assert np.array_equal(hs.map(10, 2, value_bits=8), orc.map(10, 2, value_bits=8))
+
+
+def test_state_machine_short_sequences_and_selection():
+    seqs = [np.array([0, 1, 2], np.uint8), T.repeat_rich(3, 1, 300)[0], np.array([3, 3], np.uint8),
+            T.repeat_rich(4, 1, 200)[0], np.array([2], np.uint8)]
+    orc, hs = T.Oracle(seqs), T.HostSim(seqs)
+    assert np.array_equal(hs.map(12, 1), orc.map(12, 1))
+    assert np.array_equal(hs.map(12, 1), T.brute(seqs, 12, 1))
+    iv = [(0, 2), (10, 40), (35, 60), (290, 320), (500, 506)]
+    assert np.array_equal(hs.map(12, 1, intervals=iv), orc.map(12, 1, intervals=iv))
+    # sharding: disjoint position ranges add up to the whole
+    whole = hs.map(12, 1)
+    parts = sum(hs.map(12, 1, pos_begin=b, pos_end=e).astype(np.int64) for b, e in [(0, 100), (100, 333), (333, 506)])
+    assert np.array_equal(parts, whole)
+
+
+def test_multi_file_counts_whole_index():
+    base = T.repeat_rich(13, 2, 1200)
+    rng = np.random.default_rng(5)
+    seqs, stf = [], []
+    for g in range(3):
+        for s in base:
+            s = s.copy()
+            m = rng.random(len(s)) < 0.02 * g
+            s[m] = rng.integers(0, 4, int(m.sum()), dtype=np.uint8)
+            seqs.append(s); stf.append(g)
+    stf = np.array(stf, dtype=np.uint32)
+    orc, hs = T.Oracle(seqs, seq_to_file=stf), T.HostSim(seqs)
+    for f in range(3):
+        assert np.array_equal(hs.map(25, 2, seq_to_file=stf, file_no=f), orc.map(25, 2, file_no=f))
+
+
+def test_fetch_counter_is_deterministic_and_plausible():
+    seqs = T.repeat_rich(21, 2, 4000)
+    hs = T.HostSim(seqs)
+    out, f1 = hs.map(30, 0, return_fetches=True)
+    _, f2 = hs.map(30, 0, return_fetches=True)
+    assert f1 == f2
+    n_kmers = sum(len(s) - 29 for s in seqs)
+    assert n_kmers * 20 < f1 < n_kmers * 130  # ~30 steps per strand, 1-2 blocks per step
