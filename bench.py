@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — genome positions/sec of the (K,E)-frequency hot path on a synthetic genome.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--genome-mbp 3000 --nchr 24 --seed 45] [--kmer 30] [--errors 0] [--batch-mpos 256]
+
+A step = one pass of the hot path over one batch of consecutive k-mer start positions.
+  value : positions/s, index and output resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e   : the same metric through the host-buffer C ABI call gmb_map_frequencies_range (result slice D2H
+          into pinned host memory inside the timed region)
+  roofline: algorithmic rank-block bytes (counted fetches x 64 B) / kernel time, vs the measured HBM copy peak
+  cpu_baseline: the oracle port of the reference path on this box's host cores, on a bounded window
+One JSON line on stdout (rank 0); progress on stderr.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "genome positions/sec at (K,E) on 3 Gbp"
+UNIT = "positions/s"
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genome-mbp", type=float, default=3000.0)
+    ap.add_argument("--nchr", type=int, default=24)
+    ap.add_argument("--seed", type=int, default=45)
+    ap.add_argument("--kmer", type=int, default=30)
+    ap.add_argument("--errors", type=int, default=0)
+    ap.add_argument("--batch-mpos", type=float, default=0.0, help="batch size in Mi positions (0 = by E)")
+    ap.add_argument("--extras", default="1,2", help="other E values measured after the main line ('' = none)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+def peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                sm.append(float(p[1])); mx.append(float(p[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class _DeviceBytes:
+    """__cuda_array_interface__ view of raw device memory (no copy)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def genome_limits(total, nchr):
+    per = total // nchr
+    return np.arange(nchr + 1, dtype=np.uint64) * np.uint64(per)
+
+
+def default_batch(E):
+    return {0: 256.0, 1: 64.0, 2: 8.0, 3: 1.0, 4: 0.25}[E]
+
+
+# --------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores, on a bounded window of the same genome
+# --------------------------------------------------------------------------------------------------------
+def cpu_port_rate(seqs, bwt_f, bwt_r, K, E, seconds, steps=1, warmup=0):
+    """-> (positions/s, cores, sample description, per-step ms list)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import gmtest as T
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    orc = T.Oracle(seqs, bwt=(bwt_f, bwt_r, 4))
+    log("oracle rank structure built in %.1f s" % (time.time() - t0))
+    n_text = int(orc.limits[-1])
+    per = int(orc.limits[1])
+    start = (n_text // 2 // per) * per + per // 3  # a fixed window inside one chromosome
+
+    def run(npos):
+        b = min(start, n_text - npos - K)
+        t = time.time()
+        orc.map(K, E, intervals=[(b, b + npos)], threads=cores)
+        return time.time() - t
+
+    pilot = 50_000 if E < 2 else 5_000
+    dt = run(pilot)
+    npos = int(max(pilot, min(per // 2, pilot * seconds / max(dt, 1e-3))))
+    times = []
+    for i in range(warmup + steps):
+        dt = run(npos)
+        if i >= warmup:
+            times.append(dt)
+    rate = npos * len(times) / sum(times)
+    sample = "%d consecutive positions of chr%d (-S style window, copy shortcut off), %d OpenMP threads" % (
+        npos, start // per + 1, cores)
+    return rate, cores, sample, [t * 1e3 for t in times], npos
+
+
+def main():
+    args = parse()
+    import torch
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    K, E = args.kmer, args.errors
+    total = int(args.genome_mbp * 1e6)
+    workload = "%g Mbp synthetic DNA (%d chr, seed %d), K=%d E=%d, both strands, uint16 counts" % (
+        args.genome_mbp, args.nchr, args.seed, K, E)
+
+    if args.impl == "reference" and rank != 0:
+        return 0
+
+    import genmap_b200 as gm
+    from genmap_b200 import _lib
+    if _lib.lib().gmb_device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1 and args.impl == "ours":
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic genome + index (rank 0 builds on its GPU, NCCL broadcast to the other ranks) -------
+    limits = genome_limits(total, args.nchr)
+    n_text = int(limits[-1])
+    seqs = None
+    t0 = time.time()
+    if rank == 0:
+        seqs = gm.synth_genome(total, args.nchr, args.seed)
+        log("genome generated in %.1f s" % (time.time() - t0))
+        t0 = time.time()
+        ix = gm.Index.build(seqs, device=local, on_gpu=True)
+        log("index built on GPU in %.1f s %s, blob %.2f GB" % (time.time() - t0, ix.build_timings_ms, ix.info.blob_bytes / 1e9))
+    if dist is not None:
+        nbytes = torch.zeros(1, dtype=torch.int64, device=dev)
+        if rank == 0:
+            nbytes[0] = ix.info.blob_bytes
+        dist.broadcast(nbytes, 0)
+        nb = int(nbytes.item())
+        if rank == 0:
+            # the library-owned device blob, viewed as a tensor so NCCL can broadcast it in place
+            blob_t = torch.as_tensor(_DeviceBytes(int(ix.info.device_blob), nb), device=dev)
+        else:
+            blob_t = torch.empty(nb, dtype=torch.uint8, device=dev)
+        t0 = time.time()
+        dist.broadcast(blob_t, 0)
+        torch.cuda.synchronize()
+        log("rank %d: index broadcast over NCCL in %.2f s" % (rank, time.time() - t0))
+        if rank != 0:
+            ix = gm.Index.adopt_device(blob_t.data_ptr(), nb, device=local)
+    ix.limits = limits
+
+    params = gm.SearchParams(K, E)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    if args.impl == "reference":
+        bwt_f, bwt_r = ix.export_bwt(False), ix.export_bwt(True)
+        ix.close()
+        rate, cores, sample, times, npos = cpu_port_rate(seqs, bwt_f, bwt_r, K, E, args.cpu_seconds, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": workload, "K": K, "E": E, "genome_bp": n_text, "positions_per_step": npos},
+                "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ---- one measurement = (E, batch) ---------------------------------------------------------------------
+    shard_b = n_text * rank // world
+    shard_e = n_text * (rank + 1) // world
+    out_dev = torch.zeros(n_text, dtype=torch.int16, device=dev)
+
+    def batches(E_, batch, count):
+        span = shard_e - shard_b
+        res, pos = [], 0
+        for _ in range(count):
+            if pos + batch > span:
+                pos = 0
+            b = shard_b + pos
+            res.append((b, min(b + batch, shard_e)))
+            pos += batch
+        return res
+
+    def measure(E_, batch, steps, warmup, with_e2e, sample_clocks):
+        p = gm.SearchParams(K, E_)
+        bl = batches(E_, batch, warmup + steps)
+        for b, e in bl[:warmup]:
+            ix.compute_mappability_device(p, out_dev.data_ptr(), pos_begin=b, pos_end=e, stream=stream, sync=False)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for b, e in bl[warmup:]:
+            ix.compute_mappability_device(p, out_dev.data_ptr(), pos_begin=b, pos_end=e, stream=stream, sync=False)
+        ev1.record()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        ms = ev0.elapsed_time(ev1)
+        npos = sum(e - b for b, e in bl[warmup:])
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            c = torch.tensor([npos], dtype=torch.int64, device=dev)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            npos_all = int(c.item())
+        else:
+            npos_all = npos
+        res = {"ms": ms, "positions": npos_all, "value": npos_all / (ms * 1e-3), "clocks": clocks, "batches": bl[warmup:]}
+        # rank-block fetches of exactly these batches (instrumented kernel, outside the timed region) and
+        # per-launch kernel time from CUDA events on the launching stream
+        if rank == 0:
+            f_tot, k_ms, pos0 = 0, [], 0
+            for b, e in bl[warmup:]:
+                st = ix.compute_mappability_device(p, out_dev.data_ptr(), pos_begin=b, pos_end=e, stream=stream, count_fetches=True)
+                f_tot += int(st.rank_block_fetches)
+            for b, e in bl[warmup:]:
+                st = ix.compute_mappability_device(p, out_dev.data_ptr(), pos_begin=b, pos_end=e, stream=stream)
+                k_ms.append(st.kernel_ms); pos0 += int(st.positions)
+            res.update(fetches=f_tot, kernel_ms=float(np.mean(k_ms)), searched=pos0)
+        if with_e2e:
+            host = torch.empty(batch, dtype=torch.int16).pin_memory().numpy().view(np.uint16)
+            bl2 = batches(E_, batch, 1 + steps)
+            ix.compute_mappability_range(p, bl2[0][0], bl2[0][1], out=host)
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for b, e in bl2[1:]:
+                ix.compute_mappability_range(p, b, e, out=host)
+            dt = time.perf_counter() - t0
+            npos2 = sum(e - b for b, e in bl2[1:])
+            if dist is not None:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+                c = torch.tensor([npos2], dtype=torch.int64, device=dev)
+                dist.all_reduce(c, op=dist.ReduceOp.SUM)
+                npos2 = int(c.item())
+            # per step: work-range table + step table + counters go H2D, the slice of c comes back D2H
+            res["e2e"] = {"value": npos2 / dt, "unit": UNIT,
+                          "h2d_bytes_per_step": int(3 * 8 + 4 * K * {0: 1, 1: 2, 2: 3, 3: 4, 4: 7}[E_] + 16),
+                          "d2h_bytes_per_step": int(2 * batch)}
+        return res
+
+    batch = int((args.batch_mpos or default_batch(E)) * (1 << 20))
+    batch = max(1 << 16, min(batch, (shard_e - shard_b) // 2))
+    main_r = measure(E, batch, args.steps, args.warmup, True, True)
+    peak, peak_src = peak_hbm()
+
+    def roofline(r):
+        if "fetches" not in r:
+            return None
+        per_launch = r["fetches"] * 64.0 / len(r["batches"])
+        achieved = per_launch / (r["kernel_ms"] * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tr = json.load(f)
+            key = "K%d_E%d_batch%d_genome%d" % (K, r["E"], r["batch"], n_text)
+            traffic = tr.get(key)
+        except Exception:
+            pass
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "rank_block_bytes_per_position": r["fetches"] * 64.0 / max(r["searched"], 1),
+                "kernel_ms_per_launch": r["kernel_ms"]}
+
+    main_r["E"], main_r["batch"] = E, batch
+    extras = {}
+    if rank == 0 or dist is not None:
+        for e_s in [x for x in args.extras.split(",") if x.strip() != ""]:
+            E2 = int(e_s)
+            if E2 == E:
+                continue
+            b2 = int(default_batch(E2) * (1 << 20))
+            b2 = max(1 << 14, min(b2, (shard_e - shard_b) // 2))
+            r2 = measure(E2, b2, max(2, args.steps // 2), 1, False, False)
+            r2["E"], r2["batch"] = E2, b2
+            extras["K%d_E%d" % (K, E2)] = {"value": r2["value"], "unit": UNIT, "ms_per_step": r2["ms"] / max(2, args.steps // 2),
+                                          "positions_per_step": b2, "roofline": roofline(r2)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            bwt_f, bwt_r = ix.export_bwt(False), ix.export_bwt(True)
+            rate, cores, sample, _, _ = cpu_port_rate(seqs, bwt_f, bwt_r, K, E, args.cpu_seconds)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        except Exception as ex:  # the baseline is a reported extra; never lose the GPU line over it
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": main_r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": main_r["ms"] / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": workload, "K": K, "E": E, "genome_bp": n_text, "positions_per_step_per_gpu": batch,
+                           "sharding": "positions range-partitioned over %d GPU(s), index replicated (NCCL broadcast)" % world,
+                           "cache": "inputs larger than L2: %.2f GB index vs 126 MB L2, every step searches different positions"
+                                    % (ix.info.blob_bytes / 1e9)},
+                "clocks": main_r["clocks"], "e2e": main_r.get("e2e"), "gpu_launches": args.steps,
+                "roofline": roofline(main_r), "cpu_baseline": cpu, "extra": extras}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

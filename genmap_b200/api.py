@@ -1,0 +1,184 @@
+"""Host-side mirror of the reference's interface for the map path.
+
+The reference has no library API: `genmap map` opens the index once (src/mappability.hpp:221-223) and
+calls, per FASTA file, run(index, text, ...) -> computeMappability<E>(index, text, c, searchParams, ...)
+(src/mappability.hpp:157-189, src/algo.hpp:405-410).  `Index.open/build` and `compute_mappability`
+mirror those two steps with the same argument meaning (file-local positions, counts over the whole
+index, uint8/uint16 value types, -nc / -ep switches, selection intervals) and the same error
+behaviour (E > 4 is rejected, src/mappability.hpp:187).  Everything is a thin ctypes call into the
+C ABI (include/genmap_b200.h); the arithmetic happens in the CUDA kernels.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import GenmapError, GmbIndexInfo, GmbMapStats, GmbParams, check
+
+
+def _ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _concat(seqs):
+    codes = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqs]))
+    limits = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    limits[1:] = np.cumsum([len(s) for s in seqs])
+    return codes, limits
+
+
+class SearchParams:
+    """src/common.hpp:67-74 (length, revCompl, excludePseudo) + Options.errors / value type."""
+
+    def __init__(self, length, errors=0, rev_compl=True, exclude_pseudo=False, value_bits=16):
+        self.length, self.errors, self.rev_compl = int(length), int(errors), bool(rev_compl)
+        self.exclude_pseudo, self.value_bits = bool(exclude_pseudo), int(value_bits)
+
+
+class Index:
+    """An FM index resident in the HBM of one GPU."""
+
+    def __init__(self, handle, seq_to_file=None):
+        self._h = handle
+        info = GmbIndexInfo()
+        check(_lib.lib().gmb_index_get_info(self._h, ctypes.byref(info)))
+        self.info = info
+        self.n_text, self.n_seq, self.device = int(info.n_text), int(info.n_seq), int(info.device)
+        self.seq_to_file = None if seq_to_file is None else np.ascontiguousarray(seq_to_file, dtype=np.uint32)
+        self.limits = None
+        self.build_timings_ms = None
+
+    # ---- construction ---------------------------------------------------------------------------
+    @staticmethod
+    def build_blob(seqs, with_sa=False, on_gpu=False, device=0):
+        """-> index blob as a uint8 array (host SA-IS builder, or the GPU builder copied back)."""
+        codes, limits = _concat(seqs)
+        blob, nbytes = ctypes.c_void_p(), ctypes.c_uint64()
+        flags = (_lib.GMB_BUILD_WITH_SA if with_sa else 0) | (_lib.GMB_BUILD_ON_GPU if on_gpu else 0)
+        check(_lib.lib().gmb_index_build(_ptr(codes), _ptr(limits), len(seqs), flags, device,
+                                         ctypes.byref(blob), ctypes.byref(nbytes)))
+        out = np.frombuffer(ctypes.string_at(blob, nbytes.value), dtype=np.uint8).copy()
+        _lib.lib().gmb_blob_free(blob)
+        return out
+
+    @classmethod
+    def build(cls, seqs, device=0, with_sa=False, on_gpu=True, seq_to_file=None):
+        """Index the sequences (uint8 codes 0..3) and leave the index in HBM of `device`."""
+        codes, limits = _concat(seqs)
+        h = ctypes.c_void_p()
+        if on_gpu:
+            tm = (ctypes.c_double * 4)()
+            check(_lib.lib().gmb_index_build_device(_ptr(codes), _ptr(limits), len(seqs),
+                                                    _lib.GMB_BUILD_WITH_SA if with_sa else 0, device, ctypes.byref(h), tm))
+            ix = cls(h, seq_to_file)
+            ix.build_timings_ms = dict(h2d=tm[0], sort=tm[1], pack=tm[2], total=tm[3])
+        else:
+            blob = cls.build_blob(seqs, with_sa=with_sa)
+            check(_lib.lib().gmb_index_from_blob(_ptr(blob), blob.nbytes, device, ctypes.byref(h)))
+            ix = cls(h, seq_to_file)
+        ix.limits = limits
+        return ix
+
+    @classmethod
+    def from_blob(cls, blob, device=0, seq_to_file=None):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        h = ctypes.c_void_p()
+        check(_lib.lib().gmb_index_from_blob(_ptr(blob), blob.nbytes, device, ctypes.byref(h)))
+        return cls(h, seq_to_file)
+
+    @classmethod
+    def adopt_device(cls, device_ptr, nbytes, device=0, seq_to_file=None):
+        """Wrap a blob that already sits in device memory (e.g. a torch tensor after dist.broadcast)."""
+        h = ctypes.c_void_p()
+        check(_lib.lib().gmb_index_adopt_device(ctypes.c_void_p(device_ptr), nbytes, device, ctypes.byref(h)))
+        return cls(h, seq_to_file)
+
+    @classmethod
+    def open(cls, directory, device=0, seq_to_file=None):
+        h = ctypes.c_void_p()
+        check(_lib.lib().gmb_index_open(str(directory).encode(), device, ctypes.byref(h)))
+        return cls(h, seq_to_file)
+
+    def close(self):
+        if self._h:
+            _lib.lib().gmb_index_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- the hot path ------------------------------------------------------------------------------
+    def _file_args(self, text_begin, text_len, chrom_cum, intervals):
+        if text_len is None:
+            text_begin, text_len = 0, self.n_text
+        if chrom_cum is None:
+            if self.limits is None or (text_begin, text_len) != (0, self.n_text):
+                raise ValueError("chrom_cum_lengths is required")
+            chrom_cum = self.limits
+        chrom_cum = np.ascontiguousarray(chrom_cum, dtype=np.uint64)
+        iv = None
+        if intervals is not None and len(intervals):
+            iv = np.ascontiguousarray(np.asarray(intervals, dtype=np.uint64).reshape(-1, 2))
+        return int(text_begin), int(text_len), chrom_cum, iv
+
+    def compute_mappability(self, params, text_begin=0, text_len=None, chrom_cum_lengths=None, intervals=None,
+                            count_fetches=False, return_stats=False):
+        """computeMappability<E>(index, text, c, ...) (src/algo.hpp:405-483) for one FASTA file;
+        returns the frequency vector c (uint8 / uint16, one value per text position) in host memory."""
+        tb, tl, cum, iv = self._file_args(text_begin, text_len, chrom_cum_lengths, intervals)
+        p = GmbParams(params.length, params.errors, int(params.rev_compl), int(params.exclude_pseudo),
+                      params.value_bits, int(count_fetches))
+        out = np.zeros(tl, dtype=np.uint16 if params.value_bits == 16 else np.uint8)
+        st = GmbMapStats()
+        check(_lib.lib().gmb_map_frequencies(self._h, ctypes.byref(p), tb, tl, _ptr(cum), len(cum) - 1, _ptr(iv),
+                                             0 if iv is None else len(iv), _ptr(self.seq_to_file),
+                                             0 if self.seq_to_file is None else len(self.seq_to_file), _ptr(out),
+                                             ctypes.byref(st)))
+        return (out, st) if return_stats else out
+
+    def compute_mappability_range(self, params, pos_begin, pos_end, out=None, text_begin=0, text_len=None,
+                                  chrom_cum_lengths=None, intervals=None, return_stats=False):
+        """The slice [pos_begin, pos_end) of c into host memory (`out`: a numpy array of that length,
+        e.g. a view of pinned memory)."""
+        tb, tl, cum, iv = self._file_args(text_begin, text_len, chrom_cum_lengths, intervals)
+        p = GmbParams(params.length, params.errors, int(params.rev_compl), int(params.exclude_pseudo),
+                      params.value_bits, 0)
+        dt = np.uint16 if params.value_bits == 16 else np.uint8
+        if out is None:
+            out = np.zeros(int(pos_end) - int(pos_begin), dtype=dt)
+        assert out.dtype == dt and out.size >= int(pos_end) - int(pos_begin) and out.flags["C_CONTIGUOUS"]
+        st = GmbMapStats()
+        check(_lib.lib().gmb_map_frequencies_range(
+            self._h, ctypes.byref(p), tb, tl, _ptr(cum), len(cum) - 1, _ptr(iv), 0 if iv is None else len(iv),
+            _ptr(self.seq_to_file), 0 if self.seq_to_file is None else len(self.seq_to_file), int(pos_begin),
+            int(pos_end), _ptr(out), ctypes.byref(st)))
+        return (out, st) if return_stats else out
+
+    def export_bwt(self, rev=False):
+        """BWT of T (or of T' if rev) as bytes: 0 = sentinel, 1..4 = A,C,G,T (diagnostics / tests)."""
+        out = np.zeros(int(self.info.n_bwt), dtype=np.uint8)
+        check(_lib.lib().gmb_index_export_bwt(self._h, int(rev), _ptr(out)))
+        return out
+
+    def compute_mappability_device(self, params, out_ptr, text_begin=0, text_len=None, chrom_cum_lengths=None,
+                                   intervals=None, pos_begin=0, pos_end=None, stream=0, count_fetches=False,
+                                   sync=True):
+        """Same, for the file-local position range [pos_begin, pos_end) only, writing into device memory at
+        `out_ptr` (text_len elements, zero-filled by the caller) on CUDA stream `stream`."""
+        tb, tl, cum, iv = self._file_args(text_begin, text_len, chrom_cum_lengths, intervals)
+        p = GmbParams(params.length, params.errors, int(params.rev_compl), int(params.exclude_pseudo),
+                      params.value_bits, int(count_fetches))
+        st = GmbMapStats()
+        check(_lib.lib().gmb_map_frequencies_device(
+            self._h, ctypes.byref(p), tb, tl, _ptr(cum), len(cum) - 1, _ptr(iv), 0 if iv is None else len(iv),
+            _ptr(self.seq_to_file), 0 if self.seq_to_file is None else len(self.seq_to_file), int(pos_begin),
+            tl if pos_end is None else int(pos_end), ctypes.c_void_p(out_ptr), ctypes.c_void_p(stream),
+            ctypes.byref(st) if sync else None))
+        return st if sync else None
+
+
+def compute_mappability(index, K, E=0, rev_compl=True, value_bits=16, **kw):
+    return index.compute_mappability(SearchParams(K, E, rev_compl, False, value_bits), **kw)

@@ -1,0 +1,411 @@
+// capi.cu — the C ABI of libgenmap_b200.so (include/genmap_b200.h): index handles in HBM and the
+// reference-facing gmb_map_frequencies call.  Host logic only; the device work is map_kernel.cu and
+// index_build_gpu.cu.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/genmap_b200.h"
+#include "gmb_host.h"
+#include "index_build_gpu.cuh"
+#include "map_kernel.cuh"
+
+using namespace gmb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return GMB_ERR_CUDA;
+}
+
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+} // namespace
+
+__global__ void k_decode_bwt(const RankBlock* __restrict__ B, uint64_t n, uint8_t* __restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RankBlock& b = B[i / kBlockBases];
+    const uint32_t k = (uint32_t)(i % kBlockBases);
+    out[i] = (uint8_t)(1u + (uint32_t)((b.w[k >> 6][0] >> (k & 63)) & 1u) + 2u * (uint32_t)((b.w[k >> 6][1] >> (k & 63)) & 1u));
+}
+
+__global__ void k_mark_sentinels(const uint32_t* __restrict__ S, uint32_t n_seq, uint8_t* __restrict__ out)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_seq) out[S[s]] = 0;
+}
+
+struct gmb_index {
+    int device = 0;
+    int sm_count = 0;
+    uint8_t* d_blob = nullptr;
+    bool owns_blob = false;
+    IndexHeader h{};
+    std::vector<uint64_t> limits; // host copy
+    // per-handle scratch, grown on demand
+    unsigned long long* d_counters = nullptr; // [0] work counter, [1] fetch counter
+    uint32_t* d_steps = nullptr;
+    uint64_t* d_ranges = nullptr;
+    size_t ranges_cap = 0;
+    void* d_out = nullptr;
+    size_t out_cap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+extern "C" {
+
+const char* gmb_last_error(void) { return g_err.c_str(); }
+const char* gmb_version(void) { return "genmap-b200 0.1 (index format 2, sm_100a)"; }
+
+int gmb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int gmb_index_build(const uint8_t* codes, const uint64_t* limits, uint32_t n_seq, uint32_t flags, int device,
+                    void** blob_out, uint64_t* bytes_out)
+{
+    if (!codes || !limits || !blob_out || !bytes_out) return fail(GMB_ERR_ARG, "gmb_index_build: NULL argument");
+    std::string err;
+    const bool with_sa = (flags & GMB_BUILD_WITH_SA) != 0;
+    if (flags & GMB_BUILD_ON_GPU) {
+        void* p = nullptr;
+        uint64_t bytes = 0;
+        int rc = build_index_gpu(codes, limits, n_seq, with_sa, device, &p, &bytes, err);
+        if (rc != 0) return fail(rc, err);
+        *blob_out = p;
+        *bytes_out = bytes;
+        return GMB_OK;
+    }
+    Blob b;
+    if (!build_index_host(codes, limits, n_seq, with_sa, b, err))
+        return fail(err.find("not supported") != std::string::npos || err.find("too") != std::string::npos ? GMB_ERR_UNSUPPORTED : GMB_ERR_ARG, err);
+    void* p = std::malloc(b.bytes);
+    if (!p) return fail(GMB_ERR_NOMEM, "out of host memory");
+    std::memcpy(p, b.data(), b.bytes);
+    *blob_out = p;
+    *bytes_out = b.bytes;
+    return GMB_OK;
+}
+
+void gmb_blob_free(void* blob) { std::free(blob); }
+
+int gmb_blob_save(const void* blob, uint64_t bytes, const char* path)
+{
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(GMB_ERR_IO, std::string("cannot write ") + path);
+    const size_t w = std::fwrite(blob, 1, bytes, f);
+    if (std::fclose(f) != 0 || w != bytes) return fail(GMB_ERR_IO, std::string("short write to ") + path);
+    return GMB_OK;
+}
+
+static int finish_open(gmb_index* ix, gmb_index** out)
+{
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ix->device));
+    ix->sm_count = prop.multiProcessorCount;
+    ix->limits.resize((size_t)ix->h.n_seq + 1);
+    CU(cudaMemcpy(ix->limits.data(), ix->d_blob + ix->h.off_limits, ix->limits.size() * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMalloc(&ix->d_counters, 2 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&ix->d_steps, sizeof(uint32_t) * kMaxSearches * (kMaxK + 1)));
+    CU(cudaEventCreate(&ix->ev0));
+    CU(cudaEventCreate(&ix->ev1));
+    *out = ix;
+    return GMB_OK;
+}
+
+int gmb_index_from_blob(const void* host_blob, uint64_t bytes, int device, gmb_index** out)
+{
+    if (!host_blob || !out) return fail(GMB_ERR_ARG, "gmb_index_from_blob: NULL argument");
+    std::string err;
+    if (!validate_blob(static_cast<const uint8_t*>(host_blob), bytes, err)) return fail(GMB_ERR_IO, err);
+    if (gmb_device_count() <= device || device < 0) return fail(GMB_ERR_CUDA, "no such CUDA device (the map path has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    gmb_index* ix = new (std::nothrow) gmb_index;
+    if (!ix) return fail(GMB_ERR_NOMEM, "out of host memory");
+    ix->device = device;
+    std::memcpy(&ix->h, host_blob, sizeof(IndexHeader));
+    cudaError_t e = cudaMalloc(&ix->d_blob, ix->h.total_bytes);
+    if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMalloc(index blob)"); }
+    ix->owns_blob = true;
+    e = cudaMemcpy(ix->d_blob, host_blob, ix->h.total_bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { gmb_index_close(ix); return cuda_fail(e, "cudaMemcpy(index blob)"); }
+    int rc = finish_open(ix, out);
+    if (rc != GMB_OK) gmb_index_close(ix);
+    return rc;
+}
+
+int gmb_index_build_device(const uint8_t* codes, const uint64_t* limits, uint32_t n_seq, uint32_t flags, int device,
+                           gmb_index** out, double* timings_ms)
+{
+    if (!codes || !limits || !out) return fail(GMB_ERR_ARG, "gmb_index_build_device: NULL argument");
+    std::string err;
+    uint8_t* d_blob = nullptr;
+    IndexHeader h;
+    GpuBuildTimings tm;
+    int rc = build_index_gpu_device(codes, limits, n_seq, (flags & GMB_BUILD_WITH_SA) != 0, device, &d_blob, &h, &tm, err);
+    if (rc != GMB_OK) return fail(rc, err);
+    if (timings_ms) { timings_ms[0] = tm.h2d_ms; timings_ms[1] = tm.sort_ms; timings_ms[2] = tm.pack_ms; timings_ms[3] = tm.total_ms; }
+    gmb_index* ix = new (std::nothrow) gmb_index;
+    if (!ix) { cudaFree(d_blob); return fail(GMB_ERR_NOMEM, "out of host memory"); }
+    ix->device = device;
+    ix->h = h;
+    ix->d_blob = d_blob;
+    ix->owns_blob = true;
+    rc = finish_open(ix, out);
+    if (rc != GMB_OK) gmb_index_close(ix);
+    return rc;
+}
+
+int gmb_index_adopt_device(void* device_blob, uint64_t bytes, int device, gmb_index** out)
+{
+    if (!device_blob || !out) return fail(GMB_ERR_ARG, "gmb_index_adopt_device: NULL argument");
+    if (gmb_device_count() <= device || device < 0) return fail(GMB_ERR_CUDA, "no such CUDA device");
+    CU(cudaSetDevice(device));
+    IndexHeader h;
+    if (bytes < sizeof(h)) return fail(GMB_ERR_IO, "index blob too small");
+    CU(cudaMemcpy(&h, device_blob, sizeof(h), cudaMemcpyDeviceToHost));
+    std::string err;
+    if (!validate_header(h, bytes, err)) return fail(GMB_ERR_IO, err);
+    gmb_index* ix = new (std::nothrow) gmb_index;
+    if (!ix) return fail(GMB_ERR_NOMEM, "out of host memory");
+    ix->device = device;
+    ix->h = h;
+    ix->d_blob = static_cast<uint8_t*>(device_blob);
+    ix->owns_blob = false;
+    int rc = finish_open(ix, out);
+    if (rc != GMB_OK) gmb_index_close(ix);
+    return rc;
+}
+
+int gmb_index_open(const char* dir, int device, gmb_index** out)
+{
+    if (!dir || !out) return fail(GMB_ERR_ARG, "gmb_index_open: NULL argument");
+    std::string path = std::string(dir);
+    if (!path.empty() && path.back() != '/') path += '/';
+    path += "index.gmb";
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return fail(GMB_ERR_IO, "cannot open " + path);
+    std::fseek(f, 0, SEEK_END);
+    const long long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    void* host = nullptr;
+    if (sz <= 0 || cudaMallocHost(&host, (size_t)sz) != cudaSuccess) {
+        cudaGetLastError();
+        host = std::malloc(sz > 0 ? (size_t)sz : 1);
+        if (!host) { std::fclose(f); return fail(GMB_ERR_NOMEM, "out of host memory"); }
+        const size_t r = sz > 0 ? std::fread(host, 1, (size_t)sz, f) : 0;
+        std::fclose(f);
+        int rc = (long long)r == sz ? gmb_index_from_blob(host, (uint64_t)sz, device, out) : fail(GMB_ERR_IO, "short read from " + path);
+        std::free(host);
+        return rc;
+    }
+    const size_t r = std::fread(host, 1, (size_t)sz, f);
+    std::fclose(f);
+    int rc = (long long)r == sz ? gmb_index_from_blob(host, (uint64_t)sz, device, out) : fail(GMB_ERR_IO, "short read from " + path);
+    cudaFreeHost(host);
+    return rc;
+}
+
+int gmb_index_close(gmb_index* ix)
+{
+    if (!ix) return GMB_OK;
+    cudaSetDevice(ix->device);
+    if (ix->owns_blob && ix->d_blob) cudaFree(ix->d_blob);
+    if (ix->d_counters) cudaFree(ix->d_counters);
+    if (ix->d_steps) cudaFree(ix->d_steps);
+    if (ix->d_ranges) cudaFree(ix->d_ranges);
+    if (ix->d_out) cudaFree(ix->d_out);
+    if (ix->ev0) cudaEventDestroy(ix->ev0);
+    if (ix->ev1) cudaEventDestroy(ix->ev1);
+    delete ix;
+    return GMB_OK;
+}
+
+int gmb_index_get_info(const gmb_index* ix, gmb_index_info* info)
+{
+    if (!ix || !info) return fail(GMB_ERR_ARG, "gmb_index_get_info: NULL argument");
+    std::memset(info, 0, sizeof(*info));
+    info->n_text = ix->h.n_text;
+    info->n_bwt = ix->h.n_bwt;
+    info->n_seq = ix->h.n_seq;
+    info->has_sa = ix->h.off_sa != 0;
+    info->blob_bytes = ix->h.total_bytes;
+    info->rank_block_bytes = kBlockBytes;
+    info->device_blob = ix->d_blob;
+    info->device = ix->device;
+    return GMB_OK;
+}
+
+int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len,
+                               const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t (*intervals)[2],
+                               uint64_t n_intervals, const uint32_t* seq_to_file, uint32_t n_seq,
+                               uint64_t pos_begin, uint64_t pos_end, void* out_device, void* cuda_stream,
+                               gmb_map_stats* stats)
+{
+    (void)seq_to_file; (void)n_seq;
+    if (!ix || !p || !chrom_cum || !out_device) return fail(GMB_ERR_ARG, "gmb_map_frequencies: NULL argument");
+    if (p->value_bits != 8 && p->value_bits != 16) return fail(GMB_ERR_ARG, "value_bits must be 8 or 16");
+    if (text_begin + text_len > ix->h.n_text) return fail(GMB_ERR_ARG, "text range exceeds the indexed text");
+    if (n_chrom == 0 || chrom_cum[0] != 0 || chrom_cum[n_chrom] != text_len) return fail(GMB_ERR_ARG, "chrom_cum_lengths must start at 0 and end at text_len");
+    if (p->exclude_pseudo) return fail(GMB_ERR_UNSUPPORTED, "--exclude-pseudo is not implemented on the GPU path yet");
+    if (n_intervals && !intervals) return fail(GMB_ERR_ARG, "intervals is NULL");
+    std::string err;
+    StepTables* tabs = new (std::nothrow) StepTables;
+    if (!tabs) return fail(GMB_ERR_NOMEM, "out of host memory");
+    if (!build_step_tables(p->K, p->E, *tabs, err)) { delete tabs; return fail(GMB_ERR_UNSUPPORTED, err); }
+    CU(cudaSetDevice(ix->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+
+    std::vector<WorkRange> ranges;
+    build_work_ranges(text_len, p->K, chrom_cum, n_chrom, reinterpret_cast<const uint64_t*>(intervals), n_intervals,
+                      pos_begin, pos_end, ranges);
+    const uint32_t nr = (uint32_t)ranges.size();
+    std::vector<uint64_t> host_ranges(2 * (size_t)nr + 1);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < nr; ++i) {
+        host_ranges[i] = ranges[i].begin;
+        host_ranges[nr + i] = total;
+        total += ranges[i].end - ranges[i].begin;
+    }
+    host_ranges[2 * (size_t)nr] = total;
+    if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->positions = total; }
+    if (total == 0) { delete tabs; return GMB_OK; }
+
+    if (ix->ranges_cap < host_ranges.size()) {
+        if (ix->d_ranges) cudaFree(ix->d_ranges);
+        ix->d_ranges = nullptr;
+        ix->ranges_cap = host_ranges.size() * 2;
+        CU(cudaMalloc(&ix->d_ranges, ix->ranges_cap * 8));
+    }
+    CU(cudaMemcpyAsync(ix->d_ranges, host_ranges.data(), host_ranges.size() * 8, cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(ix->d_steps, tabs->step, sizeof(uint32_t) * tabs->n_search * p->K, cudaMemcpyHostToDevice, stream));
+    CU(cudaMemsetAsync(ix->d_counters, 0, 2 * sizeof(unsigned long long), stream));
+    // the two staging copies above read pageable host memory: they have completed (staged) on return
+
+    MapLaunch L;
+    const uint8_t* base = ix->d_blob;
+    L.cx.blk[0] = reinterpret_cast<const RankBlock*>(base + ix->h.off_fwd);
+    L.cx.blk[1] = reinterpret_cast<const RankBlock*>(base + ix->h.off_rev);
+    L.cx.sent[0] = reinterpret_cast<const uint32_t*>(base + ix->h.off_sent_fwd);
+    L.cx.sent[1] = reinterpret_cast<const uint32_t*>(base + ix->h.off_sent_rev);
+    for (int c = 0; c < 4; ++c) L.cx.C[c] = (uint32_t)ix->h.C[c];
+    L.cx.n_bwt = (uint32_t)ix->h.n_bwt;
+    L.cx.steps = ix->d_steps;
+    L.cx.K = p->K;
+    L.cx.n_search = tabs->n_search;
+    L.cx.n_strands = p->revcompl ? 2u : 1u;
+    L.cx.maxv = p->value_bits == 16 ? 65535u : 255u;
+    L.E = p->E;
+    L.text = reinterpret_cast<const uint64_t*>(base + ix->h.off_text);
+    L.text_begin = text_begin;
+    L.range_begin = ix->d_ranges;
+    L.range_prefix = ix->d_ranges + nr;
+    L.n_ranges = nr;
+    L.n_work = total;
+    L.work_counter = ix->d_counters;
+    L.fetch_counter = ix->d_counters + 1;
+    L.out = out_device;
+    L.value_bits = p->value_bits;
+    L.count_fetches = p->count_fetches != 0;
+    delete tabs;
+
+    if (stats) CU(cudaEventRecord(ix->ev0, stream));
+    CU(launch_map_kernel(L, ix->sm_count, stream));
+    if (stats) {
+        CU(cudaEventRecord(ix->ev1, stream));
+        CU(cudaEventSynchronize(ix->ev1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
+        stats->kernel_ms = ms;
+        stats->kernel_launches = 1;
+        if (L.count_fetches) {
+            unsigned long long f = 0;
+            CU(cudaMemcpy(&f, ix->d_counters + 1, sizeof(f), cudaMemcpyDeviceToHost));
+            stats->rank_block_fetches = f;
+        }
+    }
+    return GMB_OK;
+}
+
+int gmb_map_frequencies_range(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len,
+                              const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t (*intervals)[2],
+                              uint64_t n_intervals, const uint32_t* seq_to_file, uint32_t n_seq,
+                              uint64_t pos_begin, uint64_t pos_end, void* out, gmb_map_stats* stats)
+{
+    if (!ix || !p || !out) return fail(GMB_ERR_ARG, "gmb_map_frequencies: NULL argument");
+    if (p->value_bits != 8 && p->value_bits != 16) return fail(GMB_ERR_ARG, "value_bits must be 8 or 16");
+    if (pos_end > text_len) pos_end = text_len;
+    if (pos_begin > pos_end) return fail(GMB_ERR_ARG, "pos_begin > pos_end");
+    CU(cudaSetDevice(ix->device));
+    const size_t elem = p->value_bits / 8;
+    const size_t bytes = (size_t)(pos_end - pos_begin) * elem;
+    if (ix->out_cap < bytes) {
+        if (ix->d_out) cudaFree(ix->d_out);
+        ix->d_out = nullptr;
+        ix->out_cap = 0;
+        CU(cudaMalloc(&ix->d_out, bytes ? bytes : 1));
+        ix->out_cap = bytes;
+    }
+    CU(cudaMemsetAsync(ix->d_out, 0, bytes, nullptr));
+    gmb_map_stats local;
+    // the kernel indexes its output by file-local position: bias the base so the slice starts at pos_begin
+    void* biased = reinterpret_cast<void*>(reinterpret_cast<uintptr_t>(ix->d_out) - (uintptr_t)pos_begin * elem);
+    int rc = gmb_map_frequencies_device(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals,
+                                        seq_to_file, n_seq, pos_begin, pos_end, biased, nullptr, &local);
+    if (rc != GMB_OK) return rc;
+    CU(cudaMemcpy(out, ix->d_out, bytes, cudaMemcpyDeviceToHost));
+    if (stats) *stats = local;
+    return GMB_OK;
+}
+
+int gmb_map_frequencies(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len,
+                        const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t (*intervals)[2],
+                        uint64_t n_intervals, const uint32_t* seq_to_file, uint32_t n_seq, void* out,
+                        gmb_map_stats* stats)
+{
+    return gmb_map_frequencies_range(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals,
+                                     seq_to_file, n_seq, 0, text_len, out, stats);
+}
+
+int gmb_index_export_bwt(gmb_index* ix, int rev, uint8_t* out_host)
+{
+    if (!ix || !out_host) return fail(GMB_ERR_ARG, "gmb_index_export_bwt: NULL argument");
+    CU(cudaSetDevice(ix->device));
+    const uint64_t n = ix->h.n_bwt;
+    uint8_t* d = nullptr;
+    CU(cudaMalloc(&d, n ? n : 1));
+    const RankBlock* B = reinterpret_cast<const RankBlock*>(ix->d_blob + (rev ? ix->h.off_rev : ix->h.off_fwd));
+    const uint32_t* S = reinterpret_cast<const uint32_t*>(ix->d_blob + (rev ? ix->h.off_sent_rev : ix->h.off_sent_fwd));
+    k_decode_bwt<<<(unsigned)((n + 255) / 256), 256>>>(B, n, d);
+    k_mark_sentinels<<<(ix->h.n_seq + 255) / 256, 256>>>(S, ix->h.n_seq, d);
+    cudaError_t e = cudaMemcpy(out_host, d, n, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "export bwt");
+    return GMB_OK;
+}
+
+} // extern "C"

@@ -189,8 +189,8 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
     const uint32_t x = dir ? st.lo_r : st.lo_f;
     const uint32_t z = dir ? st.lo_f : st.lo_r;
     const uint32_t y = x + st.size;
-    const RankBlock* B = cx.blk[dir];
-    const uint32_t* SP = cx.sent[dir];
+    const RankBlock* B = dir ? cx.blk[1] : cx.blk[0]; // selects, not indexing: keeps cx in registers
+    const uint32_t* SP = dir ? cx.sent[1] : cx.sent[0];
     const uint32_t bx = x / kBlockBases, by = y / kBlockBases;
     BlockRegs rb = load_block(B + bx);
     const Ranks R0 = block_rank(rb, x - bx * kBlockBases, x, SP);

@@ -250,11 +250,8 @@ void build_work_ranges(uint64_t text_len, uint32_t K, const uint64_t* chrom_cum,
     }
 }
 
-bool validate_blob(const uint8_t* blob, uint64_t bytes, std::string& err)
+bool validate_header(const IndexHeader& h, uint64_t bytes, std::string& err)
 {
-    if (bytes < sizeof(IndexHeader)) { err = "index blob too small"; return false; }
-    IndexHeader h;
-    std::memcpy(&h, blob, sizeof(h));
     if (h.magic != kMagic) { err = "not a genmap-b200 index (bad magic)"; return false; }
     if (h.version != kVersion) { err = "index version mismatch: rebuild the index"; return false; }
     if (h.sigma != 4) { err = "only Dna4 indices are supported"; return false; }
@@ -264,6 +261,14 @@ bool validate_blob(const uint8_t* blob, uint64_t bytes, std::string& err)
     for (uint64_t o : offs)
         if (o >= h.total_bytes || (o % 256) != 0) { err = "index header offsets out of range"; return false; }
     return true;
+}
+
+bool validate_blob(const uint8_t* blob, uint64_t bytes, std::string& err)
+{
+    if (bytes < sizeof(IndexHeader)) { err = "index blob too small"; return false; }
+    IndexHeader h;
+    std::memcpy(&h, blob, sizeof(h));
+    return validate_header(h, bytes, err);
 }
 
 } // namespace gmb

@@ -49,5 +49,6 @@ void build_work_ranges(uint64_t text_len, uint32_t K, const uint64_t* chrom_cum,
 
 // sanity-check a blob (magic, version, offsets inside total_bytes)
 bool validate_blob(const uint8_t* blob, uint64_t bytes, std::string& err);
+bool validate_header(const IndexHeader& h, uint64_t bytes, std::string& err);
 
 } // namespace gmb

@@ -1,0 +1,152 @@
+// map_kernel.cu — the (K,E)-frequency kernel for sm_100a.
+//
+// Replaces the reference's per-position loop computeMappability -> computeMappabilitySingleBlock
+// (src/algo.hpp:221-483) and its search-scheme matcher (src/find2_index_approx.hpp:223-457).
+//
+// Mapping to the machine:
+//   * one CUDA thread = one "chain" = one k-mer start at a time; a chain is a strictly dependent series
+//     of random 64-byte rank-block reads, so throughput comes from the number of chains in flight
+//     (148 SMs x 1024 resident threads ~ 150 k independent 64-B requests), not from intra-chain width.
+//   * each loop iteration is one node expansion of gmb_core.h::chain_step — the same code for every
+//     chain whatever its depth, error level or search, so warps stay converged although every lane
+//     walks a different subtree.
+//   * persistent grid (SM count x resident CTAs); lanes that finish their k-mer refill immediately
+//     from a warp-local pool fed by one global atomic per 128 positions, so repeats (whose searches are
+//     100x longer) never idle a warp.
+//   * the <= E backtracking frames live in shared memory, strided by thread (conflict-free); the
+//     step table of the search scheme is staged in shared memory once per CTA.
+#include "map_kernel.cuh"
+
+namespace gmb {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr unsigned kChunk = 128; // positions fetched per global atomic
+
+struct SmemFrames {
+    uint32_t* base; // + threadIdx.x
+    __device__ __forceinline__ void set(uint32_t lv, uint32_t i, uint32_t v) { base[(lv * kFrameWords + i) * kThreads] = v; }
+    __device__ __forceinline__ uint32_t get(uint32_t lv, uint32_t i) const { return base[(lv * kFrameWords + i) * kThreads]; }
+};
+
+__device__ __forceinline__ uint64_t work_to_pos(const uint64_t* __restrict__ rb, const uint64_t* __restrict__ rp,
+                                                uint32_t n_ranges, uint64_t w)
+{
+    uint32_t lo = 0, hi = n_ranges; // largest r with rp[r] <= w
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(rp + mid) <= w) lo = mid; else hi = mid;
+    }
+    return __ldg(rb + lo) + (w - __ldg(rp + lo));
+}
+
+template <int KW, bool COUNT, typename OutT>
+__global__ void __launch_bounds__(kThreads) map_kernel(const MapLaunch L)
+{
+    extern __shared__ uint32_t smem[];
+    const uint32_t n_steps = L.cx.n_search * L.cx.K;
+    uint32_t* steps_s = smem;
+    for (uint32_t i = threadIdx.x; i < n_steps; i += kThreads) steps_s[i] = L.cx.steps[i];
+    __syncthreads();
+
+    MapCtx cx = L.cx;
+    cx.steps = steps_s;
+    SmemFrames fr{smem + ((n_steps + 31u) & ~31u) + threadIdx.x};
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    OutT* __restrict__ out = static_cast<OutT*>(L.out);
+
+    Chain<KW> st;
+    uint64_t j = 0;
+    bool active = false, exhausted = false;
+    unsigned long long pool_next = 0, pool_end = 0; // warp-uniform
+    unsigned long long fetches = 0;
+
+    for (;;) {
+        // ---- refill: lanes without a k-mer take the next work items --------------------------------
+        const bool need = !active && !exhausted;
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        if (m) {
+            const unsigned cnt = __popc(m), rank = __popc(m & lt_mask);
+            const unsigned long long avail = pool_end - pool_next;
+            unsigned long long w;
+            if (avail < cnt) {
+                unsigned long long nb = 0;
+                if (lane == 0) nb = atomicAdd(L.work_counter, (unsigned long long)kChunk);
+                nb = __shfl_sync(0xffffffffu, nb, 0);
+                w = rank < avail ? pool_next + rank : nb + (rank - avail);
+                pool_next = nb + (cnt - avail);
+                pool_end = nb + kChunk;
+            } else {
+                w = pool_next + rank;
+                pool_next += cnt;
+            }
+            if (need) {
+                if (w >= L.n_work) {
+                    exhausted = true;
+                } else {
+                    j = work_to_pos(L.range_begin, L.range_prefix, L.n_ranges, w);
+                    load_pattern(st.pat, L.text, L.text_begin + j, cx.K);
+                    chain_begin_kmer(st, cx);
+                    active = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+
+        // ---- one node expansion per chain -------------------------------------------------------------
+        if (active) {
+            if (!chain_step(st, fr, cx, COUNT ? &fetches : nullptr)) {
+                out[j] = (OutT)st.acc;
+                active = false;
+            }
+        }
+    }
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) fetches += __shfl_xor_sync(0xffffffffu, fetches, o);
+        if (lane == 0 && fetches) atomicAdd(L.fetch_counter, fetches);
+    }
+}
+
+template <int KW, bool COUNT, typename OutT>
+cudaError_t launch_t(const MapLaunch& L, int sm_count, cudaStream_t stream)
+{
+    auto kern = map_kernel<KW, COUNT, OutT>;
+    const uint32_t n_steps = L.cx.n_search * L.cx.K;
+    const size_t smem = ((size_t)((n_steps + 31u) & ~31u) + (size_t)L.E * kFrameWords * kThreads) * sizeof(uint32_t);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    // persistent grid: every resident CTA slot of every SM, but never more threads than work items
+    unsigned long long want = (L.n_work + kThreads - 1) / kThreads;
+    unsigned long long grid = (unsigned long long)sm_count * per_sm;
+    if (want < grid) grid = want ? want : 1;
+    kern<<<(unsigned)grid, kThreads, smem, stream>>>(L);
+    return cudaGetLastError();
+}
+
+template <int KW>
+cudaError_t launch_kw(const MapLaunch& L, int sm_count, cudaStream_t stream)
+{
+    if (L.value_bits == 16)
+        return L.count_fetches ? launch_t<KW, true, uint16_t>(L, sm_count, stream) : launch_t<KW, false, uint16_t>(L, sm_count, stream);
+    return L.count_fetches ? launch_t<KW, true, uint8_t>(L, sm_count, stream) : launch_t<KW, false, uint8_t>(L, sm_count, stream);
+}
+
+} // namespace
+
+cudaError_t launch_map_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream)
+{
+    if (L.n_work == 0) return cudaSuccess;
+    if (L.cx.K <= 32) return launch_kw<1>(L, sm_count, stream);
+    if (L.cx.K <= 64) return launch_kw<2>(L, sm_count, stream);
+    if (L.cx.K <= 128) return launch_kw<4>(L, sm_count, stream);
+    return launch_kw<8>(L, sm_count, stream);
+}
+
+} // namespace gmb

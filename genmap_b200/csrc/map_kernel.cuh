@@ -1,0 +1,29 @@
+// map_kernel.cuh — launcher interface of the (K,E)-frequency kernel (map_kernel.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "gmb_core.h"
+#include "gmb_host.h"
+
+namespace gmb {
+
+struct MapLaunch {
+    MapCtx cx;                 // device pointers into the index blob (cx.steps: device copy of the step table)
+    uint32_t E;
+    const uint64_t* text;      // 2-bit packed concatenated text (device)
+    uint64_t text_begin;       // start of this FASTA file's text inside the concatenated text
+    const uint64_t* range_begin; // device: n_ranges work ranges (file-local begin positions)
+    const uint64_t* range_prefix; // device: n_ranges+1 prefix sums of the range lengths
+    uint32_t n_ranges;
+    uint64_t n_work;           // total k-mer starts to search
+    unsigned long long* work_counter;  // device, zeroed before launch
+    unsigned long long* fetch_counter; // device (only read with count_fetches)
+    void* out;                 // device, value_bits/8 bytes per file-local position
+    uint32_t value_bits;
+    bool count_fetches;
+};
+
+// Enqueue the kernel on `stream`.  Returns cudaSuccess or the launch error.
+cudaError_t launch_map_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream);
+
+} // namespace gmb

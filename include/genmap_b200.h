@@ -1,0 +1,139 @@
+/*
+ * genmap_b200.h — C ABI of libgenmap_b200.so: the B200-native drop-in for the `genmap map` hot path.
+ *
+ * What each entry point replaces in the reference (paths relative to cpockrandt/genmap):
+ *
+ *   gmb_map_frequencies      <- the call site  run(...) { std::vector<value_type> c(length(text), 0);
+ *                               switch (opt.errors) computeMappability<E>(index, text, c, searchParams, ...) }
+ *                               src/mappability.hpp:157-189, i.e. computeMappability (src/algo.hpp:405-483)
+ *                               and everything below it (src/find2_index_approx.hpp, SeqAn FM index).
+ *   gmb_index_open/_from_blob<- open(index, path, OPEN_RDONLY)            src/mappability.hpp:221-223,
+ *                               src/genmap_helper.hpp:71-98
+ *   gmb_index_build          <- buildIndex / indexCreate(fwd+rev)         src/indexing.hpp:72-149,
+ *                               src/seqan_libdivsufsort.h:35-240
+ *   gmb_last_error           <- the reference prints to stderr and exit(1)s (src/mappability.hpp:187-188)
+ *
+ * Conventions (same as the reference call site):
+ *   - `text` of a FASTA file is the infix [text_begin, text_begin + text_len) of the index's
+ *     concatenated text; positions in `out`, `chrom_cum_lengths` and `intervals` are file-local.
+ *   - occurrences are counted over the WHOLE index (all files), both strands unless revcompl == 0.
+ *   - out[j] = min(MAXV, #occurrences with <= E mismatches), 0 for the last K-1 positions of every
+ *     sequence and outside the selection intervals; MAXV = 255 (value_bits 8) or 65535 (16).
+ *   - every function returns 0 on success or a negative gmb_status; nothing throws across the ABI;
+ *     the message is available from gmb_last_error() (thread-local).
+ *   - there is NO CPU fallback: without a CUDA device (or if the kernels fail to load) the compute
+ *     entry points return GMB_ERR_CUDA.
+ * Plain pointers and sizes only; no torch / STL types in any signature.
+ */
+#ifndef GENMAP_B200_H
+#define GENMAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gmb_index gmb_index;
+
+typedef enum gmb_status {
+    GMB_OK = 0,
+    GMB_ERR_ARG = -1,         /* bad argument (K, E, sizes, NULL) */
+    GMB_ERR_UNSUPPORTED = -2, /* E > 4, K > 255, Dna5 index, index >= 2^32-1 symbols */
+    GMB_ERR_CUDA = -3,        /* no device / CUDA runtime error */
+    GMB_ERR_IO = -4,          /* index file missing / malformed */
+    GMB_ERR_NOMEM = -5
+} gmb_status;
+
+typedef struct gmb_params {
+    uint32_t K;              /* -K  k-mer length, E+2 <= K <= 255 */
+    uint32_t E;              /* -E  mismatches, 0..4 (src/mappability.hpp:175-188) */
+    uint32_t revcompl;       /* 0 = -nc (forward strand only), else both strands */
+    uint32_t exclude_pseudo; /* -ep: count distinct FASTA files instead (needs the SA section) */
+    uint32_t value_bits;     /* 8 (-fs) or 16 (-fl and the default float output) */
+    uint32_t count_fetches;  /* 1: also count rank-block fetches (instrumented kernel, slower) */
+    uint32_t reserved[2];
+} gmb_params;
+
+typedef struct gmb_index_info {
+    uint64_t n_text;      /* concatenated text length */
+    uint64_t n_bwt;       /* text + one sentinel per sequence */
+    uint32_t n_seq;
+    uint32_t has_sa;
+    uint64_t blob_bytes;  /* size of the index blob in HBM */
+    uint64_t rank_block_bytes; /* 64 */
+    void *device_blob;    /* device address of the blob (for broadcast / diagnostics) */
+    int32_t device;
+    int32_t reserved;
+} gmb_index_info;
+
+typedef struct gmb_map_stats {
+    double kernel_ms;            /* CUDA-event time of the search kernel */
+    uint64_t positions;          /* k-mer starts actually searched */
+    uint64_t rank_block_fetches; /* only with count_fetches */
+    uint32_t kernel_launches;
+    uint32_t reserved;
+} gmb_map_stats;
+
+/* flags for gmb_index_build */
+#define GMB_BUILD_WITH_SA 1u  /* keep the full suffix array (needed by -ep) */
+#define GMB_BUILD_ON_GPU  2u  /* suffix-sort on the device (prefix doubling) instead of host SA-IS */
+
+const char *gmb_last_error(void);
+const char *gmb_version(void);
+int gmb_device_count(void);
+
+/* Build an index blob in host memory from code text (0..3 = ACGT; 4 = N is rejected for now).
+ * limits: n_seq+1 cumulative offsets.  The blob is released with gmb_blob_free. */
+int gmb_index_build(const uint8_t *codes, const uint64_t *limits, uint32_t n_seq, uint32_t flags,
+                    int device, void **blob_out, uint64_t *bytes_out);
+void gmb_blob_free(void *blob);
+
+/* Build on the GPU and keep the blob in HBM: returns an opened index that owns its device blob.
+ * timings_ms (optional, 4 doubles): H2D, suffix sorting, BWT + block packing, total. */
+int gmb_index_build_device(const uint8_t *codes, const uint64_t *limits, uint32_t n_seq, uint32_t flags,
+                           int device, gmb_index **out, double *timings_ms);
+int gmb_blob_save(const void *blob, uint64_t bytes, const char *path);
+
+/* Open an index for searching on `device`: from a directory written by `genmap index`
+ * (<dir>/index.gmb), from a host blob (copied to HBM) or by adopting a blob that already sits in
+ * device memory (e.g. after an NCCL broadcast; not freed by gmb_index_close). */
+int gmb_index_open(const char *dir, int device, gmb_index **out);
+int gmb_index_from_blob(const void *host_blob, uint64_t bytes, int device, gmb_index **out);
+int gmb_index_adopt_device(void *device_blob, uint64_t bytes, int device, gmb_index **out);
+int gmb_index_close(gmb_index *idx);
+int gmb_index_get_info(const gmb_index *idx, gmb_index_info *info);
+/* Diagnostics / test support: decode one direction's BWT (rev = 0: of T, 1: of T') to one byte per
+ * row (0 = sentinel, 1..4 = A,C,G,T) into host memory (n_bwt bytes). */
+int gmb_index_export_bwt(gmb_index *idx, int rev, uint8_t *out_host);
+
+/* The hot path with HOST output (what the reference's run() does for one FASTA file).
+ * out: text_len elements of value_bits/8 bytes, overwritten.  seq_to_file / n_seq only under -ep. */
+int gmb_map_frequencies(gmb_index *idx, const gmb_params *params, uint64_t text_begin, uint64_t text_len,
+                        const uint64_t *chrom_cum_lengths, uint32_t n_chrom,
+                        const uint64_t (*intervals)[2], uint64_t n_intervals,
+                        const uint32_t *seq_to_file, uint32_t n_seq, void *out, gmb_map_stats *stats);
+
+/* Same, but only for file-local positions [pos_begin, pos_end): `out` receives pos_end - pos_begin
+ * elements (the slice).  This is what a multi-GPU host driver calls per GPU with the slices of one
+ * pinned host vector c. */
+int gmb_map_frequencies_range(gmb_index *idx, const gmb_params *params, uint64_t text_begin, uint64_t text_len,
+                              const uint64_t *chrom_cum_lengths, uint32_t n_chrom,
+                              const uint64_t (*intervals)[2], uint64_t n_intervals,
+                              const uint32_t *seq_to_file, uint32_t n_seq, uint64_t pos_begin,
+                              uint64_t pos_end, void *out, gmb_map_stats *stats);
+
+/* Same, restricted to file-local positions [pos_begin, pos_end) (range-sharding across GPUs) and
+ * writing into DEVICE memory: out_device has text_len elements; only positions inside the range are
+ * written (the caller zero-fills).  Launches on `cuda_stream` (a cudaStream_t; NULL = default
+ * stream) and does not synchronise unless stats != NULL. */
+int gmb_map_frequencies_device(gmb_index *idx, const gmb_params *params, uint64_t text_begin,
+                               uint64_t text_len, const uint64_t *chrom_cum_lengths, uint32_t n_chrom,
+                               const uint64_t (*intervals)[2], uint64_t n_intervals,
+                               const uint32_t *seq_to_file, uint32_t n_seq, uint64_t pos_begin,
+                               uint64_t pos_end, void *out_device, void *cuda_stream, gmb_map_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,185 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle, the reference's golden vectors and the
+outputs of the unmodified reference binary.  Needs a B200: run with -m gpu."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import gmtest as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gm():
+    import genmap_b200
+    from genmap_b200 import _build, _lib
+    _build.build()
+    assert _lib.lib().gmb_device_count() > 0, "no CUDA device"
+    return genmap_b200
+
+
+def _map(gm, ix, K, E, rc=True, bits=16, limits=None, stf=None, file_no=0, intervals=None, **kw):
+    stf_, tb, tl, cum, iv = T._prep(limits, stf, file_no, intervals)
+    return ix.compute_mappability(gm.SearchParams(K, E, rc, False, bits), text_begin=tb, text_len=tl,
+                                  chrom_cum_lengths=cum, intervals=iv, **kw)
+
+
+# ---- index builders ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,nchr,length", [(1, 1, 400), (2, 3, 1500), (3, 5, 77), (4, 2, 20000), (6, 4, 250000)])
+def test_gpu_index_builder_is_bit_identical_to_host_builder(gm, seed, nchr, length):
+    seqs = T.repeat_rich(seed, nchr, length)
+    host = gm.Index.build_blob(seqs, with_sa=True)
+    dev = gm.Index.build_blob(seqs, with_sa=True, on_gpu=True)
+    assert host.nbytes == dev.nbytes
+    if host.tobytes() != dev.tobytes():
+        diff = np.nonzero(host != dev)[0]
+        raise AssertionError("blobs differ at %d bytes, first offsets %s" % (len(diff), diff[:8]))
+
+
+def test_gpu_index_builder_degenerate_texts(gm):
+    for seqs in ([np.zeros(5000, np.uint8)], [np.tile(np.array([0, 1], np.uint8), 3000)] * 3,
+                 [np.array([2], np.uint8), np.array([2], np.uint8)], [np.full(193, 3, np.uint8), np.full(191, 3, np.uint8)]):
+        assert gm.Index.build_blob(seqs, with_sa=True).tobytes() == gm.Index.build_blob(seqs, with_sa=True, on_gpu=True).tobytes()
+
+
+# ---- the reference's golden vectors (Dna4 cases without -ep) ---------------------------------------
+DNA4_CASES = ["1a", "1b", "2a", "2b", "2c", "2d", "2e", "3a", "3b"]
+
+
+@pytest.mark.parametrize("case", DNA4_CASES)
+@pytest.mark.parametrize("bits", [16, 8])
+def test_cuda_matches_reference_golden(gm, case, bits):
+    cfg = T.CASES[case]
+    files, sel, folder = T.load_case(case)
+    seqs, stf, _ = T.case_layout(files)
+    _, limits = T.concat(seqs)
+    ix = gm.Index.build(seqs, on_gpu=False)
+    ext = "freq16" if bits == 16 else "freq8"
+    for fi, (base, recs) in enumerate(files):
+        iv = T.file_intervals(sel, recs)
+        if iv is None:
+            continue
+        gold = np.fromfile(os.path.join(folder, "raw_" + ext, base + ".genmap." + ext),
+                           dtype=np.uint16 if bits == 16 else np.uint8)
+        got = _map(gm, ix, cfg["K"], cfg["E"], rc=cfg["rc"], bits=bits, limits=limits, stf=stf, file_no=fi, intervals=iv)
+        assert np.array_equal(got, gold), (case, base)
+
+
+# ---- outputs of the unmodified reference binary (fixtures) -----------------------------------------
+import test_ref_fixtures as RF  # noqa: E402
+
+
+@pytest.mark.parametrize("line", [c for c in RF.CASES if not c.startswith("dna5") and "-ep" not in c],
+                         ids=lambda c: c.split("|")[0])
+def test_cuda_matches_reference_binary_fixtures(gm, line):
+    name, K, E, flags, bits, seqs, stf, outs = RF.load_fixture(line)
+    _, limits = T.concat(seqs)
+    ix = gm.Index.build(seqs, on_gpu=True)
+    for fi, gold in enumerate(outs):
+        got = _map(gm, ix, K, E, rc="-nc" not in flags, bits=bits, limits=limits, stf=stf, file_no=fi)
+        assert np.array_equal(got, gold), (name, fi, np.nonzero(got != gold)[0][:10])
+
+
+# ---- seeded inputs against the oracle ----------------------------------------------------------------
+@pytest.mark.parametrize("K,E", [(30, 0), (30, 1), (30, 2), (21, 3), (16, 4), (50, 2), (65, 1), (130, 3), (200, 2),
+                                 (2, 0), (3, 1), (4, 2), (5, 3), (6, 4), (32, 2), (33, 2)])
+def test_cuda_matches_oracle(gm, K, E):
+    seqs = T.repeat_rich(7, 3, 3000)
+    _, limits = T.concat(seqs)
+    orc = T.Oracle(seqs)
+    ix = gm.Index.build(seqs)
+    for rc in (True, False):
+        got = _map(gm, ix, K, E, rc=rc, limits=limits)
+        want = orc.map(K, E, revcompl=rc)
+        assert np.array_equal(got, want), (K, E, rc, np.nonzero(got != want)[0][:10])
+
+
+def test_cuda_edge_cases(gm):
+    # sequences shorter than K between longer ones, selection intervals, saturation, palindromes
+    seqs = [np.array([0, 1, 2], np.uint8), T.repeat_rich(3, 1, 300)[0], np.array([3, 3], np.uint8),
+            T.repeat_rich(4, 1, 200)[0], np.array([2], np.uint8)]
+    _, limits = T.concat(seqs)
+    orc, ix = T.Oracle(seqs), gm.Index.build(seqs)
+    assert np.array_equal(_map(gm, ix, 12, 1, limits=limits), orc.map(12, 1))
+    iv = [(0, 2), (10, 40), (35, 60), (290, 320), (500, 506)]
+    assert np.array_equal(_map(gm, ix, 12, 1, limits=limits, intervals=iv), orc.map(12, 1, intervals=iv))
+    # K longer than every sequence: all zeros
+    assert not _map(gm, ix, 250, 0, limits=limits).any()
+    pal = [np.tile(np.array([0, 1, 2, 3], dtype=np.uint8), 2000)]
+    _, pl = T.concat(pal)
+    po, pix = T.Oracle(pal), gm.Index.build(pal)
+    for bits in (8, 16):
+        got = _map(gm, pix, 8, 0, bits=bits, limits=pl)
+        assert np.array_equal(got, po.map(8, 0, value_bits=bits))
+        assert got.max() == (255 if bits == 8 else 3998)
+    with pytest.raises(gm.GenmapError):
+        _map(gm, ix, 30, 5, limits=limits)  # E > 4 (src/mappability.hpp:187)
+    with pytest.raises(gm.GenmapError):
+        _map(gm, ix, 3, 2, limits=limits)   # K < E + 2
+
+
+def test_cuda_fetch_counter_matches_cpu_restatement(gm):
+    """The roofline's algorithmic unit: rank-block fetches counted by the instrumented kernel must
+    equal the count of the host-compiled state machine on the same input."""
+    seqs = T.repeat_rich(21, 2, 40000)
+    _, limits = T.concat(seqs)
+    ix, hs = gm.Index.build(seqs), T.HostSim(seqs)
+    for K, E in [(30, 0), (30, 1), (30, 2)]:
+        out, st = _map(gm, ix, K, E, limits=limits, count_fetches=True, return_stats=True)
+        want, f = hs.map(K, E, return_fetches=True)
+        assert np.array_equal(out, want)
+        assert st.rank_block_fetches == f, (K, E, st.rank_block_fetches, f)
+
+
+# ---- 1 Mbp of the frozen synthetic generator: md5 pins measured with the reference --
+PINS = {0: "15a50bb1184e42daacd5569323356621", 1: "27e5f62a996ee570ba5e600972303903", 2: "4445ff36c72e8ff1a45f3ab08685d0c4"}
+
+
+@pytest.mark.parametrize("E", [0, 1, 2])
+def test_cuda_1mbp_matches_reference_md5(gm, E):
+    seqs = gm.synth_genome(1_000_000, 1, 42)
+    ix = gm.Index.build(seqs)
+    got = ix.compute_mappability(gm.SearchParams(30, E))
+    assert hashlib.md5(got.tobytes()).hexdigest() == PINS[E]
+
+
+def test_cuda_matches_reference_binary_live(gm, tmp_path):
+    """Run the unmodified reference binary on the box (it travels in oracle/_ref) and compare."""
+    if not T.have_reference():
+        pytest.skip("oracle/_ref/genmap_ref not present")
+    seqs = gm.synth_genome(2_000_000, 3, 99)
+    fa = str(tmp_path / "g.fa")
+    T.write_fasta(fa, seqs)
+    ix = gm.Index.build(seqs)
+    for K, E in [(30, 0), (24, 1), (36, 2)]:
+        ref = T.run_reference(fa, K, E)["g"]
+        got = ix.compute_mappability(gm.SearchParams(K, E))
+        assert np.array_equal(got, ref), (K, E)
+
+
+def test_cuda_sharded_ranges_compose(gm):
+    import torch
+    seqs = gm.synth_genome(400_000, 4, 5)
+    ix = gm.Index.build(seqs)
+    p = gm.SearchParams(30, 1)
+    whole = ix.compute_mappability(p)
+    buf = torch.zeros(ix.n_text, dtype=torch.int16, device="cuda:0")
+    cuts = [0, 1, 99_999, 100_010, 250_000, ix.n_text]
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        ix.compute_mappability_device(p, buf.data_ptr(), pos_begin=b, pos_end=e,
+                                      stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.cpu().numpy().view(np.uint16), whole)
+
+
+def test_cuda_range_slices_and_bwt_export(gm):
+    seqs = T.repeat_rich(9, 3, 5000)
+    ix, orc = gm.Index.build(seqs), T.Oracle(seqs)
+    p = gm.SearchParams(20, 1)
+    whole = ix.compute_mappability(p)
+    for b, e in [(0, 10), (4990, 5020), (7000, 15000)]:
+        assert np.array_equal(ix.compute_mappability_range(p, b, e), whole[b:e])
+    for rev in (False, True):
+        assert np.array_equal(ix.export_bwt(rev), orc.bwt(rev))
