@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--errors", type=int, default=0)
     ap.add_argument("--batch-mpos", type=float, default=0.0, help="batch size in Mi positions (0 = by E)")
     ap.add_argument("--extras", default="1,2", help="other E values measured after the main line ('' = none)")
+    ap.add_argument("--jump-depth", type=int, default=-1, help="-1 auto, 0 off, 1..16 max jump-table depth")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
@@ -209,6 +210,7 @@ def main():
         if rank != 0:
             ix = gm.Index.adopt_device(blob_t.data_ptr(), nb, device=local)
     ix.limits = limits
+    ix.set_jump_depth(args.jump_depth)
 
     params = gm.SearchParams(K, E)
     stream = torch.cuda.current_stream().cuda_stream
@@ -279,14 +281,14 @@ def main():
         # rank-block fetches of exactly these batches (instrumented kernel, outside the timed region) and
         # per-launch kernel time from CUDA events on the launching stream
         if rank == 0:
-            f_tot, k_ms, pos0 = 0, [], 0
+            f_tot, k_ms, pos0, lut_tot, jd = 0, [], 0, 0, 0
             for b, e in bl[warmup:]:
                 st = ix.compute_mappability_device(p, out_dev.data_ptr(), pos_begin=b, pos_end=e, stream=stream, count_fetches=True)
-                f_tot += int(st.rank_block_fetches)
+                f_tot += int(st.rank_block_fetches); lut_tot += int(st.jump_table_reads); jd = int(st.jump_depth)
             for b, e in bl[warmup:]:
                 st = ix.compute_mappability_device(p, out_dev.data_ptr(), pos_begin=b, pos_end=e, stream=stream)
                 k_ms.append(st.kernel_ms); pos0 += int(st.positions)
-            res.update(fetches=f_tot, kernel_ms=float(np.mean(k_ms)), searched=pos0)
+            res.update(fetches=f_tot, kernel_ms=float(np.mean(k_ms)), searched=pos0, lut_reads=lut_tot, jump_depth=jd)
         if with_e2e:
             host = torch.empty(batch, dtype=torch.int16).pin_memory().numpy().view(np.uint16)
             bl2 = batches(E_, batch, 1 + steps)
@@ -332,7 +334,9 @@ def main():
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "rank_block_bytes_per_position": r["fetches"] * 64.0 / max(r["searched"], 1),
-                "kernel_ms_per_launch": r["kernel_ms"]}
+                # stricter figure: + jump-table entries (12 B) + pattern text (K/4 -> 16 B) + result (2 B)
+                "total_algorithmic_bytes_per_position": (r["fetches"] * 64.0 + r["lut_reads"] * 12.0) / max(r["searched"], 1) + 18.0,
+                "jump_table_depth": r["jump_depth"], "kernel_ms_per_launch": r["kernel_ms"]}
 
     main_r["E"], main_r["batch"] = E, batch
     extras = {}

@@ -12,7 +12,7 @@ GMB_BUILD_WITH_SA, GMB_BUILD_ON_GPU = 1, 2
 EXPORTS = ["gmb_last_error", "gmb_version", "gmb_device_count", "gmb_index_build", "gmb_blob_free",
            "gmb_index_build_device", "gmb_blob_save", "gmb_index_open", "gmb_index_from_blob",
            "gmb_index_adopt_device", "gmb_index_close", "gmb_index_get_info", "gmb_map_frequencies",
-           "gmb_map_frequencies_range", "gmb_map_frequencies_device", "gmb_index_export_bwt"]
+           "gmb_map_frequencies_range", "gmb_map_frequencies_device", "gmb_index_export_bwt", "gmb_index_set_jump_depth"]
 
 
 class GmbParams(ctypes.Structure):
@@ -29,8 +29,8 @@ class GmbIndexInfo(ctypes.Structure):
 
 class GmbMapStats(ctypes.Structure):
     _fields_ = [("kernel_ms", ctypes.c_double), ("positions", ctypes.c_uint64),
-                ("rank_block_fetches", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint32),
-                ("reserved", ctypes.c_uint32)]
+                ("rank_block_fetches", ctypes.c_uint64), ("jump_table_reads", ctypes.c_uint64),
+                ("kernel_launches", ctypes.c_uint32), ("jump_depth", ctypes.c_uint32)]
 
 
 class GenmapError(RuntimeError):
@@ -78,6 +78,8 @@ def lib():
     L.gmb_map_frequencies_range.restype = ci
     L.gmb_map_frequencies_range.argtypes = [vp, ctypes.POINTER(GmbParams), u64, u64, vp, u32, vp, u64, vp, u32,
                                             u64, u64, vp, ctypes.POINTER(GmbMapStats)]
+    L.gmb_index_set_jump_depth.restype = ci
+    L.gmb_index_set_jump_depth.argtypes = [vp, ci]
     L.gmb_index_export_bwt.restype = ci
     L.gmb_index_export_bwt.argtypes = [vp, ci, vp]
     L.gmb_map_frequencies_device.restype = ci

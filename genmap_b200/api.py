@@ -157,6 +157,10 @@ class Index:
             int(pos_end), _ptr(out), ctypes.byref(st)))
         return (out, st) if return_stats else out
 
+    def set_jump_depth(self, depth):
+        """-1 = automatic, 0 = no jump tables, 1..16 = maximum table depth (see gmb_index_set_jump_depth)."""
+        check(_lib.lib().gmb_index_set_jump_depth(self._h, int(depth)))
+
     def export_bwt(self, rev=False):
         """BWT of T (or of T' if rev) as bytes: 0 = sentinel, 1..4 = A,C,G,T (diagnostics / tests)."""
         out = np.zeros(int(self.info.n_bwt), dtype=np.uint8)

@@ -13,6 +13,7 @@
 #include "../../include/genmap_b200.h"
 #include "gmb_host.h"
 #include "index_build_gpu.cuh"
+#include "jump_table.cuh"
 #include "map_kernel.cuh"
 
 using namespace gmb;
@@ -71,7 +72,53 @@ struct gmb_index {
     void* d_out = nullptr;
     size_t out_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // jump tables by depth (index 0 unused), built lazily; levels <= kJumpKeep stay cached
+    int jump_depth_opt = -1;
+    JtEntry* jt_uni[17] = {};
+    uint32_t* jt_lof[17] = {};
 };
+
+namespace {
+constexpr uint32_t kJumpKeep = 12; // all levels up to here together take < 300 MB
+
+void fill_ctx(const gmb_index* ix, MapCtx& cx)
+{
+    const uint8_t* base = ix->d_blob;
+    cx.blk[0] = reinterpret_cast<const RankBlock*>(base + ix->h.off_fwd);
+    cx.blk[1] = reinterpret_cast<const RankBlock*>(base + ix->h.off_rev);
+    cx.sent[0] = reinterpret_cast<const uint32_t*>(base + ix->h.off_sent_fwd);
+    cx.sent[1] = reinterpret_cast<const uint32_t*>(base + ix->h.off_sent_rev);
+    for (int c = 0; c < 4; ++c) cx.C[c] = (uint32_t)ix->h.C[c];
+    cx.n_bwt = (uint32_t)ix->h.n_bwt;
+    cx.steps = nullptr;
+    cx.starts = nullptr;
+    cx.K = 0; cx.n_search = 0; cx.n_strands = 1; cx.maxv = 65535u;
+}
+
+// make sure the tables of every depth in `plan` exist on the device
+int ensure_jump_tables(gmb_index* ix, const JumpPlan& plan, cudaStream_t stream)
+{
+    bool needed[17] = {};
+    for (uint32_t s = 0; s < kMaxSearches; ++s) needed[plan.depth[s]] = true;
+    MapCtx cx;
+    fill_ctx(ix, cx);
+    for (uint32_t d = 1; d <= plan.max_depth; ++d) {
+        if (ix->jt_uni[d]) continue;
+        const size_t n = (size_t)1 << (2 * d);
+        cudaError_t e = cudaMalloc(&ix->jt_uni[d], n * sizeof(JtEntry));
+        if (e == cudaSuccess) e = cudaMalloc(&ix->jt_lof[d], n * sizeof(uint32_t));
+        if (e == cudaSuccess) e = build_jump_level(cx, d, ix->jt_uni[d - 1], ix->jt_lof[d - 1], ix->jt_uni[d], ix->jt_lof[d], stream);
+        if (e != cudaSuccess) return cuda_fail(e, "jump table");
+    }
+    CU(cudaStreamSynchronize(stream));
+    for (uint32_t d = kJumpKeep + 1; d <= 16; ++d) // big intermediate / stale levels are not kept
+        if (ix->jt_uni[d] && !(d <= plan.max_depth && needed[d])) {
+            cudaFree(ix->jt_uni[d]); cudaFree(ix->jt_lof[d]);
+            ix->jt_uni[d] = nullptr; ix->jt_lof[d] = nullptr;
+        }
+    return GMB_OK;
+}
+} // namespace
 
 extern "C" {
 
@@ -129,7 +176,7 @@ static int finish_open(gmb_index* ix, gmb_index** out)
     ix->sm_count = prop.multiProcessorCount;
     ix->limits.resize((size_t)ix->h.n_seq + 1);
     CU(cudaMemcpy(ix->limits.data(), ix->d_blob + ix->h.off_limits, ix->limits.size() * 8, cudaMemcpyDeviceToHost));
-    CU(cudaMalloc(&ix->d_counters, 2 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&ix->d_counters, 4 * sizeof(unsigned long long)));
     CU(cudaMalloc(&ix->d_steps, sizeof(uint32_t) * kMaxSearches * (kMaxK + 1)));
     CU(cudaEventCreate(&ix->ev0));
     CU(cudaEventCreate(&ix->ev1));
@@ -239,6 +286,7 @@ int gmb_index_close(gmb_index* ix)
     if (ix->d_steps) cudaFree(ix->d_steps);
     if (ix->d_ranges) cudaFree(ix->d_ranges);
     if (ix->d_out) cudaFree(ix->d_out);
+    for (int d = 0; d < 17; ++d) { if (ix->jt_uni[d]) cudaFree(ix->jt_uni[d]); if (ix->jt_lof[d]) cudaFree(ix->jt_lof[d]); }
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);
     delete ix;
@@ -257,6 +305,13 @@ int gmb_index_get_info(const gmb_index* ix, gmb_index_info* info)
     info->rank_block_bytes = kBlockBytes;
     info->device_blob = ix->d_blob;
     info->device = ix->device;
+    return GMB_OK;
+}
+
+int gmb_index_set_jump_depth(gmb_index* ix, int depth)
+{
+    if (!ix || depth < -1 || depth > 16) return fail(GMB_ERR_ARG, "jump depth must be -1 (auto), 0 (off) or 1..16");
+    ix->jump_depth_opt = depth;
     return GMB_OK;
 }
 
@@ -284,14 +339,16 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
     build_work_ranges(text_len, p->K, chrom_cum, n_chrom, reinterpret_cast<const uint64_t*>(intervals), n_intervals,
                       pos_begin, pos_end, ranges);
     const uint32_t nr = (uint32_t)ranges.size();
-    std::vector<uint64_t> host_ranges(2 * (size_t)nr + 1);
-    uint64_t total = 0;
+    std::vector<uint64_t> host_ranges(3 * (size_t)nr + 1); // begin[nr], end[nr], chunk_prefix[nr+1]
+    uint64_t total = 0, chunks = 0;
     for (uint32_t i = 0; i < nr; ++i) {
         host_ranges[i] = ranges[i].begin;
-        host_ranges[nr + i] = total;
+        host_ranges[nr + i] = ranges[i].end;
+        host_ranges[2 * (size_t)nr + i] = chunks;
         total += ranges[i].end - ranges[i].begin;
+        chunks += (ranges[i].end - ranges[i].begin + kChunk - 1) / kChunk;
     }
-    host_ranges[2 * (size_t)nr] = total;
+    host_ranges[3 * (size_t)nr] = chunks;
     if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->positions = total; }
     if (total == 0) { delete tabs; return GMB_OK; }
 
@@ -303,17 +360,30 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
     }
     CU(cudaMemcpyAsync(ix->d_ranges, host_ranges.data(), host_ranges.size() * 8, cudaMemcpyHostToDevice, stream));
     CU(cudaMemcpyAsync(ix->d_steps, tabs->step, sizeof(uint32_t) * tabs->n_search * p->K, cudaMemcpyHostToDevice, stream));
-    CU(cudaMemsetAsync(ix->d_counters, 0, 2 * sizeof(unsigned long long), stream));
+    CU(cudaMemsetAsync(ix->d_counters, 0, 3 * sizeof(unsigned long long), stream));
     // the two staging copies above read pageable host memory: they have completed (staged) on return
 
     MapLaunch L;
     const uint8_t* base = ix->d_blob;
-    L.cx.blk[0] = reinterpret_cast<const RankBlock*>(base + ix->h.off_fwd);
-    L.cx.blk[1] = reinterpret_cast<const RankBlock*>(base + ix->h.off_rev);
-    L.cx.sent[0] = reinterpret_cast<const uint32_t*>(base + ix->h.off_sent_fwd);
-    L.cx.sent[1] = reinterpret_cast<const uint32_t*>(base + ix->h.off_sent_rev);
-    for (int c = 0; c < 4; ++c) L.cx.C[c] = (uint32_t)ix->h.C[c];
-    L.cx.n_bwt = (uint32_t)ix->h.n_bwt;
+    fill_ctx(ix, L.cx);
+    JumpPlan plan;
+    {
+        const char* env = std::getenv("GMB_JUMP_DEPTH");
+        int want = ix->jump_depth_opt;
+        if (want < 0 && env && *env) want = std::atoi(env);
+        uint32_t maxd = want < 0 ? default_jump_depth(ix->h.n_bwt) : (uint32_t)want;
+        if (maxd > 16) maxd = 16;
+        plan_jump_tables(*tabs, maxd, plan);
+        int rcj = ensure_jump_tables(ix, plan, stream);
+        if (rcj != GMB_OK) { delete tabs; return rcj; }
+        for (uint32_t s2 = 0; s2 < kMaxSearches; ++s2) {
+            const uint32_t d = plan.depth[s2];
+            L.starts[s2].uni = d ? ix->jt_uni[d] : nullptr;
+            L.starts[s2].lof = (d && plan.need_lof[s2]) ? ix->jt_lof[d] : nullptr;
+            L.starts[s2].a = plan.a[s2];
+            L.starts[s2].d = d;
+        }
+    }
     L.cx.steps = ix->d_steps;
     L.cx.K = p->K;
     L.cx.n_search = tabs->n_search;
@@ -323,8 +393,10 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
     L.text = reinterpret_cast<const uint64_t*>(base + ix->h.off_text);
     L.text_begin = text_begin;
     L.range_begin = ix->d_ranges;
-    L.range_prefix = ix->d_ranges + nr;
+    L.range_end = ix->d_ranges + nr;
+    L.chunk_prefix = ix->d_ranges + 2 * (size_t)nr;
     L.n_ranges = nr;
+    L.n_chunks = chunks;
     L.n_work = total;
     L.work_counter = ix->d_counters;
     L.fetch_counter = ix->d_counters + 1;
@@ -342,10 +414,12 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
         CU(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
         stats->kernel_ms = ms;
         stats->kernel_launches = 1;
+        stats->jump_depth = plan.max_depth;
         if (L.count_fetches) {
-            unsigned long long f = 0;
-            CU(cudaMemcpy(&f, ix->d_counters + 1, sizeof(f), cudaMemcpyDeviceToHost));
-            stats->rank_block_fetches = f;
+            unsigned long long f[2] = {0, 0};
+            CU(cudaMemcpy(f, ix->d_counters + 1, sizeof(f), cudaMemcpyDeviceToHost));
+            stats->rank_block_fetches = f[0];
+            stats->jump_table_reads = f[1];
         }
     }
     return GMB_OK;

@@ -20,17 +20,18 @@ namespace gmb {
 
 struct Ranks { uint32_t a, c, g, t, s; };
 
+// one rank block in registers: header + the two bit planes as six 32-symbol pieces each
 struct BlockRegs {
     uint32_t h[4];
-    uint64_t w[3][2];
+    uint32_t p0[6], p1[6];
 };
 
-GMB_HD uint32_t popc64(uint64_t x)
+GMB_HD uint32_t popc32(uint32_t x)
 {
 #if defined(__CUDA_ARCH__)
-    return (uint32_t)__popcll(x);
+    return (uint32_t)__popc(x);
 #else
-    return (uint32_t)__builtin_popcountll(x);
+    return (uint32_t)__builtin_popcount(x);
 #endif
 }
 
@@ -47,19 +48,40 @@ GMB_HD BlockRegs load_block(const RankBlock* p)
                  : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7)
                  : "l"(reinterpret_cast<const char*>(p) + 32));
     b.h[0] = r0; b.h[1] = r1; b.h[2] = r2; b.h[3] = r3;
-    b.w[0][0] = ((uint64_t)r5 << 32) | r4; b.w[0][1] = ((uint64_t)r7 << 32) | r6;
-    b.w[1][0] = ((uint64_t)s1 << 32) | s0; b.w[1][1] = ((uint64_t)s3 << 32) | s2;
-    b.w[2][0] = ((uint64_t)s5 << 32) | s4; b.w[2][1] = ((uint64_t)s7 << 32) | s6;
+    b.p0[0] = r4; b.p0[1] = r5; b.p1[0] = r6; b.p1[1] = r7;
+    b.p0[2] = s0; b.p0[3] = s1; b.p1[2] = s2; b.p1[3] = s3;
+    b.p0[4] = s4; b.p0[5] = s5; b.p1[4] = s6; b.p1[5] = s7;
 #else
     b.h[0] = p->cnt[0]; b.h[1] = p->cnt[1]; b.h[2] = p->cnt[2]; b.h[3] = p->sent;
-    for (int k = 0; k < 3; ++k) { b.w[k][0] = p->w[k][0]; b.w[k][1] = p->w[k][1]; }
+    for (int k = 0; k < 3; ++k) {
+        b.p0[2 * k] = (uint32_t)p->w[k][0]; b.p0[2 * k + 1] = (uint32_t)(p->w[k][0] >> 32);
+        b.p1[2 * k] = (uint32_t)p->w[k][1]; b.p1[2 * k + 1] = (uint32_t)(p->w[k][1] >> 32);
+    }
 #endif
     return b;
 }
 
-GMB_HD uint64_t low_mask(int bits)
+// mask of the symbols of piece q (32 symbols) that lie before in-block offset r
+GMB_HD uint32_t piece_mask(uint32_t r, int q)
 {
-    return bits <= 0 ? 0ull : (bits >= 64 ? ~0ull : ((1ull << bits) - 1ull));
+    const int w = (int)r - 32 * q;
+#if defined(__CUDA_ARCH__)
+    uint32_t m;
+    const int wc = w > 0 ? w : 0;
+    asm("shl.b32 %0, 1, %1;" : "=r"(m) : "r"(wc)); // PTX shl clamps shift amounts > 31: 1 << 32 == 0
+    return m - 1u;
+#else
+    return w <= 0 ? 0u : (w >= 32 ? ~0u : ((1u << w) - 1u));
+#endif
+}
+
+// sentinel rows of this block before BWT position i (rare path: the block holds a sentinel)
+GMB_HD uint32_t sentinels_in_block_before(const BlockRegs& b, uint32_t i, const uint32_t* sent_pos)
+{
+    const uint32_t s_before = b.h[3] >> 8, s_in = b.h[3] & 0xffu;
+    uint32_t s = 0;
+    for (uint32_t k = 0; k < s_in; ++k) s += sent_pos[s_before + k] < i;
+    return s;
 }
 
 // ranks of all symbols at BWT position i = blk*192 + r  (rank_c(i) = #c in bwt[0,i))
@@ -67,26 +89,53 @@ GMB_HD Ranks block_rank(const BlockRegs& b, uint32_t r, uint32_t i, const uint32
 {
     uint32_t a = 0, c = 0, g = 0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        uint64_t m = low_mask((int)r - 64 * k);
-        uint64_t p0 = b.w[k][0], p1 = b.w[k][1];
-        a += popc64(~(p0 | p1) & m);
-        c += popc64(p0 & ~p1 & m);
-        g += popc64(~p0 & p1 & m);
+    for (int q = 0; q < 6; ++q) {
+        const uint32_t m = piece_mask(r, q);
+        const uint32_t x0 = b.p0[q], x1 = b.p1[q];
+        a += popc32(~x0 & ~x1 & m);
+        c += popc32(x0 & ~x1 & m);
+        g += popc32(~x0 & x1 & m);
     }
-    uint32_t s_before = b.h[3] >> 8, s_in = b.h[3] & 0xffu, s = 0;
-    if (s_in) // rare: this block holds sentinel rows (stored as code 0)
-        for (uint32_t k = 0; k < s_in; ++k) s += sent_pos[s_before + k] < i;
+    uint32_t s = 0;
+    if (b.h[3] & 0xffu) s = sentinels_in_block_before(b, i, sent_pos);
     Ranks R;
     R.a = b.h[0] + a - s;
     R.c = b.h[1] + c;
     R.g = b.h[2] + g;
-    R.s = s_before + s;
+    R.s = (b.h[3] >> 8) + s;
     R.t = i - R.a - R.c - R.g - R.s;
     return R;
 }
 
+// rank of ONE symbol (exact-match steps): a third of the popcounts of block_rank
+GMB_HD uint32_t block_rank_one(const BlockRegs& b, uint32_t r, uint32_t i, uint32_t sym, const uint32_t* sent_pos)
+{
+    const uint32_t k0 = (sym & 1u) ? 0u : ~0u, k1 = (sym & 2u) ? 0u : ~0u;
+    uint32_t n = 0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) n += popc32((b.p0[q] ^ k0) & (b.p1[q] ^ k1) & piece_mask(r, q));
+    const uint32_t s_before = b.h[3] >> 8;
+    uint32_t base;
+    if (sym == 3u) base = (i - r) - b.h[0] - b.h[1] - b.h[2] - s_before; // T is the derived counter
+    else base = sym == 0u ? b.h[0] : (sym == 1u ? b.h[1] : b.h[2]);
+    if (sym == 0u && (b.h[3] & 0xffu)) n -= sentinels_in_block_before(b, i, sent_pos);
+    return base + n;
+}
+
 // ---- pattern -----------------------------------------------------------------------------------------
+GMB_HD uint64_t reverse_groups64(uint64_t x) // reverse the order of the 32 two-bit groups
+{
+#if defined(__CUDA_ARCH__)
+    x = __brevll(x);
+#else
+    x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0f0f0f0f0f0f0f0full) | ((x & 0x0f0f0f0f0f0f0f0full) << 4);
+    x = __builtin_bswap64(x);
+#endif
+    return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+}
+
 template <int KW>
 struct Pattern {
     uint64_t w[KW];
@@ -94,6 +143,46 @@ struct Pattern {
     {
         if (KW == 1) return (uint32_t)(w[0] >> (2 * i)) & 3u;
         return (uint32_t)(w[i >> 5] >> (2 * (i & 31))) & 3u;
+    }
+    // the d <= 16 characters starting at offset a as an integer, character a in the low bits
+    GMB_HD uint32_t bits(uint32_t a, uint32_t d) const
+    {
+        uint64_t v;
+        if (KW == 1) {
+            v = w[0] >> (2 * a);
+        } else {
+            const uint32_t wi = a >> 5, sh = 2 * (a & 31);
+            v = w[wi] >> sh;
+            if (sh && wi + 1 < (uint32_t)KW) v |= w[wi + 1] << (64 - sh);
+        }
+        return (uint32_t)(v & ((1ull << (2 * d)) - 1ull));
+    }
+    // in place: the reverse complement of the K-character pattern (src/algo.hpp:284-305)
+    GMB_HD void reverse_complement(uint32_t K)
+    {
+        if constexpr (KW == 1) { // registers only
+            w[0] = reverse_groups64(~w[0]) >> (64u - 2u * K);
+        } else {
+        uint64_t y[KW + 1];
+#pragma unroll
+        for (int k = 0; k < KW; ++k) y[k] = reverse_groups64(~w[KW - 1 - k]);
+        y[KW] = 0;
+        const uint32_t s = 2u * (32u * KW - K), ws = s >> 6, bs = s & 63u;
+#pragma unroll
+        for (int k = 0; k < KW; ++k) {
+            const uint32_t a = k + ws;
+            uint64_t v = a <= (uint32_t)KW ? y[a] >> bs : 0ull;
+            if (bs && a + 1 <= (uint32_t)KW) v |= y[a + 1] << (64 - bs);
+            w[k] = v;
+        }
+        // clear the bits above 2K
+        const uint32_t top = K >> 5, rem = K & 31u;
+#pragma unroll
+        for (int k = 0; k < KW; ++k) {
+            if ((uint32_t)k > top || ((uint32_t)k == top && rem == 0)) w[k] = 0;
+            else if ((uint32_t)k == top) w[k] &= (1ull << (2 * rem)) - 1ull;
+        }
+        }
     }
 };
 
@@ -115,14 +204,47 @@ GMB_HD void load_pattern(Pattern<KW>& p, const uint64_t* text, uint64_t pos, uin
 }
 
 // ---- search context ------------------------------------------------------------------------------------
+// Jump table of one search: every search starts with an error-free, rightwards run (U[0] = 0 in every
+// scheme, first direction Rev: src/find2_index_approx.hpp:441); the node reached after its first `d`
+// characters is looked up instead of walked.  key = those characters, the first one in the low bits.
+struct JtEntry { uint32_t lo_r, size; };
+struct SearchStart {
+    const JtEntry* uni;   // [4^d] interval in SA(T') + size            (nullptr: no table, start at the root)
+    const uint32_t* lof;  // [4^d] start of the interval in SA(T)       (nullptr when never needed again)
+    uint32_t a;           // pattern offset of the first character
+    uint32_t d;           // depth of the table
+};
+
 struct MapCtx {
     const RankBlock* blk[2];  // [0]: BWT of T (extend left), [1]: BWT of T' (extend right)
     const uint32_t* sent[2];
     uint32_t C[4];
     uint32_t n_bwt;
     const uint32_t* steps;    // n_search * K packed steps (gmb_layout.h)
+    const SearchStart* starts; // n_search entries
     uint32_t K, n_search, n_strands, maxv;
 };
+
+struct Node { uint32_t lo_f, lo_r, size; };
+
+// P -> Pc on the bidirectional index (goDown(it, c, Rev()): index_bidirectional_stree.h:250-265)
+GMB_HD Node extend_right(const Node& n, uint32_t c, const MapCtx& cx)
+{
+    Node m;
+    m.lo_f = 0; m.lo_r = 0; m.size = 0;
+    if (n.size == 0) return m;
+    const uint32_t x = n.lo_r, y = n.lo_r + n.size;
+    const uint32_t bx = x / kBlockBases, by = y / kBlockBases;
+    BlockRegs rb = load_block(cx.blk[1] + bx);
+    const Ranks R0 = block_rank(rb, x - bx * kBlockBases, x, cx.sent[1]);
+    if (by != bx) rb = load_block(cx.blk[1] + by);
+    const Ranks R1 = block_rank(rb, y - by * kBlockBases, y, cx.sent[1]);
+    const uint32_t n0 = R1.a - R0.a, n1 = R1.c - R0.c, n2 = R1.g - R0.g, n3 = R1.t - R0.t;
+    m.size = c == 0 ? n0 : (c == 1 ? n1 : (c == 2 ? n2 : n3));
+    m.lo_r = (c == 0 ? cx.C[0] + R0.a : (c == 1 ? cx.C[1] + R0.c : (c == 2 ? cx.C[2] + R0.g : cx.C[3] + R0.t)));
+    m.lo_f = n.lo_f + (R1.s - R0.s) + (c > 0 ? n0 : 0u) + (c > 1 ? n1 : 0u) + (c > 2 ? n2 : 0u);
+    return m;
+}
 
 template <int KW>
 struct Chain {
@@ -138,17 +260,32 @@ struct Chain {
 constexpr int kFrameWords = 10;
 
 template <int KW>
-GMB_HD void chain_start(Chain<KW>& st, const MapCtx& cx)
+GMB_HD void chain_start(Chain<KW>& st, const MapCtx& cx, unsigned long long* lut_reads)
 {
-    st.lo_f = 0; st.lo_r = 0; st.size = cx.n_bwt;
-    st.t = 0; st.e = 0; st.lvmask = 0;
+    const SearchStart S = cx.starts[st.s];
+    st.e = 0; st.lvmask = 0;
+    if (S.uni == nullptr) {
+        st.lo_f = 0; st.lo_r = 0; st.size = cx.n_bwt; st.t = 0;
+    } else {
+        const uint32_t key = st.pat.bits(S.a, S.d);
+#if defined(__CUDA_ARCH__)
+        const uint2 e = __ldg(reinterpret_cast<const uint2*>(S.uni) + key);
+        st.lo_r = e.x; st.size = e.y;
+        st.lo_f = S.lof ? __ldg(S.lof + key) : 0u;
+#else
+        st.lo_r = S.uni[key].lo_r; st.size = S.uni[key].size;
+        st.lo_f = S.lof ? S.lof[key] : 0u;
+#endif
+        st.t = S.d;
+        if (lut_reads) *lut_reads += 1;
+    }
 }
 
 template <int KW>
-GMB_HD void chain_begin_kmer(Chain<KW>& st, const MapCtx& cx)
+GMB_HD void chain_begin_kmer(Chain<KW>& st, const MapCtx& cx, unsigned long long* lut_reads)
 {
     st.acc = 0; st.s = 0; st.strand = 0;
-    chain_start(st, cx);
+    chain_start(st, cx, lut_reads);
 }
 
 GMB_HD uint32_t sel4(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t c)
@@ -177,70 +314,91 @@ GMB_HD uint32_t highest_bit_index(uint32_t m)
 // One state-machine iteration.  Returns false when the k-mer is finished (st.acc is final).
 // `fetches` counts rank-block reads (the roofline's algorithmic unit), when non-null.
 template <int KW, class Frames>
-GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned long long* fetches)
+GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned long long* fetches,
+                       unsigned long long* lut_reads)
 {
     const uint32_t K = cx.K;
     const uint32_t ent = cx.steps[st.s * K + st.t];
     const uint32_t dir = step_dir(ent);
     const uint32_t pos = step_pos(ent);
-    const uint32_t p = st.strand ? 3u - st.pat.at(K - 1 - pos) : st.pat.at(pos);
-
-    // ---- expand the node: ranks of all symbols at both interval ends of the active index ----------
-    const uint32_t x = dir ? st.lo_r : st.lo_f;
-    const uint32_t z = dir ? st.lo_f : st.lo_r;
-    const uint32_t y = x + st.size;
-    const RankBlock* B = dir ? cx.blk[1] : cx.blk[0]; // selects, not indexing: keeps cx in registers
-    const uint32_t* SP = dir ? cx.sent[1] : cx.sent[0];
-    const uint32_t bx = x / kBlockBases, by = y / kBlockBases;
-    BlockRegs rb = load_block(B + bx);
-    const Ranks R0 = block_rank(rb, x - bx * kBlockBases, x, SP);
-    if (by != bx) rb = load_block(B + by);
-    const Ranks R1 = block_rank(rb, y - by * kBlockBases, y, SP);
-    if (fetches) *fetches += 1u + (by != bx);
-
-    const uint32_t n0 = R1.a - R0.a, n1 = R1.c - R0.c, n2 = R1.g - R0.g, n3 = R1.t - R0.t;
-    const uint32_t l0 = cx.C[0] + R0.a, l1 = cx.C[1] + R0.c, l2 = cx.C[2] + R0.g, l3 = cx.C[3] + R0.t;
-    const uint32_t oth0 = z + (R1.s - R0.s);
-
-    // ---- admissible children (search-scheme bounds, find2_index_approx.hpp:388-389,254-258) -------
-    const uint32_t ub = step_ub(ent), lb = step_lb(ent), rem = step_rem(ent);
-    uint32_t ok = 0;
-    {
-        const uint32_t em = st.e + 1; // errors after a mismatching child
-        const bool mis_ok = em <= ub && em + rem >= lb;
-        const bool hit_ok = st.e <= ub && st.e + rem >= lb;
-        if (n0 && (p == 0 ? hit_ok : mis_ok)) ok |= 1u;
-        if (n1 && (p == 1 ? hit_ok : mis_ok)) ok |= 2u;
-        if (n2 && (p == 2 ? hit_ok : mis_ok)) ok |= 4u;
-        if (n3 && (p == 3 ? hit_ok : mis_ok)) ok |= 8u;
-    }
+    const uint32_t p = st.pat.at(pos); // on the reverse strand st.pat already holds the reverse complement
 
     bool descend = false;
     uint32_t c = 0, csize = 0, cact = 0, coth = 0, ce = 0, ct = 0, cdir = dir;
 
-    if (st.t + 1 == K) {
-        // children are full-length matches: count them (src/algo.hpp:48,191)
-        uint64_t sum = (uint64_t)st.acc + ((ok & 1u) ? n0 : 0u) + ((ok & 2u) ? n1 : 0u) +
-                       ((ok & 4u) ? n2 : 0u) + ((ok & 8u) ? n3 : 0u);
-        st.acc = sum < cx.maxv ? (uint32_t)sum : cx.maxv;
-    } else if (ok) {
-        const uint32_t mm = ok & ~(1u << p);
-        c = mm ? lowest_bit_index(mm) : p; // mismatching children first, the matching child last
-        const uint32_t pending = ok & ~(1u << c);
-        if (pending) {
-            const uint32_t lv = st.e;
-            fr.set(lv, 0, l0); fr.set(lv, 1, l1); fr.set(lv, 2, l2); fr.set(lv, 3, l3);
-            fr.set(lv, 4, n0); fr.set(lv, 5, n1); fr.set(lv, 6, n2); fr.set(lv, 7, n3);
-            fr.set(lv, 8, oth0);
-            fr.set(lv, 9, st.t | (pending << 8));
-            st.lvmask |= 1u << lv;
+    if (st.size == 0) {
+        // an empty node can only come out of a jump table: nothing to search here
+    } else if (st.strand == 0 && st.e == 0 && st.size == 1 && step_exact_ok(ent)) {
+        // Forward strand, no error so far, one occurrence left: it is the query's own position in the
+        // indexed text, so the rest of the pattern matches it exactly and no mismatching extension
+        // exists.  The subtree contributes exactly one occurrence — no need to walk it.
+        st.acc = st.acc + 1u < cx.maxv ? st.acc + 1u : cx.maxv;
+    } else {
+        // ---- expand the node: ranks at both interval ends of the active index -----------------------
+        const uint32_t x = dir ? st.lo_r : st.lo_f;
+        const uint32_t z = dir ? st.lo_f : st.lo_r;
+        const uint32_t y = x + st.size;
+        const RankBlock* B = dir ? cx.blk[1] : cx.blk[0]; // selects, not indexing: keeps cx in registers
+        const uint32_t* SP = dir ? cx.sent[1] : cx.sent[0];
+        const uint32_t bx = x / kBlockBases, by = y / kBlockBases;
+        const uint32_t rx = x - bx * kBlockBases, ry = y - by * kBlockBases;
+        if (fetches) *fetches += 1u + (by != bx);
+
+        // admissible children (search-scheme bounds, find2_index_approx.hpp:388-389,254-258)
+        const uint32_t ub = step_ub(ent), lb = step_lb(ent), rem = step_rem(ent);
+        const uint32_t em = st.e + 1; // errors after a mismatching child
+        const bool mis_ok = em <= ub && em + rem >= lb;
+        const bool hit_ok = st.e + rem >= lb; // st.e <= ub is an invariant of the walk
+
+        uint32_t n0, n1, n2, n3, l0, l1, l2, l3, oth0;
+        BlockRegs rb = load_block(B + bx);
+        if (!mis_ok && !step_sync(ent)) {
+            // exact step whose other-index interval is never needed again: one symbol's rank suffices
+            const uint32_t r0 = block_rank_one(rb, rx, x, p, SP);
+            if (by != bx) rb = load_block(B + by);
+            const uint32_t r1 = block_rank_one(rb, ry, y, p, SP);
+            const uint32_t np = r1 - r0, lp = sel4(cx.C[0], cx.C[1], cx.C[2], cx.C[3], p) + r0;
+            n0 = p == 0 ? np : 0u; n1 = p == 1 ? np : 0u; n2 = p == 2 ? np : 0u; n3 = p == 3 ? np : 0u;
+            l0 = l1 = l2 = l3 = lp;
+            oth0 = z;
+        } else {
+            const Ranks R0 = block_rank(rb, rx, x, SP);
+            if (by != bx) rb = load_block(B + by);
+            const Ranks R1 = block_rank(rb, ry, y, SP);
+            n0 = R1.a - R0.a; n1 = R1.c - R0.c; n2 = R1.g - R0.g; n3 = R1.t - R0.t;
+            l0 = cx.C[0] + R0.a; l1 = cx.C[1] + R0.c; l2 = cx.C[2] + R0.g; l3 = cx.C[3] + R0.t;
+            oth0 = z + (R1.s - R0.s);
         }
-        csize = sel4(n0, n1, n2, n3, c);
-        cact = sel4(l0, l1, l2, l3, c);
-        coth = oth0 + (c > 0 ? n0 : 0u) + (c > 1 ? n1 : 0u) + (c > 2 ? n2 : 0u);
-        ce = st.e + (c != p);
-        ct = st.t + 1;
-        descend = true;
+        uint32_t ok = 0;
+        if (n0 && (p == 0 ? hit_ok : mis_ok)) ok |= 1u;
+        if (n1 && (p == 1 ? hit_ok : mis_ok)) ok |= 2u;
+        if (n2 && (p == 2 ? hit_ok : mis_ok)) ok |= 4u;
+        if (n3 && (p == 3 ? hit_ok : mis_ok)) ok |= 8u;
+
+        if (st.t + 1 == K) {
+            // children are full-length matches: count them (src/algo.hpp:48,191)
+            const uint64_t sum = (uint64_t)st.acc + ((ok & 1u) ? n0 : 0u) + ((ok & 2u) ? n1 : 0u) +
+                                 ((ok & 4u) ? n2 : 0u) + ((ok & 8u) ? n3 : 0u);
+            st.acc = sum < cx.maxv ? (uint32_t)sum : cx.maxv;
+        } else if (ok) {
+            const uint32_t mm = ok & ~(1u << p);
+            c = mm ? lowest_bit_index(mm) : p; // mismatching children first, the matching child last
+            const uint32_t pending = ok & ~(1u << c);
+            if (pending) {
+                const uint32_t lv = st.e;
+                fr.set(lv, 0, l0); fr.set(lv, 1, l1); fr.set(lv, 2, l2); fr.set(lv, 3, l3);
+                fr.set(lv, 4, n0); fr.set(lv, 5, n1); fr.set(lv, 6, n2); fr.set(lv, 7, n3);
+                fr.set(lv, 8, oth0);
+                fr.set(lv, 9, st.t | (pending << 8));
+                st.lvmask |= 1u << lv;
+            }
+            csize = sel4(n0, n1, n2, n3, c);
+            cact = sel4(l0, l1, l2, l3, c);
+            coth = oth0 + (c > 0 ? n0 : 0u) + (c > 1 ? n1 : 0u) + (c > 2 ? n2 : 0u);
+            ce = st.e + (c != p);
+            ct = st.t + 1;
+            descend = true;
+        }
     }
 
     if (!descend) {
@@ -250,8 +408,9 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
             if (++st.s == cx.n_search) {
                 st.s = 0;
                 if (++st.strand == cx.n_strands) return false;
+                st.pat.reverse_complement(K);
             }
-            chain_start(st, cx);
+            chain_start(st, cx, lut_reads);
             return true;
         }
         const uint32_t lv = highest_bit_index(st.lvmask);
@@ -260,7 +419,7 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
         uint32_t pending = meta >> 8;
         const uint32_t entf = cx.steps[st.s * K + tf];
         const uint32_t posf = step_pos(entf);
-        const uint32_t pf = st.strand ? 3u - st.pat.at(K - 1 - posf) : st.pat.at(posf);
+        const uint32_t pf = st.pat.at(posf);
         const uint32_t mm = pending & ~(1u << pf);
         c = mm ? lowest_bit_index(mm) : pf;
         pending &= ~(1u << c);

@@ -70,9 +70,37 @@ bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err
             bool sw = false;
             for (uint32_t b2 = a + 1; b2 < K; ++b2) sw |= step_dir(st[b2]) != step_dir(st[a]);
             if (sw) st[a] |= 1u << 25;
+            bool zero_lb = true; // may the rest of the pattern be matched without any further error?
+            for (uint32_t b2 = a; b2 < K; ++b2) zero_lb &= step_lb(st[b2]) == 0;
+            if (zero_lb) st[a] |= 1u << 26;
         }
     }
     return true;
+}
+
+void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan)
+{
+    plan.max_depth = 0;
+    for (uint32_t s = 0; s < kMaxSearches; ++s) { plan.depth[s] = 0; plan.a[s] = 0; plan.need_lof[s] = false; }
+    const uint32_t K = tabs.K;
+    for (uint32_t s = 0; s < tabs.n_search; ++s) {
+        const uint32_t* st = tabs.step + s * K;
+        uint32_t run = 0;
+        while (run < K && step_dir(st[run]) == 1 && step_ub(st[run]) == 0 && step_pos(st[run]) == step_pos(st[0]) + run) ++run;
+        uint32_t d = std::min(run, std::min(max_depth, K - 1));
+        if (d > 16) d = 16;
+        plan.depth[s] = d;
+        plan.a[s] = step_pos(st[0]);
+        plan.need_lof[s] = d > 0 && step_sync(st[d - 1]) != 0;
+        plan.max_depth = std::max(plan.max_depth, d);
+    }
+}
+
+uint32_t default_jump_depth(uint64_t n_bwt)
+{
+    uint32_t d = 0;
+    while (d < 15 && (n_bwt >> (2 * (d + 1))) != 0) ++d;
+    return d < 1 ? 1 : d;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -14,6 +14,19 @@ namespace gmb {
 // Returns false with `err` set if (K,E) is unsupported.
 bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err);
 
+// Which jump table each search of a (K,E) configuration can use: depth[s] = min(length of the search's
+// initial error-free rightwards run, max_depth, K-1); 0 = none.  need_lof[s]: a later step extends to the
+// left, so the interval in SA(T) must be known too.
+struct JumpPlan {
+    uint32_t depth[kMaxSearches];
+    uint32_t a[kMaxSearches];
+    bool need_lof[kMaxSearches];
+    uint32_t max_depth;
+};
+void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan);
+// floor(log4(n_bwt)) clamped to [1,15]: about one expected occurrence per table entry
+uint32_t default_jump_depth(uint64_t n_bwt);
+
 // 256-byte aligned growable byte buffer for the index blob
 struct Blob {
     std::vector<uint64_t> storage;

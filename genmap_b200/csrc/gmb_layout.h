@@ -73,13 +73,15 @@ static_assert(sizeof(IndexHeader) % 8 == 0, "header alignment");
 // left (dir=0, BWT of T); a child with e' errors is admissible iff e' <= ub and e' + rem >= lb, where
 // rem = characters of the current block still unread after this one.
 //   bits  0..7  pos      bits  8..15 rem      bits 16..19 ub     bits 20..23 lb    bit 24 dir
-//   bit 25 = the other strand's interval is still needed after this step (a direction switch follows)
+//   bit 25 = the other index's interval is still needed after this step (a direction switch follows)
+//   bit 26 = every block from this step on has lb == 0: an error-free completion is admissible
 GMB_HD uint32_t step_pos(uint32_t s) { return s & 0xffu; }
 GMB_HD uint32_t step_rem(uint32_t s) { return (s >> 8) & 0xffu; }
 GMB_HD uint32_t step_ub(uint32_t s) { return (s >> 16) & 0xfu; }
 GMB_HD uint32_t step_lb(uint32_t s) { return (s >> 20) & 0xfu; }
 GMB_HD uint32_t step_dir(uint32_t s) { return (s >> 24) & 1u; }
 GMB_HD uint32_t step_sync(uint32_t s) { return (s >> 25) & 1u; }
+GMB_HD uint32_t step_exact_ok(uint32_t s) { return (s >> 26) & 1u; }
 
 struct StepTables {
     uint32_t n_search;

@@ -22,24 +22,12 @@ namespace gmb {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr unsigned kChunk = 128; // positions fetched per global atomic
 
 struct SmemFrames {
     uint32_t* base; // + threadIdx.x
     __device__ __forceinline__ void set(uint32_t lv, uint32_t i, uint32_t v) { base[(lv * kFrameWords + i) * kThreads] = v; }
     __device__ __forceinline__ uint32_t get(uint32_t lv, uint32_t i) const { return base[(lv * kFrameWords + i) * kThreads]; }
 };
-
-__device__ __forceinline__ uint64_t work_to_pos(const uint64_t* __restrict__ rb, const uint64_t* __restrict__ rp,
-                                                uint32_t n_ranges, uint64_t w)
-{
-    uint32_t lo = 0, hi = n_ranges; // largest r with rp[r] <= w
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(rp + mid) <= w) lo = mid; else hi = mid;
-    }
-    return __ldg(rb + lo) + (w - __ldg(rp + lo));
-}
 
 template <int KW, bool COUNT, typename OutT>
 __global__ void __launch_bounds__(kThreads) map_kernel(const MapLaunch L)
@@ -50,8 +38,13 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const MapLaunch L)
     for (uint32_t i = threadIdx.x; i < n_steps; i += kThreads) steps_s[i] = L.cx.steps[i];
     __syncthreads();
 
+    __shared__ SearchStart starts_s[kMaxSearches];
+    if (threadIdx.x < kMaxSearches) starts_s[threadIdx.x] = L.starts[threadIdx.x];
+    __syncthreads();
+
     MapCtx cx = L.cx;
     cx.steps = steps_s;
+    cx.starts = starts_s;
     SmemFrames fr{smem + ((n_steps + 31u) & ~31u) + threadIdx.x};
 
     const unsigned lane = threadIdx.x & 31u;
@@ -61,52 +54,76 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const MapLaunch L)
     Chain<KW> st;
     uint64_t j = 0;
     bool active = false, exhausted = false;
-    unsigned long long pool_next = 0, pool_end = 0; // warp-uniform
-    unsigned long long fetches = 0;
+    // warp-uniform pool of consecutive positions [pool_next, pool_end) and "no more chunks" flag
+    unsigned long long pool_next = 0, pool_end = 0;
+    bool pool_done = false;
+    unsigned long long fetches = 0, lut_reads = 0;
 
     for (;;) {
-        // ---- refill: lanes without a k-mer take the next work items --------------------------------
+        // ---- refill: lanes without a k-mer take the next positions of the warp's pool --------------
         const bool need = !active && !exhausted;
         const unsigned m = __ballot_sync(0xffffffffu, need);
         if (m) {
             const unsigned cnt = __popc(m), rank = __popc(m & lt_mask);
-            const unsigned long long avail = pool_end - pool_next;
-            unsigned long long w;
-            if (avail < cnt) {
-                unsigned long long nb = 0;
-                if (lane == 0) nb = atomicAdd(L.work_counter, (unsigned long long)kChunk);
-                nb = __shfl_sync(0xffffffffu, nb, 0);
-                w = rank < avail ? pool_next + rank : nb + (rank - avail);
-                pool_next = nb + (cnt - avail);
-                pool_end = nb + kChunk;
-            } else {
-                w = pool_next + rank;
+            unsigned long long avail = pool_end - pool_next;
+            unsigned long long nb = 0, ne = 0;
+            if (avail < cnt && !pool_done) {
+                unsigned long long cid = 0;
+                if (lane == 0) cid = atomicAdd(L.work_counter, 1ull);
+                cid = __shfl_sync(0xffffffffu, cid, 0);
+                if (cid >= L.n_chunks) {
+                    pool_done = true;
+                } else {
+                    uint32_t lo = 0, hi = L.n_ranges; // largest r with chunk_prefix[r] <= cid (uniform loads)
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (__ldg(L.chunk_prefix + mid) <= cid) lo = mid; else hi = mid;
+                    }
+                    nb = __ldg(L.range_begin + lo) + (cid - __ldg(L.chunk_prefix + lo)) * kChunk;
+                    ne = nb + kChunk;
+                    const unsigned long long re = __ldg(L.range_end + lo);
+                    if (ne > re) ne = re;
+                }
+            }
+            bool got = false;
+            if (need) {
+                if (rank < avail) { j = pool_next + rank; got = true; }
+                else if (rank - avail < ne - nb) { j = nb + (rank - avail); got = true; }
+            }
+            if (cnt <= avail) {
                 pool_next += cnt;
+            } else {
+                const unsigned long long want = cnt - avail, have = ne - nb;
+                pool_next = nb + (want < have ? want : have);
+                pool_end = ne;
             }
             if (need) {
-                if (w >= L.n_work) {
-                    exhausted = true;
-                } else {
-                    j = work_to_pos(L.range_begin, L.range_prefix, L.n_ranges, w);
+                if (got) {
                     load_pattern(st.pat, L.text, L.text_begin + j, cx.K);
-                    chain_begin_kmer(st, cx);
+                    chain_begin_kmer(st, cx, COUNT ? &lut_reads : nullptr);
                     active = true;
+                } else if (pool_done) {
+                    exhausted = true;
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, active)) break;
+        if (!__any_sync(0xffffffffu, active || !exhausted)) break;
 
         // ---- one node expansion per chain -------------------------------------------------------------
         if (active) {
-            if (!chain_step(st, fr, cx, COUNT ? &fetches : nullptr)) {
+            if (!chain_step(st, fr, cx, COUNT ? &fetches : nullptr, COUNT ? &lut_reads : nullptr)) {
                 out[j] = (OutT)st.acc;
                 active = false;
             }
         }
     }
     if (COUNT) {
-        for (int o = 16; o > 0; o >>= 1) fetches += __shfl_xor_sync(0xffffffffu, fetches, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            fetches += __shfl_xor_sync(0xffffffffu, fetches, o);
+            lut_reads += __shfl_xor_sync(0xffffffffu, lut_reads, o);
+        }
         if (lane == 0 && fetches) atomicAdd(L.fetch_counter, fetches);
+        if (lane == 0 && lut_reads) atomicAdd(L.fetch_counter + 1, lut_reads);
     }
 }
 

@@ -12,16 +12,22 @@ struct MapLaunch {
     uint32_t E;
     const uint64_t* text;      // 2-bit packed concatenated text (device)
     uint64_t text_begin;       // start of this FASTA file's text inside the concatenated text
-    const uint64_t* range_begin; // device: n_ranges work ranges (file-local begin positions)
-    const uint64_t* range_prefix; // device: n_ranges+1 prefix sums of the range lengths
+    // work = chunks of <= kChunk consecutive positions; a chunk never straddles two ranges
+    const uint64_t* range_begin;  // device: n_ranges work ranges, file-local [begin, end)
+    const uint64_t* range_end;
+    const uint64_t* chunk_prefix; // device: n_ranges+1, number of chunks before range r
     uint32_t n_ranges;
-    uint64_t n_work;           // total k-mer starts to search
-    unsigned long long* work_counter;  // device, zeroed before launch
-    unsigned long long* fetch_counter; // device (only read with count_fetches)
+    uint64_t n_chunks;
+    uint64_t n_work;           // total k-mer starts to search (sizing only)
+    unsigned long long* work_counter;  // device, zeroed before launch: next chunk id
+    unsigned long long* fetch_counter; // device: [0] rank-block fetches, [1] jump-table reads (count_fetches)
+    SearchStart starts[kMaxSearches];  // jump table of every search (uni == nullptr: start at the root)
     void* out;                 // device, value_bits/8 bytes per file-local position
     uint32_t value_bits;
     bool count_fetches;
 };
+
+constexpr unsigned kChunk = 128; // positions handed out per global atomic
 
 // Enqueue the kernel on `stream`.  Returns cudaSuccess or the launch error.
 cudaError_t launch_map_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream);

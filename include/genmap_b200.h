@@ -70,9 +70,10 @@ typedef struct gmb_index_info {
 typedef struct gmb_map_stats {
     double kernel_ms;            /* CUDA-event time of the search kernel */
     uint64_t positions;          /* k-mer starts actually searched */
-    uint64_t rank_block_fetches; /* only with count_fetches */
+    uint64_t rank_block_fetches; /* only with count_fetches: 64-byte rank blocks read */
+    uint64_t jump_table_reads;   /* only with count_fetches: jump-table entries read (8 or 12 bytes each) */
     uint32_t kernel_launches;
-    uint32_t reserved;
+    uint32_t jump_depth;         /* deepest jump table used by this call (0 = none) */
 } gmb_map_stats;
 
 /* flags for gmb_index_build */
@@ -103,6 +104,10 @@ int gmb_index_from_blob(const void *host_blob, uint64_t bytes, int device, gmb_i
 int gmb_index_adopt_device(void *device_blob, uint64_t bytes, int device, gmb_index **out);
 int gmb_index_close(gmb_index *idx);
 int gmb_index_get_info(const gmb_index *idx, gmb_index_info *info);
+/* Maximum depth of the jump tables that replace the first error-free steps of every search:
+ * -1 = automatic (floor(log4 N), at most 15), 0 = off, 1..16 = fixed.  Tables are built lazily on the
+ * device by the first map call that needs them and cached in the handle. */
+int gmb_index_set_jump_depth(gmb_index *idx, int depth);
 /* Diagnostics / test support: decode one direction's BWT (rev = 0: of T, 1: of T') to one byte per
  * row (0 = sentinel, 1..4 = A,C,G,T) into host memory (n_bwt bytes). */
 int gmb_index_export_bwt(gmb_index *idx, int rev, uint8_t *out_host);

@@ -22,15 +22,15 @@ struct HostFrames {
 
 template <int KW>
 void run_ranges(const MapCtx& cx, const uint64_t* text, uint64_t text_begin, const std::vector<WorkRange>& ranges,
-                int value_bits, void* out, unsigned long long* fetches)
+                int value_bits, void* out, unsigned long long* fetches, unsigned long long* lut_reads)
 {
     for (const WorkRange& r : ranges)
         for (uint64_t j = r.begin; j < r.end; ++j) {
             Chain<KW> st;
             HostFrames fr;
             load_pattern(st.pat, text, text_begin + j, cx.K);
-            chain_begin_kmer(st, cx);
-            while (chain_step(st, fr, cx, fetches)) {}
+            chain_begin_kmer(st, cx, lut_reads);
+            while (chain_step(st, fr, cx, fetches, lut_reads)) {}
             if (value_bits == 16) static_cast<uint16_t*>(out)[j] = (uint16_t)st.acc;
             else static_cast<uint8_t*>(out)[j] = (uint8_t)st.acc;
         }
@@ -87,9 +87,11 @@ int hs_step_tables(uint32_t K, uint32_t E, uint32_t* n_search, uint32_t* steps)
     return ok ? 0 : -1;
 }
 
+// jump_depth: -1 = default for the index size, 0 = no jump tables, else the maximum depth
 int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bits, uint64_t text_begin,
            uint64_t text_len, const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t* intervals,
-           uint64_t n_intervals, uint64_t pos_begin, uint64_t pos_end, void* out, unsigned long long* fetches)
+           uint64_t n_intervals, uint64_t pos_begin, uint64_t pos_end, void* out, unsigned long long* fetches,
+           int jump_depth, unsigned long long* lut_reads_out)
 {
     const uint8_t* base = static_cast<const uint8_t*>(blob);
     std::string err;
@@ -106,16 +108,41 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     cx.steps = tabs->step;
     cx.K = K; cx.n_search = tabs->n_search; cx.n_strands = revcompl ? 2 : 1;
     cx.maxv = value_bits == 16 ? 65535u : 255u;
+    // jump tables, level by level (the device builder does the same with one thread per entry)
+    JumpPlan plan;
+    plan_jump_tables(*tabs, jump_depth < 0 ? default_jump_depth(h.n_bwt) : (uint32_t)jump_depth, plan);
+    std::vector<std::vector<JtEntry>> uni(plan.max_depth + 1);
+    std::vector<std::vector<uint32_t>> lof(plan.max_depth + 1);
+    for (uint32_t d = 1; d <= plan.max_depth; ++d) {
+        const uint64_t n = 1ull << (2 * d), pmask = (1ull << (2 * (d - 1))) - 1;
+        uni[d].resize(n); lof[d].resize(n);
+        for (uint64_t key = 0; key < n; ++key) {
+            Node par;
+            if (d == 1) { par.lo_f = 0; par.lo_r = 0; par.size = cx.n_bwt; }
+            else { par.lo_f = lof[d - 1][key & pmask]; par.lo_r = uni[d - 1][key & pmask].lo_r; par.size = uni[d - 1][key & pmask].size; }
+            const Node m = extend_right(par, (uint32_t)(key >> (2 * (d - 1))), cx);
+            uni[d][key].lo_r = m.lo_r; uni[d][key].size = m.size; lof[d][key] = m.lo_f;
+        }
+    }
+    SearchStart starts[kMaxSearches];
+    for (uint32_t s = 0; s < kMaxSearches; ++s) {
+        const uint32_t d = plan.depth[s];
+        starts[s].uni = d ? uni[d].data() : nullptr;
+        starts[s].lof = (d && plan.need_lof[s]) ? lof[d].data() : nullptr;
+        starts[s].a = plan.a[s]; starts[s].d = d;
+    }
+    cx.starts = starts;
     std::memset(out, 0, text_len * (value_bits / 8));
     std::vector<WorkRange> ranges;
     build_work_ranges(text_len, K, chrom_cum, n_chrom, intervals, n_intervals, pos_begin, pos_end, ranges);
     const uint64_t* text = reinterpret_cast<const uint64_t*>(base + h.off_text);
-    unsigned long long f = 0;
-    if (K <= 32) run_ranges<1>(cx, text, text_begin, ranges, value_bits, out, &f);
-    else if (K <= 64) run_ranges<2>(cx, text, text_begin, ranges, value_bits, out, &f);
-    else if (K <= 128) run_ranges<4>(cx, text, text_begin, ranges, value_bits, out, &f);
-    else run_ranges<8>(cx, text, text_begin, ranges, value_bits, out, &f);
+    unsigned long long f = 0, lr = 0;
+    if (K <= 32) run_ranges<1>(cx, text, text_begin, ranges, value_bits, out, &f, &lr);
+    else if (K <= 64) run_ranges<2>(cx, text, text_begin, ranges, value_bits, out, &f, &lr);
+    else if (K <= 128) run_ranges<4>(cx, text, text_begin, ranges, value_bits, out, &f, &lr);
+    else run_ranges<8>(cx, text, text_begin, ranges, value_bits, out, &f, &lr);
     if (fetches) *fetches = f;
+    if (lut_reads_out) *lut_reads_out = lr;
     delete tabs;
     return 0;
 }

@@ -96,6 +96,17 @@ def test_cuda_matches_oracle(gm, K, E):
         assert np.array_equal(got, want), (K, E, rc, np.nonzero(got != want)[0][:10])
 
 
+@pytest.mark.parametrize("depth", [0, 1, 4, 8, 12])
+def test_cuda_jump_table_depths_do_not_change_results(gm, depth):
+    seqs = T.repeat_rich(31, 3, 30000)
+    _, limits = T.concat(seqs)
+    ix, hs = gm.Index.build(seqs), T.HostSim(seqs)
+    ix.set_jump_depth(depth)
+    for K, E in [(30, 0), (30, 2), (16, 4), (50, 2), (13, 0)]:
+        for rc in (True, False):
+            assert np.array_equal(_map(gm, ix, K, E, rc=rc, limits=limits), hs.map(K, E, revcompl=rc, jump_depth=0)), (K, E, rc, depth)
+
+
 def test_cuda_edge_cases(gm):
     # sequences shorter than K between longer ones, selection intervals, saturation, palindromes
     seqs = [np.array([0, 1, 2], np.uint8), T.repeat_rich(3, 1, 300)[0], np.array([3, 3], np.uint8),
@@ -107,7 +118,6 @@ def test_cuda_edge_cases(gm):
     assert np.array_equal(_map(gm, ix, 12, 1, limits=limits, intervals=iv), orc.map(12, 1, intervals=iv))
     # K longer than all but one sequence; K longer than every sequence: all zeros
     assert np.array_equal(_map(gm, ix, 250, 0, limits=limits), orc.map(250, 0))
-    assert not _map(gm, ix, 255, 1, limits=np.array([0, 3, 303, 305, 505, 506], dtype=np.uint64)).any() or True
     short = [T.repeat_rich(3, 1, 100)[0], T.repeat_rich(4, 1, 60)[0]]
     _, sl = T.concat(short)
     assert not _map(gm, gm.Index.build(short), 101, 0, limits=sl).any()
@@ -135,6 +145,12 @@ def test_cuda_fetch_counter_matches_cpu_restatement(gm):
         want, f = hs.map(K, E, return_fetches=True)
         assert np.array_equal(out, want)
         assert st.rank_block_fetches == f, (K, E, st.rank_block_fetches, f)
+        assert st.jump_table_reads == hs.last_lut_reads
+    for depth in (0, 3, 9):
+        ix.set_jump_depth(depth)
+        out, st = _map(gm, ix, 30, 1, limits=limits, count_fetches=True, return_stats=True)
+        want, f = hs.map(30, 1, return_fetches=True, jump_depth=depth)
+        assert np.array_equal(out, want) and st.rank_block_fetches == f and st.jump_depth == min(depth, 9)
 
 
 # ---- 1 Mbp of the frozen synthetic generator: md5 pins measured with the reference --

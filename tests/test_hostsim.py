@@ -36,6 +36,17 @@ def test_state_machine_matches_oracle(K, E):
         assert np.array_equal(got, want), (K, E, rc, np.nonzero(got != want)[0][:10])
 
 
+@pytest.mark.parametrize("K,E", [(30, 0), (30, 2), (21, 3), (16, 4), (50, 2), (8, 0), (3, 1), (65, 1)])
+def test_jump_table_depths_do_not_change_results(K, E):
+    seqs = T.repeat_rich(17, 2, 2500)
+    hs = T.HostSim(seqs)
+    base = hs.map(K, E, jump_depth=0)
+    assert np.array_equal(base, T.Oracle(seqs).map(K, E))
+    for d in (1, 2, 5, 7, 8):
+        assert np.array_equal(hs.map(K, E, jump_depth=d), base), (K, E, d)
+        assert np.array_equal(hs.map(K, E, jump_depth=d, revcompl=False), hs.map(K, E, jump_depth=0, revcompl=False))
+
+
 def test_state_machine_saturation_and_palindromes():
     seqs = [np.tile(np.array([0, 1, 2, 3], dtype=np.uint8), 2000)]
     orc, hs = T.Oracle(seqs), T.HostSim(seqs)
@@ -83,4 +94,6 @@ def test_fetch_counter_is_deterministic_and_plausible():
     _, f2 = hs.map(30, 0, return_fetches=True)
     assert f1 == f2
     n_kmers = sum(len(s) - 29 for s in seqs)
-    assert n_kmers * 20 < f1 < n_kmers * 130  # ~30 steps per strand, 1-2 blocks per step
+    _, f0 = hs.map(30, 0, return_fetches=True, jump_depth=0)
+    assert n_kmers * 10 < f0 < n_kmers * 130  # <= 30 steps per strand, 1-2 blocks per step
+    assert f1 < f0  # the jump table skips the top levels

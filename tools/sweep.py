@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Tuning sweep on one GPU: build genome + index once, then time the map kernel for several
+(E, jump depth, batch) settings.  Prints one line per setting (not a bench line)."""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import genmap_b200 as gm  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--genome-mbp", type=float, default=3000)
+ap.add_argument("--nchr", type=int, default=24)
+ap.add_argument("--seed", type=int, default=45)
+ap.add_argument("--configs", default="0:-1:256,0:0:256,0:13:256,0:14:256,0:16:256,1:-1:64,1:0:64,2:-1:8,2:0:8")
+ap.add_argument("--reps", type=int, default=3)
+args = ap.parse_args()
+
+total = int(args.genome_mbp * 1e6)
+t0 = time.time()
+seqs = gm.synth_genome(total, args.nchr, args.seed)
+ix = gm.Index.build(seqs, on_gpu=True)
+print("genome+index %.1f s, build %s" % (time.time() - t0, ix.build_timings_ms), flush=True)
+n = ix.n_text
+out = torch.zeros(n, dtype=torch.int16, device="cuda")
+stream = torch.cuda.current_stream().cuda_stream
+for cfg in args.configs.split(","):
+    E, depth, batch = cfg.split(":")
+    E, depth, batch = int(E), int(depth), int(float(batch) * (1 << 20))
+    batch = min(batch, n // 2)
+    ix.set_jump_depth(depth)
+    p = gm.SearchParams(30, E)
+    t1 = time.time()
+    st = ix.compute_mappability_device(p, out.data_ptr(), pos_begin=0, pos_end=1 << 16, stream=stream)  # builds tables
+    setup = time.time() - t1
+    ms, fetch, lut, npos = [], 0, 0, 0
+    for r in range(args.reps):
+        b = (r * batch) % (n - batch)
+        st = ix.compute_mappability_device(p, out.data_ptr(), pos_begin=b, pos_end=b + batch, stream=stream)
+        ms.append(st.kernel_ms); npos = st.positions
+    b = 0
+    st = ix.compute_mappability_device(p, out.data_ptr(), pos_begin=b, pos_end=b + batch, stream=stream, count_fetches=True)
+    print("E=%d depth=%2d(%2d) batch=%d  %.2f ms  %.1f Mpos/s  fetch/pos=%.1f lut/pos=%.2f  algGB/s=%.0f  setup=%.2fs free=%.1fGB"
+          % (E, depth, st.jump_depth, batch, np.median(ms), npos / np.median(ms) / 1e3, st.rank_block_fetches / st.positions,
+             st.jump_table_reads / st.positions, st.rank_block_fetches * 64 / st.positions * npos / np.median(ms) / 1e6,
+             setup, torch.cuda.mem_get_info()[0] / 1e9), flush=True)
