@@ -193,22 +193,15 @@ def main():
         ix = gm.Index.build(seqs, device=local, on_gpu=True)
         log("index built on GPU in %.1f s %s, blob %.2f GB" % (time.time() - t0, ix.build_timings_ms, ix.info.blob_bytes / 1e9))
     if dist is not None:
-        nbytes = torch.zeros(1, dtype=torch.int64, device=dev)
-        if rank == 0:
-            nbytes[0] = ix.info.blob_bytes
-        dist.broadcast(nbytes, 0)
-        nb = int(nbytes.item())
-        if rank == 0:
-            # the library-owned device blob, viewed as a tensor so NCCL can broadcast it in place
-            blob_t = torch.as_tensor(_DeviceBytes(int(ix.info.device_blob), nb), device=dev)
-        else:
-            blob_t = torch.empty(nb, dtype=torch.uint8, device=dev)
+        from genmap_b200 import parallel
+        # the library-owned device blob, viewed as a tensor so NCCL can broadcast it in place
+        blob_t = torch.as_tensor(_DeviceBytes(int(ix.info.device_blob), int(ix.info.blob_bytes)), device=dev) if rank == 0 else None
         t0 = time.time()
-        dist.broadcast(blob_t, 0)
+        blob_t = parallel.broadcast_blob(blob_t, dist, dev)
         torch.cuda.synchronize()
         log("rank %d: index broadcast over NCCL in %.2f s" % (rank, time.time() - t0))
         if rank != 0:
-            ix = gm.Index.adopt_device(blob_t.data_ptr(), nb, device=local)
+            ix = gm.Index.adopt_device(blob_t.data_ptr(), blob_t.numel(), device=local)
     ix.limits = limits
     ix.set_jump_depth(args.jump_depth)
 
@@ -229,20 +222,12 @@ def main():
         return 0
 
     # ---- one measurement = (E, batch) ---------------------------------------------------------------------
-    shard_b = n_text * rank // world
-    shard_e = n_text * (rank + 1) // world
+    from genmap_b200 import parallel
+    shard_b, shard_e = parallel.shard_range(n_text, rank, world)
     out_dev = torch.zeros(n_text, dtype=torch.int16, device=dev)
 
     def batches(E_, batch, count):
-        span = shard_e - shard_b
-        res, pos = [], 0
-        for _ in range(count):
-            if pos + batch > span:
-                pos = 0
-            b = shard_b + pos
-            res.append((b, min(b + batch, shard_e)))
-            pos += batch
-        return res
+        return parallel.step_batches(shard_b, shard_e, batch, count)
 
     def measure(E_, batch, steps, warmup, with_e2e, sample_clocks):
         p = gm.SearchParams(K, E_)
@@ -269,12 +254,8 @@ def main():
         ms = ev0.elapsed_time(ev1)
         npos = sum(e - b for b, e in bl[warmup:])
         if dist is not None:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            c = torch.tensor([npos], dtype=torch.int64, device=dev)
-            dist.all_reduce(c, op=dist.ReduceOp.SUM)
-            npos_all = int(c.item())
+            ms = parallel.max_over_ranks(ms, dist, dev)
+            npos_all = parallel.sum_over_ranks(npos, dist, dev)
         else:
             npos_all = npos
         res = {"ms": ms, "positions": npos_all, "value": npos_all / (ms * 1e-3), "clocks": clocks, "batches": bl[warmup:]}
@@ -301,12 +282,8 @@ def main():
             dt = time.perf_counter() - t0
             npos2 = sum(e - b for b, e in bl2[1:])
             if dist is not None:
-                t = torch.tensor([dt], dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dt = float(t.item())
-                c = torch.tensor([npos2], dtype=torch.int64, device=dev)
-                dist.all_reduce(c, op=dist.ReduceOp.SUM)
-                npos2 = int(c.item())
+                dt = parallel.max_over_ranks(dt, dist, dev)
+                npos2 = parallel.sum_over_ranks(npos2, dist, dev)
             # per step: work-range table + step table + counters go H2D, the slice of c comes back D2H
             res["e2e"] = {"value": npos2 / dt, "unit": UNIT,
                           "h2d_bytes_per_step": int(3 * 8 + 4 * K * {0: 1, 1: 2, 2: 3, 3: 4, 4: 7}[E_] + 16),

@@ -31,9 +31,30 @@ def is_stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+BIN_DIR = os.path.join(HERE, "bin")
+CLI = os.path.join(BIN_DIR, "genmap")
+CLI_SOURCES = [os.path.join("cli", "genmap_cli.cpp"), os.path.join("cli", "writers.hpp")]
+
+
+def build_cli(force=False, verbose=False):
+    """The `genmap` command line (host C++), linked against the library with an $ORIGIN rpath."""
+    srcs = [os.path.join(CSRC, s) for s in CLI_SOURCES]
+    if not force and os.path.exists(CLI) and all(os.path.getmtime(s) <= os.path.getmtime(CLI) for s in srcs + [LIB]):
+        return CLI
+    os.makedirs(BIN_DIR, exist_ok=True)
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-o", CLI + ".tmp", srcs[0], "-L" + LIB_DIR, "-lgenmap_b200",
+           "-Wl,-rpath,$ORIGIN/../lib"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    os.replace(CLI + ".tmp", CLI)
+    return CLI
+
+
 def build(force=False, verbose=False):
     """Compile every CUDA/C++ source of the product into genmap_b200/lib/libgenmap_b200.so."""
     if not force and not is_stale():
+        build_cli(force, verbose)
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [nvcc()] + NVCC_FLAGS + ["-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
@@ -41,6 +62,7 @@ def build(force=False, verbose=False):
         print(" ".join(cmd))
     subprocess.run(cmd, check=True, env=dict(os.environ, CC="", CXX=""))
     os.replace(LIB + ".tmp", LIB)
+    build_cli(True, verbose)
     return LIB
 
 

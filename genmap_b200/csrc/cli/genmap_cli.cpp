@@ -6,6 +6,7 @@
 #include <sys/stat.h>
 #include <sys/time.h>
 #include <dirent.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>

@@ -1,0 +1,164 @@
+// writers.hpp — output files of `genmap map`: raw (.map/.freq8/.freq16), .txt, .wig + .chrom.sizes,
+// .bedgraph, .bed.  Byte-identical to the reference's writers (src/output.hpp:10-187, dispatch and verbose
+// lines src/mappability.hpp:69-155); structured as one run-length pass feeding small format emitters.
+#pragma once
+#include <sys/time.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <iostream>
+#include <string>
+#include <vector>
+
+namespace gmbcli {
+
+enum class OutputType { mappability, frequency_small, frequency_large };
+
+struct Outputs { bool raw, txt, wig, bedgraph, bed, verbose; };
+
+inline double now_s()
+{
+    struct timeval t;
+    gettimeofday(&t, nullptr);
+    return t.tv_sec + t.tv_usec * 1e-6;
+}
+
+// buffered FILE* writer; numbers formatted like std::ostream's defaults (%g for float: 6 significant digits)
+class Sink {
+public:
+    explicit Sink(const std::string& path) : f_(std::fopen(path.c_str(), "wb")) { if (f_) std::setvbuf(f_, nullptr, _IOFBF, 1 << 20); }
+    ~Sink() { if (f_) std::fclose(f_); }
+    bool ok() const { return f_ != nullptr; }
+    void str(const std::string& s) { std::fwrite(s.data(), 1, s.size(), f_); }
+    void ch(char c) { std::fputc(c, f_); }
+    void u64(uint64_t v)
+    {
+        char buf[24];
+        int n = 0;
+        do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+        while (n) std::fputc(buf[--n], f_);
+    }
+    void flt(float v) { std::fprintf(f_, "%g", (double)v); }
+    void bytes(const void* p, size_t n) { std::fwrite(p, 1, n, f_); }
+    template <class T>
+    void value(T v, bool mappability) // a frequency, or its inverse as float (0 stays 0)
+    {
+        if (mappability) flt(v != 0 ? 1.0f / static_cast<float>(v) : 0.0f);
+        else u64(v);
+    }
+private:
+    FILE* f_;
+};
+
+struct Run { uint64_t start, len; uint32_t value; };
+
+// maximal runs of equal values inside one sequence [begin, end)
+template <class T, class F>
+void for_each_run(const T* c, uint64_t begin, uint64_t end, F&& f)
+{
+    uint64_t i = begin;
+    while (i < end) {
+        uint64_t j = i + 1;
+        while (j < end && c[j] == c[i]) ++j;
+        f(Run{i - begin, j - i, (uint32_t)c[i]});
+        i = j;
+    }
+}
+
+template <class T>
+void write_raw(const T* c, uint64_t n, const std::string& path, bool mappability)
+{
+    Sink o(path);
+    if (!o.ok()) { std::cerr << "ERROR: cannot write " << path << "\n"; return; }
+    if (!mappability) { o.bytes(c, n * sizeof(T)); return; }
+    std::vector<float> buf(1 << 16);
+    for (uint64_t i = 0; i < n;) { // src/output.hpp:17-24
+        size_t m = 0;
+        for (; m < buf.size() && i < n; ++m, ++i) buf[m] = c[i] != 0 ? 1.0f / static_cast<float>(c[i]) : 0.0f;
+        o.bytes(buf.data(), m * sizeof(float));
+    }
+}
+
+template <class T>
+void write_txt(const T* c, const std::string& prefix, const std::vector<std::string>& names,
+               const std::vector<uint64_t>& lens, bool mappability)
+{
+    Sink o(prefix + ".txt");
+    if (!o.ok()) { std::cerr << "ERROR: cannot write " << prefix << ".txt\n"; return; }
+    uint64_t begin = 0;
+    for (size_t s = 0; s < lens.size(); ++s) { // src/output.hpp:40-69: '>' name, values separated by single spaces
+        o.ch('>'); o.str(names[s]); o.ch('\n');
+        for (uint64_t i = 0; i < lens[s]; ++i) {
+            if (i) o.ch(' ');
+            o.value(c[begin + i], mappability);
+        }
+        o.ch('\n');
+        begin += lens[s];
+    }
+}
+
+template <class T>
+void write_wig(const T* c, const std::string& prefix, const std::vector<std::string>& names,
+               const std::vector<uint64_t>& lens, bool mappability)
+{
+    {
+        Sink o(prefix + ".wig");
+        if (!o.ok()) { std::cerr << "ERROR: cannot write " << prefix << ".wig\n"; return; }
+        uint64_t begin = 0;
+        for (size_t s = 0; s < lens.size(); ++s) {
+            uint64_t last_span = 0; // a new variableStep header whenever the run length changes (:96-99); reset per sequence
+            for_each_run(c, begin, begin + lens[s], [&](const Run& r) {
+                if (r.value == 0) return; // zero runs are skipped (:96)
+                if (last_span != r.len) {
+                    o.str("variableStep chrom="); o.str(names[s]); o.str(" span="); o.u64(r.len); o.ch('\n');
+                }
+                o.u64(r.start + 1); o.ch(' '); o.value(r.value, mappability); o.ch('\n'); // positions start at 1
+                last_span = r.len;
+            });
+            begin += lens[s];
+        }
+    }
+    Sink cs(prefix + ".chrom.sizes");
+    if (!cs.ok()) return;
+    for (size_t s = 0; s < lens.size(); ++s) { cs.str(names[s]); cs.ch('\t'); cs.u64(lens[s]); cs.ch('\n'); }
+}
+
+template <class T>
+void write_bedgraph(const T* c, const std::string& prefix, const std::vector<std::string>& names,
+                    const std::vector<uint64_t>& lens, bool bedgraph_format, bool mappability)
+{
+    Sink o(prefix + (bedgraph_format ? ".bedgraph" : ".bed"));
+    if (!o.ok()) { std::cerr << "ERROR: cannot write " << prefix << (bedgraph_format ? ".bedgraph" : ".bed") << "\n"; return; }
+    uint64_t begin = 0;
+    for (size_t s = 0; s < lens.size(); ++s) {
+        for_each_run(c, begin, begin + lens[s], [&](const Run& r) {
+            if (r.value == 0) return; // src/output.hpp:157
+            o.str(names[s]); o.ch('\t'); o.u64(r.start); o.ch('\t'); o.u64(r.start + r.len); o.ch('\t');
+            if (!bedgraph_format) { o.ch('-'); o.ch('\t'); }
+            o.value(r.value, mappability); o.ch('\n');
+        });
+        begin += lens[s];
+    }
+}
+
+template <class T>
+void write_outputs(const T* c, uint64_t n, const std::string& prefix, const std::vector<std::string>& names,
+                   const std::vector<uint64_t>& lens, OutputType type, const Outputs& o)
+{
+    const bool mapp = type == OutputType::mappability;
+    auto timed = [&](const char* what, auto&& fn) {
+        const double t0 = now_s();
+        fn();
+        if (o.verbose) std::cout << "- " << what << " written in " << (std::round((now_s() - t0) * 100.0) / 100.0) << " seconds\n";
+    };
+    if (o.raw) timed("RAW file", [&] {
+        write_raw(c, n, prefix + (mapp ? ".map" : type == OutputType::frequency_small ? ".freq8" : ".freq16"), mapp);
+    });
+    if (o.txt) timed("TXT file", [&] { write_txt(c, prefix, names, lens, mapp); });
+    if (o.wig) timed("WIG file", [&] { write_wig(c, prefix, names, lens, mapp); });
+    if (o.bedgraph) timed("bedgraph file", [&] { write_bedgraph(c, prefix, names, lens, true, mapp); });
+    if (o.bed) timed("BED file", [&] { write_bedgraph(c, prefix, names, lens, false, mapp); });
+}
+
+} // namespace gmbcli

@@ -1,0 +1,133 @@
+"""CPU checks of the `genmap` command line: the writers reproduce every golden output flavour of the
+reference's test cases byte for byte (rendered from the golden raw vectors, so no GPU is needed),
+`genmap index` works with the host builder, user errors give exit code 1 with the reference's messages."""
+import filecmp
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import gmtest as T
+from genmap_b200 import _build
+
+FLAVOURS = {"raw_map": ["-r"], "raw_freq8": ["-r", "-fs"], "raw_freq16": ["-r", "-fl"], "txt_map": ["-t"],
+            "txt_freq16": ["-t", "-fl"], "txt_freq8": ["-t", "-fs"], "wig_map": ["-w"], "wig_freq16": ["-w", "-fl"],
+            "bed_map": ["-bg"], "bed_freq16": ["-bg", "-fl"]}
+
+
+@pytest.fixture(scope="module")
+def genmap():
+    _build.build()
+    return _build.build_cli()
+
+
+def run(genmap, *args):
+    return subprocess.run([genmap] + [str(a) for a in args], capture_output=True, text=True)
+
+
+def make_index(genmap, case, tmp, host=True):
+    files, sel, folder = T.load_case(case)
+    idx = os.path.join(tmp, "index")
+    if T.CASES[case]["dir"]:
+        r = run(genmap, "index", "-FD", folder, "-I", idx, *(["-xh"] if host else []))
+    else:
+        r = run(genmap, "index", "-F", os.path.join(folder, "genome.fa"), "-I", idx, *(["-xh"] if host else []))
+    return r, idx, files, sel, folder
+
+
+DNA4 = [c for c in sorted(T.CASES) if c not in ("1c", "1d", "1e", "1f", "1g")]
+
+
+@pytest.mark.parametrize("case", DNA4)
+def test_index_and_writers_reproduce_golden_outputs(genmap, case, tmp_path):
+    r, idx, files, sel, folder = make_index(genmap, case, str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    assert "Index created successfully." in r.stdout
+    ids = open(os.path.join(idx, "index.ids")).read().split("\n")[:-1]
+    want = ["%s.fa;%d;%s" % (base, len(c), name) for base, recs in files for name, c in recs]
+    assert ids == want
+    n_checked = 0
+    for flav, flags in FLAVOURS.items():
+        gold_dir = os.path.join(folder, flav)
+        if not os.path.isdir(gold_dir):
+            continue
+        out = tmp_path / flav
+        out.mkdir()
+        for fi, (base, recs) in enumerate(files):
+            # render from the golden raw vector of the same value type (freq16 for the float outputs)
+            src = os.path.join(folder, "raw_freq8" if "-fs" in flags else "raw_freq16",
+                               base + ".genmap." + ("freq8" if "-fs" in flags else "freq16"))
+            if not os.path.exists(src):
+                continue
+            rr = run(genmap, "render", "-I", os.path.join(idx, "index.ids"), "-C", src, "-N", fi,
+                     "-O", str(out / (base + ".genmap")), *flags)
+            assert rr.returncode == 0, rr.stderr
+        cmp = filecmp.dircmp(gold_dir, str(out))
+        assert not cmp.left_only and not cmp.right_only and not cmp.funny_files, (flav, cmp.left_only, cmp.right_only)
+        match, mismatch, errors = filecmp.cmpfiles(gold_dir, str(out), cmp.common_files, shallow=False)
+        assert not mismatch and not errors, (case, flav, mismatch)
+        n_checked += len(match)
+    assert n_checked > 0
+
+
+@pytest.mark.parametrize("case", ["1c", "1d", "1e", "1f", "1g"])
+def test_writers_on_dna5_golden_vectors(genmap, case, tmp_path):
+    # Dna5 genomes cannot be indexed yet, but the writers are alphabet-agnostic: render from the golden raw files
+    files, sel, folder = T.load_case(case)
+    ids = tmp_path / "index.ids"
+    ids.write_text("".join("%s.fa;%d;%s\n" % (base, len(c), name) for base, recs in files for name, c in recs))
+    for flav, flags in FLAVOURS.items():
+        gold_dir = os.path.join(folder, flav)
+        if not os.path.isdir(gold_dir):
+            continue
+        out = tmp_path / flav
+        out.mkdir()
+        src = os.path.join(folder, "raw_freq8" if "-fs" in flags else "raw_freq16", "genome.genmap." + ("freq8" if "-fs" in flags else "freq16"))
+        assert run(genmap, "render", "-I", ids, "-C", src, "-N", 0, "-O", str(out / "genome.genmap"), *flags).returncode == 0
+        match, mismatch, errors = filecmp.cmpfiles(gold_dir, str(out), os.listdir(gold_dir), shallow=False)
+        assert not mismatch and not errors, (case, flav, mismatch, errors)
+
+
+def test_index_rejects_dna5_and_existing_directory(genmap, tmp_path):
+    r, idx, *_ = make_index(genmap, "1c", str(tmp_path))
+    assert r.returncode == 1 and "N" in r.stderr and not os.path.exists(idx)
+    r, idx, *_ = make_index(genmap, "1a", str(tmp_path))
+    assert r.returncode == 0
+    r, idx, *_ = make_index(genmap, "1a", str(tmp_path))
+    assert r.returncode == 1 and "already exists" in r.stderr
+
+
+def test_cli_user_errors_exit_1(genmap, tmp_path):
+    r, idx, *_ = make_index(genmap, "2a", str(tmp_path))
+    out = tmp_path / "out"
+    out.mkdir()
+    cases = [
+        (["map", "-I", idx, "-O", out, "-r"], "Missing value for option: -K, --length"),
+        (["map", "-I", idx, "-O", out, "-K", 30, "-E", 5, "-r"], "E > 4 not yet supported."),
+        (["map", "-I", idx, "-O", out, "-K", 30], "Please choose at least one output format"),
+        (["map", "-I", idx, "-O", out, "-K", 30, "-r", "-fs", "-fl"], "Cannot use both --frequency-small and --frequency-large"),
+        (["map", "-I", idx, "-O", tmp_path / "nodir" / "x", "-K", 30, "-r"], "does not exist"),
+        (["map", "-I", tmp_path / "noindex", "-O", out, "-K", 30, "-r"], "index"),
+        (["map", "-I", idx, "-O", out, "-K", 3, "-E", 2, "-r"], "K must be at least E + 2"),
+        (["map", "-I", idx, "-O", out, "-K", 30, "-E", 1, "-xo", 29, "-r"], "overlap cannot be larger"),
+        (["index", "-I", tmp_path / "i2"], "You forgot to specify --fasta-file or --fasta-directory"),
+        (["frobnicate"], "not in the list of allowed values"),
+    ]
+    for args, msg in cases:
+        r = run(genmap, *args)
+        assert r.returncode == 1, (args, r.stdout, r.stderr)
+        assert msg in r.stderr + r.stdout, (args, r.stderr)
+    assert run(genmap, "--help").returncode == 0 and run(genmap, "--version").returncode == 0
+    assert run(genmap, "map", "--help").returncode == 0
+
+
+def test_map_needs_a_gpu(genmap, tmp_path):
+    from genmap_b200 import _lib
+    if _lib.lib().gmb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    r, idx, *_ = make_index(genmap, "2a", str(tmp_path))
+    out = tmp_path / "out"
+    out.mkdir()
+    r = run(genmap, "map", "-I", idx, "-O", out, "-K", 4, "-r", "-fl")
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
