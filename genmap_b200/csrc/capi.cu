@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <algorithm>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -71,6 +73,7 @@ struct gmb_index {
     size_t ranges_cap = 0;
     void* d_out = nullptr;
     size_t out_cap = 0;
+    uint32_t* d_seq_to_file = nullptr; // --exclude-pseudo: device copy of the caller's mapping
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // jump tables by depth (index 0 unused), built lazily; levels <= kJumpKeep stay cached
     int jump_depth_opt = -1;
@@ -93,6 +96,10 @@ void fill_ctx(const gmb_index* ix, MapCtx& cx)
     cx.steps = nullptr;
     cx.starts = nullptr;
     cx.K = 0; cx.n_search = 0; cx.n_strands = 1; cx.maxv = 65535u;
+    cx.sa = ix->h.off_sa ? reinterpret_cast<const uint32_t*>(base + ix->h.off_sa) : nullptr;
+    cx.seq_start = reinterpret_cast<const uint32_t*>(base + ix->h.off_seq_start);
+    cx.seq_to_file = nullptr;
+    cx.n_seq = ix->h.n_seq; cx.own_file = 0; cx.all_files = 0;
 }
 
 // make sure the tables of every depth in `plan` exist on the device
@@ -286,6 +293,7 @@ int gmb_index_close(gmb_index* ix)
     if (ix->d_steps) cudaFree(ix->d_steps);
     if (ix->d_ranges) cudaFree(ix->d_ranges);
     if (ix->d_out) cudaFree(ix->d_out);
+    if (ix->d_seq_to_file) cudaFree(ix->d_seq_to_file);
     for (int d = 0; d < 17; ++d) { if (ix->jt_uni[d]) cudaFree(ix->jt_uni[d]); if (ix->jt_lof[d]) cudaFree(ix->jt_lof[d]); }
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);
@@ -321,17 +329,27 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
                                uint64_t pos_begin, uint64_t pos_end, void* out_device, void* cuda_stream,
                                gmb_map_stats* stats)
 {
-    (void)seq_to_file; (void)n_seq;
     if (!ix || !p || !chrom_cum || !out_device) return fail(GMB_ERR_ARG, "gmb_map_frequencies: NULL argument");
     if (p->value_bits != 8 && p->value_bits != 16) return fail(GMB_ERR_ARG, "value_bits must be 8 or 16");
     if (text_begin + text_len > ix->h.n_text) return fail(GMB_ERR_ARG, "text range exceeds the indexed text");
     if (n_chrom == 0 || chrom_cum[0] != 0 || chrom_cum[n_chrom] != text_len) return fail(GMB_ERR_ARG, "chrom_cum_lengths must start at 0 and end at text_len");
-    if (p->exclude_pseudo) return fail(GMB_ERR_UNSUPPORTED, "--exclude-pseudo is not implemented on the GPU path yet");
+    uint32_t n_files = 0, own_file = 0;
+    if (p->exclude_pseudo) {
+        if (!ix->h.off_sa) return fail(GMB_ERR_UNSUPPORTED, "--exclude-pseudo needs an index built with the full suffix array (genmap index -xs / GMB_BUILD_WITH_SA)");
+        if (!seq_to_file || n_seq != ix->h.n_seq) return fail(GMB_ERR_ARG, "--exclude-pseudo needs seq_to_file for every indexed sequence");
+        for (uint32_t s = 0; s < n_seq; ++s) n_files = std::max(n_files, seq_to_file[s] + 1);
+        if (n_files > 64) return fail(GMB_ERR_UNSUPPORTED, "--exclude-pseudo supports at most 64 FASTA files on the GPU path");
+        if (p->count_fetches) return fail(GMB_ERR_UNSUPPORTED, "count_fetches is not available with --exclude-pseudo");
+        uint32_t s0 = 0; // the sequence containing text_begin tells which file is being mapped
+        while (s0 + 1 < n_seq && ix->limits[s0 + 1] <= text_begin) ++s0;
+        own_file = seq_to_file[s0];
+    }
     if (n_intervals && !intervals) return fail(GMB_ERR_ARG, "intervals is NULL");
     std::string err;
-    StepTables* tabs = new (std::nothrow) StepTables;
+    std::unique_ptr<StepTables> tabs_owner(new (std::nothrow) StepTables);
+    StepTables* tabs = tabs_owner.get();
     if (!tabs) return fail(GMB_ERR_NOMEM, "out of host memory");
-    if (!build_step_tables(p->K, p->E, *tabs, err)) { delete tabs; return fail(GMB_ERR_UNSUPPORTED, err); }
+    if (!build_step_tables(p->K, p->E, *tabs, err, p->exclude_pseudo != 0)) return fail(GMB_ERR_UNSUPPORTED, err);
     CU(cudaSetDevice(ix->device));
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
 
@@ -350,7 +368,7 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
     }
     host_ranges[3 * (size_t)nr] = chunks;
     if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->positions = total; }
-    if (total == 0) { delete tabs; return GMB_OK; }
+    if (total == 0) return GMB_OK;
 
     if (ix->ranges_cap < host_ranges.size()) {
         if (ix->d_ranges) cudaFree(ix->d_ranges);
@@ -375,7 +393,7 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
         if (maxd > 16) maxd = 16;
         plan_jump_tables(*tabs, maxd, plan);
         int rcj = ensure_jump_tables(ix, plan, stream);
-        if (rcj != GMB_OK) { delete tabs; return rcj; }
+        if (rcj != GMB_OK) return rcj;
         for (uint32_t s2 = 0; s2 < kMaxSearches; ++s2) {
             const uint32_t d = plan.depth[s2];
             L.starts[s2].uni = d ? ix->jt_uni[d] : nullptr;
@@ -403,7 +421,14 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
     L.out = out_device;
     L.value_bits = p->value_bits;
     L.count_fetches = p->count_fetches != 0;
-    delete tabs;
+    L.exclude_pseudo = p->exclude_pseudo != 0;
+    if (L.exclude_pseudo) {
+        if (!ix->d_seq_to_file) CU(cudaMalloc(&ix->d_seq_to_file, (size_t)ix->h.n_seq * 4));
+        CU(cudaMemcpyAsync(ix->d_seq_to_file, seq_to_file, (size_t)n_seq * 4, cudaMemcpyHostToDevice, stream));
+        L.cx.seq_to_file = ix->d_seq_to_file;
+        L.cx.own_file = own_file;
+        L.cx.all_files = n_files == 64 ? ~0ull : ((1ull << n_files) - 1ull);
+    }
 
     if (stats) CU(cudaEventRecord(ix->ev0, stream));
     CU(launch_map_kernel(L, ix->sm_count, stream));

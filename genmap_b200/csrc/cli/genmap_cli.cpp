@@ -184,8 +184,9 @@ const char* kIndexHelp =
     "  -I,  --index            Path to the index (directory must not exist yet).\n"
     "  -A,  --algorithm        accepted for compatibility (divsufsort|skew); the suffix array is built on the\n"
     "                          GPU (prefix doubling) or, with --host-build / without a GPU, by host SA-IS.\n"
-    "  -S,  --sampling         accepted for compatibility; the index keeps the full suffix array when -xs is set.\n"
-    "  -xs, --with-sa          store the full suffix array (needed by --exclude-pseudo and --csv).\n"
+    "  -S,  --sampling         accepted for compatibility: the index stores the FULL suffix array (4 bytes per\n"
+    "                          base; used by --exclude-pseudo), unless --no-sa is given.\n"
+    "  -xn, --no-sa            do not store the suffix array (smaller index; --exclude-pseudo unavailable).\n"
     "  -v,  --verbose\n";
 
 int index_main(int argc, char const** argv)
@@ -193,7 +194,7 @@ int index_main(int argc, char const** argv)
     std::vector<OptSpec> specs = {{"F", "fasta-file", true}, {"FD", "fasta-directory", true}, {"I", "index", true},
                                   {"A", "algorithm", true}, {"S", "sampling", true}, {"v", "verbose", false},
                                   {"xa", "seqno", true}, {"xb", "seqpos", true}, {"xc", "bwtlen", true},
-                                  {"xs", "with-sa", false}, {"xh", "host-build", false}};
+                                  {"xn", "no-sa", false}, {"xh", "host-build", false}};
     Args a;
     int rc = parse_args("GenMap index", specs, argc, argv, a, kIndexHelp);
     if (rc == 2) return 0;
@@ -251,7 +252,7 @@ int index_main(int argc, char const** argv)
     if (ids_lines.empty()) { rmdir(index_dir.c_str()); std::cerr << "ERROR: There is no non-empty sequence in the fasta file(s).\n"; return 1; }
 
     const uint32_t n_seq = (uint32_t)(limits.size() - 1);
-    uint32_t flags = a.has("with-sa") ? GMB_BUILD_WITH_SA : 0u;
+    uint32_t flags = a.has("no-sa") ? 0u : GMB_BUILD_WITH_SA;
     const bool gpu = !a.has("host-build") && gmb_device_count() > 0;
     if (gpu) flags |= GMB_BUILD_ON_GPU;
     if (a.has("verbose")) std::cout << "Building the bidirectional FM index of " << codes.size() << " bases in " << n_seq
@@ -273,7 +274,7 @@ int index_main(int argc, char const** argv)
         for (const std::string& l : ids_lines) ids << l << '\n';
         std::ofstream info(base + "index.info"); // same keys as src/indexing.hpp:105-111 where they apply
         info << "alphabet_size:4\n" << "fasta_directory:" << (fd ? "true" : "false") << "\n"
-             << "full_suffix_array:" << (a.has("with-sa") ? "true" : "false") << "\n" << "format:genmap-b200-2\n";
+             << "full_suffix_array:" << (a.has("no-sa") ? "false" : "true") << "\n" << "format:genmap-b200-2\n";
     }
     if (a.has("verbose")) std::cout << "done in " << round2(wall() - t0) << " seconds\n";
     std::cout << "Index created successfully.\n";

@@ -223,6 +223,12 @@ struct MapCtx {
     const uint32_t* steps;    // n_search * K packed steps (gmb_layout.h)
     const SearchStart* starts; // n_search entries
     uint32_t K, n_search, n_strands, maxv;
+    // --exclude-pseudo only (src/algo.hpp:351-361): locate every hit and count distinct FASTA files
+    const uint32_t* sa;          // full suffix array of T
+    const uint32_t* seq_start;   // n_seq + 1 sequence starts inside T
+    const uint32_t* seq_to_file; // n_seq file ids (mappingSeqIdFile, src/mappability.hpp:230-250)
+    uint32_t n_seq, own_file;
+    uint64_t all_files;          // mask with one bit per FASTA file
 };
 
 struct Node { uint32_t lo_f, lo_r, size; };
@@ -253,7 +259,24 @@ struct Chain {
     uint32_t acc;              // occurrences so far (saturating)
     uint32_t t, e, s, strand;  // step, errors, search, strand of the current walk
     uint32_t lvmask;           // error levels holding a frame with pending children
+    uint64_t files;            // --exclude-pseudo: FASTA files seen so far (one bit each)
 };
+
+// --exclude-pseudo: mark the FASTA file of every occurrence in SA rows [lo, lo+n)
+// (getOccurrences -> CompressedSA::value, index_fm_compressed_sa.h:478-513, on the full SA kept in HBM;
+// file of a sequence: src/algo.hpp:354-358).  Stops as soon as every file has been seen.
+GMB_HD void ep_mark_rows(uint64_t& mask, uint32_t lo, uint32_t n, const MapCtx& cx)
+{
+    for (uint32_t r = 0; r < n && mask != cx.all_files; ++r) {
+        const uint32_t pos = cx.sa[lo + r];
+        uint32_t a = 0, b = cx.n_seq; // largest s with seq_start[s] <= pos
+        while (b - a > 1) {
+            const uint32_t mid = (a + b) >> 1;
+            if (cx.seq_start[mid] <= pos) a = mid; else b = mid;
+        }
+        mask |= 1ull << cx.seq_to_file[a];
+    }
+}
 
 // frame words: 0..3 child lo in the active index, 4..7 child sizes, 8 = lo of child 0 in the other
 // index, 9 = t | pending << 8
@@ -284,7 +307,7 @@ GMB_HD void chain_start(Chain<KW>& st, const MapCtx& cx, unsigned long long* lut
 template <int KW>
 GMB_HD void chain_begin_kmer(Chain<KW>& st, const MapCtx& cx, unsigned long long* lut_reads)
 {
-    st.acc = 0; st.s = 0; st.strand = 0;
+    st.acc = 0; st.s = 0; st.strand = 0; st.files = 0;
     chain_start(st, cx, lut_reads);
 }
 
@@ -313,7 +336,7 @@ GMB_HD uint32_t highest_bit_index(uint32_t m)
 
 // One state-machine iteration.  Returns false when the k-mer is finished (st.acc is final).
 // `fetches` counts rank-block reads (the roofline's algorithmic unit), when non-null.
-template <int KW, class Frames>
+template <int KW, bool EP, class Frames>
 GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned long long* fetches,
                        unsigned long long* lut_reads)
 {
@@ -332,7 +355,8 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
         // Forward strand, no error so far, one occurrence left: it is the query's own position in the
         // indexed text, so the rest of the pattern matches it exactly and no mismatching extension
         // exists.  The subtree contributes exactly one occurrence — no need to walk it.
-        st.acc = st.acc + 1u < cx.maxv ? st.acc + 1u : cx.maxv;
+        if (EP) st.files |= 1ull << cx.own_file;
+        else st.acc = st.acc + 1u < cx.maxv ? st.acc + 1u : cx.maxv;
     } else {
         // ---- expand the node: ranks at both interval ends of the active index -----------------------
         const uint32_t x = dir ? st.lo_r : st.lo_f;
@@ -377,9 +401,19 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
 
         if (st.t + 1 == K) {
             // children are full-length matches: count them (src/algo.hpp:48,191)
-            const uint64_t sum = (uint64_t)st.acc + ((ok & 1u) ? n0 : 0u) + ((ok & 2u) ? n1 : 0u) +
-                                 ((ok & 4u) ? n2 : 0u) + ((ok & 8u) ? n3 : 0u);
-            st.acc = sum < cx.maxv ? (uint32_t)sum : cx.maxv;
+            if (EP) {
+                // rows in SA(T): the active index's children when extending left, else the synchronised side
+                const uint32_t f0 = dir ? oth0 : l0, f1 = dir ? oth0 + n0 : l1, f2 = dir ? oth0 + n0 + n1 : l2,
+                               f3 = dir ? oth0 + n0 + n1 + n2 : l3;
+                if (ok & 1u) ep_mark_rows(st.files, f0, n0, cx);
+                if (ok & 2u) ep_mark_rows(st.files, f1, n1, cx);
+                if (ok & 4u) ep_mark_rows(st.files, f2, n2, cx);
+                if (ok & 8u) ep_mark_rows(st.files, f3, n3, cx);
+            } else {
+                const uint64_t sum = (uint64_t)st.acc + ((ok & 1u) ? n0 : 0u) + ((ok & 2u) ? n1 : 0u) +
+                                     ((ok & 4u) ? n2 : 0u) + ((ok & 8u) ? n3 : 0u);
+                st.acc = sum < cx.maxv ? (uint32_t)sum : cx.maxv;
+            }
         } else if (ok) {
             const uint32_t mm = ok & ~(1u << p);
             c = mm ? lowest_bit_index(mm) : p; // mismatching children first, the matching child last
@@ -407,7 +441,16 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
             // this search is exhausted: next search, next strand, or done
             if (++st.s == cx.n_search) {
                 st.s = 0;
-                if (++st.strand == cx.n_strands) return false;
+                if (++st.strand == cx.n_strands) {
+                    if (EP) { // distinct FASTA files with at least one occurrence on either strand (:360)
+#if defined(__CUDA_ARCH__)
+                        st.acc = (uint32_t)__popcll(st.files);
+#else
+                        st.acc = (uint32_t)__builtin_popcountll(st.files);
+#endif
+                    }
+                    return false;
+                }
                 st.pat.reverse_complement(K);
             }
             chain_start(st, cx, lut_reads);

@@ -35,7 +35,7 @@ const SchemeDef kSchemes[5] = {
 };
 } // namespace
 
-bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err)
+bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err, bool force_sync)
 {
     if (E > kMaxE) { err = "E > 4 not yet supported."; return false; } // src/mappability.hpp:187
     if (K < E + 2) { err = "K must be at least E + 2."; return false; } // undefined in the reference (rc 139)
@@ -69,7 +69,7 @@ bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err
         for (uint32_t a = 0; a < K; ++a) { // does a later step go the other way?
             bool sw = false;
             for (uint32_t b2 = a + 1; b2 < K; ++b2) sw |= step_dir(st[b2]) != step_dir(st[a]);
-            if (sw) st[a] |= 1u << 25;
+            if (sw || force_sync) st[a] |= 1u << 25;
             bool zero_lb = true; // may the rest of the pattern be matched without any further error?
             for (uint32_t b2 = a; b2 < K; ++b2) zero_lb &= step_lb(st[b2]) == 0;
             if (zero_lb) st[a] |= 1u << 26;

@@ -12,7 +12,9 @@ namespace gmb {
 // Flatten the optimum search scheme for E errors over a pattern of K characters into step tables
 // (scheme tables: src/find2_index_approx.hpp:67-134; block lengths :164-176; start/direction :149-162).
 // Returns false with `err` set if (K,E) is unsupported.
-bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err);
+// force_sync: keep both intervals of the bidirectional index in step at every step (--exclude-pseudo
+// needs the interval in SA(T) at every full-length match).
+bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err, bool force_sync = false);
 
 // Which jump table each search of a (K,E) configuration can use: depth[s] = min(length of the search's
 // initial error-free rightwards run, max_depth, K-1); 0 = none.  need_lof[s]: a later step extends to the

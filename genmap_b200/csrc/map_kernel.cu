@@ -29,7 +29,7 @@ struct SmemFrames {
     __device__ __forceinline__ uint32_t get(uint32_t lv, uint32_t i) const { return base[(lv * kFrameWords + i) * kThreads]; }
 };
 
-template <int KW, bool COUNT, typename OutT>
+template <int KW, bool COUNT, typename OutT, bool EP>
 __global__ void __launch_bounds__(kThreads) map_kernel(const MapLaunch L)
 {
     extern __shared__ uint32_t smem[];
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const MapLaunch L)
 
         // ---- one node expansion per chain -------------------------------------------------------------
         if (active) {
-            if (!chain_step(st, fr, cx, COUNT ? &fetches : nullptr, COUNT ? &lut_reads : nullptr)) {
+            if (!chain_step<KW, EP>(st, fr, cx, COUNT ? &fetches : nullptr, COUNT ? &lut_reads : nullptr)) {
                 out[j] = (OutT)st.acc;
                 active = false;
             }
@@ -127,10 +127,10 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const MapLaunch L)
     }
 }
 
-template <int KW, bool COUNT, typename OutT>
+template <int KW, bool COUNT, typename OutT, bool EP>
 cudaError_t launch_t(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
-    auto kern = map_kernel<KW, COUNT, OutT>;
+    auto kern = map_kernel<KW, COUNT, OutT, EP>;
     const uint32_t n_steps = L.cx.n_search * L.cx.K;
     const size_t smem = ((size_t)((n_steps + 31u) & ~31u) + (size_t)L.E * kFrameWords * kThreads) * sizeof(uint32_t);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -150,9 +150,14 @@ cudaError_t launch_t(const MapLaunch& L, int sm_count, cudaStream_t stream)
 template <int KW>
 cudaError_t launch_kw(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
+    if (L.exclude_pseudo) // (the fetch-counting instantiation is not built for --exclude-pseudo)
+        return L.value_bits == 16 ? launch_t<KW, false, uint16_t, true>(L, sm_count, stream)
+                                  : launch_t<KW, false, uint8_t, true>(L, sm_count, stream);
     if (L.value_bits == 16)
-        return L.count_fetches ? launch_t<KW, true, uint16_t>(L, sm_count, stream) : launch_t<KW, false, uint16_t>(L, sm_count, stream);
-    return L.count_fetches ? launch_t<KW, true, uint8_t>(L, sm_count, stream) : launch_t<KW, false, uint8_t>(L, sm_count, stream);
+        return L.count_fetches ? launch_t<KW, true, uint16_t, false>(L, sm_count, stream)
+                               : launch_t<KW, false, uint16_t, false>(L, sm_count, stream);
+    return L.count_fetches ? launch_t<KW, true, uint8_t, false>(L, sm_count, stream)
+                           : launch_t<KW, false, uint8_t, false>(L, sm_count, stream);
 }
 
 } // namespace

@@ -25,6 +25,7 @@ struct MapLaunch {
     void* out;                 // device, value_bits/8 bytes per file-local position
     uint32_t value_bits;
     bool count_fetches;
+    bool exclude_pseudo;       // cx.sa / seq_start / seq_to_file / all_files are set
 };
 
 constexpr unsigned kChunk = 128; // positions handed out per global atomic

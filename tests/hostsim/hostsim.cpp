@@ -7,6 +7,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "../../genmap_b200/csrc/gmb_core.h"
 #include "../../genmap_b200/csrc/gmb_host.h"
@@ -20,7 +21,7 @@ struct HostFrames {
     inline uint32_t get(uint32_t lv, uint32_t i) const { return w[lv][i]; }
 };
 
-template <int KW>
+template <int KW, bool EP>
 void run_ranges(const MapCtx& cx, const uint64_t* text, uint64_t text_begin, const std::vector<WorkRange>& ranges,
                 int value_bits, void* out, unsigned long long* fetches, unsigned long long* lut_reads)
 {
@@ -30,7 +31,7 @@ void run_ranges(const MapCtx& cx, const uint64_t* text, uint64_t text_begin, con
             HostFrames fr;
             load_pattern(st.pat, text, text_begin + j, cx.K);
             chain_begin_kmer(st, cx, lut_reads);
-            while (chain_step(st, fr, cx, fetches, lut_reads)) {}
+            while (chain_step<KW, EP>(st, fr, cx, fetches, lut_reads)) {}
             if (value_bits == 16) static_cast<uint16_t*>(out)[j] = (uint16_t)st.acc;
             else static_cast<uint8_t*>(out)[j] = (uint8_t)st.acc;
         }
@@ -91,13 +92,14 @@ int hs_step_tables(uint32_t K, uint32_t E, uint32_t* n_search, uint32_t* steps)
 int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bits, uint64_t text_begin,
            uint64_t text_len, const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t* intervals,
            uint64_t n_intervals, uint64_t pos_begin, uint64_t pos_end, void* out, unsigned long long* fetches,
-           int jump_depth, unsigned long long* lut_reads_out)
+           int jump_depth, unsigned long long* lut_reads_out, const uint32_t* seq_to_file, uint32_t own_file)
 {
+    const bool ep = seq_to_file != nullptr;
     const uint8_t* base = static_cast<const uint8_t*>(blob);
     std::string err;
     const IndexHeader& h = *reinterpret_cast<const IndexHeader*>(base);
     StepTables* tabs = new StepTables;
-    if (!build_step_tables(K, E, *tabs, err)) { delete tabs; return -2; }
+    if (!build_step_tables(K, E, *tabs, err, ep)) { delete tabs; return -2; }
     MapCtx cx;
     cx.blk[0] = reinterpret_cast<const RankBlock*>(base + h.off_fwd);
     cx.blk[1] = reinterpret_cast<const RankBlock*>(base + h.off_rev);
@@ -108,6 +110,17 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     cx.steps = tabs->step;
     cx.K = K; cx.n_search = tabs->n_search; cx.n_strands = revcompl ? 2 : 1;
     cx.maxv = value_bits == 16 ? 65535u : 255u;
+    cx.sa = nullptr; cx.seq_start = nullptr; cx.seq_to_file = nullptr; cx.n_seq = h.n_seq; cx.own_file = own_file; cx.all_files = 0;
+    if (ep) {
+        if (!h.off_sa) { delete tabs; return -3; }
+        cx.sa = reinterpret_cast<const uint32_t*>(base + h.off_sa);
+        cx.seq_start = reinterpret_cast<const uint32_t*>(base + h.off_seq_start);
+        cx.seq_to_file = seq_to_file;
+        uint32_t nf = 0;
+        for (uint32_t q = 0; q < h.n_seq; ++q) nf = std::max(nf, seq_to_file[q] + 1);
+        if (nf > 64) { delete tabs; return -4; }
+        cx.all_files = nf == 64 ? ~0ull : ((1ull << nf) - 1ull);
+    }
     // jump tables, level by level (the device builder does the same with one thread per entry)
     JumpPlan plan;
     plan_jump_tables(*tabs, jump_depth < 0 ? default_jump_depth(h.n_bwt) : (uint32_t)jump_depth, plan);
@@ -137,10 +150,12 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     build_work_ranges(text_len, K, chrom_cum, n_chrom, intervals, n_intervals, pos_begin, pos_end, ranges);
     const uint64_t* text = reinterpret_cast<const uint64_t*>(base + h.off_text);
     unsigned long long f = 0, lr = 0;
-    if (K <= 32) run_ranges<1>(cx, text, text_begin, ranges, value_bits, out, &f, &lr);
-    else if (K <= 64) run_ranges<2>(cx, text, text_begin, ranges, value_bits, out, &f, &lr);
-    else if (K <= 128) run_ranges<4>(cx, text, text_begin, ranges, value_bits, out, &f, &lr);
-    else run_ranges<8>(cx, text, text_begin, ranges, value_bits, out, &f, &lr);
+#define RUN_KW(KW) (ep ? run_ranges<KW, true>(cx, text, text_begin, ranges, value_bits, out, &f, &lr) \
+                       : run_ranges<KW, false>(cx, text, text_begin, ranges, value_bits, out, &f, &lr))
+    if (K <= 32) RUN_KW(1);
+    else if (K <= 64) RUN_KW(2);
+    else if (K <= 128) RUN_KW(4);
+    else RUN_KW(8);
     if (fetches) *fetches = f;
     if (lut_reads_out) *lut_reads_out = lr;
     delete tabs;

@@ -11,8 +11,8 @@ from test_cli_cpu import FLAVOURS
 
 pytestmark = pytest.mark.gpu
 
-# Dna5 genomes (1c-1g) and --exclude-pseudo (3c-3f) are not on the GPU path yet
-CASES = ["1a", "1b", "2a", "2b", "2c", "2d", "2e", "3a", "3b"]
+# Dna5 genomes (1c-1g) are not on the GPU path yet
+CASES = ["1a", "1b", "2a", "2b", "2c", "2d", "2e", "3a", "3b", "3c", "3d", "3e", "3f"]
 
 
 @pytest.fixture(scope="module")
@@ -31,7 +31,7 @@ def test_cli_reproduces_reference_golden_directories(genmap, case, builder, tmp_
     src = ["-FD", folder] if cfg["dir"] else ["-F", os.path.join(folder, "genome.fa")]
     r = subprocess.run([genmap, "index"] + src + ["-I", idx] + (["-xh"] if builder == "host" else []), capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    base_flags = ["-K", str(cfg["K"]), "-E", str(cfg["E"])] + ([] if cfg["rc"] else ["-nc"])
+    base_flags = ["-K", str(cfg["K"]), "-E", str(cfg["E"])] + ([] if cfg["rc"] else ["-nc"]) + (["-ep"] if cfg["ep"] else [])
     if os.path.exists(os.path.join(folder, "subset.bed")):
         base_flags += ["-S", os.path.join(folder, "subset.bed")]
     n = 0

@@ -203,3 +203,59 @@ def test_cuda_range_slices_and_bwt_export(gm):
         assert np.array_equal(ix.compute_mappability_range(p, b, e), whole[b:e])
     for rev in (False, True):
         assert np.array_equal(ix.export_bwt(rev), orc.bwt(rev))
+
+
+# ---- --exclude-pseudo (locate + distinct FASTA files) -------------------------------------------------
+@pytest.mark.parametrize("case", ["3c", "3d", "3e", "3f"])
+def test_cuda_exclude_pseudo_matches_reference_golden(gm, case):
+    cfg = T.CASES[case]
+    files, sel, folder = T.load_case(case)
+    seqs, stf, _ = T.case_layout(files)
+    _, limits = T.concat(seqs)
+    ix = gm.Index.build(seqs, with_sa=True, seq_to_file=stf)
+    for fi, (base, recs) in enumerate(files):
+        iv = T.file_intervals(sel, recs)
+        if iv is None:
+            continue
+        gold = np.fromfile(os.path.join(folder, "raw_freq16", base + ".genmap.freq16"), dtype=np.uint16)
+        stf_, tb, tl, cum, ivv = T._prep(limits, stf, fi, iv)
+        got = ix.compute_mappability(gm.SearchParams(cfg["K"], cfg["E"], cfg["rc"], True, 16), text_begin=tb, text_len=tl,
+                                     chrom_cum_lengths=cum, intervals=ivv)
+        assert np.array_equal(got, gold), (case, base)
+
+
+@pytest.mark.parametrize("line", [c for c in RF.CASES if "-ep" in c], ids=lambda c: c.split("|")[0])
+def test_cuda_exclude_pseudo_matches_reference_binary_fixtures(gm, line):
+    name, K, E, flags, bits, seqs, stf, outs = RF.load_fixture(line)
+    _, limits = T.concat(seqs)
+    ix = gm.Index.build(seqs, with_sa=True, seq_to_file=stf)
+    for fi, gold in enumerate(outs):
+        stf_, tb, tl, cum, _ = T._prep(limits, stf, fi, None)
+        got = ix.compute_mappability(gm.SearchParams(K, E, "-nc" not in flags, True, bits), text_begin=tb, text_len=tl,
+                                     chrom_cum_lengths=cum)
+        assert np.array_equal(got, gold), (name, fi)
+
+
+def test_cuda_exclude_pseudo_pangenome_scale_model(gm):
+    """BASELINE config 5 in miniature: 10 FASTA files x 3 chromosomes, file g = base with g % substitutions,
+    K=50 E=2 --exclude-pseudo, against the oracle."""
+    base = T.repeat_rich(46, 3, 3000)
+    rng = np.random.default_rng(46)
+    seqs, stf = [], []
+    for g in range(10):
+        for s in base:
+            s = s.copy()
+            m = rng.random(len(s)) < 0.01 * g
+            s[m] = rng.integers(0, 4, int(m.sum()), dtype=np.uint8)
+            seqs.append(s); stf.append(g)
+    stf = np.array(stf, dtype=np.uint32)
+    _, limits = T.concat(seqs)
+    orc = T.Oracle(seqs, seq_to_file=stf)
+    ix = gm.Index.build(seqs, with_sa=True, seq_to_file=stf)
+    for fi in (0, 4, 9):
+        stf_, tb, tl, cum, _ = T._prep(limits, stf, fi, None)
+        got = ix.compute_mappability(gm.SearchParams(50, 2, True, True, 16), text_begin=tb, text_len=tl, chrom_cum_lengths=cum)
+        assert np.array_equal(got, orc.map(50, 2, exclude_pseudo=True, file_no=fi)), fi
+    with pytest.raises(gm.GenmapError):  # no suffix array in the index
+        gm.Index.build(seqs, with_sa=False, seq_to_file=stf).compute_mappability(gm.SearchParams(50, 2, True, True, 16), text_begin=0,
+                                                                                  text_len=int(limits[3]), chrom_cum_lengths=limits[:4])

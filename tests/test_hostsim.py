@@ -97,3 +97,39 @@ def test_fetch_counter_is_deterministic_and_plausible():
     _, f0 = hs.map(30, 0, return_fetches=True, jump_depth=0)
     assert n_kmers * 10 < f0 < n_kmers * 130  # <= 30 steps per strand, 1-2 blocks per step
     assert f1 < f0  # the jump table skips the top levels
+
+
+@pytest.mark.parametrize("case", ["3c", "3d", "3e", "3f"])
+def test_exclude_pseudo_matches_reference_golden(case):
+    cfg = T.CASES[case]
+    files, sel, folder = T.load_case(case)
+    seqs, stf, _ = T.case_layout(files)
+    hs = T.HostSim(seqs, with_sa=True)
+    for fi, (base, recs) in enumerate(files):
+        iv = T.file_intervals(sel, recs)
+        if iv is None:
+            continue
+        import os
+        gold = np.fromfile(os.path.join(folder, "raw_freq16", base + ".genmap.freq16"), dtype=np.uint16)
+        got = hs.map(cfg["K"], cfg["E"], revcompl=cfg["rc"], seq_to_file=stf, file_no=fi, intervals=iv, exclude_pseudo=True)
+        assert np.array_equal(got, gold), (case, base)
+
+
+@pytest.mark.parametrize("K,E,rc", [(25, 2, True), (25, 1, False), (12, 0, True), (40, 3, True)])
+def test_exclude_pseudo_matches_oracle(K, E, rc):
+    base = T.repeat_rich(13, 2, 1500)
+    rng = np.random.default_rng(5)
+    seqs, stf = [], []
+    for g in range(4):
+        for s in base:
+            s = s.copy()
+            m = rng.random(len(s)) < 0.03 * g
+            s[m] = rng.integers(0, 4, int(m.sum()), dtype=np.uint8)
+            seqs.append(s); stf.append(g)
+    stf = np.array(stf, dtype=np.uint32)
+    orc, hs = T.Oracle(seqs, seq_to_file=stf), T.HostSim(seqs, with_sa=True)
+    for f in (0, 3):
+        want = orc.map(K, E, revcompl=rc, exclude_pseudo=True, file_no=f)
+        for depth in (0, -1):
+            got = hs.map(K, E, revcompl=rc, seq_to_file=stf, file_no=f, exclude_pseudo=True, jump_depth=depth)
+            assert np.array_equal(got, want), (K, E, rc, f, depth)
