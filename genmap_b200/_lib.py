@@ -4,7 +4,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libgenmap_b200.so")
+LIB_PATH = os.environ.get("GMB_LIB_PATH") or os.path.join(HERE, "lib", "libgenmap_b200.so")  # env: tuning builds only
 
 GMB_OK, GMB_ERR_ARG, GMB_ERR_UNSUPPORTED, GMB_ERR_CUDA, GMB_ERR_IO, GMB_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 GMB_BUILD_WITH_SA, GMB_BUILD_ON_GPU = 1, 2

@@ -102,26 +102,38 @@ void fill_ctx(const gmb_index* ix, MapCtx& cx)
     cx.n_seq = ix->h.n_seq; cx.own_file = 0; cx.all_files = 0;
 }
 
-// make sure the tables of every depth in `plan` exist on the device
+// make sure the tables of every depth in `plan` exist on the device (built level by level, cached)
 int ensure_jump_tables(gmb_index* ix, const JumpPlan& plan, cudaStream_t stream)
 {
-    bool needed[17] = {};
-    for (uint32_t s = 0; s < kMaxSearches; ++s) needed[plan.depth[s]] = true;
+    bool need_uni[17] = {}, need_lof[17] = {};
+    for (uint32_t s = 0; s < kMaxSearches; ++s) {
+        const uint32_t d = plan.depth[s];
+        if (d) { need_uni[d] = true; need_lof[d] = need_lof[d] || plan.need_lof[s]; }
+    }
+    uint32_t top = 0, lof_top = 0;
+    for (uint32_t d = 1; d <= 16; ++d) {
+        if (need_uni[d] && (!ix->jt_uni[d] || (need_lof[d] && !ix->jt_lof[d]))) top = d;
+        if (need_lof[d]) lof_top = d;
+    }
+    if (top == 0) return GMB_OK; // everything this call needs is cached
     MapCtx cx;
     fill_ctx(ix, cx);
-    for (uint32_t d = 1; d <= plan.max_depth; ++d) {
-        if (ix->jt_uni[d]) continue;
+    for (uint32_t d = 1; d <= top; ++d) {
+        const bool want_lof = d <= lof_top || d <= kJumpKeep;
+        if (ix->jt_uni[d] && (!want_lof || ix->jt_lof[d])) continue;
+        if (ix->jt_uni[d]) { cudaFree(ix->jt_uni[d]); ix->jt_uni[d] = nullptr; }
+        if (ix->jt_lof[d]) { cudaFree(ix->jt_lof[d]); ix->jt_lof[d] = nullptr; }
         const size_t n = (size_t)1 << (2 * d);
         cudaError_t e = cudaMalloc(&ix->jt_uni[d], n * sizeof(JtEntry));
-        if (e == cudaSuccess) e = cudaMalloc(&ix->jt_lof[d], n * sizeof(uint32_t));
+        if (e == cudaSuccess && want_lof) e = cudaMalloc(&ix->jt_lof[d], n * sizeof(uint32_t));
         if (e == cudaSuccess) e = build_jump_level(cx, d, ix->jt_uni[d - 1], ix->jt_lof[d - 1], ix->jt_uni[d], ix->jt_lof[d], stream);
         if (e != cudaSuccess) return cuda_fail(e, "jump table");
     }
     CU(cudaStreamSynchronize(stream));
     for (uint32_t d = kJumpKeep + 1; d <= 16; ++d) // big intermediate / stale levels are not kept
-        if (ix->jt_uni[d] && !(d <= plan.max_depth && needed[d])) {
-            cudaFree(ix->jt_uni[d]); cudaFree(ix->jt_lof[d]);
-            ix->jt_uni[d] = nullptr; ix->jt_lof[d] = nullptr;
+        if (ix->jt_uni[d] && !need_uni[d]) {
+            cudaFree(ix->jt_uni[d]); ix->jt_uni[d] = nullptr;
+            if (ix->jt_lof[d]) { cudaFree(ix->jt_lof[d]); ix->jt_lof[d] = nullptr; }
         }
     return GMB_OK;
 }
@@ -180,6 +192,10 @@ static int finish_open(gmb_index* ix, gmb_index** out)
 {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, ix->device));
+    if (const char* g = std::getenv("GMB_L2_FETCH")) { // tuning knob: L2 fetch granularity hint (32/64/128 bytes)
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g));
+        cudaGetLastError();
+    }
     ix->sm_count = prop.multiProcessorCount;
     ix->limits.resize((size_t)ix->h.n_seq + 1);
     CU(cudaMemcpy(ix->limits.data(), ix->d_blob + ix->h.off_limits, ix->limits.size() * 8, cudaMemcpyDeviceToHost));
@@ -391,6 +407,11 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
         if (want < 0 && env && *env) want = std::atoi(env);
         uint32_t maxd = want < 0 ? default_jump_depth(ix->h.n_bwt) : (uint32_t)want;
         if (maxd > 16) maxd = 16;
+        if (want < 0) { // automatic depth: the deepest level plus its parent must fit comfortably in free HBM
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+                while (maxd > 1 && !ix->jt_uni[maxd] && ((size_t)15 << (2 * maxd)) > free_b / 2) --maxd;
+        }
         plan_jump_tables(*tabs, maxd, plan);
         int rcj = ensure_jump_tables(ix, plan, stream);
         if (rcj != GMB_OK) return rcj;

@@ -61,6 +61,33 @@ GMB_HD BlockRegs load_block(const RankBlock* p)
     return b;
 }
 
+// b = (pred ? *p : b): the load is predicated, not branched around, so that both blocks of a node
+// expansion are requested back to back by every lane of the warp
+GMB_HD void load_block_if(BlockRegs& b, const RankBlock* p, bool pred)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %17, 0;\n\t"
+        "@q ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
+        "@q ld.global.nc.v8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%16+32];\n\t}"
+        : "+r"(b.h[0]), "+r"(b.h[1]), "+r"(b.h[2]), "+r"(b.h[3]), "+r"(b.p0[0]), "+r"(b.p0[1]), "+r"(b.p1[0]), "+r"(b.p1[1]),
+          "+r"(b.p0[2]), "+r"(b.p0[3]), "+r"(b.p1[2]), "+r"(b.p1[3]), "+r"(b.p0[4]), "+r"(b.p0[5]), "+r"(b.p1[4]), "+r"(b.p1[5])
+        : "l"(p), "r"((uint32_t)pred));
+#else
+    if (pred) b = load_block(p);
+#endif
+}
+
+// true iff `x` holds for every lane of the warp that is executing this call (host: this one chain)
+GMB_HD bool warp_all(bool x)
+{
+#if defined(__CUDA_ARCH__)
+    return __all_sync(__activemask(), x) != 0;
+#else
+    return x;
+#endif
+}
+
 // mask of the symbols of piece q (32 symbols) that lie before in-block offset r
 GMB_HD uint32_t piece_mask(uint32_t r, int q)
 {
@@ -260,6 +287,7 @@ struct Chain {
     uint32_t t, e, s, strand;  // step, errors, search, strand of the current walk
     uint32_t lvmask;           // error levels holding a frame with pending children
     uint64_t files;            // --exclude-pseudo: FASTA files seen so far (one bit each)
+    uint32_t pre_lo_f, pre_lo_r, pre_size; // jump-table entry of (reverse strand, search 0), fetched early
 };
 
 // --exclude-pseudo: mark the FASTA file of every occurrence in SA rows [lo, lo+n)
@@ -282,6 +310,18 @@ GMB_HD void ep_mark_rows(uint64_t& mask, uint32_t lo, uint32_t n, const MapCtx& 
 // index, 9 = t | pending << 8
 constexpr int kFrameWords = 10;
 
+GMB_HD void jump_lookup(const SearchStart& S, uint32_t key, uint32_t& lo_f, uint32_t& lo_r, uint32_t& size)
+{
+#if defined(__CUDA_ARCH__)
+    const uint2 e = __ldg(reinterpret_cast<const uint2*>(S.uni) + key);
+    lo_r = e.x; size = e.y;
+    lo_f = S.lof ? __ldg(S.lof + key) : 0u;
+#else
+    lo_r = S.uni[key].lo_r; size = S.uni[key].size;
+    lo_f = S.lof ? S.lof[key] : 0u;
+#endif
+}
+
 template <int KW>
 GMB_HD void chain_start(Chain<KW>& st, const MapCtx& cx, unsigned long long* lut_reads)
 {
@@ -290,15 +330,8 @@ GMB_HD void chain_start(Chain<KW>& st, const MapCtx& cx, unsigned long long* lut
     if (S.uni == nullptr) {
         st.lo_f = 0; st.lo_r = 0; st.size = cx.n_bwt; st.t = 0;
     } else {
-        const uint32_t key = st.pat.bits(S.a, S.d);
-#if defined(__CUDA_ARCH__)
-        const uint2 e = __ldg(reinterpret_cast<const uint2*>(S.uni) + key);
-        st.lo_r = e.x; st.size = e.y;
-        st.lo_f = S.lof ? __ldg(S.lof + key) : 0u;
-#else
-        st.lo_r = S.uni[key].lo_r; st.size = S.uni[key].size;
-        st.lo_f = S.lof ? S.lof[key] : 0u;
-#endif
+        if (st.strand == 1 && st.s == 0) { st.lo_f = st.pre_lo_f; st.lo_r = st.pre_lo_r; st.size = st.pre_size; }
+        else jump_lookup(S, st.pat.bits(S.a, S.d), st.lo_f, st.lo_r, st.size);
         st.t = S.d;
         if (lut_reads) *lut_reads += 1;
     }
@@ -308,6 +341,14 @@ template <int KW>
 GMB_HD void chain_begin_kmer(Chain<KW>& st, const MapCtx& cx, unsigned long long* lut_reads)
 {
     st.acc = 0; st.s = 0; st.strand = 0; st.files = 0;
+    // the reverse strand's first jump-table entry does not depend on the forward search: request it now so
+    // that its latency overlaps the forward strand instead of starting the reverse strand with a stall
+    const SearchStart S0 = cx.starts[0];
+    if (cx.n_strands > 1 && S0.uni != nullptr) {
+        Pattern<KW> rc = st.pat;
+        rc.reverse_complement(cx.K);
+        jump_lookup(S0, rc.bits(S0.a, S0.d), st.pre_lo_f, st.pre_lo_r, st.pre_size);
+    }
     chain_start(st, cx, lut_reads);
 }
 
@@ -375,20 +416,22 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
         const bool hit_ok = st.e + rem >= lb; // st.e <= ub is an invariant of the walk
 
         uint32_t n0, n1, n2, n3, l0, l1, l2, l3, oth0;
-        BlockRegs rb = load_block(B + bx);
-        if (!mis_ok && !step_sync(ent)) {
-            // exact step whose other-index interval is never needed again: one symbol's rank suffices
-            const uint32_t r0 = block_rank_one(rb, rx, x, p, SP);
-            if (by != bx) rb = load_block(B + by);
-            const uint32_t r1 = block_rank_one(rb, ry, y, p, SP);
+        // both rank blocks are requested before either is used (one memory latency per expansion)
+        const BlockRegs rbx = load_block(B + bx);
+        BlockRegs rby = rbx;
+        load_block_if(rby, B + by, by != bx);
+        // exact step whose other-index interval is never needed again: one symbol's rank suffices.  Taken
+        // only when the whole warp agrees, so that lanes never serialise two differently shaped paths.
+        if (warp_all(!mis_ok && !step_sync(ent))) {
+            const uint32_t r0 = block_rank_one(rbx, rx, x, p, SP);
+            const uint32_t r1 = block_rank_one(rby, ry, y, p, SP);
             const uint32_t np = r1 - r0, lp = sel4(cx.C[0], cx.C[1], cx.C[2], cx.C[3], p) + r0;
             n0 = p == 0 ? np : 0u; n1 = p == 1 ? np : 0u; n2 = p == 2 ? np : 0u; n3 = p == 3 ? np : 0u;
             l0 = l1 = l2 = l3 = lp;
             oth0 = z;
         } else {
-            const Ranks R0 = block_rank(rb, rx, x, SP);
-            if (by != bx) rb = load_block(B + by);
-            const Ranks R1 = block_rank(rb, ry, y, SP);
+            const Ranks R0 = block_rank(rbx, rx, x, SP);
+            const Ranks R1 = block_rank(rby, ry, y, SP);
             n0 = R1.a - R0.a; n1 = R1.c - R0.c; n2 = R1.g - R0.g; n3 = R1.t - R0.t;
             l0 = cx.C[0] + R0.a; l1 = cx.C[1] + R0.c; l2 = cx.C[2] + R0.g; l3 = cx.C[3] + R0.t;
             oth0 = z + (R1.s - R0.s);

@@ -98,9 +98,9 @@ void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan
 
 uint32_t default_jump_depth(uint64_t n_bwt)
 {
-    uint32_t d = 0;
-    while (d < 15 && (n_bwt >> (2 * (d + 1))) != 0) ++d;
-    return d < 1 ? 1 : d;
+    uint32_t d = 1; // ceil(log4(n_bwt)): the first depth at which a random d-mer is expected less than once
+    while (d < 16 && (n_bwt >> (2 * d)) != 0) ++d;
+    return d;
 }
 
 // ---------------------------------------------------------------------------------------------------

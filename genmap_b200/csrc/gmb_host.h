@@ -26,7 +26,7 @@ struct JumpPlan {
     uint32_t max_depth;
 };
 void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan);
-// floor(log4(n_bwt)) clamped to [1,15]: about one expected occurrence per table entry
+// ceil(log4(n_bwt)) clamped to [1,16]: less than one expected occurrence per table entry
 uint32_t default_jump_depth(uint64_t n_bwt);
 
 // 256-byte aligned growable byte buffer for the index blob

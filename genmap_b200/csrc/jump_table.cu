@@ -22,13 +22,13 @@ __global__ void k_jump_level(const MapCtx cx, uint32_t d, const JtEntry* __restr
     } else {
         const uint64_t pk = key & ((1ull << (2 * (d - 1))) - 1ull);
         const JtEntry e = prev_uni[pk];
-        par.lo_f = prev_lof[pk]; par.lo_r = e.lo_r; par.size = e.size;
+        par.lo_f = prev_lof ? prev_lof[pk] : 0u; par.lo_r = e.lo_r; par.size = e.size;
     }
     const Node m = extend_right(par, (uint32_t)(key >> (2 * (d - 1))), cx);
     JtEntry o;
     o.lo_r = m.lo_r; o.size = m.size;
     out_uni[key] = o;
-    out_lof[key] = m.lo_f;
+    if (out_lof) out_lof[key] = m.lo_f;
 }
 
 } // namespace

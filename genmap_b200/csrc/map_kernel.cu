@@ -22,6 +22,9 @@ namespace gmb {
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef GMB_MIN_BLOCKS
+#define GMB_MIN_BLOCKS 4 // resident CTAs per SM the register allocation must allow
+#endif
 
 struct SmemFrames {
     uint32_t* base; // + threadIdx.x
@@ -30,7 +33,7 @@ struct SmemFrames {
 };
 
 template <int KW, bool COUNT, typename OutT, bool EP>
-__global__ void __launch_bounds__(kThreads) map_kernel(const MapLaunch L)
+__global__ void __launch_bounds__(kThreads, GMB_MIN_BLOCKS) map_kernel(const MapLaunch L)
 {
     extern __shared__ uint32_t smem[];
     const uint32_t n_steps = L.cx.n_search * L.cx.K;
