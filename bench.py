@@ -50,7 +50,8 @@ def parse():
     ap.add_argument("--extras", default="1,2", help="other E values measured after the main line ('' = none)")
     ap.add_argument("--jump-depth", type=int, default=-1, help="-1 auto, 0 off, 1..16 max jump-table depth")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work of the cpu_baseline sample")
+    ap.add_argument("--ref-step-seconds", type=float, default=4.0, help="--impl reference: CPU work per step")
     return ap.parse_args()
 
 
@@ -122,38 +123,114 @@ def default_batch(E):
 
 
 # --------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path on the host cores, on a bounded window of the same genome
+# CPU arm: the reference's own implementation of the path on this box's host cores, on a bounded window of
+# the same genome.  Preferred: the UNMODIFIED reference binary (oracle/_ref/genmap_ref) reading an index in
+# its own on-disk format, written from the BWT + suffix array the GPU builder produced (its own `genmap
+# index` needs ~45 min of single-threaded divsufsort at 3 Gbp).  Fallback: the oracle port (OpenMP).
 # --------------------------------------------------------------------------------------------------------
-def cpu_port_rate(seqs, bwt_f, bwt_r, K, E, seconds, steps=1, warmup=0):
-    """-> (positions/s, cores, sample description, per-step ms list)"""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import gmtest as T
-    cores = os.cpu_count() or 1
-    t0 = time.time()
-    orc = T.Oracle(seqs, bwt=(bwt_f, bwt_r, 4))
-    log("oracle rank structure built in %.1f s" % (time.time() - t0))
-    n_text = int(orc.limits[-1])
-    per = int(orc.limits[1])
+def _window(n_text, per, K, npos):
     start = (n_text // 2 // per) * per + per // 3  # a fixed window inside one chromosome
+    b = min(start, n_text - npos - K)
+    return b, b + npos
 
-    def run(npos):
-        b = min(start, n_text - npos - K)
+
+class ReferenceCpu:
+    """`genmap_ref map -S window.bed` on a reference-format index of the bench genome."""
+    kind = "reference"
+
+    def __init__(self, seqs, ix):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import gmtest as T
+        self.T = T
+        if not T.have_reference():
+            raise RuntimeError("oracle/_ref/genmap_ref is not present")
+        self.cores = os.cpu_count() or 1
+        self.per = len(seqs[0])
+        self.n_text = sum(len(s) for s in seqs)
+        t0 = time.time()
+        bwt_f, bwt_r, sa = ix.export_bwt(False), ix.export_bwt(True), ix.export_sa()
+        self.dir = tempfile.mkdtemp(prefix="gmb_refidx_", dir=os.environ.get("GMB_TMPDIR"))
+        files = [("genome.fa", [("chr%d" % (i + 1), s) for i, s in enumerate(seqs)])]
+        T.write_seqan_index(os.path.join(self.dir, "index"), files, bwt_f, bwt_r, sa)
+        del bwt_f, bwt_r, sa
+        log("reference-format index written to %s in %.1f s" % (self.dir, time.time() - t0))
+
+    def run(self, K, E, npos):
+        b, e = _window(self.n_text, self.per, K, npos)
+        chrom, off = b // self.per, b % self.per
+        bed = os.path.join(self.dir, "window.bed")
+        with open(bed, "w") as f:
+            f.write("chr%d\t%d\t%d\n" % (chrom + 1, off, off + (e - b)))
+        out = os.path.join(self.dir, "out")
+        os.makedirs(out, exist_ok=True)
+        cmd = [self.T.REF_BIN, "map", "-I", os.path.join(self.dir, "index"), "-O", out, "-K", str(K), "-E", str(E),
+               "-r", "-fl", "-T", str(self.cores), "-v", "-S", bed]
+        res = subprocess.run(cmd, check=True, stdout=subprocess.PIPE, text=True)
+        for line in res.stdout.replace("\r", "\n").split("\n"):
+            if line.startswith("Mappability computed in"):
+                return max(float(line.split()[3]), 0.005)
+        raise RuntimeError("no timing line in the reference's output")
+
+    def sample(self, npos, K):
+        b, e = _window(self.n_text, self.per, K, npos)
+        return ("`genmap_ref map -S` on %d consecutive positions of chr%d of the same genome (<50%% of the text: "
+                "per-position work, copy shortcut off), -T %d; time = its own 'Mappability computed in' line"
+                % (npos, b // self.per + 1, self.cores))
+
+    def close(self):
+        import shutil
+        shutil.rmtree(self.dir, ignore_errors=True)
+
+
+class PortCpu:
+    """The oracle port (oracle/gm_oracle.c, OpenMP) on BWTs exported from the product index."""
+    kind = "port"
+
+    def __init__(self, seqs, ix):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import gmtest as T
+        self.cores = os.cpu_count() or 1
+        t0 = time.time()
+        self.orc = T.Oracle(seqs, bwt=(ix.export_bwt(False), ix.export_bwt(True), 4))
+        log("oracle rank structure built in %.1f s" % (time.time() - t0))
+        self.n_text, self.per = int(self.orc.limits[-1]), int(self.orc.limits[1])
+
+    def run(self, K, E, npos):
+        b, e = _window(self.n_text, self.per, K, npos)
         t = time.time()
-        orc.map(K, E, intervals=[(b, b + npos)], threads=cores)
+        self.orc.map(K, E, intervals=[(b, e)], threads=self.cores)
         return time.time() - t
 
-    pilot = 50_000 if E < 2 else 5_000
-    dt = run(pilot)
-    npos = int(max(pilot, min(per // 2, pilot * seconds / max(dt, 1e-3))))
+    def sample(self, npos, K):
+        b, _ = _window(self.n_text, self.per, K, npos)
+        return "oracle port on %d consecutive positions of chr%d (copy shortcut off), %d OpenMP threads" % (
+            npos, b // self.per + 1, self.cores)
+
+    def close(self):
+        pass
+
+
+def make_cpu_arm(seqs, ix):
+    try:
+        return ReferenceCpu(seqs, ix)
+    except Exception as ex:
+        log("reference binary arm unavailable (%r): falling back to the oracle port" % (ex,))
+        return PortCpu(seqs, ix)
+
+
+def cpu_rate(arm, K, E, seconds, steps=1, warmup=0):
+    """-> (positions/s, per-step ms, positions per step)"""
+    pilot = {0: 2_000_000, 1: 500_000, 2: 50_000, 3: 5_000, 4: 1_000}[E]
+    if arm.kind == "port":
+        pilot //= 10
+    dt = arm.run(K, E, pilot)
+    npos = int(max(pilot, min(arm.per // 2, pilot * seconds / dt)))
     times = []
     for i in range(warmup + steps):
-        dt = run(npos)
+        dt = arm.run(K, E, npos)
         if i >= warmup:
             times.append(dt)
-    rate = npos * len(times) / sum(times)
-    sample = "%d consecutive positions of chr%d (-S style window, copy shortcut off), %d OpenMP threads" % (
-        npos, start // per + 1, cores)
-    return rate, cores, sample, [t * 1e3 for t in times], npos
+    return npos * len(times) / sum(times), [t * 1e3 for t in times], npos
 
 
 def main():
@@ -190,7 +267,9 @@ def main():
         seqs = gm.synth_genome(total, args.nchr, args.seed)
         log("genome generated in %.1f s" % (time.time() - t0))
         t0 = time.time()
-        ix = gm.Index.build(seqs, device=local, on_gpu=True)
+        # the suffix array (4 B/base more HBM) is only kept when the CPU arm needs to write a reference-format index
+        want_sa = args.impl == "reference" or (world == 1 and not args.no_cpu_baseline)
+        ix = gm.Index.build(seqs, device=local, on_gpu=True, with_sa=want_sa)
         log("index built on GPU in %.1f s %s, blob %.2f GB" % (time.time() - t0, ix.build_timings_ms, ix.info.blob_bytes / 1e9))
     if dist is not None:
         from genmap_b200 import parallel
@@ -209,15 +288,17 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
 
     if args.impl == "reference":
-        bwt_f, bwt_r = ix.export_bwt(False), ix.export_bwt(True)
+        arm = make_cpu_arm(seqs, ix)
         ix.close()
-        rate, cores, sample, times, npos = cpu_port_rate(seqs, bwt_f, bwt_r, K, E, args.cpu_seconds, args.steps, args.warmup)
+        torch.cuda.empty_cache()
+        rate, times, npos = cpu_rate(arm, K, E, args.ref_step_seconds, args.steps, args.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "config": {"workload": workload, "K": K, "E": E, "genome_bp": n_text, "positions_per_step": npos},
-                "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "cpu_baseline": {"value": rate, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample(npos, K)},
                 "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        arm.close()
         print(json.dumps(line), flush=True)
         return 0
 
@@ -332,9 +413,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            bwt_f, bwt_r = ix.export_bwt(False), ix.export_bwt(True)
-            rate, cores, sample, _, _ = cpu_port_rate(seqs, bwt_f, bwt_r, K, E, args.cpu_seconds)
-            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            arm = make_cpu_arm(seqs, ix)
+            rate, _, npos_cpu = cpu_rate(arm, K, E, args.cpu_seconds)
+            cpu = {"value": rate, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample(npos_cpu, K)}
+            arm.close()
         except Exception as ex:  # the baseline is a reported extra; never lose the GPU line over it
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
 

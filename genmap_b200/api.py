@@ -167,6 +167,12 @@ class Index:
         check(_lib.lib().gmb_index_export_bwt(self._h, int(rev), _ptr(out)))
         return out
 
+    def export_sa(self):
+        """Full suffix array of the sentinel-separated text (needs an index built with with_sa=True)."""
+        out = np.zeros(int(self.info.n_bwt), dtype=np.uint32)
+        check(_lib.lib().gmb_index_export_sa(self._h, _ptr(out)))
+        return out
+
     def compute_mappability_device(self, params, out_ptr, text_begin=0, text_len=None, chrom_cum_lengths=None,
                                    intervals=None, pos_begin=0, pos_end=None, stream=0, count_fetches=False,
                                    sync=True):

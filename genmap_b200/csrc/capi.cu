@@ -511,6 +511,15 @@ int gmb_map_frequencies(gmb_index* ix, const gmb_params* p, uint64_t text_begin,
                                      seq_to_file, n_seq, 0, text_len, out, stats);
 }
 
+int gmb_index_export_sa(gmb_index* ix, uint32_t* out_host)
+{
+    if (!ix || !out_host) return fail(GMB_ERR_ARG, "gmb_index_export_sa: NULL argument");
+    if (!ix->h.off_sa) return fail(GMB_ERR_UNSUPPORTED, "the index holds no suffix array (build it with GMB_BUILD_WITH_SA)");
+    CU(cudaSetDevice(ix->device));
+    CU(cudaMemcpy(out_host, ix->d_blob + ix->h.off_sa, ix->h.n_bwt * 4, cudaMemcpyDeviceToHost));
+    return GMB_OK;
+}
+
 int gmb_index_export_bwt(gmb_index* ix, int rev, uint8_t* out_host)
 {
     if (!ix || !out_host) return fail(GMB_ERR_ARG, "gmb_index_export_bwt: NULL argument");

@@ -111,6 +111,9 @@ int gmb_index_set_jump_depth(gmb_index *idx, int depth);
 /* Diagnostics / test support: decode one direction's BWT (rev = 0: of T, 1: of T') to one byte per
  * row (0 = sentinel, 1..4 = A,C,G,T) into host memory (n_bwt bytes). */
 int gmb_index_export_bwt(gmb_index *idx, int rev, uint8_t *out_host);
+/* Copy the full suffix array of T (n_bwt uint32 positions inside the sentinel-separated text) to host
+ * memory; fails with GMB_ERR_UNSUPPORTED when the index was built without GMB_BUILD_WITH_SA. */
+int gmb_index_export_sa(gmb_index *idx, uint32_t *out_host);
 
 /* The hot path with HOST output (what the reference's run() does for one FASTA file).
  * out: text_len elements of value_bits/8 bytes, overwritten.  seq_to_file / n_seq only under -ep. */

@@ -397,3 +397,53 @@ class HostSim:
             raise RuntimeError("hs_map failed: %d" % rc)
         self.last_lut_reads = lr.value
         return (out, f.value) if return_fetches else out
+
+
+# ---------------------------------------------------------------------------------------------
+# writing the reference's on-disk index from a BWT + SA computed elsewhere (oracle/seqan_index.c)
+# ---------------------------------------------------------------------------------------------
+def write_seqan_index(directory, files, bwt_fwd, bwt_rev, sa, sampling=10):
+    """files: [(file_name, [(seq_name, codes)])] in index order.  bwt_*: uint8 rows, 0 = sentinel, 1..4 = ACGT.
+    sa: uint32 suffix array of the sentinel-separated text.  Writes everything `genmap_ref map` opens."""
+    L = oracle_lib()
+    vp, u64, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32
+    L.gmo_seqan_write_lf.restype = ctypes.c_int
+    L.gmo_seqan_write_lf.argtypes = [ctypes.c_char_p, vp, u64, vp]
+    L.gmo_seqan_write_sa.restype = ctypes.c_int
+    L.gmo_seqan_write_sa.argtypes = [ctypes.c_char_p, vp, u64, vp, u32, u32]
+    L.gmo_seqan_write_packed_text.restype = ctypes.c_int
+    L.gmo_seqan_write_packed_text.argtypes = [ctypes.c_char_p, vp, u64]
+    os.makedirs(directory, exist_ok=True)
+    base = os.path.join(directory, "index")
+    seqs = [c for _, recs in files for _, c in recs]
+    codes, limits = concat(seqs)
+    n_seq, n = len(seqs), int(limits[-1]) + len(seqs)
+
+    def string_set(path, strings):
+        raw = [s.encode() for s in strings]
+        with open(path + ".concat", "wb") as f:
+            f.write(b"".join(raw))
+        np.concatenate([[0], np.cumsum([len(r) for r in raw])]).astype("<u8").tofile(path + ".limits")
+
+    directory_flag = "true" if len(files) > 1 else "false"
+    string_set(base + ".info", ["alphabet_size:4", "sa_dimensions_i1:16", "sa_dimensions_i2:32", "bwt_dimensions:32",
+                                "sampling_rate:%d" % sampling, "fasta_directory:" + directory_flag, "packed_text:true"])
+    string_set(base + ".ids", ["%s;%d;%s" % (fn, len(c), name) for fn, recs in files for name, c in recs])
+    limits.astype("<u8").tofile(base + ".txt.limits")
+    assert L.gmo_seqan_write_packed_text((base + ".txt.concat").encode(), _ptr(codes), len(codes)) == 0
+    for rev, bwt in ((False, bwt_fwd), (True, bwt_rev)):
+        pre = base + (".rev.lf" if rev else ".lf")
+        bwt = np.ascontiguousarray(bwt, dtype=np.uint8)
+        counts = np.zeros(4, dtype=np.uint64)
+        assert L.gmo_seqan_write_lf(pre.encode(), _ptr(bwt), n, _ptr(counts)) == 0
+        pst = np.zeros(5, dtype="<u4")
+        pst[0] = n_seq
+        pst[1:] = n_seq + np.cumsum(counts)
+        pst.tofile(pre + ".pst")
+        with open(pre + ".drs", "wb") as f:
+            f.write(b"\x00")
+    seq_start = np.ascontiguousarray(limits + np.arange(n_seq + 1, dtype=np.uint64))
+    sa = np.ascontiguousarray(sa, dtype=np.uint32)
+    assert L.gmo_seqan_write_sa((base + ".sa").encode(), _ptr(sa), n, _ptr(seq_start), n_seq, sampling) == 0
+    np.array([n], dtype="<u8").tofile(base + ".sa.len")
+    return directory

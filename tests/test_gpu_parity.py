@@ -259,3 +259,24 @@ def test_cuda_exclude_pseudo_pangenome_scale_model(gm):
     with pytest.raises(gm.GenmapError):  # no suffix array in the index
         gm.Index.build(seqs, with_sa=False, seq_to_file=stf).compute_mappability(gm.SearchParams(50, 2, True, True, 16), text_begin=0,
                                                                                   text_len=int(limits[3]), chrom_cum_lengths=limits[:4])
+
+
+def test_gpu_built_index_feeds_the_unmodified_reference(gm, tmp_path):
+    """BWT + SA from the GPU builder, written in the reference's on-disk format, make the unmodified
+    reference binary produce the same frequencies as the CUDA path (this is what bench.py's CPU arm does)."""
+    if not T.have_reference():
+        pytest.skip("oracle/_ref/genmap_ref not present")
+    import subprocess
+    seqs = gm.synth_genome(1_200_000, 3, 7)
+    ix = gm.Index.build(seqs, with_sa=True)
+    files = [("genome.fa", [("chr%d" % (i + 1), s) for i, s in enumerate(seqs)])]
+    d = T.write_seqan_index(str(tmp_path / "index"), files, ix.export_bwt(False), ix.export_bwt(True), ix.export_sa())
+    out = tmp_path / "out"
+    out.mkdir()
+    bed = tmp_path / "w.bed"
+    bed.write_text("chr2\t1000\t151000\n")
+    subprocess.run([T.REF_BIN, "map", "-I", d, "-O", str(out), "-K", "30", "-E", "1", "-r", "-fl", "-S", str(bed)], check=True,
+                   stdout=subprocess.DEVNULL)
+    ref = np.fromfile(str(out / "genome.genmap.freq16"), dtype=np.uint16)
+    got = ix.compute_mappability(gm.SearchParams(30, 1), intervals=[(401000, 551000)])
+    assert np.array_equal(got, ref)

@@ -1,0 +1,46 @@
+"""The reference-format index writer (oracle/seqan_index.c + gmtest.write_seqan_index) must reproduce the
+files written by the unmodified reference's own `genmap index` byte for byte, and the reference's `map`
+must give the same frequencies on it.  Needs oracle/_ref/genmap_ref (present in the build container and,
+because oracle/_ref travels, on the GPU box)."""
+import filecmp
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import gmtest as T
+
+pytestmark = pytest.mark.skipif(not T.have_reference(), reason="oracle/_ref/genmap_ref not built")
+
+
+@pytest.mark.parametrize("seed,nchr,length,nfiles", [(5, 3, 1000, 1), (6, 1, 70000, 1), (7, 4, 40000, 1), (8, 2, 3000, 3)])
+def test_writer_is_byte_identical_to_reference_index(tmp_path, seed, nchr, length, nfiles):
+    files = []
+    for f in range(nfiles):
+        seqs = T.repeat_rich(seed + 100 * f, nchr, length)
+        files.append(("g%02d.fa" % f if nfiles > 1 else "genome.fa", [("f%ds%d" % (f, i), s) for i, s in enumerate(seqs)]))
+    src = tmp_path / "fasta"
+    src.mkdir()
+    for fn, recs in files:
+        T.write_fasta(str(src / fn), [c for _, c in recs], names=[n for n, _ in recs])
+    ref_dir = str(tmp_path / "ref_index")
+    flag = ["-FD", str(src)] if nfiles > 1 else ["-F", str(src / "genome.fa")]
+    subprocess.run([T.REF_BIN, "index"] + flag + ["-I", ref_dir], check=True, stdout=subprocess.DEVNULL)
+    seqs = [c for _, recs in files for _, c in recs]
+    hs = T.HostSim(seqs, with_sa=True)  # the product's own host builder supplies BWT and SA
+    ours = T.write_seqan_index(str(tmp_path / "our_index"), files, hs.bwt(False), hs.bwt(True), hs.sa())
+    names = sorted(os.listdir(ref_dir))
+    assert sorted(os.listdir(ours)) == names
+    match, mismatch, errors = filecmp.cmpfiles(ref_dir, ours, names, shallow=False)
+    assert not mismatch and not errors, mismatch
+    # and the reference maps on it
+    out = tmp_path / "out"
+    out.mkdir()
+    subprocess.run([T.REF_BIN, "map", "-I", ours, "-O", str(out), "-K", "20", "-E", "1", "-r", "-fl"], check=True,
+                   stdout=subprocess.DEVNULL)
+    stf = np.array([fi for fi, (_, recs) in enumerate(files) for _ in recs], dtype=np.uint32)
+    orc = T.Oracle(seqs, seq_to_file=stf)
+    for fi, (fn, _) in enumerate(files):
+        got = np.fromfile(str(out / (fn[:-3] + ".genmap.freq16")), dtype=np.uint16)
+        assert np.array_equal(got, orc.map(20, 1, file_no=fi))
