@@ -21,9 +21,10 @@ namespace gmb {
 struct Ranks { uint32_t a, c, g, t, s; };
 
 // one rank block in registers: header + the two bit planes as six 32-symbol pieces each
+constexpr int kPieces = 2 * kBlockWords; // 32-symbol pieces per plane
 struct BlockRegs {
     uint32_t h[4];
-    uint32_t p0[6], p1[6];
+    uint32_t p0[kPieces], p1[kPieces];
 };
 
 GMB_HD uint32_t popc32(uint32_t x)
@@ -39,21 +40,24 @@ GMB_HD BlockRegs load_block(const RankBlock* p)
 {
     BlockRegs b;
 #if defined(__CUDA_ARCH__)
-    // one 64-byte block = two 256-bit read-only loads (LDG.E.256 on sm_100a)
-    uint32_t r0, r1, r2, r3, r4, r5, r6, r7, s0, s1, s2, s3, s4, s5, s6, s7;
+    // 32 bytes per 256-bit read-only load (LDG.E.256 on sm_100a): one load for a 32-byte block, two for 64
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
     asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
                  : "l"(p));
-    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7)
-                 : "l"(reinterpret_cast<const char*>(p) + 32));
     b.h[0] = r0; b.h[1] = r1; b.h[2] = r2; b.h[3] = r3;
     b.p0[0] = r4; b.p0[1] = r5; b.p1[0] = r6; b.p1[1] = r7;
-    b.p0[2] = s0; b.p0[3] = s1; b.p1[2] = s2; b.p1[3] = s3;
-    b.p0[4] = s4; b.p0[5] = s5; b.p1[4] = s6; b.p1[5] = s7;
+    if constexpr (kBlockWords == 3) {
+        uint32_t s0, s1, s2, s3, s4, s5, s6, s7;
+        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7)
+                     : "l"(reinterpret_cast<const char*>(p) + 32));
+        b.p0[kPieces - 4] = s0; b.p0[kPieces - 3] = s1; b.p1[kPieces - 4] = s2; b.p1[kPieces - 3] = s3;
+        b.p0[kPieces - 2] = s4; b.p0[kPieces - 1] = s5; b.p1[kPieces - 2] = s6; b.p1[kPieces - 1] = s7;
+    }
 #else
     b.h[0] = p->cnt[0]; b.h[1] = p->cnt[1]; b.h[2] = p->cnt[2]; b.h[3] = p->sent;
-    for (int k = 0; k < 3; ++k) {
+    for (uint32_t k = 0; k < kBlockWords; ++k) {
         b.p0[2 * k] = (uint32_t)p->w[k][0]; b.p0[2 * k + 1] = (uint32_t)(p->w[k][0] >> 32);
         b.p1[2 * k] = (uint32_t)p->w[k][1]; b.p1[2 * k + 1] = (uint32_t)(p->w[k][1] >> 32);
     }
@@ -67,12 +71,18 @@ GMB_HD void load_block_if(BlockRegs& b, const RankBlock* p, bool pred)
 {
 #if defined(__CUDA_ARCH__)
     asm volatile(
-        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %17, 0;\n\t"
-        "@q ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
-        "@q ld.global.nc.v8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%16+32];\n\t}"
-        : "+r"(b.h[0]), "+r"(b.h[1]), "+r"(b.h[2]), "+r"(b.h[3]), "+r"(b.p0[0]), "+r"(b.p0[1]), "+r"(b.p1[0]), "+r"(b.p1[1]),
-          "+r"(b.p0[2]), "+r"(b.p0[3]), "+r"(b.p1[2]), "+r"(b.p1[3]), "+r"(b.p0[4]), "+r"(b.p0[5]), "+r"(b.p1[4]), "+r"(b.p1[5])
+        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
+        "@q ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+        : "+r"(b.h[0]), "+r"(b.h[1]), "+r"(b.h[2]), "+r"(b.h[3]), "+r"(b.p0[0]), "+r"(b.p0[1]), "+r"(b.p1[0]), "+r"(b.p1[1])
         : "l"(p), "r"((uint32_t)pred));
+    if constexpr (kBlockWords == 3) {
+        asm volatile(
+            "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
+            "@q ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+32];\n\t}"
+            : "+r"(b.p0[kPieces - 4]), "+r"(b.p0[kPieces - 3]), "+r"(b.p1[kPieces - 4]), "+r"(b.p1[kPieces - 3]),
+              "+r"(b.p0[kPieces - 2]), "+r"(b.p0[kPieces - 1]), "+r"(b.p1[kPieces - 2]), "+r"(b.p1[kPieces - 1])
+            : "l"(p), "r"((uint32_t)pred));
+    }
 #else
     if (pred) b = load_block(p);
 #endif
@@ -111,12 +121,12 @@ GMB_HD uint32_t sentinels_in_block_before(const BlockRegs& b, uint32_t i, const 
     return s;
 }
 
-// ranks of all symbols at BWT position i = blk*192 + r  (rank_c(i) = #c in bwt[0,i))
+// ranks of all symbols at BWT position i = blk*kBlockBases + r  (rank_c(i) = #c in bwt[0,i))
 GMB_HD Ranks block_rank(const BlockRegs& b, uint32_t r, uint32_t i, const uint32_t* sent_pos)
 {
     uint32_t a = 0, c = 0, g = 0;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) {
+    for (int q = 0; q < kPieces; ++q) {
         const uint32_t m = piece_mask(r, q);
         const uint32_t x0 = b.p0[q], x1 = b.p1[q];
         a += popc32(~x0 & ~x1 & m);
@@ -140,7 +150,7 @@ GMB_HD uint32_t block_rank_one(const BlockRegs& b, uint32_t r, uint32_t i, uint3
     const uint32_t k0 = (sym & 1u) ? 0u : ~0u, k1 = (sym & 2u) ? 0u : ~0u;
     uint32_t n = 0;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) n += popc32((b.p0[q] ^ k0) & (b.p1[q] ^ k1) & piece_mask(r, q));
+    for (int q = 0; q < kPieces; ++q) n += popc32((b.p0[q] ^ k0) & (b.p1[q] ^ k1) & piece_mask(r, q));
     const uint32_t s_before = b.h[3] >> 8;
     uint32_t base;
     if (sym == 3u) base = (i - r) - b.h[0] - b.h[1] - b.h[2] - s_before; // T is the derived counter

@@ -16,31 +16,41 @@
 
 namespace gmb {
 
-// ---- rank block: 64 bytes = one 2-sector DRAM access, 192 BWT symbols -----------------------------
+// ---- rank block: 16-byte header + W x 16 bytes of bit planes (64 BWT symbols per plane pair) --------
 //   bytes  0..15 : cntA (sentinels NOT counted), cntC, cntG  = occurrences before this block
 //                  sent  = (#sentinels before this block) << 8 | (#sentinels inside this block)
-//   bytes 16..63 : 3 x { plane0 (low code bit) u64, plane1 (high code bit) u64 }, 64 symbols each
+//   then W x { plane0 (low code bit) u64, plane1 (high code bit) u64 }, 64 symbols each
 // codes: A=0 C=1 G=2 T=3; a sentinel row is stored as code 0 and listed in `sent_pos`.
 // cntT is derived: T(i) = i - A(i) - C(i) - G(i) - $(i).
-constexpr uint32_t kBlockBases = 192;
-constexpr uint32_t kBlockBytes = 64;
+// W = 1 (default): a block is ONE 32-byte sector = one 256-bit load = one memory request per rank boundary
+//                  (measured: the memory system sustains ~2x more random 32-byte requests than 64-byte blocks
+//                  fetched as two 32-byte requests, profiles/r01/s1_randread.txt), 1.5 GB per direction at 3 Gbp.
+// W = 3          : 64-byte block, 192 symbols, 1.0 GB per direction (the first layout measured; build with
+//                  -DGMB_BLOCK_WORDS=3 to compare).
+#ifndef GMB_BLOCK_WORDS
+#define GMB_BLOCK_WORDS 1
+#endif
+constexpr uint32_t kBlockWords = GMB_BLOCK_WORDS;
+constexpr uint32_t kBlockBases = 64 * kBlockWords;
+constexpr uint32_t kBlockBytes = 16 + 16 * kBlockWords;
 constexpr uint32_t kMaxSeq = (1u << 24) - 1; // sentinel counter has 24 bits
 constexpr uint32_t kMaxK = 255;              // step tables keep pattern offsets in 8 bits
 constexpr uint32_t kMaxE = 4;                // src/mappability.hpp:187
 constexpr uint32_t kMaxSearches = 7;         // src/find2_index_approx.hpp:121-131
 
-struct alignas(64) RankBlock {
+struct alignas(kBlockBytes) RankBlock {
     uint32_t cnt[3];
     uint32_t sent;
-    uint64_t w[3][2];
+    uint64_t w[kBlockWords][2];
 };
-static_assert(sizeof(RankBlock) == 64, "rank block must be 64 bytes");
+static_assert(sizeof(RankBlock) == kBlockBytes, "rank block size");
+static_assert(kBlockWords == 1 || kBlockWords == 3, "supported layouts: 32-byte and 64-byte blocks");
 
 // ---- on-disk / in-HBM blob --------------------------------------------------------------------------
 // One contiguous, 256-byte aligned blob; offsets are relative to its start so the same bytes serve as
 // file, pinned host copy and device copy (copied verbatim, broadcast verbatim).
 constexpr uint64_t kMagic = 0x3130584449424d47ULL; // "GMBIDX01"
-constexpr uint32_t kVersion = 2;
+constexpr uint32_t kVersion = 2 + 16 * kBlockWords; // the block layout is part of the format
 
 struct IndexHeader {
     uint64_t magic;
@@ -49,7 +59,7 @@ struct IndexHeader {
     uint64_t n_bwt;          // N = text length + one sentinel per sequence
     uint64_t n_text;         // concatenated text length (no sentinels)
     uint32_t n_seq;
-    uint32_t n_blocks;       // N / 192 + 1 per direction
+    uint32_t n_blocks;       // N / kBlockBases + 1 per direction
     uint64_t C[6];           // C[c] = #symbols smaller than base c in T (sentinels included); C[4] = N
     uint64_t off_fwd;        // RankBlock[n_blocks]   BWT of T      (extend left,  reference: Fwd)
     uint64_t off_rev;        // RankBlock[n_blocks]   BWT of T'     (extend right, reference: Rev)

@@ -160,11 +160,11 @@ __global__ void k_pack_blocks(const uint8_t* __restrict__ bwt, uint64_t n, uint3
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_blocks) return;
-    uint64_t w[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    uint64_t w[kBlockWords][2];
     uint32_t a = 0, c = 0, g = 0, s = 0;
     const uint64_t base = (uint64_t)b * kBlockBases;
 #pragma unroll
-    for (int word = 0; word < 3; ++word) {
+    for (int word = 0; word < (int)kBlockWords; ++word) {
         uint64_t p0 = 0, p1 = 0;
         for (int k = 0; k < 64; ++k) {
             const uint64_t i = base + word * 64 + k;
@@ -181,7 +181,7 @@ __global__ void k_pack_blocks(const uint8_t* __restrict__ bwt, uint64_t n, uint3
     RankBlock B;
     B.cnt[0] = B.cnt[1] = B.cnt[2] = 0;
     B.sent = s;
-    for (int word = 0; word < 3; ++word) { B.w[word][0] = w[word][0]; B.w[word][1] = w[word][1]; }
+    for (int word = 0; word < (int)kBlockWords; ++word) { B.w[word][0] = w[word][0]; B.w[word][1] = w[word][1]; }
     blocks[b] = B;
     cA[b] = a; cC[b] = c; cG[b] = g; cS[b] = s;
 }

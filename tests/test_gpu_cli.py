@@ -7,7 +7,6 @@ import subprocess
 import pytest
 
 import gmtest as T
-from test_cli_cpu import FLAVOURS
 
 pytestmark = pytest.mark.gpu
 
@@ -22,34 +21,52 @@ def genmap():
     return _build.build_cli()
 
 
-@pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("builder", ["gpu", "host"])
-def test_cli_reproduces_reference_golden_directories(genmap, case, builder, tmp_path):
+VALUE_TYPES = {"map": [], "freq16": ["-fl"], "freq8": ["-fs"]}
+FORMATS = {"raw": "-r", "txt": "-t", "wig": "-w", "bed": "-bg"}  # golden folder prefix -> flag
+
+
+def _replay(genmap, case, tmp_path, host_builder=False, extra=()):
+    """tests/tests.sh for one case; one `map` call per value type writes every format at once."""
     cfg = T.CASES[case]
     folder = os.path.join(T.GOLDEN, "reference_cases", "case_" + case)
-    idx = str(tmp_path / "index")
+    idx = str(tmp_path / ("index" + "".join(extra) + ("h" if host_builder else "")))
     src = ["-FD", folder] if cfg["dir"] else ["-F", os.path.join(folder, "genome.fa")]
-    r = subprocess.run([genmap, "index"] + src + ["-I", idx] + (["-xh"] if builder == "host" else []), capture_output=True, text=True)
+    r = subprocess.run([genmap, "index"] + src + ["-I", idx] + (["-xh"] if host_builder else []), capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     base_flags = ["-K", str(cfg["K"]), "-E", str(cfg["E"])] + ([] if cfg["rc"] else ["-nc"]) + (["-ep"] if cfg["ep"] else [])
     if os.path.exists(os.path.join(folder, "subset.bed")):
         base_flags += ["-S", os.path.join(folder, "subset.bed")]
     n = 0
-    for flav, flags in FLAVOURS.items():
-        gold = os.path.join(folder, flav)
-        if not os.path.isdir(gold):
+    for vt, vflags in VALUE_TYPES.items():
+        golden = {fmt: os.path.join(folder, "%s_%s" % (fmt, vt)) for fmt in FORMATS}
+        golden = {fmt: d for fmt, d in golden.items() if os.path.isdir(d)}
+        if not golden:
             continue
-        for extra in ([], ["-xo", "1"]):  # tests.sh:47-60 re-runs with -xo: results must not change
-            out = tmp_path / (flav + "_" + "".join(extra))
-            out.mkdir()
-            r = subprocess.run([genmap, "map", "-I", idx, "-O", str(out)] + base_flags + flags + extra, capture_output=True, text=True)
-            assert r.returncode == 0, r.stderr
-            cmp = filecmp.dircmp(gold, str(out))
-            assert not cmp.left_only and not cmp.right_only, (case, flav, cmp.left_only, cmp.right_only)
-            match, mismatch, errors = filecmp.cmpfiles(gold, str(out), cmp.common_files, shallow=False)
-            assert not mismatch and not errors, (case, flav, mismatch)
+        out = tmp_path / ("out_%s_%s%s" % (vt, "".join(extra), "h" if host_builder else ""))
+        out.mkdir()
+        r = subprocess.run([genmap, "map", "-I", idx, "-O", str(out)] + base_flags + vflags + [FORMATS[f] for f in golden] + list(extra),
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        expected = set()
+        for fmt, d in golden.items():
+            names = os.listdir(d)
+            expected.update(names)
+            match, mismatch, errors = filecmp.cmpfiles(d, str(out), names, shallow=False)
+            assert not mismatch and not errors, (case, vt, fmt, mismatch, errors)
             n += len(match)
+        assert set(os.listdir(str(out))) == expected, (case, vt, set(os.listdir(str(out))) ^ expected)
     assert n > 0
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_cli_reproduces_reference_golden_directories(genmap, case, tmp_path):
+    _replay(genmap, case, tmp_path)
+
+
+@pytest.mark.parametrize("case", ["2b", "3d"])
+def test_cli_golden_with_host_built_index_and_overlap_flag(genmap, case, tmp_path):
+    _replay(genmap, case, tmp_path, host_builder=True)
+    _replay(genmap, case, tmp_path, extra=("-xo", "1"))  # tests.sh:47-60 re-runs with -xo: results must not change
 
 
 def test_cli_output_prefix_and_verbose(genmap, tmp_path):
