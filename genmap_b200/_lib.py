@@ -12,7 +12,8 @@ GMB_BUILD_WITH_SA, GMB_BUILD_ON_GPU = 1, 2
 EXPORTS = ["gmb_last_error", "gmb_version", "gmb_device_count", "gmb_index_build", "gmb_blob_free",
            "gmb_index_build_device", "gmb_blob_save", "gmb_index_open", "gmb_index_from_blob",
            "gmb_index_adopt_device", "gmb_index_close", "gmb_index_get_info", "gmb_map_frequencies",
-           "gmb_map_frequencies_range", "gmb_map_frequencies_device", "gmb_index_export_bwt", "gmb_index_export_sa", "gmb_index_set_jump_depth"]
+           "gmb_map_frequencies_range", "gmb_map_frequencies_device", "gmb_index_export_bwt", "gmb_index_export_sa", "gmb_index_set_jump_depth",
+           "gmb_index_import_reference"]
 
 
 class GmbParams(ctypes.Structure):
@@ -80,6 +81,8 @@ def lib():
                                             u64, u64, vp, ctypes.POINTER(GmbMapStats)]
     L.gmb_index_set_jump_depth.restype = ci
     L.gmb_index_set_jump_depth.argtypes = [vp, ci]
+    L.gmb_index_import_reference.restype = ci
+    L.gmb_index_import_reference.argtypes = [ctypes.c_char_p, pp, ctypes.POINTER(u64)]
     L.gmb_index_export_sa.restype = ci
     L.gmb_index_export_sa.argtypes = [vp, vp]
     L.gmb_index_export_bwt.restype = ci

@@ -61,6 +61,15 @@ class Index:
         _lib.lib().gmb_blob_free(blob)
         return out
 
+    @staticmethod
+    def import_reference_blob(directory):
+        """-> index blob converted from an index directory written by the reference's `genmap index`."""
+        blob, nbytes = ctypes.c_void_p(), ctypes.c_uint64()
+        check(_lib.lib().gmb_index_import_reference(str(directory).encode(), ctypes.byref(blob), ctypes.byref(nbytes)))
+        out = np.frombuffer(ctypes.string_at(blob, nbytes.value), dtype=np.uint8).copy()
+        _lib.lib().gmb_blob_free(blob)
+        return out
+
     @classmethod
     def build(cls, seqs, device=0, with_sa=False, on_gpu=True, seq_to_file=None):
         """Index the sequences (uint8 codes 0..3) and leave the index in HBM of `device`."""

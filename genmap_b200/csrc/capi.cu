@@ -271,14 +271,41 @@ int gmb_index_adopt_device(void* device_blob, uint64_t bytes, int device, gmb_in
     return rc;
 }
 
+int gmb_index_import_reference(const char* dir, void** blob_out, uint64_t* bytes_out)
+{
+    if (!dir || !blob_out || !bytes_out) return fail(GMB_ERR_ARG, "gmb_index_import_reference: NULL argument");
+    Blob b;
+    std::string err;
+    if (!import_reference_index(dir, b, err)) return fail(GMB_ERR_IO, err);
+    void* p = std::malloc(b.bytes);
+    if (!p) return fail(GMB_ERR_NOMEM, "out of host memory");
+    std::memcpy(p, b.data(), b.bytes);
+    *blob_out = p;
+    *bytes_out = b.bytes;
+    return GMB_OK;
+}
+
 int gmb_index_open(const char* dir, int device, gmb_index** out)
 {
     if (!dir || !out) return fail(GMB_ERR_ARG, "gmb_index_open: NULL argument");
     std::string path = std::string(dir);
     if (!path.empty() && path.back() != '/') path += '/';
+    const std::string ref_probe = path + "index.lf.drv";
     path += "index.gmb";
     FILE* f = std::fopen(path.c_str(), "rb");
-    if (!f) return fail(GMB_ERR_IO, "cannot open " + path);
+    if (!f) {
+        if (FILE* r = std::fopen(ref_probe.c_str(), "rb")) { // an index written by the reference itself
+            std::fclose(r);
+            void* blob = nullptr;
+            uint64_t bytes = 0;
+            int rc = gmb_index_import_reference(dir, &blob, &bytes);
+            if (rc != GMB_OK) return rc;
+            rc = gmb_index_from_blob(blob, bytes, device, out);
+            std::free(blob);
+            return rc;
+        }
+        return fail(GMB_ERR_IO, "cannot open " + path);
+    }
     std::fseek(f, 0, SEEK_END);
     const long long sz = std::ftell(f);
     std::fseek(f, 0, SEEK_SET);

@@ -292,12 +292,26 @@ const char* kMapHelp =
 
 struct IdRow { std::string file; uint64_t length; std::string name; };
 
+// rows of index.ids; `path` is our text file or, for an index written by the reference itself, the SeqAn
+// string set index.ids.concat + index.ids.limits (uint64 offsets)
 bool load_ids(const std::string& path, std::vector<IdRow>& rows)
 {
+    std::vector<std::string> lines;
     std::ifstream in(path);
-    if (!in) return false;
-    std::string line;
-    while (std::getline(in, line)) {
+    if (in) {
+        std::string l;
+        while (std::getline(in, l)) lines.push_back(l);
+    } else {
+        std::ifstream concat(path + ".concat", std::ios::binary), limits(path + ".limits", std::ios::binary);
+        if (!concat || !limits) return false;
+        std::string all((std::istreambuf_iterator<char>(concat)), std::istreambuf_iterator<char>());
+        std::vector<uint64_t> lim;
+        uint64_t v;
+        while (limits.read(reinterpret_cast<char*>(&v), 8)) lim.push_back(v);
+        for (size_t i = 0; i + 1 < lim.size(); ++i)
+            if (lim[i + 1] <= all.size() && lim[i] <= lim[i + 1]) lines.push_back(all.substr(lim[i], lim[i + 1] - lim[i]));
+    }
+    for (const std::string& line : lines) {
         if (line.empty()) continue;
         const size_t s1 = line.find(';'), s2 = line.find(';', s1 + 1); // src/common.hpp:10-19
         if (s1 == std::string::npos || s2 == std::string::npos) return false;
@@ -355,6 +369,7 @@ int map_main(int argc, char const** argv)
     std::string info_line, info;
     {
         std::ifstream in(index_dir + "index.info");
+        if (!in) in.open(index_dir + "index.info.concat"); // an index written by the reference itself
         if (!in) { std::cerr << "ERROR: cannot open the index at " << index_dir << " (index.info missing)\n"; return 1; }
         while (std::getline(in, info_line)) info += info_line + "\n";
     }

@@ -2,6 +2,7 @@
 #include "gmb_host.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 
 #include "sais.hpp"
@@ -238,6 +239,91 @@ bool build_index_host(const uint8_t* codes, const uint64_t* limits, uint32_t n_s
     for (uint64_t i = 0; i < n_text; ++i) text[i >> 5] |= (uint64_t)codes[i] << (2 * (i & 31));
     uint64_t* lim = reinterpret_cast<uint64_t*>(base + h.off_limits);
     uint32_t* sst = reinterpret_cast<uint32_t*>(base + h.off_seq_start);
+    for (uint32_t s = 0; s <= n_seq; ++s) { lim[s] = limits[s]; sst[s] = (uint32_t)(limits[s] + s); }
+    return true;
+}
+
+namespace {
+
+bool slurp(const std::string& path, std::vector<uint8_t>& out)
+{
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::fseek(f, 0, SEEK_END);
+    const long long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    out.resize(sz > 0 ? (size_t)sz : 0);
+    const size_t r = out.empty() ? 0 : std::fread(out.data(), 1, out.size(), f);
+    std::fclose(f);
+    return r == out.size();
+}
+
+// SeqAn fibres of one direction -> BWT symbols (0/1 = sentinel, 2..5 = A,C,G,T as pack_bwt_blocks expects)
+bool decode_reference_bwt(const std::string& prefix, uint64_t n, std::vector<uint8_t>& bwt, std::string& err)
+{
+    std::vector<uint8_t> drv, drp;
+    if (!slurp(prefix + ".drv", drv) || !slurp(prefix + ".drp", drp)) { err = "cannot read " + prefix + ".drv/.drp"; return false; }
+    if (drv.size() != (n + 31) / 32 * 14 || drp.size() != (n + 63) / 64 * 10) {
+        err = "unsupported reference index: expected 14-byte rank entries (Dna4 alphabet, 32-bit BWT dimensions)";
+        return false;
+    }
+    bwt.resize(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t w, s;
+        std::memcpy(&w, drv.data() + (i / 32) * 14, 8); // 32 values per word, value k in bits 62-2k
+        std::memcpy(&s, drp.data() + (i / 64) * 10, 8); // sentinel marker bits, bit k at 63-k
+        const uint32_t v = (uint32_t)(w >> (62 - 2 * (i % 32))) & 3u;
+        bwt[i] = ((s >> (63 - (i % 64))) & 1u) ? 1 : (uint8_t)(v + 2);
+    }
+    return true;
+}
+
+} // namespace
+
+bool import_reference_index(const std::string& dir, Blob& blob, std::string& err)
+{
+    std::string base = dir;
+    if (!base.empty() && base.back() != '/') base += '/';
+    base += "index";
+    std::vector<uint8_t> info, limits_raw, text_raw;
+    if (!slurp(base + ".info.concat", info)) { err = "cannot read " + base + ".info.concat"; return false; }
+    const std::string info_s(info.begin(), info.end());
+    if (info_s.find("alphabet_size:4") == std::string::npos) { err = "only Dna4 reference indices can be imported (alphabet_size:4)"; return false; }
+    if (info_s.find("bwt_dimensions:32") == std::string::npos || info_s.find("sa_dimensions_i1:16") == std::string::npos) {
+        err = "only the (16,32,32) reference index class can be imported";
+        return false;
+    }
+    if (!slurp(base + ".txt.limits", limits_raw) || limits_raw.size() < 16 || limits_raw.size() % 8) { err = "cannot read " + base + ".txt.limits"; return false; }
+    const uint32_t n_seq = (uint32_t)(limits_raw.size() / 8 - 1);
+    std::vector<uint64_t> limits(n_seq + 1);
+    std::memcpy(limits.data(), limits_raw.data(), limits_raw.size());
+    const uint64_t n_text = limits[n_seq], n = n_text + n_seq;
+    if (n_seq > kMaxSeq || n >= 0xFFFFFFFFull) { err = "reference index too large for the 32-bit HBM layout"; return false; }
+    if (!slurp(base + ".txt.concat", text_raw) || text_raw.size() != ((n_text + 31) / 32 + 1) * 8) { err = "cannot read " + base + ".txt.concat (packed text expected)"; return false; }
+
+    BlobPlan plan = plan_blob(n_text, n_seq, false);
+    blob.resize(plan.h.total_bytes);
+    uint8_t* b = blob.data();
+    IndexHeader& h = *reinterpret_cast<IndexHeader*>(b);
+    h = plan.h;
+    uint64_t tot[4] = {0, 0, 0, 0};
+    std::vector<uint8_t> bwt;
+    for (int rev = 0; rev < 2; ++rev) {
+        if (!decode_reference_bwt(base + (rev ? ".rev.lf" : ".lf"), n, bwt, err)) return false;
+        pack_bwt_blocks(bwt.data(), n, reinterpret_cast<RankBlock*>(b + (rev ? h.off_rev : h.off_fwd)), h.n_blocks,
+                        reinterpret_cast<uint32_t*>(b + (rev ? h.off_sent_rev : h.off_sent_fwd)), n_seq, tot);
+    }
+    h.C[0] = n_seq;
+    for (int c = 0; c < 4; ++c) h.C[c + 1] = h.C[c] + tot[c];
+    uint64_t* text = reinterpret_cast<uint64_t*>(b + h.off_text);
+    const uint8_t* words = text_raw.data() + 8; // first word = length
+    for (uint64_t i = 0; i < n_text; ++i) {
+        uint64_t w;
+        std::memcpy(&w, words + (i / 32) * 8, 8);
+        text[i >> 5] |= ((w >> (62 - 2 * (i % 32))) & 3ull) << (2 * (i & 31));
+    }
+    uint64_t* lim = reinterpret_cast<uint64_t*>(b + h.off_limits);
+    uint32_t* sst = reinterpret_cast<uint32_t*>(b + h.off_seq_start);
     for (uint32_t s = 0; s <= n_seq; ++s) { lim[s] = limits[s]; sst[s] = (uint32_t)(limits[s] + s); }
     return true;
 }

@@ -54,6 +54,12 @@ void pack_bwt_blocks(const uint8_t* bwt, uint64_t n, RankBlock* blocks, uint32_t
 bool build_index_host(const uint8_t* codes, const uint64_t* limits, uint32_t n_seq, bool with_sa, Blob& blob,
                       std::string& err);
 
+// Import an index written by the reference's own `genmap index` (SeqAn fibres index.lf.drv/.drp,
+// index.rev.lf.*, index.txt.*, index.lf.pst; src/genmap_helper.hpp:71-98 lists what `map` opens) into the
+// HBM blob layout, so that pre-built GenMap indices can be used as they are.  Dna4, (16,32,32) index
+// class only; the sampled suffix array is not imported (no --exclude-pseudo on imported indices).
+bool import_reference_index(const std::string& dir, Blob& blob, std::string& err);
+
 // Positions whose k-mer is actually searched: inside a sequence with at least K bases left
 // (everything else stays 0: resetLimits, src/algo.hpp:10-22), inside a selection interval if any
 // (src/algo.hpp:441-476), inside [pos_begin, pos_end) (multi-GPU sharding).  Sorted, disjoint.

@@ -100,6 +100,10 @@ int gmb_blob_save(const void *blob, uint64_t bytes, const char *path);
  * (<dir>/index.gmb), from a host blob (copied to HBM) or by adopting a blob that already sits in
  * device memory (e.g. after an NCCL broadcast; not freed by gmb_index_close). */
 int gmb_index_open(const char *dir, int device, gmb_index **out);
+/* Convert an index directory written by the reference's own `genmap index` (SeqAn fibres) into a host
+ * blob (release with gmb_blob_free).  gmb_index_open does this automatically when <dir>/index.gmb is
+ * absent but <dir>/index.lf.drv exists.  Dna4 indices of the default (16,32,32) width class only. */
+int gmb_index_import_reference(const char *dir, void **blob_out, uint64_t *bytes_out);
 int gmb_index_from_blob(const void *host_blob, uint64_t bytes, int device, gmb_index **out);
 int gmb_index_adopt_device(void *device_blob, uint64_t bytes, int device, gmb_index **out);
 int gmb_index_close(gmb_index *idx);

@@ -79,3 +79,24 @@ def test_cli_output_prefix_and_verbose(genmap, tmp_path):
     assert "Mappability computed in" in r.stdout
     assert filecmp.cmp(str(tmp_path / "myprefix.freq16"), os.path.join(folder, "raw_freq16", "genome.genmap.freq16"), shallow=False)
     assert os.path.exists(str(tmp_path / "myprefix.txt"))
+
+
+def test_cli_maps_on_an_index_written_by_the_reference(genmap, tmp_path):
+    """Pre-built GenMap indices are usable as they are: `genmap_ref index` -> our `genmap map`."""
+    if not T.have_reference():
+        pytest.skip("oracle/_ref/genmap_ref not present")
+    for case in ("2b", "3b"):
+        cfg = T.CASES[case]
+        folder = os.path.join(T.GOLDEN, "reference_cases", "case_" + case)
+        idx = str(tmp_path / ("refindex_" + case))
+        src = ["-FD", folder] if cfg["dir"] else ["-F", os.path.join(folder, "genome.fa")]
+        subprocess.run([T.REF_BIN, "index"] + src + ["-I", idx], check=True, stdout=subprocess.DEVNULL)
+        out = tmp_path / ("out_" + case)
+        out.mkdir()
+        r = subprocess.run([genmap, "map", "-I", idx, "-O", str(out), "-K", str(cfg["K"]), "-E", str(cfg["E"]), "-r", "-fl", "-w"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        for sub in ("raw_freq16", "wig_freq16"):
+            names = os.listdir(os.path.join(folder, sub))
+            match, mismatch, errors = filecmp.cmpfiles(os.path.join(folder, sub), str(out), names, shallow=False)
+            assert not mismatch and not errors, (case, sub, mismatch, errors)

@@ -44,3 +44,19 @@ def test_writer_is_byte_identical_to_reference_index(tmp_path, seed, nchr, lengt
     for fi, (fn, _) in enumerate(files):
         got = np.fromfile(str(out / (fn[:-3] + ".genmap.freq16")), dtype=np.uint16)
         assert np.array_equal(got, orc.map(20, 1, file_no=fi))
+
+
+@pytest.mark.parametrize("seed,nchr,length", [(15, 3, 1000), (16, 2, 70000)])
+def test_importing_a_reference_built_index_gives_our_own_blob(tmp_path, seed, nchr, length):
+    """`genmap_ref index` -> gmb_index_import_reference must equal the blob our own builder makes from the FASTA."""
+    import genmap_b200
+    seqs = T.repeat_rich(seed, nchr, length)
+    fa = str(tmp_path / "genome.fa")
+    T.write_fasta(fa, seqs)
+    ref_dir = str(tmp_path / "ref_index")
+    subprocess.run([T.REF_BIN, "index", "-F", fa, "-I", ref_dir], check=True, stdout=subprocess.DEVNULL)
+    imported = genmap_b200.Index.import_reference_blob(ref_dir)
+    ours = genmap_b200.Index.build_blob(seqs, with_sa=False)
+    assert imported.tobytes() == ours.tobytes()
+    with pytest.raises(genmap_b200.GenmapError):
+        genmap_b200.Index.import_reference_blob(str(tmp_path / "nowhere"))
