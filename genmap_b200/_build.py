@@ -43,7 +43,7 @@ def build_cli(force=False, verbose=False):
         return CLI
     os.makedirs(BIN_DIR, exist_ok=True)
     cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-o", CLI + ".tmp", srcs[0], "-L" + LIB_DIR, "-lgenmap_b200",
-           "-Wl,-rpath,$ORIGIN/../lib"]
+           "-Wl,-rpath,$ORIGIN/../lib", "-pthread"]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

@@ -20,6 +20,7 @@
 #include <set>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/genmap_b200.h"
@@ -288,7 +289,8 @@ const char* kMapHelp =
     "  -I, --index   -O, --output   -K, --length   -E, --errors (0..4)   -S, --selection\n"
     "  -nc, --no-reverse-complement   -ep, --exclude-pseudo   -fs, --frequency-small   -fl, --frequency-large\n"
     "  -r, --raw   -t, --txt   -w, --wig   -bg, --bedgraph   -d, --csv   -m, --memory-mapping (ignored)\n"
-    "  -T, --threads (host writers only)   -v, --verbose\n";
+    "  -T, --threads (host writers only)   -v, --verbose\n"
+    "  -xg, --gpus N   range-partition the positions of every FASTA file over N GPUs (index replicated; default 1)\n";
 
 struct IdRow { std::string file; uint64_t length; std::string name; };
 
@@ -327,7 +329,7 @@ int map_main(int argc, char const** argv)
                                   {"fs", "frequency-small", false}, {"fl", "frequency-large", false}, {"r", "raw", false},
                                   {"t", "txt", false}, {"w", "wig", false}, {"bg", "bedgraph", false}, {"b", "bed", false},
                                   {"d", "csv", false}, {"m", "memory-mapping", false}, {"T", "threads", true},
-                                  {"v", "verbose", false}, {"xo", "overlap", true}, {"xg", "gpu", true}};
+                                  {"v", "verbose", false}, {"xo", "overlap", true}, {"xg", "gpus", true}};
     Args a;
     int rc = parse_args("GenMap map", specs, argc, argv, a, kMapHelp);
     if (rc == 2) return 0;
@@ -342,7 +344,8 @@ int map_main(int argc, char const** argv)
     if (!to_uint(a.val["length"], K)) { std::cerr << "GenMap map: the given value '" << a.val["length"] << "' cannot be casted to integer\n"; return 1; }
     if (a.has("errors") && !to_uint(a.val["errors"], E)) { std::cerr << "GenMap map: the given value '" << a.val["errors"] << "' cannot be casted to integer\n"; return 1; }
     if (a.has("threads") && !to_uint(a.val["threads"], T)) { std::cerr << "GenMap map: the given value '" << a.val["threads"] << "' cannot be casted to integer\n"; return 1; }
-    if (a.has("gpu")) to_uint(a.val["gpu"], gpu);
+    if (a.has("gpus") && (!to_uint(a.val["gpus"], gpu) || gpu == 0)) { std::cerr << "GenMap map: --gpus needs a positive integer\n"; return 1; }
+    if (!a.has("gpus")) gpu = 1;
     const bool raw = a.has("raw"), txt = a.has("txt"), wig = a.has("wig"), bg = a.has("bedgraph"), bed = a.has("bed"), csv = a.has("csv");
     if (!wig && !bg && !bed && !raw && !txt && !csv) {
         std::cerr << "ERROR: Please choose at least one output format (i.e., --wig, --bedgraph, --bed, --raw, --txt, --csv).\n";
@@ -418,12 +421,14 @@ int map_main(int argc, char const** argv)
     }
 
     if (gmb_device_count() == 0) { std::cerr << "ERROR: no CUDA device found: the B200 build of `genmap map` has no CPU fallback.\n"; return 1; }
-    gmb_index* ix = nullptr;
-    if (gmb_index_open(index_dir.c_str(), (int)gpu, &ix) != GMB_OK) { std::cerr << "ERROR: " << gmb_last_error() << "\n"; return 1; }
+    if ((int)gpu > gmb_device_count()) { std::cerr << "ERROR: --gpus " << gpu << " requested but only " << gmb_device_count() << " CUDA device(s) found.\n"; return 1; }
+    std::vector<gmb_index*> ixs(gpu, nullptr); // the index is replicated: one copy in the HBM of every GPU
+    for (uint64_t g = 0; g < gpu; ++g)
+        if (gmb_index_open(index_dir.c_str(), (int)g, &ixs[g]) != GMB_OK) { std::cerr << "ERROR: " << gmb_last_error() << "\n"; return 1; }
     gmb_index_info iinfo;
-    gmb_index_get_info(ix, &iinfo);
+    gmb_index_get_info(ixs[0], &iinfo);
     if (a.has("verbose")) {
-        std::cout << "Index was loaded (dna4 alphabet, " << iinfo.blob_bytes << " bytes in HBM of GPU " << gpu << ").\n";
+        std::cout << "Index was loaded (dna4 alphabet, " << iinfo.blob_bytes << " bytes in the HBM of " << gpu << " GPU(s)).\n";
         std::cout << (directory ? "- Index was built on an entire directory.\n" : "- Index was built on a single fasta file.\n") << std::flush;
     }
 
@@ -472,12 +477,20 @@ int map_main(int argc, char const** argv)
         if (!(has_selection && iv.empty())) { // :309 — files without selected intervals produce no output
             std::vector<uint8_t> c(text_len * (p.value_bits / 8));
             static_assert(sizeof(std::pair<uint64_t, uint64_t>) == 16, "interval layout");
-            if (gmb_map_frequencies(ix, &p, start_pos, text_len, cum.data(), (uint32_t)lens.size(),
-                                    reinterpret_cast<const uint64_t (*)[2]>(iv.data()), iv.size(), seq_to_file.data(),
-                                    (uint32_t)seq_to_file.size(), c.data(), nullptr) != GMB_OK) {
-                std::cerr << "ERROR: " << gmb_last_error() << "\n";
-                return 1;
-            }
+            // positions are range-partitioned over the GPUs; every GPU fills its own slice of c
+            std::vector<std::string> errors(gpu);
+            std::vector<std::thread> workers;
+            for (uint64_t g = 0; g < gpu; ++g)
+                workers.emplace_back([&, g] {
+                    const uint64_t b = text_len * g / gpu, e = text_len * (g + 1) / gpu;
+                    if (gmb_map_frequencies_range(ixs[g], &p, start_pos, text_len, cum.data(), (uint32_t)lens.size(),
+                                                  reinterpret_cast<const uint64_t (*)[2]>(iv.data()), iv.size(), seq_to_file.data(),
+                                                  (uint32_t)seq_to_file.size(), b, e, c.data() + b * (p.value_bits / 8), nullptr) != GMB_OK)
+                        errors[g] = gmb_last_error();
+                });
+            for (std::thread& w : workers) w.join();
+            for (const std::string& e : errors)
+                if (!e.empty()) { std::cerr << "ERROR: " << e << "\n"; return 1; }
             if (total_files == 1) std::cout << "\rProgress: 100.00%\x1b[K\n" << std::flush;
             else {
                 std::cout << "\rFile " << file_no << " / " << total_files << ". Progress: 100.00 %\x1b[K" << std::flush;
@@ -493,7 +506,7 @@ int map_main(int argc, char const** argv)
         i = j;
     }
     if (a.has("verbose")) std::cout << "Mappability computed in " << round2(wall() - t_start) << " seconds\n";
-    gmb_index_close(ix);
+    for (gmb_index* ix : ixs) gmb_index_close(ix);
     return 0;
 }
 

@@ -100,3 +100,24 @@ def test_cli_maps_on_an_index_written_by_the_reference(genmap, tmp_path):
             names = os.listdir(os.path.join(folder, sub))
             match, mismatch, errors = filecmp.cmpfiles(os.path.join(folder, sub), str(out), names, shallow=False)
             assert not mismatch and not errors, (case, sub, mismatch, errors)
+
+
+def test_cli_multi_gpu_sharding_gives_identical_files(genmap, tmp_path):
+    from genmap_b200 import _lib
+    if _lib.lib().gmb_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import genmap_b200 as gm
+    fa = str(tmp_path / "g.fa")
+    T.write_fasta(fa, gm.synth_genome(600_000, 3, 3))
+    idx = str(tmp_path / "index")
+    assert subprocess.run([genmap, "index", "-F", fa, "-I", idx]).returncode == 0
+    outs = []
+    for n in (1, 2):
+        out = tmp_path / ("out%d" % n)
+        out.mkdir()
+        r = subprocess.run([genmap, "map", "-I", idx, "-O", str(out), "-K", "30", "-E", "1", "-r", "-fl", "-bg", "-xg", str(n)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append(out)
+    for name in os.listdir(str(outs[0])):
+        assert filecmp.cmp(str(outs[0] / name), str(outs[1] / name), shallow=False), name
