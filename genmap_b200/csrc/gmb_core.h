@@ -40,16 +40,18 @@ GMB_HD BlockRegs load_block(const RankBlock* p)
 {
     BlockRegs b;
 #if defined(__CUDA_ARCH__)
-    // 32 bytes per 256-bit read-only load (LDG.E.256 on sm_100a): one load for a 32-byte block, two for 64
+    // 32 bytes per 256-bit read-only load (LDG.E.256 on sm_100a): one load for a 32-byte block, two for 64.
+    // L2::64B: without the hint a 256-bit load makes the memory system fetch the whole 128-byte line
+    // (measured: 2.9 DRAM sectors per requested sector; 1.45 with the hint — profiles/r01/s5_ldflavor_ncu.csv)
     uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
-    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
                  : "l"(p));
     b.h[0] = r0; b.h[1] = r1; b.h[2] = r2; b.h[3] = r3;
     b.p0[0] = r4; b.p0[1] = r5; b.p1[0] = r6; b.p1[1] = r7;
     if constexpr (kBlockWords == 3) {
         uint32_t s0, s1, s2, s3, s4, s5, s6, s7;
-        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        asm volatile("ld.global.nc.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7)
                      : "l"(reinterpret_cast<const char*>(p) + 32));
         b.p0[kPieces - 4] = s0; b.p0[kPieces - 3] = s1; b.p1[kPieces - 4] = s2; b.p1[kPieces - 3] = s3;
@@ -72,13 +74,13 @@ GMB_HD void load_block_if(BlockRegs& b, const RankBlock* p, bool pred)
 #if defined(__CUDA_ARCH__)
     asm volatile(
         "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
-        "@q ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+        "@q ld.global.nc.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
         : "+r"(b.h[0]), "+r"(b.h[1]), "+r"(b.h[2]), "+r"(b.h[3]), "+r"(b.p0[0]), "+r"(b.p0[1]), "+r"(b.p1[0]), "+r"(b.p1[1])
         : "l"(p), "r"((uint32_t)pred));
     if constexpr (kBlockWords == 3) {
         asm volatile(
             "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
-            "@q ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+32];\n\t}"
+            "@q ld.global.nc.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+32];\n\t}"
             : "+r"(b.p0[kPieces - 4]), "+r"(b.p0[kPieces - 3]), "+r"(b.p1[kPieces - 4]), "+r"(b.p1[kPieces - 3]),
               "+r"(b.p0[kPieces - 2]), "+r"(b.p0[kPieces - 1]), "+r"(b.p1[kPieces - 2]), "+r"(b.p1[kPieces - 1])
             : "l"(p), "r"((uint32_t)pred));
@@ -323,9 +325,9 @@ constexpr int kFrameWords = 10;
 GMB_HD void jump_lookup(const SearchStart& S, uint32_t key, uint32_t& lo_f, uint32_t& lo_r, uint32_t& size)
 {
 #if defined(__CUDA_ARCH__)
-    const uint2 e = __ldg(reinterpret_cast<const uint2*>(S.uni) + key);
-    lo_r = e.x; size = e.y;
-    lo_f = S.lof ? __ldg(S.lof + key) : 0u;
+    asm volatile("ld.global.nc.L2::64B.v2.u32 {%0,%1}, [%2];" : "=r"(lo_r), "=r"(size) : "l"(S.uni + key));
+    lo_f = 0u;
+    if (S.lof) asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(lo_f) : "l"(S.lof + key));
 #else
     lo_r = S.uni[key].lo_r; size = S.uni[key].size;
     lo_f = S.lof ? S.lof[key] : 0u;
