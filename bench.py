@@ -390,7 +390,8 @@ def main():
     def roofline(r):
         if "fetches" not in r:
             return None
-        per_launch = r["fetches"] * 64.0 / len(r["batches"])
+        blk = float(ix.info.rank_block_bytes)  # 32: one sector per rank boundary
+        per_launch = r["fetches"] * blk / len(r["batches"])
         achieved = per_launch / (r["kernel_ms"] * 1e-3) / 1e9
         traffic = None
         try:
@@ -402,9 +403,14 @@ def main():
             pass
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "rank_block_bytes_per_position": r["fetches"] * 64.0 / max(r["searched"], 1),
+                "rank_block_bytes": blk,
+                "rank_block_bytes_per_position": r["fetches"] * blk / max(r["searched"], 1),
                 # stricter figure: + jump-table entries (12 B) + pattern text (K/4 -> 16 B) + result (2 B)
-                "total_algorithmic_bytes_per_position": (r["fetches"] * 64.0 + r["lut_reads"] * 12.0) / max(r["searched"], 1) + 18.0,
+                "total_algorithmic_bytes_per_position": (r["fetches"] * blk + r["lut_reads"] * 12.0) / max(r["searched"], 1) + 18.0,
+                # the path is bound by the RATE of dependent random memory requests, not by their bytes: one request
+                # per rank block / jump-table entry; ceiling measured with tools/randread.cu (profiles/r01/s1_randread.txt)
+                "random_requests_per_s": (r["fetches"] + r["lut_reads"]) / len(r["batches"]) / (r["kernel_ms"] * 1e-3),
+                "random_request_ceiling_per_s": 38.0e9,
                 "jump_table_depth": r["jump_depth"], "kernel_ms_per_launch": r["kernel_ms"]}
 
     main_r["E"], main_r["batch"] = E, batch
