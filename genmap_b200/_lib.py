@@ -19,7 +19,7 @@ EXPORTS = ["gmb_last_error", "gmb_version", "gmb_device_count", "gmb_index_build
 class GmbParams(ctypes.Structure):
     _fields_ = [("K", ctypes.c_uint32), ("E", ctypes.c_uint32), ("revcompl", ctypes.c_uint32),
                 ("exclude_pseudo", ctypes.c_uint32), ("value_bits", ctypes.c_uint32),
-                ("count_fetches", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 2)]
+                ("count_fetches", ctypes.c_uint32), ("block_kmers", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 class GmbIndexInfo(ctypes.Structure):

@@ -30,9 +30,10 @@ def _concat(seqs):
 class SearchParams:
     """src/common.hpp:67-74 (length, revCompl, excludePseudo) + Options.errors / value type."""
 
-    def __init__(self, length, errors=0, rev_compl=True, exclude_pseudo=False, value_bits=16):
+    def __init__(self, length, errors=0, rev_compl=True, exclude_pseudo=False, value_bits=16, block_kmers=0):
         self.length, self.errors, self.rev_compl = int(length), int(errors), bool(rev_compl)
         self.exclude_pseudo, self.value_bits = bool(exclude_pseudo), int(value_bits)
+        self.block_kmers = int(block_kmers)  # k-mers per block (K - overlap + 1 in the reference); 0 = default
 
 
 class Index:
@@ -139,7 +140,7 @@ class Index:
         returns the frequency vector c (uint8 / uint16, one value per text position) in host memory."""
         tb, tl, cum, iv = self._file_args(text_begin, text_len, chrom_cum_lengths, intervals)
         p = GmbParams(params.length, params.errors, int(params.rev_compl), int(params.exclude_pseudo),
-                      params.value_bits, int(count_fetches))
+                      params.value_bits, int(count_fetches), params.block_kmers)
         out = np.zeros(tl, dtype=np.uint16 if params.value_bits == 16 else np.uint8)
         st = GmbMapStats()
         check(_lib.lib().gmb_map_frequencies(self._h, ctypes.byref(p), tb, tl, _ptr(cum), len(cum) - 1, _ptr(iv),
@@ -154,7 +155,7 @@ class Index:
         e.g. a view of pinned memory)."""
         tb, tl, cum, iv = self._file_args(text_begin, text_len, chrom_cum_lengths, intervals)
         p = GmbParams(params.length, params.errors, int(params.rev_compl), int(params.exclude_pseudo),
-                      params.value_bits, 0)
+                      params.value_bits, 0, params.block_kmers)
         dt = np.uint16 if params.value_bits == 16 else np.uint8
         if out is None:
             out = np.zeros(int(pos_end) - int(pos_begin), dtype=dt)
@@ -189,7 +190,7 @@ class Index:
         `out_ptr` (text_len elements, zero-filled by the caller) on CUDA stream `stream`."""
         tb, tl, cum, iv = self._file_args(text_begin, text_len, chrom_cum_lengths, intervals)
         p = GmbParams(params.length, params.errors, int(params.rev_compl), int(params.exclude_pseudo),
-                      params.value_bits, int(count_fetches))
+                      params.value_bits, int(count_fetches), params.block_kmers)
         st = GmbMapStats()
         check(_lib.lib().gmb_map_frequencies_device(
             self._h, ctypes.byref(p), tb, tl, _ptr(cum), len(cum) - 1, _ptr(iv), 0 if iv is None else len(iv),

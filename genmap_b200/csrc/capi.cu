@@ -68,7 +68,7 @@ struct gmb_index {
     std::vector<uint64_t> limits; // host copy
     // per-handle scratch, grown on demand
     unsigned long long* d_counters = nullptr; // [0] work counter, [1] fetch counter
-    uint32_t* d_steps = nullptr;
+    uint32_t* d_steps = nullptr; // search tables of the current call (kTableBytes)
     uint64_t* d_ranges = nullptr;
     size_t ranges_cap = 0;
     void* d_out = nullptr;
@@ -83,6 +83,8 @@ struct gmb_index {
 
 namespace {
 constexpr uint32_t kJumpKeep = 12; // all levels up to here together take < 300 MB
+constexpr size_t kTableBytes = 256 << 10; // device scratch for the search tables of one call
+
 
 void fill_ctx(const gmb_index* ix, MapCtx& cx)
 {
@@ -93,9 +95,9 @@ void fill_ctx(const gmb_index* ix, MapCtx& cx)
     cx.sent[1] = reinterpret_cast<const uint32_t*>(base + ix->h.off_sent_rev);
     for (int c = 0; c < 4; ++c) cx.C[c] = (uint32_t)ix->h.C[c];
     cx.n_bwt = (uint32_t)ix->h.n_bwt;
-    cx.steps = nullptr;
+    cx.steps = nullptr; cx.p1_off = nullptr; cx.fl_off = nullptr;
     cx.starts = nullptr;
-    cx.K = 0; cx.n_search = 0; cx.n_strands = 1; cx.maxv = 65535u;
+    cx.K = 0; cx.B = 1; cx.n_search = 0; cx.n_strands = 1; cx.maxv = 65535u;
     cx.sa = ix->h.off_sa ? reinterpret_cast<const uint32_t*>(base + ix->h.off_sa) : nullptr;
     cx.seq_start = reinterpret_cast<const uint32_t*>(base + ix->h.off_seq_start);
     cx.seq_to_file = nullptr;
@@ -103,13 +105,14 @@ void fill_ctx(const gmb_index* ix, MapCtx& cx)
 }
 
 // make sure the tables of every depth in `plan` exist on the device (built level by level, cached)
-int ensure_jump_tables(gmb_index* ix, const JumpPlan& plan, cudaStream_t stream)
+int ensure_jump_tables(gmb_index* ix, const std::vector<JumpPlan>& plans, cudaStream_t stream)
 {
     bool need_uni[17] = {}, need_lof[17] = {};
-    for (uint32_t s = 0; s < kMaxSearches; ++s) {
-        const uint32_t d = plan.depth[s];
-        if (d) { need_uni[d] = true; need_lof[d] = need_lof[d] || plan.need_lof[s]; }
-    }
+    for (const JumpPlan& plan : plans)
+        for (uint32_t s = 0; s < kMaxSearches; ++s) {
+            const uint32_t d = plan.depth[s];
+            if (d) { need_uni[d] = true; need_lof[d] = need_lof[d] || plan.need_lof[s]; }
+        }
     uint32_t top = 0, lof_top = 0;
     for (uint32_t d = 1; d <= 16; ++d) {
         if (need_uni[d] && (!ix->jt_uni[d] || (need_lof[d] && !ix->jt_lof[d]))) top = d;
@@ -200,7 +203,7 @@ static int finish_open(gmb_index* ix, gmb_index** out)
     ix->limits.resize((size_t)ix->h.n_seq + 1);
     CU(cudaMemcpy(ix->limits.data(), ix->d_blob + ix->h.off_limits, ix->limits.size() * 8, cudaMemcpyDeviceToHost));
     CU(cudaMalloc(&ix->d_counters, 4 * sizeof(unsigned long long)));
-    CU(cudaMalloc(&ix->d_steps, sizeof(uint32_t) * kMaxSearches * (kMaxK + 1)));
+    CU(cudaMalloc(&ix->d_steps, kTableBytes));
     CU(cudaEventCreate(&ix->ev0));
     CU(cudaEventCreate(&ix->ev1));
     *out = ix;
@@ -389,10 +392,16 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
     }
     if (n_intervals && !intervals) return fail(GMB_ERR_ARG, "intervals is NULL");
     std::string err;
-    std::unique_ptr<StepTables> tabs_owner(new (std::nothrow) StepTables);
-    StepTables* tabs = tabs_owner.get();
-    if (!tabs) return fail(GMB_ERR_NOMEM, "out of host memory");
-    if (!build_step_tables(p->K, p->E, *tabs, err, p->exclude_pseudo != 0)) return fail(GMB_ERR_UNSUPPORTED, err);
+    BlockTables tabs;
+    {
+        uint32_t want_b = p->block_kmers;
+        if (want_b == 0) { const char* env = std::getenv("GMB_BLOCK_KMERS"); if (env && *env) want_b = (uint32_t)std::atoi(env); }
+        if (!build_block_tables(p->K, p->E, want_b, p->exclude_pseudo != 0, tabs, err)) return fail(GMB_ERR_UNSUPPORTED, err);
+        // the tables and the per-chain frame store live in shared memory: shrink the block if they do not fit
+        while (tabs.B > 1 && (map_kernel_smem_bytes((uint32_t)tabs.steps.size(), p->E, tabs.B, p->exclude_pseudo != 0) > (200u << 10) ||
+                              tabs.steps.size() * 4 + (tabs.B + 1) * kMaxSearches * sizeof(SearchStart) > kTableBytes))
+            if (!build_block_tables(p->K, p->E, tabs.B - 1, p->exclude_pseudo != 0, tabs, err)) return fail(GMB_ERR_UNSUPPORTED, err);
+    }
     CU(cudaSetDevice(ix->device));
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
 
@@ -400,6 +409,7 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
     build_work_ranges(text_len, p->K, chrom_cum, n_chrom, reinterpret_cast<const uint64_t*>(intervals), n_intervals,
                       pos_begin, pos_end, ranges);
     const uint32_t nr = (uint32_t)ranges.size();
+    const uint64_t chunk = std::max<uint64_t>(tabs.B, kChunk / tabs.B * tabs.B); // whole blocks per work chunk
     std::vector<uint64_t> host_ranges(3 * (size_t)nr + 1); // begin[nr], end[nr], chunk_prefix[nr+1]
     uint64_t total = 0, chunks = 0;
     for (uint32_t i = 0; i < nr; ++i) {
@@ -407,7 +417,7 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
         host_ranges[nr + i] = ranges[i].end;
         host_ranges[2 * (size_t)nr + i] = chunks;
         total += ranges[i].end - ranges[i].begin;
-        chunks += (ranges[i].end - ranges[i].begin + kChunk - 1) / kChunk;
+        chunks += (ranges[i].end - ranges[i].begin + chunk - 1) / chunk;
     }
     host_ranges[3 * (size_t)nr] = chunks;
     if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->positions = total; }
@@ -420,14 +430,14 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
         CU(cudaMalloc(&ix->d_ranges, ix->ranges_cap * 8));
     }
     CU(cudaMemcpyAsync(ix->d_ranges, host_ranges.data(), host_ranges.size() * 8, cudaMemcpyHostToDevice, stream));
-    CU(cudaMemcpyAsync(ix->d_steps, tabs->step, sizeof(uint32_t) * tabs->n_search * p->K, cudaMemcpyHostToDevice, stream));
     CU(cudaMemsetAsync(ix->d_counters, 0, 3 * sizeof(unsigned long long), stream));
-    // the two staging copies above read pageable host memory: they have completed (staged) on return
 
     MapLaunch L;
     const uint8_t* base = ix->d_blob;
     fill_ctx(ix, L.cx);
-    JumpPlan plan;
+    std::vector<JumpPlan> plans(tabs.B + 1);
+    uint32_t plan_depth = 0;
+    std::vector<SearchStart> starts((size_t)(tabs.B + 1) * kMaxSearches);
     {
         const char* env = std::getenv("GMB_JUMP_DEPTH");
         int want = ix->jump_depth_opt;
@@ -439,20 +449,39 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
             if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
                 while (maxd > 1 && !ix->jt_uni[maxd] && ((size_t)15 << (2 * maxd)) > free_b / 2) --maxd;
         }
-        plan_jump_tables(*tabs, maxd, plan);
-        int rcj = ensure_jump_tables(ix, plan, stream);
-        if (rcj != GMB_OK) return rcj;
-        for (uint32_t s2 = 0; s2 < kMaxSearches; ++s2) {
-            const uint32_t d = plan.depth[s2];
-            L.starts[s2].uni = d ? ix->jt_uni[d] : nullptr;
-            L.starts[s2].lof = (d && plan.need_lof[s2]) ? ix->jt_lof[d] : nullptr;
-            L.starts[s2].a = plan.a[s2];
-            L.starts[s2].d = d;
+        std::memset(&plans[0], 0, sizeof(JumpPlan));
+        for (uint32_t cnt = 1; cnt <= tabs.B; ++cnt) {
+            plan_jump_tables(tabs.infix[cnt], maxd, plans[cnt]);
+            plan_depth = std::max(plan_depth, plans[cnt].max_depth);
         }
+        int rcj = ensure_jump_tables(ix, plans, stream);
+        if (rcj != GMB_OK) return rcj;
+        for (uint32_t cnt = 1; cnt <= tabs.B; ++cnt)
+            for (uint32_t s2 = 0; s2 < kMaxSearches; ++s2) {
+                const uint32_t d = plans[cnt].depth[s2];
+                SearchStart& S = starts[(size_t)cnt * kMaxSearches + s2];
+                S.uni = d ? ix->jt_uni[d] : nullptr;
+                S.lof = (d && plans[cnt].need_lof[s2]) ? ix->jt_lof[d] : nullptr;
+                S.a = plans[cnt].a[s2];
+                S.d = d;
+            }
     }
+    // search tables: step words, then the jump-table starts, in one device scratch buffer
+    const size_t step_bytes = tabs.steps.size() * sizeof(uint32_t);
+    const size_t start_off = (step_bytes + 15) / 16 * 16;
+    CU(cudaMemcpyAsync(ix->d_steps, tabs.steps.data(), step_bytes, cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(ix->d_steps) + start_off, starts.data(), starts.size() * sizeof(SearchStart),
+                       cudaMemcpyHostToDevice, stream));
+    // (copies from pageable host memory are staged before the call returns, so the vectors may go out of scope)
     L.cx.steps = ix->d_steps;
+    L.cx.starts = reinterpret_cast<const SearchStart*>(reinterpret_cast<const uint8_t*>(ix->d_steps) + start_off);
+    L.cx.p1_off = nullptr; L.cx.fl_off = nullptr; // the kernel points them at its shared-memory copies
+    L.n_step_words = (uint32_t)tabs.steps.size();
+    for (uint32_t c2 = 0; c2 <= kMaxBlockKmers; ++c2) { L.p1_off[c2] = tabs.p1_off[c2]; L.fl_off[c2] = tabs.fl_off[c2]; }
+    L.chunk = (uint32_t)chunk;
     L.cx.K = p->K;
-    L.cx.n_search = tabs->n_search;
+    L.cx.B = tabs.B;
+    L.cx.n_search = tabs.n_search;
     L.cx.n_strands = p->revcompl ? 2u : 1u;
     L.cx.maxv = p->value_bits == 16 ? 65535u : 255u;
     L.E = p->E;
@@ -487,7 +516,7 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
         CU(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
         stats->kernel_ms = ms;
         stats->kernel_launches = 1;
-        stats->jump_depth = plan.max_depth;
+        stats->jump_depth = plan_depth;
         if (L.count_fetches) {
             unsigned long long f[2] = {0, 0};
             CU(cudaMemcpy(f, ix->d_counters + 1, sizeof(f), cudaMemcpyDeviceToHost));

@@ -181,6 +181,7 @@ struct Pattern {
     GMB_HD uint32_t at(uint32_t i) const
     {
         if (KW == 1) return (uint32_t)(w[0] >> (2 * i)) & 3u;
+        if (KW == 2) return (uint32_t)((i < 32 ? w[0] : w[KW - 1]) >> (2 * (i & 31))) & 3u; // select: stays in registers
         return (uint32_t)(w[i >> 5] >> (2 * (i & 31))) & 3u;
     }
     // the d <= 16 characters starting at offset a as an integer, character a in the low bits
@@ -189,6 +190,9 @@ struct Pattern {
         uint64_t v;
         if (KW == 1) {
             v = w[0] >> (2 * a);
+        } else if (KW == 2) {
+            const uint32_t sh = 2 * (a & 31);
+            v = a < 32 ? ((w[0] >> sh) | (sh ? w[KW - 1] << (64 - sh) : 0ull)) : (w[KW - 1] >> sh);
         } else {
             const uint32_t wi = a >> 5, sh = 2 * (a & 31);
             v = w[wi] >> sh;
@@ -259,9 +263,14 @@ struct MapCtx {
     const uint32_t* sent[2];
     uint32_t C[4];
     uint32_t n_bwt;
-    const uint32_t* steps;    // n_search * K packed steps (gmb_layout.h)
-    const SearchStart* starts; // n_search entries
-    uint32_t K, n_search, n_strands, maxv;
+    // search tables (gmb_host.h: BlockTables), indexed by cnt = k-mers in the block (1..B):
+    //   infix search : steps[p1_off[cnt] + search * (K - cnt + 1) + t]
+    //   flank walks  : steps[fl_off[cnt] + window * (cnt - 1) + t]
+    const uint32_t* steps;
+    const uint32_t* p1_off;
+    const uint32_t* fl_off;
+    const SearchStart* starts; // [cnt * kMaxSearches + search]
+    uint32_t K, B, n_search, n_strands, maxv;
     // --exclude-pseudo only (src/algo.hpp:351-361): locate every hit and count distinct FASTA files
     const uint32_t* sa;          // full suffix array of T
     const uint32_t* seq_start;   // n_seq + 1 sequence starts inside T
@@ -291,14 +300,23 @@ GMB_HD Node extend_right(const Node& n, uint32_t c, const MapCtx& cx)
     return m;
 }
 
+// ---- one chain = one block of cnt <= B adjacent k-mer starts -------------------------------------------
+// The cnt k-mers share the infix needle[cnt-1 .. K-1] (needle = the K+cnt-1 text characters they cover).
+// As in the reference (computeMappabilitySingleBlock, src/algo.hpp:221-308) the infix is searched once
+// with the search scheme; every infix hit with e errors is then completed, window by window, through the
+// window's flank characters with the remaining E - e errors (the job of extend/approxSearch/extendExact,
+// src/algo.hpp:26-218, here a plain bounded walk per window).  cnt = 1 is the one-k-mer-per-chain case.
+constexpr uint32_t kNoWin = 0xffu;
+
 template <int KW>
 struct Chain {
-    Pattern<KW> pat;
+    Pattern<KW> pat;           // the needle; on the reverse strand its reverse complement
     uint32_t lo_f, lo_r, size; // current node: [lo_f, lo_f+size) in SA(T), [lo_r, lo_r+size) in SA(T')
-    uint32_t acc;              // occurrences so far (saturating)
+    uint32_t acc;              // B == 1: occurrences so far (saturating); B > 1: counts live in the frame store
     uint32_t t, e, s, strand;  // step, errors, search, strand of the current walk
     uint32_t lvmask;           // error levels holding a frame with pending children
-    uint64_t files;            // --exclude-pseudo: FASTA files seen so far (one bit each)
+    uint32_t cnt, win, leaf_e; // k-mers in this block; window being completed (kNoWin: infix search); errors of the infix hit
+    uint64_t files;            // B == 1, --exclude-pseudo: FASTA files seen so far (one bit each)
     uint32_t pre_lo_f, pre_lo_r, pre_size; // jump-table entry of (reverse strand, search 0), fetched early
 };
 
@@ -318,9 +336,18 @@ GMB_HD void ep_mark_rows(uint64_t& mask, uint32_t lo, uint32_t n, const MapCtx& 
     }
 }
 
-// frame words: 0..3 child lo in the active index, 4..7 child sizes, 8 = lo of child 0 in the other
-// index, 9 = t | pending << 8
+// Frame store of a chain (shared memory on the device):
+//   E mismatch frames x kFrameWords: 0..3 child lo in the active index, 4..7 child sizes, 8 = lo of child 0
+//                                    in the other index, 9 = t | pending << 8
+//   then kLeafWords for the infix hit being completed (lo_f, lo_r, size),
+//   then, when B > 1, one counter per window (+ two words of file mask per window under --exclude-pseudo).
+// Accessors: set/get(level, word) for the mismatch frames, xset/xget(word) for the rest.
 constexpr int kFrameWords = 10;
+constexpr int kLeafWords = 3;
+GMB_HD uint32_t frame_store_words(uint32_t E, uint32_t B, bool ep)
+{
+    return E * kFrameWords + kLeafWords + (B > 1 ? B * (ep ? 3u : 1u) : 0u);
+}
 
 GMB_HD void jump_lookup(const SearchStart& S, uint32_t key, uint32_t& lo_f, uint32_t& lo_r, uint32_t& size)
 {
@@ -334,11 +361,12 @@ GMB_HD void jump_lookup(const SearchStart& S, uint32_t key, uint32_t& lo_f, uint
 #endif
 }
 
+// start the infix search number st.s on the current strand
 template <int KW>
 GMB_HD void chain_start(Chain<KW>& st, const MapCtx& cx, unsigned long long* lut_reads)
 {
-    const SearchStart S = cx.starts[st.s];
-    st.e = 0; st.lvmask = 0;
+    const SearchStart S = cx.starts[st.cnt * kMaxSearches + st.s];
+    st.e = 0; st.lvmask = 0; st.win = kNoWin; st.leaf_e = 0;
     if (S.uni == nullptr) {
         st.lo_f = 0; st.lo_r = 0; st.size = cx.n_bwt; st.t = 0;
     } else {
@@ -349,19 +377,38 @@ GMB_HD void chain_start(Chain<KW>& st, const MapCtx& cx, unsigned long long* lut
     }
 }
 
-template <int KW>
-GMB_HD void chain_begin_kmer(Chain<KW>& st, const MapCtx& cx, unsigned long long* lut_reads)
+// st.pat (needle of K + cnt - 1 characters) and st.cnt are set by the caller
+template <int KW, bool EP, class Frames>
+GMB_HD void chain_begin_block(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned long long* lut_reads)
 {
     st.acc = 0; st.s = 0; st.strand = 0; st.files = 0;
+    if (cx.B > 1) {
+        const uint32_t per = EP ? 3u : 1u;
+        for (uint32_t w = 0; w < st.cnt * per; ++w) fr.xset(kLeafWords + w, 0u);
+    }
     // the reverse strand's first jump-table entry does not depend on the forward search: request it now so
     // that its latency overlaps the forward strand instead of starting the reverse strand with a stall
-    const SearchStart S0 = cx.starts[0];
+    const SearchStart S0 = cx.starts[st.cnt * kMaxSearches];
     if (cx.n_strands > 1 && S0.uni != nullptr) {
         Pattern<KW> rc = st.pat;
-        rc.reverse_complement(cx.K);
+        rc.reverse_complement(cx.K + st.cnt - 1);
         jump_lookup(S0, rc.bits(S0.a, S0.d), st.pre_lo_f, st.pre_lo_r, st.pre_size);
     }
     chain_start(st, cx, lut_reads);
+}
+
+// result of window w (position j0 + w) once chain_step has returned false
+template <int KW, bool EP, class Frames>
+GMB_HD uint32_t chain_result(const Chain<KW>& st, const Frames& fr, const MapCtx& cx, uint32_t w)
+{
+    if (cx.B == 1) return st.acc;
+    if (!EP) return fr.xget(kLeafWords + w);
+    const uint64_t m = (uint64_t)fr.xget(kLeafWords + st.cnt + 2 * w) | ((uint64_t)fr.xget(kLeafWords + st.cnt + 2 * w + 1) << 32);
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popcll(m);
+#else
+    return (uint32_t)__builtin_popcountll(m);
+#endif
 }
 
 GMB_HD uint32_t sel4(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t c)
@@ -387,17 +434,47 @@ GMB_HD uint32_t highest_bit_index(uint32_t m)
 #endif
 }
 
-// One state-machine iteration.  Returns false when the k-mer is finished (st.acc is final).
+// add `n` occurrences (or, under --exclude-pseudo, the files of SA rows [lo, lo+n)) to window `w` of the strand
+template <int KW, bool EP, class Frames>
+GMB_HD void chain_count(Chain<KW>& st, Frames& fr, const MapCtx& cx, uint32_t w, uint32_t lo, uint32_t n, bool own_only)
+{
+    const uint32_t widx = st.strand ? st.cnt - 1u - w : w; // reverse-strand windows run backwards (src/algo.hpp:304)
+    if (EP) {
+        uint64_t m = cx.B == 1 ? st.files
+                               : (uint64_t)fr.xget(kLeafWords + st.cnt + 2 * widx) | ((uint64_t)fr.xget(kLeafWords + st.cnt + 2 * widx + 1) << 32);
+        if (own_only) m |= 1ull << cx.own_file;
+        else ep_mark_rows(m, lo, n, cx);
+        if (cx.B == 1) st.files = m;
+        else { fr.xset(kLeafWords + st.cnt + 2 * widx, (uint32_t)m); fr.xset(kLeafWords + st.cnt + 2 * widx + 1, (uint32_t)(m >> 32)); }
+    } else {
+        const uint32_t old = cx.B == 1 ? st.acc : fr.xget(kLeafWords + widx);
+        const uint64_t sum = (uint64_t)old + n;
+        const uint32_t v = sum < cx.maxv ? (uint32_t)sum : cx.maxv; // saturating (src/algo.hpp:48,191)
+        if (cx.B == 1) st.acc = v; else fr.xset(kLeafWords + widx, v);
+    }
+}
+
+// One state-machine iteration.  Returns false when the block is finished (results via chain_result).
 // `fetches` counts rank-block reads (the roofline's algorithmic unit), when non-null.
 template <int KW, bool EP, class Frames>
 GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned long long* fetches,
                        unsigned long long* lut_reads)
 {
-    const uint32_t K = cx.K;
-    const uint32_t ent = cx.steps[st.s * K + st.t];
+    const uint32_t K = cx.K, cnt = st.cnt;
+    const uint32_t Li = K - cnt + 1; // infix length
+
+    if (st.win == kNoWin && st.t == Li) {
+        // the whole infix is matched (only reached when cnt > 1): this node is an infix hit; complete it for
+        // every window, starting with window 0.  Frames of levels >= e are free here.
+        fr.xset(0, st.lo_f); fr.xset(1, st.lo_r); fr.xset(2, st.size);
+        st.leaf_e = st.e; st.win = 0; st.t = 0;
+    }
+    const bool in_flank = st.win != kNoWin;
+    const uint32_t T = in_flank ? cnt - 1u : Li; // steps of the current walk
+    const uint32_t tab = in_flank ? cx.fl_off[cnt] + st.win * (cnt - 1u) : cx.p1_off[cnt] + st.s * Li;
+    const uint32_t ent = cx.steps[tab + st.t];
     const uint32_t dir = step_dir(ent);
-    const uint32_t pos = step_pos(ent);
-    const uint32_t p = st.pat.at(pos); // on the reverse strand st.pat already holds the reverse complement
+    const uint32_t p = st.pat.at(step_pos(ent)); // on the reverse strand st.pat already holds the reverse complement
 
     bool descend = false;
     uint32_t c = 0, csize = 0, cact = 0, coth = 0, ce = 0, ct = 0, cdir = dir;
@@ -407,9 +484,9 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
     } else if (st.strand == 0 && st.e == 0 && st.size == 1 && step_exact_ok(ent)) {
         // Forward strand, no error so far, one occurrence left: it is the query's own position in the
         // indexed text, so the rest of the pattern matches it exactly and no mismatching extension
-        // exists.  The subtree contributes exactly one occurrence — no need to walk it.
-        if (EP) st.files |= 1ull << cx.own_file;
-        else st.acc = st.acc + 1u < cx.maxv ? st.acc + 1u : cx.maxv;
+        // exists.  The subtree contributes exactly one occurrence per window — no need to walk it.
+        if (in_flank) chain_count<KW, EP>(st, fr, cx, st.win, 0, 1, true);
+        else for (uint32_t w = 0; w < cnt; ++w) chain_count<KW, EP>(st, fr, cx, w, 0, 1, true);
     } else {
         // ---- expand the node: ranks at both interval ends of the active index -----------------------
         const uint32_t x = dir ? st.lo_r : st.lo_f;
@@ -454,20 +531,21 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
         if (n2 && (p == 2 ? hit_ok : mis_ok)) ok |= 4u;
         if (n3 && (p == 3 ? hit_ok : mis_ok)) ok |= 8u;
 
-        if (st.t + 1 == K) {
-            // children are full-length matches: count them (src/algo.hpp:48,191)
+        if (st.t + 1 == T && (in_flank || cnt == 1)) {
+            // children are full-length matches of one window: count them (src/algo.hpp:48,191)
+            const uint32_t w = in_flank ? st.win : 0u;
             if (EP) {
                 // rows in SA(T): the active index's children when extending left, else the synchronised side
                 const uint32_t f0 = dir ? oth0 : l0, f1 = dir ? oth0 + n0 : l1, f2 = dir ? oth0 + n0 + n1 : l2,
                                f3 = dir ? oth0 + n0 + n1 + n2 : l3;
-                if (ok & 1u) ep_mark_rows(st.files, f0, n0, cx);
-                if (ok & 2u) ep_mark_rows(st.files, f1, n1, cx);
-                if (ok & 4u) ep_mark_rows(st.files, f2, n2, cx);
-                if (ok & 8u) ep_mark_rows(st.files, f3, n3, cx);
+                if (ok & 1u) chain_count<KW, EP>(st, fr, cx, w, f0, n0, false);
+                if (ok & 2u) chain_count<KW, EP>(st, fr, cx, w, f1, n1, false);
+                if (ok & 4u) chain_count<KW, EP>(st, fr, cx, w, f2, n2, false);
+                if (ok & 8u) chain_count<KW, EP>(st, fr, cx, w, f3, n3, false);
             } else {
-                const uint64_t sum = (uint64_t)st.acc + ((ok & 1u) ? n0 : 0u) + ((ok & 2u) ? n1 : 0u) +
-                                     ((ok & 4u) ? n2 : 0u) + ((ok & 8u) ? n3 : 0u);
-                st.acc = sum < cx.maxv ? (uint32_t)sum : cx.maxv;
+                const uint64_t sum = (uint64_t)((ok & 1u) ? n0 : 0u) + ((ok & 2u) ? n1 : 0u) + ((ok & 4u) ? n2 : 0u) +
+                                     ((ok & 8u) ? n3 : 0u);
+                chain_count<KW, EP>(st, fr, cx, w, 0, sum < cx.maxv ? (uint32_t)sum : cx.maxv, false);
             }
         } else if (ok) {
             const uint32_t mm = ok & ~(1u << p);
@@ -491,13 +569,29 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
     }
 
     if (!descend) {
-        // ---- backtrack: deepest error level that still has pending children ------------------------
-        if (st.lvmask == 0) {
+        // ---- backtrack ---------------------------------------------------------------------------------
+        // While an infix hit is being completed, the frames of its window walks sit at levels >= leaf_e and
+        // the infix search's own pending frames below that.
+        uint32_t cand = st.lvmask;
+        if (st.win != kNoWin) {
+            cand = (st.lvmask >> st.leaf_e) << st.leaf_e;
+            if (cand == 0) {
+                // this window is done: next window from the saved infix hit, or back to the infix search
+                if (++st.win < cnt) {
+                    st.lo_f = fr.xget(0); st.lo_r = fr.xget(1); st.size = fr.xget(2);
+                    st.e = st.leaf_e; st.t = 0;
+                    return true;
+                }
+                st.win = kNoWin;
+                cand = st.lvmask;
+            }
+        }
+        if (cand == 0) {
             // this search is exhausted: next search, next strand, or done
             if (++st.s == cx.n_search) {
                 st.s = 0;
                 if (++st.strand == cx.n_strands) {
-                    if (EP) { // distinct FASTA files with at least one occurrence on either strand (:360)
+                    if (EP && cx.B == 1) { // distinct FASTA files with at least one occurrence on either strand (:360)
 #if defined(__CUDA_ARCH__)
                         st.acc = (uint32_t)__popcll(st.files);
 #else
@@ -506,18 +600,18 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
                     }
                     return false;
                 }
-                st.pat.reverse_complement(K);
+                st.pat.reverse_complement(K + cnt - 1);
             }
             chain_start(st, cx, lut_reads);
             return true;
         }
-        const uint32_t lv = highest_bit_index(st.lvmask);
+        const uint32_t lv = highest_bit_index(cand);
         const uint32_t meta = fr.get(lv, 9);
         const uint32_t tf = meta & 0xffu;
         uint32_t pending = meta >> 8;
-        const uint32_t entf = cx.steps[st.s * K + tf];
-        const uint32_t posf = step_pos(entf);
-        const uint32_t pf = st.pat.at(posf);
+        const uint32_t tabf = st.win != kNoWin ? cx.fl_off[cnt] + st.win * (cnt - 1u) : cx.p1_off[cnt] + st.s * Li;
+        const uint32_t entf = cx.steps[tabf + tf];
+        const uint32_t pf = st.pat.at(step_pos(entf));
         const uint32_t mm = pending & ~(1u << pf);
         c = mm ? lowest_bit_index(mm) : pf;
         pending &= ~(1u << c);

@@ -79,6 +79,53 @@ bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err
     return true;
 }
 
+uint32_t default_block_kmers(uint32_t K, uint32_t E)
+{
+    // E = 0: with the jump tables a k-mer costs 2-3 rank-block reads, sharing an infix cannot beat that.
+    // E >= 1: the infix search dominates and is shared by the block; more k-mers per block shorten the infix,
+    // which makes its search bushier (same trade-off as the reference's overlap, src/mappability.hpp:519-543).
+    if (E == 0) return 1;
+    uint32_t b = E == 1 ? 8u : (E == 2 ? 6u : 4u);
+    const uint32_t cap = K > E + 1 ? K - E - 1 : 1; // the infix must keep one character per scheme block
+    while (b > 1 && (b > cap || b * 4 > K)) --b;    // and stay most of the k-mer
+    return b < 1 ? 1 : b;
+}
+
+bool build_block_tables(uint32_t K, uint32_t E, uint32_t B, bool force_sync, BlockTables& out, std::string& err)
+{
+    if (E > kMaxE) { err = "E > 4 not yet supported."; return false; }
+    if (K < E + 2) { err = "K must be at least E + 2."; return false; }
+    if (B == 0) B = default_block_kmers(K, E);
+    if (B > kMaxBlockKmers) B = kMaxBlockKmers;
+    while (B > 1 && (B + E + 1 > K || K + B - 2 > 255)) --B; // the infix keeps >= E + 2 characters; offsets fit 8 bits
+    if (K + B - 2 > 255) { err = "K > 255 is not supported."; return false; }
+    out.K = K; out.E = E; out.B = B;
+    out.steps.clear();
+    out.infix.assign(B + 1, StepTables());
+    for (uint32_t cnt = 1; cnt <= B; ++cnt) {
+        const uint32_t Li = K - cnt + 1;
+        StepTables& t = out.infix[cnt];
+        if (!build_step_tables(Li, E, t, err, force_sync || cnt > 1)) return false; // flanks need both intervals
+        out.n_search = t.n_search;
+        out.p1_off[cnt] = (uint32_t)out.steps.size();
+        for (uint32_t i = 0; i < t.n_search * Li; ++i) {
+            t.step[i] += cnt - 1; // pattern offsets in needle coordinates: the infix starts at cnt - 1
+            out.steps.push_back(t.step[i]);
+        }
+        out.fl_off[cnt] = (uint32_t)out.steps.size();
+        for (uint32_t w = 0; w < cnt; ++w) {
+            // window w = needle[w .. w+K): left flank needle[cnt-2 .. w] (right to left), then right flank needle[K .. K+w-1]
+            for (uint32_t q = cnt - 1; q > w; --q) {
+                const bool sync = force_sync || w > 0; // right-flank steps follow
+                out.steps.push_back((q - 1) | (E << 16) | (0u << 24) | ((sync ? 1u : 0u) << 25) | (1u << 26));
+            }
+            for (uint32_t q = 0; q < w; ++q)
+                out.steps.push_back((K + q) | (E << 16) | (1u << 24) | ((force_sync ? 1u : 0u) << 25) | (1u << 26));
+        }
+    }
+    return true;
+}
+
 void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan)
 {
     plan.max_depth = 0;

@@ -16,6 +16,21 @@ namespace gmb {
 // needs the interval in SA(T) at every full-length match).
 bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err, bool force_sync = false);
 
+// Search tables of a (K,E) configuration for blocks of up to B adjacent k-mers (see Chain in gmb_core.h):
+// for every block size cnt = 1..B the scheme's step table over the common infix (K - cnt + 1 characters,
+// offsets in needle coordinates) and, per window, the steps through its flank characters (left flank from
+// the infix outwards, then right flank) with the error budget E and no lower bound.
+struct BlockTables {
+    uint32_t K = 0, E = 0, B = 0, n_search = 0;
+    uint32_t p1_off[kMaxBlockKmers + 1] = {};
+    uint32_t fl_off[kMaxBlockKmers + 1] = {};
+    std::vector<uint32_t> steps;
+    std::vector<StepTables> infix; // [cnt] the per-cnt infix tables (index 0 unused), kept for jump-table planning
+};
+// B == 0 picks the default for (K,E).  force_sync: see build_step_tables.
+bool build_block_tables(uint32_t K, uint32_t E, uint32_t B, bool force_sync, BlockTables& out, std::string& err);
+uint32_t default_block_kmers(uint32_t K, uint32_t E);
+
 // Which jump table each search of a (K,E) configuration can use: depth[s] = min(length of the search's
 // initial error-free rightwards run, max_depth, K-1); 0 = none.  need_lof[s]: a later step extends to the
 // left, so the interval in SA(T) must be known too.

@@ -37,6 +37,7 @@ constexpr uint32_t kMaxSeq = (1u << 24) - 1; // sentinel counter has 24 bits
 constexpr uint32_t kMaxK = 255;              // step tables keep pattern offsets in 8 bits
 constexpr uint32_t kMaxE = 4;                // src/mappability.hpp:187
 constexpr uint32_t kMaxSearches = 7;         // src/find2_index_approx.hpp:121-131
+constexpr uint32_t kMaxBlockKmers = 16;      // adjacent k-mers searched together through their common infix
 
 struct alignas(kBlockBytes) RankBlock {
     uint32_t cnt[3];

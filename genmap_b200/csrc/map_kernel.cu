@@ -27,48 +27,66 @@ constexpr int kThreads = 256;
 #endif
 
 struct SmemFrames {
-    uint32_t* base; // + threadIdx.x
+    uint32_t* base;  // + threadIdx.x; word i of this chain at base[i * kThreads] (conflict-free)
+    uint32_t xoff;   // first word after the E mismatch frames
     __device__ __forceinline__ void set(uint32_t lv, uint32_t i, uint32_t v) { base[(lv * kFrameWords + i) * kThreads] = v; }
     __device__ __forceinline__ uint32_t get(uint32_t lv, uint32_t i) const { return base[(lv * kFrameWords + i) * kThreads]; }
+    __device__ __forceinline__ void xset(uint32_t i, uint32_t v) { base[(xoff + i) * kThreads] = v; }
+    __device__ __forceinline__ uint32_t xget(uint32_t i) const { return base[(xoff + i) * kThreads]; }
 };
+
+__host__ __device__ inline uint32_t align32(uint32_t x) { return (x + 31u) & ~31u; }
+constexpr uint32_t kStartWords = sizeof(SearchStart) / 4;
 
 template <int KW, bool COUNT, typename OutT, bool EP>
 __global__ void __launch_bounds__(kThreads, GMB_MIN_BLOCKS) map_kernel(const MapLaunch L)
 {
+    // shared memory: step tables | jump-table starts | offsets | per-chain frame store
     extern __shared__ uint32_t smem[];
-    const uint32_t n_steps = L.cx.n_search * L.cx.K;
+    const uint32_t n_start_words = (L.cx.B + 1) * kMaxSearches * kStartWords;
     uint32_t* steps_s = smem;
-    for (uint32_t i = threadIdx.x; i < n_steps; i += kThreads) steps_s[i] = L.cx.steps[i];
-    __syncthreads();
-
-    __shared__ SearchStart starts_s[kMaxSearches];
-    if (threadIdx.x < kMaxSearches) starts_s[threadIdx.x] = L.starts[threadIdx.x];
+    uint32_t* starts_s = steps_s + align32(L.n_step_words);
+    uint32_t* offs_s = starts_s + align32(n_start_words);
+    uint32_t* frames_s = offs_s + align32(2 * (kMaxBlockKmers + 1));
+    for (uint32_t i = threadIdx.x; i < L.n_step_words; i += kThreads) steps_s[i] = L.cx.steps[i];
+    for (uint32_t i = threadIdx.x; i < n_start_words; i += kThreads) starts_s[i] = reinterpret_cast<const uint32_t*>(L.cx.starts)[i];
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (uint32_t i = 0; i <= kMaxBlockKmers; ++i) { // static indices: the parameter struct stays in constant memory
+            offs_s[i] = L.p1_off[i];
+            offs_s[kMaxBlockKmers + 1 + i] = L.fl_off[i];
+        }
+    }
     __syncthreads();
 
     MapCtx cx = L.cx;
     cx.steps = steps_s;
-    cx.starts = starts_s;
-    SmemFrames fr{smem + ((n_steps + 31u) & ~31u) + threadIdx.x};
+    cx.starts = reinterpret_cast<const SearchStart*>(starts_s);
+    cx.p1_off = offs_s;
+    cx.fl_off = offs_s + kMaxBlockKmers + 1;
+    SmemFrames fr{frames_s + threadIdx.x, L.E * kFrameWords};
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     OutT* __restrict__ out = static_cast<OutT*>(L.out);
+    const unsigned long long B = cx.B;
 
     Chain<KW> st;
-    uint64_t j = 0;
+    uint64_t j = 0; // first position of the chain's block
     bool active = false, exhausted = false;
-    // warp-uniform pool of consecutive positions [pool_next, pool_end) and "no more chunks" flag
+    // warp-uniform pool of consecutive positions [pool_next, pool_end) and "no more chunks" flag;
+    // every refilling lane takes the next B positions (fewer at the end of a chunk)
     unsigned long long pool_next = 0, pool_end = 0;
     bool pool_done = false;
     unsigned long long fetches = 0, lut_reads = 0;
 
     for (;;) {
-        // ---- refill: lanes without a k-mer take the next positions of the warp's pool --------------
+        // ---- refill: lanes without a block take the next positions of the warp's pool ---------------
         const bool need = !active && !exhausted;
         const unsigned m = __ballot_sync(0xffffffffu, need);
         if (m) {
             const unsigned cnt = __popc(m), rank = __popc(m & lt_mask);
-            unsigned long long avail = pool_end - pool_next;
+            const unsigned long long avail = (pool_end - pool_next + B - 1) / B; // blocks left in the pool
             unsigned long long nb = 0, ne = 0;
             if (avail < cnt && !pool_done) {
                 unsigned long long cid = 0;
@@ -82,28 +100,33 @@ __global__ void __launch_bounds__(kThreads, GMB_MIN_BLOCKS) map_kernel(const Map
                         const uint32_t mid = (lo + hi) >> 1;
                         if (__ldg(L.chunk_prefix + mid) <= cid) lo = mid; else hi = mid;
                     }
-                    nb = __ldg(L.range_begin + lo) + (cid - __ldg(L.chunk_prefix + lo)) * kChunk;
-                    ne = nb + kChunk;
+                    nb = __ldg(L.range_begin + lo) + (cid - __ldg(L.chunk_prefix + lo)) * L.chunk;
+                    ne = nb + L.chunk;
                     const unsigned long long re = __ldg(L.range_end + lo);
                     if (ne > re) ne = re;
                 }
             }
+            const unsigned long long fresh = (ne - nb + B - 1) / B; // blocks in the new chunk
+            unsigned long long jend = 0;
             bool got = false;
             if (need) {
-                if (rank < avail) { j = pool_next + rank; got = true; }
-                else if (rank - avail < ne - nb) { j = nb + (rank - avail); got = true; }
+                if (rank < avail) { j = pool_next + rank * B; jend = pool_end; got = true; }
+                else if (rank - avail < fresh) { j = nb + (rank - avail) * B; jend = ne; got = true; }
             }
             if (cnt <= avail) {
-                pool_next += cnt;
+                pool_next += cnt * B;
+                if (pool_next > pool_end) pool_next = pool_end;
             } else {
-                const unsigned long long want = cnt - avail, have = ne - nb;
-                pool_next = nb + (want < have ? want : have);
+                const unsigned long long want = cnt - avail;
+                pool_next = nb + (want < fresh ? want : fresh) * B;
+                if (pool_next > ne) pool_next = ne;
                 pool_end = ne;
             }
             if (need) {
                 if (got) {
-                    load_pattern(st.pat, L.text, L.text_begin + j, cx.K);
-                    chain_begin_kmer(st, cx, COUNT ? &lut_reads : nullptr);
+                    st.cnt = (uint32_t)(jend - j < B ? jend - j : B);
+                    load_pattern(st.pat, L.text, L.text_begin + j, cx.K + st.cnt - 1);
+                    chain_begin_block<KW, EP>(st, fr, cx, COUNT ? &lut_reads : nullptr);
                     active = true;
                 } else if (pool_done) {
                     exhausted = true;
@@ -115,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, GMB_MIN_BLOCKS) map_kernel(const Map
         // ---- one node expansion per chain -------------------------------------------------------------
         if (active) {
             if (!chain_step<KW, EP>(st, fr, cx, COUNT ? &fetches : nullptr, COUNT ? &lut_reads : nullptr)) {
-                out[j] = (OutT)st.acc;
+                for (uint32_t w = 0; w < st.cnt; ++w) out[j + w] = (OutT)chain_result<KW, EP>(st, fr, cx, w);
                 active = false;
             }
         }
@@ -134,16 +157,15 @@ template <int KW, bool COUNT, typename OutT, bool EP>
 cudaError_t launch_t(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
     auto kern = map_kernel<KW, COUNT, OutT, EP>;
-    const uint32_t n_steps = L.cx.n_search * L.cx.K;
-    const size_t smem = ((size_t)((n_steps + 31u) & ~31u) + (size_t)L.E * kFrameWords * kThreads) * sizeof(uint32_t);
+    const size_t smem = map_kernel_smem_bytes(L.n_step_words, L.E, L.cx.B, EP);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    // persistent grid: every resident CTA slot of every SM, but never more threads than work items
-    unsigned long long want = (L.n_work + kThreads - 1) / kThreads;
+    // persistent grid: every resident CTA slot of every SM, but never more threads than blocks of work
+    unsigned long long want = (L.n_work / L.cx.B + kThreads) / kThreads;
     unsigned long long grid = (unsigned long long)sm_count * per_sm;
     if (want < grid) grid = want ? want : 1;
     kern<<<(unsigned)grid, kThreads, smem, stream>>>(L);
@@ -165,13 +187,20 @@ cudaError_t launch_kw(const MapLaunch& L, int sm_count, cudaStream_t stream)
 
 } // namespace
 
+size_t map_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool ep)
+{
+    const size_t tables = align32(n_step_words) + align32((B + 1) * kMaxSearches * kStartWords) + align32(2 * (kMaxBlockKmers + 1));
+    return (tables + (size_t)frame_store_words(E, B, ep) * kThreads) * sizeof(uint32_t);
+}
+
 cudaError_t launch_map_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
     if (L.n_work == 0) return cudaSuccess;
-    if (L.cx.K <= 32) return launch_kw<1>(L, sm_count, stream);
-    if (L.cx.K <= 64) return launch_kw<2>(L, sm_count, stream);
-    if (L.cx.K <= 128) return launch_kw<4>(L, sm_count, stream);
-    return launch_kw<8>(L, sm_count, stream);
+    const uint32_t needle = L.cx.K + L.cx.B - 1; // characters a chain keeps in registers
+    if (needle <= 32) return launch_kw<1>(L, sm_count, stream);
+    if (needle <= 64) return launch_kw<2>(L, sm_count, stream);
+    if (needle <= 128) return launch_kw<4>(L, sm_count, stream);
+    return launch_kw<9>(L, sm_count, stream);
 }
 
 } // namespace gmb

@@ -8,11 +8,15 @@
 namespace gmb {
 
 struct MapLaunch {
-    MapCtx cx;                 // device pointers into the index blob (cx.steps: device copy of the step table)
+    MapCtx cx;                 // device pointers into the index blob; cx.steps / cx.starts: device copies of the
+                               // search tables (n_step_words words, then (B+1)*kMaxSearches SearchStart entries)
     uint32_t E;
+    uint32_t n_step_words;
+    uint32_t p1_off[kMaxBlockKmers + 1], fl_off[kMaxBlockKmers + 1];
+    uint32_t chunk;            // positions per work chunk: a multiple of cx.B
     const uint64_t* text;      // 2-bit packed concatenated text (device)
     uint64_t text_begin;       // start of this FASTA file's text inside the concatenated text
-    // work = chunks of <= kChunk consecutive positions; a chunk never straddles two ranges
+    // work = chunks of <= `chunk` consecutive positions; a chunk never straddles two ranges
     const uint64_t* range_begin;  // device: n_ranges work ranges, file-local [begin, end)
     const uint64_t* range_end;
     const uint64_t* chunk_prefix; // device: n_ranges+1, number of chunks before range r
@@ -21,14 +25,16 @@ struct MapLaunch {
     uint64_t n_work;           // total k-mer starts to search (sizing only)
     unsigned long long* work_counter;  // device, zeroed before launch: next chunk id
     unsigned long long* fetch_counter; // device: [0] rank-block fetches, [1] jump-table reads (count_fetches)
-    SearchStart starts[kMaxSearches];  // jump table of every search (uni == nullptr: start at the root)
     void* out;                 // device, value_bits/8 bytes per file-local position
     uint32_t value_bits;
     bool count_fetches;
     bool exclude_pseudo;       // cx.sa / seq_start / seq_to_file / all_files are set
 };
 
-constexpr unsigned kChunk = 128; // positions handed out per global atomic
+constexpr unsigned kChunk = 128; // positions handed out per global atomic (rounded down to a multiple of B)
+
+// dynamic shared memory the kernel needs for these tables (the host shrinks B if this exceeds the SM's limit)
+size_t map_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool ep);
 
 // Enqueue the kernel on `stream`.  Returns cudaSuccess or the launch error.
 cudaError_t launch_map_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream);

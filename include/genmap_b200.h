@@ -52,7 +52,10 @@ typedef struct gmb_params {
     uint32_t exclude_pseudo; /* -ep: count distinct FASTA files instead (needs the SA section) */
     uint32_t value_bits;     /* 8 (-fs) or 16 (-fl and the default float output) */
     uint32_t count_fetches;  /* 1: also count rank-block fetches (instrumented kernel, slower) */
-    uint32_t reserved[2];
+    uint32_t block_kmers;    /* adjacent k-mers searched together through their common infix (the reference's
+                                K - overlap + 1, src/algo.hpp:416); 0 = default for (K,E), 1 = one k-mer at a
+                                time; results do not depend on it (tests/tests.sh:47-60 checks the same for -xo) */
+    uint32_t reserved;
 } gmb_params;
 
 typedef struct gmb_index_info {

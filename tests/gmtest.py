@@ -350,7 +350,7 @@ def hostsim_lib():
         L.hs_step_tables.argtypes = [u32, u32, ctypes.POINTER(u32), vp]
         L.hs_map.restype = ci
         L.hs_map.argtypes = [vp, u32, u32, ci, ci, u64, u64, vp, u32, vp, u64, u64, u64, vp, ctypes.POINTER(ctypes.c_ulonglong),
-                             ci, ctypes.POINTER(ctypes.c_ulonglong), vp, u32]
+                             ci, ctypes.POINTER(ctypes.c_ulonglong), vp, u32, u32]
         _hs = L
     return _hs
 
@@ -386,13 +386,14 @@ class HostSim:
         return out
 
     def map(self, K, E, revcompl=True, value_bits=16, seq_to_file=None, file_no=0, intervals=None,
-            pos_begin=0, pos_end=None, return_fetches=False, jump_depth=-1, exclude_pseudo=False):
+            pos_begin=0, pos_end=None, return_fetches=False, jump_depth=-1, exclude_pseudo=False, block_kmers=0):
         stf, tb, tl, cum, iv = _prep(self.limits, seq_to_file, file_no, intervals)
         out = np.zeros(tl, dtype=np.uint16 if value_bits == 16 else np.uint8)
         f, lr = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
         rc = self.L.hs_map(self.blob, K, E, int(revcompl), value_bits, tb, tl, _ptr(cum), len(cum) - 1, _ptr(iv),
                            0 if iv is None else len(iv), pos_begin, tl if pos_end is None else pos_end, _ptr(out),
-                           ctypes.byref(f), jump_depth, ctypes.byref(lr), _ptr(stf) if exclude_pseudo else None, file_no)
+                           ctypes.byref(f), jump_depth, ctypes.byref(lr), _ptr(stf) if exclude_pseudo else None, file_no,
+                           block_kmers)
         if rc != 0:
             raise RuntimeError("hs_map failed: %d" % rc)
         self.last_lut_reads = lr.value

@@ -17,8 +17,11 @@ using namespace gmb;
 namespace {
 struct HostFrames {
     uint32_t w[kMaxE][kFrameWords];
+    uint32_t x[kLeafWords + 3 * kMaxBlockKmers];
     inline void set(uint32_t lv, uint32_t i, uint32_t v) { w[lv][i] = v; }
     inline uint32_t get(uint32_t lv, uint32_t i) const { return w[lv][i]; }
+    inline void xset(uint32_t i, uint32_t v) { x[i] = v; }
+    inline uint32_t xget(uint32_t i) const { return x[i]; }
 };
 
 template <int KW, bool EP>
@@ -26,14 +29,18 @@ void run_ranges(const MapCtx& cx, const uint64_t* text, uint64_t text_begin, con
                 int value_bits, void* out, unsigned long long* fetches, unsigned long long* lut_reads)
 {
     for (const WorkRange& r : ranges)
-        for (uint64_t j = r.begin; j < r.end; ++j) {
+        for (uint64_t j0 = r.begin; j0 < r.end; j0 += cx.B) { // blocks of up to B adjacent k-mers, never across ranges
             Chain<KW> st;
             HostFrames fr;
-            load_pattern(st.pat, text, text_begin + j, cx.K);
-            chain_begin_kmer(st, cx, lut_reads);
+            st.cnt = (uint32_t)std::min<uint64_t>(cx.B, r.end - j0);
+            load_pattern(st.pat, text, text_begin + j0, cx.K + st.cnt - 1);
+            chain_begin_block<KW, EP>(st, fr, cx, lut_reads);
             while (chain_step<KW, EP>(st, fr, cx, fetches, lut_reads)) {}
-            if (value_bits == 16) static_cast<uint16_t*>(out)[j] = (uint16_t)st.acc;
-            else static_cast<uint8_t*>(out)[j] = (uint8_t)st.acc;
+            for (uint32_t w = 0; w < st.cnt; ++w) {
+                const uint32_t v = chain_result<KW, EP>(st, fr, cx, w);
+                if (value_bits == 16) static_cast<uint16_t*>(out)[j0 + w] = (uint16_t)v;
+                else static_cast<uint8_t*>(out)[j0 + w] = (uint8_t)v;
+            }
         }
 }
 } // namespace
@@ -92,14 +99,16 @@ int hs_step_tables(uint32_t K, uint32_t E, uint32_t* n_search, uint32_t* steps)
 int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bits, uint64_t text_begin,
            uint64_t text_len, const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t* intervals,
            uint64_t n_intervals, uint64_t pos_begin, uint64_t pos_end, void* out, unsigned long long* fetches,
-           int jump_depth, unsigned long long* lut_reads_out, const uint32_t* seq_to_file, uint32_t own_file)
+           int jump_depth, unsigned long long* lut_reads_out, const uint32_t* seq_to_file, uint32_t own_file,
+           uint32_t block_kmers)
 {
     const bool ep = seq_to_file != nullptr;
     const uint8_t* base = static_cast<const uint8_t*>(blob);
     std::string err;
     const IndexHeader& h = *reinterpret_cast<const IndexHeader*>(base);
-    StepTables* tabs = new StepTables;
-    if (!build_step_tables(K, E, *tabs, err, ep)) { delete tabs; return -2; }
+    BlockTables tabs;
+    if (!build_block_tables(K, E, block_kmers, ep, tabs, err)) return -2;
+    const uint32_t B = tabs.B;
     MapCtx cx;
     cx.blk[0] = reinterpret_cast<const RankBlock*>(base + h.off_fwd);
     cx.blk[1] = reinterpret_cast<const RankBlock*>(base + h.off_rev);
@@ -107,26 +116,33 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     cx.sent[1] = reinterpret_cast<const uint32_t*>(base + h.off_sent_rev);
     for (int c = 0; c < 4; ++c) cx.C[c] = (uint32_t)h.C[c];
     cx.n_bwt = (uint32_t)h.n_bwt;
-    cx.steps = tabs->step;
-    cx.K = K; cx.n_search = tabs->n_search; cx.n_strands = revcompl ? 2 : 1;
+    cx.steps = tabs.steps.data();
+    cx.p1_off = tabs.p1_off;
+    cx.fl_off = tabs.fl_off;
+    cx.K = K; cx.B = B; cx.n_search = tabs.n_search; cx.n_strands = revcompl ? 2 : 1;
     cx.maxv = value_bits == 16 ? 65535u : 255u;
     cx.sa = nullptr; cx.seq_start = nullptr; cx.seq_to_file = nullptr; cx.n_seq = h.n_seq; cx.own_file = own_file; cx.all_files = 0;
     if (ep) {
-        if (!h.off_sa) { delete tabs; return -3; }
+        if (!h.off_sa) return -3;
         cx.sa = reinterpret_cast<const uint32_t*>(base + h.off_sa);
         cx.seq_start = reinterpret_cast<const uint32_t*>(base + h.off_seq_start);
         cx.seq_to_file = seq_to_file;
         uint32_t nf = 0;
         for (uint32_t q = 0; q < h.n_seq; ++q) nf = std::max(nf, seq_to_file[q] + 1);
-        if (nf > 64) { delete tabs; return -4; }
+        if (nf > 64) return -4;
         cx.all_files = nf == 64 ? ~0ull : ((1ull << nf) - 1ull);
     }
     // jump tables, level by level (the device builder does the same with one thread per entry)
-    JumpPlan plan;
-    plan_jump_tables(*tabs, jump_depth < 0 ? default_jump_depth(h.n_bwt) : (uint32_t)jump_depth, plan);
-    std::vector<std::vector<JtEntry>> uni(plan.max_depth + 1);
-    std::vector<std::vector<uint32_t>> lof(plan.max_depth + 1);
-    for (uint32_t d = 1; d <= plan.max_depth; ++d) {
+    const uint32_t want_depth = jump_depth < 0 ? default_jump_depth(h.n_bwt) : (uint32_t)jump_depth;
+    std::vector<JumpPlan> plans(B + 1);
+    uint32_t max_depth = 0;
+    for (uint32_t cnt = 1; cnt <= B; ++cnt) {
+        plan_jump_tables(tabs.infix[cnt], want_depth, plans[cnt]);
+        max_depth = std::max(max_depth, plans[cnt].max_depth);
+    }
+    std::vector<std::vector<JtEntry>> uni(max_depth + 1);
+    std::vector<std::vector<uint32_t>> lof(max_depth + 1);
+    for (uint32_t d = 1; d <= max_depth; ++d) {
         const uint64_t n = 1ull << (2 * d), pmask = (1ull << (2 * (d - 1))) - 1;
         uni[d].resize(n); lof[d].resize(n);
         for (uint64_t key = 0; key < n; ++key) {
@@ -137,14 +153,16 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
             uni[d][key].lo_r = m.lo_r; uni[d][key].size = m.size; lof[d][key] = m.lo_f;
         }
     }
-    SearchStart starts[kMaxSearches];
-    for (uint32_t s = 0; s < kMaxSearches; ++s) {
-        const uint32_t d = plan.depth[s];
-        starts[s].uni = d ? uni[d].data() : nullptr;
-        starts[s].lof = (d && plan.need_lof[s]) ? lof[d].data() : nullptr;
-        starts[s].a = plan.a[s]; starts[s].d = d;
-    }
-    cx.starts = starts;
+    std::vector<SearchStart> starts((B + 1) * kMaxSearches);
+    for (uint32_t cnt = 1; cnt <= B; ++cnt)
+        for (uint32_t s = 0; s < kMaxSearches; ++s) {
+            const uint32_t d = plans[cnt].depth[s];
+            SearchStart& S = starts[cnt * kMaxSearches + s];
+            S.uni = d ? uni[d].data() : nullptr;
+            S.lof = (d && plans[cnt].need_lof[s]) ? lof[d].data() : nullptr;
+            S.a = plans[cnt].a[s]; S.d = d;
+        }
+    cx.starts = starts.data();
     std::memset(out, 0, text_len * (value_bits / 8));
     std::vector<WorkRange> ranges;
     build_work_ranges(text_len, K, chrom_cum, n_chrom, intervals, n_intervals, pos_begin, pos_end, ranges);
@@ -152,13 +170,13 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     unsigned long long f = 0, lr = 0;
 #define RUN_KW(KW) (ep ? run_ranges<KW, true>(cx, text, text_begin, ranges, value_bits, out, &f, &lr) \
                        : run_ranges<KW, false>(cx, text, text_begin, ranges, value_bits, out, &f, &lr))
-    if (K <= 32) RUN_KW(1);
-    else if (K <= 64) RUN_KW(2);
-    else if (K <= 128) RUN_KW(4);
-    else RUN_KW(8);
+    const uint32_t needle = K + B - 1; // characters a chain keeps in registers
+    if (needle <= 32) RUN_KW(1);
+    else if (needle <= 64) RUN_KW(2);
+    else if (needle <= 128) RUN_KW(4);
+    else RUN_KW(9);
     if (fetches) *fetches = f;
     if (lut_reads_out) *lut_reads_out = lr;
-    delete tabs;
     return 0;
 }
 

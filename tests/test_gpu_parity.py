@@ -108,6 +108,20 @@ def test_cuda_jump_table_depths_do_not_change_results(gm):
                 assert np.array_equal(_map(gm, ix, K, E, rc=rc, limits=limits), want), (K, E, rc, depth)
 
 
+@pytest.mark.parametrize("K,E", [(30, 1), (30, 2), (21, 3), (16, 4), (50, 2), (9, 1), (65, 1)])
+def test_cuda_block_size_does_not_change_results(gm, K, E):
+    """k-mers per block (the reference's -xo / overlap): every value gives the same counts (tests/tests.sh:47-60)."""
+    seqs = T.repeat_rich(7, 3, 2500) + [np.array([0, 1, 2], np.uint8), T.repeat_rich(9, 1, K + 3)[0]]
+    _, limits = T.concat(seqs)
+    orc, ix = T.Oracle(seqs), gm.Index.build(seqs)
+    want, want_nc = orc.map(K, E), orc.map(K, E, revcompl=False)
+    for B in (1, 2, 3, 5, 8, 16, 0):
+        p = gm.SearchParams(K, E, block_kmers=B)
+        assert np.array_equal(ix.compute_mappability(p, chrom_cum_lengths=limits), want), (K, E, B)
+        p = gm.SearchParams(K, E, rev_compl=False, block_kmers=B)
+        assert np.array_equal(ix.compute_mappability(p, chrom_cum_lengths=limits), want_nc), (K, E, B)
+
+
 def test_cuda_edge_cases(gm):
     # sequences shorter than K between longer ones, selection intervals, saturation, palindromes
     seqs = [np.array([0, 1, 2], np.uint8), T.repeat_rich(3, 1, 300)[0], np.array([3, 3], np.uint8),

@@ -133,3 +133,46 @@ def test_exclude_pseudo_matches_oracle(K, E, rc):
         for depth in (0, -1):
             got = hs.map(K, E, revcompl=rc, seq_to_file=stf, file_no=f, exclude_pseudo=True, jump_depth=depth)
             assert np.array_equal(got, want), (K, E, rc, f, depth)
+
+
+@pytest.mark.parametrize("K,E", [(30, 0), (30, 1), (30, 2), (21, 3), (16, 4), (50, 2), (9, 1), (3, 1), (4, 2), (65, 1), (33, 2)])
+def test_block_size_does_not_change_results(K, E):
+    """The reference's -xo invariance (tests/tests.sh:47-60): any number of k-mers per block gives the same counts."""
+    seqs = T.repeat_rich(7, 3, 2000) + [np.array([0, 1, 2], np.uint8), T.repeat_rich(9, 1, K + 3)[0]]
+    orc, hs = T.Oracle(seqs), T.HostSim(seqs)
+    want = orc.map(K, E)
+    want_nc = orc.map(K, E, revcompl=False)
+    for B in (1, 2, 3, 5, 8, 16, 0):
+        for depth in (0, -1):
+            assert np.array_equal(hs.map(K, E, block_kmers=B, jump_depth=depth), want), (K, E, B, depth)
+        assert np.array_equal(hs.map(K, E, block_kmers=B, revcompl=False), want_nc), (K, E, B)
+
+
+def test_blocked_search_saturation_selection_and_exclude_pseudo():
+    pal = [np.tile(np.array([0, 1, 2, 3], dtype=np.uint8), 1500)]
+    po, ph = T.Oracle(pal), T.HostSim(pal)
+    for bits in (8, 16):
+        for B in (1, 4, 7):
+            assert np.array_equal(ph.map(10, 2, value_bits=bits, block_kmers=B), po.map(10, 2, value_bits=bits))
+    seqs = T.repeat_rich(3, 2, 400)
+    orc, hs = T.Oracle(seqs), T.HostSim(seqs)
+    iv = [(0, 2), (10, 41), (35, 61), (390, 420), (700, 800)]
+    for B in (1, 3, 6):
+        assert np.array_equal(hs.map(12, 1, intervals=iv, block_kmers=B), orc.map(12, 1, intervals=iv))
+        parts = sum(hs.map(12, 1, pos_begin=b, pos_end=e, block_kmers=B).astype(np.int64) for b, e in [(0, 101), (101, 333), (333, 800)])
+        assert np.array_equal(parts, orc.map(12, 1))
+    base = T.repeat_rich(13, 2, 900)
+    rng = np.random.default_rng(5)
+    ms, stf = [], []
+    for g in range(4):
+        for s in base:
+            s = s.copy()
+            m = rng.random(len(s)) < 0.03 * g
+            s[m] = rng.integers(0, 4, int(m.sum()), dtype=np.uint8)
+            ms.append(s); stf.append(g)
+    stf = np.array(stf, dtype=np.uint32)
+    mo, mh = T.Oracle(ms, seq_to_file=stf), T.HostSim(ms, with_sa=True)
+    for f in (0, 2):
+        want = mo.map(25, 2, exclude_pseudo=True, file_no=f)
+        for B in (1, 4, 6):
+            assert np.array_equal(mh.map(25, 2, seq_to_file=stf, file_no=f, exclude_pseudo=True, block_kmers=B), want), (f, B)

@@ -29,11 +29,12 @@ n = ix.n_text
 out = torch.zeros(n, dtype=torch.int16, device="cuda")
 stream = torch.cuda.current_stream().cuda_stream
 for cfg in args.configs.split(","):
-    E, depth, batch = cfg.split(":")
-    E, depth, batch = int(E), int(depth), int(float(batch) * (1 << 20))
+    parts = cfg.split(":")
+    E, depth, batch = int(parts[0]), int(parts[1]), int(float(parts[2]) * (1 << 20))
+    blk = int(parts[3]) if len(parts) > 3 else 0
     batch = min(batch, n // 2)
     ix.set_jump_depth(depth)
-    p = gm.SearchParams(30, E)
+    p = gm.SearchParams(30, E, block_kmers=blk)
     t1 = time.time()
     st = ix.compute_mappability_device(p, out.data_ptr(), pos_begin=0, pos_end=1 << 16, stream=stream)  # builds tables
     setup = time.time() - t1
@@ -44,7 +45,7 @@ for cfg in args.configs.split(","):
         ms.append(st.kernel_ms); npos = st.positions
     b = 0
     st = ix.compute_mappability_device(p, out.data_ptr(), pos_begin=b, pos_end=b + batch, stream=stream, count_fetches=True)
-    print("E=%d depth=%2d(%2d) batch=%d  %.2f ms  %.1f Mpos/s  fetch/pos=%.1f lut/pos=%.2f  algGB/s=%.0f  setup=%.2fs free=%.1fGB"
-          % (E, depth, st.jump_depth, batch, np.median(ms), npos / np.median(ms) / 1e3, st.rank_block_fetches / st.positions,
+    print("E=%d B=%d depth=%2d(%2d) batch=%d  %.2f ms  %.1f Mpos/s  fetch/pos=%.1f lut/pos=%.2f  algGB/s=%.0f  setup=%.2fs free=%.1fGB"
+          % (E, blk, depth, st.jump_depth, batch, np.median(ms), npos / np.median(ms) / 1e3, st.rank_block_fetches / st.positions,
              st.jump_table_reads / st.positions, st.rank_block_fetches * 64 / st.positions * npos / np.median(ms) / 1e6,
              setup, torch.cuda.mem_get_info()[0] / 1e9), flush=True)
