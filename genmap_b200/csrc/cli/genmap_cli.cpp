@@ -357,7 +357,7 @@ int map_main(int argc, char const** argv)
     }
     const gmbcli::OutputType otype = a.has("frequency-small") ? gmbcli::OutputType::frequency_small
                                    : a.has("frequency-large") ? gmbcli::OutputType::frequency_large : gmbcli::OutputType::mappability;
-    if (a.has("overlap")) { // src/mappability.hpp:527-541 — validated for compatibility, irrelevant to the GPU kernel
+    if (a.has("overlap")) { // src/mappability.hpp:527-541: xo + 1 adjacent k-mers are searched through their common infix
         if (!to_uint(a.val["overlap"], xo)) { std::cerr << "GenMap map: the given value '" << a.val["overlap"] << "' cannot be casted to integer\n"; return 1; }
         const uint64_t mo = std::min<uint64_t>(K - 1, K - E - 2);
         if (xo > mo) { std::cerr << "ERROR: overlap cannot be larger than min(K - 1, K - E - 2) = " << mo << ".\n"; return 1; }
@@ -446,6 +446,7 @@ int map_main(int argc, char const** argv)
     p.revcompl = !a.has("no-reverse-complement");
     p.exclude_pseudo = a.has("exclude-pseudo");
     p.value_bits = otype == gmbcli::OutputType::frequency_small ? 8 : 16; // floats derive from uint16 (:390-393)
+    p.block_kmers = a.has("overlap") ? (uint32_t)xo + 1u : 0u;            // stepSize = K - overlap + 1 (src/algo.hpp:416); 0 = default
 
     const double t_start = wall();
     uint64_t start_pos = 0;

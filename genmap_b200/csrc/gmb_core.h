@@ -362,10 +362,12 @@ GMB_HD void jump_lookup(const SearchStart& S, uint32_t key, uint32_t& lo_f, uint
 }
 
 // start the infix search number st.s on the current strand
-template <int KW>
+// (BLK = false is the one-k-mer-per-chain instantiation: cnt == 1 is a compile-time fact there, so all the
+// window bookkeeping disappears and the count stays in a register)
+template <int KW, bool BLK>
 GMB_HD void chain_start(Chain<KW>& st, const MapCtx& cx, unsigned long long* lut_reads)
 {
-    const SearchStart S = cx.starts[st.cnt * kMaxSearches + st.s];
+    const SearchStart S = cx.starts[(BLK ? st.cnt : 1u) * kMaxSearches + st.s];
     st.e = 0; st.lvmask = 0; st.win = kNoWin; st.leaf_e = 0;
     if (S.uni == nullptr) {
         st.lo_f = 0; st.lo_r = 0; st.size = cx.n_bwt; st.t = 0;
@@ -378,30 +380,31 @@ GMB_HD void chain_start(Chain<KW>& st, const MapCtx& cx, unsigned long long* lut
 }
 
 // st.pat (needle of K + cnt - 1 characters) and st.cnt are set by the caller
-template <int KW, bool EP, class Frames>
+template <int KW, bool EP, bool BLK, class Frames>
 GMB_HD void chain_begin_block(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned long long* lut_reads)
 {
     st.acc = 0; st.s = 0; st.strand = 0; st.files = 0;
-    if (cx.B > 1) {
+    if (!BLK) st.cnt = 1;
+    if (BLK) {
         const uint32_t per = EP ? 3u : 1u;
         for (uint32_t w = 0; w < st.cnt * per; ++w) fr.xset(kLeafWords + w, 0u);
     }
     // the reverse strand's first jump-table entry does not depend on the forward search: request it now so
     // that its latency overlaps the forward strand instead of starting the reverse strand with a stall
-    const SearchStart S0 = cx.starts[st.cnt * kMaxSearches];
+    const SearchStart S0 = cx.starts[(BLK ? st.cnt : 1u) * kMaxSearches];
     if (cx.n_strands > 1 && S0.uni != nullptr) {
         Pattern<KW> rc = st.pat;
-        rc.reverse_complement(cx.K + st.cnt - 1);
+        rc.reverse_complement(cx.K + (BLK ? st.cnt : 1u) - 1);
         jump_lookup(S0, rc.bits(S0.a, S0.d), st.pre_lo_f, st.pre_lo_r, st.pre_size);
     }
-    chain_start(st, cx, lut_reads);
+    chain_start<KW, BLK>(st, cx, lut_reads);
 }
 
 // result of window w (position j0 + w) once chain_step has returned false
-template <int KW, bool EP, class Frames>
+template <int KW, bool EP, bool BLK, class Frames>
 GMB_HD uint32_t chain_result(const Chain<KW>& st, const Frames& fr, const MapCtx& cx, uint32_t w)
 {
-    if (cx.B == 1) return st.acc;
+    if (!BLK) return st.acc;
     if (!EP) return fr.xget(kLeafWords + w);
     const uint64_t m = (uint64_t)fr.xget(kLeafWords + st.cnt + 2 * w) | ((uint64_t)fr.xget(kLeafWords + st.cnt + 2 * w + 1) << 32);
 #if defined(__CUDA_ARCH__)
@@ -435,43 +438,43 @@ GMB_HD uint32_t highest_bit_index(uint32_t m)
 }
 
 // add `n` occurrences (or, under --exclude-pseudo, the files of SA rows [lo, lo+n)) to window `w` of the strand
-template <int KW, bool EP, class Frames>
+template <int KW, bool EP, bool BLK, class Frames>
 GMB_HD void chain_count(Chain<KW>& st, Frames& fr, const MapCtx& cx, uint32_t w, uint32_t lo, uint32_t n, bool own_only)
 {
-    const uint32_t widx = st.strand ? st.cnt - 1u - w : w; // reverse-strand windows run backwards (src/algo.hpp:304)
+    const uint32_t widx = !BLK ? 0u : (st.strand ? st.cnt - 1u - w : w); // reverse-strand windows run backwards (src/algo.hpp:304)
     if (EP) {
-        uint64_t m = cx.B == 1 ? st.files
+        uint64_t m = !BLK ? st.files
                                : (uint64_t)fr.xget(kLeafWords + st.cnt + 2 * widx) | ((uint64_t)fr.xget(kLeafWords + st.cnt + 2 * widx + 1) << 32);
         if (own_only) m |= 1ull << cx.own_file;
         else ep_mark_rows(m, lo, n, cx);
-        if (cx.B == 1) st.files = m;
+        if (!BLK) st.files = m;
         else { fr.xset(kLeafWords + st.cnt + 2 * widx, (uint32_t)m); fr.xset(kLeafWords + st.cnt + 2 * widx + 1, (uint32_t)(m >> 32)); }
     } else {
-        const uint32_t old = cx.B == 1 ? st.acc : fr.xget(kLeafWords + widx);
+        const uint32_t old = !BLK ? st.acc : fr.xget(kLeafWords + widx);
         const uint64_t sum = (uint64_t)old + n;
         const uint32_t v = sum < cx.maxv ? (uint32_t)sum : cx.maxv; // saturating (src/algo.hpp:48,191)
-        if (cx.B == 1) st.acc = v; else fr.xset(kLeafWords + widx, v);
+        if (!BLK) st.acc = v; else fr.xset(kLeafWords + widx, v);
     }
 }
 
 // One state-machine iteration.  Returns false when the block is finished (results via chain_result).
 // `fetches` counts rank-block reads (the roofline's algorithmic unit), when non-null.
-template <int KW, bool EP, class Frames>
+template <int KW, bool EP, bool BLK, class Frames>
 GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned long long* fetches,
                        unsigned long long* lut_reads)
 {
-    const uint32_t K = cx.K, cnt = st.cnt;
+    const uint32_t K = cx.K, cnt = BLK ? st.cnt : 1u;
     const uint32_t Li = K - cnt + 1; // infix length
 
-    if (st.win == kNoWin && st.t == Li) {
+    if (BLK && st.win == kNoWin && st.t == Li) {
         // the whole infix is matched (only reached when cnt > 1): this node is an infix hit; complete it for
         // every window, starting with window 0.  Frames of levels >= e are free here.
         fr.xset(0, st.lo_f); fr.xset(1, st.lo_r); fr.xset(2, st.size);
         st.leaf_e = st.e; st.win = 0; st.t = 0;
     }
-    const bool in_flank = st.win != kNoWin;
+    const bool in_flank = BLK && st.win != kNoWin;
     const uint32_t T = in_flank ? cnt - 1u : Li; // steps of the current walk
-    const uint32_t tab = in_flank ? cx.fl_off[cnt] + st.win * (cnt - 1u) : cx.p1_off[cnt] + st.s * Li;
+    const uint32_t tab = in_flank ? cx.fl_off[cnt] + st.win * (cnt - 1u) : (BLK ? cx.p1_off[cnt] : 0u) + st.s * Li;
     const uint32_t ent = cx.steps[tab + st.t];
     const uint32_t dir = step_dir(ent);
     const uint32_t p = st.pat.at(step_pos(ent)); // on the reverse strand st.pat already holds the reverse complement
@@ -485,8 +488,8 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
         // Forward strand, no error so far, one occurrence left: it is the query's own position in the
         // indexed text, so the rest of the pattern matches it exactly and no mismatching extension
         // exists.  The subtree contributes exactly one occurrence per window — no need to walk it.
-        if (in_flank) chain_count<KW, EP>(st, fr, cx, st.win, 0, 1, true);
-        else for (uint32_t w = 0; w < cnt; ++w) chain_count<KW, EP>(st, fr, cx, w, 0, 1, true);
+        if (in_flank) chain_count<KW, EP, BLK>(st, fr, cx, st.win, 0, 1, true);
+        else for (uint32_t w = 0; w < cnt; ++w) chain_count<KW, EP, BLK>(st, fr, cx, w, 0, 1, true);
     } else {
         // ---- expand the node: ranks at both interval ends of the active index -----------------------
         const uint32_t x = dir ? st.lo_r : st.lo_f;
@@ -538,14 +541,14 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
                 // rows in SA(T): the active index's children when extending left, else the synchronised side
                 const uint32_t f0 = dir ? oth0 : l0, f1 = dir ? oth0 + n0 : l1, f2 = dir ? oth0 + n0 + n1 : l2,
                                f3 = dir ? oth0 + n0 + n1 + n2 : l3;
-                if (ok & 1u) chain_count<KW, EP>(st, fr, cx, w, f0, n0, false);
-                if (ok & 2u) chain_count<KW, EP>(st, fr, cx, w, f1, n1, false);
-                if (ok & 4u) chain_count<KW, EP>(st, fr, cx, w, f2, n2, false);
-                if (ok & 8u) chain_count<KW, EP>(st, fr, cx, w, f3, n3, false);
+                if (ok & 1u) chain_count<KW, EP, BLK>(st, fr, cx, w, f0, n0, false);
+                if (ok & 2u) chain_count<KW, EP, BLK>(st, fr, cx, w, f1, n1, false);
+                if (ok & 4u) chain_count<KW, EP, BLK>(st, fr, cx, w, f2, n2, false);
+                if (ok & 8u) chain_count<KW, EP, BLK>(st, fr, cx, w, f3, n3, false);
             } else {
                 const uint64_t sum = (uint64_t)((ok & 1u) ? n0 : 0u) + ((ok & 2u) ? n1 : 0u) + ((ok & 4u) ? n2 : 0u) +
                                      ((ok & 8u) ? n3 : 0u);
-                chain_count<KW, EP>(st, fr, cx, w, 0, sum < cx.maxv ? (uint32_t)sum : cx.maxv, false);
+                chain_count<KW, EP, BLK>(st, fr, cx, w, 0, sum < cx.maxv ? (uint32_t)sum : cx.maxv, false);
             }
         } else if (ok) {
             const uint32_t mm = ok & ~(1u << p);
@@ -573,7 +576,7 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
         // While an infix hit is being completed, the frames of its window walks sit at levels >= leaf_e and
         // the infix search's own pending frames below that.
         uint32_t cand = st.lvmask;
-        if (st.win != kNoWin) {
+        if (BLK && st.win != kNoWin) {
             cand = (st.lvmask >> st.leaf_e) << st.leaf_e;
             if (cand == 0) {
                 // this window is done: next window from the saved infix hit, or back to the infix search
@@ -591,7 +594,7 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
             if (++st.s == cx.n_search) {
                 st.s = 0;
                 if (++st.strand == cx.n_strands) {
-                    if (EP && cx.B == 1) { // distinct FASTA files with at least one occurrence on either strand (:360)
+                    if (EP && !BLK) { // distinct FASTA files with at least one occurrence on either strand (:360)
 #if defined(__CUDA_ARCH__)
                         st.acc = (uint32_t)__popcll(st.files);
 #else
@@ -602,14 +605,14 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
                 }
                 st.pat.reverse_complement(K + cnt - 1);
             }
-            chain_start(st, cx, lut_reads);
+            chain_start<KW, BLK>(st, cx, lut_reads);
             return true;
         }
         const uint32_t lv = highest_bit_index(cand);
         const uint32_t meta = fr.get(lv, 9);
         const uint32_t tf = meta & 0xffu;
         uint32_t pending = meta >> 8;
-        const uint32_t tabf = st.win != kNoWin ? cx.fl_off[cnt] + st.win * (cnt - 1u) : cx.p1_off[cnt] + st.s * Li;
+        const uint32_t tabf = (BLK && st.win != kNoWin) ? cx.fl_off[cnt] + st.win * (cnt - 1u) : (BLK ? cx.p1_off[cnt] : 0u) + st.s * Li;
         const uint32_t entf = cx.steps[tabf + tf];
         const uint32_t pf = st.pat.at(step_pos(entf));
         const uint32_t mm = pending & ~(1u << pf);

@@ -85,7 +85,7 @@ uint32_t default_block_kmers(uint32_t K, uint32_t E)
     // E >= 1: the infix search dominates and is shared by the block; more k-mers per block shorten the infix,
     // which makes its search bushier (same trade-off as the reference's overlap, src/mappability.hpp:519-543).
     if (E == 0) return 1;
-    uint32_t b = E == 1 ? 8u : (E == 2 ? 6u : 4u);
+    uint32_t b = E == 1 ? 4u : (E == 2 ? 6u : 4u);    // measured at 3 Gbp, K = 30: profiles/r01/s7_sweep_block_sizes.txt
     const uint32_t cap = K > E + 1 ? K - E - 1 : 1; // the infix must keep one character per scheme block
     while (b > 1 && (b > cap || b * 4 > K)) --b;    // and stay most of the k-mer
     return b < 1 ? 1 : b;

@@ -38,7 +38,7 @@ struct SmemFrames {
 __host__ __device__ inline uint32_t align32(uint32_t x) { return (x + 31u) & ~31u; }
 constexpr uint32_t kStartWords = sizeof(SearchStart) / 4;
 
-template <int KW, bool COUNT, typename OutT, bool EP>
+template <int KW, bool COUNT, typename OutT, bool EP, bool BLK>
 __global__ void __launch_bounds__(kThreads, GMB_MIN_BLOCKS) map_kernel(const MapLaunch L)
 {
     // shared memory: step tables | jump-table starts | offsets | per-chain frame store
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, GMB_MIN_BLOCKS) map_kernel(const Map
                 if (got) {
                     st.cnt = (uint32_t)(jend - j < B ? jend - j : B);
                     load_pattern(st.pat, L.text, L.text_begin + j, cx.K + st.cnt - 1);
-                    chain_begin_block<KW, EP>(st, fr, cx, COUNT ? &lut_reads : nullptr);
+                    chain_begin_block<KW, EP, BLK>(st, fr, cx, COUNT ? &lut_reads : nullptr);
                     active = true;
                 } else if (pool_done) {
                     exhausted = true;
@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(kThreads, GMB_MIN_BLOCKS) map_kernel(const Map
 
         // ---- one node expansion per chain -------------------------------------------------------------
         if (active) {
-            if (!chain_step<KW, EP>(st, fr, cx, COUNT ? &fetches : nullptr, COUNT ? &lut_reads : nullptr)) {
-                for (uint32_t w = 0; w < st.cnt; ++w) out[j + w] = (OutT)chain_result<KW, EP>(st, fr, cx, w);
+            if (!chain_step<KW, EP, BLK>(st, fr, cx, COUNT ? &fetches : nullptr, COUNT ? &lut_reads : nullptr)) {
+                for (uint32_t w = 0; w < st.cnt; ++w) out[j + w] = (OutT)chain_result<KW, EP, BLK>(st, fr, cx, w);
                 active = false;
             }
         }
@@ -153,10 +153,10 @@ __global__ void __launch_bounds__(kThreads, GMB_MIN_BLOCKS) map_kernel(const Map
     }
 }
 
-template <int KW, bool COUNT, typename OutT, bool EP>
-cudaError_t launch_t(const MapLaunch& L, int sm_count, cudaStream_t stream)
+template <int KW, bool COUNT, typename OutT, bool EP, bool BLK>
+cudaError_t launch_b(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
-    auto kern = map_kernel<KW, COUNT, OutT, EP>;
+    auto kern = map_kernel<KW, COUNT, OutT, EP, BLK>;
     const size_t smem = map_kernel_smem_bytes(L.n_step_words, L.E, L.cx.B, EP);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -170,6 +170,12 @@ cudaError_t launch_t(const MapLaunch& L, int sm_count, cudaStream_t stream)
     if (want < grid) grid = want ? want : 1;
     kern<<<(unsigned)grid, kThreads, smem, stream>>>(L);
     return cudaGetLastError();
+}
+
+template <int KW, bool COUNT, typename OutT, bool EP>
+cudaError_t launch_t(const MapLaunch& L, int sm_count, cudaStream_t stream)
+{
+    return L.cx.B > 1 ? launch_b<KW, COUNT, OutT, EP, true>(L, sm_count, stream) : launch_b<KW, COUNT, OutT, EP, false>(L, sm_count, stream);
 }
 
 template <int KW>

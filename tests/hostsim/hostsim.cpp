@@ -24,7 +24,7 @@ struct HostFrames {
     inline uint32_t xget(uint32_t i) const { return x[i]; }
 };
 
-template <int KW, bool EP>
+template <int KW, bool EP, bool BLK>
 void run_ranges(const MapCtx& cx, const uint64_t* text, uint64_t text_begin, const std::vector<WorkRange>& ranges,
                 int value_bits, void* out, unsigned long long* fetches, unsigned long long* lut_reads)
 {
@@ -34,10 +34,10 @@ void run_ranges(const MapCtx& cx, const uint64_t* text, uint64_t text_begin, con
             HostFrames fr;
             st.cnt = (uint32_t)std::min<uint64_t>(cx.B, r.end - j0);
             load_pattern(st.pat, text, text_begin + j0, cx.K + st.cnt - 1);
-            chain_begin_block<KW, EP>(st, fr, cx, lut_reads);
-            while (chain_step<KW, EP>(st, fr, cx, fetches, lut_reads)) {}
+            chain_begin_block<KW, EP, BLK>(st, fr, cx, lut_reads);
+            while (chain_step<KW, EP, BLK>(st, fr, cx, fetches, lut_reads)) {}
             for (uint32_t w = 0; w < st.cnt; ++w) {
-                const uint32_t v = chain_result<KW, EP>(st, fr, cx, w);
+                const uint32_t v = chain_result<KW, EP, BLK>(st, fr, cx, w);
                 if (value_bits == 16) static_cast<uint16_t*>(out)[j0 + w] = (uint16_t)v;
                 else static_cast<uint8_t*>(out)[j0 + w] = (uint8_t)v;
             }
@@ -168,8 +168,9 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     build_work_ranges(text_len, K, chrom_cum, n_chrom, intervals, n_intervals, pos_begin, pos_end, ranges);
     const uint64_t* text = reinterpret_cast<const uint64_t*>(base + h.off_text);
     unsigned long long f = 0, lr = 0;
-#define RUN_KW(KW) (ep ? run_ranges<KW, true>(cx, text, text_begin, ranges, value_bits, out, &f, &lr) \
-                       : run_ranges<KW, false>(cx, text, text_begin, ranges, value_bits, out, &f, &lr))
+#define RUN_KB(KW, BLK) (ep ? run_ranges<KW, true, BLK>(cx, text, text_begin, ranges, value_bits, out, &f, &lr) \
+                            : run_ranges<KW, false, BLK>(cx, text, text_begin, ranges, value_bits, out, &f, &lr))
+#define RUN_KW(KW) (B > 1 ? RUN_KB(KW, true) : RUN_KB(KW, false))
     const uint32_t needle = K + B - 1; // characters a chain keeps in registers
     if (needle <= 32) RUN_KW(1);
     else if (needle <= 64) RUN_KW(2);
