@@ -422,9 +422,9 @@ def main():
                 continue
             b2 = int(default_batch(E2) * (1 << 20))
             b2 = max(1 << 14, min(b2, (shard_e - shard_b) // 2))
-            r2 = measure(E2, b2, max(2, args.steps // 2), 1, False, False)
+            r2 = measure(E2, b2, max(3, args.steps // 2), 3, False, False)
             r2["E"], r2["batch"] = E2, b2
-            extras["K%d_E%d" % (K, E2)] = {"value": r2["value"], "unit": UNIT, "ms_per_step": r2["ms"] / max(2, args.steps // 2),
+            extras["K%d_E%d" % (K, E2)] = {"value": r2["value"], "unit": UNIT, "ms_per_step": r2["ms"] / max(3, args.steps // 2),
                                           "positions_per_step": b2, "roofline": roofline(r2)}
 
     cpu = None
@@ -433,6 +433,10 @@ def main():
             arm = make_cpu_arm(seqs, ix)
             rate, _, npos_cpu = cpu_rate(arm, K, E, args.cpu_seconds)
             cpu = {"value": rate, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample(npos_cpu, K)}
+            for name, ex in extras.items():  # the same CPU arm for the other (K,E) lines, shorter samples
+                E2 = int(name.split("_E")[1])
+                r2, _, n2 = cpu_rate(arm, K, E2, args.cpu_seconds / 2)
+                ex["cpu_baseline"] = {"value": r2, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample(n2, K)}
             arm.close()
         except Exception as ex:  # the baseline is a reported extra; never lose the GPU line over it
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}

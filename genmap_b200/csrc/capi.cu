@@ -75,6 +75,8 @@ struct gmb_index {
     size_t out_cap = 0;
     uint32_t* d_seq_to_file = nullptr; // --exclude-pseudo: device copy of the caller's mapping
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr; // host-output pipeline (gmb_map_frequencies_range)
+    cudaEvent_t ev_piece[2] = {nullptr, nullptr};
     // jump tables by depth (index 0 unused), built lazily; levels <= kJumpKeep stay cached
     int jump_depth_opt = -1;
     JtEntry* jt_uni[17] = {};
@@ -341,6 +343,9 @@ int gmb_index_close(gmb_index* ix)
     if (ix->d_out) cudaFree(ix->d_out);
     if (ix->d_seq_to_file) cudaFree(ix->d_seq_to_file);
     for (int d = 0; d < 17; ++d) { if (ix->jt_uni[d]) cudaFree(ix->jt_uni[d]); if (ix->jt_lof[d]) cudaFree(ix->jt_lof[d]); }
+    if (ix->s_compute) cudaStreamDestroy(ix->s_compute);
+    if (ix->s_copy) cudaStreamDestroy(ix->s_copy);
+    for (int i = 0; i < 2; ++i) if (ix->ev_piece[i]) cudaEventDestroy(ix->ev_piece[i]);
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);
     delete ix;
@@ -369,11 +374,15 @@ int gmb_index_set_jump_depth(gmb_index* ix, int depth)
     return GMB_OK;
 }
 
-int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len,
-                               const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t (*intervals)[2],
-                               uint64_t n_intervals, const uint32_t* seq_to_file, uint32_t n_seq,
-                               uint64_t pos_begin, uint64_t pos_end, void* out_device, void* cuda_stream,
-                               gmb_map_stats* stats)
+} // extern "C"
+
+// stats != nullptr && timed: bracket the kernel with events and wait for it; stats != nullptr && !timed: only
+// fill the host-side fields (positions, jump depth) and return without synchronising
+static int map_device_impl(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len,
+                           const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t (*intervals)[2],
+                           uint64_t n_intervals, const uint32_t* seq_to_file, uint32_t n_seq,
+                           uint64_t pos_begin, uint64_t pos_end, void* out_device, void* cuda_stream,
+                           gmb_map_stats* stats, bool timed)
 {
     if (!ix || !p || !chrom_cum || !out_device) return fail(GMB_ERR_ARG, "gmb_map_frequencies: NULL argument");
     if (p->value_bits != 8 && p->value_bits != 16) return fail(GMB_ERR_ARG, "value_bits must be 8 or 16");
@@ -507,9 +516,10 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
         L.cx.all_files = n_files == 64 ? ~0ull : ((1ull << n_files) - 1ull);
     }
 
-    if (stats) CU(cudaEventRecord(ix->ev0, stream));
+    if (stats) { stats->jump_depth = plan_depth; stats->kernel_launches = 1; }
+    if (stats && timed) CU(cudaEventRecord(ix->ev0, stream));
     CU(launch_map_kernel(L, ix->sm_count, stream));
-    if (stats) {
+    if (stats && timed) {
         CU(cudaEventRecord(ix->ev1, stream));
         CU(cudaEventSynchronize(ix->ev1));
         float ms = 0.f;
@@ -525,6 +535,18 @@ int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text
         }
     }
     return GMB_OK;
+}
+
+extern "C" {
+
+int gmb_map_frequencies_device(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len,
+                               const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t (*intervals)[2],
+                               uint64_t n_intervals, const uint32_t* seq_to_file, uint32_t n_seq,
+                               uint64_t pos_begin, uint64_t pos_end, void* out_device, void* cuda_stream,
+                               gmb_map_stats* stats)
+{
+    return map_device_impl(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, seq_to_file, n_seq,
+                           pos_begin, pos_end, out_device, cuda_stream, stats, true);
 }
 
 int gmb_map_frequencies_range(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len,
@@ -546,14 +568,50 @@ int gmb_map_frequencies_range(gmb_index* ix, const gmb_params* p, uint64_t text_
         CU(cudaMalloc(&ix->d_out, bytes ? bytes : 1));
         ix->out_cap = bytes;
     }
-    CU(cudaMemsetAsync(ix->d_out, 0, bytes, nullptr));
-    gmb_map_stats local;
     // the kernel indexes its output by file-local position: bias the base so the slice starts at pos_begin
     void* biased = reinterpret_cast<void*>(reinterpret_cast<uintptr_t>(ix->d_out) - (uintptr_t)pos_begin * elem);
-    int rc = gmb_map_frequencies_device(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals,
-                                        seq_to_file, n_seq, pos_begin, pos_end, biased, nullptr, &local);
-    if (rc != GMB_OK) return rc;
-    CU(cudaMemcpy(out, ix->d_out, bytes, cudaMemcpyDeviceToHost));
+    gmb_map_stats local;
+    std::memset(&local, 0, sizeof(local));
+    const uint64_t piece = 32ull << 20; // positions per pipeline stage
+    if (p->count_fetches || pos_end - pos_begin <= piece) {
+        CU(cudaMemsetAsync(ix->d_out, 0, bytes, nullptr));
+        int rc = map_device_impl(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, seq_to_file, n_seq,
+                                 pos_begin, pos_end, biased, nullptr, &local, true);
+        if (rc != GMB_OK) return rc;
+        CU(cudaMemcpy(out, ix->d_out, bytes, cudaMemcpyDeviceToHost));
+    } else {
+        // pipeline: the search of piece i+1 (compute stream) overlaps the device-to-host copy of piece i (copy stream)
+        if (!ix->s_compute) {
+            CU(cudaStreamCreateWithFlags(&ix->s_compute, cudaStreamNonBlocking));
+            CU(cudaStreamCreateWithFlags(&ix->s_copy, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&ix->ev_piece[0], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ix->ev_piece[1], cudaEventDisableTiming));
+        }
+        CU(cudaMemsetAsync(ix->d_out, 0, bytes, ix->s_compute));
+        CU(cudaEventRecord(ix->ev0, ix->s_compute));
+        uint32_t n_piece = 0;
+        for (uint64_t b = pos_begin; b < pos_end; b += piece, ++n_piece) {
+            const uint64_t e = std::min(b + piece, pos_end);
+            gmb_map_stats st;
+            int rc = map_device_impl(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, seq_to_file,
+                                     n_seq, b, e, biased, ix->s_compute, &st, false);
+            if (rc != GMB_OK) { cudaStreamSynchronize(ix->s_compute); cudaStreamSynchronize(ix->s_copy); return rc; }
+            local.positions += st.positions;
+            local.kernel_launches += st.kernel_launches;
+            local.jump_depth = st.jump_depth;
+            CU(cudaEventRecord(ix->ev_piece[n_piece & 1], ix->s_compute));
+            CU(cudaStreamWaitEvent(ix->s_copy, ix->ev_piece[n_piece & 1], 0));
+            CU(cudaMemcpyAsync(static_cast<uint8_t*>(out) + (b - pos_begin) * elem,
+                               static_cast<const uint8_t*>(ix->d_out) + (b - pos_begin) * elem, (e - b) * elem,
+                               cudaMemcpyDeviceToHost, ix->s_copy));
+        }
+        CU(cudaEventRecord(ix->ev1, ix->s_compute));
+        CU(cudaStreamSynchronize(ix->s_compute));
+        CU(cudaStreamSynchronize(ix->s_copy));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
+        local.kernel_ms = ms;
+    }
     if (stats) *stats = local;
     return GMB_OK;
 }

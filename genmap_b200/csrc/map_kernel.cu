@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kThreads, GMB_MIN_BLOCKS) map_kernel(const Map
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     OutT* __restrict__ out = static_cast<OutT*>(L.out);
-    const unsigned long long B = cx.B;
+    const unsigned long long B = BLK ? cx.B : 1ull;
 
     Chain<KW> st;
     uint64_t j = 0; // first position of the chain's block
