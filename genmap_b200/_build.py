@@ -57,10 +57,26 @@ def build(force=False, verbose=False):
         build_cli(force, verbose)
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc()] + NVCC_FLAGS + ["-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
+    obj_dir = os.path.join(HERE, "..", "build", "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    env = dict(os.environ, CC="", CXX="")
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, src.replace(".", "_") + ".o")
+        cmd = [nvcc()] + flags + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True, env=env)
+        return obj
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    cmd = [nvcc()] + NVCC_FLAGS + ["-o", LIB + ".tmp"] + objs
     if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True, env=dict(os.environ, CC="", CXX=""))
+        print(" ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True, env=env)
     os.replace(LIB + ".tmp", LIB)
     build_cli(True, verbose)
     return LIB

@@ -25,7 +25,7 @@ class GmbParams(ctypes.Structure):
 class GmbIndexInfo(ctypes.Structure):
     _fields_ = [("n_text", ctypes.c_uint64), ("n_bwt", ctypes.c_uint64), ("n_seq", ctypes.c_uint32),
                 ("has_sa", ctypes.c_uint32), ("blob_bytes", ctypes.c_uint64), ("rank_block_bytes", ctypes.c_uint64),
-                ("device_blob", ctypes.c_void_p), ("device", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("device_blob", ctypes.c_void_p), ("device", ctypes.c_int32), ("alphabet_size", ctypes.c_int32)]
 
 
 class GmbMapStats(ctypes.Structure):

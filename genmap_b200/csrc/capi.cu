@@ -53,6 +53,17 @@ __global__ void k_decode_bwt(const RankBlock* __restrict__ B, uint64_t n, uint8_
     out[i] = (uint8_t)(1u + (uint32_t)((b.w[k >> 6][0] >> (k & 63)) & 1u) + 2u * (uint32_t)((b.w[k >> 6][1] >> (k & 63)) & 1u));
 }
 
+__global__ void k_decode_bwt5(const RankBlock5* __restrict__ B, uint64_t n, uint8_t* __restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RankBlock5& b = B[i / kBlockBases5];
+    const uint32_t k = (uint32_t)(i % kBlockBases5);
+    uint32_t c = 0;
+    for (int pl = 0; pl < 3; ++pl) c |= ((b.plane[pl][k >> 5] >> (k & 31)) & 1u) << pl;
+    out[i] = (uint8_t)(1u + c);
+}
+
 __global__ void k_mark_sentinels(const uint32_t* __restrict__ S, uint32_t n_seq, uint8_t* __restrict__ out)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,11 +102,11 @@ constexpr size_t kTableBytes = 256 << 10; // device scratch for the search table
 void fill_ctx(const gmb_index* ix, MapCtx& cx)
 {
     const uint8_t* base = ix->d_blob;
-    cx.blk[0] = reinterpret_cast<const RankBlock*>(base + ix->h.off_fwd);
-    cx.blk[1] = reinterpret_cast<const RankBlock*>(base + ix->h.off_rev);
+    cx.blk[0] = base + ix->h.off_fwd;
+    cx.blk[1] = base + ix->h.off_rev;
     cx.sent[0] = reinterpret_cast<const uint32_t*>(base + ix->h.off_sent_fwd);
     cx.sent[1] = reinterpret_cast<const uint32_t*>(base + ix->h.off_sent_rev);
-    for (int c = 0; c < 4; ++c) cx.C[c] = (uint32_t)ix->h.C[c];
+    for (int c = 0; c < 5; ++c) cx.C[c] = (uint32_t)ix->h.C[c];
     cx.n_bwt = (uint32_t)ix->h.n_bwt;
     cx.steps = nullptr; cx.p1_off = nullptr; cx.fl_off = nullptr;
     cx.starts = nullptr;
@@ -131,7 +142,7 @@ int ensure_jump_tables(gmb_index* ix, const std::vector<JumpPlan>& plans, cudaSt
         const size_t n = (size_t)1 << (2 * d);
         cudaError_t e = cudaMalloc(&ix->jt_uni[d], n * sizeof(JtEntry));
         if (e == cudaSuccess && want_lof) e = cudaMalloc(&ix->jt_lof[d], n * sizeof(uint32_t));
-        if (e == cudaSuccess) e = build_jump_level(cx, d, ix->jt_uni[d - 1], ix->jt_lof[d - 1], ix->jt_uni[d], ix->jt_lof[d], stream);
+        if (e == cudaSuccess) e = build_jump_level(cx, ix->h.sigma, d, ix->jt_uni[d - 1], ix->jt_lof[d - 1], ix->jt_uni[d], ix->jt_lof[d], stream);
         if (e != cudaSuccess) return cuda_fail(e, "jump table");
     }
     CU(cudaStreamSynchronize(stream));
@@ -361,7 +372,8 @@ int gmb_index_get_info(const gmb_index* ix, gmb_index_info* info)
     info->n_seq = ix->h.n_seq;
     info->has_sa = ix->h.off_sa != 0;
     info->blob_bytes = ix->h.total_bytes;
-    info->rank_block_bytes = kBlockBytes;
+    info->rank_block_bytes = block_bytes(ix->h.sigma);
+    info->alphabet_size = (int32_t)ix->h.sigma;
     info->device_blob = ix->d_blob;
     info->device = ix->device;
     return GMB_OK;
@@ -407,7 +419,7 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p, uint64_t text_beg
         if (want_b == 0) { const char* env = std::getenv("GMB_BLOCK_KMERS"); if (env && *env) want_b = (uint32_t)std::atoi(env); }
         if (!build_block_tables(p->K, p->E, want_b, p->exclude_pseudo != 0, tabs, err)) return fail(GMB_ERR_UNSUPPORTED, err);
         // the tables and the per-chain frame store live in shared memory: shrink the block if they do not fit
-        while (tabs.B > 1 && (map_kernel_smem_bytes((uint32_t)tabs.steps.size(), p->E, tabs.B, p->exclude_pseudo != 0) > (200u << 10) ||
+        while (tabs.B > 1 && (map_kernel_smem_bytes((uint32_t)tabs.steps.size(), p->E, tabs.B, p->exclude_pseudo != 0, ix->h.sigma) > (200u << 10) ||
                               tabs.steps.size() * 4 + (tabs.B + 1) * kMaxSearches * sizeof(SearchStart) > kTableBytes))
             if (!build_block_tables(p->K, p->E, tabs.B - 1, p->exclude_pseudo != 0, tabs, err)) return fail(GMB_ERR_UNSUPPORTED, err);
     }
@@ -494,7 +506,9 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p, uint64_t text_beg
     L.cx.n_strands = p->revcompl ? 2u : 1u;
     L.cx.maxv = p->value_bits == 16 ? 65535u : 255u;
     L.E = p->E;
+    L.sigma = ix->h.sigma;
     L.text = reinterpret_cast<const uint64_t*>(base + ix->h.off_text);
+    L.nmask = ix->h.sigma == 5 ? reinterpret_cast<const uint64_t*>(base + ix->h.off_nmask) : nullptr;
     L.text_begin = text_begin;
     L.range_begin = ix->d_ranges;
     L.range_end = ix->d_ranges + nr;
@@ -641,9 +655,10 @@ int gmb_index_export_bwt(gmb_index* ix, int rev, uint8_t* out_host)
     const uint64_t n = ix->h.n_bwt;
     uint8_t* d = nullptr;
     CU(cudaMalloc(&d, n ? n : 1));
-    const RankBlock* B = reinterpret_cast<const RankBlock*>(ix->d_blob + (rev ? ix->h.off_rev : ix->h.off_fwd));
+    const uint8_t* Bp = ix->d_blob + (rev ? ix->h.off_rev : ix->h.off_fwd);
     const uint32_t* S = reinterpret_cast<const uint32_t*>(ix->d_blob + (rev ? ix->h.off_sent_rev : ix->h.off_sent_fwd));
-    k_decode_bwt<<<(unsigned)((n + 255) / 256), 256>>>(B, n, d);
+    if (ix->h.sigma == 5) k_decode_bwt5<<<(unsigned)((n + 255) / 256), 256>>>(reinterpret_cast<const RankBlock5*>(Bp), n, d);
+    else k_decode_bwt<<<(unsigned)((n + 255) / 256), 256>>>(reinterpret_cast<const RankBlock*>(Bp), n, d);
     k_mark_sentinels<<<(ix->h.n_seq + 255) / 256, 256>>>(S, ix->h.n_seq, d);
     cudaError_t e = cudaMemcpy(out_host, d, n, cudaMemcpyDeviceToHost);
     cudaFree(d);

@@ -274,7 +274,8 @@ int index_main(int argc, char const** argv)
         std::ofstream ids(base + "index.ids");
         for (const std::string& l : ids_lines) ids << l << '\n';
         std::ofstream info(base + "index.info"); // same keys as src/indexing.hpp:105-111 where they apply
-        info << "alphabet_size:4\n" << "fasta_directory:" << (fd ? "true" : "false") << "\n"
+        const bool dna5 = std::find(codes.begin(), codes.end(), (uint8_t)4) != codes.end(); // src/indexing.hpp:459-473
+        info << "alphabet_size:" << (dna5 ? 5 : 4) << "\n" << "fasta_directory:" << (fd ? "true" : "false") << "\n"
              << "full_suffix_array:" << (a.has("no-sa") ? "false" : "true") << "\n" << "format:genmap-b200-2\n";
     }
     if (a.has("verbose")) std::cout << "done in " << round2(wall() - t0) << " seconds\n";
@@ -428,7 +429,7 @@ int map_main(int argc, char const** argv)
     gmb_index_info iinfo;
     gmb_index_get_info(ixs[0], &iinfo);
     if (a.has("verbose")) {
-        std::cout << "Index was loaded (dna4 alphabet, " << iinfo.blob_bytes << " bytes in the HBM of " << gpu << " GPU(s)).\n";
+        std::cout << "Index was loaded (" << (iinfo.alphabet_size == 5 ? "dna5" : "dna4") << " alphabet, " << iinfo.blob_bytes << " bytes in the HBM of " << gpu << " GPU(s)).\n";
         std::cout << (directory ? "- Index was built on an entire directory.\n" : "- Index was built on a single fasta file.\n") << std::flush;
     }
 

@@ -161,6 +161,61 @@ GMB_HD uint32_t block_rank_one(const BlockRegs& b, uint32_t r, uint32_t i, uint3
     return base + n;
 }
 
+// ---- Dna5 (sigma = 5) rank block: three planes, 96 symbols, two 256-bit loads ---------------------------
+struct BlockRegs5 {
+    uint32_t h[5];            // A, C, G, T before the block; sent
+    uint32_t p0[3], p1[3], p2[3];
+};
+
+GMB_HD BlockRegs5 load_block5(const RankBlock5* p)
+{
+    BlockRegs5 b;
+#if defined(__CUDA_ARCH__)
+    uint32_t r0, r1, r2, r3, r4, r6, r7, s0, s1, s2, s3, s4, s5, s6;
+    [[maybe_unused]] uint32_t r5, s7; // padding words of the block
+    asm volatile("ld.global.nc.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "l"(p));
+    asm volatile("ld.global.nc.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+32];"
+                 : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7) : "l"(p));
+    b.h[0] = r0; b.h[1] = r1; b.h[2] = r2; b.h[3] = r3; b.h[4] = r4;
+    b.p0[0] = r6; b.p0[1] = r7; b.p0[2] = s0;
+    b.p1[0] = s1; b.p1[1] = s2; b.p1[2] = s3;
+    b.p2[0] = s4; b.p2[1] = s5; b.p2[2] = s6;
+#else
+    for (int c = 0; c < 4; ++c) b.h[c] = p->cnt[c];
+    b.h[4] = p->sent;
+    for (int q = 0; q < 3; ++q) { b.p0[q] = p->plane[0][q]; b.p1[q] = p->plane[1][q]; b.p2[q] = p->plane[2][q]; }
+#endif
+    return b;
+}
+
+// ranks of all symbols (c[4] = N) at BWT position i = blk*96 + r
+struct Ranks5 { uint32_t c[5]; uint32_t s; };
+GMB_HD Ranks5 block_rank5(const BlockRegs5& b, uint32_t r, uint32_t i, const uint32_t* sent_pos)
+{
+    uint32_t a = 0, c = 0, g = 0, t = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const uint32_t m = piece_mask(r, q);
+        const uint32_t x0 = b.p0[q], x1 = b.p1[q], x2 = b.p2[q];
+        a += popc32(~x0 & ~x1 & ~x2 & m);
+        c += popc32(x0 & ~x1 & m);
+        g += popc32(~x0 & x1 & m);
+        t += popc32(x0 & x1 & m);
+    }
+    const uint32_t s_before = b.h[4] >> 8, s_in = b.h[4] & 0xffu;
+    uint32_t s = 0;
+    for (uint32_t k = 0; k < s_in; ++k) s += sent_pos[s_before + k] < i;
+    Ranks5 R;
+    R.c[0] = b.h[0] + a - s;
+    R.c[1] = b.h[1] + c;
+    R.c[2] = b.h[2] + g;
+    R.c[3] = b.h[3] + t;
+    R.s = s_before + s;
+    R.c[4] = i - R.c[0] - R.c[1] - R.c[2] - R.c[3] - R.s;
+    return R;
+}
+
 // ---- pattern -----------------------------------------------------------------------------------------
 GMB_HD uint64_t reverse_groups64(uint64_t x) // reverse the order of the 32 two-bit groups
 {
@@ -175,14 +230,48 @@ GMB_HD uint64_t reverse_groups64(uint64_t x) // reverse the order of the 32 two-
     return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
 }
 
-template <int KW>
+GMB_HD uint32_t reverse_bits32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+    return __builtin_bswap32(x);
+#endif
+}
+
+// KW words of 32 two-bit characters; SIGMA == 5 adds one N-mask bit per character (nm[k] covers w[k])
+template <int KW, int SIGMA = 4>
 struct Pattern {
     uint64_t w[KW];
+    uint32_t nm[SIGMA == 5 ? KW : 1];
     GMB_HD uint32_t at(uint32_t i) const
     {
+        if (SIGMA == 5) {
+            const uint32_t nbit = KW == 1 ? (nm[0] >> i) & 1u : (nm[i >> 5] >> (i & 31)) & 1u;
+            if (nbit) return 4u; // N (src/algo.hpp:111-112: a pattern N never matches)
+        }
         if (KW == 1) return (uint32_t)(w[0] >> (2 * i)) & 3u;
         if (KW == 2) return (uint32_t)((i < 32 ? w[0] : w[KW - 1]) >> (2 * (i & 31))) & 3u; // select: stays in registers
         return (uint32_t)(w[i >> 5] >> (2 * (i & 31))) & 3u;
+    }
+    // does any of the d <= 16 characters starting at offset a equal N?
+    GMB_HD bool has_n(uint32_t a, uint32_t d) const
+    {
+        if constexpr (SIGMA == 5) {
+            for (uint32_t i = a; i < a + d; ++i)
+                if ((nm[KW == 1 ? 0 : (i >> 5)] >> (i & 31)) & 1u) return true;
+        }
+        return false;
+    }
+    GMB_HD bool has_n() const
+    {
+        uint32_t any = 0;
+        if constexpr (SIGMA == 5)
+            for (int k = 0; k < KW; ++k) any |= nm[k];
+        return any != 0;
     }
     // the d <= 16 characters starting at offset a as an integer, character a in the low bits
     GMB_HD uint32_t bits(uint32_t a, uint32_t d) const
@@ -203,6 +292,13 @@ struct Pattern {
     // in place: the reverse complement of the K-character pattern (src/algo.hpp:284-305)
     GMB_HD void reverse_complement(uint32_t K)
     {
+        if constexpr (SIGMA == 5) { // N stays N: reverse the mask over the K characters
+            uint32_t out[KW];
+            for (int k = 0; k < KW; ++k) out[k] = 0;
+            for (uint32_t i = 0; i < K; ++i)
+                if ((nm[KW == 1 ? 0 : (i >> 5)] >> (i & 31)) & 1u) { const uint32_t j = K - 1 - i; out[KW == 1 ? 0 : (j >> 5)] |= 1u << (j & 31); }
+            for (int k = 0; k < KW; ++k) nm[k] = out[k];
+        }
         if constexpr (KW == 1) { // registers only
             w[0] = reverse_groups64(~w[0]) >> (64u - 2u * K);
         } else {
@@ -229,10 +325,27 @@ struct Pattern {
     }
 };
 
-// 2-bit packed text (32 bases per uint64, base i in bits 2*(i&31)) -> the K bases starting at `pos`
-template <int KW>
-GMB_HD void load_pattern(Pattern<KW>& p, const uint64_t* text, uint64_t pos, uint32_t K)
+// 2-bit packed text (32 bases per uint64, base i in bits 2*(i&31)) -> the K bases starting at `pos`;
+// nmask (Dna5 only): bit i of the N mask, 64 positions per uint64
+template <int KW, int SIGMA>
+GMB_HD void load_pattern(Pattern<KW, SIGMA>& p, const uint64_t* text, const uint64_t* nmask, uint64_t pos, uint32_t K)
 {
+    if constexpr (SIGMA == 5) {
+        for (int k = 0; k < KW; ++k) {
+            uint32_t v = 0;
+            if (32u * k < K) {
+                const uint64_t q = pos + 32u * k;
+                const uint64_t lo = nmask[q >> 6], hi = nmask[(q >> 6) + 1];
+                const uint32_t sh = (uint32_t)(q & 63);
+                v = (uint32_t)(sh ? (lo >> sh) | (hi << (64 - sh)) : lo);
+                const uint32_t left = K - 32u * k;
+                if (left < 32) v &= (1u << left) - 1u;
+            }
+            p.nm[k] = v;
+        }
+    } else {
+        p.nm[0] = 0;
+    }
     uint64_t wi = pos >> 5;
     uint32_t sh = 2u * (uint32_t)(pos & 31);
 #pragma unroll
@@ -259,9 +372,9 @@ struct SearchStart {
 };
 
 struct MapCtx {
-    const RankBlock* blk[2];  // [0]: BWT of T (extend left), [1]: BWT of T' (extend right)
+    const void* blk[2];       // [0]: BWT of T (extend left), [1]: BWT of T' (extend right); RankBlock or RankBlock5
     const uint32_t* sent[2];
-    uint32_t C[4];
+    uint32_t C[5];            // C[c] = #symbols smaller than base c (sentinels included); C[4] only for Dna5
     uint32_t n_bwt;
     // search tables (gmb_host.h: BlockTables), indexed by cnt = k-mers in the block (1..B):
     //   infix search : steps[p1_off[cnt] + search * (K - cnt + 1) + t]
@@ -281,22 +394,77 @@ struct MapCtx {
 
 struct Node { uint32_t lo_f, lo_r, size; };
 
+// Children of a node in one direction: for every symbol c of the alphabet the size n[c] of the child
+// interval and its start l[c] in the ACTIVE index; oth0 = start of child 0 in the OTHER index (child c
+// starts at oth0 + n[0] + ... + n[c-1]: `smaller` of index_fm_stree.h:256-278 with the sentinels first).
+template <int SIGMA>
+struct Children { uint32_t n[SIGMA], l[SIGMA], oth0; };
+
+// Both rank blocks of the node are requested before either is used (one memory latency per expansion).
+// `dir` selects the index: 1 = BWT of T' (extend right), 0 = BWT of T (extend left).
+template <int SIGMA>
+GMB_HD Children<SIGMA> expand_node(const MapCtx& cx, uint32_t dir, uint32_t x, uint32_t size, uint32_t z, unsigned long long* fetches)
+{
+    Children<SIGMA> ch;
+    const uint32_t y = x + size;
+    const uint32_t* SP = dir ? cx.sent[1] : cx.sent[0];
+    if constexpr (SIGMA == 4) {
+        const RankBlock* B = static_cast<const RankBlock*>(dir ? cx.blk[1] : cx.blk[0]);
+        const uint32_t bx = x / kBlockBases, by = y / kBlockBases;
+        if (fetches) *fetches += 1u + (by != bx);
+        const BlockRegs rbx = load_block(B + bx);
+        BlockRegs rby = rbx;
+        load_block_if(rby, B + by, by != bx);
+        const Ranks R0 = block_rank(rbx, x - bx * kBlockBases, x, SP);
+        const Ranks R1 = block_rank(rby, y - by * kBlockBases, y, SP);
+        ch.n[0] = R1.a - R0.a; ch.n[1] = R1.c - R0.c; ch.n[2] = R1.g - R0.g; ch.n[3] = R1.t - R0.t;
+        ch.l[0] = cx.C[0] + R0.a; ch.l[1] = cx.C[1] + R0.c; ch.l[2] = cx.C[2] + R0.g; ch.l[3] = cx.C[3] + R0.t;
+        ch.oth0 = z + (R1.s - R0.s);
+    } else {
+        const RankBlock5* B = static_cast<const RankBlock5*>(dir ? cx.blk[1] : cx.blk[0]);
+        const uint32_t bx = x / kBlockBases5, by = y / kBlockBases5;
+        if (fetches) *fetches += 1u + (by != bx);
+        const BlockRegs5 rbx = load_block5(B + bx);
+        const BlockRegs5 rby = by != bx ? load_block5(B + by) : rbx;
+        const Ranks5 R0 = block_rank5(rbx, x - bx * kBlockBases5, x, SP);
+        const Ranks5 R1 = block_rank5(rby, y - by * kBlockBases5, y, SP);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { ch.n[c] = R1.c[c] - R0.c[c]; ch.l[c] = cx.C[c] + R0.c[c]; }
+        ch.oth0 = z + (R1.s - R0.s);
+    }
+    return ch;
+}
+
+// select element c of a small array with compile-time indices only (keeps the array in registers)
+template <int SIGMA>
+GMB_HD uint32_t pick(const uint32_t (&v)[SIGMA], uint32_t c)
+{
+    uint32_t r = v[SIGMA - 1];
+#pragma unroll
+    for (int k = SIGMA - 2; k >= 0; --k) r = c == (uint32_t)k ? v[k] : r;
+    return r;
+}
+// n[0] + ... + n[c-1]
+template <int SIGMA>
+GMB_HD uint32_t sum_below(const uint32_t (&n)[SIGMA], uint32_t c)
+{
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < SIGMA - 1; ++k) r += c > (uint32_t)k ? n[k] : 0u;
+    return r;
+}
+
 // P -> Pc on the bidirectional index (goDown(it, c, Rev()): index_bidirectional_stree.h:250-265)
+template <int SIGMA>
 GMB_HD Node extend_right(const Node& n, uint32_t c, const MapCtx& cx)
 {
     Node m;
     m.lo_f = 0; m.lo_r = 0; m.size = 0;
     if (n.size == 0) return m;
-    const uint32_t x = n.lo_r, y = n.lo_r + n.size;
-    const uint32_t bx = x / kBlockBases, by = y / kBlockBases;
-    BlockRegs rb = load_block(cx.blk[1] + bx);
-    const Ranks R0 = block_rank(rb, x - bx * kBlockBases, x, cx.sent[1]);
-    if (by != bx) rb = load_block(cx.blk[1] + by);
-    const Ranks R1 = block_rank(rb, y - by * kBlockBases, y, cx.sent[1]);
-    const uint32_t n0 = R1.a - R0.a, n1 = R1.c - R0.c, n2 = R1.g - R0.g, n3 = R1.t - R0.t;
-    m.size = c == 0 ? n0 : (c == 1 ? n1 : (c == 2 ? n2 : n3));
-    m.lo_r = (c == 0 ? cx.C[0] + R0.a : (c == 1 ? cx.C[1] + R0.c : (c == 2 ? cx.C[2] + R0.g : cx.C[3] + R0.t)));
-    m.lo_f = n.lo_f + (R1.s - R0.s) + (c > 0 ? n0 : 0u) + (c > 1 ? n1 : 0u) + (c > 2 ? n2 : 0u);
+    const Children<SIGMA> ch = expand_node<SIGMA>(cx, 1, n.lo_r, n.size, n.lo_f, nullptr);
+    m.size = pick<SIGMA>(ch.n, c);
+    m.lo_r = pick<SIGMA>(ch.l, c);
+    m.lo_f = ch.oth0 + sum_below<SIGMA>(ch.n, c);
     return m;
 }
 
@@ -308,9 +476,9 @@ GMB_HD Node extend_right(const Node& n, uint32_t c, const MapCtx& cx)
 // src/algo.hpp:26-218, here a plain bounded walk per window).  cnt = 1 is the one-k-mer-per-chain case.
 constexpr uint32_t kNoWin = 0xffu;
 
-template <int KW>
+template <int KW, int SIGMA = 4>
 struct Chain {
-    Pattern<KW> pat;           // the needle; on the reverse strand its reverse complement
+    Pattern<KW, SIGMA> pat;    // the needle; on the reverse strand its reverse complement
     uint32_t lo_f, lo_r, size; // current node: [lo_f, lo_f+size) in SA(T), [lo_r, lo_r+size) in SA(T')
     uint32_t acc;              // B == 1: occurrences so far (saturating); B > 1: counts live in the frame store
     uint32_t t, e, s, strand;  // step, errors, search, strand of the current walk
@@ -318,6 +486,7 @@ struct Chain {
     uint32_t cnt, win, leaf_e; // k-mers in this block; window being completed (kNoWin: infix search); errors of the infix hit
     uint64_t files;            // B == 1, --exclude-pseudo: FASTA files seen so far (one bit each)
     uint32_t pre_lo_f, pre_lo_r, pre_size; // jump-table entry of (reverse strand, search 0), fetched early
+    bool has_n;                // Dna5: the needle contains N (then no occurrence is error-free)
 };
 
 // --exclude-pseudo: mark the FASTA file of every occurrence in SA rows [lo, lo+n)
@@ -337,16 +506,19 @@ GMB_HD void ep_mark_rows(uint64_t& mask, uint32_t lo, uint32_t n, const MapCtx& 
 }
 
 // Frame store of a chain (shared memory on the device):
-//   E mismatch frames x kFrameWords: 0..3 child lo in the active index, 4..7 child sizes, 8 = lo of child 0
-//                                    in the other index, 9 = t | pending << 8
+//   E mismatch frames x (2*SIGMA + 2) words: child lo in the active index [SIGMA], child sizes [SIGMA],
+//                                            lo of child 0 in the other index, t | pending << 8
 //   then kLeafWords for the infix hit being completed (lo_f, lo_r, size),
-//   then, when B > 1, one counter per window (+ two words of file mask per window under --exclude-pseudo).
+//   then, in the blocked instantiation, one counter per window (+ two words of file mask per window under
+//   --exclude-pseudo).
 // Accessors: set/get(level, word) for the mismatch frames, xset/xget(word) for the rest.
-constexpr int kFrameWords = 10;
+constexpr int kFrameWords = 10;  // SIGMA == 4
+constexpr int kFrameWords5 = 12; // SIGMA == 5
 constexpr int kLeafWords = 3;
-GMB_HD uint32_t frame_store_words(uint32_t E, uint32_t B, bool ep)
+GMB_HD constexpr uint32_t frame_words(int sigma) { return sigma == 5 ? kFrameWords5 : kFrameWords; }
+GMB_HD uint32_t frame_store_words(uint32_t E, uint32_t B, bool ep, int sigma, bool blocked)
 {
-    return E * kFrameWords + kLeafWords + (B > 1 ? B * (ep ? 3u : 1u) : 0u);
+    return E * frame_words(sigma) + kLeafWords + (blocked ? B * (ep ? 3u : 1u) : 0u);
 }
 
 GMB_HD void jump_lookup(const SearchStart& S, uint32_t key, uint32_t& lo_f, uint32_t& lo_r, uint32_t& size)
@@ -364,8 +536,8 @@ GMB_HD void jump_lookup(const SearchStart& S, uint32_t key, uint32_t& lo_f, uint
 // start the infix search number st.s on the current strand
 // (BLK = false is the one-k-mer-per-chain instantiation: cnt == 1 is a compile-time fact there, so all the
 // window bookkeeping disappears and the count stays in a register)
-template <int KW, bool BLK>
-GMB_HD void chain_start(Chain<KW>& st, const MapCtx& cx, unsigned long long* lut_reads)
+template <int KW, bool BLK, int SIGMA>
+GMB_HD void chain_start(Chain<KW, SIGMA>& st, const MapCtx& cx, unsigned long long* lut_reads)
 {
     const SearchStart S = cx.starts[(BLK ? st.cnt : 1u) * kMaxSearches + st.s];
     st.e = 0; st.lvmask = 0; st.win = kNoWin; st.leaf_e = 0;
@@ -373,6 +545,7 @@ GMB_HD void chain_start(Chain<KW>& st, const MapCtx& cx, unsigned long long* lut
         st.lo_f = 0; st.lo_r = 0; st.size = cx.n_bwt; st.t = 0;
     } else {
         if (st.strand == 1 && st.s == 0) { st.lo_f = st.pre_lo_f; st.lo_r = st.pre_lo_r; st.size = st.pre_size; }
+        else if (SIGMA == 5 && st.pat.has_n(S.a, S.d)) { st.lo_f = 0; st.lo_r = 0; st.size = 0; } // N never matches
         else jump_lookup(S, st.pat.bits(S.a, S.d), st.lo_f, st.lo_r, st.size);
         st.t = S.d;
         if (lut_reads) *lut_reads += 1;
@@ -380,11 +553,12 @@ GMB_HD void chain_start(Chain<KW>& st, const MapCtx& cx, unsigned long long* lut
 }
 
 // st.pat (needle of K + cnt - 1 characters) and st.cnt are set by the caller
-template <int KW, bool EP, bool BLK, class Frames>
-GMB_HD void chain_begin_block(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned long long* lut_reads)
+template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
+GMB_HD void chain_begin_block(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, unsigned long long* lut_reads)
 {
     st.acc = 0; st.s = 0; st.strand = 0; st.files = 0;
     if (!BLK) st.cnt = 1;
+    st.has_n = st.pat.has_n();
     if (BLK) {
         const uint32_t per = EP ? 3u : 1u;
         for (uint32_t w = 0; w < st.cnt * per; ++w) fr.xset(kLeafWords + w, 0u);
@@ -393,16 +567,17 @@ GMB_HD void chain_begin_block(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsig
     // that its latency overlaps the forward strand instead of starting the reverse strand with a stall
     const SearchStart S0 = cx.starts[(BLK ? st.cnt : 1u) * kMaxSearches];
     if (cx.n_strands > 1 && S0.uni != nullptr) {
-        Pattern<KW> rc = st.pat;
+        Pattern<KW, SIGMA> rc = st.pat;
         rc.reverse_complement(cx.K + (BLK ? st.cnt : 1u) - 1);
-        jump_lookup(S0, rc.bits(S0.a, S0.d), st.pre_lo_f, st.pre_lo_r, st.pre_size);
+        if (SIGMA == 5 && rc.has_n(S0.a, S0.d)) { st.pre_lo_f = 0; st.pre_lo_r = 0; st.pre_size = 0; }
+        else jump_lookup(S0, rc.bits(S0.a, S0.d), st.pre_lo_f, st.pre_lo_r, st.pre_size);
     }
-    chain_start<KW, BLK>(st, cx, lut_reads);
+    chain_start<KW, BLK, SIGMA>(st, cx, lut_reads);
 }
 
 // result of window w (position j0 + w) once chain_step has returned false
-template <int KW, bool EP, bool BLK, class Frames>
-GMB_HD uint32_t chain_result(const Chain<KW>& st, const Frames& fr, const MapCtx& cx, uint32_t w)
+template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
+GMB_HD uint32_t chain_result(const Chain<KW, SIGMA>& st, const Frames& fr, const MapCtx& cx, uint32_t w)
 {
     if (!BLK) return st.acc;
     if (!EP) return fr.xget(kLeafWords + w);
@@ -412,11 +587,6 @@ GMB_HD uint32_t chain_result(const Chain<KW>& st, const Frames& fr, const MapCtx
 #else
     return (uint32_t)__builtin_popcountll(m);
 #endif
-}
-
-GMB_HD uint32_t sel4(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t c)
-{
-    return c == 0 ? v0 : (c == 1 ? v1 : (c == 2 ? v2 : v3));
 }
 
 GMB_HD uint32_t lowest_bit_index(uint32_t m)
@@ -438,13 +608,13 @@ GMB_HD uint32_t highest_bit_index(uint32_t m)
 }
 
 // add `n` occurrences (or, under --exclude-pseudo, the files of SA rows [lo, lo+n)) to window `w` of the strand
-template <int KW, bool EP, bool BLK, class Frames>
-GMB_HD void chain_count(Chain<KW>& st, Frames& fr, const MapCtx& cx, uint32_t w, uint32_t lo, uint32_t n, bool own_only)
+template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
+GMB_HD void chain_count(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, uint32_t w, uint32_t lo, uint32_t n, bool own_only)
 {
     const uint32_t widx = !BLK ? 0u : (st.strand ? st.cnt - 1u - w : w); // reverse-strand windows run backwards (src/algo.hpp:304)
     if (EP) {
         uint64_t m = !BLK ? st.files
-                               : (uint64_t)fr.xget(kLeafWords + st.cnt + 2 * widx) | ((uint64_t)fr.xget(kLeafWords + st.cnt + 2 * widx + 1) << 32);
+                          : (uint64_t)fr.xget(kLeafWords + st.cnt + 2 * widx) | ((uint64_t)fr.xget(kLeafWords + st.cnt + 2 * widx + 1) << 32);
         if (own_only) m |= 1ull << cx.own_file;
         else ep_mark_rows(m, lo, n, cx);
         if (!BLK) st.files = m;
@@ -459,10 +629,11 @@ GMB_HD void chain_count(Chain<KW>& st, Frames& fr, const MapCtx& cx, uint32_t w,
 
 // One state-machine iteration.  Returns false when the block is finished (results via chain_result).
 // `fetches` counts rank-block reads (the roofline's algorithmic unit), when non-null.
-template <int KW, bool EP, bool BLK, class Frames>
-GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned long long* fetches,
+template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
+GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, unsigned long long* fetches,
                        unsigned long long* lut_reads)
 {
+    constexpr uint32_t kNone = 0xffu; // "no symbol": the pattern character is N
     const uint32_t K = cx.K, cnt = BLK ? st.cnt : 1u;
     const uint32_t Li = K - cnt + 1; // infix length
 
@@ -477,29 +648,25 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
     const uint32_t tab = in_flank ? cx.fl_off[cnt] + st.win * (cnt - 1u) : (BLK ? cx.p1_off[cnt] : 0u) + st.s * Li;
     const uint32_t ent = cx.steps[tab + st.t];
     const uint32_t dir = step_dir(ent);
-    const uint32_t p = st.pat.at(step_pos(ent)); // on the reverse strand st.pat already holds the reverse complement
+    // on the reverse strand st.pat already holds the reverse complement; a pattern N matches nothing
+    const uint32_t pc = st.pat.at(step_pos(ent));
+    const uint32_t p = (SIGMA == 5 && pc == 4u) ? kNone : pc;
 
     bool descend = false;
     uint32_t c = 0, csize = 0, cact = 0, coth = 0, ce = 0, ct = 0, cdir = dir;
 
     if (st.size == 0) {
         // an empty node can only come out of a jump table: nothing to search here
-    } else if (st.strand == 0 && st.e == 0 && st.size == 1 && step_exact_ok(ent)) {
+    } else if (st.strand == 0 && st.e == 0 && st.size == 1 && step_exact_ok(ent) && !(SIGMA == 5 && st.has_n)) {
         // Forward strand, no error so far, one occurrence left: it is the query's own position in the
         // indexed text, so the rest of the pattern matches it exactly and no mismatching extension
         // exists.  The subtree contributes exactly one occurrence per window — no need to walk it.
-        if (in_flank) chain_count<KW, EP, BLK>(st, fr, cx, st.win, 0, 1, true);
-        else for (uint32_t w = 0; w < cnt; ++w) chain_count<KW, EP, BLK>(st, fr, cx, w, 0, 1, true);
+        if (in_flank) chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, st.win, 0, 1, true);
+        else for (uint32_t w = 0; w < cnt; ++w) chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, w, 0, 1, true);
     } else {
         // ---- expand the node: ranks at both interval ends of the active index -----------------------
         const uint32_t x = dir ? st.lo_r : st.lo_f;
         const uint32_t z = dir ? st.lo_f : st.lo_r;
-        const uint32_t y = x + st.size;
-        const RankBlock* B = dir ? cx.blk[1] : cx.blk[0]; // selects, not indexing: keeps cx in registers
-        const uint32_t* SP = dir ? cx.sent[1] : cx.sent[0];
-        const uint32_t bx = x / kBlockBases, by = y / kBlockBases;
-        const uint32_t rx = x - bx * kBlockBases, ry = y - by * kBlockBases;
-        if (fetches) *fetches += 1u + (by != bx);
 
         // admissible children (search-scheme bounds, find2_index_approx.hpp:388-389,254-258)
         const uint32_t ub = step_ub(ent), lb = step_lb(ent), rem = step_rem(ent);
@@ -507,64 +674,67 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
         const bool mis_ok = em <= ub && em + rem >= lb;
         const bool hit_ok = st.e + rem >= lb; // st.e <= ub is an invariant of the walk
 
-        uint32_t n0, n1, n2, n3, l0, l1, l2, l3, oth0;
-        // both rank blocks are requested before either is used (one memory latency per expansion)
-        const BlockRegs rbx = load_block(B + bx);
-        BlockRegs rby = rbx;
-        load_block_if(rby, B + by, by != bx);
-        // exact step whose other-index interval is never needed again: one symbol's rank suffices.  Taken
-        // only when the whole warp agrees, so that lanes never serialise two differently shaped paths.
-        if (warp_all(!mis_ok && !step_sync(ent))) {
-            const uint32_t r0 = block_rank_one(rbx, rx, x, p, SP);
-            const uint32_t r1 = block_rank_one(rby, ry, y, p, SP);
-            const uint32_t np = r1 - r0, lp = sel4(cx.C[0], cx.C[1], cx.C[2], cx.C[3], p) + r0;
-            n0 = p == 0 ? np : 0u; n1 = p == 1 ? np : 0u; n2 = p == 2 ? np : 0u; n3 = p == 3 ? np : 0u;
-            l0 = l1 = l2 = l3 = lp;
-            oth0 = z;
-        } else {
-            const Ranks R0 = block_rank(rbx, rx, x, SP);
-            const Ranks R1 = block_rank(rby, ry, y, SP);
-            n0 = R1.a - R0.a; n1 = R1.c - R0.c; n2 = R1.g - R0.g; n3 = R1.t - R0.t;
-            l0 = cx.C[0] + R0.a; l1 = cx.C[1] + R0.c; l2 = cx.C[2] + R0.g; l3 = cx.C[3] + R0.t;
-            oth0 = z + (R1.s - R0.s);
+        Children<SIGMA> ch;
+        bool fast = false;
+        if constexpr (SIGMA == 4) {
+            // exact step whose other-index interval is never needed again: one symbol's rank suffices.  Taken
+            // only when the whole warp agrees, so that lanes never serialise two differently shaped paths.
+            fast = warp_all(!mis_ok && !step_sync(ent));
+            if (fast) {
+                const uint32_t y = x + st.size;
+                const RankBlock* B = static_cast<const RankBlock*>(dir ? cx.blk[1] : cx.blk[0]);
+                const uint32_t* SP = dir ? cx.sent[1] : cx.sent[0];
+                const uint32_t bx = x / kBlockBases, by = y / kBlockBases;
+                if (fetches) *fetches += 1u + (by != bx);
+                const BlockRegs rbx = load_block(B + bx);
+                BlockRegs rby = rbx;
+                load_block_if(rby, B + by, by != bx);
+                const uint32_t r0 = block_rank_one(rbx, x - bx * kBlockBases, x, p, SP);
+                const uint32_t r1 = block_rank_one(rby, y - by * kBlockBases, y, p, SP);
+                const uint32_t np = r1 - r0, lp = (p == 0 ? cx.C[0] : (p == 1 ? cx.C[1] : (p == 2 ? cx.C[2] : cx.C[3]))) + r0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { ch.n[k] = p == (uint32_t)k ? np : 0u; ch.l[k] = lp; }
+                ch.oth0 = z;
+            }
         }
+        if (!fast) ch = expand_node<SIGMA>(cx, dir, x, st.size, z, fetches);
+
         uint32_t ok = 0;
-        if (n0 && (p == 0 ? hit_ok : mis_ok)) ok |= 1u;
-        if (n1 && (p == 1 ? hit_ok : mis_ok)) ok |= 2u;
-        if (n2 && (p == 2 ? hit_ok : mis_ok)) ok |= 4u;
-        if (n3 && (p == 3 ? hit_ok : mis_ok)) ok |= 8u;
+#pragma unroll
+        for (int k = 0; k < SIGMA; ++k)
+            if (ch.n[k] && (p == (uint32_t)k ? hit_ok : mis_ok)) ok |= 1u << k;
+        const uint32_t hit_bit = p == kNone ? 0u : (1u << p);
 
         if (st.t + 1 == T && (in_flank || cnt == 1)) {
             // children are full-length matches of one window: count them (src/algo.hpp:48,191)
             const uint32_t w = in_flank ? st.win : 0u;
             if (EP) {
                 // rows in SA(T): the active index's children when extending left, else the synchronised side
-                const uint32_t f0 = dir ? oth0 : l0, f1 = dir ? oth0 + n0 : l1, f2 = dir ? oth0 + n0 + n1 : l2,
-                               f3 = dir ? oth0 + n0 + n1 + n2 : l3;
-                if (ok & 1u) chain_count<KW, EP, BLK>(st, fr, cx, w, f0, n0, false);
-                if (ok & 2u) chain_count<KW, EP, BLK>(st, fr, cx, w, f1, n1, false);
-                if (ok & 4u) chain_count<KW, EP, BLK>(st, fr, cx, w, f2, n2, false);
-                if (ok & 8u) chain_count<KW, EP, BLK>(st, fr, cx, w, f3, n3, false);
+#pragma unroll
+                for (int k = 0; k < SIGMA; ++k)
+                    if (ok & (1u << k))
+                        chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, w, dir ? ch.oth0 + sum_below<SIGMA>(ch.n, (uint32_t)k) : ch.l[k], ch.n[k], false);
             } else {
-                const uint64_t sum = (uint64_t)((ok & 1u) ? n0 : 0u) + ((ok & 2u) ? n1 : 0u) + ((ok & 4u) ? n2 : 0u) +
-                                     ((ok & 8u) ? n3 : 0u);
-                chain_count<KW, EP, BLK>(st, fr, cx, w, 0, sum < cx.maxv ? (uint32_t)sum : cx.maxv, false);
+                uint64_t sum = 0;
+#pragma unroll
+                for (int k = 0; k < SIGMA; ++k) sum += (ok & (1u << k)) ? ch.n[k] : 0u;
+                chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, w, 0, sum < cx.maxv ? (uint32_t)sum : cx.maxv, false);
             }
         } else if (ok) {
-            const uint32_t mm = ok & ~(1u << p);
+            const uint32_t mm = ok & ~hit_bit;
             c = mm ? lowest_bit_index(mm) : p; // mismatching children first, the matching child last
             const uint32_t pending = ok & ~(1u << c);
             if (pending) {
                 const uint32_t lv = st.e;
-                fr.set(lv, 0, l0); fr.set(lv, 1, l1); fr.set(lv, 2, l2); fr.set(lv, 3, l3);
-                fr.set(lv, 4, n0); fr.set(lv, 5, n1); fr.set(lv, 6, n2); fr.set(lv, 7, n3);
-                fr.set(lv, 8, oth0);
-                fr.set(lv, 9, st.t | (pending << 8));
+#pragma unroll
+                for (int k = 0; k < SIGMA; ++k) { fr.set(lv, k, ch.l[k]); fr.set(lv, SIGMA + k, ch.n[k]); }
+                fr.set(lv, 2 * SIGMA, ch.oth0);
+                fr.set(lv, 2 * SIGMA + 1, st.t | (pending << 8));
                 st.lvmask |= 1u << lv;
             }
-            csize = sel4(n0, n1, n2, n3, c);
-            cact = sel4(l0, l1, l2, l3, c);
-            coth = oth0 + (c > 0 ? n0 : 0u) + (c > 1 ? n1 : 0u) + (c > 2 ? n2 : 0u);
+            csize = pick<SIGMA>(ch.n, c);
+            cact = pick<SIGMA>(ch.l, c);
+            coth = ch.oth0 + sum_below<SIGMA>(ch.n, c);
             ce = st.e + (c != p);
             ct = st.t + 1;
             descend = true;
@@ -605,25 +775,28 @@ GMB_HD bool chain_step(Chain<KW>& st, Frames& fr, const MapCtx& cx, unsigned lon
                 }
                 st.pat.reverse_complement(K + cnt - 1);
             }
-            chain_start<KW, BLK>(st, cx, lut_reads);
+            chain_start<KW, BLK, SIGMA>(st, cx, lut_reads);
             return true;
         }
         const uint32_t lv = highest_bit_index(cand);
-        const uint32_t meta = fr.get(lv, 9);
+        const uint32_t meta = fr.get(lv, 2 * SIGMA + 1);
         const uint32_t tf = meta & 0xffu;
         uint32_t pending = meta >> 8;
         const uint32_t tabf = (BLK && st.win != kNoWin) ? cx.fl_off[cnt] + st.win * (cnt - 1u) : (BLK ? cx.p1_off[cnt] : 0u) + st.s * Li;
         const uint32_t entf = cx.steps[tabf + tf];
-        const uint32_t pf = st.pat.at(step_pos(entf));
-        const uint32_t mm = pending & ~(1u << pf);
+        const uint32_t pcf = st.pat.at(step_pos(entf));
+        const uint32_t pf = (SIGMA == 5 && pcf == 4u) ? kNone : pcf;
+        const uint32_t mm = pending & ~(pf == kNone ? 0u : (1u << pf));
         c = mm ? lowest_bit_index(mm) : pf;
         pending &= ~(1u << c);
-        if (pending) fr.set(lv, 9, tf | (pending << 8));
+        if (pending) fr.set(lv, 2 * SIGMA + 1, tf | (pending << 8));
         else st.lvmask &= ~(1u << lv);
-        const uint32_t f0 = fr.get(lv, 4), f1 = fr.get(lv, 5), f2 = fr.get(lv, 6);
-        csize = fr.get(lv, 4 + c);
+        uint32_t below = 0;
+#pragma unroll
+        for (int k = 0; k < SIGMA - 1; ++k) below += c > (uint32_t)k ? fr.get(lv, SIGMA + k) : 0u;
+        csize = fr.get(lv, SIGMA + c);
         cact = fr.get(lv, c);
-        coth = fr.get(lv, 8) + (c > 0 ? f0 : 0u) + (c > 1 ? f1 : 0u) + (c > 2 ? f2 : 0u);
+        coth = fr.get(lv, 2 * SIGMA) + below;
         ce = lv + (c != pf);
         ct = tf + 1;
         cdir = step_dir(entf);

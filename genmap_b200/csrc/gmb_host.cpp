@@ -156,26 +156,27 @@ uint32_t default_jump_depth(uint64_t n_bwt)
 // ---------------------------------------------------------------------------------------------------
 static uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
-BlobPlan plan_blob(uint64_t n_text, uint32_t n_seq, bool with_sa)
+BlobPlan plan_blob(uint64_t n_text, uint32_t n_seq, bool with_sa, uint32_t sigma)
 {
     BlobPlan p;
     std::memset(&p.h, 0, sizeof(p.h));
     IndexHeader& h = p.h;
     h.magic = kMagic;
     h.version = kVersion;
-    h.sigma = 4;
+    h.sigma = sigma;
     h.n_text = n_text;
     h.n_seq = n_seq;
     h.n_bwt = n_text + n_seq;
-    h.n_blocks = (uint32_t)(h.n_bwt / kBlockBases + 1);
+    h.n_blocks = (uint32_t)(h.n_bwt / block_bases(sigma) + 1);
     uint64_t o = align_up(sizeof(IndexHeader), 256);
-    h.off_fwd = o;        o = align_up(o + (uint64_t)h.n_blocks * sizeof(RankBlock), 256);
-    h.off_rev = o;        o = align_up(o + (uint64_t)h.n_blocks * sizeof(RankBlock), 256);
+    h.off_fwd = o;        o = align_up(o + (uint64_t)h.n_blocks * block_bytes(sigma), 256);
+    h.off_rev = o;        o = align_up(o + (uint64_t)h.n_blocks * block_bytes(sigma), 256);
     h.off_sent_fwd = o;   o = align_up(o + (uint64_t)n_seq * 4, 256);
     h.off_sent_rev = o;   o = align_up(o + (uint64_t)n_seq * 4, 256);
     h.off_text = o;       o = align_up(o + (n_text / 32 + 2) * 8, 256);
     h.off_limits = o;     o = align_up(o + ((uint64_t)n_seq + 1) * 8, 256);
     h.off_seq_start = o;  o = align_up(o + ((uint64_t)n_seq + 1) * 4, 256);
+    if (sigma == 5) { h.off_nmask = o; o = align_up(o + (n_text / 64 + 2) * 8, 256); }
     if (with_sa) { h.off_sa = o; o = align_up(o + h.n_bwt * 4, 256); }
     h.total_bytes = o;
     return p;
@@ -212,6 +213,34 @@ void pack_bwt_blocks(const uint8_t* bwt, uint64_t n, RankBlock* blocks, uint32_t
     for (int c = 0; c < 4; ++c) tot[c] = cnt[c];
 }
 
+void pack_bwt_blocks5(const uint8_t* bwt, uint64_t n, RankBlock5* blocks, uint32_t n_blocks, uint32_t* sent_pos,
+                      uint32_t n_seq, uint64_t tot[5])
+{
+    uint64_t cnt[5] = {0, 0, 0, 0, 0};
+    uint32_t n_sent = 0;
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        RankBlock5& B = blocks[b];
+        std::memset(&B, 0, sizeof(B));
+        for (int c = 0; c < 4; ++c) B.cnt[c] = (uint32_t)cnt[c];
+        const uint32_t sent_before = n_sent;
+        for (uint32_t k = 0; k < kBlockBases5; ++k) {
+            const uint64_t i = (uint64_t)b * kBlockBases5 + k;
+            if (i >= n) break;
+            const uint8_t s = bwt[i];
+            if (s < 2) { // sentinel row: stored as code 0, listed on the side
+                if (n_sent < n_seq) sent_pos[n_sent] = (uint32_t)i;
+                ++n_sent;
+                continue;
+            }
+            const uint32_t c = s - 2u;
+            ++cnt[c];
+            for (int pl = 0; pl < 3; ++pl) B.plane[pl][k >> 5] |= ((c >> pl) & 1u) << (k & 31);
+        }
+        B.sent = (sent_before << 8) | (n_sent - sent_before);
+    }
+    for (int c = 0; c < 5; ++c) tot[c] = cnt[c];
+}
+
 namespace {
 
 // T (or T') as SA-IS input: '#' = 0 (last symbol, unique smallest), '$' = 1, A,C,G,T = 2..5.
@@ -232,19 +261,20 @@ void make_symbols(const uint8_t* codes, const uint64_t* limits, uint32_t n_seq, 
 }
 
 template <class Idx>
-void build_direction(const std::vector<uint8_t>& t, RankBlock* blocks, uint32_t n_blocks, uint32_t* sent_pos,
-                     uint32_t n_seq, uint64_t tot[4], uint32_t* sa_out)
+void build_direction(const std::vector<uint8_t>& t, void* blocks, uint32_t n_blocks, uint32_t* sent_pos,
+                     uint32_t n_seq, uint64_t tot[5], uint32_t* sa_out, uint32_t sigma)
 {
     const uint64_t n = t.size();
     std::vector<Idx> sa(n);
-    suffix_array<Idx>(t.data(), sa.data(), (Idx)n, (Idx)6);
+    suffix_array<Idx>(t.data(), sa.data(), (Idx)n, (Idx)7);
     std::vector<uint8_t> bwt(n);
     for (uint64_t i = 0; i < n; ++i) {
         const uint64_t p = (uint64_t)sa[i];
         bwt[i] = p ? t[p - 1] : t[n - 1]; // src/seqan_libdivsufsort.h:165-229
         if (sa_out) sa_out[i] = (uint32_t)p;
     }
-    pack_bwt_blocks(bwt.data(), n, blocks, n_blocks, sent_pos, n_seq, tot);
+    if (sigma == 5) pack_bwt_blocks5(bwt.data(), n, static_cast<RankBlock5*>(blocks), n_blocks, sent_pos, n_seq, tot);
+    else { tot[4] = 0; pack_bwt_blocks(bwt.data(), n, static_cast<RankBlock*>(blocks), n_blocks, sent_pos, n_seq, tot); }
 }
 
 } // namespace
@@ -259,31 +289,39 @@ bool build_index_host(const uint8_t* codes, const uint64_t* limits, uint32_t n_s
     if (n >= 0xFFFFFFFFull) { err = "index too large: text + sentinels must stay below 2^32 - 1"; return false; }
     for (uint32_t s = 0; s < n_seq; ++s)
         if (limits[s + 1] <= limits[s]) { err = "empty sequence in input (skip empty records before indexing)"; return false; }
-    for (uint64_t i = 0; i < n_text; ++i)
-        if (codes[i] > 3) { err = "sequence contains N: Dna5 indices are not supported by the GPU path yet"; return false; }
+    uint32_t sigma = 4;
+    for (uint64_t i = 0; i < n_text; ++i) {
+        if (codes[i] > 4) { err = "invalid base code (expected 0..3 = ACGT, 4 = N)"; return false; }
+        if (codes[i] == 4) sigma = 5; // src/indexing.hpp:459-473: any N makes it a Dna5 index
+    }
 
-    BlobPlan plan = plan_blob(n_text, n_seq, with_sa);
+    BlobPlan plan = plan_blob(n_text, n_seq, with_sa, sigma);
     blob.resize(plan.h.total_bytes);
     uint8_t* base = blob.data();
     IndexHeader& h = *reinterpret_cast<IndexHeader*>(base);
     h = plan.h;
 
     std::vector<uint8_t> t;
-    uint64_t tot[4];
+    uint64_t tot[5] = {0, 0, 0, 0, 0};
     for (int rev = 0; rev < 2; ++rev) {
         make_symbols(codes, limits, n_seq, rev != 0, t);
-        RankBlock* blocks = reinterpret_cast<RankBlock*>(base + (rev ? h.off_rev : h.off_fwd));
+        void* blocks = base + (rev ? h.off_rev : h.off_fwd);
         uint32_t* sent = reinterpret_cast<uint32_t*>(base + (rev ? h.off_sent_rev : h.off_sent_fwd));
         uint32_t* sa_out = (!rev && with_sa) ? reinterpret_cast<uint32_t*>(base + h.off_sa) : nullptr;
-        if (n < 0x7FFFFFF0ull) build_direction<int32_t>(t, blocks, h.n_blocks, sent, n_seq, tot, sa_out);
-        else                   build_direction<int64_t>(t, blocks, h.n_blocks, sent, n_seq, tot, sa_out);
+        if (n < 0x7FFFFFF0ull) build_direction<int32_t>(t, blocks, h.n_blocks, sent, n_seq, tot, sa_out, sigma);
+        else                   build_direction<int64_t>(t, blocks, h.n_blocks, sent, n_seq, tot, sa_out, sigma);
     }
     // C array with the sentinels counted as smallest symbols (src/seqan_libdivsufsort.h:231-233)
     h.C[0] = n_seq;
-    for (int c = 0; c < 4; ++c) h.C[c + 1] = h.C[c] + tot[c];
+    for (int c = 0; c < 5; ++c) h.C[c + 1] = h.C[c] + tot[c];
 
     uint64_t* text = reinterpret_cast<uint64_t*>(base + h.off_text);
-    for (uint64_t i = 0; i < n_text; ++i) text[i >> 5] |= (uint64_t)codes[i] << (2 * (i & 31));
+    for (uint64_t i = 0; i < n_text; ++i) text[i >> 5] |= (uint64_t)(codes[i] & 3u) << (2 * (i & 31));
+    if (sigma == 5) {
+        uint64_t* nm = reinterpret_cast<uint64_t*>(base + h.off_nmask);
+        for (uint64_t i = 0; i < n_text; ++i)
+            if (codes[i] == 4) nm[i >> 6] |= 1ull << (i & 63);
+    }
     uint64_t* lim = reinterpret_cast<uint64_t*>(base + h.off_limits);
     uint32_t* sst = reinterpret_cast<uint32_t*>(base + h.off_seq_start);
     for (uint32_t s = 0; s <= n_seq; ++s) { lim[s] = limits[s]; sst[s] = (uint32_t)(limits[s] + s); }
@@ -353,7 +391,7 @@ bool import_reference_index(const std::string& dir, Blob& blob, std::string& err
     uint8_t* b = blob.data();
     IndexHeader& h = *reinterpret_cast<IndexHeader*>(b);
     h = plan.h;
-    uint64_t tot[4] = {0, 0, 0, 0};
+    uint64_t tot[5] = {0, 0, 0, 0, 0};
     std::vector<uint8_t> bwt;
     for (int rev = 0; rev < 2; ++rev) {
         if (!decode_reference_bwt(base + (rev ? ".rev.lf" : ".lf"), n, bwt, err)) return false;
@@ -361,7 +399,7 @@ bool import_reference_index(const std::string& dir, Blob& blob, std::string& err
                         reinterpret_cast<uint32_t*>(b + (rev ? h.off_sent_rev : h.off_sent_fwd)), n_seq, tot);
     }
     h.C[0] = n_seq;
-    for (int c = 0; c < 4; ++c) h.C[c + 1] = h.C[c] + tot[c];
+    for (int c = 0; c < 5; ++c) h.C[c + 1] = h.C[c] + tot[c];
     uint64_t* text = reinterpret_cast<uint64_t*>(b + h.off_text);
     const uint8_t* words = text_raw.data() + 8; // first word = length
     for (uint64_t i = 0; i < n_text; ++i) {
@@ -415,10 +453,11 @@ bool validate_header(const IndexHeader& h, uint64_t bytes, std::string& err)
 {
     if (h.magic != kMagic) { err = "not a genmap-b200 index (bad magic)"; return false; }
     if (h.version != kVersion) { err = "index version mismatch: rebuild the index"; return false; }
-    if (h.sigma != 4) { err = "only Dna4 indices are supported"; return false; }
+    if (h.sigma != 4 && h.sigma != 5) { err = "unsupported alphabet size in the index header"; return false; }
     if (h.total_bytes > bytes) { err = "index blob truncated"; return false; }
-    if (h.n_bwt != h.n_text + h.n_seq || h.n_blocks != h.n_bwt / kBlockBases + 1) { err = "index header inconsistent"; return false; }
-    const uint64_t offs[] = {h.off_fwd, h.off_rev, h.off_sent_fwd, h.off_sent_rev, h.off_text, h.off_limits, h.off_seq_start, h.off_sa};
+    if (h.n_bwt != h.n_text + h.n_seq || h.n_blocks != h.n_bwt / block_bases(h.sigma) + 1) { err = "index header inconsistent"; return false; }
+    if (h.sigma == 5 && !h.off_nmask) { err = "Dna5 index without N mask"; return false; }
+    const uint64_t offs[] = {h.off_fwd, h.off_rev, h.off_sent_fwd, h.off_sent_rev, h.off_text, h.off_limits, h.off_seq_start, h.off_sa, h.off_nmask};
     for (uint64_t o : offs)
         if (o >= h.total_bytes || (o % 256) != 0) { err = "index header offsets out of range"; return false; }
     return true;

@@ -57,15 +57,19 @@ struct Blob {
 struct BlobPlan {
     IndexHeader h;
 };
-BlobPlan plan_blob(uint64_t n_text, uint32_t n_seq, bool with_sa);
+BlobPlan plan_blob(uint64_t n_text, uint32_t n_seq, bool with_sa, uint32_t sigma = 4);
+inline uint32_t block_bases(uint32_t sigma) { return sigma == 5 ? kBlockBases5 : kBlockBases; }
+inline uint32_t block_bytes(uint32_t sigma) { return sigma == 5 ? (uint32_t)sizeof(RankBlock5) : kBlockBytes; }
 
-// Pack one direction's BWT (symbols: 0/1 = sentinel, 2..5 = A,C,G,T) into rank blocks + sentinel list.
-// Returns per-base totals in tot[4].
+// Pack one direction's BWT (symbols: 0/1 = sentinel, 2..5 = A,C,G,T, 6 = N) into rank blocks + sentinel list.
+// Returns per-base totals in tot[].  The Dna5 variant fills RankBlock5.
 void pack_bwt_blocks(const uint8_t* bwt, uint64_t n, RankBlock* blocks, uint32_t n_blocks, uint32_t* sent_pos,
                      uint32_t n_seq, uint64_t tot[4]);
+void pack_bwt_blocks5(const uint8_t* bwt, uint64_t n, RankBlock5* blocks, uint32_t n_blocks, uint32_t* sent_pos,
+                      uint32_t n_seq, uint64_t tot[5]);
 
-// Build the whole index on the host.  codes: 0..3 = ACGT (4 = N is rejected: Dna5 indices are not
-// supported by the GPU path yet); limits: n_seq+1 cumulative offsets.
+// Build the whole index on the host.  codes: 0..3 = ACGT, 4 = N (any N makes it a Dna5 index, as in
+// src/indexing.hpp:459-473); limits: n_seq+1 cumulative offsets.
 bool build_index_host(const uint8_t* codes, const uint64_t* limits, uint32_t n_seq, bool with_sa, Blob& blob,
                       std::string& err);
 

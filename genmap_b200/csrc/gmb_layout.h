@@ -47,16 +47,29 @@ struct alignas(kBlockBytes) RankBlock {
 static_assert(sizeof(RankBlock) == kBlockBytes, "rank block size");
 static_assert(kBlockWords == 1 || kBlockWords == 3, "supported layouts: 32-byte and 64-byte blocks");
 
+// ---- Dna5 rank block (genomes containing N): 64 bytes, 96 BWT symbols, three bit planes ----------------
+// codes A=0 C=1 G=2 T=3 N=4 (plane 2 set only for N); counters for A,C,G,T, N is derived:
+// N(i) = i - A - C - G - T - $.  Sentinel rows as in the Dna4 block (code 0 + side list).
+constexpr uint32_t kBlockBases5 = 96;
+struct alignas(64) RankBlock5 {
+    uint32_t cnt[4];
+    uint32_t sent;
+    uint32_t pad0;
+    uint32_t plane[3][3]; // [plane][32-symbol piece]
+    uint32_t pad1;
+};
+static_assert(sizeof(RankBlock5) == 64, "Dna5 rank block size");
+
 // ---- on-disk / in-HBM blob --------------------------------------------------------------------------
 // One contiguous, 256-byte aligned blob; offsets are relative to its start so the same bytes serve as
 // file, pinned host copy and device copy (copied verbatim, broadcast verbatim).
 constexpr uint64_t kMagic = 0x3130584449424d47ULL; // "GMBIDX01"
-constexpr uint32_t kVersion = 2 + 16 * kBlockWords; // the block layout is part of the format
+constexpr uint32_t kVersion = 3 + 16 * kBlockWords; // the block layout is part of the format
 
 struct IndexHeader {
     uint64_t magic;
     uint32_t version;
-    uint32_t sigma;          // 4 (Dna4). 5 (Dna5) is rejected by the GPU path for now.
+    uint32_t sigma;          // 4 (Dna4: RankBlock) or 5 (Dna5, the text contains N: RankBlock5 + N mask)
     uint64_t n_bwt;          // N = text length + one sentinel per sequence
     uint64_t n_text;         // concatenated text length (no sentinels)
     uint32_t n_seq;
@@ -73,8 +86,9 @@ struct IndexHeader {
                              // RAM; 4 bytes/row (12 GB at 3 Gbp) is affordable in 180 GB of HBM and
                              // makes locate one read instead of an LF walk.  Only -ep / csv need it.
     uint64_t off_seq_start;  // uint32[n_seq + 1] start of every sequence inside T (limits[i] + i)
+    uint64_t off_nmask;      // sigma == 5: uint64[n_text/64 + 2], bit i set <=> text position i is N (0 = absent)
     uint64_t total_bytes;
-    uint64_t reserved[8];
+    uint64_t reserved[7];
 };
 static_assert(sizeof(IndexHeader) % 8 == 0, "header alignment");
 

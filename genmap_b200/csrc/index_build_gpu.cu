@@ -4,7 +4,7 @@
 // Replaces (as a one-off preprocessing step, not on the timed map path) the reference's
 // single-threaded divsufsort + createRankDictionary (src/seqan_libdivsufsort.h:35-240), which takes
 // ~45 min at 3 Gbp.  The order produced is exactly the host builder's (gmb_host.cpp): suffixes of
-// s1$s2$...sm# compared as plain strings with '#' < '$' < A < C < G < T.
+// s1$s2$...sm# compared as plain strings with '#' < '$' < A < C < G < T < N.
 //
 // Algorithm (Manber-Myers doubling with discarding):
 //   1. sort all suffixes by their first 21 symbols (3 bits each = one 63-bit radix-sort key);
@@ -45,7 +45,7 @@ struct DevBuf {
 
 inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kTB - 1) / kTB); }
 
-// T (rev = 0) or T' (rev = 1) as symbols: '#' = 0 (last), '$' = 1, A,C,G,T = 2..5
+// T (rev = 0) or T' (rev = 1) as symbols: '#' = 0 (last), '$' = 1, A,C,G,T = 2..5, N = 6
 __global__ void k_make_symbols(const uint8_t* __restrict__ codes, const uint64_t* __restrict__ limits,
                                const uint32_t* __restrict__ seq_start, uint32_t n_seq, uint64_t n, int rev,
                                uint8_t* __restrict__ sym)
@@ -198,6 +198,52 @@ __global__ void k_headers(uint32_t n_blocks, RankBlock* __restrict__ blocks, con
     blocks[b].sent = (cS[b] << 8) | (blocks[b].sent & 0xffu);
 }
 
+// Dna5 flavour of the two kernels above (RankBlock5: 96 symbols, three planes, counters for A,C,G,T)
+__global__ void k_pack_blocks5(const uint8_t* __restrict__ bwt, uint64_t n, uint32_t n_blocks, RankBlock5* __restrict__ blocks,
+                               uint32_t* __restrict__ cA, uint32_t* __restrict__ cC, uint32_t* __restrict__ cG,
+                               uint32_t* __restrict__ cT, uint32_t* __restrict__ cS)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    RankBlock5 B;
+    uint32_t cnt[4] = {0, 0, 0, 0}, s = 0;
+    const uint64_t base = (uint64_t)b * kBlockBases5;
+#pragma unroll
+    for (int piece = 0; piece < 3; ++piece) {
+        uint32_t p0 = 0, p1 = 0, p2 = 0;
+        for (int k = 0; k < 32; ++k) {
+            const uint64_t i = base + piece * 32 + k;
+            if (i >= n) break;
+            const uint32_t v = bwt[i];
+            if (v < 2) { ++s; continue; }
+            const uint32_t code = v - 2u;
+            cnt[0] += code == 0; cnt[1] += code == 1; cnt[2] += code == 2; cnt[3] += code == 3;
+            p0 |= (code & 1u) << k;
+            p1 |= ((code >> 1) & 1u) << k;
+            p2 |= (code >> 2) << k;
+        }
+        B.plane[0][piece] = p0; B.plane[1][piece] = p1; B.plane[2][piece] = p2;
+    }
+    B.cnt[0] = B.cnt[1] = B.cnt[2] = B.cnt[3] = 0;
+    B.sent = s;
+    B.pad0 = B.pad1 = 0;
+    blocks[b] = B;
+    cA[b] = cnt[0]; cC[b] = cnt[1]; cG[b] = cnt[2]; cT[b] = cnt[3]; cS[b] = s;
+}
+
+__global__ void k_headers5(uint32_t n_blocks, RankBlock5* __restrict__ blocks, const uint32_t* __restrict__ cA,
+                           const uint32_t* __restrict__ cC, const uint32_t* __restrict__ cG, const uint32_t* __restrict__ cT,
+                           const uint32_t* __restrict__ cS)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    blocks[b].cnt[0] = cA[b];
+    blocks[b].cnt[1] = cC[b];
+    blocks[b].cnt[2] = cG[b];
+    blocks[b].cnt[3] = cT[b];
+    blocks[b].sent = (cS[b] << 8) | (blocks[b].sent & 0xffu);
+}
+
 struct IsSentinel {
     const uint8_t* bwt;
     __device__ bool operator()(uint32_t k) const { return bwt[k] < 2; }
@@ -215,10 +261,25 @@ __global__ void k_pack_text(const uint8_t* __restrict__ codes, uint64_t n_text, 
     text[wi] = v;
 }
 
-__global__ void k_check_codes(const uint8_t* __restrict__ codes, uint64_t n_text, int* __restrict__ bad)
+__global__ void k_pack_nmask(const uint8_t* __restrict__ codes, uint64_t n_text, uint64_t n_words, uint64_t* __restrict__ nmask)
+{
+    const uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= n_words) return;
+    uint64_t v = 0;
+    for (int k = 0; k < 64; ++k) {
+        const uint64_t i = wi * 64 + k;
+        if (i < n_text && codes[i] == 4) v |= 1ull << k;
+    }
+    nmask[wi] = v;
+}
+
+// flags[0]: a code outside 0..4; flags[1]: the text contains N (-> Dna5 index, src/indexing.hpp:459-473)
+__global__ void k_check_codes(const uint8_t* __restrict__ codes, uint64_t n_text, int* __restrict__ flags)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_text && codes[i] > 3) *bad = 1;
+    if (i >= n_text) return;
+    if (codes[i] > 4) flags[0] = 1;
+    else if (codes[i] == 4) flags[1] = 1;
 }
 
 #define CUB_(call)                                                                          \
@@ -323,31 +384,32 @@ int build_index_gpu_device(const uint8_t* codes, const uint64_t* limits, uint32_
     CUB_(cudaSetDevice(device));
     const auto t_start = std::chrono::steady_clock::now();
 
-    BlobPlan plan = plan_blob(n_text, n_seq, with_sa);
-    IndexHeader h = plan.h;
-    DevBuf blob;
-    CUB_(blob.alloc(h.total_bytes));
-    uint8_t* base = blob.as<uint8_t>();
-    CUB_(cudaMemset(base, 0, h.total_bytes));
-
     // inputs
     DevBuf d_codes, d_sym, d_bwt, d_bad;
     CUB_(d_codes.alloc(n_text));
     CUB_(d_sym.alloc(n + 64));
     CUB_(d_bwt.alloc(n));
-    CUB_(d_bad.alloc(sizeof(int)));
+    CUB_(d_bad.alloc(2 * sizeof(int)));
     CUB_(cudaMemcpy(d_codes.p, codes, n_text, cudaMemcpyHostToDevice));
+    CUB_(cudaMemset(d_bad.p, 0, 2 * sizeof(int)));
+    k_check_codes<<<grid_for(n_text), kTB>>>(d_codes.as<uint8_t>(), n_text, d_bad.as<int>());
+    int bad[2] = {0, 0};
+    CUB_(cudaMemcpy(bad, d_bad.p, sizeof(bad), cudaMemcpyDeviceToHost));
+    if (bad[0]) { err = "invalid base code (expected 0..3 = ACGT, 4 = N)"; return GMB_ERR_ARG; }
+    const uint32_t sigma = bad[1] ? 5 : 4;
+
+    BlobPlan plan = plan_blob(n_text, n_seq, with_sa, sigma);
+    IndexHeader h = plan.h;
+    DevBuf blob;
+    CUB_(blob.alloc(h.total_bytes));
+    uint8_t* base = blob.as<uint8_t>();
+    CUB_(cudaMemset(base, 0, h.total_bytes));
     std::vector<uint32_t> seq_start((size_t)n_seq + 1);
     for (uint32_t s = 0; s <= n_seq; ++s) seq_start[s] = (uint32_t)(limits[s] + s);
     uint64_t* d_limits = reinterpret_cast<uint64_t*>(base + h.off_limits);
     uint32_t* d_seq_start = reinterpret_cast<uint32_t*>(base + h.off_seq_start);
     CUB_(cudaMemcpy(d_limits, limits, ((size_t)n_seq + 1) * 8, cudaMemcpyHostToDevice));
     CUB_(cudaMemcpy(d_seq_start, seq_start.data(), seq_start.size() * 4, cudaMemcpyHostToDevice));
-    CUB_(cudaMemset(d_bad.p, 0, sizeof(int)));
-    k_check_codes<<<grid_for(n_text), kTB>>>(d_codes.as<uint8_t>(), n_text, d_bad.as<int>());
-    int bad = 0;
-    CUB_(cudaMemcpy(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost));
-    if (bad) { err = "sequence contains N: Dna5 indices are not supported by the GPU path yet"; return GMB_ERR_UNSUPPORTED; }
     if (timings) timings->h2d_ms = ms_since(t_start);
 
     // sort buffers, sized for the first (full) round
@@ -371,12 +433,13 @@ int build_index_gpu_device(const uint8_t* codes, const uint64_t* limits, uint32_
         CUB_(B.temp.alloc(B.temp_bytes));
     }
 
-    DevBuf cA, cC, cG, cS;
+    DevBuf cA, cC, cG, cT, cS;
     CUB_(cA.alloc((size_t)h.n_blocks * 4)); CUB_(cC.alloc((size_t)h.n_blocks * 4));
-    CUB_(cG.alloc((size_t)h.n_blocks * 4)); CUB_(cS.alloc((size_t)h.n_blocks * 4));
+    CUB_(cG.alloc((size_t)h.n_blocks * 4)); CUB_(cT.alloc((size_t)h.n_blocks * 4));
+    CUB_(cS.alloc((size_t)h.n_blocks * 4));
 
     double sort_ms = 0, pack_ms = 0;
-    uint64_t totA = 0, totC = 0, totG = 0;
+    uint64_t tot[4] = {0, 0, 0, 0};
     for (int rev = 0; rev < 2; ++rev) {
         auto t0 = std::chrono::steady_clock::now();
         CUB_(cudaMemset(d_sym.p, 0, n + 64));
@@ -392,21 +455,30 @@ int build_index_gpu_device(const uint8_t* codes, const uint64_t* limits, uint32_
         t0 = std::chrono::steady_clock::now();
         uint32_t* sa = B.sa.as<uint32_t>();
         k_bwt<<<grid_for(n), kTB>>>(sa, d_sym.as<uint8_t>(), n, d_bwt.as<uint8_t>());
-        RankBlock* blocks = reinterpret_cast<RankBlock*>(base + (rev ? h.off_rev : h.off_fwd));
-        k_pack_blocks<<<grid_for(h.n_blocks), kTB>>>(d_bwt.as<uint8_t>(), n, h.n_blocks, blocks, cA.as<uint32_t>(),
-                                                      cC.as<uint32_t>(), cG.as<uint32_t>(), cS.as<uint32_t>());
+        uint8_t* blocks = base + (rev ? h.off_rev : h.off_fwd);
+        uint32_t* cs[5] = {cA.as<uint32_t>(), cC.as<uint32_t>(), cG.as<uint32_t>(), cT.as<uint32_t>(), cS.as<uint32_t>()};
+        if (sigma == 5)
+            k_pack_blocks5<<<grid_for(h.n_blocks), kTB>>>(d_bwt.as<uint8_t>(), n, h.n_blocks, reinterpret_cast<RankBlock5*>(blocks),
+                                                           cs[0], cs[1], cs[2], cs[3], cs[4]);
+        else
+            k_pack_blocks<<<grid_for(h.n_blocks), kTB>>>(d_bwt.as<uint8_t>(), n, h.n_blocks, reinterpret_cast<RankBlock*>(blocks),
+                                                          cs[0], cs[1], cs[2], cs[4]);
         CUB_(cudaGetLastError());
-        uint32_t last[3], lastx[3];
-        uint32_t* cs[4] = {cA.as<uint32_t>(), cC.as<uint32_t>(), cG.as<uint32_t>(), cS.as<uint32_t>()};
-        for (int c = 0; c < 3; ++c) CUB_(cudaMemcpy(&last[c], cs[c] + (h.n_blocks - 1), 4, cudaMemcpyDeviceToHost));
-        for (int c = 0; c < 4; ++c) {
+        const int n_counted = sigma == 5 ? 4 : 3; // symbols with a counter; the last one is derived
+        uint32_t last[4] = {0, 0, 0, 0}, lastx[4] = {0, 0, 0, 0};
+        for (int c = 0; c < n_counted; ++c) CUB_(cudaMemcpy(&last[c], cs[c] + (h.n_blocks - 1), 4, cudaMemcpyDeviceToHost));
+        for (int c = 0; c < 5; ++c) {
+            if (c == 3 && sigma != 5) continue;
             size_t tb = B.temp_bytes;
             CUB_(cub::DeviceScan::ExclusiveSum(B.temp.p, tb, cs[c], cs[c], (uint64_t)h.n_blocks));
         }
-        for (int c = 0; c < 3; ++c) CUB_(cudaMemcpy(&lastx[c], cs[c] + (h.n_blocks - 1), 4, cudaMemcpyDeviceToHost));
-        k_headers<<<grid_for(h.n_blocks), kTB>>>(h.n_blocks, blocks, cs[0], cs[1], cs[2], cs[3]);
+        for (int c = 0; c < n_counted; ++c) CUB_(cudaMemcpy(&lastx[c], cs[c] + (h.n_blocks - 1), 4, cudaMemcpyDeviceToHost));
+        if (sigma == 5)
+            k_headers5<<<grid_for(h.n_blocks), kTB>>>(h.n_blocks, reinterpret_cast<RankBlock5*>(blocks), cs[0], cs[1], cs[2], cs[3], cs[4]);
+        else
+            k_headers<<<grid_for(h.n_blocks), kTB>>>(h.n_blocks, reinterpret_cast<RankBlock*>(blocks), cs[0], cs[1], cs[2], cs[4]);
         CUB_(cudaGetLastError());
-        if (!rev) { totA = (uint64_t)last[0] + lastx[0]; totC = (uint64_t)last[1] + lastx[1]; totG = (uint64_t)last[2] + lastx[2]; }
+        if (!rev) for (int c = 0; c < n_counted; ++c) tot[c] = (uint64_t)last[c] + lastx[c];
         uint32_t* sent = reinterpret_cast<uint32_t*>(base + (rev ? h.off_sent_rev : h.off_sent_fwd));
         {
             size_t tb = B.temp_bytes;
@@ -425,12 +497,14 @@ int build_index_gpu_device(const uint8_t* codes, const uint64_t* limits, uint32_
     }
     // C array with the sentinels as smallest symbols (src/seqan_libdivsufsort.h:231-233)
     h.C[0] = n_seq;
-    h.C[1] = h.C[0] + totA;
-    h.C[2] = h.C[1] + totC;
-    h.C[3] = h.C[2] + totG;
-    h.C[4] = n;
+    for (int c = 0; c < 3; ++c) h.C[c + 1] = h.C[c] + tot[c];
+    h.C[4] = sigma == 5 ? h.C[3] + tot[3] : n;
+    h.C[5] = n;
     k_pack_text<<<grid_for(n_text / 32 + 2), kTB>>>(d_codes.as<uint8_t>(), n_text, n_text / 32 + 2,
                                                      reinterpret_cast<uint64_t*>(base + h.off_text));
+    if (sigma == 5)
+        k_pack_nmask<<<grid_for(n_text / 64 + 2), kTB>>>(d_codes.as<uint8_t>(), n_text, n_text / 64 + 2,
+                                                          reinterpret_cast<uint64_t*>(base + h.off_nmask));
     CUB_(cudaGetLastError());
     CUB_(cudaMemcpy(base, &h, sizeof(h), cudaMemcpyHostToDevice));
     CUB_(cudaDeviceSynchronize());

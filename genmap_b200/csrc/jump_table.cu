@@ -9,6 +9,7 @@ namespace gmb {
 
 namespace {
 
+template <int SIGMA>
 __global__ void k_jump_level(const MapCtx cx, uint32_t d, const JtEntry* __restrict__ prev_uni,
                              const uint32_t* __restrict__ prev_lof, JtEntry* __restrict__ out_uni,
                              uint32_t* __restrict__ out_lof)
@@ -24,7 +25,7 @@ __global__ void k_jump_level(const MapCtx cx, uint32_t d, const JtEntry* __restr
         const JtEntry e = prev_uni[pk];
         par.lo_f = prev_lof ? prev_lof[pk] : 0u; par.lo_r = e.lo_r; par.size = e.size;
     }
-    const Node m = extend_right(par, (uint32_t)(key >> (2 * (d - 1))), cx);
+    const Node m = extend_right<SIGMA>(par, (uint32_t)(key >> (2 * (d - 1))), cx); // keys are A,C,G,T only
     JtEntry o;
     o.lo_r = m.lo_r; o.size = m.size;
     out_uni[key] = o;
@@ -33,13 +34,14 @@ __global__ void k_jump_level(const MapCtx cx, uint32_t d, const JtEntry* __restr
 
 } // namespace
 
-cudaError_t build_jump_level(const MapCtx& cx, uint32_t d, const JtEntry* prev_uni, const uint32_t* prev_lof,
+cudaError_t build_jump_level(const MapCtx& cx, uint32_t sigma, uint32_t d, const JtEntry* prev_uni, const uint32_t* prev_lof,
                              JtEntry* out_uni, uint32_t* out_lof, cudaStream_t stream)
 {
     const uint64_t n = 1ull << (2 * d);
     const unsigned threads = 256;
     const unsigned long long blocks = (n + threads - 1) / threads;
-    k_jump_level<<<(unsigned)blocks, threads, 0, stream>>>(cx, d, prev_uni, prev_lof, out_uni, out_lof);
+    if (sigma == 5) k_jump_level<5><<<(unsigned)blocks, threads, 0, stream>>>(cx, d, prev_uni, prev_lof, out_uni, out_lof);
+    else k_jump_level<4><<<(unsigned)blocks, threads, 0, stream>>>(cx, d, prev_uni, prev_lof, out_uni, out_lof);
     return cudaGetLastError();
 }
 

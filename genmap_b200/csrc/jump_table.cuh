@@ -8,7 +8,7 @@ namespace gmb {
 
 // Level d from level d-1 (d == 1: from the root): one thread per d-mer extends its (d-1)-mer parent by
 // one character to the right on the bidirectional index.  out_uni / out_lof have 4^d entries.
-cudaError_t build_jump_level(const MapCtx& cx, uint32_t d, const JtEntry* prev_uni, const uint32_t* prev_lof,
+cudaError_t build_jump_level(const MapCtx& cx, uint32_t sigma, uint32_t d, const JtEntry* prev_uni, const uint32_t* prev_lof,
                              JtEntry* out_uni, uint32_t* out_lof, cudaStream_t stream);
 
 } // namespace gmb

@@ -26,11 +26,12 @@ constexpr int kThreads = 256;
 #define GMB_MIN_BLOCKS 4 // resident CTAs per SM the register allocation must allow
 #endif
 
+template <int FW> // words per mismatch frame (10 for Dna4, 12 for Dna5)
 struct SmemFrames {
     uint32_t* base;  // + threadIdx.x; word i of this chain at base[i * kThreads] (conflict-free)
     uint32_t xoff;   // first word after the E mismatch frames
-    __device__ __forceinline__ void set(uint32_t lv, uint32_t i, uint32_t v) { base[(lv * kFrameWords + i) * kThreads] = v; }
-    __device__ __forceinline__ uint32_t get(uint32_t lv, uint32_t i) const { return base[(lv * kFrameWords + i) * kThreads]; }
+    __device__ __forceinline__ void set(uint32_t lv, uint32_t i, uint32_t v) { base[(lv * FW + i) * kThreads] = v; }
+    __device__ __forceinline__ uint32_t get(uint32_t lv, uint32_t i) const { return base[(lv * FW + i) * kThreads]; }
     __device__ __forceinline__ void xset(uint32_t i, uint32_t v) { base[(xoff + i) * kThreads] = v; }
     __device__ __forceinline__ uint32_t xget(uint32_t i) const { return base[(xoff + i) * kThreads]; }
 };
@@ -38,8 +39,8 @@ struct SmemFrames {
 __host__ __device__ inline uint32_t align32(uint32_t x) { return (x + 31u) & ~31u; }
 constexpr uint32_t kStartWords = sizeof(SearchStart) / 4;
 
-template <int KW, bool COUNT, typename OutT, bool EP, bool BLK>
-__global__ void __launch_bounds__(kThreads, GMB_MIN_BLOCKS) map_kernel(const MapLaunch L)
+template <int KW, bool COUNT, typename OutT, bool EP, bool BLK, int SIGMA>
+__global__ void __launch_bounds__(kThreads, SIGMA == 5 ? 2 : GMB_MIN_BLOCKS) map_kernel(const MapLaunch L)
 {
     // shared memory: step tables | jump-table starts | offsets | per-chain frame store
     extern __shared__ uint32_t smem[];
@@ -64,14 +65,14 @@ __global__ void __launch_bounds__(kThreads, GMB_MIN_BLOCKS) map_kernel(const Map
     cx.starts = reinterpret_cast<const SearchStart*>(starts_s);
     cx.p1_off = offs_s;
     cx.fl_off = offs_s + kMaxBlockKmers + 1;
-    SmemFrames fr{frames_s + threadIdx.x, L.E * kFrameWords};
+    SmemFrames<(int)frame_words(SIGMA)> fr{frames_s + threadIdx.x, L.E * frame_words(SIGMA)};
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     OutT* __restrict__ out = static_cast<OutT*>(L.out);
     const unsigned long long B = BLK ? cx.B : 1ull;
 
-    Chain<KW> st;
+    Chain<KW, SIGMA> st;
     uint64_t j = 0; // first position of the chain's block
     bool active = false, exhausted = false;
     // warp-uniform pool of consecutive positions [pool_next, pool_end) and "no more chunks" flag;
@@ -125,8 +126,8 @@ __global__ void __launch_bounds__(kThreads, GMB_MIN_BLOCKS) map_kernel(const Map
             if (need) {
                 if (got) {
                     st.cnt = (uint32_t)(jend - j < B ? jend - j : B);
-                    load_pattern(st.pat, L.text, L.text_begin + j, cx.K + st.cnt - 1);
-                    chain_begin_block<KW, EP, BLK>(st, fr, cx, COUNT ? &lut_reads : nullptr);
+                    load_pattern(st.pat, L.text, L.nmask, L.text_begin + j, cx.K + st.cnt - 1);
+                    chain_begin_block<KW, EP, BLK, SIGMA>(st, fr, cx, COUNT ? &lut_reads : nullptr);
                     active = true;
                 } else if (pool_done) {
                     exhausted = true;
@@ -137,8 +138,8 @@ __global__ void __launch_bounds__(kThreads, GMB_MIN_BLOCKS) map_kernel(const Map
 
         // ---- one node expansion per chain -------------------------------------------------------------
         if (active) {
-            if (!chain_step<KW, EP, BLK>(st, fr, cx, COUNT ? &fetches : nullptr, COUNT ? &lut_reads : nullptr)) {
-                for (uint32_t w = 0; w < st.cnt; ++w) out[j + w] = (OutT)chain_result<KW, EP, BLK>(st, fr, cx, w);
+            if (!chain_step<KW, EP, BLK, SIGMA>(st, fr, cx, COUNT ? &fetches : nullptr, COUNT ? &lut_reads : nullptr)) {
+                for (uint32_t w = 0; w < st.cnt; ++w) out[j + w] = (OutT)chain_result<KW, EP, BLK, SIGMA>(st, fr, cx, w);
                 active = false;
             }
         }
@@ -153,11 +154,11 @@ __global__ void __launch_bounds__(kThreads, GMB_MIN_BLOCKS) map_kernel(const Map
     }
 }
 
-template <int KW, bool COUNT, typename OutT, bool EP, bool BLK>
+template <int KW, bool COUNT, typename OutT, bool EP, bool BLK, int SIGMA>
 cudaError_t launch_b(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
-    auto kern = map_kernel<KW, COUNT, OutT, EP, BLK>;
-    const size_t smem = map_kernel_smem_bytes(L.n_step_words, L.E, L.cx.B, EP);
+    auto kern = map_kernel<KW, COUNT, OutT, EP, BLK, SIGMA>;
+    const size_t smem = map_kernel_smem_bytes(L.n_step_words, L.E, L.cx.B, EP, SIGMA);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -175,7 +176,9 @@ cudaError_t launch_b(const MapLaunch& L, int sm_count, cudaStream_t stream)
 template <int KW, bool COUNT, typename OutT, bool EP>
 cudaError_t launch_t(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
-    return L.cx.B > 1 ? launch_b<KW, COUNT, OutT, EP, true>(L, sm_count, stream) : launch_b<KW, COUNT, OutT, EP, false>(L, sm_count, stream);
+    // Dna5 indices always run the blocked instantiation (it covers B == 1) to keep the number of kernels down
+    if (L.sigma == 5) return launch_b<KW, COUNT, OutT, EP, true, 5>(L, sm_count, stream);
+    return L.cx.B > 1 ? launch_b<KW, COUNT, OutT, EP, true, 4>(L, sm_count, stream) : launch_b<KW, COUNT, OutT, EP, false, 4>(L, sm_count, stream);
 }
 
 template <int KW>
@@ -193,10 +196,10 @@ cudaError_t launch_kw(const MapLaunch& L, int sm_count, cudaStream_t stream)
 
 } // namespace
 
-size_t map_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool ep)
+size_t map_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool ep, uint32_t sigma)
 {
     const size_t tables = align32(n_step_words) + align32((B + 1) * kMaxSearches * kStartWords) + align32(2 * (kMaxBlockKmers + 1));
-    return (tables + (size_t)frame_store_words(E, B, ep) * kThreads) * sizeof(uint32_t);
+    return (tables + (size_t)frame_store_words(E, B, ep, (int)sigma, B > 1 || sigma == 5) * kThreads) * sizeof(uint32_t);
 }
 
 cudaError_t launch_map_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream)

@@ -14,7 +14,9 @@ struct MapLaunch {
     uint32_t n_step_words;
     uint32_t p1_off[kMaxBlockKmers + 1], fl_off[kMaxBlockKmers + 1];
     uint32_t chunk;            // positions per work chunk: a multiple of cx.B
+    uint32_t sigma;            // 4 or 5: alphabet of the index (selects the rank-block layout)
     const uint64_t* text;      // 2-bit packed concatenated text (device)
+    const uint64_t* nmask;     // sigma == 5: N mask of the text, one bit per position
     uint64_t text_begin;       // start of this FASTA file's text inside the concatenated text
     // work = chunks of <= `chunk` consecutive positions; a chunk never straddles two ranges
     const uint64_t* range_begin;  // device: n_ranges work ranges, file-local [begin, end)
@@ -34,7 +36,7 @@ struct MapLaunch {
 constexpr unsigned kChunk = 128; // positions handed out per global atomic (rounded down to a multiple of B)
 
 // dynamic shared memory the kernel needs for these tables (the host shrinks B if this exceeds the SM's limit)
-size_t map_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool ep);
+size_t map_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool ep, uint32_t sigma);
 
 // Enqueue the kernel on `stream`.  Returns cudaSuccess or the launch error.
 cudaError_t launch_map_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream);

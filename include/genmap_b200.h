@@ -39,7 +39,7 @@ typedef struct gmb_index gmb_index;
 typedef enum gmb_status {
     GMB_OK = 0,
     GMB_ERR_ARG = -1,         /* bad argument (K, E, sizes, NULL) */
-    GMB_ERR_UNSUPPORTED = -2, /* E > 4, K > 255, Dna5 index, index >= 2^32-1 symbols */
+    GMB_ERR_UNSUPPORTED = -2, /* E > 4, K > 255, index >= 2^32-1 symbols */
     GMB_ERR_CUDA = -3,        /* no device / CUDA runtime error */
     GMB_ERR_IO = -4,          /* index file missing / malformed */
     GMB_ERR_NOMEM = -5
@@ -64,10 +64,10 @@ typedef struct gmb_index_info {
     uint32_t n_seq;
     uint32_t has_sa;
     uint64_t blob_bytes;  /* size of the index blob in HBM */
-    uint64_t rank_block_bytes; /* 64 */
+    uint64_t rank_block_bytes; /* 32 (Dna4: 64 symbols per block) or 64 (Dna5: 96 symbols per block) */
     void *device_blob;    /* device address of the blob (for broadcast / diagnostics) */
     int32_t device;
-    int32_t reserved;
+    int32_t alphabet_size; /* 4 = Dna4; 5 = Dna5, chosen when the text contains N (src/indexing.hpp:459-473) */
 } gmb_index_info;
 
 typedef struct gmb_map_stats {
@@ -87,7 +87,7 @@ const char *gmb_last_error(void);
 const char *gmb_version(void);
 int gmb_device_count(void);
 
-/* Build an index blob in host memory from code text (0..3 = ACGT; 4 = N is rejected for now).
+/* Build an index blob in host memory from code text (0..3 = ACGT, 4 = N; any N makes it a Dna5 index).
  * limits: n_seq+1 cumulative offsets.  The blob is released with gmb_blob_free. */
 int gmb_index_build(const uint8_t *codes, const uint64_t *limits, uint32_t n_seq, uint32_t flags,
                     int device, void **blob_out, uint64_t *bytes_out);
@@ -116,7 +116,7 @@ int gmb_index_get_info(const gmb_index *idx, gmb_index_info *info);
  * device by the first map call that needs them and cached in the handle. */
 int gmb_index_set_jump_depth(gmb_index *idx, int depth);
 /* Diagnostics / test support: decode one direction's BWT (rev = 0: of T, 1: of T') to one byte per
- * row (0 = sentinel, 1..4 = A,C,G,T) into host memory (n_bwt bytes). */
+ * row (0 = sentinel, 1..5 = A,C,G,T,N) into host memory (n_bwt bytes). */
 int gmb_index_export_bwt(gmb_index *idx, int rev, uint8_t *out_host);
 /* Copy the full suffix array of T (n_bwt uint32 positions inside the sentinel-separated text) to host
  * memory; fails with GMB_ERR_UNSUPPORTED when the index was built without GMB_BUILD_WITH_SA. */

@@ -16,7 +16,7 @@ using namespace gmb;
 
 namespace {
 struct HostFrames {
-    uint32_t w[kMaxE][kFrameWords];
+    uint32_t w[kMaxE][kFrameWords5];
     uint32_t x[kLeafWords + 3 * kMaxBlockKmers];
     inline void set(uint32_t lv, uint32_t i, uint32_t v) { w[lv][i] = v; }
     inline uint32_t get(uint32_t lv, uint32_t i) const { return w[lv][i]; }
@@ -24,20 +24,21 @@ struct HostFrames {
     inline uint32_t xget(uint32_t i) const { return x[i]; }
 };
 
-template <int KW, bool EP, bool BLK>
-void run_ranges(const MapCtx& cx, const uint64_t* text, uint64_t text_begin, const std::vector<WorkRange>& ranges,
-                int value_bits, void* out, unsigned long long* fetches, unsigned long long* lut_reads)
+template <int KW, bool EP, bool BLK, int SIGMA>
+void run_ranges(const MapCtx& cx, const uint64_t* text, const uint64_t* nmask, uint64_t text_begin,
+                const std::vector<WorkRange>& ranges, int value_bits, void* out, unsigned long long* fetches,
+                unsigned long long* lut_reads)
 {
     for (const WorkRange& r : ranges)
         for (uint64_t j0 = r.begin; j0 < r.end; j0 += cx.B) { // blocks of up to B adjacent k-mers, never across ranges
-            Chain<KW> st;
+            Chain<KW, SIGMA> st;
             HostFrames fr;
             st.cnt = (uint32_t)std::min<uint64_t>(cx.B, r.end - j0);
-            load_pattern(st.pat, text, text_begin + j0, cx.K + st.cnt - 1);
-            chain_begin_block<KW, EP, BLK>(st, fr, cx, lut_reads);
-            while (chain_step<KW, EP, BLK>(st, fr, cx, fetches, lut_reads)) {}
+            load_pattern(st.pat, text, nmask, text_begin + j0, cx.K + st.cnt - 1);
+            chain_begin_block<KW, EP, BLK, SIGMA>(st, fr, cx, lut_reads);
+            while (chain_step<KW, EP, BLK, SIGMA>(st, fr, cx, fetches, lut_reads)) {}
             for (uint32_t w = 0; w < st.cnt; ++w) {
-                const uint32_t v = chain_result<KW, EP, BLK>(st, fr, cx, w);
+                const uint32_t v = chain_result<KW, EP, BLK, SIGMA>(st, fr, cx, w);
                 if (value_bits == 16) static_cast<uint16_t*>(out)[j0 + w] = (uint16_t)v;
                 else static_cast<uint8_t*>(out)[j0 + w] = (uint8_t)v;
             }
@@ -66,12 +67,23 @@ void hs_export_bwt(const void* blob, int rev, uint8_t* out)
 {
     const uint8_t* base = static_cast<const uint8_t*>(blob);
     const IndexHeader& h = *reinterpret_cast<const IndexHeader*>(base);
-    const RankBlock* B = reinterpret_cast<const RankBlock*>(base + (rev ? h.off_rev : h.off_fwd));
     const uint32_t* sent = reinterpret_cast<const uint32_t*>(base + (rev ? h.off_sent_rev : h.off_sent_fwd));
-    for (uint64_t i = 0; i < h.n_bwt; ++i) {
-        const RankBlock& b = B[i / kBlockBases];
-        const uint32_t k = (uint32_t)(i % kBlockBases);
-        out[i] = (uint8_t)(1 + (((b.w[k >> 6][0] >> (k & 63)) & 1) | (((b.w[k >> 6][1] >> (k & 63)) & 1) << 1)));
+    if (h.sigma == 5) {
+        const RankBlock5* B = reinterpret_cast<const RankBlock5*>(base + (rev ? h.off_rev : h.off_fwd));
+        for (uint64_t i = 0; i < h.n_bwt; ++i) {
+            const RankBlock5& b = B[i / kBlockBases5];
+            const uint32_t k = (uint32_t)(i % kBlockBases5);
+            uint32_t c = 0;
+            for (int pl = 0; pl < 3; ++pl) c |= ((b.plane[pl][k >> 5] >> (k & 31)) & 1u) << pl;
+            out[i] = (uint8_t)(1 + c);
+        }
+    } else {
+        const RankBlock* B = reinterpret_cast<const RankBlock*>(base + (rev ? h.off_rev : h.off_fwd));
+        for (uint64_t i = 0; i < h.n_bwt; ++i) {
+            const RankBlock& b = B[i / kBlockBases];
+            const uint32_t k = (uint32_t)(i % kBlockBases);
+            out[i] = (uint8_t)(1 + (((b.w[k >> 6][0] >> (k & 63)) & 1) | (((b.w[k >> 6][1] >> (k & 63)) & 1) << 1)));
+        }
     }
     for (uint32_t s = 0; s < h.n_seq; ++s) out[sent[s]] = 0;
 }
@@ -110,11 +122,12 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     if (!build_block_tables(K, E, block_kmers, ep, tabs, err)) return -2;
     const uint32_t B = tabs.B;
     MapCtx cx;
-    cx.blk[0] = reinterpret_cast<const RankBlock*>(base + h.off_fwd);
-    cx.blk[1] = reinterpret_cast<const RankBlock*>(base + h.off_rev);
+    cx.blk[0] = base + h.off_fwd;
+    cx.blk[1] = base + h.off_rev;
     cx.sent[0] = reinterpret_cast<const uint32_t*>(base + h.off_sent_fwd);
     cx.sent[1] = reinterpret_cast<const uint32_t*>(base + h.off_sent_rev);
-    for (int c = 0; c < 4; ++c) cx.C[c] = (uint32_t)h.C[c];
+    for (int c = 0; c < 5; ++c) cx.C[c] = (uint32_t)h.C[c];
+    const uint32_t sigma = h.sigma;
     cx.n_bwt = (uint32_t)h.n_bwt;
     cx.steps = tabs.steps.data();
     cx.p1_off = tabs.p1_off;
@@ -149,7 +162,8 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
             Node par;
             if (d == 1) { par.lo_f = 0; par.lo_r = 0; par.size = cx.n_bwt; }
             else { par.lo_f = lof[d - 1][key & pmask]; par.lo_r = uni[d - 1][key & pmask].lo_r; par.size = uni[d - 1][key & pmask].size; }
-            const Node m = extend_right(par, (uint32_t)(key >> (2 * (d - 1))), cx);
+            const Node m = sigma == 5 ? extend_right<5>(par, (uint32_t)(key >> (2 * (d - 1))), cx)
+                                      : extend_right<4>(par, (uint32_t)(key >> (2 * (d - 1))), cx);
             uni[d][key].lo_r = m.lo_r; uni[d][key].size = m.size; lof[d][key] = m.lo_f;
         }
     }
@@ -167,10 +181,12 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     std::vector<WorkRange> ranges;
     build_work_ranges(text_len, K, chrom_cum, n_chrom, intervals, n_intervals, pos_begin, pos_end, ranges);
     const uint64_t* text = reinterpret_cast<const uint64_t*>(base + h.off_text);
+    const uint64_t* nmask = sigma == 5 ? reinterpret_cast<const uint64_t*>(base + h.off_nmask) : nullptr;
     unsigned long long f = 0, lr = 0;
-#define RUN_KB(KW, BLK) (ep ? run_ranges<KW, true, BLK>(cx, text, text_begin, ranges, value_bits, out, &f, &lr) \
-                            : run_ranges<KW, false, BLK>(cx, text, text_begin, ranges, value_bits, out, &f, &lr))
-#define RUN_KW(KW) (B > 1 ? RUN_KB(KW, true) : RUN_KB(KW, false))
+#define RUN_KS(KW, BLK, SG) (ep ? run_ranges<KW, true, BLK, SG>(cx, text, nmask, text_begin, ranges, value_bits, out, &f, &lr) \
+                                : run_ranges<KW, false, BLK, SG>(cx, text, nmask, text_begin, ranges, value_bits, out, &f, &lr))
+#define RUN_KB(KW, BLK) (sigma == 5 ? RUN_KS(KW, BLK, 5) : RUN_KS(KW, BLK, 4))
+#define RUN_KW(KW) ((B > 1 || sigma == 5) ? RUN_KB(KW, true) : RUN_KB(KW, false))
     const uint32_t needle = K + B - 1; // characters a chain keeps in registers
     if (needle <= 32) RUN_KW(1);
     else if (needle <= 64) RUN_KW(2);

@@ -46,10 +46,17 @@ def test_host_builder_blob_is_deterministic_and_matches_hostsim(lib):
 
 def test_builder_rejects_bad_input(lib):
     with pytest.raises(genmap_b200.GenmapError) as e:
-        genmap_b200.Index.build_blob([np.array([0, 1, 4, 2], np.uint8)])
-    assert e.value.code == _lib.GMB_ERR_UNSUPPORTED and "N" in str(e.value)
+        genmap_b200.Index.build_blob([np.array([0, 1, 5, 2], np.uint8)])
+    assert e.value.code == _lib.GMB_ERR_ARG and "invalid base code" in str(e.value)
     with pytest.raises(genmap_b200.GenmapError):
         genmap_b200.Index.build_blob([np.array([0, 1], np.uint8), np.zeros(0, np.uint8)])
+
+
+def test_n_makes_a_dna5_blob(lib):
+    # src/indexing.hpp:459-473: one N anywhere switches the whole index to the Dna5 alphabet
+    hdr4 = np.frombuffer(genmap_b200.Index.build_blob([np.array([0, 1, 3, 2] * 8, np.uint8)]), np.uint32, 4)
+    hdr5 = np.frombuffer(genmap_b200.Index.build_blob([np.array([0, 1, 4, 2] * 8, np.uint8)]), np.uint32, 4)
+    assert hdr4[3] == 4 and hdr5[3] == 5
 
 
 def test_no_cpu_fallback(lib):

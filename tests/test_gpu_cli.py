@@ -10,8 +10,7 @@ import gmtest as T
 
 pytestmark = pytest.mark.gpu
 
-# Dna5 genomes (1c-1g) are not on the GPU path yet
-CASES = ["1a", "1b", "2a", "2b", "2c", "2d", "2e", "3a", "3b", "3c", "3d", "3e", "3f"]
+CASES = sorted(T.CASES)  # all 18 of tests/CMakeLists.txt:56-73 (1c-1g are genomes with N: Dna5 indices)
 
 
 @pytest.fixture(scope="module")
@@ -63,7 +62,7 @@ def test_cli_reproduces_reference_golden_directories(genmap, case, tmp_path):
     _replay(genmap, case, tmp_path)
 
 
-@pytest.mark.parametrize("case", ["2b", "3d"])
+@pytest.mark.parametrize("case", ["1g", "2b", "3d"])
 def test_cli_golden_with_host_built_index_and_overlap_flag(genmap, case, tmp_path):
     _replay(genmap, case, tmp_path, host_builder=True)
     _replay(genmap, case, tmp_path, extra=("-xo", "1"))  # tests.sh:47-60 re-runs with -xo: results must not change

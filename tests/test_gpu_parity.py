@@ -27,9 +27,12 @@ def _map(gm, ix, K, E, rc=True, bits=16, limits=None, stf=None, file_no=0, inter
 
 
 # ---- index builders ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("with_n", [False, True], ids=["dna4", "dna5"])
 @pytest.mark.parametrize("seed,nchr,length", [(1, 1, 400), (2, 3, 1500), (3, 5, 77), (4, 2, 20000), (6, 4, 250000)])
-def test_gpu_index_builder_is_bit_identical_to_host_builder(gm, seed, nchr, length):
-    seqs = T.repeat_rich(seed, nchr, length)
+def test_gpu_index_builder_is_bit_identical_to_host_builder(gm, seed, nchr, length, with_n):
+    seqs = T.repeat_rich(seed, nchr, length, with_n=with_n)
+    if with_n:
+        seqs[0][5:45] = 4  # a run of N as in an assembly gap
     host = gm.Index.build_blob(seqs, with_sa=True)
     dev = gm.Index.build_blob(seqs, with_sa=True, on_gpu=True)
     assert host.nbytes == dev.nbytes
@@ -44,18 +47,18 @@ def test_gpu_index_builder_degenerate_texts(gm):
         assert gm.Index.build_blob(seqs, with_sa=True).tobytes() == gm.Index.build_blob(seqs, with_sa=True, on_gpu=True).tobytes()
 
 
-# ---- the reference's golden vectors (Dna4 cases without -ep) ---------------------------------------
-DNA4_CASES = ["1a", "1b", "2a", "2b", "2c", "2d", "2e", "3a", "3b"]
+# ---- the reference's golden vectors (cases without -ep; 1c-1g are Dna5 genomes) ---------------------
+GOLDEN_CASES = ["1a", "1b", "1c", "1d", "1e", "1f", "1g", "2a", "2b", "2c", "2d", "2e", "3a", "3b"]
 
 
-@pytest.mark.parametrize("case", DNA4_CASES)
+@pytest.mark.parametrize("case", GOLDEN_CASES)
 @pytest.mark.parametrize("bits", [16, 8])
 def test_cuda_matches_reference_golden(gm, case, bits):
     cfg = T.CASES[case]
     files, sel, folder = T.load_case(case)
     seqs, stf, _ = T.case_layout(files)
     _, limits = T.concat(seqs)
-    ix = gm.Index.build(seqs, on_gpu=False)
+    ix = gm.Index.build(seqs, on_gpu=bits == 8)
     ext = "freq16" if bits == 16 else "freq8"
     for fi, (base, recs) in enumerate(files):
         iv = T.file_intervals(sel, recs)
@@ -71,7 +74,7 @@ def test_cuda_matches_reference_golden(gm, case, bits):
 import test_ref_fixtures as RF  # noqa: E402
 
 
-@pytest.mark.parametrize("line", [c for c in RF.CASES if not c.startswith("dna5") and "-ep" not in c],
+@pytest.mark.parametrize("line", [c for c in RF.CASES if "-ep" not in c],
                          ids=lambda c: c.split("|")[0])
 def test_cuda_matches_reference_binary_fixtures(gm, line):
     name, K, E, flags, bits, seqs, stf, outs = RF.load_fixture(line)
@@ -94,6 +97,74 @@ def test_cuda_matches_oracle(gm, K, E):
         got = _map(gm, ix, K, E, rc=rc, limits=limits)
         want = orc.map(K, E, revcompl=rc)
         assert np.array_equal(got, want), (K, E, rc, np.nonzero(got != want)[0][:10])
+
+
+@pytest.mark.parametrize("K,E", [(20, 0), (20, 1), (20, 2), (14, 3), (9, 4), (30, 2), (40, 1), (70, 2), (140, 1), (2, 0), (3, 1)])
+def test_cuda_dna5_matches_oracle(gm, K, E):
+    """Genomes with N (Dna5 index, src/indexing.hpp:459-473): N in the text is an ordinary fifth symbol, N in the
+    k-mer never matches (SeqAn's ordValue comparison is on the text side only through the index alphabet)."""
+    seqs = T.repeat_rich(11, 3, 2500, with_n=True)
+    seqs[1][100:160] = 4
+    seqs[2][-5:] = 4
+    _, limits = T.concat(seqs)
+    orc, ix = T.Oracle(seqs), gm.Index.build(seqs)
+    assert ix.info.alphabet_size == 5 and ix.info.rank_block_bytes == 64
+    for rc in (True, False):
+        want = orc.map(K, E, revcompl=rc)
+        for B in (1, 3, 0):
+            for depth in (0, -1):
+                ix.set_jump_depth(depth)
+                p = gm.SearchParams(K, E, rev_compl=rc, block_kmers=B)
+                got = ix.compute_mappability(p, chrom_cum_lengths=limits)
+                assert np.array_equal(got, want), (K, E, rc, B, depth, np.nonzero(got != want)[0][:10])
+
+
+def test_cuda_dna5_exclude_pseudo_bwt_export_and_fetch_counter(gm):
+    base = T.repeat_rich(13, 2, 900, with_n=True)
+    rng = np.random.default_rng(5)
+    ms, stf = [], []
+    for g in range(3):
+        for s in base:
+            s = s.copy()
+            m = (rng.random(len(s)) < 0.03 * g) & (s < 4)
+            s[m] = rng.integers(0, 4, int(m.sum()), dtype=np.uint8)
+            ms.append(s); stf.append(g)
+    stf = np.array(stf, dtype=np.uint32)
+    _, limits = T.concat(ms)
+    mo, ix, hs = T.Oracle(ms, seq_to_file=stf), gm.Index.build(ms, with_sa=True, seq_to_file=stf), T.HostSim(ms)
+    for rev in (False, True):
+        assert np.array_equal(ix.export_bwt(rev), mo.bwt(rev))
+    assert np.array_equal(ix.export_sa(), mo.sa().astype(np.uint32))
+    for f in (0, 2):
+        want = mo.map(22, 2, exclude_pseudo=True, file_no=f)
+        stf_, tb, tl, cum, _ = T._prep(limits, stf, f, None)
+        for B in (1, 4):
+            got = ix.compute_mappability(gm.SearchParams(22, 2, True, True, 16, block_kmers=B), text_begin=tb, text_len=tl,
+                                         chrom_cum_lengths=cum)
+            assert np.array_equal(got, want), (f, B)
+    for K, E in [(20, 0), (20, 2)]:
+        out, st = _map(gm, ix, K, E, limits=limits, count_fetches=True, return_stats=True)
+        want, f = hs.map(K, E, return_fetches=True)
+        assert np.array_equal(out, want) and st.rank_block_fetches == f and st.jump_table_reads == hs.last_lut_reads
+
+
+def test_cuda_dna5_matches_reference_binary_live(gm, tmp_path):
+    if not T.have_reference():
+        pytest.skip("oracle/_ref/genmap_ref not present")
+    seqs = gm.synth_genome(600_000, 3, 123)
+    rng = np.random.default_rng(8)
+    for s in seqs:  # gaps and scattered N
+        a = int(rng.integers(0, len(s) - 5000))
+        s[a:a + 3000] = 4
+        s[rng.integers(0, len(s), 40)] = 4
+    fa = str(tmp_path / "g.fa")
+    T.write_fasta(fa, seqs)
+    ix = gm.Index.build(seqs)
+    assert ix.info.alphabet_size == 5
+    for K, E in [(30, 0), (24, 1), (36, 2)]:
+        ref = T.run_reference(fa, K, E)["g"]
+        got = ix.compute_mappability(gm.SearchParams(K, E))
+        assert np.array_equal(got, ref), (K, E)
 
 
 def test_cuda_jump_table_depths_do_not_change_results(gm):

@@ -176,3 +176,67 @@ def test_blocked_search_saturation_selection_and_exclude_pseudo():
         want = mo.map(25, 2, exclude_pseudo=True, file_no=f)
         for B in (1, 4, 6):
             assert np.array_equal(mh.map(25, 2, seq_to_file=stf, file_no=f, exclude_pseudo=True, block_kmers=B), want), (f, B)
+
+
+# ---- Dna5: genomes containing N (src/algo.hpp:111-112,148-149: a pattern N never matches, a text N costs an error) ----
+def test_dna5_index_builder_matches_oracle():
+    for seed, nchr, length in [(11, 3, 800), (12, 1, 5000)]:
+        seqs = T.repeat_rich(seed, nchr, length, with_n=True)
+        seqs[0][10:40] = 4  # a run of N
+        orc, hs = T.Oracle(seqs), T.HostSim(seqs, with_sa=True)
+        assert orc.sigma == 5
+        for rev in (False, True):
+            assert np.array_equal(orc.bwt(rev), hs.bwt(rev))
+        assert np.array_equal(orc.sa().astype(np.uint32), hs.sa())
+
+
+@pytest.mark.parametrize("case", ["1c", "1d", "1e", "1f", "1g"])
+def test_dna5_matches_reference_golden(case):
+    import os
+    cfg = T.CASES[case]
+    files, sel, folder = T.load_case(case)
+    seqs, stf, _ = T.case_layout(files)
+    hs = T.HostSim(seqs)
+    for bits, ext in ((16, "freq16"), (8, "freq8")):
+        gold = np.fromfile(os.path.join(folder, "raw_" + ext, "genome.genmap." + ext), dtype=np.uint16 if bits == 16 else np.uint8)
+        iv = T.file_intervals(sel, files[0][1])
+        for B in (1, 0):
+            got = hs.map(cfg["K"], cfg["E"], revcompl=cfg["rc"], value_bits=bits, intervals=iv, block_kmers=B)
+            assert np.array_equal(got, gold), (case, bits, B)
+
+
+@pytest.mark.parametrize("K,E", [(20, 0), (20, 1), (20, 2), (14, 3), (9, 4), (30, 2), (40, 1)])
+def test_dna5_matches_oracle(K, E):
+    seqs = T.repeat_rich(11, 3, 2500, with_n=True)
+    seqs[1][100:160] = 4
+    seqs[2][-5:] = 4
+    orc, hs = T.Oracle(seqs), T.HostSim(seqs)
+    for rc in (True, False):
+        want = orc.map(K, E, revcompl=rc)
+        for B in (1, 3, 0):
+            for depth in (0, -1):
+                got = hs.map(K, E, revcompl=rc, block_kmers=B, jump_depth=depth)
+                assert np.array_equal(got, want), (K, E, rc, B, depth, np.nonzero(got != want)[0][:10])
+
+
+def test_dna5_exclude_pseudo_and_reference_fixtures():
+    import test_ref_fixtures as RF
+    for line in [c for c in RF.CASES if c.startswith("dna5")]:
+        name, K, E, flags, bits, seqs, stf, outs = RF.load_fixture(line)
+        hs = T.HostSim(seqs)
+        assert np.array_equal(hs.map(K, E, value_bits=bits), outs[0]), name
+    base = T.repeat_rich(13, 2, 900, with_n=True)
+    rng = np.random.default_rng(5)
+    ms, stf = [], []
+    for g in range(3):
+        for s in base:
+            s = s.copy()
+            m = (rng.random(len(s)) < 0.03 * g) & (s < 4)
+            s[m] = rng.integers(0, 4, int(m.sum()), dtype=np.uint8)
+            ms.append(s); stf.append(g)
+    stf = np.array(stf, dtype=np.uint32)
+    mo, mh = T.Oracle(ms, seq_to_file=stf), T.HostSim(ms, with_sa=True)
+    for f in (0, 2):
+        want = mo.map(22, 2, exclude_pseudo=True, file_no=f)
+        for B in (1, 4):
+            assert np.array_equal(mh.map(22, 2, seq_to_file=stf, file_no=f, exclude_pseudo=True, block_kmers=B), want), (f, B)

@@ -18,11 +18,21 @@ ap.add_argument("--nchr", type=int, default=24)
 ap.add_argument("--seed", type=int, default=45)
 ap.add_argument("--configs", default="0:-1:256,0:0:256,0:13:256,0:14:256,0:16:256,1:-1:64,1:0:64,2:-1:8,2:0:8")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--n-frac", type=float, default=0.0, help="fraction of every chromosome turned into runs of N (-> Dna5 index)")
 args = ap.parse_args()
 
 total = int(args.genome_mbp * 1e6)
 t0 = time.time()
 seqs = gm.synth_genome(total, args.nchr, args.seed)
+if args.n_frac > 0:  # assembly-gap model: one long run per chromosome (centromere) + a few short ones
+    rng = np.random.default_rng(args.seed + 1)
+    for s in seqs:
+        big = int(len(s) * args.n_frac * 0.9)
+        a = int(rng.integers(0, len(s) - big))
+        s[a:a + big] = 4
+        small = max(1, int(len(s) * args.n_frac * 0.1) // 20)
+        for a in rng.integers(0, len(s) - small, 20):
+            s[int(a):int(a) + small] = 4
 ix = gm.Index.build(seqs, on_gpu=True)
 print("genome+index %.1f s, build %s" % (time.time() - t0, ix.build_timings_ms), flush=True)
 n = ix.n_text
@@ -47,5 +57,5 @@ for cfg in args.configs.split(","):
     st = ix.compute_mappability_device(p, out.data_ptr(), pos_begin=b, pos_end=b + batch, stream=stream, count_fetches=True)
     print("E=%d B=%d depth=%2d(%2d) batch=%d  %.2f ms  %.1f Mpos/s  fetch/pos=%.1f lut/pos=%.2f  algGB/s=%.0f  setup=%.2fs free=%.1fGB"
           % (E, blk, depth, st.jump_depth, batch, np.median(ms), npos / np.median(ms) / 1e3, st.rank_block_fetches / st.positions,
-             st.jump_table_reads / st.positions, st.rank_block_fetches * 64 / st.positions * npos / np.median(ms) / 1e6,
+             st.jump_table_reads / st.positions, st.rank_block_fetches * ix.info.rank_block_bytes / st.positions * npos / np.median(ms) / 1e6,
              setup, torch.cuda.mem_get_info()[0] / 1e9), flush=True)
