@@ -390,6 +390,9 @@ struct MapCtx {
     const uint32_t* seq_to_file; // n_seq file ids (mappingSeqIdFile, src/mappability.hpp:230-250)
     uint32_t n_seq, own_file;
     uint64_t all_files;          // mask with one bit per FASTA file
+    // locate instantiation only (csv output, src/algo.hpp:311-343): second pass writes the SA value of every
+    // occurrence; nullptr in the first (counting) pass
+    uint32_t* loc_rows;
 };
 
 struct Node { uint32_t lo_f, lo_r, size; };
@@ -487,6 +490,10 @@ struct Chain {
     uint64_t files;            // B == 1, --exclude-pseudo: FASTA files seen so far (one bit each)
     uint32_t pre_lo_f, pre_lo_r, pre_size; // jump-table entry of (reverse strand, search 0), fetched early
     bool has_n;                // Dna5: the needle contains N (then no occurrence is error-free)
+    // locate instantiation: occurrences found so far per strand (not saturated) and where this k-mer's two
+    // lists start in cx.loc_rows
+    uint32_t occ_fwd, occ_rev;
+    uint64_t loc_at_fwd, loc_at_rev;
 };
 
 // --exclude-pseudo: mark the FASTA file of every occurrence in SA rows [lo, lo+n)
@@ -556,7 +563,7 @@ GMB_HD void chain_start(Chain<KW, SIGMA>& st, const MapCtx& cx, unsigned long lo
 template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
 GMB_HD void chain_begin_block(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, unsigned long long* lut_reads)
 {
-    st.acc = 0; st.s = 0; st.strand = 0; st.files = 0;
+    st.acc = 0; st.s = 0; st.strand = 0; st.files = 0; st.occ_fwd = 0; st.occ_rev = 0;
     if (!BLK) st.cnt = 1;
     st.has_n = st.pat.has_n();
     if (BLK) {
@@ -608,9 +615,20 @@ GMB_HD uint32_t highest_bit_index(uint32_t m)
 }
 
 // add `n` occurrences (or, under --exclude-pseudo, the files of SA rows [lo, lo+n)) to window `w` of the strand
-template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
+template <int KW, bool EP, bool BLK, int SIGMA, class Frames, bool LOC = false>
 GMB_HD void chain_count(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, uint32_t w, uint32_t lo, uint32_t n, bool own_only)
 {
+    if constexpr (LOC) {
+        // csv lists (src/algo.hpp:327-343): the occurrences are SA rows [lo, lo+n) of T; counted per strand in
+        // the first pass, written behind the ones already found in the second
+        const uint32_t have = st.strand ? st.occ_rev : st.occ_fwd;
+        if (cx.loc_rows) {
+            const uint64_t at = (st.strand ? st.loc_at_rev : st.loc_at_fwd) + have;
+            for (uint32_t r = 0; r < n; ++r) cx.loc_rows[at + r] = cx.sa[lo + r];
+        }
+        if (st.strand) st.occ_rev = have + n; else st.occ_fwd = have + n;
+        return;
+    }
     const uint32_t widx = !BLK ? 0u : (st.strand ? st.cnt - 1u - w : w); // reverse-strand windows run backwards (src/algo.hpp:304)
     if (EP) {
         uint64_t m = !BLK ? st.files
@@ -629,10 +647,12 @@ GMB_HD void chain_count(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, uint
 
 // One state-machine iteration.  Returns false when the block is finished (results via chain_result).
 // `fetches` counts rank-block reads (the roofline's algorithmic unit), when non-null.
-template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
+// LOC (locate instantiation, one k-mer per chain, EP tables): every occurrence is reported, not counted.
+template <int KW, bool EP, bool BLK, int SIGMA, class Frames, bool LOC = false>
 GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, unsigned long long* fetches,
                        unsigned long long* lut_reads)
 {
+    static_assert(!LOC || (EP && !BLK), "the locate instantiation keeps both intervals in step and owns one k-mer");
     constexpr uint32_t kNone = 0xffu; // "no symbol": the pattern character is N
     const uint32_t K = cx.K, cnt = BLK ? st.cnt : 1u;
     const uint32_t Li = K - cnt + 1; // infix length
@@ -657,7 +677,7 @@ GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, unsig
 
     if (st.size == 0) {
         // an empty node can only come out of a jump table: nothing to search here
-    } else if (st.strand == 0 && st.e == 0 && st.size == 1 && step_exact_ok(ent) && !(SIGMA == 5 && st.has_n)) {
+    } else if (!LOC && st.strand == 0 && st.e == 0 && st.size == 1 && step_exact_ok(ent) && !(SIGMA == 5 && st.has_n)) {
         // Forward strand, no error so far, one occurrence left: it is the query's own position in the
         // indexed text, so the rest of the pattern matches it exactly and no mismatching extension
         // exists.  The subtree contributes exactly one occurrence per window — no need to walk it.
@@ -713,7 +733,7 @@ GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, unsig
 #pragma unroll
                 for (int k = 0; k < SIGMA; ++k)
                     if (ok & (1u << k))
-                        chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, w, dir ? ch.oth0 + sum_below<SIGMA>(ch.n, (uint32_t)k) : ch.l[k], ch.n[k], false);
+                        chain_count<KW, EP, BLK, SIGMA, Frames, LOC>(st, fr, cx, w, dir ? ch.oth0 + sum_below<SIGMA>(ch.n, (uint32_t)k) : ch.l[k], ch.n[k], false);
             } else {
                 uint64_t sum = 0;
 #pragma unroll
