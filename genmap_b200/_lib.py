@@ -13,7 +13,7 @@ EXPORTS = ["gmb_last_error", "gmb_version", "gmb_device_count", "gmb_index_build
            "gmb_index_build_device", "gmb_blob_save", "gmb_index_open", "gmb_index_from_blob",
            "gmb_index_adopt_device", "gmb_index_close", "gmb_index_get_info", "gmb_map_frequencies",
            "gmb_map_frequencies_range", "gmb_map_frequencies_device", "gmb_index_export_bwt", "gmb_index_export_sa", "gmb_index_set_jump_depth",
-           "gmb_index_import_reference"]
+           "gmb_index_import_reference", "gmb_map_locations", "gmb_locations_free"]
 
 
 class GmbParams(ctypes.Structure):
@@ -31,7 +31,13 @@ class GmbIndexInfo(ctypes.Structure):
 class GmbMapStats(ctypes.Structure):
     _fields_ = [("kernel_ms", ctypes.c_double), ("positions", ctypes.c_uint64),
                 ("rank_block_fetches", ctypes.c_uint64), ("jump_table_reads", ctypes.c_uint64),
-                ("kernel_launches", ctypes.c_uint32), ("jump_depth", ctypes.c_uint32)]
+                ("kernel_launches", ctypes.c_uint32), ("jump_depth", ctypes.c_uint32),
+                ("fetches_by_size", ctypes.c_uint64 * 8), ("thin_paths", ctypes.c_uint64)]
+
+
+class GmbLocations(ctypes.Structure):
+    _fields_ = [("pos_begin", ctypes.c_uint64), ("pos_end", ctypes.c_uint64), ("n_locations", ctypes.c_uint64),
+                ("offsets", ctypes.POINTER(ctypes.c_uint64)), ("loc", ctypes.c_void_p), ("kernel_ms", ctypes.c_double)]
 
 
 class GenmapError(RuntimeError):
@@ -90,6 +96,10 @@ def lib():
     L.gmb_map_frequencies_device.restype = ci
     L.gmb_map_frequencies_device.argtypes = [vp, ctypes.POINTER(GmbParams), u64, u64, vp, u32, vp, u64, vp, u32,
                                              u64, u64, vp, vp, ctypes.POINTER(GmbMapStats)]
+    L.gmb_map_locations.restype = ci
+    L.gmb_map_locations.argtypes = [vp, ctypes.POINTER(GmbParams), u64, u64, vp, u32, vp, u64, u64, u64, u64,
+                                    ctypes.POINTER(GmbLocations)]
+    L.gmb_locations_free.argtypes = [ctypes.POINTER(GmbLocations)]
     _lib = L
     return L
 

@@ -13,7 +13,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import GenmapError, GmbIndexInfo, GmbMapStats, GmbParams, check
+from ._lib import GenmapError, GmbIndexInfo, GmbLocations, GmbMapStats, GmbParams, check
 
 
 def _ptr(a):
@@ -166,6 +166,30 @@ class Index:
             _ptr(self.seq_to_file), 0 if self.seq_to_file is None else len(self.seq_to_file), int(pos_begin),
             int(pos_end), _ptr(out), ctypes.byref(st)))
         return (out, st) if return_stats else out
+
+    def compute_locations(self, params, pos_begin=0, pos_end=None, text_begin=0, text_len=None, chrom_cum_lengths=None,
+                          intervals=None, max_locations=0):
+        """The csvComputation branch (src/algo.hpp:311-346) for the file-local positions [pos_begin, pos_end):
+        -> (offsets uint64[2n+1], loc uint32[m, 2]) with list (j, strand) = loc[offsets[2(j-pos_begin)+strand] :
+        offsets[2(j-pos_begin)+strand+1]], rows = (sequence number, offset), sorted; strand 0 = +, 1 = -."""
+        tb, tl, cum, iv = self._file_args(text_begin, text_len, chrom_cum_lengths, intervals)
+        pos_end = tl if pos_end is None else int(pos_end)
+        p = GmbParams(params.length, params.errors, int(params.rev_compl), 0, 16, 0, 1)
+        offs, locs, b = [], [], int(pos_begin)
+        while b < pos_end:
+            r = GmbLocations()
+            check(_lib.lib().gmb_map_locations(self._h, ctypes.byref(p), tb, tl, _ptr(cum), len(cum) - 1, _ptr(iv),
+                                               0 if iv is None else len(iv), b, pos_end, int(max_locations), ctypes.byref(r)))
+            n = int(r.pos_end - r.pos_begin)
+            o = np.ctypeslib.as_array(r.offsets, shape=(2 * n + 1,)).copy()
+            l = (np.frombuffer(ctypes.string_at(r.loc, 8 * int(r.n_locations)), dtype=np.uint32).reshape(-1, 2).copy()
+                 if r.n_locations else np.zeros((0, 2), np.uint32))
+            base = offs[-1][-1] if offs else np.uint64(0)
+            offs.append(o[(1 if offs else 0):] + base)
+            locs.append(l)
+            b = int(r.pos_end)
+            _lib.lib().gmb_locations_free(ctypes.byref(r))
+        return np.concatenate(offs), np.concatenate(locs)
 
     def set_jump_depth(self, depth):
         """-1 = automatic, 0 = no jump tables, 1..16 = maximum table depth (see gmb_index_set_jump_depth)."""

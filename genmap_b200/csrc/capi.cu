@@ -16,6 +16,7 @@
 #include "gmb_host.h"
 #include "index_build_gpu.cuh"
 #include "jump_table.cuh"
+#include "locate.cuh"
 #include "map_kernel.cuh"
 
 using namespace gmb;
@@ -78,7 +79,7 @@ struct gmb_index {
     IndexHeader h{};
     std::vector<uint64_t> limits; // host copy
     // per-handle scratch, grown on demand
-    unsigned long long* d_counters = nullptr; // [0] work counter, [1] fetch counter
+    unsigned long long* d_counters = nullptr; // [0] work counter, [1..11] fetch counters (map_kernel.cuh)
     uint32_t* d_steps = nullptr; // search tables of the current call (kTableBytes)
     uint64_t* d_ranges = nullptr;
     size_t ranges_cap = 0;
@@ -115,6 +116,7 @@ void fill_ctx(const gmb_index* ix, MapCtx& cx)
     cx.seq_start = reinterpret_cast<const uint32_t*>(base + ix->h.off_seq_start);
     cx.seq_to_file = nullptr;
     cx.n_seq = ix->h.n_seq; cx.own_file = 0; cx.all_files = 0;
+    cx.loc_rows = nullptr;
 }
 
 // make sure the tables of every depth in `plan` exist on the device (built level by level, cached)
@@ -215,7 +217,7 @@ static int finish_open(gmb_index* ix, gmb_index** out)
     ix->sm_count = prop.multiProcessorCount;
     ix->limits.resize((size_t)ix->h.n_seq + 1);
     CU(cudaMemcpy(ix->limits.data(), ix->d_blob + ix->h.off_limits, ix->limits.size() * 8, cudaMemcpyDeviceToHost));
-    CU(cudaMalloc(&ix->d_counters, 4 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&ix->d_counters, 16 * sizeof(unsigned long long)));
     CU(cudaMalloc(&ix->d_steps, kTableBytes));
     CU(cudaEventCreate(&ix->ev0));
     CU(cudaEventCreate(&ix->ev1));
@@ -390,13 +392,28 @@ int gmb_index_set_jump_depth(gmb_index* ix, int depth)
 
 // stats != nullptr && timed: bracket the kernel with events and wait for it; stats != nullptr && !timed: only
 // fill the host-side fields (positions, jump depth) and return without synchronising
-static int map_device_impl(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len,
+// One pass of the locate path (gmb_map_locations): counting (rows == nullptr: out_device receives two uint32 list
+// lengths per position of [pos0, ...)) or filling (rows / off set).
+struct LocPass {
+    const uint64_t* off;
+    uint32_t* rows;
+    uint64_t pos0;
+};
+
+static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_begin, uint64_t text_len,
                            const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t (*intervals)[2],
                            uint64_t n_intervals, const uint32_t* seq_to_file, uint32_t n_seq,
                            uint64_t pos_begin, uint64_t pos_end, void* out_device, void* cuda_stream,
-                           gmb_map_stats* stats, bool timed)
+                           gmb_map_stats* stats, bool timed, const LocPass* loc = nullptr)
 {
-    if (!ix || !p || !chrom_cum || !out_device) return fail(GMB_ERR_ARG, "gmb_map_frequencies: NULL argument");
+    if (!ix || !p_in || !chrom_cum || !out_device) return fail(GMB_ERR_ARG, "gmb_map_frequencies: NULL argument");
+    gmb_params params = *p_in;
+    if (loc) { // one k-mer per chain on tables that keep both intervals in step; no file reduction, no counters
+        params.exclude_pseudo = 0; params.count_fetches = 0; params.block_kmers = 1; params.value_bits = 16;
+        if (!ix->h.off_sa) return fail(GMB_ERR_UNSUPPORTED, "locations (csv output) need an index built with the full suffix array (GMB_BUILD_WITH_SA)");
+    }
+    const gmb_params* p = &params;
+    const bool sync_tables = p->exclude_pseudo != 0 || loc != nullptr;
     if (p->value_bits != 8 && p->value_bits != 16) return fail(GMB_ERR_ARG, "value_bits must be 8 or 16");
     if (text_begin + text_len > ix->h.n_text) return fail(GMB_ERR_ARG, "text range exceeds the indexed text");
     if (n_chrom == 0 || chrom_cum[0] != 0 || chrom_cum[n_chrom] != text_len) return fail(GMB_ERR_ARG, "chrom_cum_lengths must start at 0 and end at text_len");
@@ -417,11 +434,11 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p, uint64_t text_beg
     {
         uint32_t want_b = p->block_kmers;
         if (want_b == 0) { const char* env = std::getenv("GMB_BLOCK_KMERS"); if (env && *env) want_b = (uint32_t)std::atoi(env); }
-        if (!build_block_tables(p->K, p->E, want_b, p->exclude_pseudo != 0, tabs, err)) return fail(GMB_ERR_UNSUPPORTED, err);
+        if (!build_block_tables(p->K, p->E, want_b, sync_tables, tabs, err)) return fail(GMB_ERR_UNSUPPORTED, err);
         // the tables and the per-chain frame store live in shared memory: shrink the block if they do not fit
-        while (tabs.B > 1 && (map_kernel_smem_bytes((uint32_t)tabs.steps.size(), p->E, tabs.B, p->exclude_pseudo != 0, ix->h.sigma) > (200u << 10) ||
+        while (tabs.B > 1 && (map_kernel_smem_bytes((uint32_t)tabs.steps.size(), p->E, tabs.B, sync_tables, ix->h.sigma, true) > (200u << 10) ||
                               tabs.steps.size() * 4 + (tabs.B + 1) * kMaxSearches * sizeof(SearchStart) > kTableBytes))
-            if (!build_block_tables(p->K, p->E, tabs.B - 1, p->exclude_pseudo != 0, tabs, err)) return fail(GMB_ERR_UNSUPPORTED, err);
+            if (!build_block_tables(p->K, p->E, tabs.B - 1, sync_tables, tabs, err)) return fail(GMB_ERR_UNSUPPORTED, err);
     }
     CU(cudaSetDevice(ix->device));
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
@@ -451,7 +468,7 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p, uint64_t text_beg
         CU(cudaMalloc(&ix->d_ranges, ix->ranges_cap * 8));
     }
     CU(cudaMemcpyAsync(ix->d_ranges, host_ranges.data(), host_ranges.size() * 8, cudaMemcpyHostToDevice, stream));
-    CU(cudaMemsetAsync(ix->d_counters, 0, 3 * sizeof(unsigned long long), stream));
+    CU(cudaMemsetAsync(ix->d_counters, 0, 16 * sizeof(unsigned long long), stream));
 
     MapLaunch L;
     const uint8_t* base = ix->d_blob;
@@ -530,9 +547,13 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p, uint64_t text_beg
         L.cx.all_files = n_files == 64 ? ~0ull : ((1ull << n_files) - 1ull);
     }
 
+    L.cx.loc_rows = loc ? loc->rows : nullptr;
+    L.loc_off = loc ? loc->off : nullptr;
+    L.loc_pos0 = loc ? loc->pos0 : 0;
+
     if (stats) { stats->jump_depth = plan_depth; stats->kernel_launches = 1; }
     if (stats && timed) CU(cudaEventRecord(ix->ev0, stream));
-    CU(launch_map_kernel(L, ix->sm_count, stream));
+    CU(loc ? launch_locate_kernel(L, ix->sm_count, stream) : launch_map_kernel(L, ix->sm_count, stream));
     if (stats && timed) {
         CU(cudaEventRecord(ix->ev1, stream));
         CU(cudaEventSynchronize(ix->ev1));
@@ -542,10 +563,12 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p, uint64_t text_beg
         stats->kernel_launches = 1;
         stats->jump_depth = plan_depth;
         if (L.count_fetches) {
-            unsigned long long f[2] = {0, 0};
+            unsigned long long f[11] = {};
             CU(cudaMemcpy(f, ix->d_counters + 1, sizeof(f), cudaMemcpyDeviceToHost));
             stats->rank_block_fetches = f[0];
             stats->jump_table_reads = f[1];
+            for (int k = 0; k < 8; ++k) stats->fetches_by_size[k] = f[2 + k];
+            stats->thin_paths = f[10];
         }
     }
     return GMB_OK;
@@ -637,6 +660,108 @@ int gmb_map_frequencies(gmb_index* ix, const gmb_params* p, uint64_t text_begin,
 {
     return gmb_map_frequencies_range(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals,
                                      seq_to_file, n_seq, 0, text_len, out, stats);
+}
+
+} // extern "C"
+
+/* ---- locations (csv output) ------------------------------------------------------------------------------- */
+namespace {
+struct DevBuf { // frees on scope exit
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+} // namespace
+
+extern "C" {
+
+void gmb_locations_free(gmb_locations* L)
+{
+    if (!L) return;
+    std::free(L->offsets);
+    std::free(L->loc);
+    L->offsets = nullptr; L->loc = nullptr; L->n_locations = 0;
+}
+
+int gmb_map_locations(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len,
+                      const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t (*intervals)[2],
+                      uint64_t n_intervals, uint64_t pos_begin, uint64_t pos_end, uint64_t max_locations,
+                      gmb_locations* out)
+{
+    if (!ix || !p || !out || !chrom_cum) return fail(GMB_ERR_ARG, "gmb_map_locations: NULL argument");
+    std::memset(out, 0, sizeof(*out));
+    if (pos_end > text_len) pos_end = text_len;
+    if (pos_begin >= pos_end) return fail(GMB_ERR_ARG, "gmb_map_locations: empty position range");
+    const uint64_t kMaxPositions = 4ull << 20, kMaxRows = 1ull << 30;
+    if (pos_end - pos_begin > kMaxPositions) pos_end = pos_begin + kMaxPositions;
+    if (max_locations == 0) max_locations = 64ull << 20;
+    if (max_locations > kMaxRows) max_locations = kMaxRows;
+    CU(cudaSetDevice(ix->device));
+    const uint64_t npos = pos_end - pos_begin, n_lists = 2 * npos;
+
+    // pass 1: list lengths, then their prefix sums
+    DevBuf counts, offs, temp;
+    CU(counts.alloc((n_lists + 1) * 4));
+    CU(offs.alloc((n_lists + 1) * 8));
+    CU(cudaMemsetAsync(counts.p, 0, (n_lists + 1) * 4, nullptr));
+    gmb_map_stats st1, st2;
+    std::memset(&st2, 0, sizeof(st2));
+    LocPass pass1{nullptr, nullptr, pos_begin};
+    int rc = map_device_impl(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, nullptr, 0, pos_begin,
+                             pos_end, counts.p, nullptr, &st1, true, &pass1);
+    if (rc != GMB_OK) return rc;
+    size_t temp_bytes = 0;
+    CU(locate_scan_counts(counts.as<uint32_t>(), n_lists, offs.as<uint64_t>(), nullptr, temp_bytes, nullptr));
+    CU(temp.alloc(temp_bytes));
+    CU(locate_scan_counts(counts.as<uint32_t>(), n_lists, offs.as<uint64_t>(), temp.p, temp_bytes, nullptr));
+    uint64_t* h_off = static_cast<uint64_t*>(std::malloc((n_lists + 1) * 8));
+    if (!h_off) return fail(GMB_ERR_NOMEM, "out of host memory");
+    cudaError_t e = cudaMemcpy(h_off, offs.p, (n_lists + 1) * 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { std::free(h_off); return cuda_fail(e, "cudaMemcpy(list offsets)"); }
+
+    // keep as many whole positions as fit into max_locations (always at least one)
+    uint64_t m = npos;
+    if (h_off[n_lists] > max_locations) {
+        uint64_t lo = 1, hi = npos; // largest m with h_off[2m] <= max_locations, at least 1
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi + 1) / 2;
+            if (h_off[2 * mid] <= max_locations) lo = mid; else hi = mid - 1;
+        }
+        m = lo;
+    }
+    const uint64_t n_rows = h_off[2 * m];
+    if (n_rows > (1ull << 31)) { std::free(h_off); return fail(GMB_ERR_UNSUPPORTED, "a single k-mer has more than 2^31 occurrences"); }
+    gmb_location* h_loc = static_cast<gmb_location*>(std::malloc(n_rows ? n_rows * sizeof(gmb_location) : 1));
+    if (!h_loc) { std::free(h_off); return fail(GMB_ERR_NOMEM, "out of host memory"); }
+    auto bail = [&](int code) { std::free(h_off); std::free(h_loc); return code; };
+
+    if (n_rows) {
+        // pass 2: the same search writes the SA value of every occurrence; sort every list; positions -> (seq, offset)
+        DevBuf rows, sorted, loc, temp2;
+        if ((e = rows.alloc(n_rows * 4)) != cudaSuccess || (e = sorted.alloc(n_rows * 4)) != cudaSuccess ||
+            (e = loc.alloc(n_rows * sizeof(gmb_location))) != cudaSuccess)
+            return bail(cuda_fail(e, "cudaMalloc(locations)"));
+        LocPass pass2{offs.as<uint64_t>(), rows.as<uint32_t>(), pos_begin};
+        rc = map_device_impl(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, nullptr, 0, pos_begin,
+                             pos_begin + m, counts.p, nullptr, &st2, true, &pass2);
+        if (rc != GMB_OK) return bail(rc);
+        size_t tb = 0;
+        if ((e = locate_sort_lists(rows.as<uint32_t>(), sorted.as<uint32_t>(), n_rows, offs.as<uint64_t>(), 2 * m, nullptr, tb, nullptr)) != cudaSuccess ||
+            (e = temp2.alloc(tb)) != cudaSuccess ||
+            (e = locate_sort_lists(rows.as<uint32_t>(), sorted.as<uint32_t>(), n_rows, offs.as<uint64_t>(), 2 * m, temp2.p, tb, nullptr)) != cudaSuccess ||
+            (e = locate_convert(sorted.as<uint32_t>(), n_rows, reinterpret_cast<const uint32_t*>(ix->d_blob + ix->h.off_seq_start),
+                                ix->h.n_seq, loc.p, nullptr)) != cudaSuccess ||
+            (e = cudaMemcpy(h_loc, loc.p, n_rows * sizeof(gmb_location), cudaMemcpyDeviceToHost)) != cudaSuccess)
+            return bail(cuda_fail(e, "locations"));
+    }
+    out->pos_begin = pos_begin;
+    out->pos_end = pos_begin + m;
+    out->n_locations = n_rows;
+    out->offsets = h_off;
+    out->loc = h_loc;
+    out->kernel_ms = st1.kernel_ms + st2.kernel_ms;
+    return GMB_OK;
 }
 
 int gmb_index_export_sa(gmb_index* ix, uint32_t* out_host)

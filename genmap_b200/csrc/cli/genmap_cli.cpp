@@ -323,6 +323,61 @@ bool load_ids(const std::string& path, std::vector<IdRow>& rows)
     return !rows.empty();
 }
 
+// ---- csv (src/output.hpp:189-288) ----------------------------------------------------------------------
+// One line per k-mer that has at least one occurrence and whose window stays inside its sequence
+// (src/algo.hpp:377-385): "seq,pos" of the k-mer, then per indexed FASTA file the "|"-separated occurrences
+// on the + strand, then (unless -nc) the same for the - strand; sequence numbers are local to each file.
+// The lists come from gmb_map_locations piece by piece, so memory stays bounded however long the file is
+// (the reference keeps a std::map of all k-mers of the file, src/mappability.hpp:168-170).
+struct CsvFile { std::string name; uint32_t last_seq; };
+
+bool write_csv(gmb_index* ix, const gmb_params& p, uint64_t text_begin, uint64_t text_len, const std::vector<uint64_t>& cum,
+               const std::vector<std::pair<uint64_t, uint64_t>>& iv, const std::vector<CsvFile>& files, const std::string& path)
+{
+    gmbcli::Sink out(path);
+    if (!out.ok()) { std::cerr << "ERROR: cannot write " << path << "\n"; return false; }
+    out.str("\"k-mer\"");
+    for (const CsvFile& f : files) out.str(";\"+ strand " + f.name + "\"");
+    if (p.revcompl)
+        for (const CsvFile& f : files) out.str(";\"- strand " + f.name + "\"");
+    out.ch('\n');
+    size_t chrom = 0;
+    for (uint64_t b = 0; b < text_len;) {
+        gmb_locations L;
+        if (gmb_map_locations(ix, &p, text_begin, text_len, cum.data(), (uint32_t)cum.size() - 1,
+                              reinterpret_cast<const uint64_t (*)[2]>(iv.data()), iv.size(), b, text_len, 0, &L) != GMB_OK) {
+            std::cerr << "ERROR: " << gmb_last_error() << "\n";
+            return false;
+        }
+        for (uint64_t j = L.pos_begin; j < L.pos_end; ++j) {
+            const uint64_t* o = L.offsets + 2 * (j - L.pos_begin);
+            if (o[2] == o[0]) continue; // no hit on either strand (k-mers with N; positions that were not searched)
+            while (cum[chrom + 1] <= j) ++chrom;
+            out.u64(chrom); out.ch(','); out.u64(j - cum[chrom]);
+            for (int strand = 0; strand < (p.revcompl ? 2 : 1); ++strand) {
+                uint64_t i = o[strand];
+                const uint64_t end = o[strand + 1];
+                uint32_t before = 0; // sequences in the previous FASTA files
+                for (const CsvFile& f : files) {
+                    out.ch(';');
+                    bool first = true;
+                    while (i < end && L.loc[i].seq <= f.last_seq) {
+                        if (!first) out.ch('|');
+                        out.u64(L.loc[i].seq - before); out.ch(','); out.u64(L.loc[i].pos);
+                        first = false;
+                        ++i;
+                    }
+                    before = f.last_seq + 1;
+                }
+            }
+            out.ch('\n');
+        }
+        b = L.pos_end;
+        gmb_locations_free(&L);
+    }
+    return true;
+}
+
 int map_main(int argc, char const** argv)
 {
     std::vector<OptSpec> specs = {{"I", "index", true}, {"O", "output", true}, {"E", "errors", true}, {"K", "length", true},
@@ -365,7 +420,6 @@ int map_main(int argc, char const** argv)
     }
     if (E > 4) { std::cerr << "E > 4 not yet supported.\n"; return 1; } // src/mappability.hpp:187
     if (K < E + 2) { std::cerr << "ERROR: K must be at least E + 2.\n"; return 1; }
-    if (csv) { std::cerr << "ERROR: --csv output is not supported by the B200 build yet.\n"; return 1; }
 
     std::string index_dir = a.val["index"];
     if (index_dir.back() != '/') index_dir += '/';
@@ -441,6 +495,11 @@ int map_main(int argc, char const** argv)
         seq_to_file[i] = total_files;
     }
     ++total_files;
+    std::vector<CsvFile> csv_files; // every indexed FASTA file with its last sequence number (src/output.hpp:200-213)
+    for (size_t i = 0; i < rows.size(); ++i)
+        if (i + 1 == rows.size() || rows[i + 1].file != rows[i].file) csv_files.push_back(CsvFile{rows[i].file, (uint32_t)i});
+    if (csv && !iinfo.has_sa) { std::cerr << "ERROR: --csv needs an index that stores the suffix array (built without --no-sa).\n"; return 1; }
+    const bool want_freq = raw || txt || wig || bg || bed;
 
     gmb_params p{};
     p.K = (uint32_t)K; p.E = (uint32_t)E;
@@ -477,12 +536,12 @@ int map_main(int argc, char const** argv)
         }
         const uint64_t text_len = cum.back();
         if (!(has_selection && iv.empty())) { // :309 — files without selected intervals produce no output
-            std::vector<uint8_t> c(text_len * (p.value_bits / 8));
+            std::vector<uint8_t> c(want_freq ? text_len * (p.value_bits / 8) : 0);
             static_assert(sizeof(std::pair<uint64_t, uint64_t>) == 16, "interval layout");
             // positions are range-partitioned over the GPUs; every GPU fills its own slice of c
             std::vector<std::string> errors(gpu);
             std::vector<std::thread> workers;
-            for (uint64_t g = 0; g < gpu; ++g)
+            for (uint64_t g = 0; want_freq && g < gpu; ++g)
                 workers.emplace_back([&, g] {
                     const uint64_t b = text_len * g / gpu, e = text_len * (g + 1) / gpu;
                     if (gmb_map_frequencies_range(ixs[g], &p, start_pos, text_len, cum.data(), (uint32_t)lens.size(),
@@ -501,8 +560,14 @@ int map_main(int argc, char const** argv)
             std::string prefix = out_path;
             if (!includes_filename) prefix += rows[i].file.substr(0, rows[i].file.find_last_of('.')) + ".genmap"; // :76-78
             gmbcli::Outputs o{raw, txt, wig, bg, bed, a.has("verbose")};
-            if (p.value_bits == 8) gmbcli::write_outputs(c.data(), text_len, prefix, names, lens, otype, o);
+            if (!want_freq) {}
+            else if (p.value_bits == 8) gmbcli::write_outputs(c.data(), text_len, prefix, names, lens, otype, o);
             else gmbcli::write_outputs(reinterpret_cast<const uint16_t*>(c.data()), text_len, prefix, names, lens, otype, o);
+            if (csv) {
+                const double t_csv = wall();
+                if (!write_csv(ixs[0], p, start_pos, text_len, cum, iv, csv_files, prefix + ".csv")) return 1;
+                if (a.has("verbose")) std::cout << "- CSV file written in " << round2(wall() - t_csv) << " seconds\n";
+            }
         }
         start_pos += text_len;
         i = j;

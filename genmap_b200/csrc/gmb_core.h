@@ -397,6 +397,30 @@ struct MapCtx {
 
 struct Node { uint32_t lo_f, lo_r, size; };
 
+// Counters of the instrumented (count_fetches) instantiation: rank-block fetches in total and by the size of
+// the interval being expanded (1, 2, 3-4, 5-8, 9-16, 17-32, 33-64, 65+), and the number of "thin paths"
+// (maximal runs of expansions of one-row intervals: what a locate + text comparison could replace).
+struct FetchStats {
+    unsigned long long total;
+    unsigned long long by_size[8];
+    unsigned long long thin_paths;
+};
+constexpr int kFetchStatWords = 10;
+GMB_HD uint32_t size_bucket(uint32_t n)
+{
+    if (n <= 1u) return 0u;
+#if defined(__CUDA_ARCH__)
+    const uint32_t b = 32u - (uint32_t)__clz((int)(n - 1u));
+#else
+    const uint32_t b = 32u - (uint32_t)__builtin_clz(n - 1u);
+#endif
+    return b < 7u ? b : 7u;
+}
+GMB_HD void count_fetch(FetchStats* f, uint32_t size, uint32_t n)
+{
+    if (f) { f->total += n; f->by_size[size_bucket(size)] += n; }
+}
+
 // Children of a node in one direction: for every symbol c of the alphabet the size n[c] of the child
 // interval and its start l[c] in the ACTIVE index; oth0 = start of child 0 in the OTHER index (child c
 // starts at oth0 + n[0] + ... + n[c-1]: `smaller` of index_fm_stree.h:256-278 with the sentinels first).
@@ -406,7 +430,7 @@ struct Children { uint32_t n[SIGMA], l[SIGMA], oth0; };
 // Both rank blocks of the node are requested before either is used (one memory latency per expansion).
 // `dir` selects the index: 1 = BWT of T' (extend right), 0 = BWT of T (extend left).
 template <int SIGMA>
-GMB_HD Children<SIGMA> expand_node(const MapCtx& cx, uint32_t dir, uint32_t x, uint32_t size, uint32_t z, unsigned long long* fetches)
+GMB_HD Children<SIGMA> expand_node(const MapCtx& cx, uint32_t dir, uint32_t x, uint32_t size, uint32_t z, FetchStats* fetches)
 {
     Children<SIGMA> ch;
     const uint32_t y = x + size;
@@ -414,7 +438,7 @@ GMB_HD Children<SIGMA> expand_node(const MapCtx& cx, uint32_t dir, uint32_t x, u
     if constexpr (SIGMA == 4) {
         const RankBlock* B = static_cast<const RankBlock*>(dir ? cx.blk[1] : cx.blk[0]);
         const uint32_t bx = x / kBlockBases, by = y / kBlockBases;
-        if (fetches) *fetches += 1u + (by != bx);
+        count_fetch(fetches, size, 1u + (by != bx));
         const BlockRegs rbx = load_block(B + bx);
         BlockRegs rby = rbx;
         load_block_if(rby, B + by, by != bx);
@@ -426,7 +450,7 @@ GMB_HD Children<SIGMA> expand_node(const MapCtx& cx, uint32_t dir, uint32_t x, u
     } else {
         const RankBlock5* B = static_cast<const RankBlock5*>(dir ? cx.blk[1] : cx.blk[0]);
         const uint32_t bx = x / kBlockBases5, by = y / kBlockBases5;
-        if (fetches) *fetches += 1u + (by != bx);
+        count_fetch(fetches, size, 1u + (by != bx));
         const BlockRegs5 rbx = load_block5(B + bx);
         const BlockRegs5 rby = by != bx ? load_block5(B + by) : rbx;
         const Ranks5 R0 = block_rank5(rbx, x - bx * kBlockBases5, x, SP);
@@ -494,6 +518,7 @@ struct Chain {
     // lists start in cx.loc_rows
     uint32_t occ_fwd, occ_rev;
     uint64_t loc_at_fwd, loc_at_rev;
+    bool thin;                 // instrumented instantiation: the previous expansion was of a one-row interval
 };
 
 // --exclude-pseudo: mark the FASTA file of every occurrence in SA rows [lo, lo+n)
@@ -547,7 +572,7 @@ template <int KW, bool BLK, int SIGMA>
 GMB_HD void chain_start(Chain<KW, SIGMA>& st, const MapCtx& cx, unsigned long long* lut_reads)
 {
     const SearchStart S = cx.starts[(BLK ? st.cnt : 1u) * kMaxSearches + st.s];
-    st.e = 0; st.lvmask = 0; st.win = kNoWin; st.leaf_e = 0;
+    st.e = 0; st.lvmask = 0; st.win = kNoWin; st.leaf_e = 0; st.thin = false;
     if (S.uni == nullptr) {
         st.lo_f = 0; st.lo_r = 0; st.size = cx.n_bwt; st.t = 0;
     } else {
@@ -649,7 +674,7 @@ GMB_HD void chain_count(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, uint
 // `fetches` counts rank-block reads (the roofline's algorithmic unit), when non-null.
 // LOC (locate instantiation, one k-mer per chain, EP tables): every occurrence is reported, not counted.
 template <int KW, bool EP, bool BLK, int SIGMA, class Frames, bool LOC = false>
-GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, unsigned long long* fetches,
+GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, FetchStats* fetches,
                        unsigned long long* lut_reads)
 {
     static_assert(!LOC || (EP && !BLK), "the locate instantiation keeps both intervals in step and owns one k-mer");
@@ -685,6 +710,10 @@ GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, unsig
         else for (uint32_t w = 0; w < cnt; ++w) chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, w, 0, 1, true);
     } else {
         // ---- expand the node: ranks at both interval ends of the active index -----------------------
+        if (fetches) { // a run of one-row expansions starts here unless the parent was one already
+            if (st.size == 1 && !st.thin) ++fetches->thin_paths;
+            st.thin = st.size == 1;
+        }
         const uint32_t x = dir ? st.lo_r : st.lo_f;
         const uint32_t z = dir ? st.lo_f : st.lo_r;
 
@@ -705,7 +734,7 @@ GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, unsig
                 const RankBlock* B = static_cast<const RankBlock*>(dir ? cx.blk[1] : cx.blk[0]);
                 const uint32_t* SP = dir ? cx.sent[1] : cx.sent[0];
                 const uint32_t bx = x / kBlockBases, by = y / kBlockBases;
-                if (fetches) *fetches += 1u + (by != bx);
+                count_fetch(fetches, st.size, 1u + (by != bx));
                 const BlockRegs rbx = load_block(B + bx);
                 BlockRegs rby = rbx;
                 load_block_if(rby, B + by, by != bx);
@@ -763,6 +792,7 @@ GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, unsig
 
     if (!descend) {
         // ---- backtrack ---------------------------------------------------------------------------------
+        st.thin = false;
         // While an infix hit is being completed, the frames of its window walks sit at levels >= leaf_e and
         // the infix search's own pending frames below that.
         uint32_t cand = st.lvmask;

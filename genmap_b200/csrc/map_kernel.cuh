@@ -26,19 +26,28 @@ struct MapLaunch {
     uint64_t n_chunks;
     uint64_t n_work;           // total k-mer starts to search (sizing only)
     unsigned long long* work_counter;  // device, zeroed before launch: next chunk id
-    unsigned long long* fetch_counter; // device: [0] rank-block fetches, [1] jump-table reads (count_fetches)
+    unsigned long long* fetch_counter; // device, 11 words (count_fetches): [0] rank-block fetches, [1] jump-table reads,
+                                       // [2..9] fetches by interval size, [10] thin paths
     void* out;                 // device, value_bits/8 bytes per file-local position
     uint32_t value_bits;
     bool count_fetches;
     bool exclude_pseudo;       // cx.sa / seq_start / seq_to_file / all_files are set
+    // locate instantiation (launch_locate_kernel): `out` holds two uint32 list lengths per position of
+    // [loc_pos0, ...) in the counting pass; the fill pass (cx.loc_rows != nullptr) reads the list starts from loc_off
+    const uint64_t* loc_off;
+    uint64_t loc_pos0;
 };
 
 constexpr unsigned kChunk = 128; // positions handed out per global atomic (rounded down to a multiple of B)
 
 // dynamic shared memory the kernel needs for these tables (the host shrinks B if this exceeds the SM's limit)
-size_t map_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool ep, uint32_t sigma);
+// (`blocked`: the instantiation that keeps per-window counters in the frame store: B > 1 or a Dna5 index)
+size_t map_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool ep, uint32_t sigma, bool blocked);
 
 // Enqueue the kernel on `stream`.  Returns cudaSuccess or the launch error.
 cudaError_t launch_map_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream);
+
+// Locate variant (locate_kernel.cu): one k-mer per chain, every occurrence reported (csv output).
+cudaError_t launch_locate_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream);
 
 } // namespace gmb

@@ -77,6 +77,10 @@ typedef struct gmb_map_stats {
     uint64_t jump_table_reads;   /* only with count_fetches: jump-table entries read (8 or 12 bytes each) */
     uint32_t kernel_launches;
     uint32_t jump_depth;         /* deepest jump table used by this call (0 = none) */
+    /* only with count_fetches: the fetches split by the size of the suffix-array interval being expanded
+     * (1, 2, 3-4, 5-8, 9-16, 17-32, 33-64, 65+) and the number of maximal runs of one-row expansions */
+    uint64_t fetches_by_size[8];
+    uint64_t thin_paths;
 } gmb_map_stats;
 
 /* flags for gmb_index_build */
@@ -147,6 +151,38 @@ int gmb_map_frequencies_device(gmb_index *idx, const gmb_params *params, uint64_
                                const uint64_t (*intervals)[2], uint64_t n_intervals,
                                const uint32_t *seq_to_file, uint32_t n_seq, uint64_t pos_begin,
                                uint64_t pos_end, void *out_device, void *cuda_stream, gmb_map_stats *stats);
+
+/* ---- locations: what the csv output needs (the csvComputation branch of computeMappabilitySingleBlock,
+ * src/algo.hpp:311-343, and the `locations` map it fills; consumed by saveCsv, src/output.hpp:189-288) ----
+ * For every file-local position j of [pos_begin, pos_end') the sorted list of all occurrences (<= E mismatches)
+ * of the k-mer at j on the + strand and, unless revcompl == 0, of its reverse complement (the "- strand" column):
+ *     list (j, s) = loc[offsets[2*(j-pos_begin)+s] .. offsets[2*(j-pos_begin)+s+1])      s = 0 (+), 1 (-)
+ * Each occurrence is the reference's Pair<TSeqNo,TSeqPos> (src/common.hpp:59-63): sequence number over the whole
+ * index and offset inside that sequence; lists are sorted by (seq, pos) like src/algo.hpp:335,346.  Lists are NOT
+ * saturated.  Positions that are not searched (window leaves its sequence, outside the selection) have empty
+ * lists — exactly the k-mers the reference does not emit (src/algo.hpp:377-385).
+ * One call covers positions [pos_begin, out->pos_end) with out->pos_end <= pos_end chosen so that at most
+ * `max_locations` occurrences (0 = default, 64 Mi) are returned, but always at least one position; the caller
+ * continues from out->pos_end.  Needs an index with the suffix-array section.  The arrays are owned by the
+ * library until gmb_locations_free(). */
+typedef struct gmb_location {
+    uint32_t seq;
+    uint32_t pos;
+} gmb_location;
+
+typedef struct gmb_locations {
+    uint64_t pos_begin, pos_end;
+    uint64_t n_locations;
+    uint64_t *offsets;     /* 2 * (pos_end - pos_begin) + 1 */
+    gmb_location *loc;     /* n_locations */
+    double kernel_ms;      /* both search passes */
+} gmb_locations;
+
+int gmb_map_locations(gmb_index *idx, const gmb_params *params, uint64_t text_begin, uint64_t text_len,
+                      const uint64_t *chrom_cum_lengths, uint32_t n_chrom,
+                      const uint64_t (*intervals)[2], uint64_t n_intervals, uint64_t pos_begin,
+                      uint64_t pos_end, uint64_t max_locations, gmb_locations *out);
+void gmb_locations_free(gmb_locations *locations);
 
 #ifdef __cplusplus
 }

@@ -865,3 +865,31 @@ int gmo_brute(const uint8_t *codes, const uint64_t *limits, uint32_t n_seq, cons
     free(sel);
     return 0;
 }
+
+/* Definition-level csv lists (the csvComputation branch, src/algo.hpp:311-346): every occurrence with <= E
+ * mismatches of the k-mer at concatenated-text position `pos` (strand 0) or of its reverse complement
+ * (strand 1: the "- strand" column), as (sequence, offset) pairs in the order std::sort gives them (:335,:346).
+ * The k-mer is read from the concatenated text like the reference does (it may span two sequences; the caller
+ * decides which positions are emitted, :377-385).  Returns the number of occurrences; at most `cap` are written. */
+uint64_t gmo_brute_locations(const uint8_t *codes, const uint64_t *limits, uint32_t n_seq, uint32_t K, uint32_t E,
+                             uint64_t pos, int strand, uint32_t *seq_out, uint32_t *pos_out, uint64_t cap)
+{
+    uint8_t pat[256];
+    uint64_t n = 0;
+    if (K > 255 || pos + K > limits[n_seq]) return 0;
+    for (uint32_t k = 0; k < K; ++k) {
+        uint8_t ch = strand ? codes[pos + K - 1 - k] : codes[pos + k];
+        pat[k] = (strand && ch < GMO_N) ? (uint8_t)(3 - ch) : ch;
+    }
+    for (uint32_t s = 0; s < n_seq; ++s)
+        for (uint64_t q = limits[s]; q + K <= limits[s + 1]; ++q) {
+            uint32_t mm = 0;
+            for (uint32_t k = 0; k < K && mm <= E; ++k)
+                mm += (pat[k] == GMO_N) || (codes[q + k] != pat[k]); /* a pattern N never matches (src/algo.hpp:111-112) */
+            if (mm <= E) {
+                if (n < cap) { seq_out[n] = s; pos_out[n] = (uint32_t)(q - limits[s]); }
+                ++n;
+            }
+        }
+    return n;
+}

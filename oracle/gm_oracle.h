@@ -72,6 +72,12 @@ int gmo_brute(const uint8_t *codes, const uint64_t *limits, uint32_t n_seq, cons
               const uint64_t *intervals, uint64_t n_intervals, const uint32_t *seq_to_file,
               void *out);
 
+/* Definition-level csv lists of ONE k-mer (src/algo.hpp:311-346): all occurrences (<= E mismatches) of the
+ * k-mer at concatenated-text position `pos` (strand 0) or of its reverse complement (strand 1) as sorted
+ * (sequence, offset) pairs.  Returns the number of occurrences; at most `cap` are written. */
+uint64_t gmo_brute_locations(const uint8_t *codes, const uint64_t *limits, uint32_t n_seq, uint32_t K, uint32_t E,
+                             uint64_t pos, int strand, uint32_t *seq_out, uint32_t *pos_out, uint64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

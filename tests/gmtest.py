@@ -142,6 +142,8 @@ def oracle_lib():
         L.gmo_map.argtypes = [vp, ctypes.POINTER(_Params), u64, u64, vp, u32, vp, u64, vp, vp]
         L.gmo_brute.restype = ctypes.c_int
         L.gmo_brute.argtypes = [vp, vp, u32, ctypes.POINTER(_Params), u64, u64, vp, u32, vp, u64, vp, vp]
+        L.gmo_brute_locations.restype = u64
+        L.gmo_brute_locations.argtypes = [vp, vp, u32, u32, u32, u64, ctypes.c_int, vp, vp, u64]
         _lib = L
     return _lib
 
@@ -228,6 +230,69 @@ def brute(seqs, K, E, revcompl=True, exclude_pseudo=False, value_bits=16, seq_to
                      _ptr(iv), 0 if iv is None else len(iv), _ptr(stf), _ptr(out))
     assert rc == 0
     return out
+
+
+def brute_locations(seqs, K, E, positions, revcompl=True):
+    """Definition-level csv lists: {concatenated-text position: (plus, minus)} with plus/minus = lists of
+    (sequence, offset) in sorted order (oracle/gm_oracle.c:gmo_brute_locations)."""
+    L = oracle_lib()
+    codes, limits = concat(seqs)
+    cap = int(limits[-1]) + 1
+    sq, ps = np.zeros(cap, dtype=np.uint32), np.zeros(cap, dtype=np.uint32)
+    out = {}
+    for pos in positions:
+        both = []
+        for strand in ((0, 1) if revcompl else (0,)):
+            n = L.gmo_brute_locations(_ptr(codes), _ptr(limits), len(seqs), K, E, int(pos), strand, _ptr(sq), _ptr(ps), cap)
+            both.append(list(zip(sq[:n].tolist(), ps[:n].tolist())))
+        if not revcompl:
+            both.append([])
+        out[int(pos)] = tuple(both)
+    return out
+
+
+def valid_starts(limits, K, text_begin=0, text_len=None):
+    """file-local positions whose K-window stays inside its sequence (the k-mers the reference emits, src/algo.hpp:380)"""
+    limits = np.asarray(limits, dtype=np.int64)
+    end = int(limits[-1]) if text_len is None else text_begin + text_len
+    out = []
+    for s in range(len(limits) - 1):
+        b, e = int(limits[s]), int(limits[s + 1])
+        if b >= text_begin and e <= end:
+            out.extend(range(b - text_begin, max(b, e - K + 1) - text_begin))
+    return out
+
+
+def csv_render(lists, chrom_cum, file_names, file_last_seq, revcompl):
+    """saveCsv (src/output.hpp:189-288) for one FASTA file from {file-local position: (plus, minus)} lists of
+    (global sequence, offset): one line per k-mer with at least one occurrence (src/algo.hpp:377-385)."""
+    cum = np.asarray(chrom_cum, dtype=np.int64)
+    lines = ['"k-mer"' + "".join(';"+ strand %s"' % f for f in file_names)
+             + ("".join(';"- strand %s"' % f for f in file_names) if revcompl else "")]
+    for j in sorted(lists):
+        plus, minus = lists[j]
+        if not plus and not minus:
+            continue
+        ch = int(np.searchsorted(cum, j, side="right") - 1)
+        line = "%d,%d" % (ch, j - cum[ch])
+        for lst in ((plus, minus) if revcompl else (plus,)):
+            i, before = 0, 0
+            for last in file_last_seq:
+                col = []
+                while i < len(lst) and lst[i][0] <= last:
+                    col.append("%d,%d" % (lst[i][0] - before, lst[i][1]))
+                    i += 1
+                line += ";" + "|".join(col)
+                before = last + 1
+        lines.append(line)
+    return "\n".join(lines) + "\n"
+
+
+def lists_from_arrays(offsets, loc, pos_begin=0):
+    """(offsets, loc) of gmb_map_locations / Index.compute_locations -> {position: (plus, minus)}"""
+    loc = [tuple(x) for x in np.asarray(loc).tolist()]
+    off = np.asarray(offsets).astype(np.int64)
+    return {pos_begin + j: (loc[off[2 * j]:off[2 * j + 1]], loc[off[2 * j + 1]:off[2 * j + 2]]) for j in range((len(off) - 1) // 2)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -349,8 +414,10 @@ def hostsim_lib():
         L.hs_step_tables.restype = ci
         L.hs_step_tables.argtypes = [u32, u32, ctypes.POINTER(u32), vp]
         L.hs_map.restype = ci
-        L.hs_map.argtypes = [vp, u32, u32, ci, ci, u64, u64, vp, u32, vp, u64, u64, u64, vp, ctypes.POINTER(ctypes.c_ulonglong),
+        L.hs_map.argtypes = [vp, u32, u32, ci, ci, u64, u64, vp, u32, vp, u64, u64, u64, vp, vp,
                              ci, ctypes.POINTER(ctypes.c_ulonglong), vp, u32, u32]
+        L.hs_locate.restype = ci
+        L.hs_locate.argtypes = [vp, u32, u32, ci, u64, u64, vp, u32, vp, u64, u64, u64, ci, vp, ctypes.POINTER(vp)]
         _hs = L
     return _hs
 
@@ -389,15 +456,36 @@ class HostSim:
             pos_begin=0, pos_end=None, return_fetches=False, jump_depth=-1, exclude_pseudo=False, block_kmers=0):
         stf, tb, tl, cum, iv = _prep(self.limits, seq_to_file, file_no, intervals)
         out = np.zeros(tl, dtype=np.uint16 if value_bits == 16 else np.uint8)
-        f, lr = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        f, lr = (ctypes.c_ulonglong * 10)(), ctypes.c_ulonglong(0)
         rc = self.L.hs_map(self.blob, K, E, int(revcompl), value_bits, tb, tl, _ptr(cum), len(cum) - 1, _ptr(iv),
                            0 if iv is None else len(iv), pos_begin, tl if pos_end is None else pos_end, _ptr(out),
-                           ctypes.byref(f), jump_depth, ctypes.byref(lr), _ptr(stf) if exclude_pseudo else None, file_no,
+                           f, jump_depth, ctypes.byref(lr), _ptr(stf) if exclude_pseudo else None, file_no,
                            block_kmers)
         if rc != 0:
             raise RuntimeError("hs_map failed: %d" % rc)
         self.last_lut_reads = lr.value
-        return (out, f.value) if return_fetches else out
+        self.last_fetch_stats = list(f)  # total, by interval size [8], thin paths
+        return (out, f[0]) if return_fetches else out
+
+    def locate(self, K, E, revcompl=True, seq_to_file=None, file_no=0, intervals=None, pos_begin=0, pos_end=None,
+               jump_depth=-1):
+        """csv lists of the file-local positions [pos_begin, pos_end) -> {position: (plus, minus)}, (seq, offset) pairs"""
+        stf, tb, tl, cum, iv = _prep(self.limits, seq_to_file, file_no, intervals)
+        pos_end = tl if pos_end is None else pos_end
+        off = np.zeros(2 * (pos_end - pos_begin) + 1, dtype=np.uint64)
+        rows = ctypes.c_void_p()
+        rc = self.L.hs_locate(self.blob, K, E, int(revcompl), tb, tl, _ptr(cum), len(cum) - 1, _ptr(iv),
+                              0 if iv is None else len(iv), pos_begin, pos_end, jump_depth, _ptr(off), ctypes.byref(rows))
+        if rc != 0:
+            raise RuntimeError("hs_locate failed: %d" % rc)
+        n = int(off[-1])
+        r = np.frombuffer(ctypes.string_at(rows, 4 * n), dtype=np.uint32).astype(np.int64) if n else np.zeros(0, np.int64)
+        self.L.hs_free(rows)
+        seq_start = np.asarray(self.limits, dtype=np.int64) + np.arange(self.n_seq + 1)
+        sq = np.searchsorted(seq_start, r, side="right") - 1
+        pairs = list(zip(sq.tolist(), (r - seq_start[sq]).tolist()))
+        return {pos_begin + j: (pairs[int(off[2 * j]):int(off[2 * j + 1])], pairs[int(off[2 * j + 1]):int(off[2 * j + 2])])
+                for j in range(pos_end - pos_begin)}
 
 
 # ---------------------------------------------------------------------------------------------

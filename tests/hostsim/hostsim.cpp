@@ -26,7 +26,7 @@ struct HostFrames {
 
 template <int KW, bool EP, bool BLK, int SIGMA>
 void run_ranges(const MapCtx& cx, const uint64_t* text, const uint64_t* nmask, uint64_t text_begin,
-                const std::vector<WorkRange>& ranges, int value_bits, void* out, unsigned long long* fetches,
+                const std::vector<WorkRange>& ranges, int value_bits, void* out, FetchStats* fetches,
                 unsigned long long* lut_reads)
 {
     for (const WorkRange& r : ranges)
@@ -43,6 +43,34 @@ void run_ranges(const MapCtx& cx, const uint64_t* text, const uint64_t* nmask, u
                 else static_cast<uint8_t*>(out)[j0 + w] = (uint8_t)v;
             }
         }
+}
+// the locate instantiation (csv lists): counting pass, prefix sums, filling pass, per-list sort — the
+// same sequence locate_kernel.cu / gmb_map_locations run on the device
+template <int KW, int SIGMA>
+void run_locate(MapCtx cx, const uint64_t* text, const uint64_t* nmask, uint64_t text_begin, const std::vector<WorkRange>& ranges,
+                uint64_t pos0, uint64_t npos, std::vector<uint64_t>& off, std::vector<uint32_t>& rows)
+{
+    std::vector<uint32_t> counts(2 * npos + 1, 0);
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            off.assign(2 * npos + 1, 0);
+            for (uint64_t i = 0; i < 2 * npos; ++i) off[i + 1] = off[i] + counts[i];
+            rows.assign(off[2 * npos], 0);
+            cx.loc_rows = rows.data();
+        }
+        for (const WorkRange& r : ranges)
+            for (uint64_t j = r.begin; j < r.end; ++j) {
+                Chain<KW, SIGMA> st;
+                HostFrames fr;
+                st.cnt = 1;
+                load_pattern(st.pat, text, nmask, text_begin + j, cx.K);
+                chain_begin_block<KW, true, false, SIGMA>(st, fr, cx, nullptr);
+                if (pass == 1) { st.loc_at_fwd = off[2 * (j - pos0)]; st.loc_at_rev = off[2 * (j - pos0) + 1]; }
+                while (chain_step<KW, true, false, SIGMA, HostFrames, true>(st, fr, cx, nullptr, nullptr)) {}
+                if (pass == 0) { counts[2 * (j - pos0)] = st.occ_fwd; counts[2 * (j - pos0) + 1] = st.occ_rev; }
+            }
+    }
+    for (uint64_t i = 0; i < 2 * npos; ++i) std::sort(rows.begin() + off[i], rows.begin() + off[i + 1]);
 }
 } // namespace
 
@@ -108,6 +136,7 @@ int hs_step_tables(uint32_t K, uint32_t E, uint32_t* n_search, uint32_t* steps)
 }
 
 // jump_depth: -1 = default for the index size, 0 = no jump tables, else the maximum depth
+// fetches (optional): 10 words — total, by interval size [8], thin paths (gmb_core.h: FetchStats)
 int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bits, uint64_t text_begin,
            uint64_t text_len, const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t* intervals,
            uint64_t n_intervals, uint64_t pos_begin, uint64_t pos_end, void* out, unsigned long long* fetches,
@@ -135,6 +164,7 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     cx.K = K; cx.B = B; cx.n_search = tabs.n_search; cx.n_strands = revcompl ? 2 : 1;
     cx.maxv = value_bits == 16 ? 65535u : 255u;
     cx.sa = nullptr; cx.seq_start = nullptr; cx.seq_to_file = nullptr; cx.n_seq = h.n_seq; cx.own_file = own_file; cx.all_files = 0;
+    cx.loc_rows = nullptr;
     if (ep) {
         if (!h.off_sa) return -3;
         cx.sa = reinterpret_cast<const uint32_t*>(base + h.off_sa);
@@ -182,7 +212,8 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     build_work_ranges(text_len, K, chrom_cum, n_chrom, intervals, n_intervals, pos_begin, pos_end, ranges);
     const uint64_t* text = reinterpret_cast<const uint64_t*>(base + h.off_text);
     const uint64_t* nmask = sigma == 5 ? reinterpret_cast<const uint64_t*>(base + h.off_nmask) : nullptr;
-    unsigned long long f = 0, lr = 0;
+    FetchStats f{};
+    unsigned long long lr = 0;
 #define RUN_KS(KW, BLK, SG) (ep ? run_ranges<KW, true, BLK, SG>(cx, text, nmask, text_begin, ranges, value_bits, out, &f, &lr) \
                                 : run_ranges<KW, false, BLK, SG>(cx, text, nmask, text_begin, ranges, value_bits, out, &f, &lr))
 #define RUN_KB(KW, BLK) (sigma == 5 ? RUN_KS(KW, BLK, 5) : RUN_KS(KW, BLK, 4))
@@ -192,8 +223,83 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     else if (needle <= 64) RUN_KW(2);
     else if (needle <= 128) RUN_KW(4);
     else RUN_KW(9);
-    if (fetches) *fetches = f;
+    if (fetches) { fetches[0] = f.total; for (int k = 0; k < 8; ++k) fetches[1 + k] = f.by_size[k]; fetches[9] = f.thin_paths; }
     if (lut_reads_out) *lut_reads_out = lr;
+    return 0;
+}
+
+// csv lists of the file-local positions [pos_begin, pos_end): offsets_out has 2*(pos_end-pos_begin)+1 entries;
+// rows (sorted positions inside the sentinel-separated text T) are malloc'ed into *rows_out (hs_free).
+int hs_locate(const void* blob, uint32_t K, uint32_t E, int revcompl, uint64_t text_begin, uint64_t text_len,
+              const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t* intervals, uint64_t n_intervals,
+              uint64_t pos_begin, uint64_t pos_end, int jump_depth, uint64_t* offsets_out, uint32_t** rows_out)
+{
+    const uint8_t* base = static_cast<const uint8_t*>(blob);
+    std::string err;
+    const IndexHeader& h = *reinterpret_cast<const IndexHeader*>(base);
+    if (!h.off_sa) return -3;
+    BlockTables tabs;
+    if (!build_block_tables(K, E, 1, true, tabs, err)) return -2;
+    MapCtx cx;
+    cx.blk[0] = base + h.off_fwd;
+    cx.blk[1] = base + h.off_rev;
+    cx.sent[0] = reinterpret_cast<const uint32_t*>(base + h.off_sent_fwd);
+    cx.sent[1] = reinterpret_cast<const uint32_t*>(base + h.off_sent_rev);
+    for (int c = 0; c < 5; ++c) cx.C[c] = (uint32_t)h.C[c];
+    const uint32_t sigma = h.sigma;
+    cx.n_bwt = (uint32_t)h.n_bwt;
+    cx.steps = tabs.steps.data();
+    cx.p1_off = tabs.p1_off;
+    cx.fl_off = tabs.fl_off;
+    cx.K = K; cx.B = 1; cx.n_search = tabs.n_search; cx.n_strands = revcompl ? 2 : 1;
+    cx.maxv = 65535u;
+    cx.sa = reinterpret_cast<const uint32_t*>(base + h.off_sa);
+    cx.seq_start = reinterpret_cast<const uint32_t*>(base + h.off_seq_start);
+    cx.seq_to_file = nullptr; cx.n_seq = h.n_seq; cx.own_file = 0; cx.all_files = 0;
+    cx.loc_rows = nullptr;
+    const uint32_t want_depth = jump_depth < 0 ? default_jump_depth(h.n_bwt) : (uint32_t)jump_depth;
+    JumpPlan plan;
+    plan_jump_tables(tabs.infix[1], want_depth, plan);
+    std::vector<std::vector<JtEntry>> uni(plan.max_depth + 1);
+    std::vector<std::vector<uint32_t>> lof(plan.max_depth + 1);
+    for (uint32_t d = 1; d <= plan.max_depth; ++d) {
+        const uint64_t n = 1ull << (2 * d), pmask = (1ull << (2 * (d - 1))) - 1;
+        uni[d].resize(n); lof[d].resize(n);
+        for (uint64_t key = 0; key < n; ++key) {
+            Node par;
+            if (d == 1) { par.lo_f = 0; par.lo_r = 0; par.size = cx.n_bwt; }
+            else { par.lo_f = lof[d - 1][key & pmask]; par.lo_r = uni[d - 1][key & pmask].lo_r; par.size = uni[d - 1][key & pmask].size; }
+            const Node m = sigma == 5 ? extend_right<5>(par, (uint32_t)(key >> (2 * (d - 1))), cx)
+                                      : extend_right<4>(par, (uint32_t)(key >> (2 * (d - 1))), cx);
+            uni[d][key].lo_r = m.lo_r; uni[d][key].size = m.size; lof[d][key] = m.lo_f;
+        }
+    }
+    std::vector<SearchStart> starts(2 * kMaxSearches);
+    for (uint32_t s = 0; s < kMaxSearches; ++s) {
+        const uint32_t d = plan.depth[s];
+        SearchStart& S = starts[kMaxSearches + s];
+        S.uni = d ? uni[d].data() : nullptr;
+        S.lof = (d && plan.need_lof[s]) ? lof[d].data() : nullptr;
+        S.a = plan.a[s]; S.d = d;
+    }
+    cx.starts = starts.data();
+    std::vector<WorkRange> ranges;
+    build_work_ranges(text_len, K, chrom_cum, n_chrom, intervals, n_intervals, pos_begin, pos_end, ranges);
+    const uint64_t* text = reinterpret_cast<const uint64_t*>(base + h.off_text);
+    const uint64_t* nmask = sigma == 5 ? reinterpret_cast<const uint64_t*>(base + h.off_nmask) : nullptr;
+    std::vector<uint64_t> off;
+    std::vector<uint32_t> rows;
+    const uint64_t npos = pos_end - pos_begin;
+#define LOC_KW(KW) (sigma == 5 ? run_locate<KW, 5>(cx, text, nmask, text_begin, ranges, pos_begin, npos, off, rows) \
+                               : run_locate<KW, 4>(cx, text, nmask, text_begin, ranges, pos_begin, npos, off, rows))
+    if (K <= 32) LOC_KW(1);
+    else if (K <= 64) LOC_KW(2);
+    else if (K <= 128) LOC_KW(4);
+    else LOC_KW(9);
+    std::memcpy(offsets_out, off.data(), off.size() * 8);
+    uint32_t* r = static_cast<uint32_t*>(std::malloc(rows.size() * 4 + 4));
+    std::memcpy(r, rows.data(), rows.size() * 4);
+    *rows_out = r;
     return 0;
 }
 

@@ -54,6 +54,16 @@ def _replay(genmap, case, tmp_path, host_builder=False, extra=()):
             assert not mismatch and not errors, (case, vt, fmt, mismatch, errors)
             n += len(match)
         assert set(os.listdir(str(out))) == expected, (case, vt, set(os.listdir(str(out))) ^ expected)
+    # csv (`-d`, tests/CMakeLists.txt:52-53): its own map call, like the reference's test matrix
+    golden = os.path.join(folder, "csv")
+    out = tmp_path / ("out_csv_%s%s" % ("".join(extra), "h" if host_builder else ""))
+    out.mkdir()
+    r = subprocess.run([genmap, "map", "-I", idx, "-O", str(out)] + base_flags + ["-d"] + list(extra), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    names = os.listdir(golden)
+    match, mismatch, errors = filecmp.cmpfiles(golden, str(out), names, shallow=False)
+    assert not mismatch and not errors, (case, "csv", mismatch, errors)
+    assert set(os.listdir(str(out))) == set(names)
     assert n > 0
 
 
@@ -122,3 +132,29 @@ def test_cli_multi_gpu_sharding_gives_identical_files(genmap, tmp_path):
         outs.append(out)
     for name in os.listdir(str(outs[0])):
         assert filecmp.cmp(str(outs[0] / name), str(outs[1] / name), shallow=False), name
+
+
+def test_cli_csv_matches_the_reference_binary(genmap, tmp_path):
+    """`-d` next to other formats, E > 0, multi-sequence, with and without a selection: byte-identical csv."""
+    if not T.have_reference():
+        pytest.skip("oracle/_ref/genmap_ref not present")
+    import genmap_b200 as gm
+    fa = str(tmp_path / "g.fa")
+    T.write_fasta(fa, T.repeat_rich(21, 3, 4000))
+    bed = str(tmp_path / "sel.bed")
+    with open(bed, "w") as f:
+        f.write("chr1\t100\t900\nchr3\t3500\t4000\n")
+    ref_idx, idx = str(tmp_path / "ref_index"), str(tmp_path / "index")
+    subprocess.run([T.REF_BIN, "index", "-F", fa, "-I", ref_idx], check=True, stdout=subprocess.DEVNULL)
+    assert subprocess.run([genmap, "index", "-F", fa, "-I", idx]).returncode == 0
+    for tag, flags in (("e1", ["-K", "20", "-E", "1"]), ("e2nc", ["-K", "24", "-E", "2", "-nc"]), ("sel", ["-K", "16", "-E", "1", "-S", bed])):
+        outs = []
+        for binary, index in ((T.REF_BIN, ref_idx), (genmap, idx)):
+            out = tmp_path / ("out_%s_%d" % (tag, len(outs)))
+            out.mkdir()
+            r = subprocess.run([binary, "map", "-I", index, "-O", str(out)] + flags + ["-d", "-r", "-fl"], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            outs.append(out)
+        for name in ("g.genmap.csv", "g.genmap.freq16"):
+            assert filecmp.cmp(str(outs[0] / name), str(outs[1] / name), shallow=False), (tag, name)
+        assert os.path.getsize(str(outs[1] / "g.genmap.csv")) > 10000

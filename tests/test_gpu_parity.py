@@ -366,3 +366,49 @@ def test_gpu_built_index_feeds_the_unmodified_reference(gm, tmp_path):
     ref = np.fromfile(str(out / "genome.genmap.freq16"), dtype=np.uint16)
     got = ix.compute_mappability(gm.SearchParams(30, 1), intervals=[(401000, 551000)])
     assert np.array_equal(got, ref)
+
+
+# ---- locations (csv lists): gmb_map_locations ------------------------------------------------------------------
+@pytest.mark.parametrize("with_n", [False, True], ids=["dna4", "dna5"])
+@pytest.mark.parametrize("K,E,rc", [(12, 0, True), (14, 2, True), (10, 2, False), (33, 3, True), (70, 1, True)])
+def test_cuda_locations_match_definition(gm, K, E, rc, with_n):
+    seqs = T.repeat_rich(7, 3, 700, with_n=with_n)
+    _, limits = T.concat(seqs)
+    ix = gm.Index.build(seqs, with_sa=True)
+    off, loc = ix.compute_locations(gm.SearchParams(K, E, rc))
+    got = T.lists_from_arrays(off, loc)
+    want = T.brute_locations(seqs, K, E, T.valid_starts(limits, K), revcompl=rc)
+    assert len(loc) > int(limits[-1]) // 2
+    for j in range(int(limits[-1])):
+        assert got[j] == want.get(j, ([], [])), j
+    # a small budget forces many continuation calls; a range in the middle; an index built on the host
+    off2, loc2 = ix.compute_locations(gm.SearchParams(K, E, rc), max_locations=50)
+    assert np.array_equal(off, off2) and np.array_equal(loc, loc2)
+    off3, loc3 = ix.compute_locations(gm.SearchParams(K, E, rc), pos_begin=300, pos_end=900)
+    assert T.lists_from_arrays(off3, loc3, 300) == {j: got[j] for j in range(300, 900)}
+    ixh = gm.Index.build(seqs, with_sa=True, on_gpu=False)
+    off4, loc4 = ixh.compute_locations(gm.SearchParams(K, E, rc))
+    assert np.array_equal(off, off4) and np.array_equal(loc, loc4)
+
+
+def test_cuda_locations_match_host_state_machine_and_counts(gm):
+    """Larger genome: the lists equal the host-compiled state machine's, and their lengths are the unsaturated
+    frequencies (countOccurrences summed over itAll, src/algo.hpp:318-326)."""
+    seqs = gm.synth_genome(300_000, 3, 11)
+    _, limits = T.concat(seqs)
+    ix = gm.Index.build(seqs, with_sa=True)
+    hs = T.HostSim(seqs, with_sa=True)
+    for K, E in ((30, 0), (30, 2), (20, 1)):
+        off, loc = ix.compute_locations(gm.SearchParams(K, E), pos_begin=100_000, pos_end=140_000)
+        want = hs.locate(K, E, pos_begin=100_000, pos_end=140_000)
+        assert T.lists_from_arrays(off, loc, 100_000) == want, (K, E)
+        freq = ix.compute_mappability(gm.SearchParams(K, E))[100_000:140_000]
+        n = (off[2::2] - off[:-2:2]).astype(np.int64)
+        assert np.array_equal(np.minimum(n, 65535), freq.astype(np.int64)), (K, E)
+
+
+def test_cuda_locations_need_the_suffix_array(gm):
+    ix = gm.Index.build(T.repeat_rich(7, 1, 500), with_sa=False)
+    with pytest.raises(gm.GenmapError) as e:
+        ix.compute_locations(gm.SearchParams(12, 0))
+    assert "suffix array" in str(e.value)

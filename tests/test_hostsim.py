@@ -1,5 +1,7 @@
 """CPU checks of the product's host code and of the kernel's search state machine compiled for the host
 (tests/hostsim): index builder vs the oracle's naive suffix sort, counts vs the oracle / brute force."""
+import os
+
 import numpy as np
 import pytest
 
@@ -240,3 +242,42 @@ def test_dna5_exclude_pseudo_and_reference_fixtures():
         want = mo.map(22, 2, exclude_pseudo=True, file_no=f)
         for B in (1, 4):
             assert np.array_equal(mh.map(22, 2, seq_to_file=stf, file_no=f, exclude_pseudo=True, block_kmers=B), want), (f, B)
+
+
+# ---- locate instantiation (csv lists, src/algo.hpp:311-346) ---------------------------------------------------
+@pytest.mark.parametrize("with_n", [False, True])
+@pytest.mark.parametrize("K,E,rc", [(12, 0, True), (12, 1, True), (14, 2, True), (10, 2, False), (33, 3, True)])
+def test_locate_lists_match_definition(K, E, rc, with_n):
+    seqs = T.repeat_rich(7, 3, 700, with_n=with_n)
+    hs = T.HostSim(seqs, with_sa=True)
+    _, limits = T.concat(seqs)
+    got = hs.locate(K, E, revcompl=rc)
+    want = T.brute_locations(seqs, K, E, T.valid_starts(limits, K), revcompl=rc)
+    assert sum(len(a) + len(b) for a, b in got.values()) > int(limits[-1]) // 2
+    for j in range(int(limits[-1])):
+        assert got[j] == want.get(j, ([], [])), j
+    for depth in (0, 3):  # jump tables do not change the lists
+        assert hs.locate(K, E, revcompl=rc, jump_depth=depth) == got
+
+
+@pytest.mark.parametrize("case", sorted(T.CASES))
+def test_locate_lists_reproduce_reference_golden_csv(case):
+    """All 18 csv goldens (tests/CMakeLists.txt:52-53, `-d`), selection and multi-FASTA cases included."""
+    cfg = T.CASES[case]
+    files, sel, folder = T.load_case(case)
+    seqs, stf, _ = T.case_layout(files)
+    hs = T.HostSim(seqs, with_sa=True)
+    names = [f + ".fa" for f, _ in files]
+    last = (np.cumsum([len(recs) for _, recs in files]) - 1).tolist()
+    made = {}
+    for fi, (fn, recs) in enumerate(files):
+        iv = T.file_intervals(sel, recs)
+        if iv is None:
+            continue
+        lists = hs.locate(cfg["K"], cfg["E"], revcompl=cfg["rc"], seq_to_file=stf, file_no=fi, intervals=iv)
+        cum = np.concatenate([[0], np.cumsum([len(c) for _, c in recs])])
+        made[fn + ".genmap.csv"] = T.csv_render(lists, cum, names, last, cfg["rc"])
+    gold = os.path.join(folder, "csv")
+    assert set(made) == set(os.listdir(gold))
+    for fn, text in made.items():
+        assert text == open(os.path.join(gold, fn)).read(), (case, fn)
