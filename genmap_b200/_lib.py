@@ -13,7 +13,7 @@ EXPORTS = ["gmb_last_error", "gmb_version", "gmb_device_count", "gmb_index_build
            "gmb_index_build_device", "gmb_blob_save", "gmb_index_open", "gmb_index_from_blob",
            "gmb_index_adopt_device", "gmb_index_close", "gmb_index_get_info", "gmb_map_frequencies",
            "gmb_map_frequencies_range", "gmb_map_frequencies_device", "gmb_index_export_bwt", "gmb_index_export_sa", "gmb_index_set_jump_depth",
-           "gmb_index_import_reference", "gmb_map_locations", "gmb_locations_free"]
+           "gmb_index_import_reference", "gmb_map_locations", "gmb_locations_free", "gmb_map_runs", "gmb_runs_free"]
 
 
 class GmbParams(ctypes.Structure):
@@ -38,6 +38,12 @@ class GmbMapStats(ctypes.Structure):
 class GmbLocations(ctypes.Structure):
     _fields_ = [("pos_begin", ctypes.c_uint64), ("pos_end", ctypes.c_uint64), ("n_locations", ctypes.c_uint64),
                 ("offsets", ctypes.POINTER(ctypes.c_uint64)), ("loc", ctypes.c_void_p), ("kernel_ms", ctypes.c_double)]
+
+
+class GmbRuns(ctypes.Structure):
+    _fields_ = [("pos_begin", ctypes.c_uint64), ("pos_end", ctypes.c_uint64), ("n_runs", ctypes.c_uint64),
+                ("start", ctypes.POINTER(ctypes.c_uint64)), ("value", ctypes.POINTER(ctypes.c_uint16)),
+                ("kernel_ms", ctypes.c_double), ("rle_ms", ctypes.c_double)]
 
 
 class GenmapError(RuntimeError):
@@ -100,6 +106,10 @@ def lib():
     L.gmb_map_locations.argtypes = [vp, ctypes.POINTER(GmbParams), u64, u64, vp, u32, vp, u64, u64, u64, u64,
                                     ctypes.POINTER(GmbLocations)]
     L.gmb_locations_free.argtypes = [ctypes.POINTER(GmbLocations)]
+    L.gmb_map_runs.restype = ci
+    L.gmb_map_runs.argtypes = [vp, ctypes.POINTER(GmbParams), u64, u64, vp, u32, vp, u64, vp, u32, u64, u64,
+                               ctypes.POINTER(GmbRuns), ctypes.POINTER(GmbMapStats)]
+    L.gmb_runs_free.argtypes = [ctypes.POINTER(GmbRuns)]
     _lib = L
     return L
 

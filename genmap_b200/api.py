@@ -13,7 +13,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import GenmapError, GmbIndexInfo, GmbLocations, GmbMapStats, GmbParams, check
+from ._lib import GenmapError, GmbIndexInfo, GmbLocations, GmbMapStats, GmbParams, GmbRuns, check
 
 
 def _ptr(a):
@@ -190,6 +190,26 @@ class Index:
             b = int(r.pos_end)
             _lib.lib().gmb_locations_free(ctypes.byref(r))
         return np.concatenate(offs), np.concatenate(locs)
+
+    def compute_runs(self, params, pos_begin=0, pos_end=None, text_begin=0, text_len=None, chrom_cum_lengths=None,
+                     intervals=None, return_timings=False):
+        """The frequency vector of [pos_begin, pos_end) run-length encoded on the device (what saveWig / saveBedGraph
+        scan for, src/output.hpp:73-187) -> (start uint64[n], value uint16[n]); run r = [start[r], start[r+1])."""
+        tb, tl, cum, iv = self._file_args(text_begin, text_len, chrom_cum_lengths, intervals)
+        pos_end = tl if pos_end is None else int(pos_end)
+        p = GmbParams(params.length, params.errors, int(params.rev_compl), int(params.exclude_pseudo),
+                      params.value_bits, 0, params.block_kmers)
+        r = GmbRuns()
+        check(_lib.lib().gmb_map_runs(self._h, ctypes.byref(p), tb, tl, _ptr(cum), len(cum) - 1, _ptr(iv),
+                                      0 if iv is None else len(iv), _ptr(self.seq_to_file),
+                                      0 if self.seq_to_file is None else len(self.seq_to_file), int(pos_begin), pos_end,
+                                      ctypes.byref(r), None))
+        n = int(r.n_runs)
+        start = np.ctypeslib.as_array(r.start, shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+        value = np.ctypeslib.as_array(r.value, shape=(n,)).copy() if n else np.zeros(0, np.uint16)
+        tm = (r.kernel_ms, r.rle_ms)
+        _lib.lib().gmb_runs_free(ctypes.byref(r))
+        return (start, value, tm) if return_timings else (start, value)
 
     def set_jump_depth(self, depth):
         """-1 = automatic, 0 = no jump tables, 1..16 = maximum table depth (see gmb_index_set_jump_depth)."""

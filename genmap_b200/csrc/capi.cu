@@ -17,6 +17,7 @@
 #include "index_build_gpu.cuh"
 #include "jump_table.cuh"
 #include "locate.cuh"
+#include "rle.cuh"
 #include "map_kernel.cuh"
 
 using namespace gmb;
@@ -61,7 +62,7 @@ __global__ void k_decode_bwt5(const RankBlock5* __restrict__ B, uint64_t n, uint
     const RankBlock5& b = B[i / kBlockBases5];
     const uint32_t k = (uint32_t)(i % kBlockBases5);
     uint32_t c = 0;
-    for (int pl = 0; pl < 3; ++pl) c |= ((b.plane[pl][k >> 5] >> (k & 31)) & 1u) << pl;
+    for (int pl = 0; pl < 3; ++pl) c |= ((b.plane[pl] >> k) & 1u) << pl;
     out[i] = (uint8_t)(1u + c);
 }
 
@@ -761,6 +762,77 @@ int gmb_map_locations(gmb_index* ix, const gmb_params* p, uint64_t text_begin, u
     out->offsets = h_off;
     out->loc = h_loc;
     out->kernel_ms = st1.kernel_ms + st2.kernel_ms;
+    return GMB_OK;
+}
+
+/* ---- runs (track writers) ------------------------------------------------------------------------------------ */
+void gmb_runs_free(gmb_runs* R)
+{
+    if (!R) return;
+    std::free(R->start);
+    std::free(R->value);
+    R->start = nullptr; R->value = nullptr; R->n_runs = 0;
+}
+
+int gmb_map_runs(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len, const uint64_t* chrom_cum,
+                 uint32_t n_chrom, const uint64_t (*intervals)[2], uint64_t n_intervals, const uint32_t* seq_to_file,
+                 uint32_t n_seq, uint64_t pos_begin, uint64_t pos_end, gmb_runs* out, gmb_map_stats* stats)
+{
+    if (!ix || !p || !out || !chrom_cum) return fail(GMB_ERR_ARG, "gmb_map_runs: NULL argument");
+    std::memset(out, 0, sizeof(*out));
+    if (p->value_bits != 8 && p->value_bits != 16) return fail(GMB_ERR_ARG, "value_bits must be 8 or 16");
+    if (pos_end > text_len) pos_end = text_len;
+    if (pos_begin > pos_end) return fail(GMB_ERR_ARG, "pos_begin > pos_end");
+    out->pos_begin = pos_begin; out->pos_end = pos_end;
+    if (pos_begin == pos_end) return GMB_OK;
+    CU(cudaSetDevice(ix->device));
+    const size_t elem = p->value_bits / 8;
+    const size_t bytes = (size_t)(pos_end - pos_begin) * elem;
+    if (ix->out_cap < bytes) {
+        if (ix->d_out) cudaFree(ix->d_out);
+        ix->d_out = nullptr;
+        ix->out_cap = 0;
+        CU(cudaMalloc(&ix->d_out, bytes));
+        ix->out_cap = bytes;
+    }
+    void* biased = reinterpret_cast<void*>(reinterpret_cast<uintptr_t>(ix->d_out) - (uintptr_t)pos_begin * elem);
+    CU(cudaMemsetAsync(ix->d_out, 0, bytes, nullptr));
+    gmb_map_stats local;
+    int rc = map_device_impl(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, seq_to_file, n_seq,
+                             pos_begin, pos_end, biased, nullptr, &local, true);
+    if (rc != GMB_OK) return rc;
+    if (stats) *stats = local;
+    out->kernel_ms = local.kernel_ms;
+
+    DevBuf cum, temp, starts, values;
+    CU(cum.alloc(((size_t)n_chrom + 1) * 8));
+    CU(cudaMemcpyAsync(cum.p, chrom_cum, ((size_t)n_chrom + 1) * 8, cudaMemcpyHostToDevice, nullptr));
+    unsigned long long* d_count = ix->d_counters + 12;
+    CU(cudaEventRecord(ix->ev0, nullptr));
+    size_t tb1 = 0, tb2 = 0;
+    CU(rle_count(biased, p->value_bits, cum.as<uint64_t>(), n_chrom, pos_begin, pos_end, d_count, nullptr, tb1, nullptr));
+    CU(rle_select(biased, p->value_bits, cum.as<uint64_t>(), n_chrom, pos_begin, pos_end, nullptr, d_count, nullptr, tb2, nullptr));
+    CU(temp.alloc(std::max(tb1, tb2)));
+    CU(rle_count(biased, p->value_bits, cum.as<uint64_t>(), n_chrom, pos_begin, pos_end, d_count, temp.p, tb1, nullptr));
+    unsigned long long n_runs = 0;
+    CU(cudaMemcpy(&n_runs, d_count, sizeof(n_runs), cudaMemcpyDeviceToHost));
+    CU(starts.alloc(n_runs * 8));
+    CU(values.alloc(n_runs * 2));
+    CU(rle_select(biased, p->value_bits, cum.as<uint64_t>(), n_chrom, pos_begin, pos_end, starts.as<uint64_t>(), d_count, temp.p, tb2, nullptr));
+    CU(rle_gather(biased, p->value_bits, starts.as<uint64_t>(), n_runs, values.as<uint16_t>(), nullptr));
+    CU(cudaEventRecord(ix->ev1, nullptr));
+    uint64_t* h_start = static_cast<uint64_t*>(std::malloc(n_runs * 8 + 8));
+    uint16_t* h_value = static_cast<uint16_t*>(std::malloc(n_runs * 2 + 2));
+    if (!h_start || !h_value) { std::free(h_start); std::free(h_value); return fail(GMB_ERR_NOMEM, "out of host memory"); }
+    cudaError_t e = cudaMemcpy(h_start, starts.p, n_runs * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_value, values.p, n_runs * 2, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { std::free(h_start); std::free(h_value); return cuda_fail(e, "cudaMemcpy(runs)"); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ix->ev0, ix->ev1);
+    out->rle_ms = ms;
+    out->n_runs = n_runs;
+    out->start = h_start;
+    out->value = h_value;
     return GMB_OK;
 }
 

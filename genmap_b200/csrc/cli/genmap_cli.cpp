@@ -385,7 +385,8 @@ int map_main(int argc, char const** argv)
                                   {"fs", "frequency-small", false}, {"fl", "frequency-large", false}, {"r", "raw", false},
                                   {"t", "txt", false}, {"w", "wig", false}, {"bg", "bedgraph", false}, {"b", "bed", false},
                                   {"d", "csv", false}, {"m", "memory-mapping", false}, {"T", "threads", true},
-                                  {"v", "verbose", false}, {"xo", "overlap", true}, {"xg", "gpus", true}};
+                                  {"v", "verbose", false}, {"xo", "overlap", true}, {"xg", "gpus", true},
+                                  {"xv", "host-runs", false}};
     Args a;
     int rc = parse_args("GenMap map", specs, argc, argv, a, kMapHelp);
     if (rc == 2) return 0;
@@ -500,6 +501,9 @@ int map_main(int argc, char const** argv)
         if (i + 1 == rows.size() || rows[i + 1].file != rows[i].file) csv_files.push_back(CsvFile{rows[i].file, (uint32_t)i});
     if (csv && !iinfo.has_sa) { std::cerr << "ERROR: --csv needs an index that stores the suffix array (built without --no-sa).\n"; return 1; }
     const bool want_freq = raw || txt || wig || bg || bed;
+    // only track formats asked for: the runs are found on the GPU and the vector never comes to the host
+    // (--host-runs keeps the host scan, for comparison)
+    const bool device_runs = want_freq && !raw && !txt && !a.has("host-runs");
 
     gmb_params p{};
     p.K = (uint32_t)K; p.E = (uint32_t)E;
@@ -536,7 +540,10 @@ int map_main(int argc, char const** argv)
         }
         const uint64_t text_len = cum.back();
         if (!(has_selection && iv.empty())) { // :309 — files without selected intervals produce no output
-            std::vector<uint8_t> c(want_freq ? text_len * (p.value_bits / 8) : 0);
+            std::vector<uint8_t> c(want_freq && !device_runs ? text_len * (p.value_bits / 8) : 0);
+            std::vector<uint64_t> run_start; // device_runs: the slices of all GPUs, concatenated
+            std::vector<uint16_t> run_value;
+            std::vector<gmb_runs> slices(gpu);
             static_assert(sizeof(std::pair<uint64_t, uint64_t>) == 16, "interval layout");
             // positions are range-partitioned over the GPUs; every GPU fills its own slice of c
             std::vector<std::string> errors(gpu);
@@ -544,7 +551,12 @@ int map_main(int argc, char const** argv)
             for (uint64_t g = 0; want_freq && g < gpu; ++g)
                 workers.emplace_back([&, g] {
                     const uint64_t b = text_len * g / gpu, e = text_len * (g + 1) / gpu;
-                    if (gmb_map_frequencies_range(ixs[g], &p, start_pos, text_len, cum.data(), (uint32_t)lens.size(),
+                    if (device_runs) {
+                        if (gmb_map_runs(ixs[g], &p, start_pos, text_len, cum.data(), (uint32_t)lens.size(),
+                                         reinterpret_cast<const uint64_t (*)[2]>(iv.data()), iv.size(), seq_to_file.data(),
+                                         (uint32_t)seq_to_file.size(), b, e, &slices[g], nullptr) != GMB_OK)
+                            errors[g] = gmb_last_error();
+                    } else if (gmb_map_frequencies_range(ixs[g], &p, start_pos, text_len, cum.data(), (uint32_t)lens.size(),
                                                   reinterpret_cast<const uint64_t (*)[2]>(iv.data()), iv.size(), seq_to_file.data(),
                                                   (uint32_t)seq_to_file.size(), b, e, c.data() + b * (p.value_bits / 8), nullptr) != GMB_OK)
                         errors[g] = gmb_last_error();
@@ -552,6 +564,18 @@ int map_main(int argc, char const** argv)
             for (std::thread& w : workers) w.join();
             for (const std::string& e : errors)
                 if (!e.empty()) { std::cerr << "ERROR: " << e << "\n"; return 1; }
+            if (device_runs) { // a run that continues across a slice boundary is one run
+                for (uint64_t g = 0; g < gpu; ++g) {
+                    for (uint64_t r = 0; r < slices[g].n_runs; ++r) {
+                        const uint64_t st = slices[g].start[r];
+                        const bool seq_start = std::binary_search(cum.begin(), cum.end(), st);
+                        if (r == 0 && !run_start.empty() && !seq_start && run_value.back() == slices[g].value[r]) continue;
+                        run_start.push_back(st);
+                        run_value.push_back(slices[g].value[r]);
+                    }
+                    gmb_runs_free(&slices[g]);
+                }
+            }
             if (total_files == 1) std::cout << "\rProgress: 100.00%\x1b[K\n" << std::flush;
             else {
                 std::cout << "\rFile " << file_no << " / " << total_files << ". Progress: 100.00 %\x1b[K" << std::flush;
@@ -561,6 +585,8 @@ int map_main(int argc, char const** argv)
             if (!includes_filename) prefix += rows[i].file.substr(0, rows[i].file.find_last_of('.')) + ".genmap"; // :76-78
             gmbcli::Outputs o{raw, txt, wig, bg, bed, a.has("verbose")};
             if (!want_freq) {}
+            else if (device_runs)
+                gmbcli::write_track_outputs(gmbcli::ListRuns{run_start.data(), run_value.data(), run_start.size(), cum}, prefix, names, lens, otype, o);
             else if (p.value_bits == 8) gmbcli::write_outputs(c.data(), text_len, prefix, names, lens, otype, o);
             else gmbcli::write_outputs(reinterpret_cast<const uint16_t*>(c.data()), text_len, prefix, names, lens, otype, o);
             if (csv) {
@@ -583,7 +609,8 @@ int render_main(int argc, char const** argv)
 {
     std::vector<OptSpec> specs = {{"I", "ids", true}, {"C", "counts", true}, {"O", "output", true}, {"N", "file-no", true},
                                   {"fs", "frequency-small", false}, {"fl", "frequency-large", false}, {"r", "raw", false},
-                                  {"t", "txt", false}, {"w", "wig", false}, {"bg", "bedgraph", false}, {"b", "bed", false}};
+                                  {"t", "txt", false}, {"w", "wig", false}, {"bg", "bedgraph", false}, {"b", "bed", false},
+                                  {"xr", "via-runs", false}};
     Args a;
     int rc = parse_args("GenMap render", specs, argc, argv, a, "genmap render -I index.ids -C counts.freq16|.freq8 -N file_no -O prefix [-fs|-fl] -r -t -w -bg -b\n");
     if (rc) return rc == 2 ? 0 : 1;
@@ -608,6 +635,16 @@ int render_main(int argc, char const** argv)
     const gmbcli::OutputType otype = a.has("frequency-small") ? gmbcli::OutputType::frequency_small
                                    : a.has("frequency-large") ? gmbcli::OutputType::frequency_large : gmbcli::OutputType::mappability;
     gmbcli::Outputs o{a.has("raw"), a.has("txt"), a.has("wig"), a.has("bedgraph"), a.has("bed"), false};
+    if (a.has("via-runs")) { // the track writers fed from a run list shaped like gmb_map_runs' (a run starts at every sequence start)
+        const std::vector<uint64_t> cum = gmbcli::cumulative(lens);
+        std::vector<uint64_t> st;
+        std::vector<uint16_t> val;
+        auto at = [&](uint64_t i) { return in8 ? (uint16_t)buf[i] : reinterpret_cast<const uint16_t*>(buf.data())[i]; };
+        for (uint64_t i = 0; i < n; ++i)
+            if (i == 0 || at(i) != at(i - 1) || std::binary_search(cum.begin(), cum.end(), i)) { st.push_back(i); val.push_back(at(i)); }
+        gmbcli::write_track_outputs(gmbcli::ListRuns{st.data(), val.data(), st.size(), cum}, a.val["output"], names, lens, otype, o);
+        return 0;
+    }
     if (in8) gmbcli::write_outputs(buf.data(), n, a.val["output"], names, lens, otype, o);
     else gmbcli::write_outputs(reinterpret_cast<const uint16_t*>(buf.data()), n, a.val["output"], names, lens, otype, o);
     return 0;

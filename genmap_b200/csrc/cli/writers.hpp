@@ -4,6 +4,7 @@
 #pragma once
 #include <sys/time.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -66,6 +67,37 @@ void for_each_run(const T* c, uint64_t begin, uint64_t end, F&& f)
     }
 }
 
+// Where the track writers get their runs from: the frequency vector in host memory (scanned here), or the run
+// list the GPU produced (gmb_map_runs: only the runs were copied to the host).
+template <class T>
+struct VectorRuns {
+    const T* c;
+    const std::vector<uint64_t>& cum; // cumulative sequence lengths, first = 0
+    template <class F> void runs(size_t s, F&& f) const { for_each_run(c, cum[s], cum[s + 1], f); }
+};
+
+struct ListRuns {
+    const uint64_t* start; // ascending file-local run starts; a new run at every sequence start
+    const uint16_t* value;
+    uint64_t n;
+    const std::vector<uint64_t>& cum;
+    template <class F> void runs(size_t s, F&& f) const
+    {
+        uint64_t r = std::lower_bound(start, start + n, cum[s]) - start;
+        for (; r < n && start[r] < cum[s + 1]; ++r) {
+            const uint64_t end = r + 1 < n ? std::min(start[r + 1], cum[s + 1]) : cum[s + 1];
+            f(Run{start[r] - cum[s], end - start[r], value[r]});
+        }
+    }
+};
+
+inline std::vector<uint64_t> cumulative(const std::vector<uint64_t>& lens)
+{
+    std::vector<uint64_t> cum{0};
+    for (uint64_t l : lens) cum.push_back(cum.back() + l);
+    return cum;
+}
+
 template <class T>
 void write_raw(const T* c, uint64_t n, const std::string& path, bool mappability)
 {
@@ -98,17 +130,16 @@ void write_txt(const T* c, const std::string& prefix, const std::vector<std::str
     }
 }
 
-template <class T>
-void write_wig(const T* c, const std::string& prefix, const std::vector<std::string>& names,
+template <class Source>
+void write_wig(const Source& src, const std::string& prefix, const std::vector<std::string>& names,
                const std::vector<uint64_t>& lens, bool mappability)
 {
     {
         Sink o(prefix + ".wig");
         if (!o.ok()) { std::cerr << "ERROR: cannot write " << prefix << ".wig\n"; return; }
-        uint64_t begin = 0;
         for (size_t s = 0; s < lens.size(); ++s) {
             uint64_t last_span = 0; // a new variableStep header whenever the run length changes (:96-99); reset per sequence
-            for_each_run(c, begin, begin + lens[s], [&](const Run& r) {
+            src.runs(s, [&](const Run& r) {
                 if (r.value == 0) return; // zero runs are skipped (:96)
                 if (last_span != r.len) {
                     o.str("variableStep chrom="); o.str(names[s]); o.str(" span="); o.u64(r.len); o.ch('\n');
@@ -116,7 +147,6 @@ void write_wig(const T* c, const std::string& prefix, const std::vector<std::str
                 o.u64(r.start + 1); o.ch(' '); o.value(r.value, mappability); o.ch('\n'); // positions start at 1
                 last_span = r.len;
             });
-            begin += lens[s];
         }
     }
     Sink cs(prefix + ".chrom.sizes");
@@ -124,21 +154,19 @@ void write_wig(const T* c, const std::string& prefix, const std::vector<std::str
     for (size_t s = 0; s < lens.size(); ++s) { cs.str(names[s]); cs.ch('\t'); cs.u64(lens[s]); cs.ch('\n'); }
 }
 
-template <class T>
-void write_bedgraph(const T* c, const std::string& prefix, const std::vector<std::string>& names,
+template <class Source>
+void write_bedgraph(const Source& src, const std::string& prefix, const std::vector<std::string>& names,
                     const std::vector<uint64_t>& lens, bool bedgraph_format, bool mappability)
 {
     Sink o(prefix + (bedgraph_format ? ".bedgraph" : ".bed"));
     if (!o.ok()) { std::cerr << "ERROR: cannot write " << prefix << (bedgraph_format ? ".bedgraph" : ".bed") << "\n"; return; }
-    uint64_t begin = 0;
     for (size_t s = 0; s < lens.size(); ++s) {
-        for_each_run(c, begin, begin + lens[s], [&](const Run& r) {
+        src.runs(s, [&](const Run& r) {
             if (r.value == 0) return; // src/output.hpp:157
             o.str(names[s]); o.ch('\t'); o.u64(r.start); o.ch('\t'); o.u64(r.start + r.len); o.ch('\t');
             if (!bedgraph_format) { o.ch('-'); o.ch('\t'); }
             o.value(r.value, mappability); o.ch('\n');
         });
-        begin += lens[s];
     }
 }
 
@@ -156,9 +184,26 @@ void write_outputs(const T* c, uint64_t n, const std::string& prefix, const std:
         write_raw(c, n, prefix + (mapp ? ".map" : type == OutputType::frequency_small ? ".freq8" : ".freq16"), mapp);
     });
     if (o.txt) timed("TXT file", [&] { write_txt(c, prefix, names, lens, mapp); });
-    if (o.wig) timed("WIG file", [&] { write_wig(c, prefix, names, lens, mapp); });
-    if (o.bedgraph) timed("bedgraph file", [&] { write_bedgraph(c, prefix, names, lens, true, mapp); });
-    if (o.bed) timed("BED file", [&] { write_bedgraph(c, prefix, names, lens, false, mapp); });
+    const std::vector<uint64_t> cum = cumulative(lens);
+    const VectorRuns<T> src{c, cum};
+    if (o.wig) timed("WIG file", [&] { write_wig(src, prefix, names, lens, mapp); });
+    if (o.bedgraph) timed("bedgraph file", [&] { write_bedgraph(src, prefix, names, lens, true, mapp); });
+    if (o.bed) timed("BED file", [&] { write_bedgraph(src, prefix, names, lens, false, mapp); });
+}
+
+// the track formats from a run list (no frequency vector on the host)
+inline void write_track_outputs(const ListRuns& src, const std::string& prefix, const std::vector<std::string>& names,
+                                const std::vector<uint64_t>& lens, OutputType type, const Outputs& o)
+{
+    const bool mapp = type == OutputType::mappability;
+    auto timed = [&](const char* what, auto&& fn) {
+        const double t0 = now_s();
+        fn();
+        if (o.verbose) std::cout << "- " << what << " written in " << (std::round((now_s() - t0) * 100.0) / 100.0) << " seconds\n";
+    };
+    if (o.wig) timed("WIG file", [&] { write_wig(src, prefix, names, lens, mapp); });
+    if (o.bedgraph) timed("bedgraph file", [&] { write_bedgraph(src, prefix, names, lens, true, mapp); });
+    if (o.bed) timed("BED file", [&] { write_bedgraph(src, prefix, names, lens, false, mapp); });
 }
 
 } // namespace gmbcli

@@ -161,48 +161,53 @@ GMB_HD uint32_t block_rank_one(const BlockRegs& b, uint32_t r, uint32_t i, uint3
     return base + n;
 }
 
-// ---- Dna5 (sigma = 5) rank block: three planes, 96 symbols, two 256-bit loads ---------------------------
+// ---- Dna5 (sigma = 5) rank block: three planes, 32 symbols, one 256-bit load -----------------------------
 struct BlockRegs5 {
     uint32_t h[5];            // A, C, G, T before the block; sent
-    uint32_t p0[3], p1[3], p2[3];
+    uint32_t p0, p1, p2;
 };
 
 GMB_HD BlockRegs5 load_block5(const RankBlock5* p)
 {
     BlockRegs5 b;
 #if defined(__CUDA_ARCH__)
-    uint32_t r0, r1, r2, r3, r4, r6, r7, s0, s1, s2, s3, s4, s5, s6;
-    [[maybe_unused]] uint32_t r5, s7; // padding words of the block
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
     asm volatile("ld.global.nc.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "l"(p));
-    asm volatile("ld.global.nc.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+32];"
-                 : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7) : "l"(p));
     b.h[0] = r0; b.h[1] = r1; b.h[2] = r2; b.h[3] = r3; b.h[4] = r4;
-    b.p0[0] = r6; b.p0[1] = r7; b.p0[2] = s0;
-    b.p1[0] = s1; b.p1[1] = s2; b.p1[2] = s3;
-    b.p2[0] = s4; b.p2[1] = s5; b.p2[2] = s6;
+    b.p0 = r5; b.p1 = r6; b.p2 = r7;
 #else
     for (int c = 0; c < 4; ++c) b.h[c] = p->cnt[c];
     b.h[4] = p->sent;
-    for (int q = 0; q < 3; ++q) { b.p0[q] = p->plane[0][q]; b.p1[q] = p->plane[1][q]; b.p2[q] = p->plane[2][q]; }
+    b.p0 = p->plane[0]; b.p1 = p->plane[1]; b.p2 = p->plane[2];
 #endif
     return b;
 }
 
-// ranks of all symbols (c[4] = N) at BWT position i = blk*96 + r
+// b = (pred ? *p : b), predicated like load_block_if
+GMB_HD void load_block5_if(BlockRegs5& b, const RankBlock5* p, bool pred)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
+        "@q ld.global.nc.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+        : "+r"(b.h[0]), "+r"(b.h[1]), "+r"(b.h[2]), "+r"(b.h[3]), "+r"(b.h[4]), "+r"(b.p0), "+r"(b.p1), "+r"(b.p2)
+        : "l"(p), "r"((uint32_t)pred));
+#else
+    if (pred) b = load_block5(p);
+#endif
+}
+
+// ranks of all symbols (c[4] = N) at BWT position i = blk*32 + r
 struct Ranks5 { uint32_t c[5]; uint32_t s; };
 GMB_HD Ranks5 block_rank5(const BlockRegs5& b, uint32_t r, uint32_t i, const uint32_t* sent_pos)
 {
-    uint32_t a = 0, c = 0, g = 0, t = 0;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        const uint32_t m = piece_mask(r, q);
-        const uint32_t x0 = b.p0[q], x1 = b.p1[q], x2 = b.p2[q];
-        a += popc32(~x0 & ~x1 & ~x2 & m);
-        c += popc32(x0 & ~x1 & m);
-        g += popc32(~x0 & x1 & m);
-        t += popc32(x0 & x1 & m);
-    }
+    const uint32_t m = piece_mask(r, 0);
+    const uint32_t x0 = b.p0, x1 = b.p1, x2 = b.p2;
+    const uint32_t a = popc32(~x0 & ~x1 & ~x2 & m);
+    const uint32_t c = popc32(x0 & ~x1 & m);
+    const uint32_t g = popc32(~x0 & x1 & m);
+    const uint32_t t = popc32(x0 & x1 & m);
     const uint32_t s_before = b.h[4] >> 8, s_in = b.h[4] & 0xffu;
     uint32_t s = 0;
     for (uint32_t k = 0; k < s_in; ++k) s += sent_pos[s_before + k] < i;
@@ -452,7 +457,8 @@ GMB_HD Children<SIGMA> expand_node(const MapCtx& cx, uint32_t dir, uint32_t x, u
         const uint32_t bx = x / kBlockBases5, by = y / kBlockBases5;
         count_fetch(fetches, size, 1u + (by != bx));
         const BlockRegs5 rbx = load_block5(B + bx);
-        const BlockRegs5 rby = by != bx ? load_block5(B + by) : rbx;
+        BlockRegs5 rby = rbx;
+        load_block5_if(rby, B + by, by != bx);
         const Ranks5 R0 = block_rank5(rbx, x - bx * kBlockBases5, x, SP);
         const Ranks5 R1 = block_rank5(rby, y - by * kBlockBases5, y, SP);
 #pragma unroll

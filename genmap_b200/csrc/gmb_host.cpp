@@ -234,7 +234,7 @@ void pack_bwt_blocks5(const uint8_t* bwt, uint64_t n, RankBlock5* blocks, uint32
             }
             const uint32_t c = s - 2u;
             ++cnt[c];
-            for (int pl = 0; pl < 3; ++pl) B.plane[pl][k >> 5] |= ((c >> pl) & 1u) << (k & 31);
+            for (int pl = 0; pl < 3; ++pl) B.plane[pl] |= ((c >> pl) & 1u) << k;
         }
         B.sent = (sent_before << 8) | (n_sent - sent_before);
     }

@@ -47,24 +47,25 @@ struct alignas(kBlockBytes) RankBlock {
 static_assert(sizeof(RankBlock) == kBlockBytes, "rank block size");
 static_assert(kBlockWords == 1 || kBlockWords == 3, "supported layouts: 32-byte and 64-byte blocks");
 
-// ---- Dna5 rank block (genomes containing N): 64 bytes, 96 BWT symbols, three bit planes ----------------
+// ---- Dna5 rank block (genomes containing N): 32 bytes, 32 BWT symbols, three bit planes ----------------
 // codes A=0 C=1 G=2 T=3 N=4 (plane 2 set only for N); counters for A,C,G,T, N is derived:
 // N(i) = i - A - C - G - T - $.  Sentinel rows as in the Dna4 block (code 0 + side list).
-constexpr uint32_t kBlockBases5 = 96;
-struct alignas(64) RankBlock5 {
+// Like the Dna4 block it is ONE 32-byte sector = one memory request per rank boundary: the path is bound by the
+// request rate, not by bytes (the first Dna5 layout, 64 bytes / 96 symbols = two requests per boundary, ran
+// 3x slower than Dna4 at E = 0: profiles/r01/s10_sweep_dna5.txt).  1 byte per symbol and direction.
+constexpr uint32_t kBlockBases5 = 32;
+struct alignas(32) RankBlock5 {
     uint32_t cnt[4];
     uint32_t sent;
-    uint32_t pad0;
-    uint32_t plane[3][3]; // [plane][32-symbol piece]
-    uint32_t pad1;
+    uint32_t plane[3]; // 32 symbols per plane
 };
-static_assert(sizeof(RankBlock5) == 64, "Dna5 rank block size");
+static_assert(sizeof(RankBlock5) == 32, "Dna5 rank block size");
 
 // ---- on-disk / in-HBM blob --------------------------------------------------------------------------
 // One contiguous, 256-byte aligned blob; offsets are relative to its start so the same bytes serve as
 // file, pinned host copy and device copy (copied verbatim, broadcast verbatim).
 constexpr uint64_t kMagic = 0x3130584449424d47ULL; // "GMBIDX01"
-constexpr uint32_t kVersion = 3 + 16 * kBlockWords; // the block layout is part of the format
+constexpr uint32_t kVersion = 4 + 16 * kBlockWords; // the block layouts are part of the format
 
 struct IndexHeader {
     uint64_t magic;

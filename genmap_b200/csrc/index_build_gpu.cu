@@ -198,7 +198,7 @@ __global__ void k_headers(uint32_t n_blocks, RankBlock* __restrict__ blocks, con
     blocks[b].sent = (cS[b] << 8) | (blocks[b].sent & 0xffu);
 }
 
-// Dna5 flavour of the two kernels above (RankBlock5: 96 symbols, three planes, counters for A,C,G,T)
+// Dna5 flavour of the two kernels above (RankBlock5: 32 symbols, three planes, counters for A,C,G,T)
 __global__ void k_pack_blocks5(const uint8_t* __restrict__ bwt, uint64_t n, uint32_t n_blocks, RankBlock5* __restrict__ blocks,
                                uint32_t* __restrict__ cA, uint32_t* __restrict__ cC, uint32_t* __restrict__ cG,
                                uint32_t* __restrict__ cT, uint32_t* __restrict__ cS)
@@ -208,25 +208,21 @@ __global__ void k_pack_blocks5(const uint8_t* __restrict__ bwt, uint64_t n, uint
     RankBlock5 B;
     uint32_t cnt[4] = {0, 0, 0, 0}, s = 0;
     const uint64_t base = (uint64_t)b * kBlockBases5;
-#pragma unroll
-    for (int piece = 0; piece < 3; ++piece) {
-        uint32_t p0 = 0, p1 = 0, p2 = 0;
-        for (int k = 0; k < 32; ++k) {
-            const uint64_t i = base + piece * 32 + k;
-            if (i >= n) break;
-            const uint32_t v = bwt[i];
-            if (v < 2) { ++s; continue; }
-            const uint32_t code = v - 2u;
-            cnt[0] += code == 0; cnt[1] += code == 1; cnt[2] += code == 2; cnt[3] += code == 3;
-            p0 |= (code & 1u) << k;
-            p1 |= ((code >> 1) & 1u) << k;
-            p2 |= (code >> 2) << k;
-        }
-        B.plane[0][piece] = p0; B.plane[1][piece] = p1; B.plane[2][piece] = p2;
+    uint32_t p0 = 0, p1 = 0, p2 = 0;
+    for (int k = 0; k < 32; ++k) {
+        const uint64_t i = base + k;
+        if (i >= n) break;
+        const uint32_t v = bwt[i];
+        if (v < 2) { ++s; continue; }
+        const uint32_t code = v - 2u;
+        cnt[0] += code == 0; cnt[1] += code == 1; cnt[2] += code == 2; cnt[3] += code == 3;
+        p0 |= (code & 1u) << k;
+        p1 |= ((code >> 1) & 1u) << k;
+        p2 |= (code >> 2) << k;
     }
+    B.plane[0] = p0; B.plane[1] = p1; B.plane[2] = p2;
     B.cnt[0] = B.cnt[1] = B.cnt[2] = B.cnt[3] = 0;
     B.sent = s;
-    B.pad0 = B.pad1 = 0;
     blocks[b] = B;
     cA[b] = cnt[0]; cC[b] = cnt[1]; cG[b] = cnt[2]; cT[b] = cnt[3]; cS[b] = s;
 }

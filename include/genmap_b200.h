@@ -64,7 +64,7 @@ typedef struct gmb_index_info {
     uint32_t n_seq;
     uint32_t has_sa;
     uint64_t blob_bytes;  /* size of the index blob in HBM */
-    uint64_t rank_block_bytes; /* 32 (Dna4: 64 symbols per block) or 64 (Dna5: 96 symbols per block) */
+    uint64_t rank_block_bytes; /* one 32-byte sector: 64 symbols (Dna4) or 32 symbols (Dna5) per block */
     void *device_blob;    /* device address of the blob (for broadcast / diagnostics) */
     int32_t device;
     int32_t alphabet_size; /* 4 = Dna4; 5 = Dna5, chosen when the text contains N (src/indexing.hpp:459-473) */
@@ -183,6 +183,29 @@ int gmb_map_locations(gmb_index *idx, const gmb_params *params, uint64_t text_be
                       const uint64_t (*intervals)[2], uint64_t n_intervals, uint64_t pos_begin,
                       uint64_t pos_end, uint64_t max_locations, gmb_locations *out);
 void gmb_locations_free(gmb_locations *locations);
+
+/* ---- runs: the frequency vector of one FASTA file, run-length encoded on the device ----------------------
+ * What the track writers consume (saveWig / saveBedGraph scan c for maximal runs of equal values inside every
+ * sequence, src/output.hpp:73-187).  Same arguments and semantics as gmb_map_frequencies_range, but instead of
+ * the vector the call returns its runs inside [pos_begin, pos_end): run r covers file-local positions
+ * [start[r], start[r+1]) (the last one ends at pos_end) and has value[r] (0 = not computed / tail, like c).
+ * A new run starts at every sequence start, so no run spans two sequences.  Only the runs leave the GPU
+ * (10 bytes per run instead of value_bits/8 bytes per position).  Released with gmb_runs_free(). */
+typedef struct gmb_runs {
+    uint64_t pos_begin, pos_end;
+    uint64_t n_runs;
+    uint64_t *start;   /* n_runs file-local start positions, ascending */
+    uint16_t *value;   /* n_runs values */
+    double kernel_ms;  /* the search kernel */
+    double rle_ms;     /* run detection + compaction on the device */
+} gmb_runs;
+
+int gmb_map_runs(gmb_index *idx, const gmb_params *params, uint64_t text_begin, uint64_t text_len,
+                 const uint64_t *chrom_cum_lengths, uint32_t n_chrom,
+                 const uint64_t (*intervals)[2], uint64_t n_intervals,
+                 const uint32_t *seq_to_file, uint32_t n_seq, uint64_t pos_begin, uint64_t pos_end,
+                 gmb_runs *out, gmb_map_stats *stats);
+void gmb_runs_free(gmb_runs *runs);
 
 #ifdef __cplusplus
 }

@@ -102,7 +102,7 @@ void hs_export_bwt(const void* blob, int rev, uint8_t* out)
             const RankBlock5& b = B[i / kBlockBases5];
             const uint32_t k = (uint32_t)(i % kBlockBases5);
             uint32_t c = 0;
-            for (int pl = 0; pl < 3; ++pl) c |= ((b.plane[pl][k >> 5] >> (k & 31)) & 1u) << pl;
+            for (int pl = 0; pl < 3; ++pl) c |= ((b.plane[pl] >> k) & 1u) << pl;
             out[i] = (uint8_t)(1 + c);
         }
     } else {

@@ -45,11 +45,15 @@ def test_index_and_writers_reproduce_golden_outputs(genmap, case, tmp_path):
     want = ["%s.fa;%d;%s" % (base, len(c), name) for base, recs in files for name, c in recs]
     assert ids == want
     n_checked = 0
-    for flav, flags in FLAVOURS.items():
+    # every flavour through the vector writers; the track formats once more from a run list shaped like the
+    # one the GPU returns (gmb_map_runs), which is what `map -w/-bg/-b` without -r/-t uses
+    todo = [(flav, flags, "") for flav, flags in FLAVOURS.items()]
+    todo += [(flav, flags + ["-xr"], "_runs") for flav, flags in FLAVOURS.items() if flav.startswith(("wig", "bed"))]
+    for flav, flags, tag in todo:
         gold_dir = os.path.join(folder, flav)
         if not os.path.isdir(gold_dir):
             continue
-        out = tmp_path / flav
+        out = tmp_path / (flav + tag)
         out.mkdir()
         for fi, (base, recs) in enumerate(files):
             # render from the golden raw vector of the same value type (freq16 for the float outputs)

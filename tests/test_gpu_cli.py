@@ -54,6 +54,21 @@ def _replay(genmap, case, tmp_path, host_builder=False, extra=()):
             assert not mismatch and not errors, (case, vt, fmt, mismatch, errors)
             n += len(match)
         assert set(os.listdir(str(out))) == expected, (case, vt, set(os.listdir(str(out))) ^ expected)
+    # only track formats: the runs come from the GPU (gmb_map_runs), the vector never reaches the host
+    for vt, vflags in VALUE_TYPES.items():
+        golden = {fmt: os.path.join(folder, "%s_%s" % (fmt, vt)) for fmt in ("wig", "bed")}
+        golden = {fmt: d for fmt, d in golden.items() if os.path.isdir(d)}
+        if not golden:
+            continue
+        out = tmp_path / ("out_runs_%s_%s%s" % (vt, "".join(extra), "h" if host_builder else ""))
+        out.mkdir()
+        r = subprocess.run([genmap, "map", "-I", idx, "-O", str(out)] + base_flags + vflags + [FORMATS[f] for f in golden] + list(extra),
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        for fmt, d in golden.items():
+            names = os.listdir(d)
+            match, mismatch, errors = filecmp.cmpfiles(d, str(out), names, shallow=False)
+            assert not mismatch and not errors, (case, vt, fmt, "device runs", mismatch, errors)
     # csv (`-d`, tests/CMakeLists.txt:52-53): its own map call, like the reference's test matrix
     golden = os.path.join(folder, "csv")
     out = tmp_path / ("out_csv_%s%s" % ("".join(extra), "h" if host_builder else ""))
@@ -130,6 +145,13 @@ def test_cli_multi_gpu_sharding_gives_identical_files(genmap, tmp_path):
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         outs.append(out)
+        # device runs, one slice per GPU merged on the host: the same bedgraph
+        out2 = tmp_path / ("out%d_runs" % n)
+        out2.mkdir()
+        r = subprocess.run([genmap, "map", "-I", idx, "-O", str(out2), "-K", "30", "-E", "1", "-fl", "-bg", "-w", "-xg", str(n)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert filecmp.cmp(str(out / "g.genmap.bedgraph"), str(out2 / "g.genmap.bedgraph"), shallow=False)
     for name in os.listdir(str(outs[0])):
         assert filecmp.cmp(str(outs[0] / name), str(outs[1] / name), shallow=False), name
 

@@ -108,7 +108,7 @@ def test_cuda_dna5_matches_oracle(gm, K, E):
     seqs[2][-5:] = 4
     _, limits = T.concat(seqs)
     orc, ix = T.Oracle(seqs), gm.Index.build(seqs)
-    assert ix.info.alphabet_size == 5 and ix.info.rank_block_bytes == 64
+    assert ix.info.alphabet_size == 5 and ix.info.rank_block_bytes == 32
     for rc in (True, False):
         want = orc.map(K, E, revcompl=rc)
         for B in (1, 3, 0):
@@ -412,3 +412,43 @@ def test_cuda_locations_need_the_suffix_array(gm):
     with pytest.raises(gm.GenmapError) as e:
         ix.compute_locations(gm.SearchParams(12, 0))
     assert "suffix array" in str(e.value)
+
+
+# ---- runs (device run-length encoding for the track writers): gmb_map_runs -------------------------------------
+def _host_runs(c, cum, b, e):
+    cum = np.asarray(cum, dtype=np.int64)
+    head = np.ones(e - b, dtype=bool)
+    head[1:] = c[b + 1:e] != c[b:e - 1]
+    inside = cum[(cum > b) & (cum < e)] - b
+    head[inside] = True
+    start = np.nonzero(head)[0] + b
+    return start.astype(np.uint64), c[start].astype(np.uint16)
+
+
+@pytest.mark.parametrize("bits", [16, 8])
+def test_cuda_runs_equal_host_scan_of_the_vector(gm, bits):
+    seqs = T.repeat_rich(9, 5, 3000) + [np.array([0, 1, 2], np.uint8)] + T.repeat_rich(10, 2, 40)
+    _, limits = T.concat(seqs)
+    ix = gm.Index.build(seqs)
+    n = int(limits[-1])
+    for K, E, iv in ((12, 0, None), (16, 1, None), (10, 2, [(50, 4000), (9000, 9100)])):
+        p = gm.SearchParams(K, E, value_bits=bits)
+        c = ix.compute_mappability(p, intervals=iv)
+        for b, e in ((0, n), (777, 9001), (3000, 3001)):
+            start, value = ix.compute_runs(p, pos_begin=b, pos_end=e, intervals=iv)
+            ws, wv = _host_runs(c, limits, b, e)
+            assert np.array_equal(start, ws) and np.array_equal(value, wv), (K, E, b, e)
+
+
+def test_cuda_runs_on_a_larger_genome_roundtrip(gm):
+    """size-independent property: expanding the runs gives back the vector"""
+    seqs = gm.synth_genome(3_000_000, 4, 17)
+    _, limits = T.concat(seqs)
+    ix = gm.Index.build(seqs)
+    p = gm.SearchParams(30, 1)
+    c = ix.compute_mappability(p)
+    start, value = ix.compute_runs(p)
+    assert len(start) < len(c) // 4
+    ends = np.append(start[1:], len(c)).astype(np.int64)
+    assert np.array_equal(np.repeat(value, ends - start.astype(np.int64)), c)
+    assert np.isin(np.asarray(limits[:-1], dtype=np.uint64), start).all()
