@@ -41,11 +41,28 @@ public:
         while (n) std::fputc(buf[--n], f_);
     }
     void flt(float v) { std::fprintf(f_, "%g", (double)v); }
+    // 1/v as the reference prints it (operator<< of a float: %g), from a table: only 65536 different values exist
+    void inverse(uint32_t v)
+    {
+        struct Table {
+            std::vector<char> text; // 16 bytes per value: length, then the characters
+            Table() : text(16u << 16)
+            {
+                for (uint32_t x = 0; x < (1u << 16); ++x) {
+                    const float f = x != 0 ? 1.0f / static_cast<float>(x) : 0.0f;
+                    text[16 * x] = (char)std::snprintf(&text[16 * x + 1], 15, "%g", (double)f);
+                }
+            }
+        };
+        static const Table table;
+        if (v >= (1u << 16)) { flt(1.0f / static_cast<float>(v)); return; }
+        std::fwrite(&table.text[16 * v + 1], 1, (size_t)table.text[16 * v], f_);
+    }
     void bytes(const void* p, size_t n) { std::fwrite(p, 1, n, f_); }
     template <class T>
     void value(T v, bool mappability) // a frequency, or its inverse as float (0 stays 0)
     {
-        if (mappability) flt(v != 0 ? 1.0f / static_cast<float>(v) : 0.0f);
+        if (mappability) inverse((uint32_t)v);
         else u64(v);
     }
 private:

@@ -266,8 +266,12 @@ struct Pattern {
     GMB_HD bool has_n(uint32_t a, uint32_t d) const
     {
         if constexpr (SIGMA == 5) {
-            for (uint32_t i = a; i < a + d; ++i)
-                if ((nm[KW == 1 ? 0 : (i >> 5)] >> (i & 31)) & 1u) return true;
+            const uint32_t m = (1u << d) - 1u; // d <= 16
+            if (KW == 1) return ((nm[0] >> a) & m) != 0;
+            const uint32_t wi = a >> 5, sh = a & 31u;
+            uint32_t v = nm[wi] >> sh;
+            if (sh && wi + 1 < (uint32_t)KW) v |= nm[wi + 1] << (32u - sh);
+            return (v & m) != 0;
         }
         return false;
     }
@@ -297,12 +301,23 @@ struct Pattern {
     // in place: the reverse complement of the K-character pattern (src/algo.hpp:284-305)
     GMB_HD void reverse_complement(uint32_t K)
     {
-        if constexpr (SIGMA == 5) { // N stays N: reverse the mask over the K characters
-            uint32_t out[KW];
-            for (int k = 0; k < KW; ++k) out[k] = 0;
-            for (uint32_t i = 0; i < K; ++i)
-                if ((nm[KW == 1 ? 0 : (i >> 5)] >> (i & 31)) & 1u) { const uint32_t j = K - 1 - i; out[KW == 1 ? 0 : (j >> 5)] |= 1u << (j & 31); }
-            for (int k = 0; k < KW; ++k) nm[k] = out[k];
+        if constexpr (SIGMA == 5) { // N stays N: reverse the mask over the K characters (bit i -> bit K-1-i)
+            if constexpr (KW == 1) {
+                nm[0] = reverse_bits32(nm[0]) >> (32u - K);
+            } else {
+                uint32_t y[KW + 1];
+#pragma unroll
+                for (int k = 0; k < KW; ++k) y[k] = reverse_bits32(nm[KW - 1 - k]);
+                y[KW] = 0;
+                const uint32_t sft = 32u * KW - K, ws = sft >> 5, bs = sft & 31u; // drop the 32*KW - K unused low bits
+#pragma unroll
+                for (int k = 0; k < KW; ++k) {
+                    const uint32_t a = k + ws;
+                    uint32_t v = a <= (uint32_t)KW ? y[a < (uint32_t)KW ? a : KW] >> bs : 0u;
+                    if (bs && a + 1 <= (uint32_t)KW) v |= y[a + 1] << (32u - bs);
+                    nm[k] = v;
+                }
+            }
         }
         if constexpr (KW == 1) { // registers only
             w[0] = reverse_groups64(~w[0]) >> (64u - 2u * K);

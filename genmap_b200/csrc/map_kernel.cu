@@ -24,8 +24,8 @@ namespace {
 template <int KW, bool COUNT, typename OutT, bool EP>
 cudaError_t launch_t(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
-    // Dna5 indices always run the blocked instantiation (it covers B == 1) to keep the number of kernels down
-    if (L.sigma == 5) return launch_b<KW, COUNT, OutT, EP, true, 5>(L, sm_count, stream);
+    if (L.sigma == 5)
+        return L.cx.B > 1 ? launch_b<KW, COUNT, OutT, EP, true, 5>(L, sm_count, stream) : launch_b<KW, COUNT, OutT, EP, false, 5>(L, sm_count, stream);
     return L.cx.B > 1 ? launch_b<KW, COUNT, OutT, EP, true, 4>(L, sm_count, stream) : launch_b<KW, COUNT, OutT, EP, false, 4>(L, sm_count, stream);
 }
 

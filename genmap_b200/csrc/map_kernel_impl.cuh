@@ -11,6 +11,9 @@ constexpr int kThreads = 256;
 #ifndef GMB_MIN_BLOCKS
 #define GMB_MIN_BLOCKS 4 // resident CTAs per SM the register allocation must allow
 #endif
+#ifndef GMB_MIN_BLOCKS5
+#define GMB_MIN_BLOCKS5 3 // Dna5 indices, blocked instantiation (five-way children, 12-word frames): 3 CTAs / 80 registers
+#endif                    // measured best (profiles/r01/s15_sweep_dna5_*.txt); the one-k-mer instantiation fits 64 like Dna4
 
 template <int FW> // words per mismatch frame (10 for Dna4, 12 for Dna5)
 struct SmemFrames {
@@ -26,7 +29,7 @@ __host__ __device__ inline uint32_t align32(uint32_t x) { return (x + 31u) & ~31
 constexpr uint32_t kStartWords = sizeof(SearchStart) / 4;
 
 template <int KW, bool COUNT, typename OutT, bool EP, bool BLK, int SIGMA, bool LOC = false>
-__global__ void __launch_bounds__(kThreads, SIGMA == 5 ? 2 : GMB_MIN_BLOCKS) map_kernel(const MapLaunch L)
+__global__ void __launch_bounds__(kThreads, (SIGMA == 5 && BLK) ? GMB_MIN_BLOCKS5 : GMB_MIN_BLOCKS) map_kernel(const MapLaunch L)
 {
     // shared memory: step tables | jump-table starts | offsets | per-chain frame store
     extern __shared__ uint32_t smem[];

@@ -217,7 +217,7 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
 #define RUN_KS(KW, BLK, SG) (ep ? run_ranges<KW, true, BLK, SG>(cx, text, nmask, text_begin, ranges, value_bits, out, &f, &lr) \
                                 : run_ranges<KW, false, BLK, SG>(cx, text, nmask, text_begin, ranges, value_bits, out, &f, &lr))
 #define RUN_KB(KW, BLK) (sigma == 5 ? RUN_KS(KW, BLK, 5) : RUN_KS(KW, BLK, 4))
-#define RUN_KW(KW) ((B > 1 || sigma == 5) ? RUN_KB(KW, true) : RUN_KB(KW, false))
+#define RUN_KW(KW) (B > 1 ? RUN_KB(KW, true) : RUN_KB(KW, false))
     const uint32_t needle = K + B - 1; // characters a chain keeps in registers
     if (needle <= 32) RUN_KW(1);
     else if (needle <= 64) RUN_KW(2);
