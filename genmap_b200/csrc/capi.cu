@@ -393,6 +393,12 @@ int gmb_index_set_jump_depth(gmb_index* ix, int depth)
 
 // stats != nullptr && timed: bracket the kernel with events and wait for it; stats != nullptr && !timed: only
 // fill the host-side fields (positions, jump depth) and return without synchronising
+namespace {
+int ep_many_files(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len, const uint64_t* chrom_cum,
+                  uint32_t n_chrom, const uint64_t (*intervals)[2], uint64_t n_intervals, const uint32_t* seq_to_file,
+                  uint32_t n_seq, uint64_t pos_begin, uint64_t pos_end, void* out_device, gmb_map_stats* stats);
+}
+
 // One pass of the locate path (gmb_map_locations): counting (rows == nullptr: out_device receives two uint32 list
 // lengths per position of [pos0, ...)) or filling (rows / off set).
 struct LocPass {
@@ -423,7 +429,11 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
         if (!ix->h.off_sa) return fail(GMB_ERR_UNSUPPORTED, "--exclude-pseudo needs an index built with the full suffix array (genmap index -xs / GMB_BUILD_WITH_SA)");
         if (!seq_to_file || n_seq != ix->h.n_seq) return fail(GMB_ERR_ARG, "--exclude-pseudo needs seq_to_file for every indexed sequence");
         for (uint32_t s = 0; s < n_seq; ++s) n_files = std::max(n_files, seq_to_file[s] + 1);
-        if (n_files > 64) return fail(GMB_ERR_UNSUPPORTED, "--exclude-pseudo supports at most 64 FASTA files on the GPU path");
+        if (n_files > 64) { // more files than the kernel's 64-bit file mask holds: locate + distinct-file count
+            if (cuda_stream) return fail(GMB_ERR_UNSUPPORTED, "--exclude-pseudo with more than 64 FASTA files runs on the default stream only");
+            return ep_many_files(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, seq_to_file, n_seq,
+                                 pos_begin, pos_end, out_device, stats);
+        }
         if (p->count_fetches) return fail(GMB_ERR_UNSUPPORTED, "count_fetches is not available with --exclude-pseudo");
         uint32_t s0 = 0; // the sequence containing text_begin tells which file is being mapped
         while (s0 + 1 < n_seq && ix->limits[s0 + 1] <= text_begin) ++s0;
@@ -611,7 +621,10 @@ int gmb_map_frequencies_range(gmb_index* ix, const gmb_params* p, uint64_t text_
     gmb_map_stats local;
     std::memset(&local, 0, sizeof(local));
     const uint64_t piece = 32ull << 20; // positions per pipeline stage
-    if (p->count_fetches || pos_end - pos_begin <= piece) {
+    bool many_files = false; // --exclude-pseudo beyond 64 files runs unpipelined on the default stream (ep_many_files)
+    if (p->exclude_pseudo && seq_to_file)
+        for (uint32_t s2 = 0; s2 < n_seq && !many_files; ++s2) many_files = seq_to_file[s2] >= 64;
+    if (p->count_fetches || many_files || pos_end - pos_begin <= piece) {
         CU(cudaMemsetAsync(ix->d_out, 0, bytes, nullptr));
         int rc = map_device_impl(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, seq_to_file, n_seq,
                                  pos_begin, pos_end, biased, nullptr, &local, true);
@@ -685,6 +698,114 @@ void gmb_locations_free(gmb_locations* L)
     L->offsets = nullptr; L->loc = nullptr; L->n_locations = 0;
 }
 
+} // extern "C"
+
+namespace {
+// The sorted occurrence lists of the positions [pos_begin, pos_begin + m) on the device (the two search passes,
+// the scan and the segmented sort of locate_kernel.cu); list offsets also on the host.
+struct LocatePiece {
+    DevBuf counts, offs, rows, sorted;
+    uint64_t m = 0, n_rows = 0;
+    uint64_t* h_off = nullptr; // 2 * npos + 1 offsets (only the first 2 * m + 1 belong to the piece); malloc'ed
+    double kernel_ms = 0;
+    ~LocatePiece() { std::free(h_off); }
+};
+
+int locate_piece(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len, const uint64_t* chrom_cum,
+                 uint32_t n_chrom, const uint64_t (*intervals)[2], uint64_t n_intervals, uint64_t pos_begin,
+                 uint64_t pos_end, uint64_t max_locations, LocatePiece& P)
+{
+    const uint64_t kMaxPositions = 4ull << 20, kMaxRows = 1ull << 30;
+    if (pos_end - pos_begin > kMaxPositions) pos_end = pos_begin + kMaxPositions;
+    if (max_locations == 0) max_locations = 64ull << 20;
+    if (max_locations > kMaxRows) max_locations = kMaxRows;
+    CU(cudaSetDevice(ix->device));
+    const uint64_t npos = pos_end - pos_begin, n_lists = 2 * npos;
+
+    // pass 1: list lengths, then their prefix sums
+    DevBuf temp;
+    CU(P.counts.alloc((n_lists + 1) * 4));
+    CU(P.offs.alloc((n_lists + 1) * 8));
+    CU(cudaMemsetAsync(P.counts.p, 0, (n_lists + 1) * 4, nullptr));
+    gmb_map_stats st1, st2;
+    std::memset(&st2, 0, sizeof(st2));
+    LocPass pass1{nullptr, nullptr, pos_begin};
+    int rc = map_device_impl(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, nullptr, 0, pos_begin,
+                             pos_end, P.counts.p, nullptr, &st1, true, &pass1);
+    if (rc != GMB_OK) return rc;
+    size_t temp_bytes = 0;
+    CU(locate_scan_counts(P.counts.as<uint32_t>(), n_lists, P.offs.as<uint64_t>(), nullptr, temp_bytes, nullptr));
+    CU(temp.alloc(temp_bytes));
+    CU(locate_scan_counts(P.counts.as<uint32_t>(), n_lists, P.offs.as<uint64_t>(), temp.p, temp_bytes, nullptr));
+    P.h_off = static_cast<uint64_t*>(std::malloc((n_lists + 1) * 8));
+    if (!P.h_off) return fail(GMB_ERR_NOMEM, "out of host memory");
+    CU(cudaMemcpy(P.h_off, P.offs.p, (n_lists + 1) * 8, cudaMemcpyDeviceToHost));
+
+    // keep as many whole positions as fit into max_locations (always at least one)
+    uint64_t m = npos;
+    if (P.h_off[n_lists] > max_locations) {
+        uint64_t lo = 1, hi = npos; // largest m with h_off[2m] <= max_locations, at least 1
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi + 1) / 2;
+            if (P.h_off[2 * mid] <= max_locations) lo = mid; else hi = mid - 1;
+        }
+        m = lo;
+    }
+    P.m = m;
+    P.n_rows = P.h_off[2 * m];
+    if (P.n_rows > (1ull << 31)) return fail(GMB_ERR_UNSUPPORTED, "a single k-mer has more than 2^31 occurrences");
+    if (P.n_rows) {
+        // pass 2: the same search writes the SA value of every occurrence; then every list is sorted
+        DevBuf temp2;
+        CU(P.rows.alloc(P.n_rows * 4));
+        CU(P.sorted.alloc(P.n_rows * 4));
+        LocPass pass2{P.offs.as<uint64_t>(), P.rows.as<uint32_t>(), pos_begin};
+        rc = map_device_impl(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, nullptr, 0, pos_begin,
+                             pos_begin + m, P.counts.p, nullptr, &st2, true, &pass2);
+        if (rc != GMB_OK) return rc;
+        size_t tb = 0;
+        CU(locate_sort_lists(P.rows.as<uint32_t>(), P.sorted.as<uint32_t>(), P.n_rows, P.offs.as<uint64_t>(), 2 * m, nullptr, tb, nullptr));
+        CU(temp2.alloc(tb));
+        CU(locate_sort_lists(P.rows.as<uint32_t>(), P.sorted.as<uint32_t>(), P.n_rows, P.offs.as<uint64_t>(), 2 * m, temp2.p, tb, nullptr));
+        CU(cudaStreamSynchronize(nullptr)); // temp2 is released on return
+    }
+    P.kernel_ms = st1.kernel_ms + st2.kernel_ms;
+    return GMB_OK;
+}
+
+// --exclude-pseudo with more FASTA files than the 64-bit file mask of the search kernel holds: locate every
+// occurrence (locate_piece) and count the distinct files of each k-mer's two sorted lists on the device.
+int ep_many_files(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len, const uint64_t* chrom_cum,
+                  uint32_t n_chrom, const uint64_t (*intervals)[2], uint64_t n_intervals, const uint32_t* seq_to_file,
+                  uint32_t n_seq, uint64_t pos_begin, uint64_t pos_end, void* out_device, gmb_map_stats* stats)
+{
+    for (uint32_t s = 1; s < n_seq; ++s)
+        if (seq_to_file[s] < seq_to_file[s - 1])
+            return fail(GMB_ERR_UNSUPPORTED, "--exclude-pseudo with more than 64 FASTA files needs file ids that do not decrease along the sequences");
+    CU(cudaSetDevice(ix->device));
+    if (!ix->d_seq_to_file) CU(cudaMalloc(&ix->d_seq_to_file, (size_t)ix->h.n_seq * 4));
+    CU(cudaMemcpy(ix->d_seq_to_file, seq_to_file, (size_t)n_seq * 4, cudaMemcpyHostToDevice));
+    if (pos_end > text_len) pos_end = text_len;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    gmb_params q = *p;
+    q.exclude_pseudo = 0;
+    for (uint64_t b = pos_begin; b < pos_end;) {
+        LocatePiece P;
+        int rc = locate_piece(ix, &q, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, b, pos_end, 0, P);
+        if (rc != GMB_OK) return rc;
+        CU(locate_distinct_files(P.sorted.as<uint32_t>(), P.offs.as<uint64_t>(), P.m, reinterpret_cast<const uint32_t*>(ix->d_blob + ix->h.off_seq_start),
+                                 ix->h.n_seq, ix->d_seq_to_file, out_device, p->value_bits, b, nullptr));
+        CU(cudaStreamSynchronize(nullptr));
+        if (stats) { stats->kernel_ms += P.kernel_ms; stats->kernel_launches += 3; }
+        b += P.m;
+    }
+    if (stats) stats->positions = pos_end - pos_begin;
+    return GMB_OK;
+}
+} // namespace
+
+extern "C" {
+
 int gmb_map_locations(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len,
                       const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t (*intervals)[2],
                       uint64_t n_intervals, uint64_t pos_begin, uint64_t pos_end, uint64_t max_locations,
@@ -694,74 +815,26 @@ int gmb_map_locations(gmb_index* ix, const gmb_params* p, uint64_t text_begin, u
     std::memset(out, 0, sizeof(*out));
     if (pos_end > text_len) pos_end = text_len;
     if (pos_begin >= pos_end) return fail(GMB_ERR_ARG, "gmb_map_locations: empty position range");
-    const uint64_t kMaxPositions = 4ull << 20, kMaxRows = 1ull << 30;
-    if (pos_end - pos_begin > kMaxPositions) pos_end = pos_begin + kMaxPositions;
-    if (max_locations == 0) max_locations = 64ull << 20;
-    if (max_locations > kMaxRows) max_locations = kMaxRows;
-    CU(cudaSetDevice(ix->device));
-    const uint64_t npos = pos_end - pos_begin, n_lists = 2 * npos;
-
-    // pass 1: list lengths, then their prefix sums
-    DevBuf counts, offs, temp;
-    CU(counts.alloc((n_lists + 1) * 4));
-    CU(offs.alloc((n_lists + 1) * 8));
-    CU(cudaMemsetAsync(counts.p, 0, (n_lists + 1) * 4, nullptr));
-    gmb_map_stats st1, st2;
-    std::memset(&st2, 0, sizeof(st2));
-    LocPass pass1{nullptr, nullptr, pos_begin};
-    int rc = map_device_impl(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, nullptr, 0, pos_begin,
-                             pos_end, counts.p, nullptr, &st1, true, &pass1);
+    LocatePiece P;
+    int rc = locate_piece(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, pos_begin, pos_end, max_locations, P);
     if (rc != GMB_OK) return rc;
-    size_t temp_bytes = 0;
-    CU(locate_scan_counts(counts.as<uint32_t>(), n_lists, offs.as<uint64_t>(), nullptr, temp_bytes, nullptr));
-    CU(temp.alloc(temp_bytes));
-    CU(locate_scan_counts(counts.as<uint32_t>(), n_lists, offs.as<uint64_t>(), temp.p, temp_bytes, nullptr));
-    uint64_t* h_off = static_cast<uint64_t*>(std::malloc((n_lists + 1) * 8));
-    if (!h_off) return fail(GMB_ERR_NOMEM, "out of host memory");
-    cudaError_t e = cudaMemcpy(h_off, offs.p, (n_lists + 1) * 8, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) { std::free(h_off); return cuda_fail(e, "cudaMemcpy(list offsets)"); }
-
-    // keep as many whole positions as fit into max_locations (always at least one)
-    uint64_t m = npos;
-    if (h_off[n_lists] > max_locations) {
-        uint64_t lo = 1, hi = npos; // largest m with h_off[2m] <= max_locations, at least 1
-        while (lo < hi) {
-            const uint64_t mid = (lo + hi + 1) / 2;
-            if (h_off[2 * mid] <= max_locations) lo = mid; else hi = mid - 1;
-        }
-        m = lo;
-    }
-    const uint64_t n_rows = h_off[2 * m];
-    if (n_rows > (1ull << 31)) { std::free(h_off); return fail(GMB_ERR_UNSUPPORTED, "a single k-mer has more than 2^31 occurrences"); }
-    gmb_location* h_loc = static_cast<gmb_location*>(std::malloc(n_rows ? n_rows * sizeof(gmb_location) : 1));
-    if (!h_loc) { std::free(h_off); return fail(GMB_ERR_NOMEM, "out of host memory"); }
-    auto bail = [&](int code) { std::free(h_off); std::free(h_loc); return code; };
-
-    if (n_rows) {
-        // pass 2: the same search writes the SA value of every occurrence; sort every list; positions -> (seq, offset)
-        DevBuf rows, sorted, loc, temp2;
-        if ((e = rows.alloc(n_rows * 4)) != cudaSuccess || (e = sorted.alloc(n_rows * 4)) != cudaSuccess ||
-            (e = loc.alloc(n_rows * sizeof(gmb_location))) != cudaSuccess)
-            return bail(cuda_fail(e, "cudaMalloc(locations)"));
-        LocPass pass2{offs.as<uint64_t>(), rows.as<uint32_t>(), pos_begin};
-        rc = map_device_impl(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, nullptr, 0, pos_begin,
-                             pos_begin + m, counts.p, nullptr, &st2, true, &pass2);
-        if (rc != GMB_OK) return bail(rc);
-        size_t tb = 0;
-        if ((e = locate_sort_lists(rows.as<uint32_t>(), sorted.as<uint32_t>(), n_rows, offs.as<uint64_t>(), 2 * m, nullptr, tb, nullptr)) != cudaSuccess ||
-            (e = temp2.alloc(tb)) != cudaSuccess ||
-            (e = locate_sort_lists(rows.as<uint32_t>(), sorted.as<uint32_t>(), n_rows, offs.as<uint64_t>(), 2 * m, temp2.p, tb, nullptr)) != cudaSuccess ||
-            (e = locate_convert(sorted.as<uint32_t>(), n_rows, reinterpret_cast<const uint32_t*>(ix->d_blob + ix->h.off_seq_start),
-                                ix->h.n_seq, loc.p, nullptr)) != cudaSuccess ||
-            (e = cudaMemcpy(h_loc, loc.p, n_rows * sizeof(gmb_location), cudaMemcpyDeviceToHost)) != cudaSuccess)
-            return bail(cuda_fail(e, "locations"));
+    gmb_location* h_loc = static_cast<gmb_location*>(std::malloc(P.n_rows ? P.n_rows * sizeof(gmb_location) : 1));
+    if (!h_loc) return fail(GMB_ERR_NOMEM, "out of host memory");
+    if (P.n_rows) { // positions inside T -> (sequence, offset)
+        DevBuf loc;
+        cudaError_t e = loc.alloc(P.n_rows * sizeof(gmb_location));
+        if (e == cudaSuccess) e = locate_convert(P.sorted.as<uint32_t>(), P.n_rows, reinterpret_cast<const uint32_t*>(ix->d_blob + ix->h.off_seq_start),
+                                                 ix->h.n_seq, loc.p, nullptr);
+        if (e == cudaSuccess) e = cudaMemcpy(h_loc, loc.p, P.n_rows * sizeof(gmb_location), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { std::free(h_loc); return cuda_fail(e, "locations"); }
     }
     out->pos_begin = pos_begin;
-    out->pos_end = pos_begin + m;
-    out->n_locations = n_rows;
-    out->offsets = h_off;
+    out->pos_end = pos_begin + P.m;
+    out->n_locations = P.n_rows;
+    out->offsets = P.h_off;
+    P.h_off = nullptr; // ownership moves to the caller
     out->loc = h_loc;
-    out->kernel_ms = st1.kernel_ms + st2.kernel_ms;
+    out->kernel_ms = P.kernel_ms;
     return GMB_OK;
 }
 

@@ -290,7 +290,7 @@ const char* kMapHelp =
     "  -I, --index   -O, --output   -K, --length   -E, --errors (0..4)   -S, --selection\n"
     "  -nc, --no-reverse-complement   -ep, --exclude-pseudo   -fs, --frequency-small   -fl, --frequency-large\n"
     "  -r, --raw   -t, --txt   -w, --wig   -bg, --bedgraph   -d, --csv   -m, --memory-mapping (ignored)\n"
-    "  -T, --threads (host writers only)   -v, --verbose\n"
+    "  -T, --threads (host threads formatting the txt output; default: all)   -v, --verbose\n"
     "  -xg, --gpus N   range-partition the positions of every FASTA file over N GPUs (index replicated; default 1)\n";
 
 struct IdRow { std::string file; uint64_t length; std::string name; };
@@ -583,7 +583,8 @@ int map_main(int argc, char const** argv)
             }
             std::string prefix = out_path;
             if (!includes_filename) prefix += rows[i].file.substr(0, rows[i].file.find_last_of('.')) + ".genmap"; // :76-78
-            gmbcli::Outputs o{raw, txt, wig, bg, bed, a.has("verbose")};
+            gmbcli::Outputs o{raw, txt, wig, bg, bed, a.has("verbose"),
+                              (unsigned)(a.has("threads") ? std::max<uint64_t>(1, T) : std::max(1u, std::thread::hardware_concurrency()))};
             if (!want_freq) {}
             else if (device_runs)
                 gmbcli::write_track_outputs(gmbcli::ListRuns{run_start.data(), run_value.data(), run_start.size(), cum}, prefix, names, lens, otype, o);
@@ -634,7 +635,7 @@ int render_main(int argc, char const** argv)
     if (!in.read(reinterpret_cast<char*>(buf.data()), (std::streamsize)buf.size())) { std::cerr << "ERROR: short counts file\n"; return 1; }
     const gmbcli::OutputType otype = a.has("frequency-small") ? gmbcli::OutputType::frequency_small
                                    : a.has("frequency-large") ? gmbcli::OutputType::frequency_large : gmbcli::OutputType::mappability;
-    gmbcli::Outputs o{a.has("raw"), a.has("txt"), a.has("wig"), a.has("bedgraph"), a.has("bed"), false};
+    gmbcli::Outputs o{a.has("raw"), a.has("txt"), a.has("wig"), a.has("bedgraph"), a.has("bed"), false, 3u};
     if (a.has("via-runs")) { // the track writers fed from a run list shaped like gmb_map_runs' (a run starts at every sequence start)
         const std::vector<uint64_t> cum = gmbcli::cumulative(lens);
         std::vector<uint64_t> st;

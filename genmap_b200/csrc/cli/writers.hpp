@@ -10,13 +10,14 @@
 #include <cstdio>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace gmbcli {
 
 enum class OutputType { mappability, frequency_small, frequency_large };
 
-struct Outputs { bool raw, txt, wig, bedgraph, bed, verbose; };
+struct Outputs { bool raw, txt, wig, bedgraph, bed, verbose; unsigned threads = 1; };
 
 inline double now_s()
 {
@@ -44,8 +45,14 @@ public:
     // 1/v as the reference prints it (operator<< of a float: %g), from a table: only 65536 different values exist
     void inverse(uint32_t v)
     {
+        if (v >= (1u << 16)) { flt(1.0f / static_cast<float>(v)); return; }
+        const char* t = inverse_text(v);
+        std::fwrite(t + 1, 1, (size_t)t[0], f_);
+    }
+    static const char* inverse_text(uint32_t v) // 16 bytes per value: length, then the characters
+    {
         struct Table {
-            std::vector<char> text; // 16 bytes per value: length, then the characters
+            std::vector<char> text;
             Table() : text(16u << 16)
             {
                 for (uint32_t x = 0; x < (1u << 16); ++x) {
@@ -55,8 +62,7 @@ public:
             }
         };
         static const Table table;
-        if (v >= (1u << 16)) { flt(1.0f / static_cast<float>(v)); return; }
-        std::fwrite(&table.text[16 * v + 1], 1, (size_t)table.text[16 * v], f_);
+        return &table.text[16 * v];
     }
     void bytes(const void* p, size_t n) { std::fwrite(p, 1, n, f_); }
     template <class T>
@@ -129,18 +135,55 @@ void write_raw(const T* c, uint64_t n, const std::string& path, bool mappability
     }
 }
 
+// values [begin, end) of one sequence as text, separated by single spaces (no leading / trailing separator)
+template <class T>
+void format_values(const T* c, uint64_t begin, uint64_t end, bool mappability, std::string& out)
+{
+    out.clear();
+    out.reserve((end - begin) * (mappability ? 6 : 3));
+    char buf[24];
+    for (uint64_t i = begin; i < end; ++i) {
+        if (i != begin) out.push_back(' ');
+        const uint32_t v = (uint32_t)c[i];
+        if (mappability) {
+            const char* t = Sink::inverse_text(v);
+            out.append(t + 1, (size_t)t[0]);
+        } else {
+            int n = 0;
+            uint32_t x = v;
+            do { buf[n++] = (char)('0' + x % 10); x /= 10; } while (x);
+            while (n) out.push_back(buf[--n]);
+        }
+    }
+}
+
+// src/output.hpp:40-69: '>' name, then the values of the sequence separated by single spaces.  Formatting is the
+// cost (one number per position): `threads` workers format consecutive chunks, the file is written in order.
 template <class T>
 void write_txt(const T* c, const std::string& prefix, const std::vector<std::string>& names,
-               const std::vector<uint64_t>& lens, bool mappability)
+               const std::vector<uint64_t>& lens, bool mappability, unsigned threads = 1)
 {
     Sink o(prefix + ".txt");
     if (!o.ok()) { std::cerr << "ERROR: cannot write " << prefix << ".txt\n"; return; }
+    if (threads < 1) threads = 1;
+    const uint64_t chunk = 2u << 20;
+    std::vector<std::string> bufs(threads);
     uint64_t begin = 0;
-    for (size_t s = 0; s < lens.size(); ++s) { // src/output.hpp:40-69: '>' name, values separated by single spaces
+    for (size_t s = 0; s < lens.size(); ++s) {
         o.ch('>'); o.str(names[s]); o.ch('\n');
-        for (uint64_t i = 0; i < lens[s]; ++i) {
-            if (i) o.ch(' ');
-            o.value(c[begin + i], mappability);
+        for (uint64_t at = 0; at < lens[s]; at += chunk * threads) {
+            std::vector<std::thread> workers;
+            unsigned used = 0;
+            for (unsigned t = 0; t < threads && at + t * chunk < lens[s]; ++t, ++used) {
+                const uint64_t b = begin + at + t * chunk, e = std::min(begin + lens[s], b + chunk);
+                if (threads == 1) format_values(c, b, e, mappability, bufs[t]);
+                else workers.emplace_back([&, t, b, e] { format_values(c, b, e, mappability, bufs[t]); });
+            }
+            for (std::thread& w : workers) w.join();
+            for (unsigned t = 0; t < used; ++t) {
+                if (at + t * chunk) o.ch(' ');
+                o.str(bufs[t]);
+            }
         }
         o.ch('\n');
         begin += lens[s];
@@ -200,7 +243,7 @@ void write_outputs(const T* c, uint64_t n, const std::string& prefix, const std:
     if (o.raw) timed("RAW file", [&] {
         write_raw(c, n, prefix + (mapp ? ".map" : type == OutputType::frequency_small ? ".freq8" : ".freq16"), mapp);
     });
-    if (o.txt) timed("TXT file", [&] { write_txt(c, prefix, names, lens, mapp); });
+    if (o.txt) timed("TXT file", [&] { write_txt(c, prefix, names, lens, mapp, o.threads); });
     const std::vector<uint64_t> cum = cumulative(lens);
     const VectorRuns<T> src{c, cum};
     if (o.wig) timed("WIG file", [&] { write_wig(src, prefix, names, lens, mapp); });

@@ -343,21 +343,26 @@ bool slurp(const std::string& path, std::vector<uint8_t>& out)
     return r == out.size();
 }
 
-// SeqAn fibres of one direction -> BWT symbols (0/1 = sentinel, 2..5 = A,C,G,T as pack_bwt_blocks expects)
-bool decode_reference_bwt(const std::string& prefix, uint64_t n, std::vector<uint8_t>& bwt, std::string& err)
+// SeqAn fibres of one direction -> BWT symbols (0/1 = sentinel, 2..6 = A,C,G,T,N as pack_bwt_blocks[5] expect).
+// Rank entries (SEQAN/index/index_fm_rank_dictionary_levels.h:197-209): one 64-bit word of packed values, value k in
+// the bits starting at (per_word-1-k)*bits, followed by sigma-1 uint16 block counters: 32 two-bit values + 3 counters
+// = 14 bytes (Dna4), 21 three-bit values + 4 counters = 16 bytes (Dna5).
+bool decode_reference_bwt(const std::string& prefix, uint64_t n, uint32_t sigma, std::vector<uint8_t>& bwt, std::string& err)
 {
     std::vector<uint8_t> drv, drp;
     if (!slurp(prefix + ".drv", drv) || !slurp(prefix + ".drp", drp)) { err = "cannot read " + prefix + ".drv/.drp"; return false; }
-    if (drv.size() != (n + 31) / 32 * 14 || drp.size() != (n + 63) / 64 * 10) {
-        err = "unsupported reference index: expected 14-byte rank entries (Dna4 alphabet, 32-bit BWT dimensions)";
+    const uint32_t bits = sigma == 5 ? 3 : 2, per_word = 64 / bits, entry = 8 + 2 * (sigma - 1);
+    if (drv.size() != (n + per_word - 1) / per_word * entry || drp.size() != (n + 63) / 64 * 10) {
+        err = "unsupported reference index: unexpected size of the rank dictionary (32-bit BWT dimensions expected)";
         return false;
     }
     bwt.resize(n);
     for (uint64_t i = 0; i < n; ++i) {
         uint64_t w, s;
-        std::memcpy(&w, drv.data() + (i / 32) * 14, 8); // 32 values per word, value k in bits 62-2k
+        std::memcpy(&w, drv.data() + (i / per_word) * entry, 8);
         std::memcpy(&s, drp.data() + (i / 64) * 10, 8); // sentinel marker bits, bit k at 63-k
-        const uint32_t v = (uint32_t)(w >> (62 - 2 * (i % 32))) & 3u;
+        const uint32_t v = (uint32_t)(w >> ((per_word - 1 - i % per_word) * bits)) & ((1u << bits) - 1u);
+        if (v >= sigma) { err = "corrupt rank dictionary in the reference index"; return false; }
         bwt[i] = ((s >> (63 - (i % 64))) & 1u) ? 1 : (uint8_t)(v + 2);
     }
     return true;
@@ -373,7 +378,8 @@ bool import_reference_index(const std::string& dir, Blob& blob, std::string& err
     std::vector<uint8_t> info, limits_raw, text_raw;
     if (!slurp(base + ".info.concat", info)) { err = "cannot read " + base + ".info.concat"; return false; }
     const std::string info_s(info.begin(), info.end());
-    if (info_s.find("alphabet_size:4") == std::string::npos) { err = "only Dna4 reference indices can be imported (alphabet_size:4)"; return false; }
+    const uint32_t sigma = info_s.find("alphabet_size:5") != std::string::npos ? 5u : 4u;
+    if (sigma == 4 && info_s.find("alphabet_size:4") == std::string::npos) { err = "only Dna4 / Dna5 reference indices can be imported"; return false; }
     if (info_s.find("bwt_dimensions:32") == std::string::npos || info_s.find("sa_dimensions_i1:16") == std::string::npos) {
         err = "only the (16,32,32) reference index class can be imported";
         return false;
@@ -384,9 +390,11 @@ bool import_reference_index(const std::string& dir, Blob& blob, std::string& err
     std::memcpy(limits.data(), limits_raw.data(), limits_raw.size());
     const uint64_t n_text = limits[n_seq], n = n_text + n_seq;
     if (n_seq > kMaxSeq || n >= 0xFFFFFFFFull) { err = "reference index too large for the 32-bit HBM layout"; return false; }
-    if (!slurp(base + ".txt.concat", text_raw) || text_raw.size() != ((n_text + 31) / 32 + 1) * 8) { err = "cannot read " + base + ".txt.concat (packed text expected)"; return false; }
+    // packed text (src/indexing.hpp: packed_text:true): a length word, then 32 two-bit (Dna4) or 21 three-bit (Dna5) values per word
+    const uint32_t tbits = sigma == 5 ? 3 : 2, tper = 64 / tbits;
+    if (!slurp(base + ".txt.concat", text_raw) || text_raw.size() != ((n_text + tper - 1) / tper + 1) * 8) { err = "cannot read " + base + ".txt.concat (packed text expected)"; return false; }
 
-    BlobPlan plan = plan_blob(n_text, n_seq, false);
+    BlobPlan plan = plan_blob(n_text, n_seq, false, sigma);
     blob.resize(plan.h.total_bytes);
     uint8_t* b = blob.data();
     IndexHeader& h = *reinterpret_cast<IndexHeader*>(b);
@@ -394,18 +402,23 @@ bool import_reference_index(const std::string& dir, Blob& blob, std::string& err
     uint64_t tot[5] = {0, 0, 0, 0, 0};
     std::vector<uint8_t> bwt;
     for (int rev = 0; rev < 2; ++rev) {
-        if (!decode_reference_bwt(base + (rev ? ".rev.lf" : ".lf"), n, bwt, err)) return false;
-        pack_bwt_blocks(bwt.data(), n, reinterpret_cast<RankBlock*>(b + (rev ? h.off_rev : h.off_fwd)), h.n_blocks,
-                        reinterpret_cast<uint32_t*>(b + (rev ? h.off_sent_rev : h.off_sent_fwd)), n_seq, tot);
+        if (!decode_reference_bwt(base + (rev ? ".rev.lf" : ".lf"), n, sigma, bwt, err)) return false;
+        void* blocks = b + (rev ? h.off_rev : h.off_fwd);
+        uint32_t* sent = reinterpret_cast<uint32_t*>(b + (rev ? h.off_sent_rev : h.off_sent_fwd));
+        if (sigma == 5) pack_bwt_blocks5(bwt.data(), n, static_cast<RankBlock5*>(blocks), h.n_blocks, sent, n_seq, tot);
+        else pack_bwt_blocks(bwt.data(), n, static_cast<RankBlock*>(blocks), h.n_blocks, sent, n_seq, tot);
     }
     h.C[0] = n_seq;
     for (int c = 0; c < 5; ++c) h.C[c + 1] = h.C[c] + tot[c];
     uint64_t* text = reinterpret_cast<uint64_t*>(b + h.off_text);
+    uint64_t* nm = sigma == 5 ? reinterpret_cast<uint64_t*>(b + h.off_nmask) : nullptr;
     const uint8_t* words = text_raw.data() + 8; // first word = length
     for (uint64_t i = 0; i < n_text; ++i) {
         uint64_t w;
-        std::memcpy(&w, words + (i / 32) * 8, 8);
-        text[i >> 5] |= ((w >> (62 - 2 * (i % 32))) & 3ull) << (2 * (i & 31));
+        std::memcpy(&w, words + (i / tper) * 8, 8);
+        const uint32_t v = (uint32_t)(w >> ((tper - 1 - i % tper) * tbits)) & ((1u << tbits) - 1u);
+        text[i >> 5] |= (uint64_t)(v & 3u) << (2 * (i & 31));
+        if (v == 4 && nm) nm[i >> 6] |= 1ull << (i & 63);
     }
     uint64_t* lim = reinterpret_cast<uint64_t*>(b + h.off_limits);
     uint32_t* sst = reinterpret_cast<uint32_t*>(b + h.off_seq_start);

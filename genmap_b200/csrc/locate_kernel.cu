@@ -46,6 +46,42 @@ __global__ void k_rows_to_locations(const uint32_t* __restrict__ rows, uint64_t 
     out[i] = make_uint2(a, pos - __ldg(seq_start + a));
 }
 
+__device__ __forceinline__ uint32_t file_of_row(uint32_t pos, const uint32_t* __restrict__ seq_start, uint32_t n_seq,
+                                                const uint32_t* __restrict__ seq_to_file)
+{
+    uint32_t a = 0, b = n_seq;
+    while (b - a > 1) {
+        const uint32_t mid = (a + b) >> 1;
+        if (__ldg(seq_start + mid) <= pos) a = mid; else b = mid;
+    }
+    return __ldg(seq_to_file + a);
+}
+
+// distinct files in the union of the + and - lists of one position (src/algo.hpp:351-361); both lists are sorted by
+// text position, so their file ids do not decrease: a two-pointer merge counts the changes
+template <typename OutT>
+__global__ void k_distinct_files(const uint32_t* __restrict__ rows, const uint64_t* __restrict__ off, uint64_t n_pos,
+                                 const uint32_t* __restrict__ seq_start, uint32_t n_seq, const uint32_t* __restrict__ seq_to_file,
+                                 OutT* __restrict__ out, uint64_t pos0)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_pos) return;
+    uint64_t a = off[2 * j], b = off[2 * j + 1];
+    const uint64_t ea = b, eb = off[2 * j + 2];
+    if (a == eb) return; // not searched / no occurrence: the caller's zero stays
+    constexpr uint32_t kNone = 0xffffffffu;
+    uint32_t fa = a < ea ? file_of_row(rows[a], seq_start, n_seq, seq_to_file) : kNone;
+    uint32_t fb = b < eb ? file_of_row(rows[b], seq_start, n_seq, seq_to_file) : kNone;
+    uint32_t last = kNone, cnt = 0;
+    while (fa != kNone || fb != kNone) {
+        const uint32_t f = fa < fb ? fa : fb;
+        if (f != last) { ++cnt; last = f; }
+        if (fa == f) { ++a; fa = a < ea ? file_of_row(rows[a], seq_start, n_seq, seq_to_file) : kNone; }
+        else { ++b; fb = b < eb ? file_of_row(rows[b], seq_start, n_seq, seq_to_file) : kNone; }
+    }
+    out[pos0 + j] = (OutT)cnt;
+}
+
 struct CountToU64 {
     __host__ __device__ uint64_t operator()(uint32_t x) const { return x; }
 };
@@ -82,6 +118,17 @@ cudaError_t locate_convert(const uint32_t* rows, uint64_t n_rows, const uint32_t
 {
     if (n_rows == 0) return cudaSuccess;
     k_rows_to_locations<<<(unsigned)((n_rows + 255) / 256), 256, 0, stream>>>(rows, n_rows, seq_start, n_seq, static_cast<uint2*>(out));
+    return cudaGetLastError();
+}
+
+cudaError_t locate_distinct_files(const uint32_t* rows, const uint64_t* offsets, uint64_t n_pos, const uint32_t* seq_start,
+                                  uint32_t n_seq, const uint32_t* seq_to_file, void* out, uint32_t value_bits, uint64_t pos0,
+                                  cudaStream_t stream)
+{
+    if (n_pos == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n_pos + 255) / 256);
+    if (value_bits == 16) k_distinct_files<<<grid, 256, 0, stream>>>(rows, offsets, n_pos, seq_start, n_seq, seq_to_file, static_cast<uint16_t*>(out), pos0);
+    else k_distinct_files<<<grid, 256, 0, stream>>>(rows, offsets, n_pos, seq_start, n_seq, seq_to_file, static_cast<uint8_t*>(out), pos0);
     return cudaGetLastError();
 }
 

@@ -109,7 +109,7 @@ int gmb_blob_save(const void *blob, uint64_t bytes, const char *path);
 int gmb_index_open(const char *dir, int device, gmb_index **out);
 /* Convert an index directory written by the reference's own `genmap index` (SeqAn fibres) into a host
  * blob (release with gmb_blob_free).  gmb_index_open does this automatically when <dir>/index.gmb is
- * absent but <dir>/index.lf.drv exists.  Dna4 indices of the default (16,32,32) width class only. */
+ * absent but <dir>/index.lf.drv exists.  Dna4 and Dna5 indices of the default (16,32,32) width class. */
 int gmb_index_import_reference(const char *dir, void **blob_out, uint64_t *bytes_out);
 int gmb_index_from_blob(const void *host_blob, uint64_t bytes, int device, gmb_index **out);
 int gmb_index_adopt_device(void *device_blob, uint64_t bytes, int device, gmb_index **out);

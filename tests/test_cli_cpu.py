@@ -115,3 +115,25 @@ def test_map_needs_a_gpu(genmap, tmp_path):
     out.mkdir()
     r = run(genmap, "map", "-I", idx, "-O", out, "-K", 4, "-r", "-fl")
     assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+def test_txt_writer_chunks_and_threads(genmap, tmp_path):
+    """Sequences longer than one formatting chunk (2 Mi values), formatted by several threads: same text as a
+    straight rendering (src/output.hpp:40-69), for frequencies and for their inverses."""
+    rng = np.random.default_rng(5)
+    lens = [5_000_003, 2_097_152, 7]
+    c = rng.integers(0, 40, sum(lens)).astype(np.uint16)
+    c[rng.integers(0, len(c), 1000)] = 65535
+    c.tofile(str(tmp_path / "c.freq16"))
+    with open(str(tmp_path / "index.ids"), "w") as f:
+        for i, n in enumerate(lens):
+            f.write("g.fa;%d;s%d\n" % (n, i))
+    for flags, fmt in ((["-fl"], lambda v: "%d" % v), ([], lambda v: "%g" % np.float32(1.0 / np.float32(v)) if v else "0")):
+        r = run(genmap, "render", "-I", tmp_path / "index.ids", "-C", tmp_path / "c.freq16", "-N", 0, "-O", tmp_path / "o", "-t", *flags)
+        assert r.returncode == 0, r.stderr
+        lut = {int(v): fmt(int(v)) for v in np.unique(c)}
+        want, b = [], 0
+        for i, n in enumerate(lens):
+            want.append(">s%d\n%s\n" % (i, " ".join(lut[int(v)] for v in c[b:b + n])))
+            b += n
+        assert open(str(tmp_path / "o.txt")).read() == "".join(want)

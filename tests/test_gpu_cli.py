@@ -111,7 +111,7 @@ def test_cli_maps_on_an_index_written_by_the_reference(genmap, tmp_path):
     """Pre-built GenMap indices are usable as they are: `genmap_ref index` -> our `genmap map`."""
     if not T.have_reference():
         pytest.skip("oracle/_ref/genmap_ref not present")
-    for case in ("2b", "3b"):
+    for case in ("2b", "3b", "1f"):  # 1f: a genome with N, i.e. a Dna5 index of the reference
         cfg = T.CASES[case]
         folder = os.path.join(T.GOLDEN, "reference_cases", "case_" + case)
         idx = str(tmp_path / ("refindex_" + case))

@@ -452,3 +452,29 @@ def test_cuda_runs_on_a_larger_genome_roundtrip(gm):
     ends = np.append(start[1:], len(c)).astype(np.int64)
     assert np.array_equal(np.repeat(value, ends - start.astype(np.int64)), c)
     assert np.isin(np.asarray(limits[:-1], dtype=np.uint64), start).all()
+
+
+def test_cuda_exclude_pseudo_with_more_than_64_files(gm):
+    """Beyond the kernel's 64-bit file mask the library locates every occurrence and counts distinct files on the
+    device (ep_many_files): 70 single-sequence files + one with three sequences, against the oracle."""
+    rng = np.random.default_rng(70)
+    base = T.repeat_rich(70, 1, 600)[0]
+    seqs, stf = [], []
+    for g in range(70):
+        s = base.copy()
+        m = rng.random(len(s)) < 0.0008 * g
+        s[m] = rng.integers(0, 4, int(m.sum()), dtype=np.uint8)
+        seqs.append(s); stf.append(g)
+    for extra in T.repeat_rich(71, 3, 300):
+        seqs.append(extra); stf.append(70)
+    stf = np.array(stf, dtype=np.uint32)
+    _, limits = T.concat(seqs)
+    orc = T.Oracle(seqs, seq_to_file=stf)
+    ix = gm.Index.build(seqs, with_sa=True, seq_to_file=stf)
+    for K, E, rc, bits in ((20, 0, True, 16), (24, 1, True, 8), (16, 2, False, 16)):
+        for fi in (0, 33, 69, 70):
+            _, tb, tl, cum, _ = T._prep(limits, stf, fi, None)
+            got = ix.compute_mappability(gm.SearchParams(K, E, rc, True, bits), text_begin=tb, text_len=tl, chrom_cum_lengths=cum)
+            want = orc.map(K, E, revcompl=rc, exclude_pseudo=True, value_bits=bits, file_no=fi)
+            assert np.array_equal(got, want), (K, E, fi)
+            assert fi != 0 or got.max() > 50

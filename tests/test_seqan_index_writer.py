@@ -46,11 +46,12 @@ def test_writer_is_byte_identical_to_reference_index(tmp_path, seed, nchr, lengt
         assert np.array_equal(got, orc.map(20, 1, file_no=fi))
 
 
+@pytest.mark.parametrize("with_n", [False, True], ids=["dna4", "dna5"])
 @pytest.mark.parametrize("seed,nchr,length", [(15, 3, 1000), (16, 2, 70000)])
-def test_importing_a_reference_built_index_gives_our_own_blob(tmp_path, seed, nchr, length):
+def test_importing_a_reference_built_index_gives_our_own_blob(tmp_path, seed, nchr, length, with_n):
     """`genmap_ref index` -> gmb_index_import_reference must equal the blob our own builder makes from the FASTA."""
     import genmap_b200
-    seqs = T.repeat_rich(seed, nchr, length)
+    seqs = T.repeat_rich(seed, nchr, length, with_n=with_n)
     fa = str(tmp_path / "genome.fa")
     T.write_fasta(fa, seqs)
     ref_dir = str(tmp_path / "ref_index")
