@@ -13,7 +13,7 @@ EXPORTS = ["gmb_last_error", "gmb_version", "gmb_device_count", "gmb_index_build
            "gmb_index_build_device", "gmb_blob_save", "gmb_index_open", "gmb_index_from_blob",
            "gmb_index_adopt_device", "gmb_index_close", "gmb_index_get_info", "gmb_map_frequencies",
            "gmb_map_frequencies_range", "gmb_map_frequencies_device", "gmb_index_export_bwt", "gmb_index_export_sa", "gmb_index_set_jump_depth",
-           "gmb_index_import_reference", "gmb_map_locations", "gmb_locations_free", "gmb_map_runs", "gmb_runs_free"]
+           "gmb_index_import_reference", "gmb_map_locations", "gmb_locations_free", "gmb_map_runs", "gmb_runs_free", "gmb_index_replicate"]
 
 
 class GmbParams(ctypes.Structure):
@@ -81,6 +81,8 @@ def lib():
     L.gmb_index_from_blob.argtypes = [vp, u64, ci, pp]
     L.gmb_index_adopt_device.restype = ci
     L.gmb_index_adopt_device.argtypes = [vp, u64, ci, pp]
+    L.gmb_index_replicate.restype = ci
+    L.gmb_index_replicate.argtypes = [vp, ci, pp]
     L.gmb_index_close.restype = ci
     L.gmb_index_close.argtypes = [vp]
     L.gmb_index_get_info.restype = ci

@@ -109,6 +109,14 @@ class Index:
         check(_lib.lib().gmb_index_open(str(directory).encode(), device, ctypes.byref(h)))
         return cls(h, seq_to_file)
 
+    def replicate(self, device):
+        """A copy of this index in the HBM of another GPU of the node (peer-to-peer copy over NVLink)."""
+        h = ctypes.c_void_p()
+        check(_lib.lib().gmb_index_replicate(self._h, int(device), ctypes.byref(h)))
+        ix = Index(h, self.seq_to_file)
+        ix.limits = self.limits
+        return ix
+
     def close(self):
         if self._h:
             _lib.lib().gmb_index_close(self._h)

@@ -290,6 +290,32 @@ int gmb_index_adopt_device(void* device_blob, uint64_t bytes, int device, gmb_in
     return rc;
 }
 
+int gmb_index_replicate(const gmb_index* src, int device, gmb_index** out)
+{
+    if (!src || !out) return fail(GMB_ERR_ARG, "gmb_index_replicate: NULL argument");
+    if (gmb_device_count() <= device || device < 0) return fail(GMB_ERR_CUDA, "no such CUDA device");
+    gmb_index* ix = new (std::nothrow) gmb_index;
+    if (!ix) return fail(GMB_ERR_NOMEM, "out of host memory");
+    ix->device = device;
+    ix->h = src->h;
+    ix->jump_depth_opt = src->jump_depth_opt;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->d_blob, src->h.total_bytes);
+    if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMalloc(index replica)"); }
+    ix->owns_blob = true;
+    int can = 0; // direct NVLink / PCIe peer copy when the devices can address each other; staged by the driver otherwise
+    if (device != src->device && cudaDeviceCanAccessPeer(&can, device, src->device) == cudaSuccess && can) {
+        cudaDeviceEnablePeerAccess(src->device, 0);
+        cudaGetLastError(); // already enabled is fine
+    }
+    e = device == src->device ? cudaMemcpy(ix->d_blob, src->d_blob, src->h.total_bytes, cudaMemcpyDeviceToDevice)
+                              : cudaMemcpyPeer(ix->d_blob, device, src->d_blob, src->device, src->h.total_bytes);
+    if (e != cudaSuccess) { gmb_index_close(ix); return cuda_fail(e, "cudaMemcpyPeer(index blob)"); }
+    int rc = finish_open(ix, out);
+    if (rc != GMB_OK) gmb_index_close(ix);
+    return rc;
+}
+
 int gmb_index_import_reference(const char* dir, void** blob_out, uint64_t* bytes_out)
 {
     if (!dir || !blob_out || !bytes_out) return fail(GMB_ERR_ARG, "gmb_index_import_reference: NULL argument");
@@ -445,11 +471,11 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
     {
         uint32_t want_b = p->block_kmers;
         if (want_b == 0) { const char* env = std::getenv("GMB_BLOCK_KMERS"); if (env && *env) want_b = (uint32_t)std::atoi(env); }
-        if (!build_block_tables(p->K, p->E, want_b, sync_tables, tabs, err)) return fail(GMB_ERR_UNSUPPORTED, err);
+        if (!build_block_tables(p->K, p->E, want_b, sync_tables, tabs, err, ix->h.n_bwt, block_bases(ix->h.sigma))) return fail(GMB_ERR_UNSUPPORTED, err);
         // the tables and the per-chain frame store live in shared memory: shrink the block if they do not fit
         while (tabs.B > 1 && (map_kernel_smem_bytes((uint32_t)tabs.steps.size(), p->E, tabs.B, sync_tables, ix->h.sigma, true) > (200u << 10) ||
                               tabs.steps.size() * 4 + (tabs.B + 1) * kMaxSearches * sizeof(SearchStart) > kTableBytes))
-            if (!build_block_tables(p->K, p->E, tabs.B - 1, sync_tables, tabs, err)) return fail(GMB_ERR_UNSUPPORTED, err);
+            if (!build_block_tables(p->K, p->E, tabs.B - 1, sync_tables, tabs, err, ix->h.n_bwt, block_bases(ix->h.sigma))) return fail(GMB_ERR_UNSUPPORTED, err);
     }
     CU(cudaSetDevice(ix->device));
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);

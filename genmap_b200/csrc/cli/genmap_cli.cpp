@@ -479,8 +479,9 @@ int map_main(int argc, char const** argv)
     if (gmb_device_count() == 0) { std::cerr << "ERROR: no CUDA device found: the B200 build of `genmap map` has no CPU fallback.\n"; return 1; }
     if ((int)gpu > gmb_device_count()) { std::cerr << "ERROR: --gpus " << gpu << " requested but only " << gmb_device_count() << " CUDA device(s) found.\n"; return 1; }
     std::vector<gmb_index*> ixs(gpu, nullptr); // the index is replicated: one copy in the HBM of every GPU
-    for (uint64_t g = 0; g < gpu; ++g)
-        if (gmb_index_open(index_dir.c_str(), (int)g, &ixs[g]) != GMB_OK) { std::cerr << "ERROR: " << gmb_last_error() << "\n"; return 1; }
+    if (gmb_index_open(index_dir.c_str(), 0, &ixs[0]) != GMB_OK) { std::cerr << "ERROR: " << gmb_last_error() << "\n"; return 1; }
+    for (uint64_t g = 1; g < gpu; ++g) // read once, then GPU-to-GPU copies over NVLink
+        if (gmb_index_replicate(ixs[0], (int)g, &ixs[g]) != GMB_OK) { std::cerr << "ERROR: " << gmb_last_error() << "\n"; return 1; }
     gmb_index_info iinfo;
     gmb_index_get_info(ixs[0], &iinfo);
     if (a.has("verbose")) {

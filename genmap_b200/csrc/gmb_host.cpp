@@ -2,7 +2,9 @@
 #include "gmb_host.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sais.hpp"
@@ -36,7 +38,94 @@ const SchemeDef kSchemes[5] = {
 };
 } // namespace
 
-bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err, bool force_sync)
+// ---------------------------------------------------------------------------------------------------
+// Part lengths.  The reference splits the pattern into nb parts of equal length (floor(K/nb), the first K mod nb
+// one longer: src/find2_index_approx.hpp:164-176).  Any split into nb non-empty parts keeps a scheme exhaustive
+// and non-redundant (its validity depends on the errors per part, not on the part lengths), so the counts do
+// not depend on it — but the size of the search tree does, strongly: on a text of N symbols every node of depth
+// < log4 N exists, so errors allowed close to the root are expensive and the best split depends on N.  Measured
+// at 3 Gbp, K = 30, E = 2: 406 rank-block fetches per position with the equal split, 281 with (5,6,7,7)
+// (profiles/r01/s18_parts_e2.txt).  expected_fetches() is the model used to pick the split: expected number of
+// existing trie nodes (x 1..2 blocks each) on an iid text, the query's own occurrence counted as certain; it
+// tracks the measured fetch counts within 5 %.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+double expected_fetches(const SchemeDef& sd, const uint32_t* len, uint32_t E, double N, uint32_t B, uint32_t jump_max, uint32_t block_bases)
+{
+    const uint32_t nb = sd.n_blocks;
+    uint32_t Li = 0;
+    for (uint32_t b = 0; b < nb; ++b) Li += len[b];
+    double total = 0.0;
+    std::vector<uint32_t> ub(Li), lb(Li), rem(Li);
+    std::vector<char> exact_ok(Li + 1);
+    for (uint32_t s = 0; s < sd.n_search; ++s) {
+        uint32_t t = 0;
+        for (uint32_t i = 0; i < nb; ++i) {
+            const uint32_t n = len[sd.pi[s][i] - 1u];
+            for (uint32_t k = 0; k < n; ++k, ++t) { ub[t] = sd.up[s][i]; lb[t] = sd.lo[s][i]; rem[t] = n - 1 - k; }
+        }
+        exact_ok[Li] = 1;
+        for (uint32_t q = Li; q-- > 0;) exact_ok[q] = exact_ok[q + 1] && lb[q] == 0;
+        uint32_t d = 0; // steps answered by the jump table
+        while (d < Li && d < jump_max && d + 1 < Li && ub[d] == 0) ++d;
+        for (int strand = 0; strand < 2; ++strand) {
+            double cnt[kMaxE + 2] = {1.0, 0, 0, 0, 0, 0};
+            double lam = N;
+            for (t = 0; t < Li; ++t, lam *= 0.25) {
+                const double pex = lam > 30 ? 1.0 : 1.0 - std::exp(-lam);   // a given string of length t occurs
+                const double size = pex > 0 ? std::max(1.0, lam / pex) : 1.0; // rows of an existing node
+                const double fc = 1.0 + std::min(1.0, size / block_bases);   // blocks per expansion
+                if (t >= d)
+                    for (uint32_t e = 0; e <= E; ++e) {
+                        if (cnt[e] == 0) continue;
+                        if (e == 0 && strand == 0) total += (size <= 1.0 && exact_ok[t]) ? 0.0 : fc; // the query's own path
+                        else total += cnt[e] * pex * fc;
+                    }
+                double nxt[kMaxE + 2] = {0, 0, 0, 0, 0, 0};
+                for (uint32_t e = 0; e <= E; ++e) {
+                    if (cnt[e] == 0) continue;
+                    if (e + rem[t] >= lb[t]) nxt[e] += cnt[e];
+                    if (e + 1 <= ub[t] && e + 1 + rem[t] >= lb[t]) nxt[e + 1] += 3.0 * cnt[e];
+                }
+                for (uint32_t e = 0; e <= E + 1; ++e) cnt[e] = nxt[e];
+            }
+            const double pleaf = lam > 30 ? 1.0 : 1.0 - std::exp(-lam); // infix hits are completed window by window
+            for (uint32_t e = 0; e <= E; ++e) {
+                const double hits = (e == 0 && strand == 0) ? 1.0 : cnt[e] * pleaf;
+                total += hits * B * (B - 1) * 0.5 * (e == E ? 1.0 : 1.5);
+            }
+        }
+    }
+    return total / B;
+}
+
+// steepest descent over single-character moves between parts, from the reference's equal split
+void choose_part_lengths(const SchemeDef& sd, uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t B, uint32_t block_bases, uint32_t* len)
+{
+    const uint32_t nb = sd.n_blocks;
+    if (nb < 2 || n_bwt == 0 || K < 2 * nb) return;
+    const uint32_t jump_max = default_jump_depth(n_bwt);
+    double best = expected_fetches(sd, len, E, (double)n_bwt, B, jump_max, block_bases);
+    for (int round = 0; round < 256; ++round) {
+        int bi = -1, bj = -1;
+        double bc = best * (1.0 - 1e-6);
+        for (uint32_t i = 0; i < nb; ++i)
+            for (uint32_t j = 0; j < nb; ++j) {
+                if (i == j || len[i] <= 1) continue;
+                --len[i]; ++len[j];
+                const double c = expected_fetches(sd, len, E, (double)n_bwt, B, jump_max, block_bases);
+                ++len[i]; --len[j];
+                if (c < bc) { bc = c; bi = (int)i; bj = (int)j; }
+            }
+        if (bi < 0) break;
+        --len[bi]; ++len[bj];
+        best = bc;
+    }
+}
+} // namespace
+
+bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err, bool force_sync, uint64_t n_bwt, uint32_t block_kmers,
+                       uint32_t block_bases)
 {
     if (E > kMaxE) { err = "E > 4 not yet supported."; return false; } // src/mappability.hpp:187
     if (K < E + 2) { err = "K must be at least E + 2."; return false; } // undefined in the reference (rc 139)
@@ -45,8 +134,37 @@ bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err
     const uint32_t nb = sd.n_blocks;
     // block lengths over the whole k-mer: floor(K/nb), the first K mod nb blocks one longer (:164-176)
     uint32_t len[6], begin[6];
+    for (uint32_t b = 0; b < nb; ++b) len[b] = K / nb + (b < K % nb);
+    const char* model_env = std::getenv("GMB_PART_MODEL"); // "0": keep the reference's equal split
+    if (n_bwt != 0 && !(model_env && model_env[0] == '0')) choose_part_lengths(sd, K, E, n_bwt, block_kmers ? block_kmers : 1, block_bases, len);
+    // Tuning knob (results never depend on it: any split into nb non-empty parts keeps the scheme exhaustive and
+    // non-redundant, only the size of the search tree changes): relative part lengths, e.g. GMB_PART_WEIGHTS=5,5,8,8
+    if (const char* env = std::getenv("GMB_PART_WEIGHTS")) {
+        double w[6], sum = 0;
+        uint32_t got = 0;
+        for (const char* q = env; *q && got < 6;) {
+            char* end = nullptr;
+            const double v = std::strtod(q, &end);
+            if (end == q) break;
+            w[got++] = v > 0 ? v : 0;
+            q = *end == ',' ? end + 1 : end;
+        }
+        if (got == nb && K >= 2 * nb) {
+            for (uint32_t b = 0; b < nb; ++b) sum += w[b];
+            uint32_t used = 0;
+            for (uint32_t b = 0; b < nb && sum > 0; ++b) {
+                len[b] = std::max<uint32_t>(1, (uint32_t)(K * w[b] / sum + 0.5));
+                used += len[b];
+            }
+            // fix rounding on the longest part so that the parts add up to K
+            while (sum > 0 && used != K) {
+                uint32_t big = 0;
+                for (uint32_t b = 1; b < nb; ++b) if (len[b] > len[big]) big = b;
+                if (used > K) { --len[big]; --used; } else { ++len[big]; ++used; }
+            }
+        }
+    }
     for (uint32_t b = 0, o = 0; b < nb; ++b) {
-        len[b] = K / nb + (b < K % nb);
         begin[b] = o;
         o += len[b];
     }
@@ -91,7 +209,8 @@ uint32_t default_block_kmers(uint32_t K, uint32_t E)
     return b < 1 ? 1 : b;
 }
 
-bool build_block_tables(uint32_t K, uint32_t E, uint32_t B, bool force_sync, BlockTables& out, std::string& err)
+bool build_block_tables(uint32_t K, uint32_t E, uint32_t B, bool force_sync, BlockTables& out, std::string& err, uint64_t n_bwt,
+                        uint32_t block_bases)
 {
     if (E > kMaxE) { err = "E > 4 not yet supported."; return false; }
     if (K < E + 2) { err = "K must be at least E + 2."; return false; }
@@ -105,7 +224,7 @@ bool build_block_tables(uint32_t K, uint32_t E, uint32_t B, bool force_sync, Blo
     for (uint32_t cnt = 1; cnt <= B; ++cnt) {
         const uint32_t Li = K - cnt + 1;
         StepTables& t = out.infix[cnt];
-        if (!build_step_tables(Li, E, t, err, force_sync || cnt > 1)) return false; // flanks need both intervals
+        if (!build_step_tables(Li, E, t, err, force_sync || cnt > 1, n_bwt, cnt, block_bases)) return false; // flanks need both intervals
         out.n_search = t.n_search;
         out.p1_off[cnt] = (uint32_t)out.steps.size();
         for (uint32_t i = 0; i < t.n_search * Li; ++i) {

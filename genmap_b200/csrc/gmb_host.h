@@ -14,7 +14,10 @@ namespace gmb {
 // Returns false with `err` set if (K,E) is unsupported.
 // force_sync: keep both intervals of the bidirectional index in step at every step (--exclude-pseudo
 // needs the interval in SA(T) at every full-length match).
-bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err, bool force_sync = false);
+// n_bwt != 0: the part lengths are chosen for a text of n_bwt symbols (see choose_part_lengths in gmb_host.cpp);
+// n_bwt == 0: the reference's equal split.  Results never depend on the split.
+bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err, bool force_sync = false, uint64_t n_bwt = 0,
+                       uint32_t block_kmers = 1, uint32_t block_bases = 64);
 
 // Search tables of a (K,E) configuration for blocks of up to B adjacent k-mers (see Chain in gmb_core.h):
 // for every block size cnt = 1..B the scheme's step table over the common infix (K - cnt + 1 characters,
@@ -28,7 +31,8 @@ struct BlockTables {
     std::vector<StepTables> infix; // [cnt] the per-cnt infix tables (index 0 unused), kept for jump-table planning
 };
 // B == 0 picks the default for (K,E).  force_sync: see build_step_tables.
-bool build_block_tables(uint32_t K, uint32_t E, uint32_t B, bool force_sync, BlockTables& out, std::string& err);
+bool build_block_tables(uint32_t K, uint32_t E, uint32_t B, bool force_sync, BlockTables& out, std::string& err, uint64_t n_bwt = 0,
+                        uint32_t block_bases = 64);
 uint32_t default_block_kmers(uint32_t K, uint32_t E);
 
 // Which jump table each search of a (K,E) configuration can use: depth[s] = min(length of the search's

@@ -113,6 +113,11 @@ int gmb_index_open(const char *dir, int device, gmb_index **out);
 int gmb_index_import_reference(const char *dir, void **blob_out, uint64_t *bytes_out);
 int gmb_index_from_blob(const void *host_blob, uint64_t bytes, int device, gmb_index **out);
 int gmb_index_adopt_device(void *device_blob, uint64_t bytes, int device, gmb_index **out);
+/* Replicate an opened index into the HBM of another GPU of the same node with a peer-to-peer copy (NVLink /
+ * NVSwitch when the devices can address each other): how a single-process host (the `genmap` CLI with --gpus N)
+ * puts the index on every GPU after reading it once.  Multi-process hosts broadcast the blob themselves (NCCL)
+ * and call gmb_index_adopt_device. */
+int gmb_index_replicate(const gmb_index *src, int device, gmb_index **out);
 int gmb_index_close(gmb_index *idx);
 int gmb_index_get_info(const gmb_index *idx, gmb_index_info *info);
 /* Maximum depth of the jump tables that replace the first error-free steps of every search:

@@ -148,7 +148,7 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     std::string err;
     const IndexHeader& h = *reinterpret_cast<const IndexHeader*>(base);
     BlockTables tabs;
-    if (!build_block_tables(K, E, block_kmers, ep, tabs, err)) return -2;
+    if (!build_block_tables(K, E, block_kmers, ep, tabs, err, h.n_bwt, block_bases(h.sigma))) return -2;
     const uint32_t B = tabs.B;
     MapCtx cx;
     cx.blk[0] = base + h.off_fwd;
@@ -239,7 +239,7 @@ int hs_locate(const void* blob, uint32_t K, uint32_t E, int revcompl, uint64_t t
     const IndexHeader& h = *reinterpret_cast<const IndexHeader*>(base);
     if (!h.off_sa) return -3;
     BlockTables tabs;
-    if (!build_block_tables(K, E, 1, true, tabs, err)) return -2;
+    if (!build_block_tables(K, E, 1, true, tabs, err, h.n_bwt, block_bases(h.sigma))) return -2;
     MapCtx cx;
     cx.blk[0] = base + h.off_fwd;
     cx.blk[1] = base + h.off_rev;

@@ -478,3 +478,17 @@ def test_cuda_exclude_pseudo_with_more_than_64_files(gm):
             want = orc.map(K, E, revcompl=rc, exclude_pseudo=True, value_bits=bits, file_no=fi)
             assert np.array_equal(got, want), (K, E, fi)
             assert fi != 0 or got.max() > 50
+
+
+def test_cuda_index_replica_on_a_second_gpu(gm):
+    from genmap_b200 import _lib
+    if _lib.lib().gmb_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    seqs = gm.synth_genome(500_000, 3, 23)
+    ix0 = gm.Index.build(seqs, device=0)
+    ix1 = ix0.replicate(1)
+    assert ix1.device == 1 and int(ix1.info.blob_bytes) == int(ix0.info.blob_bytes)
+    for K, E in ((30, 0), (24, 2)):
+        assert np.array_equal(ix0.compute_mappability(gm.SearchParams(K, E)), ix1.compute_mappability(gm.SearchParams(K, E)))
+    same = ix0.replicate(0)  # a second copy on the same device also works
+    assert np.array_equal(same.compute_mappability(gm.SearchParams(30, 1)), ix0.compute_mappability(gm.SearchParams(30, 1)))
