@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "sais.hpp"
 
@@ -209,12 +210,69 @@ uint32_t default_block_kmers(uint32_t K, uint32_t E)
     return b < 1 ? 1 : b;
 }
 
+// Block size by the same model: expected fetches per position of the best split for every B; the largest B within
+// 3 % of the minimum (equal fetch counts favour the larger block: fewer chain start-ups).  Measured at 3 Gbp, K = 30
+// (profiles/r01/s19_sweep_model1.txt): the model is 4 % above the counted fetches for B = 3..8 and ranks them alike.
+uint32_t model_block_kmers(uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t block_bases)
+{
+    if (E == 0 || n_bwt == 0) return default_block_kmers(K, E);
+    const SchemeDef& sd = kSchemes[E];
+    double cost[13];
+    uint32_t top = 0;
+    double best = 0;
+    for (uint32_t B = 1; B <= 12; ++B) {
+        if (B + E + 1 > K || K + B - 2 > 255 || K - B + 1 < 2 * sd.n_blocks) break;
+        const uint32_t Li = K - B + 1;
+        uint32_t len[6];
+        for (uint32_t b = 0; b < sd.n_blocks; ++b) len[b] = Li / sd.n_blocks + (b < Li % sd.n_blocks);
+        choose_part_lengths(sd, Li, E, n_bwt, B, block_bases, len);
+        cost[B] = expected_fetches(sd, len, E, (double)n_bwt, B, default_jump_depth(n_bwt), block_bases);
+        if (top == 0 || cost[B] < best) best = cost[B];
+        top = B;
+    }
+    if (top == 0) return 1;
+    uint32_t pick = 1;
+    for (uint32_t B = 1; B <= top; ++B)
+        if (cost[B] <= 1.03 * best) pick = B;
+    return pick;
+}
+
+static bool build_block_tables_uncached(uint32_t K, uint32_t E, uint32_t B, bool force_sync, BlockTables& out, std::string& err,
+                                        uint64_t n_bwt, uint32_t block_bases);
+
+// The tables of one (K, E, B, text size) are asked for by every map call (every pipeline piece): keep the last few.
 bool build_block_tables(uint32_t K, uint32_t E, uint32_t B, bool force_sync, BlockTables& out, std::string& err, uint64_t n_bwt,
                         uint32_t block_bases)
 {
+    struct Entry { std::string key; BlockTables tabs; };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    const char* e1 = std::getenv("GMB_PART_MODEL");
+    const char* e2 = std::getenv("GMB_PART_WEIGHTS");
+    char buf[160];
+    std::snprintf(buf, sizeof buf, "%u/%u/%u/%d/%llu/%u/", K, E, B, force_sync ? 1 : 0, (unsigned long long)n_bwt, block_bases);
+    const std::string key = std::string(buf) + (e1 ? e1 : "") + "/" + (e2 ? e2 : "");
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (const Entry& en : cache)
+            if (en.key == key) { out = en.tabs; return true; }
+    }
+    if (!build_block_tables_uncached(K, E, B, force_sync, out, err, n_bwt, block_bases)) return false;
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() >= 8) cache.erase(cache.begin());
+    cache.push_back(Entry{key, out});
+    return true;
+}
+
+static bool build_block_tables_uncached(uint32_t K, uint32_t E, uint32_t B, bool force_sync, BlockTables& out, std::string& err,
+                                        uint64_t n_bwt, uint32_t block_bases)
+{
     if (E > kMaxE) { err = "E > 4 not yet supported."; return false; }
     if (K < E + 2) { err = "K must be at least E + 2."; return false; }
-    if (B == 0) B = default_block_kmers(K, E);
+    if (B == 0) {
+        const char* model_env = std::getenv("GMB_PART_MODEL");
+        B = (n_bwt != 0 && !(model_env && model_env[0] == '0')) ? model_block_kmers(K, E, n_bwt, block_bases) : default_block_kmers(K, E);
+    }
     if (B > kMaxBlockKmers) B = kMaxBlockKmers;
     while (B > 1 && (B + E + 1 > K || K + B - 2 > 255)) --B; // the infix keeps >= E + 2 characters; offsets fit 8 bits
     if (K + B - 2 > 255) { err = "K > 255 is not supported."; return false; }

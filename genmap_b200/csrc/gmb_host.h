@@ -34,6 +34,8 @@ struct BlockTables {
 bool build_block_tables(uint32_t K, uint32_t E, uint32_t B, bool force_sync, BlockTables& out, std::string& err, uint64_t n_bwt = 0,
                         uint32_t block_bases = 64);
 uint32_t default_block_kmers(uint32_t K, uint32_t E);
+// B for a text of n_bwt symbols by the expected-fetch model (gmb_host.cpp); falls back to default_block_kmers
+uint32_t model_block_kmers(uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t block_bases);
 
 // Which jump table each search of a (K,E) configuration can use: depth[s] = min(length of the search's
 // initial error-free rightwards run, max_depth, K-1); 0 = none.  need_lof[s]: a later step extends to the
