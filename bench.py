@@ -216,6 +216,17 @@ class PortCpu:
         pass
 
 
+def index_for_cpu_arm(seqs, ix, device):
+    """An index of the same genome that holds the suffix array (rebuilt on the GPU: ~2 s at 3 Gbp)."""
+    import genmap_b200 as gm
+    import torch
+    if ix.info.has_sa:
+        return ix
+    ix.close()
+    torch.cuda.empty_cache()
+    return gm.Index.build(seqs, device=device, on_gpu=True, with_sa=True)
+
+
 def make_cpu_arm(seqs, ix):
     try:
         return ReferenceCpu(seqs, ix)
@@ -278,9 +289,9 @@ def main():
         seqs = gm.synth_genome(total, args.nchr, args.seed)
         log("genome generated in %.1f s" % (time.time() - t0))
         t0 = time.time()
-        # the suffix array (4 B/base more HBM) is only kept when the CPU arm needs to write a reference-format index
-        want_sa = args.impl == "reference" or (world == 1 and not args.no_cpu_baseline)
-        ix = gm.Index.build(seqs, device=local, on_gpu=True, with_sa=want_sa)
+        # the suffix array (4 B/base more HBM) is only needed by the CPU arm, to write a reference-format index: the
+        # timed index is the one `genmap index --no-sa` builds; the CPU arm builds its own afterwards (index_for_cpu_arm)
+        ix = gm.Index.build(seqs, device=local, on_gpu=True, with_sa=args.impl == "reference")
         log("index built on GPU in %.1f s %s, blob %.2f GB" % (time.time() - t0, ix.build_timings_ms, ix.info.blob_bytes / 1e9))
     if dist is not None:
         from genmap_b200 import parallel
@@ -411,6 +422,9 @@ def main():
                 # per rank block / jump-table entry; ceiling measured with tools/randread.cu (profiles/r01/s1_randread.txt)
                 "random_requests_per_s": (r["fetches"] + r["lut_reads"]) / len(r["batches"]) / (r["kernel_ms"] * 1e-3),
                 "random_request_ceiling_per_s": 38.0e9,
+                # what the DRAM actually does: 64-byte accesses per second (ncu traffic / 64 B / kernel time); the
+                # random-read microbenchmark tops out at ~38 G/s of these
+                "dram_64B_accesses_per_s": (traffic / 64.0 / (r["kernel_ms"] * 1e-3)) if traffic else None,
                 "jump_table_depth": r["jump_depth"], "kernel_ms_per_launch": r["kernel_ms"]}
 
     main_r["E"], main_r["batch"] = E, batch
@@ -428,8 +442,11 @@ def main():
                                           "positions_per_step": b2, "roofline": roofline(r2)}
 
     cpu = None
+    index_gb = ix.info.blob_bytes / 1e9
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
+            del out_dev
+            ix = index_for_cpu_arm(seqs, ix, local)
             arm = make_cpu_arm(seqs, ix)
             rate, _, npos_cpu = cpu_rate(arm, K, E, args.cpu_seconds)
             cpu = {"value": rate, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample(npos_cpu, K)}
@@ -448,7 +465,7 @@ def main():
                 "config": {"workload": workload, "K": K, "E": E, "genome_bp": n_text, "positions_per_step_per_gpu": batch,
                            "sharding": "positions range-partitioned over %d GPU(s), index replicated (NCCL broadcast)" % world,
                            "cache": "inputs larger than L2: %.2f GB index vs 126 MB L2, every step searches different positions"
-                                    % (ix.info.blob_bytes / 1e9)},
+                                    % index_gb},
                 "clocks": main_r["clocks"], "e2e": main_r.get("e2e"), "gpu_launches": args.steps,
                 "roofline": roofline(main_r), "cpu_baseline": cpu, "extra": extras}
         print(json.dumps(line), flush=True)
