@@ -394,7 +394,7 @@ def main():
         return res
 
     batch = int((args.batch_mpos or default_batch(E)) * (1 << 20))
-    batch = max(1 << 16, min(batch, (shard_e - shard_b) // 2))
+    batch = max(1 << 16, min(batch, shard_e - shard_b))
     main_r = measure(E, batch, args.steps, args.warmup, True, True)
     peak, peak_src = peak_hbm()
 
@@ -435,7 +435,7 @@ def main():
             if E2 == E:
                 continue
             b2 = int(default_batch(E2) * (1 << 20))
-            b2 = max(1 << 14, min(b2, (shard_e - shard_b) // 2))
+            b2 = max(1 << 14, min(b2, shard_e - shard_b))
             r2 = measure(E2, b2, max(3, args.steps // 2), 3, False, False)
             r2["E"], r2["batch"] = E2, b2
             extras["K%d_E%d" % (K, E2)] = {"value": r2["value"], "unit": UNIT, "ms_per_step": r2["ms"] / max(3, args.steps // 2),
