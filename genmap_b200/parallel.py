@@ -11,13 +11,16 @@ def shard_range(n_positions, rank, world):
 
 
 def step_batches(shard_begin, shard_end, batch, count):
-    """`count` consecutive batches of `batch` positions inside the shard, wrapping around at its end."""
+    """`count` consecutive batches of `batch` positions inside the shard, wrapping around at its end.  When the
+    shard holds fewer than two whole batches, the batch that would run over the end is moved back to end at it, so
+    consecutive steps still search different ranges."""
     span = shard_end - shard_begin
     batch = min(batch, span)
-    res, pos = [], 0
+    res, pos, moved_back = [], 0, False
     for _ in range(count):
         if pos + batch > span:
-            pos = 0
+            moved_back = not moved_back and 0 < span - batch < batch
+            pos = span - batch if moved_back else 0
         res.append((shard_begin + pos, shard_begin + pos + batch))
         pos += batch
     return res

@@ -281,3 +281,25 @@ def test_locate_lists_reproduce_reference_golden_csv(case):
     assert set(made) == set(os.listdir(gold))
     for fn, text in made.items():
         assert text == open(os.path.join(gold, fn)).read(), (case, fn)
+
+
+# ---- part lengths / block size chosen by the expected-fetch model (gmb_host.cpp: choose_part_lengths) -----------
+def test_part_length_model_changes_the_tree_not_the_counts(monkeypatch):
+    import genmap_b200 as gm
+    seqs = gm.synth_genome(2_000_000, 2, 77)
+    hs = T.HostSim(seqs)
+    res = {}
+    for name, env in (("equal", {"GMB_PART_MODEL": "0"}), ("model", {}), ("forced", {"GMB_PART_WEIGHTS": "9,1,1,9"})):
+        monkeypatch.delenv("GMB_PART_MODEL", raising=False)
+        monkeypatch.delenv("GMB_PART_WEIGHTS", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for K, E in ((24, 2), (36, 3), (24, 1)):
+            res[name, K, E] = hs.map(K, E, pos_begin=500_000, pos_end=500_000 + (400 if E == 3 else 4000), return_fetches=True)
+    for K, E in ((24, 2), (36, 3), (24, 1)):
+        assert np.array_equal(res["equal", K, E][0], res["model", K, E][0]), (K, E)
+        assert np.array_equal(res["equal", K, E][0], res["forced", K, E][0]), (K, E)
+    # fewer rank-block fetches with the model where the scheme has more than two parts; never more at E = 1
+    assert res["model", 24, 2][1] < 0.85 * res["equal", 24, 2][1]
+    assert res["model", 36, 3][1] < 0.9 * res["equal", 36, 3][1]
+    assert res["model", 24, 1][1] <= res["equal", 24, 1][1]

@@ -64,3 +64,5 @@ def test_shard_ranges_tile_exactly():
             assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
     bl = parallel.step_batches(100, 1100, 300, 5)
     assert bl == [(100, 400), (400, 700), (700, 1000), (100, 400), (400, 700)]
+    assert parallel.step_batches(0, 375, 268, 4) == [(0, 268), (107, 375), (0, 268), (107, 375)]
+    assert parallel.step_batches(0, 300, 300, 2) == [(0, 300), (0, 300)]
