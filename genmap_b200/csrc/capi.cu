@@ -94,6 +94,9 @@ struct gmb_index {
     int jump_depth_opt = -1;
     JtEntry* jt_uni[17] = {};
     uint32_t* jt_lof[17] = {};
+    JtFull* jt_full[17] = {};    // both intervals per entry (searches that need the interval in SA(T) after the jump)
+    uint32_t* d_variants = nullptr; // substituted-offset sets of the current call's searches
+    size_t variants_cap = 0;
 };
 
 namespace {
@@ -120,40 +123,76 @@ void fill_ctx(const gmb_index* ix, MapCtx& cx)
     cx.loc_rows = nullptr;
 }
 
-// make sure the tables of every depth in `plan` exist on the device (built level by level, cached)
-int ensure_jump_tables(gmb_index* ix, const std::vector<JumpPlan>& plans, cudaStream_t stream)
+struct JumpNeeds { bool uni[17] = {}, lof[17] = {}, full[17] = {}; uint32_t top = 0; };
+
+JumpNeeds jump_needs(const std::vector<JumpPlan>& plans)
 {
-    bool need_uni[17] = {}, need_lof[17] = {};
+    JumpNeeds n;
     for (const JumpPlan& plan : plans)
         for (uint32_t s = 0; s < kMaxSearches; ++s) {
             const uint32_t d = plan.depth[s];
-            if (d) { need_uni[d] = true; need_lof[d] = need_lof[d] || plan.need_lof[s]; }
+            if (!d) continue;
+            if (plan.need_lof[s]) n.full[d] = true; else n.uni[d] = true;
+            n.top = std::max(n.top, d);
         }
-    uint32_t top = 0, lof_top = 0;
-    for (uint32_t d = 1; d <= 16; ++d) {
-        if (need_uni[d] && (!ix->jt_uni[d] || (need_lof[d] && !ix->jt_lof[d]))) top = d;
-        if (need_lof[d]) lof_top = d;
+    return n;
+}
+
+// big levels (> kJumpKeep) the current call does not use are dropped: they are rebuilt in about a second when needed
+void evict_stale_jump_tables(gmb_index* ix, const JumpNeeds& n)
+{
+    for (uint32_t d = kJumpKeep + 1; d <= 16; ++d) {
+        if (ix->jt_uni[d] && !n.uni[d]) { cudaFree(ix->jt_uni[d]); ix->jt_uni[d] = nullptr; }
+        if (ix->jt_lof[d]) { cudaFree(ix->jt_lof[d]); ix->jt_lof[d] = nullptr; }
+        if (ix->jt_full[d] && !n.full[d]) { cudaFree(ix->jt_full[d]); ix->jt_full[d] = nullptr; }
     }
+}
+
+// bytes that still have to be allocated for these needs (tables + the transient parent levels of the deepest one)
+size_t missing_jump_bytes(const gmb_index* ix, const JumpNeeds& n)
+{
+    size_t bytes = 0;
+    uint32_t deepest_missing = 0;
+    for (uint32_t d = 1; d <= 16; ++d) {
+        const size_t e = (size_t)1 << (2 * d);
+        if (n.uni[d] && !ix->jt_uni[d]) { bytes += e * sizeof(JtEntry); deepest_missing = d; }
+        if (n.full[d] && !ix->jt_full[d]) { bytes += e * sizeof(JtFull); deepest_missing = d; }
+    }
+    for (uint32_t d = 1; d < deepest_missing; ++d) // every level below is built as uni + lof on the way
+        if (!ix->jt_uni[d] || !ix->jt_lof[d]) bytes += ((size_t)1 << (2 * d)) * (sizeof(JtEntry) + sizeof(uint32_t));
+    return bytes;
+}
+
+// make sure the tables these needs name exist on the device (built level by level, cached)
+int ensure_jump_tables(gmb_index* ix, const JumpNeeds& n, cudaStream_t stream)
+{
+    uint32_t top = 0;
+    for (uint32_t d = 1; d <= 16; ++d)
+        if ((n.uni[d] && !ix->jt_uni[d]) || (n.full[d] && !ix->jt_full[d])) top = d;
     if (top == 0) return GMB_OK; // everything this call needs is cached
     MapCtx cx;
     fill_ctx(ix, cx);
     for (uint32_t d = 1; d <= top; ++d) {
-        const bool want_lof = d <= lof_top || d <= kJumpKeep;
-        if (ix->jt_uni[d] && (!want_lof || ix->jt_lof[d])) continue;
-        if (ix->jt_uni[d]) { cudaFree(ix->jt_uni[d]); ix->jt_uni[d] = nullptr; }
-        if (ix->jt_lof[d]) { cudaFree(ix->jt_lof[d]); ix->jt_lof[d] = nullptr; }
-        const size_t n = (size_t)1 << (2 * d);
-        cudaError_t e = cudaMalloc(&ix->jt_uni[d], n * sizeof(JtEntry));
-        if (e == cudaSuccess && want_lof) e = cudaMalloc(&ix->jt_lof[d], n * sizeof(uint32_t));
-        if (e == cudaSuccess) e = build_jump_level(cx, ix->h.sigma, d, ix->jt_uni[d - 1], ix->jt_lof[d - 1], ix->jt_uni[d], ix->jt_lof[d], stream);
-        if (e != cudaSuccess) return cuda_fail(e, "jump table");
+        const size_t e = (size_t)1 << (2 * d);
+        const bool parent_for_later = d < top; // deeper levels extend this one: needs uni + lof
+        if ((parent_for_later || n.uni[d]) && !(ix->jt_uni[d] && (!parent_for_later || ix->jt_lof[d]))) {
+            if (ix->jt_uni[d]) { cudaFree(ix->jt_uni[d]); ix->jt_uni[d] = nullptr; }
+            if (ix->jt_lof[d]) { cudaFree(ix->jt_lof[d]); ix->jt_lof[d] = nullptr; }
+            cudaError_t err = cudaMalloc(&ix->jt_uni[d], e * sizeof(JtEntry));
+            if (err == cudaSuccess && parent_for_later) err = cudaMalloc(&ix->jt_lof[d], e * sizeof(uint32_t));
+            if (err == cudaSuccess)
+                err = build_jump_level(cx, ix->h.sigma, d, ix->jt_uni[d - 1], ix->jt_lof[d - 1], ix->jt_uni[d], ix->jt_lof[d], nullptr, stream);
+            if (err != cudaSuccess) return cuda_fail(err, "jump table");
+        }
+        if (n.full[d] && !ix->jt_full[d]) {
+            cudaError_t err = cudaMalloc(&ix->jt_full[d], e * sizeof(JtFull));
+            if (err == cudaSuccess)
+                err = build_jump_level(cx, ix->h.sigma, d, ix->jt_uni[d - 1], ix->jt_lof[d - 1], nullptr, nullptr, ix->jt_full[d], stream);
+            if (err != cudaSuccess) return cuda_fail(err, "jump table");
+        }
     }
     CU(cudaStreamSynchronize(stream));
-    for (uint32_t d = kJumpKeep + 1; d <= 16; ++d) // big intermediate / stale levels are not kept
-        if (ix->jt_uni[d] && !need_uni[d]) {
-            cudaFree(ix->jt_uni[d]); ix->jt_uni[d] = nullptr;
-            if (ix->jt_lof[d]) { cudaFree(ix->jt_lof[d]); ix->jt_lof[d] = nullptr; }
-        }
+    evict_stale_jump_tables(ix, n);
     return GMB_OK;
 }
 } // namespace
@@ -382,7 +421,8 @@ int gmb_index_close(gmb_index* ix)
     if (ix->d_ranges) cudaFree(ix->d_ranges);
     if (ix->d_out) cudaFree(ix->d_out);
     if (ix->d_seq_to_file) cudaFree(ix->d_seq_to_file);
-    for (int d = 0; d < 17; ++d) { if (ix->jt_uni[d]) cudaFree(ix->jt_uni[d]); if (ix->jt_lof[d]) cudaFree(ix->jt_lof[d]); }
+    for (int d = 0; d < 17; ++d) { if (ix->jt_uni[d]) cudaFree(ix->jt_uni[d]); if (ix->jt_lof[d]) cudaFree(ix->jt_lof[d]); if (ix->jt_full[d]) cudaFree(ix->jt_full[d]); }
+    if (ix->d_variants) cudaFree(ix->d_variants);
     if (ix->s_compute) cudaStreamDestroy(ix->s_compute);
     if (ix->s_copy) cudaStreamDestroy(ix->s_copy);
     for (int i = 0; i < 2; ++i) if (ix->ev_piece[i]) cudaEventDestroy(ix->ev_piece[i]);
@@ -513,33 +553,63 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
     std::vector<JumpPlan> plans(tabs.B + 1);
     uint32_t plan_depth = 0;
     std::vector<SearchStart> starts((size_t)(tabs.B + 1) * kMaxSearches);
+    std::vector<uint32_t> variants;
     {
         const char* env = std::getenv("GMB_JUMP_DEPTH");
         int want = ix->jump_depth_opt;
         if (want < 0 && env && *env) want = std::atoi(env);
         uint32_t maxd = want < 0 ? default_jump_depth(ix->h.n_bwt) : (uint32_t)want;
         if (maxd > 16) maxd = 16;
-        if (want < 0) { // automatic depth: the deepest level plus its parent must fit comfortably in free HBM
+        JumpNeeds needs;
+        for (;;) {
+            plan_depth = 0;
+            for (uint32_t cnt = 0; cnt <= tabs.B; ++cnt) {
+                JumpPlan& pl = plans[cnt];
+                if (cnt == 0) { pl = JumpPlan(); std::memset(pl.depth, 0, sizeof(pl.depth)); pl.max_depth = 0; continue; }
+                plan_jump_tables(tabs.infix[cnt], maxd, pl, p->E, ix->h.n_bwt, ix->h.sigma, cnt);
+                plan_depth = std::max(plan_depth, pl.max_depth);
+            }
+            needs = jump_needs(plans);
+            if (want >= 0 || maxd <= 1) break; // a fixed depth is taken as it is
+            // automatic depth: what is missing must fit comfortably in free HBM once stale levels are dropped
+            evict_stale_jump_tables(ix, needs);
             size_t free_b = 0, total_b = 0;
-            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
-                while (maxd > 1 && !ix->jt_uni[maxd] && ((size_t)15 << (2 * maxd)) > free_b / 2) --maxd;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); break; }
+            if (missing_jump_bytes(ix, needs) <= free_b / 10 * 8) break;
+            --maxd;
         }
-        std::memset(&plans[0], 0, sizeof(JumpPlan));
-        for (uint32_t cnt = 1; cnt <= tabs.B; ++cnt) {
-            plan_jump_tables(tabs.infix[cnt], maxd, plans[cnt]);
-            plan_depth = std::max(plan_depth, plans[cnt].max_depth);
-        }
-        int rcj = ensure_jump_tables(ix, plans, stream);
+        int rcj = ensure_jump_tables(ix, needs, stream);
         if (rcj != GMB_OK) return rcj;
         for (uint32_t cnt = 1; cnt <= tabs.B; ++cnt)
             for (uint32_t s2 = 0; s2 < kMaxSearches; ++s2) {
                 const uint32_t d = plans[cnt].depth[s2];
                 SearchStart& S = starts[(size_t)cnt * kMaxSearches + s2];
-                S.uni = d ? ix->jt_uni[d] : nullptr;
-                S.lof = (d && plans[cnt].need_lof[s2]) ? ix->jt_lof[d] : nullptr;
+                std::memset(&S, 0, sizeof(S));
+                const bool full = d && plans[cnt].need_lof[s2];
+                S.uni = (d && !full) ? ix->jt_uni[d] : nullptr;
+                S.lof = nullptr;
+                S.full = full ? ix->jt_full[d] : nullptr;
                 S.a = plans[cnt].a[s2];
                 S.d = d;
+                S.n_var = std::max(1u, plans[cnt].n_var[s2]);
             }
+        // lay the variant sets of all tables out in one array and turn the indices into device pointers
+        std::vector<size_t> base_of(tabs.B + 1, 0);
+        for (uint32_t cnt = 1; cnt <= tabs.B; ++cnt) {
+            base_of[cnt] = variants.size();
+            variants.insert(variants.end(), plans[cnt].variants.begin(), plans[cnt].variants.end());
+            if (plans[cnt].variants.empty()) variants.push_back(0xffffffffu);
+        }
+        if (ix->variants_cap < variants.size()) {
+            if (ix->d_variants) cudaFree(ix->d_variants);
+            ix->d_variants = nullptr;
+            ix->variants_cap = variants.size() * 2 + 64;
+            CU(cudaMalloc(&ix->d_variants, ix->variants_cap * sizeof(uint32_t)));
+        }
+        CU(cudaMemcpyAsync(ix->d_variants, variants.data(), variants.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        for (uint32_t cnt = 1; cnt <= tabs.B; ++cnt)
+            for (uint32_t s2 = 0; s2 < kMaxSearches; ++s2)
+                starts[(size_t)cnt * kMaxSearches + s2].var = ix->d_variants + base_of[cnt] + plans[cnt].var_off[s2];
     }
     // search tables: step words, then the jump-table starts, in one device scratch buffer
     const size_t step_bytes = tabs.steps.size() * sizeof(uint32_t);

@@ -383,12 +383,21 @@ GMB_HD void load_pattern(Pattern<KW, SIGMA>& p, const uint64_t* text, const uint
 // Jump table of one search: every search starts with an error-free, rightwards run (U[0] = 0 in every
 // scheme, first direction Rev: src/find2_index_approx.hpp:441); the node reached after its first `d`
 // characters is looked up instead of walked.  key = those characters, the first one in the low bits.
+// Beyond the error-free prefix a search may be entered once per ADMISSIBLE STRING of length d: the mismatches the
+// scheme allows inside the key window are substituted into the key and every resulting key is read (`var`: the
+// admissible sets of substituted key offsets, one byte each, 0xff = unused; a set of m offsets stands for 3^m
+// keys).  One table read replaces the walk through the dense top of the trie (JumpPlan, gmb_host.h).
 struct JtEntry { uint32_t lo_r, size; };
+struct JtFull { uint32_t lo_r, size, lo_f, pad; }; // both intervals in one 16-byte entry: one memory request
 struct SearchStart {
     const JtEntry* uni;   // [4^d] interval in SA(T') + size            (nullptr: no table, start at the root)
-    const uint32_t* lof;  // [4^d] start of the interval in SA(T)       (nullptr when never needed again)
-    uint32_t a;           // pattern offset of the first character
+    const uint32_t* lof;  // [4^d] start of the interval in SA(T)       (nullptr when never needed again or `full` is set)
+    const JtFull* full;   // [4^d] both intervals                       (set instead of uni/lof when SA(T) is needed)
+    const uint32_t* var;  // n_var sets of substituted key offsets
+    uint32_t a;           // pattern offset of the first character of the key window
     uint32_t d;           // depth of the table
+    uint32_t n_var;
+    uint32_t pad;
 };
 
 struct MapCtx {
@@ -540,6 +549,7 @@ struct Chain {
     uint32_t occ_fwd, occ_rev;
     uint64_t loc_at_fwd, loc_at_rev;
     bool thin;                 // instrumented instantiation: the previous expansion was of a one-row interval
+    uint32_t var, sub, nsub;   // entry into the current search: set of substituted key offsets, which of its 3^m keys, 3^m
 };
 
 // --exclude-pseudo: mark the FASTA file of every occurrence in SA rows [lo, lo+n)
@@ -577,10 +587,16 @@ GMB_HD uint32_t frame_store_words(uint32_t E, uint32_t B, bool ep, int sigma, bo
 GMB_HD void jump_lookup(const SearchStart& S, uint32_t key, uint32_t& lo_f, uint32_t& lo_r, uint32_t& size)
 {
 #if defined(__CUDA_ARCH__)
+    if (S.full) {
+        [[maybe_unused]] uint32_t pad;
+        asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo_r), "=r"(size), "=r"(lo_f), "=r"(pad) : "l"(S.full + key));
+        return;
+    }
     asm volatile("ld.global.nc.L2::64B.v2.u32 {%0,%1}, [%2];" : "=r"(lo_r), "=r"(size) : "l"(S.uni + key));
     lo_f = 0u;
     if (S.lof) asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(lo_f) : "l"(S.lof + key));
 #else
+    if (S.full) { lo_r = S.full[key].lo_r; size = S.full[key].size; lo_f = S.full[key].lo_f; return; }
     lo_r = S.uni[key].lo_r; size = S.uni[key].size;
     lo_f = S.lof ? S.lof[key] : 0u;
 #endif
@@ -594,12 +610,28 @@ GMB_HD void chain_start(Chain<KW, SIGMA>& st, const MapCtx& cx, unsigned long lo
 {
     const SearchStart S = cx.starts[(BLK ? st.cnt : 1u) * kMaxSearches + st.s];
     st.e = 0; st.lvmask = 0; st.win = kNoWin; st.leaf_e = 0; st.thin = false;
-    if (S.uni == nullptr) {
-        st.lo_f = 0; st.lo_r = 0; st.size = cx.n_bwt; st.t = 0;
+    if (S.uni == nullptr && S.full == nullptr) {
+        st.lo_f = 0; st.lo_r = 0; st.size = cx.n_bwt; st.t = 0; st.nsub = 1;
     } else {
-        if (st.strand == 1 && st.s == 0) { st.lo_f = st.pre_lo_f; st.lo_r = st.pre_lo_r; st.size = st.pre_size; }
-        else if (SIGMA == 5 && st.pat.has_n(S.a, S.d)) { st.lo_f = 0; st.lo_r = 0; st.size = 0; } // N never matches
-        else jump_lookup(S, st.pat.bits(S.a, S.d), st.lo_f, st.lo_r, st.size);
+#if defined(__CUDA_ARCH__)
+        const uint32_t set = __ldg(S.var + st.var);
+#else
+        const uint32_t set = S.var[st.var];
+#endif
+        if (st.strand == 1 && st.s == 0 && set == 0xffffffffu) { st.lo_f = st.pre_lo_f; st.lo_r = st.pre_lo_r; st.size = st.pre_size; st.nsub = 1; }
+        else if (set == kDeadVariant || (SIGMA == 5 && st.pat.has_n(S.a, S.d))) { st.lo_f = 0; st.lo_r = 0; st.size = 0; st.nsub = 1; } // N never matches
+        else {
+            // substitute: offset p of the set gets one of the three other characters (XOR with 1..3), chosen by the
+            // base-3 digits of st.sub
+            uint32_t key = st.pat.bits(S.a, S.d), e = 0, q = st.sub, n3 = 1;
+#pragma unroll
+            for (uint32_t k = 0; k < kMaxE; ++k) {
+                const uint32_t p = (set >> (8 * k)) & 0xffu;
+                if (p != 0xffu) { key ^= (1u + q % 3u) << (2u * p); q /= 3u; n3 *= 3u; ++e; }
+            }
+            jump_lookup(S, key, st.lo_f, st.lo_r, st.size);
+            st.e = e; st.nsub = n3;
+        }
         st.t = S.d;
         if (lut_reads) *lut_reads += 1;
     }
@@ -609,7 +641,7 @@ GMB_HD void chain_start(Chain<KW, SIGMA>& st, const MapCtx& cx, unsigned long lo
 template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
 GMB_HD void chain_begin_block(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, unsigned long long* lut_reads)
 {
-    st.acc = 0; st.s = 0; st.strand = 0; st.files = 0; st.occ_fwd = 0; st.occ_rev = 0;
+    st.acc = 0; st.s = 0; st.strand = 0; st.files = 0; st.occ_fwd = 0; st.occ_rev = 0; st.var = 0; st.sub = 0; st.nsub = 1;
     if (!BLK) st.cnt = 1;
     st.has_n = st.pat.has_n();
     if (BLK) {
@@ -619,7 +651,7 @@ GMB_HD void chain_begin_block(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx
     // the reverse strand's first jump-table entry does not depend on the forward search: request it now so
     // that its latency overlaps the forward strand instead of starting the reverse strand with a stall
     const SearchStart S0 = cx.starts[(BLK ? st.cnt : 1u) * kMaxSearches];
-    if (cx.n_strands > 1 && S0.uni != nullptr) {
+    if (cx.n_strands > 1 && (S0.uni != nullptr || S0.full != nullptr)) {
         Pattern<KW, SIGMA> rc = st.pat;
         rc.reverse_complement(cx.K + (BLK ? st.cnt : 1u) - 1);
         if (SIGMA == 5 && rc.has_n(S0.a, S0.d)) { st.pre_lo_f = 0; st.pre_lo_r = 0; st.pre_size = 0; }
@@ -831,7 +863,12 @@ GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, Fetch
             }
         }
         if (cand == 0) {
-            // this search is exhausted: next search, next strand, or done
+            // this entry into the search is exhausted: its next key, the next set of substituted offsets, ...
+            if (++st.sub < st.nsub) { chain_start<KW, BLK, SIGMA>(st, cx, lut_reads); return true; }
+            st.sub = 0;
+            if (++st.var < cx.starts[(BLK ? st.cnt : 1u) * kMaxSearches + st.s].n_var) { chain_start<KW, BLK, SIGMA>(st, cx, lut_reads); return true; }
+            st.var = 0;
+            // ... then the next search, the next strand, or done
             if (++st.s == cx.n_search) {
                 st.s = 0;
                 if (++st.strand == cx.n_strands) {

@@ -51,51 +51,105 @@ const SchemeDef kSchemes[5] = {
 // tracks the measured fetch counts within 5 %.
 // ---------------------------------------------------------------------------------------------------
 namespace {
-double expected_fetches(const SchemeDef& sd, const uint32_t* len, uint32_t E, double N, uint32_t B, uint32_t jump_max, uint32_t block_bases)
+// Expected cost of one search on an iid text of N symbols, depth by depth (see the comment above).
+struct SearchProfile {
+    uint32_t Li = 0, run = 0;          // steps; leading steps that allow no error
+    double walk[2][kMaxK + 1];         // expected rank-block fetches of the nodes of depth t, strand 0 / 1
+    double nstr[kMaxK + 2];            // strings of length t the scheme admits (error placements x 3^errors)
+    double leaf[2];                    // window completions per infix hit
+};
+
+void profile_search(const uint32_t* ub, const uint32_t* lb, const uint32_t* rem, uint32_t Li, uint32_t E, double N, uint32_t B,
+                    uint32_t block_bases, SearchProfile& P)
+{
+    P.Li = Li;
+    P.run = 0;
+    while (P.run < Li && ub[P.run] == 0) ++P.run;
+    std::vector<char> exact_ok(Li + 1);
+    exact_ok[Li] = 1;
+    for (uint32_t q = Li; q-- > 0;) exact_ok[q] = exact_ok[q + 1] && lb[q] == 0;
+    double cnt[kMaxE + 2] = {1.0, 0, 0, 0, 0, 0};
+    double lam = N;
+    for (uint32_t t = 0; t < Li; ++t, lam *= 0.25) {
+        const double pex = lam > 30 ? 1.0 : 1.0 - std::exp(-lam);   // a given string of length t occurs
+        const double size = pex > 0 ? std::max(1.0, lam / pex) : 1.0; // rows of an existing node
+        const double fc = 1.0 + std::min(1.0, size / block_bases);   // blocks per expansion
+        P.walk[0][t] = P.walk[1][t] = 0.0;
+        P.nstr[t] = 0.0;
+        for (uint32_t e = 0; e <= E; ++e) {
+            if (cnt[e] == 0) continue;
+            P.nstr[t] += cnt[e];
+            P.walk[1][t] += cnt[e] * pex * fc;
+            if (e == 0) P.walk[0][t] += (size <= 1.0 && exact_ok[t]) ? 0.0 : fc; // the query's own path
+            else P.walk[0][t] += cnt[e] * pex * fc;
+        }
+        double nxt[kMaxE + 2] = {0, 0, 0, 0, 0, 0};
+        for (uint32_t e = 0; e <= E; ++e) {
+            if (cnt[e] == 0) continue;
+            if (e + rem[t] >= lb[t]) nxt[e] += cnt[e];
+            if (e + 1 <= ub[t] && e + 1 + rem[t] >= lb[t]) nxt[e + 1] += 3.0 * cnt[e];
+        }
+        for (uint32_t e = 0; e <= E + 1; ++e) cnt[e] = nxt[e];
+    }
+    const double pleaf = lam > 30 ? 1.0 : 1.0 - std::exp(-lam); // infix hits are completed window by window
+    P.nstr[Li] = 0;
+    P.leaf[0] = P.leaf[1] = 0.0;
+    for (uint32_t e = 0; e <= E; ++e) {
+        P.nstr[Li] += cnt[e];
+        const double w = B * (B - 1) * 0.5 * (e == E ? 1.0 : 1.5);
+        P.leaf[0] += (e == 0 ? 1.0 : cnt[e] * pleaf) * w;
+        P.leaf[1] += cnt[e] * pleaf * w;
+    }
+}
+
+// Depth at which the search is entered through the jump table.  Up to `run` the table replaces an error-free
+// walk (one entry); deeper, every admissible string of that length is looked up (its mismatches substituted into
+// the key: one table read per string, both strands) instead of walking the dense top of the trie.  Returns the
+// depth that minimises expected table reads + expected fetches below it; *cost = that minimum (both strands).
+constexpr double kMaxVariantStrings = 3000.0;
+uint32_t best_jump_depth(const SearchProfile& P, uint32_t dmax, bool allow_variants, double* cost)
+{
+    const uint32_t top = std::min(dmax, P.Li > 0 ? P.Li - 1 : 0u);
+    const uint32_t first = std::min(P.run, top);
+    std::vector<double> below(P.Li + 1, 0.0); // expected fetches of all depths >= t, both strands
+    for (uint32_t t = P.Li; t-- > 0;) below[t] = below[t + 1] + P.walk[0][t] + P.walk[1][t];
+    uint32_t best_d = first;
+    double best = (first > 0 ? 2.0 : 0.0) + below[first];
+    if (allow_variants)
+        for (uint32_t d = first + 1; d <= top; ++d) {
+            if (P.nstr[d] > kMaxVariantStrings) break;
+            const double c = 2.0 * P.nstr[d] + below[d];
+            if (c < best) { best = c; best_d = d; }
+        }
+    if (cost) *cost = best + P.leaf[0] + P.leaf[1];
+    return best_d;
+}
+
+bool variants_enabled(uint64_t n_bwt, uint32_t sigma)
+{
+    const char* env = std::getenv("GMB_JUMP_VARIANTS"); // "0": enter every search through its error-free prefix only
+    return n_bwt != 0 && sigma == 4 && !(env && env[0] == '0');
+}
+
+double expected_fetches(const SchemeDef& sd, const uint32_t* len, uint32_t E, double N, uint32_t B, uint32_t jump_max, uint32_t block_bases,
+                        bool allow_variants)
 {
     const uint32_t nb = sd.n_blocks;
     uint32_t Li = 0;
     for (uint32_t b = 0; b < nb; ++b) Li += len[b];
     double total = 0.0;
     std::vector<uint32_t> ub(Li), lb(Li), rem(Li);
-    std::vector<char> exact_ok(Li + 1);
+    SearchProfile P;
     for (uint32_t s = 0; s < sd.n_search; ++s) {
         uint32_t t = 0;
         for (uint32_t i = 0; i < nb; ++i) {
             const uint32_t n = len[sd.pi[s][i] - 1u];
             for (uint32_t k = 0; k < n; ++k, ++t) { ub[t] = sd.up[s][i]; lb[t] = sd.lo[s][i]; rem[t] = n - 1 - k; }
         }
-        exact_ok[Li] = 1;
-        for (uint32_t q = Li; q-- > 0;) exact_ok[q] = exact_ok[q + 1] && lb[q] == 0;
-        uint32_t d = 0; // steps answered by the jump table
-        while (d < Li && d < jump_max && d + 1 < Li && ub[d] == 0) ++d;
-        for (int strand = 0; strand < 2; ++strand) {
-            double cnt[kMaxE + 2] = {1.0, 0, 0, 0, 0, 0};
-            double lam = N;
-            for (t = 0; t < Li; ++t, lam *= 0.25) {
-                const double pex = lam > 30 ? 1.0 : 1.0 - std::exp(-lam);   // a given string of length t occurs
-                const double size = pex > 0 ? std::max(1.0, lam / pex) : 1.0; // rows of an existing node
-                const double fc = 1.0 + std::min(1.0, size / block_bases);   // blocks per expansion
-                if (t >= d)
-                    for (uint32_t e = 0; e <= E; ++e) {
-                        if (cnt[e] == 0) continue;
-                        if (e == 0 && strand == 0) total += (size <= 1.0 && exact_ok[t]) ? 0.0 : fc; // the query's own path
-                        else total += cnt[e] * pex * fc;
-                    }
-                double nxt[kMaxE + 2] = {0, 0, 0, 0, 0, 0};
-                for (uint32_t e = 0; e <= E; ++e) {
-                    if (cnt[e] == 0) continue;
-                    if (e + rem[t] >= lb[t]) nxt[e] += cnt[e];
-                    if (e + 1 <= ub[t] && e + 1 + rem[t] >= lb[t]) nxt[e + 1] += 3.0 * cnt[e];
-                }
-                for (uint32_t e = 0; e <= E + 1; ++e) cnt[e] = nxt[e];
-            }
-            const double pleaf = lam > 30 ? 1.0 : 1.0 - std::exp(-lam); // infix hits are completed window by window
-            for (uint32_t e = 0; e <= E; ++e) {
-                const double hits = (e == 0 && strand == 0) ? 1.0 : cnt[e] * pleaf;
-                total += hits * B * (B - 1) * 0.5 * (e == E ? 1.0 : 1.5);
-            }
-        }
+        profile_search(ub.data(), lb.data(), rem.data(), Li, E, N, B, block_bases, P);
+        double c = 0;
+        best_jump_depth(P, jump_max, allow_variants, &c);
+        total += c;
     }
     return total / B;
 }
@@ -103,10 +157,11 @@ double expected_fetches(const SchemeDef& sd, const uint32_t* len, uint32_t E, do
 // steepest descent over single-character moves between parts, from the reference's equal split
 void choose_part_lengths(const SchemeDef& sd, uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t B, uint32_t block_bases, uint32_t* len)
 {
+    const bool av = variants_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u);
     const uint32_t nb = sd.n_blocks;
     if (nb < 2 || n_bwt == 0 || K < 2 * nb) return;
     const uint32_t jump_max = default_jump_depth(n_bwt);
-    double best = expected_fetches(sd, len, E, (double)n_bwt, B, jump_max, block_bases);
+    double best = expected_fetches(sd, len, E, (double)n_bwt, B, jump_max, block_bases, av);
     for (int round = 0; round < 256; ++round) {
         int bi = -1, bj = -1;
         double bc = best * (1.0 - 1e-6);
@@ -114,7 +169,7 @@ void choose_part_lengths(const SchemeDef& sd, uint32_t K, uint32_t E, uint64_t n
             for (uint32_t j = 0; j < nb; ++j) {
                 if (i == j || len[i] <= 1) continue;
                 --len[i]; ++len[j];
-                const double c = expected_fetches(sd, len, E, (double)n_bwt, B, jump_max, block_bases);
+                const double c = expected_fetches(sd, len, E, (double)n_bwt, B, jump_max, block_bases, av);
                 ++len[i]; --len[j];
                 if (c < bc) { bc = c; bi = (int)i; bj = (int)j; }
             }
@@ -226,7 +281,8 @@ uint32_t model_block_kmers(uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t bloc
         uint32_t len[6];
         for (uint32_t b = 0; b < sd.n_blocks; ++b) len[b] = Li / sd.n_blocks + (b < Li % sd.n_blocks);
         choose_part_lengths(sd, Li, E, n_bwt, B, block_bases, len);
-        cost[B] = expected_fetches(sd, len, E, (double)n_bwt, B, default_jump_depth(n_bwt), block_bases);
+        cost[B] = expected_fetches(sd, len, E, (double)n_bwt, B, default_jump_depth(n_bwt), block_bases,
+                                   variants_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u));
         if (top == 0 || cost[B] < best) best = cost[B];
         top = B;
     }
@@ -303,20 +359,54 @@ static bool build_block_tables_uncached(uint32_t K, uint32_t E, uint32_t B, bool
     return true;
 }
 
-void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan)
+namespace {
+// every set of mismatching steps among the first d steps that the scheme admits (the nodes of depth d of the
+// search's trie, up to the choice of the substituted characters), as up to kMaxE key offsets per set
+void enumerate_variants(const uint32_t* st, uint32_t d, uint32_t E, uint32_t a, uint32_t t, uint32_t e, uint32_t set, std::vector<uint32_t>& out)
+{
+    if (t == d) { out.push_back(set); return; }
+    const uint32_t ub = step_ub(st[t]), lb = step_lb(st[t]), rem = step_rem(st[t]);
+    if (e + rem >= lb) enumerate_variants(st, d, E, a, t + 1, e, set, out); // the pattern's own character
+    if (e + 1 <= ub && e + 1 + rem >= lb && e < kMaxE) {                    // a substituted character here
+        const uint32_t off = step_pos(st[t]) - a;
+        const uint32_t with = (set & ~(0xffu << (8 * e))) | (off << (8 * e));
+        enumerate_variants(st, d, E, a, t + 1, e + 1, with, out);
+    }
+}
+} // namespace
+
+void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan, uint32_t E, uint64_t n_bwt, uint32_t sigma,
+                      uint32_t block_kmers)
 {
     plan.max_depth = 0;
-    for (uint32_t s = 0; s < kMaxSearches; ++s) { plan.depth[s] = 0; plan.a[s] = 0; plan.need_lof[s] = false; }
+    plan.variants.clear();
+    for (uint32_t s = 0; s < kMaxSearches; ++s) { plan.depth[s] = 0; plan.a[s] = 0; plan.need_lof[s] = false; plan.var_off[s] = 0; plan.n_var[s] = 0; }
     const uint32_t K = tabs.K;
+    const bool allow = variants_enabled(n_bwt, sigma);
+    if (max_depth > 16) max_depth = 16;
+    std::vector<uint32_t> ub(K), lb(K), rem(K);
+    SearchProfile P;
     for (uint32_t s = 0; s < tabs.n_search; ++s) {
         const uint32_t* st = tabs.step + s * K;
-        uint32_t run = 0;
-        while (run < K && step_dir(st[run]) == 1 && step_ub(st[run]) == 0 && step_pos(st[run]) == step_pos(st[0]) + run) ++run;
-        uint32_t d = std::min(run, std::min(max_depth, K - 1));
-        if (d > 16) d = 16;
+        for (uint32_t t = 0; t < K; ++t) { ub[t] = step_ub(st[t]); lb[t] = step_lb(st[t]); rem[t] = step_rem(st[t]); }
+        profile_search(ub.data(), lb.data(), rem.data(), K, E, n_bwt ? (double)n_bwt : 1.0, block_kmers ? block_kmers : 1,
+                       block_bases(sigma), P);
+        const uint32_t d = best_jump_depth(P, max_depth, allow, nullptr);
         plan.depth[s] = d;
-        plan.a[s] = step_pos(st[0]);
-        plan.need_lof[s] = d > 0 && step_sync(st[d - 1]) != 0;
+        plan.var_off[s] = (uint32_t)plan.variants.size();
+        if (d == 0) { plan.n_var[s] = 1; plan.variants.push_back(0xffffffffu); continue; }
+        uint32_t a = step_pos(st[0]);
+        for (uint32_t t = 0; t < d; ++t) a = std::min(a, step_pos(st[t])); // the consumed window is contiguous: [a, a + d)
+        plan.a[s] = a;
+        enumerate_variants(st, d, E, a, 0, 0, 0xffffffffu, plan.variants);
+        if (plan.variants.size() == plan.var_off[s]) plan.variants.push_back(kDeadVariant); // no admissible string of this length
+        plan.n_var[s] = (uint32_t)plan.variants.size() - plan.var_off[s];
+        // the error-free string first (the reverse strand's first read is requested early under that assumption)
+        for (uint32_t v = plan.var_off[s]; v < plan.variants.size(); ++v)
+            if (plan.variants[v] == 0xffffffffu) { std::swap(plan.variants[v], plan.variants[plan.var_off[s]]); break; }
+        bool left_later = false; // the interval in SA(T) is the active one for every later step to the left
+        for (uint32_t t = d; t < K; ++t) left_later |= step_dir(st[t]) == 0;
+        plan.need_lof[s] = step_sync(st[d - 1]) != 0 || left_later;
         plan.max_depth = std::max(plan.max_depth, d);
     }
 }

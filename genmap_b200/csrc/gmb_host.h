@@ -37,16 +37,23 @@ uint32_t default_block_kmers(uint32_t K, uint32_t E);
 // B for a text of n_bwt symbols by the expected-fetch model (gmb_host.cpp); falls back to default_block_kmers
 uint32_t model_block_kmers(uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t block_bases);
 
-// Which jump table each search of a (K,E) configuration can use: depth[s] = min(length of the search's
-// initial error-free rightwards run, max_depth, K-1); 0 = none.  need_lof[s]: a later step extends to the
-// left, so the interval in SA(T) must be known too.
+// How every search of a (K,E) configuration is entered through the jump tables.  depth[s]: length of the key
+// (0 = no table: start at the root); a[s]: pattern offset of the key window [a, a + depth) (the region the first
+// depth steps consume, contiguous whatever their directions).  Up to the search's error-free prefix one key is read;
+// deeper (chosen by the expected-fetch model when the text size is known) every string of that length the scheme
+// admits is read instead of walking to it: variants[var_off[s] .. + n_var[s]) lists the admissible sets of
+// substituted key offsets (one byte each, 0xff = unused; the error-free set first), each standing for 3^|set| keys.
+// need_lof[s]: the interval in SA(T) is needed after the jump (a later step extends to the left / both are kept in step).
 struct JumpPlan {
     uint32_t depth[kMaxSearches];
     uint32_t a[kMaxSearches];
     bool need_lof[kMaxSearches];
+    uint32_t var_off[kMaxSearches], n_var[kMaxSearches];
+    std::vector<uint32_t> variants;
     uint32_t max_depth;
 };
-void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan);
+void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan, uint32_t E = 0, uint64_t n_bwt = 0, uint32_t sigma = 4,
+                      uint32_t block_kmers = 1);
 // ceil(log4(n_bwt)) clamped to [1,16]: less than one expected occurrence per table entry
 uint32_t default_jump_depth(uint64_t n_bwt);
 

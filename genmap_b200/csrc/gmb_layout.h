@@ -38,6 +38,7 @@ constexpr uint32_t kMaxK = 255;              // step tables keep pattern offsets
 constexpr uint32_t kMaxE = 4;                // src/mappability.hpp:187
 constexpr uint32_t kMaxSearches = 7;         // src/find2_index_approx.hpp:121-131
 constexpr uint32_t kMaxBlockKmers = 16;      // adjacent k-mers searched together through their common infix
+constexpr uint32_t kDeadVariant = 0xfffffffeu; // jump-table entry set of a search that admits no string of the key's length
 
 struct alignas(kBlockBytes) RankBlock {
     uint32_t cnt[3];

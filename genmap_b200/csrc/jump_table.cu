@@ -12,7 +12,7 @@ namespace {
 template <int SIGMA>
 __global__ void k_jump_level(const MapCtx cx, uint32_t d, const JtEntry* __restrict__ prev_uni,
                              const uint32_t* __restrict__ prev_lof, JtEntry* __restrict__ out_uni,
-                             uint32_t* __restrict__ out_lof)
+                             uint32_t* __restrict__ out_lof, JtFull* __restrict__ out_full)
 {
     const uint64_t n = 1ull << (2 * d);
     const uint64_t key = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -26,6 +26,12 @@ __global__ void k_jump_level(const MapCtx cx, uint32_t d, const JtEntry* __restr
         par.lo_f = prev_lof ? prev_lof[pk] : 0u; par.lo_r = e.lo_r; par.size = e.size;
     }
     const Node m = extend_right<SIGMA>(par, (uint32_t)(key >> (2 * (d - 1))), cx); // keys are A,C,G,T only
+    if (out_full) {
+        JtFull f;
+        f.lo_r = m.lo_r; f.size = m.size; f.lo_f = m.lo_f; f.pad = 0;
+        out_full[key] = f;
+        return;
+    }
     JtEntry o;
     o.lo_r = m.lo_r; o.size = m.size;
     out_uni[key] = o;
@@ -35,13 +41,13 @@ __global__ void k_jump_level(const MapCtx cx, uint32_t d, const JtEntry* __restr
 } // namespace
 
 cudaError_t build_jump_level(const MapCtx& cx, uint32_t sigma, uint32_t d, const JtEntry* prev_uni, const uint32_t* prev_lof,
-                             JtEntry* out_uni, uint32_t* out_lof, cudaStream_t stream)
+                             JtEntry* out_uni, uint32_t* out_lof, JtFull* out_full, cudaStream_t stream)
 {
     const uint64_t n = 1ull << (2 * d);
     const unsigned threads = 256;
     const unsigned long long blocks = (n + threads - 1) / threads;
-    if (sigma == 5) k_jump_level<5><<<(unsigned)blocks, threads, 0, stream>>>(cx, d, prev_uni, prev_lof, out_uni, out_lof);
-    else k_jump_level<4><<<(unsigned)blocks, threads, 0, stream>>>(cx, d, prev_uni, prev_lof, out_uni, out_lof);
+    if (sigma == 5) k_jump_level<5><<<(unsigned)blocks, threads, 0, stream>>>(cx, d, prev_uni, prev_lof, out_uni, out_lof, out_full);
+    else k_jump_level<4><<<(unsigned)blocks, threads, 0, stream>>>(cx, d, prev_uni, prev_lof, out_uni, out_lof, out_full);
     return cudaGetLastError();
 }
 

@@ -72,6 +72,21 @@ void run_locate(MapCtx cx, const uint64_t* text, const uint64_t* nmask, uint64_t
     }
     for (uint64_t i = 0; i < 2 * npos; ++i) std::sort(rows.begin() + off[i], rows.begin() + off[i + 1]);
 }
+void build_host_jump_levels(const MapCtx& cx, uint32_t sigma, uint32_t max_depth, std::vector<std::vector<JtFull>>& full)
+{
+    for (uint32_t d = 1; d <= max_depth; ++d) {
+        const uint64_t n = 1ull << (2 * d), pmask = (1ull << (2 * (d - 1))) - 1;
+        full[d].resize(n);
+        for (uint64_t key = 0; key < n; ++key) {
+            Node par;
+            if (d == 1) { par.lo_f = 0; par.lo_r = 0; par.size = cx.n_bwt; }
+            else { const JtFull& q = full[d - 1][key & pmask]; par.lo_f = q.lo_f; par.lo_r = q.lo_r; par.size = q.size; }
+            const Node m = sigma == 5 ? extend_right<5>(par, (uint32_t)(key >> (2 * (d - 1))), cx)
+                                      : extend_right<4>(par, (uint32_t)(key >> (2 * (d - 1))), cx);
+            full[d][key] = JtFull{m.lo_r, m.size, m.lo_f, 0u};
+        }
+    }
+}
 } // namespace
 
 extern "C" {
@@ -180,31 +195,21 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     std::vector<JumpPlan> plans(B + 1);
     uint32_t max_depth = 0;
     for (uint32_t cnt = 1; cnt <= B; ++cnt) {
-        plan_jump_tables(tabs.infix[cnt], want_depth, plans[cnt]);
+        plan_jump_tables(tabs.infix[cnt], want_depth, plans[cnt], E, h.n_bwt, sigma, cnt);
         max_depth = std::max(max_depth, plans[cnt].max_depth);
     }
-    std::vector<std::vector<JtEntry>> uni(max_depth + 1);
-    std::vector<std::vector<uint32_t>> lof(max_depth + 1);
-    for (uint32_t d = 1; d <= max_depth; ++d) {
-        const uint64_t n = 1ull << (2 * d), pmask = (1ull << (2 * (d - 1))) - 1;
-        uni[d].resize(n); lof[d].resize(n);
-        for (uint64_t key = 0; key < n; ++key) {
-            Node par;
-            if (d == 1) { par.lo_f = 0; par.lo_r = 0; par.size = cx.n_bwt; }
-            else { par.lo_f = lof[d - 1][key & pmask]; par.lo_r = uni[d - 1][key & pmask].lo_r; par.size = uni[d - 1][key & pmask].size; }
-            const Node m = sigma == 5 ? extend_right<5>(par, (uint32_t)(key >> (2 * (d - 1))), cx)
-                                      : extend_right<4>(par, (uint32_t)(key >> (2 * (d - 1))), cx);
-            uni[d][key].lo_r = m.lo_r; uni[d][key].size = m.size; lof[d][key] = m.lo_f;
-        }
-    }
+    std::vector<std::vector<JtFull>> full(max_depth + 1);
+    build_host_jump_levels(cx, sigma, max_depth, full);
     std::vector<SearchStart> starts((B + 1) * kMaxSearches);
     for (uint32_t cnt = 1; cnt <= B; ++cnt)
         for (uint32_t s = 0; s < kMaxSearches; ++s) {
             const uint32_t d = plans[cnt].depth[s];
             SearchStart& S = starts[cnt * kMaxSearches + s];
-            S.uni = d ? uni[d].data() : nullptr;
-            S.lof = (d && plans[cnt].need_lof[s]) ? lof[d].data() : nullptr;
+            std::memset(&S, 0, sizeof(S));
+            S.full = d ? full[d].data() : nullptr; // (the device uses 8-byte entries where SA(T) is not needed: same values)
             S.a = plans[cnt].a[s]; S.d = d;
+            S.n_var = std::max(1u, plans[cnt].n_var[s]);
+            S.var = plans[cnt].variants.data() + plans[cnt].var_off[s];
         }
     cx.starts = starts.data();
     std::memset(out, 0, text_len * (value_bits / 8));
@@ -259,28 +264,18 @@ int hs_locate(const void* blob, uint32_t K, uint32_t E, int revcompl, uint64_t t
     cx.loc_rows = nullptr;
     const uint32_t want_depth = jump_depth < 0 ? default_jump_depth(h.n_bwt) : (uint32_t)jump_depth;
     JumpPlan plan;
-    plan_jump_tables(tabs.infix[1], want_depth, plan);
-    std::vector<std::vector<JtEntry>> uni(plan.max_depth + 1);
-    std::vector<std::vector<uint32_t>> lof(plan.max_depth + 1);
-    for (uint32_t d = 1; d <= plan.max_depth; ++d) {
-        const uint64_t n = 1ull << (2 * d), pmask = (1ull << (2 * (d - 1))) - 1;
-        uni[d].resize(n); lof[d].resize(n);
-        for (uint64_t key = 0; key < n; ++key) {
-            Node par;
-            if (d == 1) { par.lo_f = 0; par.lo_r = 0; par.size = cx.n_bwt; }
-            else { par.lo_f = lof[d - 1][key & pmask]; par.lo_r = uni[d - 1][key & pmask].lo_r; par.size = uni[d - 1][key & pmask].size; }
-            const Node m = sigma == 5 ? extend_right<5>(par, (uint32_t)(key >> (2 * (d - 1))), cx)
-                                      : extend_right<4>(par, (uint32_t)(key >> (2 * (d - 1))), cx);
-            uni[d][key].lo_r = m.lo_r; uni[d][key].size = m.size; lof[d][key] = m.lo_f;
-        }
-    }
+    plan_jump_tables(tabs.infix[1], want_depth, plan, E, h.n_bwt, sigma, 1);
+    std::vector<std::vector<JtFull>> full(plan.max_depth + 1);
+    build_host_jump_levels(cx, sigma, plan.max_depth, full);
     std::vector<SearchStart> starts(2 * kMaxSearches);
     for (uint32_t s = 0; s < kMaxSearches; ++s) {
         const uint32_t d = plan.depth[s];
         SearchStart& S = starts[kMaxSearches + s];
-        S.uni = d ? uni[d].data() : nullptr;
-        S.lof = (d && plan.need_lof[s]) ? lof[d].data() : nullptr;
+        std::memset(&S, 0, sizeof(S));
+        S.full = d ? full[d].data() : nullptr;
         S.a = plan.a[s]; S.d = d;
+        S.n_var = std::max(1u, plan.n_var[s]);
+        S.var = plan.variants.data() + plan.var_off[s];
     }
     cx.starts = starts.data();
     std::vector<WorkRange> ranges;
