@@ -566,7 +566,7 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
             for (uint32_t cnt = 0; cnt <= tabs.B; ++cnt) {
                 JumpPlan& pl = plans[cnt];
                 if (cnt == 0) { pl = JumpPlan(); std::memset(pl.depth, 0, sizeof(pl.depth)); pl.max_depth = 0; continue; }
-                plan_jump_tables(tabs.infix[cnt], maxd, pl, p->E, ix->h.n_bwt, ix->h.sigma, cnt);
+                plan_jump_tables(tabs.infix[cnt], maxd, pl, p->E, ix->h.n_bwt, ix->h.sigma, cnt, tabs.B > 1 && !loc);
                 plan_depth = std::max(plan_depth, pl.max_depth);
             }
             needs = jump_needs(plans);
@@ -609,7 +609,11 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
         CU(cudaMemcpyAsync(ix->d_variants, variants.data(), variants.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
         for (uint32_t cnt = 1; cnt <= tabs.B; ++cnt)
             for (uint32_t s2 = 0; s2 < kMaxSearches; ++s2)
-                starts[(size_t)cnt * kMaxSearches + s2].var = ix->d_variants + base_of[cnt] + plans[cnt].var_off[s2];
+            {
+                SearchStart& S = starts[(size_t)cnt * kMaxSearches + s2];
+                S.var = ix->d_variants + base_of[cnt] + plans[cnt].var_off[s2];
+                S.set0 = plans[cnt].variants.empty() ? 0xffffffffu : variants[base_of[cnt] + plans[cnt].var_off[s2]];
+            }
     }
     // search tables: step words, then the jump-table starts, in one device scratch buffer
     const size_t step_bytes = tabs.steps.size() * sizeof(uint32_t);

@@ -397,7 +397,7 @@ struct SearchStart {
     uint32_t a;           // pattern offset of the first character of the key window
     uint32_t d;           // depth of the table
     uint32_t n_var;
-    uint32_t pad;
+    uint32_t set0;        // var[0], kept inline: the first entry needs no extra read
 };
 
 struct MapCtx {
@@ -605,29 +605,35 @@ GMB_HD void jump_lookup(const SearchStart& S, uint32_t key, uint32_t& lo_f, uint
 // start the infix search number st.s on the current strand
 // (BLK = false is the one-k-mer-per-chain instantiation: cnt == 1 is a compile-time fact there, so all the
 // window bookkeeping disappears and the count stays in a register)
+// (the one-k-mer instantiation, BLK = false, enters every search through its error-free prefix only: the host
+// plans no substituted keys for it, which keeps the E = 0 path lean)
 template <int KW, bool BLK, int SIGMA>
 GMB_HD void chain_start(Chain<KW, SIGMA>& st, const MapCtx& cx, unsigned long long* lut_reads)
 {
+    constexpr bool VAR = BLK;
     const SearchStart S = cx.starts[(BLK ? st.cnt : 1u) * kMaxSearches + st.s];
     st.e = 0; st.lvmask = 0; st.win = kNoWin; st.leaf_e = 0; st.thin = false;
     if (S.uni == nullptr && S.full == nullptr) {
         st.lo_f = 0; st.lo_r = 0; st.size = cx.n_bwt; st.t = 0; st.nsub = 1;
     } else {
 #if defined(__CUDA_ARCH__)
-        const uint32_t set = __ldg(S.var + st.var);
+        const uint32_t set = (!VAR || st.var == 0) ? S.set0 : __ldg(S.var + st.var);
 #else
-        const uint32_t set = S.var[st.var];
+        const uint32_t set = (!VAR || st.var == 0) ? S.set0 : S.var[st.var];
 #endif
         if (st.strand == 1 && st.s == 0 && set == 0xffffffffu) { st.lo_f = st.pre_lo_f; st.lo_r = st.pre_lo_r; st.size = st.pre_size; st.nsub = 1; }
         else if (set == kDeadVariant || (SIGMA == 5 && st.pat.has_n(S.a, S.d))) { st.lo_f = 0; st.lo_r = 0; st.size = 0; st.nsub = 1; } // N never matches
         else {
             // substitute: offset p of the set gets one of the three other characters (XOR with 1..3), chosen by the
             // base-3 digits of st.sub
-            uint32_t key = st.pat.bits(S.a, S.d), e = 0, q = st.sub, n3 = 1;
+            uint32_t key = st.pat.bits(S.a, S.d), e = 0, n3 = 1;
+            if (VAR && set != 0xffffffffu) {
+                uint32_t q = st.sub;
 #pragma unroll
-            for (uint32_t k = 0; k < kMaxE; ++k) {
-                const uint32_t p = (set >> (8 * k)) & 0xffu;
-                if (p != 0xffu) { key ^= (1u + q % 3u) << (2u * p); q /= 3u; n3 *= 3u; ++e; }
+                for (uint32_t k = 0; k < kMaxE; ++k) {
+                    const uint32_t p = (set >> (8 * k)) & 0xffu;
+                    if (p != 0xffu) { key ^= (1u + q % 3u) << (2u * p); q /= 3u; n3 *= 3u; ++e; }
+                }
             }
             jump_lookup(S, key, st.lo_f, st.lo_r, st.size);
             st.e = e; st.nsub = n3;
@@ -864,10 +870,12 @@ GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, Fetch
         }
         if (cand == 0) {
             // this entry into the search is exhausted: its next key, the next set of substituted offsets, ...
-            if (++st.sub < st.nsub) { chain_start<KW, BLK, SIGMA>(st, cx, lut_reads); return true; }
-            st.sub = 0;
-            if (++st.var < cx.starts[(BLK ? st.cnt : 1u) * kMaxSearches + st.s].n_var) { chain_start<KW, BLK, SIGMA>(st, cx, lut_reads); return true; }
-            st.var = 0;
+            if constexpr (BLK) {
+                if (++st.sub < st.nsub) { chain_start<KW, BLK, SIGMA>(st, cx, lut_reads); return true; }
+                st.sub = 0;
+                if (++st.var < cx.starts[st.cnt * kMaxSearches + st.s].n_var) { chain_start<KW, BLK, SIGMA>(st, cx, lut_reads); return true; }
+                st.var = 0;
+            }
             // ... then the next search, the next strand, or done
             if (++st.s == cx.n_search) {
                 st.s = 0;

@@ -157,7 +157,7 @@ double expected_fetches(const SchemeDef& sd, const uint32_t* len, uint32_t E, do
 // steepest descent over single-character moves between parts, from the reference's equal split
 void choose_part_lengths(const SchemeDef& sd, uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t B, uint32_t block_bases, uint32_t* len)
 {
-    const bool av = variants_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u);
+    const bool av = B > 1 && variants_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u); // (the one-k-mer kernel has none)
     const uint32_t nb = sd.n_blocks;
     if (nb < 2 || n_bwt == 0 || K < 2 * nb) return;
     const uint32_t jump_max = default_jump_depth(n_bwt);
@@ -282,7 +282,7 @@ uint32_t model_block_kmers(uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t bloc
         for (uint32_t b = 0; b < sd.n_blocks; ++b) len[b] = Li / sd.n_blocks + (b < Li % sd.n_blocks);
         choose_part_lengths(sd, Li, E, n_bwt, B, block_bases, len);
         cost[B] = expected_fetches(sd, len, E, (double)n_bwt, B, default_jump_depth(n_bwt), block_bases,
-                                   variants_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u));
+                                   B > 1 && variants_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u));
         if (top == 0 || cost[B] < best) best = cost[B];
         top = B;
     }
@@ -376,13 +376,13 @@ void enumerate_variants(const uint32_t* st, uint32_t d, uint32_t E, uint32_t a, 
 } // namespace
 
 void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan, uint32_t E, uint64_t n_bwt, uint32_t sigma,
-                      uint32_t block_kmers)
+                      uint32_t block_kmers, bool allow_variants)
 {
     plan.max_depth = 0;
     plan.variants.clear();
     for (uint32_t s = 0; s < kMaxSearches; ++s) { plan.depth[s] = 0; plan.a[s] = 0; plan.need_lof[s] = false; plan.var_off[s] = 0; plan.n_var[s] = 0; }
     const uint32_t K = tabs.K;
-    const bool allow = variants_enabled(n_bwt, sigma);
+    const bool allow = allow_variants && variants_enabled(n_bwt, sigma);
     if (max_depth > 16) max_depth = 16;
     std::vector<uint32_t> ub(K), lb(K), rem(K);
     SearchProfile P;
@@ -410,6 +410,8 @@ void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan
         plan.max_depth = std::max(plan.max_depth, d);
     }
 }
+
+bool jump_variants_enabled(uint64_t n_bwt, uint32_t sigma) { return variants_enabled(n_bwt, sigma); }
 
 uint32_t default_jump_depth(uint64_t n_bwt)
 {

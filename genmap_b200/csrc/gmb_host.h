@@ -52,8 +52,10 @@ struct JumpPlan {
     std::vector<uint32_t> variants;
     uint32_t max_depth;
 };
+// allow_variants: the launch uses the blocked instantiation of the kernel (the one-k-mer instantiation enters every
+// search through its error-free prefix only)
 void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan, uint32_t E = 0, uint64_t n_bwt = 0, uint32_t sigma = 4,
-                      uint32_t block_kmers = 1);
+                      uint32_t block_kmers = 1, bool allow_variants = false);
 // ceil(log4(n_bwt)) clamped to [1,16]: less than one expected occurrence per table entry
 uint32_t default_jump_depth(uint64_t n_bwt);
 

@@ -195,7 +195,7 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     std::vector<JumpPlan> plans(B + 1);
     uint32_t max_depth = 0;
     for (uint32_t cnt = 1; cnt <= B; ++cnt) {
-        plan_jump_tables(tabs.infix[cnt], want_depth, plans[cnt], E, h.n_bwt, sigma, cnt);
+        plan_jump_tables(tabs.infix[cnt], want_depth, plans[cnt], E, h.n_bwt, sigma, cnt, B > 1);
         max_depth = std::max(max_depth, plans[cnt].max_depth);
     }
     std::vector<std::vector<JtFull>> full(max_depth + 1);
@@ -210,6 +210,7 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
             S.a = plans[cnt].a[s]; S.d = d;
             S.n_var = std::max(1u, plans[cnt].n_var[s]);
             S.var = plans[cnt].variants.data() + plans[cnt].var_off[s];
+            S.set0 = S.var[0];
         }
     cx.starts = starts.data();
     std::memset(out, 0, text_len * (value_bits / 8));
@@ -264,7 +265,7 @@ int hs_locate(const void* blob, uint32_t K, uint32_t E, int revcompl, uint64_t t
     cx.loc_rows = nullptr;
     const uint32_t want_depth = jump_depth < 0 ? default_jump_depth(h.n_bwt) : (uint32_t)jump_depth;
     JumpPlan plan;
-    plan_jump_tables(tabs.infix[1], want_depth, plan, E, h.n_bwt, sigma, 1);
+    plan_jump_tables(tabs.infix[1], want_depth, plan, E, h.n_bwt, sigma, 1, false);
     std::vector<std::vector<JtFull>> full(plan.max_depth + 1);
     build_host_jump_levels(cx, sigma, plan.max_depth, full);
     std::vector<SearchStart> starts(2 * kMaxSearches);
@@ -276,6 +277,7 @@ int hs_locate(const void* blob, uint32_t K, uint32_t E, int revcompl, uint64_t t
         S.a = plan.a[s]; S.d = d;
         S.n_var = std::max(1u, plan.n_var[s]);
         S.var = plan.variants.data() + plan.var_off[s];
+        S.set0 = S.var[0];
     }
     cx.starts = starts.data();
     std::vector<WorkRange> ranges;
