@@ -416,8 +416,8 @@ def main():
                 "traffic": traffic, "peak_source": peak_src,
                 "rank_block_bytes": blk,
                 "rank_block_bytes_per_position": r["fetches"] * blk / max(r["searched"], 1),
-                # stricter figure: + jump-table entries (12 B) + pattern text (K/4 -> 16 B) + result (2 B)
-                "total_algorithmic_bytes_per_position": (r["fetches"] * blk + r["lut_reads"] * 12.0) / max(r["searched"], 1) + 18.0,
+                # stricter figure: + jump-table entries (16 B) + pattern text (K/4 -> 16 B) + result (2 B)
+                "total_algorithmic_bytes_per_position": (r["fetches"] * blk + r["lut_reads"] * 16.0) / max(r["searched"], 1) + 18.0,
                 # the path is bound by the RATE of dependent random memory requests, not by their bytes: one request
                 # per rank block / jump-table entry; ceiling measured with tools/randread.cu (profiles/r01/s1_randread.txt)
                 "random_requests_per_s": (r["fetches"] + r["lut_reads"]) / len(r["batches"]) / (r["kernel_ms"] * 1e-3),

@@ -125,14 +125,17 @@ void fill_ctx(const gmb_index* ix, MapCtx& cx)
 
 struct JumpNeeds { bool uni[17] = {}, lof[17] = {}, full[17] = {}; uint32_t top = 0; };
 
-JumpNeeds jump_needs(const std::vector<JumpPlan>& plans)
+// use_full: the blocked instantiation reads both intervals as one 16-byte entry; the one-k-mer instantiation keeps
+// 8-byte entries plus a separate array for the interval in SA(T)
+JumpNeeds jump_needs(const std::vector<JumpPlan>& plans, bool use_full)
 {
     JumpNeeds n;
     for (const JumpPlan& plan : plans)
         for (uint32_t s = 0; s < kMaxSearches; ++s) {
             const uint32_t d = plan.depth[s];
             if (!d) continue;
-            if (plan.need_lof[s]) n.full[d] = true; else n.uni[d] = true;
+            if (plan.need_lof[s] && use_full) n.full[d] = true;
+            else { n.uni[d] = true; if (plan.need_lof[s]) n.lof[d] = true; }
             n.top = std::max(n.top, d);
         }
     return n;
@@ -143,7 +146,7 @@ void evict_stale_jump_tables(gmb_index* ix, const JumpNeeds& n)
 {
     for (uint32_t d = kJumpKeep + 1; d <= 16; ++d) {
         if (ix->jt_uni[d] && !n.uni[d]) { cudaFree(ix->jt_uni[d]); ix->jt_uni[d] = nullptr; }
-        if (ix->jt_lof[d]) { cudaFree(ix->jt_lof[d]); ix->jt_lof[d] = nullptr; }
+        if (ix->jt_lof[d] && !n.lof[d]) { cudaFree(ix->jt_lof[d]); ix->jt_lof[d] = nullptr; }
         if (ix->jt_full[d] && !n.full[d]) { cudaFree(ix->jt_full[d]); ix->jt_full[d] = nullptr; }
     }
 }
@@ -156,6 +159,7 @@ size_t missing_jump_bytes(const gmb_index* ix, const JumpNeeds& n)
     for (uint32_t d = 1; d <= 16; ++d) {
         const size_t e = (size_t)1 << (2 * d);
         if (n.uni[d] && !ix->jt_uni[d]) { bytes += e * sizeof(JtEntry); deepest_missing = d; }
+        if (n.lof[d] && !ix->jt_lof[d]) { bytes += e * sizeof(uint32_t); deepest_missing = d; }
         if (n.full[d] && !ix->jt_full[d]) { bytes += e * sizeof(JtFull); deepest_missing = d; }
     }
     for (uint32_t d = 1; d < deepest_missing; ++d) // every level below is built as uni + lof on the way
@@ -168,18 +172,19 @@ int ensure_jump_tables(gmb_index* ix, const JumpNeeds& n, cudaStream_t stream)
 {
     uint32_t top = 0;
     for (uint32_t d = 1; d <= 16; ++d)
-        if ((n.uni[d] && !ix->jt_uni[d]) || (n.full[d] && !ix->jt_full[d])) top = d;
+        if ((n.uni[d] && !ix->jt_uni[d]) || (n.lof[d] && !ix->jt_lof[d]) || (n.full[d] && !ix->jt_full[d])) top = d;
     if (top == 0) return GMB_OK; // everything this call needs is cached
     MapCtx cx;
     fill_ctx(ix, cx);
     for (uint32_t d = 1; d <= top; ++d) {
         const size_t e = (size_t)1 << (2 * d);
         const bool parent_for_later = d < top; // deeper levels extend this one: needs uni + lof
-        if ((parent_for_later || n.uni[d]) && !(ix->jt_uni[d] && (!parent_for_later || ix->jt_lof[d]))) {
+        const bool want_lof = parent_for_later || n.lof[d];
+        if ((parent_for_later || n.uni[d]) && !(ix->jt_uni[d] && (!want_lof || ix->jt_lof[d]))) {
             if (ix->jt_uni[d]) { cudaFree(ix->jt_uni[d]); ix->jt_uni[d] = nullptr; }
             if (ix->jt_lof[d]) { cudaFree(ix->jt_lof[d]); ix->jt_lof[d] = nullptr; }
             cudaError_t err = cudaMalloc(&ix->jt_uni[d], e * sizeof(JtEntry));
-            if (err == cudaSuccess && parent_for_later) err = cudaMalloc(&ix->jt_lof[d], e * sizeof(uint32_t));
+            if (err == cudaSuccess && want_lof) err = cudaMalloc(&ix->jt_lof[d], e * sizeof(uint32_t));
             if (err == cudaSuccess)
                 err = build_jump_level(cx, ix->h.sigma, d, ix->jt_uni[d - 1], ix->jt_lof[d - 1], ix->jt_uni[d], ix->jt_lof[d], nullptr, stream);
             if (err != cudaSuccess) return cuda_fail(err, "jump table");
@@ -561,6 +566,7 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
         uint32_t maxd = want < 0 ? default_jump_depth(ix->h.n_bwt) : (uint32_t)want;
         if (maxd > 16) maxd = 16;
         JumpNeeds needs;
+        const bool use_full = tabs.B > 1 && !loc; // the blocked instantiation
         for (;;) {
             plan_depth = 0;
             for (uint32_t cnt = 0; cnt <= tabs.B; ++cnt) {
@@ -569,7 +575,7 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
                 plan_jump_tables(tabs.infix[cnt], maxd, pl, p->E, ix->h.n_bwt, ix->h.sigma, cnt, tabs.B > 1 && !loc);
                 plan_depth = std::max(plan_depth, pl.max_depth);
             }
-            needs = jump_needs(plans);
+            needs = jump_needs(plans, use_full);
             if (want >= 0 || maxd <= 1) break; // a fixed depth is taken as it is
             // automatic depth: what is missing must fit comfortably in free HBM once stale levels are dropped
             evict_stale_jump_tables(ix, needs);
@@ -585,9 +591,9 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
                 const uint32_t d = plans[cnt].depth[s2];
                 SearchStart& S = starts[(size_t)cnt * kMaxSearches + s2];
                 std::memset(&S, 0, sizeof(S));
-                const bool full = d && plans[cnt].need_lof[s2];
+                const bool full = d && plans[cnt].need_lof[s2] && use_full;
                 S.uni = (d && !full) ? ix->jt_uni[d] : nullptr;
-                S.lof = nullptr;
+                S.lof = (d && !full && plans[cnt].need_lof[s2]) ? ix->jt_lof[d] : nullptr;
                 S.full = full ? ix->jt_full[d] : nullptr;
                 S.a = plans[cnt].a[s2];
                 S.d = d;

@@ -602,6 +602,20 @@ GMB_HD void jump_lookup(const SearchStart& S, uint32_t key, uint32_t& lo_f, uint
 #endif
 }
 
+// the one-k-mer instantiation reads 8-byte entries (+ the separate SA(T) array when needed): its tables never hold
+// 16-byte entries
+GMB_HD void jump_lookup_lean(const SearchStart& S, uint32_t key, uint32_t& lo_f, uint32_t& lo_r, uint32_t& size)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.global.nc.L2::64B.v2.u32 {%0,%1}, [%2];" : "=r"(lo_r), "=r"(size) : "l"(S.uni + key));
+    lo_f = 0u;
+    if (S.lof) asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(lo_f) : "l"(S.lof + key));
+#else
+    lo_r = S.uni[key].lo_r; size = S.uni[key].size;
+    lo_f = S.lof ? S.lof[key] : 0u;
+#endif
+}
+
 // start the infix search number st.s on the current strand
 // (BLK = false is the one-k-mer-per-chain instantiation: cnt == 1 is a compile-time fact there, so all the
 // window bookkeeping disappears and the count stays in a register)
@@ -610,16 +624,29 @@ GMB_HD void jump_lookup(const SearchStart& S, uint32_t key, uint32_t& lo_f, uint
 template <int KW, bool BLK, int SIGMA>
 GMB_HD void chain_start(Chain<KW, SIGMA>& st, const MapCtx& cx, unsigned long long* lut_reads)
 {
-    constexpr bool VAR = BLK;
-    const SearchStart S = cx.starts[(BLK ? st.cnt : 1u) * kMaxSearches + st.s];
+    if constexpr (!BLK) {
+        const SearchStart& S = cx.starts[kMaxSearches + st.s];
+        st.e = 0; st.lvmask = 0; st.win = kNoWin; st.leaf_e = 0; st.thin = false;
+        if (S.uni == nullptr) {
+            st.lo_f = 0; st.lo_r = 0; st.size = cx.n_bwt; st.t = 0;
+        } else {
+            if (st.strand == 1 && st.s == 0) { st.lo_f = st.pre_lo_f; st.lo_r = st.pre_lo_r; st.size = st.pre_size; }
+            else if (S.set0 == kDeadVariant || (SIGMA == 5 && st.pat.has_n(S.a, S.d))) { st.lo_f = 0; st.lo_r = 0; st.size = 0; } // N never matches
+            else jump_lookup_lean(S, st.pat.bits(S.a, S.d), st.lo_f, st.lo_r, st.size);
+            st.t = S.d;
+            if (lut_reads) *lut_reads += 1;
+        }
+        return;
+    } else {
+    const SearchStart S = cx.starts[st.cnt * kMaxSearches + st.s];
     st.e = 0; st.lvmask = 0; st.win = kNoWin; st.leaf_e = 0; st.thin = false;
     if (S.uni == nullptr && S.full == nullptr) {
         st.lo_f = 0; st.lo_r = 0; st.size = cx.n_bwt; st.t = 0; st.nsub = 1;
     } else {
 #if defined(__CUDA_ARCH__)
-        const uint32_t set = (!VAR || st.var == 0) ? S.set0 : __ldg(S.var + st.var);
+        const uint32_t set = st.var == 0 ? S.set0 : __ldg(S.var + st.var);
 #else
-        const uint32_t set = (!VAR || st.var == 0) ? S.set0 : S.var[st.var];
+        const uint32_t set = st.var == 0 ? S.set0 : S.var[st.var];
 #endif
         if (st.strand == 1 && st.s == 0 && set == 0xffffffffu) { st.lo_f = st.pre_lo_f; st.lo_r = st.pre_lo_r; st.size = st.pre_size; st.nsub = 1; }
         else if (set == kDeadVariant || (SIGMA == 5 && st.pat.has_n(S.a, S.d))) { st.lo_f = 0; st.lo_r = 0; st.size = 0; st.nsub = 1; } // N never matches
@@ -627,7 +654,7 @@ GMB_HD void chain_start(Chain<KW, SIGMA>& st, const MapCtx& cx, unsigned long lo
             // substitute: offset p of the set gets one of the three other characters (XOR with 1..3), chosen by the
             // base-3 digits of st.sub
             uint32_t key = st.pat.bits(S.a, S.d), e = 0, n3 = 1;
-            if (VAR && set != 0xffffffffu) {
+            if (set != 0xffffffffu) {
                 uint32_t q = st.sub;
 #pragma unroll
                 for (uint32_t k = 0; k < kMaxE; ++k) {
@@ -640,6 +667,7 @@ GMB_HD void chain_start(Chain<KW, SIGMA>& st, const MapCtx& cx, unsigned long lo
         }
         st.t = S.d;
         if (lut_reads) *lut_reads += 1;
+    }
     }
 }
 
@@ -657,11 +685,12 @@ GMB_HD void chain_begin_block(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx
     // the reverse strand's first jump-table entry does not depend on the forward search: request it now so
     // that its latency overlaps the forward strand instead of starting the reverse strand with a stall
     const SearchStart S0 = cx.starts[(BLK ? st.cnt : 1u) * kMaxSearches];
-    if (cx.n_strands > 1 && (S0.uni != nullptr || S0.full != nullptr)) {
+    if (cx.n_strands > 1 && (S0.uni != nullptr || (BLK && S0.full != nullptr))) {
         Pattern<KW, SIGMA> rc = st.pat;
         rc.reverse_complement(cx.K + (BLK ? st.cnt : 1u) - 1);
         if (SIGMA == 5 && rc.has_n(S0.a, S0.d)) { st.pre_lo_f = 0; st.pre_lo_r = 0; st.pre_size = 0; }
-        else jump_lookup(S0, rc.bits(S0.a, S0.d), st.pre_lo_f, st.pre_lo_r, st.pre_size);
+        else if (BLK) jump_lookup(S0, rc.bits(S0.a, S0.d), st.pre_lo_f, st.pre_lo_r, st.pre_size);
+        else jump_lookup_lean(S0, rc.bits(S0.a, S0.d), st.pre_lo_f, st.pre_lo_r, st.pre_size);
     }
     chain_start<KW, BLK, SIGMA>(st, cx, lut_reads);
 }

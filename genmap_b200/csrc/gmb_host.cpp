@@ -283,6 +283,9 @@ uint32_t model_block_kmers(uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t bloc
         choose_part_lengths(sd, Li, E, n_bwt, B, block_bases, len);
         cost[B] = expected_fetches(sd, len, E, (double)n_bwt, B, default_jump_depth(n_bwt), block_bases,
                                    B > 1 && variants_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u));
+        // a Dna5 needle longer than 32 characters no longer fits one register word per plane: measured 1.55x slower per
+        // fetch (profiles/r01/s25_sweep_dna5.txt vs s20_sweep_dna5.txt)
+        if (block_bases == kBlockBases5 && K + B - 1 > 32 && K <= 32) cost[B] *= 1.5;
         if (top == 0 || cost[B] < best) best = cost[B];
         top = B;
     }

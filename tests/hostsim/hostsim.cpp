@@ -200,13 +200,19 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     }
     std::vector<std::vector<JtFull>> full(max_depth + 1);
     build_host_jump_levels(cx, sigma, max_depth, full);
+    std::vector<std::vector<JtEntry>> uni(max_depth + 1);   // what the one-k-mer instantiation reads (B == 1)
+    std::vector<std::vector<uint32_t>> lof(max_depth + 1);
+    if (B == 1)
+        for (uint32_t d = 1; d <= max_depth; ++d)
+            for (const JtFull& q : full[d]) { uni[d].push_back(JtEntry{q.lo_r, q.size}); lof[d].push_back(q.lo_f); }
     std::vector<SearchStart> starts((B + 1) * kMaxSearches);
     for (uint32_t cnt = 1; cnt <= B; ++cnt)
         for (uint32_t s = 0; s < kMaxSearches; ++s) {
             const uint32_t d = plans[cnt].depth[s];
             SearchStart& S = starts[cnt * kMaxSearches + s];
             std::memset(&S, 0, sizeof(S));
-            S.full = d ? full[d].data() : nullptr; // (the device uses 8-byte entries where SA(T) is not needed: same values)
+            if (B == 1) { S.uni = d ? uni[d].data() : nullptr; S.lof = (d && plans[cnt].need_lof[s]) ? lof[d].data() : nullptr; }
+            else S.full = d ? full[d].data() : nullptr; // (the device uses 8-byte entries where SA(T) is not needed: same values)
             S.a = plans[cnt].a[s]; S.d = d;
             S.n_var = std::max(1u, plans[cnt].n_var[s]);
             S.var = plans[cnt].variants.data() + plans[cnt].var_off[s];
@@ -268,12 +274,17 @@ int hs_locate(const void* blob, uint32_t K, uint32_t E, int revcompl, uint64_t t
     plan_jump_tables(tabs.infix[1], want_depth, plan, E, h.n_bwt, sigma, 1, false);
     std::vector<std::vector<JtFull>> full(plan.max_depth + 1);
     build_host_jump_levels(cx, sigma, plan.max_depth, full);
+    std::vector<std::vector<JtEntry>> uni(plan.max_depth + 1);
+    std::vector<std::vector<uint32_t>> lof(plan.max_depth + 1);
+    for (uint32_t d = 1; d <= plan.max_depth; ++d)
+        for (const JtFull& q : full[d]) { uni[d].push_back(JtEntry{q.lo_r, q.size}); lof[d].push_back(q.lo_f); }
     std::vector<SearchStart> starts(2 * kMaxSearches);
     for (uint32_t s = 0; s < kMaxSearches; ++s) {
         const uint32_t d = plan.depth[s];
         SearchStart& S = starts[kMaxSearches + s];
         std::memset(&S, 0, sizeof(S));
-        S.full = d ? full[d].data() : nullptr;
+        S.uni = d ? uni[d].data() : nullptr;
+        S.lof = (d && plan.need_lof[s]) ? lof[d].data() : nullptr;
         S.a = plan.a[s]; S.d = d;
         S.n_var = std::max(1u, plan.n_var[s]);
         S.var = plan.variants.data() + plan.var_off[s];
