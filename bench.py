@@ -425,6 +425,8 @@ def main():
                 # what the DRAM actually does: 64-byte accesses per second (ncu traffic / 64 B / kernel time); the
                 # random-read microbenchmark tops out at ~38 G/s of these
                 "dram_64B_accesses_per_s": (traffic / 64.0 / (r["kernel_ms"] * 1e-3)) if traffic else None,
+                # the same fraction on the stricter figure (rank blocks + 16-byte jump-table entries)
+                "frac_with_table_reads": (r["fetches"] * blk + r["lut_reads"] * 16.0) / len(r["batches"]) / (r["kernel_ms"] * 1e-3) / 1e9 / peak,
                 "jump_table_depth": r["jump_depth"], "kernel_ms_per_launch": r["kernel_ms"]}
 
     main_r["E"], main_r["batch"] = E, batch
