@@ -303,3 +303,30 @@ def test_part_length_model_changes_the_tree_not_the_counts(monkeypatch):
     assert res["model", 24, 2][1] < 0.85 * res["equal", 24, 2][1]
     assert res["model", 36, 3][1] < 0.9 * res["equal", 36, 3][1]
     assert res["model", 24, 1][1] <= res["equal", 24, 1][1]
+
+
+def test_substituted_jump_table_keys_change_the_accesses_not_the_counts(monkeypatch):
+    """Entering a search once per admissible string (JumpPlan.variants) against walking from its error-free prefix:
+    identical counts, fewer rank-block fetches, more table reads; all E, both value types, -ep, selection."""
+    import genmap_b200 as gm
+    seqs = gm.synth_genome(2_000_000, 2, 78)
+    hs = T.HostSim(seqs, with_sa=True)
+    stf = np.array([0, 1], dtype=np.uint32)
+    res = {}
+    for name, val in (("walk", "0"), ("keys", "1")):
+        monkeypatch.setenv("GMB_JUMP_VARIANTS", val)
+        for K, E, n in ((24, 1, 4000), (24, 2, 3000), (30, 3, 300), (36, 4, 60)):
+            out, f = hs.map(K, E, pos_begin=400_000, pos_end=400_000 + n, return_fetches=True)
+            res[name, K, E] = (out, f, hs.last_lut_reads)
+        res[name, "ep"] = hs.map(20, 2, seq_to_file=stf, file_no=1, exclude_pseudo=True, pos_begin=1000, pos_end=3000, value_bits=8)
+        res[name, "sel"] = hs.map(22, 2, revcompl=False, intervals=[(500, 900), (999_990, 1_000_400)])
+    for key in [k for k in res if k[0] == "walk"]:
+        a, b = res[key], res[("keys",) + key[1:]]
+        if isinstance(a, tuple):
+            assert np.array_equal(a[0], b[0]), key
+        else:
+            assert np.array_equal(a, b), key
+    for K, E in ((24, 2), (30, 3), (36, 4)):
+        walk, keys = res["walk", K, E], res["keys", K, E]
+        assert keys[1] + keys[2] < 0.85 * (walk[1] + walk[2]), (K, E, walk[1:], keys[1:])  # fewer accesses in total
+        assert keys[2] > walk[2]                                                            # ... through more table reads
