@@ -26,7 +26,12 @@ cudaError_t launch_t(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
     if (L.sigma == 5)
         return L.cx.B > 1 ? launch_b<KW, COUNT, OutT, EP, true, 5>(L, sm_count, stream) : launch_b<KW, COUNT, OutT, EP, false, 5>(L, sm_count, stream);
-    return L.cx.B > 1 ? launch_b<KW, COUNT, OutT, EP, true, 4>(L, sm_count, stream) : launch_b<KW, COUNT, OutT, EP, false, 4>(L, sm_count, stream);
+    if (L.cx.B <= 1) return launch_b<KW, COUNT, OutT, EP, false, 4>(L, sm_count, stream);
+    // Blocked Dna4 kernels: up to E = 2 they are bound by instruction issue since the jump tables answer for the dense
+    // top of the trie, and 3 CTAs x 80 registers (no spills) beat 4 x 64; E >= 3 still wants the extra chains in flight
+    // (profiles/r01/s28_sweep_*.txt: E=1 35.0 -> 31.9 ms, E=2 35.2 -> 33.9 ms, E=3 19.7 -> 22.6 ms with 3 CTAs)
+    return L.E <= 2 ? launch_b<KW, COUNT, OutT, EP, true, 4, false, 3>(L, sm_count, stream)
+                    : launch_b<KW, COUNT, OutT, EP, true, 4, false, GMB_MIN_BLOCKS>(L, sm_count, stream);
 }
 
 template <int KW>

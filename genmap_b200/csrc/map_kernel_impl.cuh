@@ -28,8 +28,9 @@ struct SmemFrames {
 __host__ __device__ inline uint32_t align32(uint32_t x) { return (x + 31u) & ~31u; }
 constexpr uint32_t kStartWords = sizeof(SearchStart) / 4;
 
-template <int KW, bool COUNT, typename OutT, bool EP, bool BLK, int SIGMA, bool LOC = false>
-__global__ void __launch_bounds__(kThreads, (SIGMA == 5 && BLK) ? GMB_MIN_BLOCKS5 : GMB_MIN_BLOCKS) map_kernel(const MapLaunch L)
+// MINB: resident CTAs per SM the register allocation must allow (Dna4; Dna5 blocked: GMB_MIN_BLOCKS5)
+template <int KW, bool COUNT, typename OutT, bool EP, bool BLK, int SIGMA, bool LOC = false, int MINB = GMB_MIN_BLOCKS>
+__global__ void __launch_bounds__(kThreads, (SIGMA == 5 && BLK) ? GMB_MIN_BLOCKS5 : MINB) map_kernel(const MapLaunch L)
 {
     // shared memory: step tables | jump-table starts | offsets | per-chain frame store
     extern __shared__ uint32_t smem[];
@@ -155,10 +156,10 @@ __global__ void __launch_bounds__(kThreads, (SIGMA == 5 && BLK) ? GMB_MIN_BLOCKS
     }
 }
 
-template <int KW, bool COUNT, typename OutT, bool EP, bool BLK, int SIGMA, bool LOC = false>
+template <int KW, bool COUNT, typename OutT, bool EP, bool BLK, int SIGMA, bool LOC = false, int MINB = GMB_MIN_BLOCKS>
 cudaError_t launch_b(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
-    auto kern = map_kernel<KW, COUNT, OutT, EP, BLK, SIGMA, LOC>;
+    auto kern = map_kernel<KW, COUNT, OutT, EP, BLK, SIGMA, LOC, MINB>;
     const size_t smem = map_kernel_smem_bytes(L.n_step_words, L.E, L.cx.B, EP, SIGMA, BLK);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
