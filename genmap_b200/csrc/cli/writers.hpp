@@ -107,12 +107,72 @@ struct ListRuns {
     template <class F> void runs(size_t s, F&& f) const
     {
         uint64_t r = std::lower_bound(start, start + n, cum[s]) - start;
-        for (; r < n && start[r] < cum[s + 1]; ++r) {
-            const uint64_t end = r + 1 < n ? std::min(start[r + 1], cum[s + 1]) : cum[s + 1];
-            f(Run{start[r] - cum[s], end - start[r], value[r]});
-        }
+        for (; r < n && start[r] < cum[s + 1]; ++r) f(at(r, s));
+    }
+    // run indices [first, last) of sequence s, and run r of that sequence
+    std::pair<uint64_t, uint64_t> range(size_t s) const
+    {
+        return {(uint64_t)(std::lower_bound(start, start + n, cum[s]) - start), (uint64_t)(std::lower_bound(start, start + n, cum[s + 1]) - start)};
+    }
+    Run at(uint64_t r, size_t s) const
+    {
+        const uint64_t end = r + 1 < n ? std::min(start[r + 1], cum[s + 1]) : cum[s + 1];
+        return Run{start[r] - cum[s], end - start[r], value[r]};
     }
 };
+
+// text building blocks of the parallel run formatters
+inline void append_u64(std::string& out, uint64_t v)
+{
+    char buf[24];
+    int n = 0;
+    do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) out.push_back(buf[--n]);
+}
+inline void append_value(std::string& out, uint32_t v, bool mappability)
+{
+    if (!mappability) { append_u64(out, v); return; }
+    if (v >= (1u << 16)) { char b[32]; out.append(b, (size_t)std::snprintf(b, sizeof b, "%g", (double)(1.0f / static_cast<float>(v)))); return; }
+    const char* t = Sink::inverse_text(v);
+    out.append(t + 1, (size_t)t[0]);
+}
+
+// Formats the runs of every sequence with `threads` workers (consecutive chunks of runs, written in order).
+// emit(run, last_span, seq, out): appends the text of one run; last_span = length of the previous run of the
+// sequence that was written (value != 0), 0 if none — the only state the wig format carries from run to run.
+template <class Emit>
+void format_runs_parallel(const ListRuns& src, size_t n_seq, unsigned threads, Sink& o, Emit&& emit)
+{
+    if (threads < 1) threads = 1;
+    const uint64_t chunk = 1u << 18; // runs per work item
+    std::vector<std::string> bufs(threads);
+    for (size_t s = 0; s < n_seq; ++s) {
+        const std::pair<uint64_t, uint64_t> rr = src.range(s);
+        for (uint64_t at = rr.first; at < rr.second; at += chunk * threads) {
+            std::vector<std::thread> workers;
+            unsigned used = 0;
+            for (unsigned t = 0; t < threads && at + t * chunk < rr.second; ++t, ++used) {
+                const uint64_t b = at + t * chunk, e = std::min(rr.second, b + chunk);
+                auto work = [&, t, b, e, s] {
+                    uint64_t last_span = 0;
+                    for (uint64_t r = b; r-- > rr.first;) // the nearest earlier run of this sequence that was written
+                        if (src.value[r] != 0) { last_span = src.at(r, s).len; break; }
+                    std::string& out = bufs[t];
+                    out.clear();
+                    for (uint64_t r = b; r < e; ++r) {
+                        const Run run = src.at(r, s);
+                        if (run.value == 0) continue;
+                        emit(run, last_span, s, out);
+                        last_span = run.len;
+                    }
+                };
+                if (threads == 1) work(); else workers.emplace_back(work);
+            }
+            for (std::thread& w : workers) w.join();
+            for (unsigned t = 0; t < used; ++t) o.str(bufs[t]);
+        }
+    }
+}
 
 inline std::vector<uint64_t> cumulative(const std::vector<uint64_t>& lens)
 {
@@ -251,6 +311,37 @@ void write_outputs(const T* c, uint64_t n, const std::string& prefix, const std:
     if (o.bed) timed("BED file", [&] { write_bedgraph(src, prefix, names, lens, false, mapp); });
 }
 
+// run-list overloads: the same files, formatted by several host threads
+inline void write_wig_runs(const ListRuns& src, const std::string& prefix, const std::vector<std::string>& names,
+                           const std::vector<uint64_t>& lens, bool mappability, unsigned threads)
+{
+    {
+        Sink o(prefix + ".wig");
+        if (!o.ok()) { std::cerr << "ERROR: cannot write " << prefix << ".wig\n"; return; }
+        format_runs_parallel(src, lens.size(), threads, o, [&](const Run& r, uint64_t last_span, size_t s, std::string& out) {
+            if (last_span != r.len) { // src/output.hpp:96-99
+                out += "variableStep chrom="; out += names[s]; out += " span="; append_u64(out, r.len); out.push_back('\n');
+            }
+            append_u64(out, r.start + 1); out.push_back(' '); append_value(out, r.value, mappability); out.push_back('\n');
+        });
+    }
+    Sink cs(prefix + ".chrom.sizes");
+    if (!cs.ok()) return;
+    for (size_t s = 0; s < lens.size(); ++s) { cs.str(names[s]); cs.ch('\t'); cs.u64(lens[s]); cs.ch('\n'); }
+}
+
+inline void write_bedgraph_runs(const ListRuns& src, const std::string& prefix, const std::vector<std::string>& names,
+                                const std::vector<uint64_t>& lens, bool bedgraph_format, bool mappability, unsigned threads)
+{
+    Sink o(prefix + (bedgraph_format ? ".bedgraph" : ".bed"));
+    if (!o.ok()) { std::cerr << "ERROR: cannot write " << prefix << (bedgraph_format ? ".bedgraph" : ".bed") << "\n"; return; }
+    format_runs_parallel(src, lens.size(), threads, o, [&](const Run& r, uint64_t, size_t s, std::string& out) {
+        out += names[s]; out.push_back('\t'); append_u64(out, r.start); out.push_back('\t'); append_u64(out, r.start + r.len); out.push_back('\t');
+        if (!bedgraph_format) { out.push_back('-'); out.push_back('\t'); }
+        append_value(out, r.value, mappability); out.push_back('\n');
+    });
+}
+
 // the track formats from a run list (no frequency vector on the host)
 inline void write_track_outputs(const ListRuns& src, const std::string& prefix, const std::vector<std::string>& names,
                                 const std::vector<uint64_t>& lens, OutputType type, const Outputs& o)
@@ -261,9 +352,9 @@ inline void write_track_outputs(const ListRuns& src, const std::string& prefix, 
         fn();
         if (o.verbose) std::cout << "- " << what << " written in " << (std::round((now_s() - t0) * 100.0) / 100.0) << " seconds\n";
     };
-    if (o.wig) timed("WIG file", [&] { write_wig(src, prefix, names, lens, mapp); });
-    if (o.bedgraph) timed("bedgraph file", [&] { write_bedgraph(src, prefix, names, lens, true, mapp); });
-    if (o.bed) timed("BED file", [&] { write_bedgraph(src, prefix, names, lens, false, mapp); });
+    if (o.wig) timed("WIG file", [&] { write_wig_runs(src, prefix, names, lens, mapp, o.threads); });
+    if (o.bedgraph) timed("bedgraph file", [&] { write_bedgraph_runs(src, prefix, names, lens, true, mapp, o.threads); });
+    if (o.bed) timed("BED file", [&] { write_bedgraph_runs(src, prefix, names, lens, false, mapp, o.threads); });
 }
 
 } // namespace gmbcli

@@ -137,3 +137,28 @@ def test_txt_writer_chunks_and_threads(genmap, tmp_path):
             want.append(">s%d\n%s\n" % (i, " ".join(lut[int(v)] for v in c[b:b + n])))
             b += n
         assert open(str(tmp_path / "o.txt")).read() == "".join(want)
+
+
+def test_track_writers_from_run_lists_in_chunks_and_threads(genmap, tmp_path):
+    """More runs than one formatting chunk (2^18) per sequence, zero runs at chunk borders, equal run lengths across
+    borders (the wig header rule): the threaded run-list writers give the files of the serial vector writers."""
+    rng = np.random.default_rng(6)
+    lens = [1_300_000, 700_001, 5]
+    c = rng.integers(0, 3, sum(lens)).astype(np.uint16)            # short runs, many zeros
+    c[200_000:700_000] = np.repeat(rng.integers(0, 4, 250_000), 2)  # long stretch of runs of length 2
+    c[rng.integers(0, len(c), 500)] = 65535
+    c.tofile(str(tmp_path / "c.freq16"))
+    with open(str(tmp_path / "index.ids"), "w") as f:
+        for i, n in enumerate(lens):
+            f.write("g.fa;%d;s%d\n" % (n, i))
+    for flags in (["-fl"], []):
+        outs = []
+        for tag, extra in (("vec", []), ("runs", ["-xr"])):
+            out = tmp_path / ("o_%s_%d" % (tag, len(flags)))
+            r = run(genmap, "render", "-I", tmp_path / "index.ids", "-C", tmp_path / "c.freq16", "-N", 0, "-O", out, "-w", "-bg", "-b",
+                    *flags, *extra)
+            assert r.returncode == 0, r.stderr
+            outs.append(str(out))
+        for ext in (".wig", ".bedgraph", ".bed", ".chrom.sizes"):
+            assert filecmp.cmp(outs[0] + ext, outs[1] + ext, shallow=False), (flags, ext)
+        assert os.path.getsize(outs[0] + ".wig") > 5_000_000
