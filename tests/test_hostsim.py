@@ -330,3 +330,34 @@ def test_substituted_jump_table_keys_change_the_accesses_not_the_counts(monkeypa
         walk, keys = res["walk", K, E], res["keys", K, E]
         assert keys[1] + keys[2] < 0.85 * (walk[1] + walk[2]), (K, E, walk[1:], keys[1:])  # fewer accesses in total
         assert keys[2] > walk[2]                                                            # ... through more table reads
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_state_machine_fuzz_against_the_definition(seed, monkeypatch):
+    """Random small genomes (Dna4 and Dna5) x random (K, E, strand, block size, jump depth, value type, table entries
+    with / without substituted keys, -ep) against the definition-level counter."""
+    rng = np.random.default_rng(seed)
+    for _ in range(14):
+        nfiles, per, length = int(rng.integers(1, 4)), int(rng.integers(1, 3)), int(rng.integers(30, 600))
+        base = T.repeat_rich(int(rng.integers(0, 1 << 30)), per, length, with_n=rng.random() < 0.3)
+        seqs, stf = [], []
+        for g in range(nfiles):
+            for b in base:
+                b = b.copy()
+                m = rng.random(len(b)) < 0.03 * g
+                b[m] = rng.integers(0, 4, int(m.sum()), dtype=np.uint8)
+                seqs.append(b); stf.append(g)
+        stf = np.array(stf, dtype=np.uint32)
+        hs = T.HostSim(seqs, with_sa=True)
+        for _ in range(4):
+            E = int(rng.integers(0, 5)); K = int(rng.integers(E + 2, 36))
+            if K * (1 + E) > 80 and length > 300:
+                continue
+            rc, B = bool(rng.random() < 0.7), int(rng.integers(0, 7))
+            depth, bits = int(rng.choice([-1, -1, 1, 3, 8])), int(rng.choice([8, 16]))
+            ep = nfiles > 1 and rng.random() < 0.4
+            fi = int(rng.integers(0, nfiles))
+            monkeypatch.setenv("GMB_JUMP_VARIANTS", "1" if rng.random() < 0.8 else "0")
+            want = T.brute(seqs, K, E, revcompl=rc, value_bits=bits, exclude_pseudo=ep, seq_to_file=stf, file_no=fi)
+            got = hs.map(K, E, revcompl=rc, value_bits=bits, block_kmers=B, jump_depth=depth, exclude_pseudo=ep, seq_to_file=stf, file_no=fi)
+            assert np.array_equal(got, want), dict(seed=seed, K=K, E=E, rc=rc, B=B, depth=depth, bits=bits, ep=ep, fi=fi)
