@@ -438,7 +438,13 @@ def main():
                 continue
             b2 = int(default_batch(E2) * (1 << 20))
             b2 = max(1 << 14, min(b2, shard_e - shard_b))
-            r2 = measure(E2, b2, max(3, args.steps // 2), 3, False, False)
+            try:
+                r2 = measure(E2, b2, max(3, args.steps // 2), 3, False, False)
+            except Exception as ex:  # an extra must never cost the headline line (single process only: with several
+                if dist is not None:  # ranks a one-sided failure would leave the others waiting in a collective)
+                    raise
+                extras["K%d_E%d" % (K, E2)] = {"value": None, "unit": UNIT, "error": repr(ex)}
+                continue
             r2["E"], r2["batch"] = E2, b2
             extras["K%d_E%d" % (K, E2)] = {"value": r2["value"], "unit": UNIT, "ms_per_step": r2["ms"] / max(3, args.steps // 2),
                                           "positions_per_step": b2, "roofline": roofline(r2)}
@@ -453,6 +459,8 @@ def main():
             rate, _, npos_cpu = cpu_rate(arm, K, E, args.cpu_seconds)
             cpu = {"value": rate, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample(npos_cpu, K)}
             for name, ex in extras.items():  # the same CPU arm for the other (K,E) lines, shorter samples
+                if ex.get("value") is None:
+                    continue
                 E2 = int(name.split("_E")[1])
                 r2, _, n2 = cpu_rate(arm, K, E2, args.cpu_seconds / 2)
                 ex["cpu_baseline"] = {"value": r2, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample(n2, K)}
