@@ -80,7 +80,7 @@ struct gmb_index {
     IndexHeader h{};
     std::vector<uint64_t> limits; // host copy
     // per-handle scratch, grown on demand
-    unsigned long long* d_counters = nullptr; // [0] work counter, [1..11] fetch counters (map_kernel.cuh)
+    unsigned long long* d_counters = nullptr; // [0] work counter, [1..12] fetch counters (map_kernel.cuh), [14] run count
     uint32_t* d_steps = nullptr; // search tables of the current call (kTableBytes)
     uint64_t* d_ranges = nullptr;
     size_t ranges_cap = 0;
@@ -680,12 +680,13 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
         stats->kernel_launches = 1;
         stats->jump_depth = plan_depth;
         if (L.count_fetches) {
-            unsigned long long f[11] = {};
+            unsigned long long f[12] = {};
             CU(cudaMemcpy(f, ix->d_counters + 1, sizeof(f), cudaMemcpyDeviceToHost));
             stats->rank_block_fetches = f[0];
             stats->jump_table_reads = f[1];
             for (int k = 0; k < 8; ++k) stats->fetches_by_size[k] = f[2 + k];
             stats->thin_paths = f[10];
+            stats->iterations = f[11];
         }
     }
     return GMB_OK;
@@ -986,7 +987,7 @@ int gmb_map_runs(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64
     DevBuf cum, temp, starts, values;
     CU(cum.alloc(((size_t)n_chrom + 1) * 8));
     CU(cudaMemcpyAsync(cum.p, chrom_cum, ((size_t)n_chrom + 1) * 8, cudaMemcpyHostToDevice, nullptr));
-    unsigned long long* d_count = ix->d_counters + 12;
+    unsigned long long* d_count = ix->d_counters + 14;
     CU(cudaEventRecord(ix->ev0, nullptr));
     size_t tb1 = 0, tb2 = 0;
     CU(rle_count(biased, p->value_bits, cum.as<uint64_t>(), n_chrom, pos_begin, pos_end, d_count, nullptr, tb1, nullptr));

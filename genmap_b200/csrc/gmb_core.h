@@ -433,8 +433,9 @@ struct FetchStats {
     unsigned long long total;
     unsigned long long by_size[8];
     unsigned long long thin_paths;
+    unsigned long long iterations; // passes through the state machine (expansions, table reads, window switches)
 };
-constexpr int kFetchStatWords = 10;
+constexpr int kFetchStatWords = 11;
 GMB_HD uint32_t size_bucket(uint32_t n)
 {
     if (n <= 1u) return 0u;
@@ -769,6 +770,7 @@ GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, Fetch
     constexpr uint32_t kNone = 0xffu; // "no symbol": the pattern character is N
     const uint32_t K = cx.K, cnt = BLK ? st.cnt : 1u;
     const uint32_t Li = K - cnt + 1; // infix length
+    if (fetches) ++fetches->iterations;
 
     if (BLK && st.win == kNoWin && st.t == Li) {
         // the whole infix is matched (only reached when cnt > 1): this node is an infix hit; complete it for

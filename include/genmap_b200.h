@@ -81,6 +81,7 @@ typedef struct gmb_map_stats {
      * (1, 2, 3-4, 5-8, 9-16, 17-32, 33-64, 65+) and the number of maximal runs of one-row expansions */
     uint64_t fetches_by_size[8];
     uint64_t thin_paths;
+    uint64_t iterations;         /* only with count_fetches: passes of all chains through the search state machine */
 } gmb_map_stats;
 
 /* flags for gmb_index_build */

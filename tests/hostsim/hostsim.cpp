@@ -151,7 +151,7 @@ int hs_step_tables(uint32_t K, uint32_t E, uint32_t* n_search, uint32_t* steps)
 }
 
 // jump_depth: -1 = default for the index size, 0 = no jump tables, else the maximum depth
-// fetches (optional): 10 words — total, by interval size [8], thin paths (gmb_core.h: FetchStats)
+// fetches (optional): 11 words — total, by interval size [8], thin paths, iterations (gmb_core.h: FetchStats)
 int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bits, uint64_t text_begin,
            uint64_t text_len, const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t* intervals,
            uint64_t n_intervals, uint64_t pos_begin, uint64_t pos_end, void* out, unsigned long long* fetches,
@@ -235,7 +235,7 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     else if (needle <= 64) RUN_KW(2);
     else if (needle <= 128) RUN_KW(4);
     else RUN_KW(9);
-    if (fetches) { fetches[0] = f.total; for (int k = 0; k < 8; ++k) fetches[1 + k] = f.by_size[k]; fetches[9] = f.thin_paths; }
+    if (fetches) { fetches[0] = f.total; for (int k = 0; k < 8; ++k) fetches[1 + k] = f.by_size[k]; fetches[9] = f.thin_paths; fetches[10] = f.iterations; }
     if (lut_reads_out) *lut_reads_out = lr;
     return 0;
 }

@@ -60,6 +60,6 @@ for cfg in args.configs.split(","):
              st.jump_table_reads / st.positions, st.rank_block_fetches * ix.info.rank_block_bytes / st.positions * npos / np.median(ms) / 1e6,
              setup, torch.cuda.mem_get_info()[0] / 1e9), flush=True)
     tot = max(1, st.rank_block_fetches)
-    print("    fetches by interval size 1|2|3-4|5-8|9-16|17-32|33-64|65+ : %s   thin paths/pos=%.2f (%.1f fetches each)"
+    print("    fetches by interval size 1|2|3-4|5-8|9-16|17-32|33-64|65+ : %s   thin paths/pos=%.2f (%.1f fetches each)  iterations/pos=%.1f"
           % (" ".join("%.1f%%" % (100.0 * x / tot) for x in st.fetches_by_size), st.thin_paths / st.positions,
-             st.fetches_by_size[0] / max(1, st.thin_paths)), flush=True)
+             st.fetches_by_size[0] / max(1, st.thin_paths), st.iterations / st.positions), flush=True)
