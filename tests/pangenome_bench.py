@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""BASELINE config 5 on one GPU: 10 FASTA files x 300 Mbp synthetic pan-genome, K=50 E=2 --exclude-pseudo.
+"""TEST INFRASTRUCTURE (lives under tests/ because its --cpu leg runs the reference binary of oracle/_ref).
+BASELINE config 5 on one GPU: 10 FASTA files x 300 Mbp synthetic pan-genome, K=50 E=2 --exclude-pseudo.
 
 File g = the base genome (3 x 100 Mbp, seed 46) with g % iid substitutions, all ten indexed
 together (3 Gbp + the full suffix array).  Times the search kernel on batches of positions of several files and,
@@ -17,7 +18,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # gmtest (reference-binary runner) for the --cpu leg
 import genmap_b200 as gm  # noqa: E402
 
 

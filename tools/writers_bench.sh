@@ -6,10 +6,11 @@ MBP=${1:-250}
 W=$(mktemp -d /dev/shm/gmb_wr_XXXX)
 python - "$MBP" "$W" <<'PY'
 import sys, os
-sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
-import genmap_b200 as gm, gmtest as T
+sys.path.insert(0, os.getcwd())
+import genmap_b200 as gm
+from genmap_b200 import synth
 mbp, w = float(sys.argv[1]), sys.argv[2]
-T.write_fasta(os.path.join(w, "g.fa"), gm.synth_genome(int(mbp * 1e6), 5, 44))
+synth.write_fasta(os.path.join(w, "g.fa"), gm.synth_genome(int(mbp * 1e6), 5, 44))
 PY
 G=genmap_b200/bin/genmap
 /usr/bin/time -v true 2>/dev/null || true
