@@ -8,8 +8,10 @@ A step = one pass of the hot path over one batch of consecutive k-mer start posi
   value : positions/s, index and output resident in HBM, CUDA events on the launching stream, max over ranks
   e2e   : the same metric through the host-buffer C ABI call gmb_map_frequencies_range (result slice D2H
           into pinned host memory inside the timed region)
-  roofline: algorithmic rank-block bytes (counted fetches x 64 B) / kernel time, vs the measured HBM copy peak
-  cpu_baseline: the oracle port of the reference path on this box's host cores, on a bounded window
+  roofline: algorithmic rank-block bytes (counted fetches x 32 B) / kernel time, vs the measured HBM copy peak
+  cpu_baseline: the unmodified reference binary (oracle/_ref/genmap_ref; the oracle port only if it is missing) on
+          this box's host cores, on a bounded window of the same genome
+  parity  : the reference's counts on that window compared with the GPU's (bit-exact or the line says so)
 One JSON line on stdout (rank 0); progress on stderr.
 """
 import argparse
@@ -171,6 +173,10 @@ class ReferenceCpu:
         cmd = [self.T.REF_BIN, "map", "-I", os.path.join(self.dir, "index"), "-O", out, "-K", str(K), "-E", str(E),
                "-r", "-fl", "-T", str(self.cores), "-v", "-S", bed]
         res = subprocess.run(cmd, check=True, stdout=subprocess.PIPE, text=True)
+        # the counts the reference wrote for this window (saveRaw, src/output.hpp:10-31): kept for the parity check
+        raw = np.memmap(os.path.join(out, "genome.genmap.freq16"), dtype=np.uint16, mode="r")
+        self.last_window = (b, e, np.array(raw[b:e]))
+        del raw
         for line in res.stdout.replace("\r", "\n").split("\n"):
             if line.startswith("Mappability computed in"):
                 return max(float(line.split()[3]), 0.005)
@@ -204,8 +210,10 @@ class PortCpu:
     def run(self, K, E, npos):
         b, e = _window(self.n_text, self.per, K, npos)
         t = time.time()
-        self.orc.map(K, E, intervals=[(b, e)], threads=self.cores)
-        return time.time() - t
+        c = self.orc.map(K, E, intervals=[(b, e)], threads=self.cores)
+        dt = time.time() - t
+        self.last_window = (b, e, np.array(c[b:e]))
+        return dt
 
     def sample(self, npos, K):
         b, _ = _window(self.n_text, self.per, K, npos)
@@ -253,6 +261,16 @@ def cpu_rate(arm, K, E, seconds, steps=1, warmup=0):
         if i >= warmup:
             times.append(dt)
     return npos * len(times) / sum(times), [t * 1e3 for t in times], npos
+
+
+def parity_check(arm, ix, K, E):
+    """The counts the CPU arm produced on its last window against the GPU's on the same positions."""
+    import genmap_b200 as gm
+    b, e, ref = arm.last_window
+    got = ix.compute_mappability_range(gm.SearchParams(K, E), b, e)
+    diff = np.nonzero(got != ref)[0]
+    return {"positions": int(e - b), "window": [int(b), int(e)], "equal": bool(len(diff) == 0), "mismatches": int(len(diff)),
+            "against": arm.kind, "nonunique_in_window": int((ref > 1).sum()), "max_count": int(ref.max()) if len(ref) else 0}
 
 
 def main():
@@ -404,26 +422,30 @@ def main():
         blk = float(ix.info.rank_block_bytes)  # 32: one sector per rank boundary
         per_launch = r["fetches"] * blk / len(r["batches"])
         achieved = per_launch / (r["kernel_ms"] * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                 tr = json.load(f)
             key = "K%d_E%d_batch%d_genome%d" % (K, r["E"], r["batch"], n_text)
             traffic = tr.get(key)
+            traffic_src = tr.get("_source")
+            if isinstance(traffic, dict):  # {"bytes": per-launch DRAM bytes, "git": sha of the kernel measured, "csv": file}
+                traffic_src = "%s @ %s" % (traffic.get("csv"), traffic.get("git"))
+                traffic = traffic.get("bytes")
         except Exception:
-            pass
+            traffic_src = None
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "rank_block_bytes": blk,
                 "rank_block_bytes_per_position": r["fetches"] * blk / max(r["searched"], 1),
                 # stricter figure: + jump-table entries (16 B) + pattern text (K/4 -> 16 B) + result (2 B)
                 "total_algorithmic_bytes_per_position": (r["fetches"] * blk + r["lut_reads"] * 16.0) / max(r["searched"], 1) + 18.0,
-                # the path is bound by the RATE of dependent random memory requests, not by their bytes: one request
-                # per rank block / jump-table entry; ceiling measured with tools/randread.cu (profiles/r01/s1_randread.txt)
+                # one dependent random request per rank block / jump-table entry; for scale, the best row of the
+                # pointer-chase microbenchmark (tools/randread.cu, profiles/r01/s1_randread.txt: 2048 threads/SM x 4 loads
+                # in flight) reaches 45.8 G 32-byte hops/s — a reference point, not a ceiling of this kernel
                 "random_requests_per_s": (r["fetches"] + r["lut_reads"]) / len(r["batches"]) / (r["kernel_ms"] * 1e-3),
-                "random_request_ceiling_per_s": 38.0e9,
-                # what the DRAM actually does: 64-byte accesses per second (ncu traffic / 64 B / kernel time); the
-                # random-read microbenchmark tops out at ~38 G/s of these
+                "random_request_rate_best_microbenchmark_per_s": 45.8e9,
+                # what the DRAM actually does: 64-byte accesses per second (ncu traffic / 64 B / kernel time)
                 "dram_64B_accesses_per_s": (traffic / 64.0 / (r["kernel_ms"] * 1e-3)) if traffic else None,
                 # the same fraction on the stricter figure (rank blocks + 16-byte jump-table entries)
                 "frac_with_table_reads": (r["fetches"] * blk + r["lut_reads"] * 16.0) / len(r["batches"]) / (r["kernel_ms"] * 1e-3) / 1e9 / peak,
@@ -439,7 +461,7 @@ def main():
             b2 = int(default_batch(E2) * (1 << 20))
             b2 = max(1 << 14, min(b2, shard_e - shard_b))
             try:
-                r2 = measure(E2, b2, max(3, args.steps // 2), 3, False, False)
+                r2 = measure(E2, b2, max(3, args.steps // 2), 3, True, False)
             except Exception as ex:  # an extra must never cost the headline line (single process only: with several
                 if dist is not None:  # ranks a one-sided failure would leave the others waiting in a collective)
                     raise
@@ -447,10 +469,13 @@ def main():
                 continue
             r2["E"], r2["batch"] = E2, b2
             extras["K%d_E%d" % (K, E2)] = {"value": r2["value"], "unit": UNIT, "ms_per_step": r2["ms"] / max(3, args.steps // 2),
-                                          "positions_per_step": b2, "roofline": roofline(r2)}
+                                          "positions_per_step": b2, "e2e": r2.get("e2e"), "roofline": roofline(r2)}
 
     cpu = None
+    parity = {}
     index_gb = ix.info.blob_bytes / 1e9
+    hbm = {"index_blob": int(ix.info.blob_bytes), "jump_tables": int(ix.refresh_info().jump_table_bytes),
+           "result_vector": int(2 * n_text)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             del out_dev
@@ -458,12 +483,16 @@ def main():
             arm = make_cpu_arm(seqs, ix)
             rate, _, npos_cpu = cpu_rate(arm, K, E, args.cpu_seconds)
             cpu = {"value": rate, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample(npos_cpu, K)}
+            parity["K%d_E%d" % (K, E)] = parity_check(arm, ix, K, E)
+            log("parity %s" % (parity,))
             for name, ex in extras.items():  # the same CPU arm for the other (K,E) lines, shorter samples
                 if ex.get("value") is None:
                     continue
                 E2 = int(name.split("_E")[1])
                 r2, _, n2 = cpu_rate(arm, K, E2, args.cpu_seconds / 2)
                 ex["cpu_baseline"] = {"value": r2, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample(n2, K)}
+                parity[name] = parity_check(arm, ix, K, E2)
+                log("parity %s: %s" % (name, parity[name]))
             arm.close()
         except Exception as ex:  # the baseline is a reported extra; never lose the GPU line over it
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
@@ -475,7 +504,9 @@ def main():
                 "config": {"workload": workload, "K": K, "E": E, "genome_bp": n_text, "positions_per_step_per_gpu": batch,
                            "sharding": "positions range-partitioned over %d GPU(s), index replicated (NCCL broadcast)" % world,
                            "cache": "inputs larger than L2: %.2f GB index vs 126 MB L2, every step searches different positions"
-                                    % index_gb},
+                                    % index_gb,
+                           "hbm_bytes": hbm},
+                "parity": parity or None,
                 "clocks": main_r["clocks"], "e2e": main_r.get("e2e"), "gpu_launches": args.steps,
                 "roofline": roofline(main_r), "cpu_baseline": cpu, "extra": extras}
         print(json.dumps(line), flush=True)

@@ -13,7 +13,8 @@ EXPORTS = ["gmb_last_error", "gmb_version", "gmb_device_count", "gmb_index_build
            "gmb_index_build_device", "gmb_blob_save", "gmb_index_open", "gmb_index_from_blob",
            "gmb_index_adopt_device", "gmb_index_close", "gmb_index_get_info", "gmb_map_frequencies",
            "gmb_map_frequencies_range", "gmb_map_frequencies_device", "gmb_index_export_bwt", "gmb_index_export_sa", "gmb_index_set_jump_depth",
-           "gmb_index_import_reference", "gmb_map_locations", "gmb_locations_free", "gmb_map_runs", "gmb_runs_free", "gmb_index_replicate"]
+           "gmb_index_import_reference", "gmb_map_locations", "gmb_locations_free", "gmb_map_runs", "gmb_runs_free", "gmb_index_replicate",
+           "gmb_index_set_plan_text_size", "gmb_progress"]
 
 
 class GmbParams(ctypes.Structure):
@@ -25,7 +26,8 @@ class GmbParams(ctypes.Structure):
 class GmbIndexInfo(ctypes.Structure):
     _fields_ = [("n_text", ctypes.c_uint64), ("n_bwt", ctypes.c_uint64), ("n_seq", ctypes.c_uint32),
                 ("has_sa", ctypes.c_uint32), ("blob_bytes", ctypes.c_uint64), ("rank_block_bytes", ctypes.c_uint64),
-                ("device_blob", ctypes.c_void_p), ("device", ctypes.c_int32), ("alphabet_size", ctypes.c_int32)]
+                ("device_blob", ctypes.c_void_p), ("device", ctypes.c_int32), ("alphabet_size", ctypes.c_int32),
+                ("jump_table_bytes", ctypes.c_uint64)]
 
 
 class GmbMapStats(ctypes.Structure):
@@ -95,6 +97,10 @@ def lib():
                                             u64, u64, vp, ctypes.POINTER(GmbMapStats)]
     L.gmb_index_set_jump_depth.restype = ci
     L.gmb_index_set_jump_depth.argtypes = [vp, ci]
+    L.gmb_index_set_plan_text_size.restype = ci
+    L.gmb_index_set_plan_text_size.argtypes = [vp, u64]
+    L.gmb_progress.restype = ci
+    L.gmb_progress.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.gmb_index_import_reference.restype = ci
     L.gmb_index_import_reference.argtypes = [ctypes.c_char_p, pp, ctypes.POINTER(u64)]
     L.gmb_index_export_sa.restype = ci

@@ -223,6 +223,20 @@ class Index:
         """-1 = automatic, 0 = no jump tables, 1..16 = maximum table depth (see gmb_index_set_jump_depth)."""
         check(_lib.lib().gmb_index_set_jump_depth(self._h, int(depth)))
 
+    def set_plan_text_size(self, n_symbols):
+        """Plan the searches as if the text had n_symbols symbols (0 = the index's own size); counts never change."""
+        check(_lib.lib().gmb_index_set_plan_text_size(self._h, int(n_symbols)))
+
+    def progress(self):
+        """(positions handed out so far, positions of the call) of the map call in flight on this handle."""
+        d, t = ctypes.c_uint64(), ctypes.c_uint64()
+        check(_lib.lib().gmb_progress(self._h, ctypes.byref(d), ctypes.byref(t)))
+        return int(d.value), int(t.value)
+
+    def refresh_info(self):
+        check(_lib.lib().gmb_index_get_info(self._h, ctypes.byref(self.info)))
+        return self.info
+
     def export_bwt(self, rev=False):
         """BWT of T (or of T' if rev) as bytes: 0 = sentinel, 1..4 = A,C,G,T (diagnostics / tests)."""
         out = np.zeros(int(self.info.n_bwt), dtype=np.uint8)

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <algorithm>
+#include <atomic>
 #include <memory>
 #include <string>
 #include <vector>
@@ -81,7 +82,6 @@ struct gmb_index {
     std::vector<uint64_t> limits; // host copy
     // per-handle scratch, grown on demand
     unsigned long long* d_counters = nullptr; // [0] work counter, [1..12] fetch counters (map_kernel.cuh), [14] run count
-    uint32_t* d_steps = nullptr; // search tables of the current call (kTableBytes)
     uint64_t* d_ranges = nullptr;
     size_t ranges_cap = 0;
     void* d_out = nullptr;
@@ -95,8 +95,29 @@ struct gmb_index {
     JtEntry* jt_uni[17] = {};
     uint32_t* jt_lof[17] = {};
     JtFull* jt_full[17] = {};    // both intervals per entry (searches that need the interval in SA(T) after the jump)
-    uint32_t* d_variants = nullptr; // substituted-offset sets of the current call's searches
-    size_t variants_cap = 0;
+    uint64_t jt_epoch = 0;       // bumped whenever a jump table is freed: cached plans holding its address are re-made
+    uint64_t plan_n = 0;         // plan the searches as if the text had this many symbols (0 = the index's own n_bwt)
+    // search plans by configuration (tables on the device, ready to launch): a map call of a configuration seen
+    // before uploads nothing but its work ranges
+    std::vector<std::unique_ptr<struct MapPlan>> plans;
+    uint64_t plan_clock = 0;
+    // progress of the call in flight (gmb_progress): positions of finished pieces + chunks the kernel has handed out
+    // d_counters[15] = positions of the pieces already finished (written in stream order by the host-output pipeline)
+    std::atomic<uint64_t> prog_total{0}, prog_chunk{0};
+    bool prog_in_pipeline = false;
+    cudaStream_t s_progress = nullptr;
+};
+
+// Everything a launch needs for one configuration (K, E, block size, table flavour, jump depth, model text size)
+struct MapPlan {
+    std::string key;
+    BlockTables tabs;
+    uint32_t plan_depth = 0;
+    uint32_t* d_tables = nullptr; // step words | SearchStart entries | substituted-offset sets
+    size_t start_off = 0;
+    uint64_t jt_epoch = ~0ull;    // ix->jt_epoch the SearchStart entries were written for
+    uint64_t last_use = 0;
+    ~MapPlan() { if (d_tables) cudaFree(d_tables); }
 };
 
 namespace {
@@ -141,14 +162,19 @@ JumpNeeds jump_needs(const std::vector<JumpPlan>& plans, bool use_full)
     return n;
 }
 
-// big levels (> kJumpKeep) the current call does not use are dropped: they are rebuilt in about a second when needed
-void evict_stale_jump_tables(gmb_index* ix, const JumpNeeds& n)
+// Drop the big levels (> kJumpKeep) the current call does not use; they are rebuilt in about a second when needed.
+// Only done when HBM is short: tables of other configurations stay cached otherwise.  Returns the bytes freed.
+size_t evict_stale_jump_tables(gmb_index* ix, const JumpNeeds& n)
 {
+    size_t freed = 0;
     for (uint32_t d = kJumpKeep + 1; d <= 16; ++d) {
-        if (ix->jt_uni[d] && !n.uni[d]) { cudaFree(ix->jt_uni[d]); ix->jt_uni[d] = nullptr; }
-        if (ix->jt_lof[d] && !n.lof[d]) { cudaFree(ix->jt_lof[d]); ix->jt_lof[d] = nullptr; }
-        if (ix->jt_full[d] && !n.full[d]) { cudaFree(ix->jt_full[d]); ix->jt_full[d] = nullptr; }
+        const size_t e = (size_t)1 << (2 * d);
+        if (ix->jt_uni[d] && !n.uni[d]) { cudaFree(ix->jt_uni[d]); ix->jt_uni[d] = nullptr; freed += e * sizeof(JtEntry); }
+        if (ix->jt_lof[d] && !n.lof[d]) { cudaFree(ix->jt_lof[d]); ix->jt_lof[d] = nullptr; freed += e * sizeof(uint32_t); }
+        if (ix->jt_full[d] && !n.full[d]) { cudaFree(ix->jt_full[d]); ix->jt_full[d] = nullptr; freed += e * sizeof(JtFull); }
     }
+    if (freed) ++ix->jt_epoch;
+    return freed;
 }
 
 // bytes that still have to be allocated for these needs (tables + the transient parent levels of the deepest one)
@@ -167,6 +193,30 @@ size_t missing_jump_bytes(const gmb_index* ix, const JumpNeeds& n)
     return bytes;
 }
 
+size_t jump_table_bytes(const gmb_index* ix)
+{
+    size_t bytes = 0;
+    for (uint32_t d = 1; d <= 16; ++d) {
+        const size_t e = (size_t)1 << (2 * d);
+        if (ix->jt_uni[d]) bytes += e * sizeof(JtEntry);
+        if (ix->jt_lof[d]) bytes += e * sizeof(uint32_t);
+        if (ix->jt_full[d]) bytes += e * sizeof(JtFull);
+    }
+    return bytes;
+}
+
+// cudaMalloc that, when HBM is short, drops the cached tables this call does not use and tries again
+template <class T>
+cudaError_t jt_alloc(gmb_index* ix, const JumpNeeds& n, T** p, size_t bytes)
+{
+    cudaError_t err = cudaMalloc(p, bytes);
+    if (err == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        if (evict_stale_jump_tables(ix, n)) err = cudaMalloc(p, bytes);
+    }
+    return err;
+}
+
 // make sure the tables these needs name exist on the device (built level by level, cached)
 int ensure_jump_tables(gmb_index* ix, const JumpNeeds& n, cudaStream_t stream)
 {
@@ -176,28 +226,34 @@ int ensure_jump_tables(gmb_index* ix, const JumpNeeds& n, cudaStream_t stream)
     if (top == 0) return GMB_OK; // everything this call needs is cached
     MapCtx cx;
     fill_ctx(ix, cx);
+    bool transient[17] = {}; // big parent levels built only to reach a deeper one: dropped again below
     for (uint32_t d = 1; d <= top; ++d) {
         const size_t e = (size_t)1 << (2 * d);
         const bool parent_for_later = d < top; // deeper levels extend this one: needs uni + lof
         const bool want_lof = parent_for_later || n.lof[d];
         if ((parent_for_later || n.uni[d]) && !(ix->jt_uni[d] && (!want_lof || ix->jt_lof[d]))) {
-            if (ix->jt_uni[d]) { cudaFree(ix->jt_uni[d]); ix->jt_uni[d] = nullptr; }
-            if (ix->jt_lof[d]) { cudaFree(ix->jt_lof[d]); ix->jt_lof[d] = nullptr; }
-            cudaError_t err = cudaMalloc(&ix->jt_uni[d], e * sizeof(JtEntry));
-            if (err == cudaSuccess && want_lof) err = cudaMalloc(&ix->jt_lof[d], e * sizeof(uint32_t));
+            if (ix->jt_uni[d]) { cudaFree(ix->jt_uni[d]); ix->jt_uni[d] = nullptr; ++ix->jt_epoch; }
+            if (ix->jt_lof[d]) { cudaFree(ix->jt_lof[d]); ix->jt_lof[d] = nullptr; ++ix->jt_epoch; }
+            transient[d] = d > kJumpKeep && !n.uni[d] && !n.lof[d];
+            cudaError_t err = jt_alloc(ix, n, &ix->jt_uni[d], e * sizeof(JtEntry));
+            if (err == cudaSuccess && want_lof) err = jt_alloc(ix, n, &ix->jt_lof[d], e * sizeof(uint32_t));
             if (err == cudaSuccess)
                 err = build_jump_level(cx, ix->h.sigma, d, ix->jt_uni[d - 1], ix->jt_lof[d - 1], ix->jt_uni[d], ix->jt_lof[d], nullptr, stream);
             if (err != cudaSuccess) return cuda_fail(err, "jump table");
         }
         if (n.full[d] && !ix->jt_full[d]) {
-            cudaError_t err = cudaMalloc(&ix->jt_full[d], e * sizeof(JtFull));
+            cudaError_t err = jt_alloc(ix, n, &ix->jt_full[d], e * sizeof(JtFull));
             if (err == cudaSuccess)
                 err = build_jump_level(cx, ix->h.sigma, d, ix->jt_uni[d - 1], ix->jt_lof[d - 1], nullptr, nullptr, ix->jt_full[d], stream);
             if (err != cudaSuccess) return cuda_fail(err, "jump table");
         }
     }
     CU(cudaStreamSynchronize(stream));
-    evict_stale_jump_tables(ix, n);
+    for (uint32_t d = kJumpKeep + 1; d <= 16; ++d)
+        if (transient[d]) {
+            if (ix->jt_uni[d] && !n.uni[d]) { cudaFree(ix->jt_uni[d]); ix->jt_uni[d] = nullptr; ++ix->jt_epoch; }
+            if (ix->jt_lof[d] && !n.lof[d]) { cudaFree(ix->jt_lof[d]); ix->jt_lof[d] = nullptr; ++ix->jt_epoch; }
+        }
     return GMB_OK;
 }
 } // namespace
@@ -263,9 +319,9 @@ static int finish_open(gmb_index* ix, gmb_index** out)
     ix->limits.resize((size_t)ix->h.n_seq + 1);
     CU(cudaMemcpy(ix->limits.data(), ix->d_blob + ix->h.off_limits, ix->limits.size() * 8, cudaMemcpyDeviceToHost));
     CU(cudaMalloc(&ix->d_counters, 16 * sizeof(unsigned long long)));
-    CU(cudaMalloc(&ix->d_steps, kTableBytes));
     CU(cudaEventCreate(&ix->ev0));
     CU(cudaEventCreate(&ix->ev1));
+    CU(cudaStreamCreateWithFlags(&ix->s_progress, cudaStreamNonBlocking));
     *out = ix;
     return GMB_OK;
 }
@@ -422,12 +478,12 @@ int gmb_index_close(gmb_index* ix)
     cudaSetDevice(ix->device);
     if (ix->owns_blob && ix->d_blob) cudaFree(ix->d_blob);
     if (ix->d_counters) cudaFree(ix->d_counters);
-    if (ix->d_steps) cudaFree(ix->d_steps);
     if (ix->d_ranges) cudaFree(ix->d_ranges);
     if (ix->d_out) cudaFree(ix->d_out);
     if (ix->d_seq_to_file) cudaFree(ix->d_seq_to_file);
     for (int d = 0; d < 17; ++d) { if (ix->jt_uni[d]) cudaFree(ix->jt_uni[d]); if (ix->jt_lof[d]) cudaFree(ix->jt_lof[d]); if (ix->jt_full[d]) cudaFree(ix->jt_full[d]); }
-    if (ix->d_variants) cudaFree(ix->d_variants);
+    ix->plans.clear();
+    if (ix->s_progress) cudaStreamDestroy(ix->s_progress);
     if (ix->s_compute) cudaStreamDestroy(ix->s_compute);
     if (ix->s_copy) cudaStreamDestroy(ix->s_copy);
     for (int i = 0; i < 2; ++i) if (ix->ev_piece[i]) cudaEventDestroy(ix->ev_piece[i]);
@@ -450,6 +506,33 @@ int gmb_index_get_info(const gmb_index* ix, gmb_index_info* info)
     info->alphabet_size = (int32_t)ix->h.sigma;
     info->device_blob = ix->d_blob;
     info->device = ix->device;
+    info->jump_table_bytes = jump_table_bytes(ix);
+    return GMB_OK;
+}
+
+int gmb_index_set_plan_text_size(gmb_index* ix, uint64_t n_symbols)
+{
+    if (!ix) return fail(GMB_ERR_ARG, "gmb_index_set_plan_text_size: NULL argument");
+    ix->plan_n = n_symbols;
+    return GMB_OK;
+}
+
+int gmb_progress(gmb_index* ix, uint64_t* done, uint64_t* total)
+{
+    if (!ix || !done || !total) return fail(GMB_ERR_ARG, "gmb_progress: NULL argument");
+    *total = ix->prog_total.load();
+    uint64_t d = 0;
+    const uint64_t chunk = ix->prog_chunk.load();
+    if (chunk && ix->s_progress && ix->d_counters) { // chunks the kernel in flight has handed out + finished pieces
+        unsigned long long c[16] = {};
+        if (cudaSetDevice(ix->device) == cudaSuccess &&
+            cudaMemcpyAsync(c, ix->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ix->s_progress) == cudaSuccess &&
+            cudaStreamSynchronize(ix->s_progress) == cudaSuccess)
+            d = (uint64_t)c[0] * chunk + (uint64_t)c[15];
+        else
+            cudaGetLastError();
+    }
+    *done = d < *total ? d : *total;
     return GMB_OK;
 }
 
@@ -478,6 +561,131 @@ struct LocPass {
     uint64_t pos0;
 };
 
+// The search plan of a configuration: step tables, block size, how every search enters through the jump tables —
+// built once per handle and configuration, with its tables left on the device.  (Round 1 rebuilt and re-uploaded all
+// of it on every call, i.e. once per 32 Mi-position piece of the host-output pipeline.)
+static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool loc, cudaStream_t stream, MapPlan** out)
+{
+    uint32_t want_b = p->block_kmers;
+    if (want_b == 0) { const char* env = std::getenv("GMB_BLOCK_KMERS"); if (env && *env) want_b = (uint32_t)std::atoi(env); }
+    const char* env_depth = std::getenv("GMB_JUMP_DEPTH");
+    int want = ix->jump_depth_opt;
+    if (want < 0 && env_depth && *env_depth) want = std::atoi(env_depth);
+    const uint64_t model_n = ix->plan_n ? ix->plan_n : ix->h.n_bwt;
+    const char* e1 = std::getenv("GMB_PART_MODEL");
+    const char* e2 = std::getenv("GMB_PART_WEIGHTS");
+    const char* e3 = std::getenv("GMB_JUMP_VARIANTS");
+    char buf[200];
+    std::snprintf(buf, sizeof buf, "%u/%u/%u/%d/%d/%d/%llu/", p->K, p->E, want_b, sync_tables ? 1 : 0, loc ? 1 : 0, want,
+                  (unsigned long long)model_n);
+    const std::string key = std::string(buf) + (e1 ? e1 : "") + "/" + (e2 ? e2 : "") + "/" + (e3 ? e3 : "");
+    MapPlan* plan = nullptr;
+    for (auto& q : ix->plans)
+        if (q->key == key) plan = q.get();
+    std::string err;
+    if (!plan) {
+        std::unique_ptr<MapPlan> np(new (std::nothrow) MapPlan);
+        if (!np) return fail(GMB_ERR_NOMEM, "out of host memory");
+        np->key = key;
+        BlockTables& tabs = np->tabs;
+        if (!build_block_tables(p->K, p->E, want_b, sync_tables, tabs, err, model_n, block_bases(ix->h.sigma))) return fail(GMB_ERR_UNSUPPORTED, err);
+        // the tables and the per-chain frame store live in shared memory: shrink the block if they do not fit
+        while (tabs.B > 1 && (map_kernel_smem_bytes((uint32_t)tabs.steps.size(), p->E, tabs.B, sync_tables, ix->h.sigma, true) > (200u << 10) ||
+                              tabs.steps.size() * 4 + (tabs.B + 1) * kMaxSearches * sizeof(SearchStart) > kTableBytes))
+            if (!build_block_tables(p->K, p->E, tabs.B - 1, sync_tables, tabs, err, model_n, block_bases(ix->h.sigma))) return fail(GMB_ERR_UNSUPPORTED, err);
+        if (ix->plans.size() >= 12) { // drop the least recently used plan
+            size_t lru = 0;
+            for (size_t i = 1; i < ix->plans.size(); ++i) if (ix->plans[i]->last_use < ix->plans[lru]->last_use) lru = i;
+            CU(cudaDeviceSynchronize()); // a kernel in flight may still read its tables
+            ix->plans.erase(ix->plans.begin() + (long)lru);
+        }
+        plan = np.get();
+        ix->plans.push_back(std::move(np));
+    }
+    plan->last_use = ++ix->plan_clock;
+    *out = plan;
+    if (plan->d_tables && plan->jt_epoch == ix->jt_epoch) return GMB_OK;
+
+    // ---- (re)plan the jump-table entries and put the tables on the device -------------------------------------
+    const BlockTables& tabs = plan->tabs;
+    std::vector<JumpPlan> plans(tabs.B + 1);
+    std::vector<SearchStart> starts((size_t)(tabs.B + 1) * kMaxSearches);
+    std::vector<uint32_t> variants;
+    uint32_t plan_depth = 0;
+    uint32_t maxd = want < 0 ? default_jump_depth(model_n) : (uint32_t)want;
+    if (maxd > 16) maxd = 16;
+    JumpNeeds needs;
+    const bool use_full = tabs.B > 1 && !loc; // the blocked instantiation
+    for (;;) {
+        plan_depth = 0;
+        for (uint32_t cnt = 0; cnt <= tabs.B; ++cnt) {
+            JumpPlan& pl = plans[cnt];
+            if (cnt == 0) { pl = JumpPlan(); std::memset(pl.depth, 0, sizeof(pl.depth)); pl.max_depth = 0; continue; }
+            plan_jump_tables(tabs.infix[cnt], maxd, pl, p->E, model_n, ix->h.sigma, cnt, tabs.B > 1 && !loc);
+            plan_depth = std::max(plan_depth, pl.max_depth);
+        }
+        needs = jump_needs(plans, use_full);
+        if (want >= 0 || maxd <= 1) break; // a fixed depth is taken as it is
+        // automatic depth: what is missing must fit comfortably in free HBM, if need be after dropping the cached
+        // tables this configuration does not use
+        size_t free_b = 0, total_b = 0;
+        const size_t missing = missing_jump_bytes(ix, needs);
+        if (missing == 0) break;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); break; }
+        if (missing <= free_b / 10 * 8) break;
+        CU(cudaStreamSynchronize(stream));
+        if (evict_stale_jump_tables(ix, needs)) {
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); break; }
+            if (missing_jump_bytes(ix, needs) <= free_b / 10 * 8) break;
+        }
+        --maxd;
+    }
+    int rcj = ensure_jump_tables(ix, needs, stream);
+    if (rcj != GMB_OK) return rcj;
+    for (uint32_t cnt = 1; cnt <= tabs.B; ++cnt)
+        for (uint32_t s2 = 0; s2 < kMaxSearches; ++s2) {
+            const uint32_t d = plans[cnt].depth[s2];
+            SearchStart& S = starts[(size_t)cnt * kMaxSearches + s2];
+            std::memset(&S, 0, sizeof(S));
+            const bool full = d && plans[cnt].need_lof[s2] && use_full;
+            S.uni = (d && !full) ? ix->jt_uni[d] : nullptr;
+            S.lof = (d && !full && plans[cnt].need_lof[s2]) ? ix->jt_lof[d] : nullptr;
+            S.full = full ? ix->jt_full[d] : nullptr;
+            S.a = plans[cnt].a[s2];
+            S.d = d;
+            S.n_var = std::max(1u, plans[cnt].n_var[s2]);
+        }
+    // lay the variant sets of all tables out in one array behind the starts and turn the indices into device pointers
+    std::vector<size_t> base_of(tabs.B + 1, 0);
+    for (uint32_t cnt = 1; cnt <= tabs.B; ++cnt) {
+        base_of[cnt] = variants.size();
+        variants.insert(variants.end(), plans[cnt].variants.begin(), plans[cnt].variants.end());
+        if (plans[cnt].variants.empty()) variants.push_back(0xffffffffu);
+    }
+    const size_t step_bytes = tabs.steps.size() * sizeof(uint32_t);
+    const size_t start_off = (step_bytes + 15) / 16 * 16;
+    const size_t var_off = start_off + starts.size() * sizeof(SearchStart);
+    const size_t total = var_off + variants.size() * sizeof(uint32_t);
+    CU(cudaStreamSynchronize(stream)); // nothing in flight reads the old tables while they are replaced
+    if (plan->d_tables) { cudaFree(plan->d_tables); plan->d_tables = nullptr; }
+    CU(cudaMalloc(&plan->d_tables, total));
+    uint8_t* dt = reinterpret_cast<uint8_t*>(plan->d_tables);
+    for (uint32_t cnt = 1; cnt <= tabs.B; ++cnt)
+        for (uint32_t s2 = 0; s2 < kMaxSearches; ++s2) {
+            SearchStart& S = starts[(size_t)cnt * kMaxSearches + s2];
+            S.var = reinterpret_cast<const uint32_t*>(dt + var_off) + base_of[cnt] + plans[cnt].var_off[s2];
+            S.set0 = plans[cnt].variants.empty() ? 0xffffffffu : variants[base_of[cnt] + plans[cnt].var_off[s2]];
+        }
+    CU(cudaMemcpyAsync(dt, tabs.steps.data(), step_bytes, cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(dt + start_off, starts.data(), starts.size() * sizeof(SearchStart), cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(dt + var_off, variants.data(), variants.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    CU(cudaStreamSynchronize(stream)); // pageable sources: staged before the vectors go out of scope
+    plan->start_off = start_off;
+    plan->plan_depth = plan_depth;
+    plan->jt_epoch = ix->jt_epoch;
+    return GMB_OK;
+}
+
 static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_begin, uint64_t text_len,
                            const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t (*intervals)[2],
                            uint64_t n_intervals, const uint32_t* seq_to_file, uint32_t n_seq,
@@ -497,7 +705,7 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
     if (n_chrom == 0 || chrom_cum[0] != 0 || chrom_cum[n_chrom] != text_len) return fail(GMB_ERR_ARG, "chrom_cum_lengths must start at 0 and end at text_len");
     uint32_t n_files = 0, own_file = 0;
     if (p->exclude_pseudo) {
-        if (!ix->h.off_sa) return fail(GMB_ERR_UNSUPPORTED, "--exclude-pseudo needs an index built with the full suffix array (genmap index -xs / GMB_BUILD_WITH_SA)");
+        if (!ix->h.off_sa) return fail(GMB_ERR_UNSUPPORTED, "--exclude-pseudo needs an index built with the full suffix array (`genmap index` without --no-sa / GMB_BUILD_WITH_SA)");
         if (!seq_to_file || n_seq != ix->h.n_seq) return fail(GMB_ERR_ARG, "--exclude-pseudo needs seq_to_file for every indexed sequence");
         for (uint32_t s = 0; s < n_seq; ++s) n_files = std::max(n_files, seq_to_file[s] + 1);
         if (n_files > 64) { // more files than the kernel's 64-bit file mask holds: locate + distinct-file count
@@ -511,19 +719,14 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
         own_file = seq_to_file[s0];
     }
     if (n_intervals && !intervals) return fail(GMB_ERR_ARG, "intervals is NULL");
-    std::string err;
-    BlockTables tabs;
-    {
-        uint32_t want_b = p->block_kmers;
-        if (want_b == 0) { const char* env = std::getenv("GMB_BLOCK_KMERS"); if (env && *env) want_b = (uint32_t)std::atoi(env); }
-        if (!build_block_tables(p->K, p->E, want_b, sync_tables, tabs, err, ix->h.n_bwt, block_bases(ix->h.sigma))) return fail(GMB_ERR_UNSUPPORTED, err);
-        // the tables and the per-chain frame store live in shared memory: shrink the block if they do not fit
-        while (tabs.B > 1 && (map_kernel_smem_bytes((uint32_t)tabs.steps.size(), p->E, tabs.B, sync_tables, ix->h.sigma, true) > (200u << 10) ||
-                              tabs.steps.size() * 4 + (tabs.B + 1) * kMaxSearches * sizeof(SearchStart) > kTableBytes))
-            if (!build_block_tables(p->K, p->E, tabs.B - 1, sync_tables, tabs, err, ix->h.n_bwt, block_bases(ix->h.sigma))) return fail(GMB_ERR_UNSUPPORTED, err);
-    }
     CU(cudaSetDevice(ix->device));
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    MapPlan* plan = nullptr;
+    {
+        int rcp = get_plan(ix, p, sync_tables, loc != nullptr, stream, &plan);
+        if (rcp != GMB_OK) return rcp;
+    }
+    const BlockTables& tabs = plan->tabs;
 
     std::vector<WorkRange> ranges;
     build_work_ranges(text_len, p->K, chrom_cum, n_chrom, reinterpret_cast<const uint64_t*>(intervals), n_intervals,
@@ -550,86 +753,16 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
         CU(cudaMalloc(&ix->d_ranges, ix->ranges_cap * 8));
     }
     CU(cudaMemcpyAsync(ix->d_ranges, host_ranges.data(), host_ranges.size() * 8, cudaMemcpyHostToDevice, stream));
-    CU(cudaMemsetAsync(ix->d_counters, 0, 16 * sizeof(unsigned long long), stream));
+    CU(cudaMemsetAsync(ix->d_counters, 0, (ix->prog_in_pipeline ? 15 : 16) * sizeof(unsigned long long), stream));
+    ix->prog_chunk.store(chunk);
+    if (!ix->prog_in_pipeline) ix->prog_total.store(total);
 
     MapLaunch L;
     const uint8_t* base = ix->d_blob;
     fill_ctx(ix, L.cx);
-    std::vector<JumpPlan> plans(tabs.B + 1);
-    uint32_t plan_depth = 0;
-    std::vector<SearchStart> starts((size_t)(tabs.B + 1) * kMaxSearches);
-    std::vector<uint32_t> variants;
-    {
-        const char* env = std::getenv("GMB_JUMP_DEPTH");
-        int want = ix->jump_depth_opt;
-        if (want < 0 && env && *env) want = std::atoi(env);
-        uint32_t maxd = want < 0 ? default_jump_depth(ix->h.n_bwt) : (uint32_t)want;
-        if (maxd > 16) maxd = 16;
-        JumpNeeds needs;
-        const bool use_full = tabs.B > 1 && !loc; // the blocked instantiation
-        for (;;) {
-            plan_depth = 0;
-            for (uint32_t cnt = 0; cnt <= tabs.B; ++cnt) {
-                JumpPlan& pl = plans[cnt];
-                if (cnt == 0) { pl = JumpPlan(); std::memset(pl.depth, 0, sizeof(pl.depth)); pl.max_depth = 0; continue; }
-                plan_jump_tables(tabs.infix[cnt], maxd, pl, p->E, ix->h.n_bwt, ix->h.sigma, cnt, tabs.B > 1 && !loc);
-                plan_depth = std::max(plan_depth, pl.max_depth);
-            }
-            needs = jump_needs(plans, use_full);
-            if (want >= 0 || maxd <= 1) break; // a fixed depth is taken as it is
-            // automatic depth: what is missing must fit comfortably in free HBM once stale levels are dropped
-            evict_stale_jump_tables(ix, needs);
-            size_t free_b = 0, total_b = 0;
-            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); break; }
-            if (missing_jump_bytes(ix, needs) <= free_b / 10 * 8) break;
-            --maxd;
-        }
-        int rcj = ensure_jump_tables(ix, needs, stream);
-        if (rcj != GMB_OK) return rcj;
-        for (uint32_t cnt = 1; cnt <= tabs.B; ++cnt)
-            for (uint32_t s2 = 0; s2 < kMaxSearches; ++s2) {
-                const uint32_t d = plans[cnt].depth[s2];
-                SearchStart& S = starts[(size_t)cnt * kMaxSearches + s2];
-                std::memset(&S, 0, sizeof(S));
-                const bool full = d && plans[cnt].need_lof[s2] && use_full;
-                S.uni = (d && !full) ? ix->jt_uni[d] : nullptr;
-                S.lof = (d && !full && plans[cnt].need_lof[s2]) ? ix->jt_lof[d] : nullptr;
-                S.full = full ? ix->jt_full[d] : nullptr;
-                S.a = plans[cnt].a[s2];
-                S.d = d;
-                S.n_var = std::max(1u, plans[cnt].n_var[s2]);
-            }
-        // lay the variant sets of all tables out in one array and turn the indices into device pointers
-        std::vector<size_t> base_of(tabs.B + 1, 0);
-        for (uint32_t cnt = 1; cnt <= tabs.B; ++cnt) {
-            base_of[cnt] = variants.size();
-            variants.insert(variants.end(), plans[cnt].variants.begin(), plans[cnt].variants.end());
-            if (plans[cnt].variants.empty()) variants.push_back(0xffffffffu);
-        }
-        if (ix->variants_cap < variants.size()) {
-            if (ix->d_variants) cudaFree(ix->d_variants);
-            ix->d_variants = nullptr;
-            ix->variants_cap = variants.size() * 2 + 64;
-            CU(cudaMalloc(&ix->d_variants, ix->variants_cap * sizeof(uint32_t)));
-        }
-        CU(cudaMemcpyAsync(ix->d_variants, variants.data(), variants.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        for (uint32_t cnt = 1; cnt <= tabs.B; ++cnt)
-            for (uint32_t s2 = 0; s2 < kMaxSearches; ++s2)
-            {
-                SearchStart& S = starts[(size_t)cnt * kMaxSearches + s2];
-                S.var = ix->d_variants + base_of[cnt] + plans[cnt].var_off[s2];
-                S.set0 = plans[cnt].variants.empty() ? 0xffffffffu : variants[base_of[cnt] + plans[cnt].var_off[s2]];
-            }
-    }
-    // search tables: step words, then the jump-table starts, in one device scratch buffer
-    const size_t step_bytes = tabs.steps.size() * sizeof(uint32_t);
-    const size_t start_off = (step_bytes + 15) / 16 * 16;
-    CU(cudaMemcpyAsync(ix->d_steps, tabs.steps.data(), step_bytes, cudaMemcpyHostToDevice, stream));
-    CU(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(ix->d_steps) + start_off, starts.data(), starts.size() * sizeof(SearchStart),
-                       cudaMemcpyHostToDevice, stream));
-    // (copies from pageable host memory are staged before the call returns, so the vectors may go out of scope)
-    L.cx.steps = ix->d_steps;
-    L.cx.starts = reinterpret_cast<const SearchStart*>(reinterpret_cast<const uint8_t*>(ix->d_steps) + start_off);
+    const uint32_t plan_depth = plan->plan_depth;
+    L.cx.steps = plan->d_tables;
+    L.cx.starts = reinterpret_cast<const SearchStart*>(reinterpret_cast<const uint8_t*>(plan->d_tables) + plan->start_off);
     L.cx.p1_off = nullptr; L.cx.fl_off = nullptr; // the kernel points them at its shared-memory copies
     L.n_step_words = (uint32_t)tabs.steps.size();
     for (uint32_t c2 = 0; c2 <= kMaxBlockKmers; ++c2) { L.p1_off[c2] = tabs.p1_off[c2]; L.fl_off[c2] = tabs.fl_off[c2]; }
@@ -746,7 +879,11 @@ int gmb_map_frequencies_range(gmb_index* ix, const gmb_params* p, uint64_t text_
             CU(cudaEventCreateWithFlags(&ix->ev_piece[1], cudaEventDisableTiming));
         }
         CU(cudaMemsetAsync(ix->d_out, 0, bytes, ix->s_compute));
+        CU(cudaMemsetAsync(ix->d_counters + 15, 0, sizeof(unsigned long long), ix->s_compute));
         CU(cudaEventRecord(ix->ev0, ix->s_compute));
+        ix->prog_total.store(pos_end - pos_begin);
+        struct PipelineFlag { bool& f; ~PipelineFlag() { f = false; } } in_pipeline{ix->prog_in_pipeline};
+        ix->prog_in_pipeline = true;
         uint32_t n_piece = 0;
         for (uint64_t b = pos_begin; b < pos_end; b += piece, ++n_piece) {
             const uint64_t e = std::min(b + piece, pos_end);
@@ -757,6 +894,8 @@ int gmb_map_frequencies_range(gmb_index* ix, const gmb_params* p, uint64_t text_
             local.positions += st.positions;
             local.kernel_launches += st.kernel_launches;
             local.jump_depth = st.jump_depth;
+            const unsigned long long done_so_far = local.positions; // staged at once (pageable source)
+            CU(cudaMemcpyAsync(ix->d_counters + 15, &done_so_far, sizeof(done_so_far), cudaMemcpyHostToDevice, ix->s_compute));
             CU(cudaEventRecord(ix->ev_piece[n_piece & 1], ix->s_compute));
             CU(cudaStreamWaitEvent(ix->s_copy, ix->ev_piece[n_piece & 1], 0));
             CU(cudaMemcpyAsync(static_cast<uint8_t*>(out) + (b - pos_begin) * elem,
@@ -769,6 +908,7 @@ int gmb_map_frequencies_range(gmb_index* ix, const gmb_params* p, uint64_t text_
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
         local.kernel_ms = ms;
+        ix->prog_total.store(local.positions);
     }
     if (stats) *stats = local;
     return GMB_OK;

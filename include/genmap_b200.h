@@ -23,6 +23,11 @@
  *     the message is available from gmb_last_error() (thread-local).
  *   - there is NO CPU fallback: without a CUDA device (or if the kernels fail to load) the compute
  *     entry points return GMB_ERR_CUDA.
+ *   - ONE call in flight per handle: a handle keeps per-call device scratch (work ranges, work counter) and
+ *     may rebuild or drop its cached jump tables when the configuration changes.  Calls on one handle must come
+ *     from one host thread at a time and, for the asynchronous gmb_map_frequencies_device, on one CUDA stream
+ *     (stream order then protects the scratch).  Use one handle per stream / host thread (gmb_index_replicate
+ *     onto the same device gives an independent handle).
  * Plain pointers and sizes only; no torch / STL types in any signature.
  */
 #ifndef GENMAP_B200_H
@@ -68,13 +73,14 @@ typedef struct gmb_index_info {
     void *device_blob;    /* device address of the blob (for broadcast / diagnostics) */
     int32_t device;
     int32_t alphabet_size; /* 4 = Dna4; 5 = Dna5, chosen when the text contains N (src/indexing.hpp:459-473) */
+    uint64_t jump_table_bytes; /* HBM currently held by the handle's jump tables (built lazily by the map calls) */
 } gmb_index_info;
 
 typedef struct gmb_map_stats {
     double kernel_ms;            /* CUDA-event time of the search kernel */
     uint64_t positions;          /* k-mer starts actually searched */
-    uint64_t rank_block_fetches; /* only with count_fetches: 64-byte rank blocks read */
-    uint64_t jump_table_reads;   /* only with count_fetches: jump-table entries read (8 or 12 bytes each) */
+    uint64_t rank_block_fetches; /* only with count_fetches: 32-byte rank blocks read */
+    uint64_t jump_table_reads;   /* only with count_fetches: jump-table entries read (8, 12 or 16 bytes each) */
     uint32_t kernel_launches;
     uint32_t jump_depth;         /* deepest jump table used by this call (0 = none) */
     /* only with count_fetches: the fetches split by the size of the suffix-array interval being expanded
@@ -121,10 +127,18 @@ int gmb_index_adopt_device(void *device_blob, uint64_t bytes, int device, gmb_in
 int gmb_index_replicate(const gmb_index *src, int device, gmb_index **out);
 int gmb_index_close(gmb_index *idx);
 int gmb_index_get_info(const gmb_index *idx, gmb_index_info *info);
-/* Maximum depth of the jump tables that replace the first error-free steps of every search:
- * -1 = automatic (floor(log4 N), at most 15), 0 = off, 1..16 = fixed.  Tables are built lazily on the
- * device by the first map call that needs them and cached in the handle. */
+/* Maximum depth of the jump tables that replace the first steps of every search:
+ * -1 = automatic (ceil(log4 N), at most 16, less when HBM is short), 0 = off, 1..16 = fixed.  Tables are built
+ * lazily on the device by the first map call that needs them and cached in the handle. */
 int gmb_index_set_jump_depth(gmb_index *idx, int depth);
+/* Plan the searches (part lengths of the search scheme, k-mers per block, jump-table entry depths) as if the
+ * text had n_symbols symbols; 0 = the index's own size (default).  Results never depend on the plan, only the
+ * cost does: this is how the plan of a 3 Gbp genome is exercised on a small one (tests), or a plan pinned. */
+int gmb_index_set_plan_text_size(gmb_index *idx, uint64_t n_symbols);
+/* Progress of the map call in flight on this handle, readable from another host thread (what the reference prints
+ * as "Progress: x%", src/common.hpp:94-131, src/algo.hpp:478-481): k-mer start positions handed out so far and
+ * the total of the call.  Both are 0 before the first call. */
+int gmb_progress(gmb_index *idx, uint64_t *done, uint64_t *total);
 /* Diagnostics / test support: decode one direction's BWT (rev = 0: of T, 1: of T') to one byte per
  * row (0 = sentinel, 1..5 = A,C,G,T,N) into host memory (n_bwt bytes). */
 int gmb_index_export_bwt(gmb_index *idx, int rev, uint8_t *out_host);

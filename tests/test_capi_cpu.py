@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.GmbParams) == 32
-    assert ctypes.sizeof(_lib.GmbIndexInfo) == 56
+    assert ctypes.sizeof(_lib.GmbIndexInfo) == 64
     assert ctypes.sizeof(_lib.GmbMapStats) == 120
 
 

@@ -492,3 +492,121 @@ def test_cuda_index_replica_on_a_second_gpu(gm):
         assert np.array_equal(ix0.compute_mappability(gm.SearchParams(K, E)), ix1.compute_mappability(gm.SearchParams(K, E)))
     same = ix0.replicate(0)  # a second copy on the same device also works
     assert np.array_equal(same.compute_mappability(gm.SearchParams(30, 1)), ix0.compute_mappability(gm.SearchParams(30, 1)))
+
+
+# ---- the code paths that only exist at the benchmarked scale, exercised on small genomes -------------------------
+# (the 3 Gbp bench runs jump tables of depth 13-16 — 4^16 entries, 16-byte entries with both intervals,
+# substituted keys at depth 15/16 — and model-chosen part lengths / block sizes that no small genome selects by
+# itself.  The plan depends on the text size only through the planner, so the planner is told a size.)
+def _close(ix):
+    import torch
+    ix.close()
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("with_n", [False, True], ids=["dna4", "dna5"])
+def test_cuda_plan_of_a_3gbp_genome_on_a_small_one(gm, with_n):
+    """The exact search plan of the 3 Gbp bench genome (block sizes, part lengths, entry depths up to 16 with
+    substituted keys, 34-69 GB tables) executed on a 3 x 6 kbp genome, against the oracle."""
+    seqs = T.repeat_rich(31, 3, 6000, with_n=with_n)
+    _, limits = T.concat(seqs)
+    ix, orc = gm.Index.build(seqs), T.Oracle(seqs)
+    ix.set_plan_text_size(3_000_000_024)
+    deepest = 0
+    try:
+        for K, E in [(30, 0), (30, 1), (30, 2), (50, 2), (36, 3)]:
+            for rc in (True, False):
+                want = orc.map(K, E, revcompl=rc)
+                for B in (0, 1):
+                    p = gm.SearchParams(K, E, rev_compl=rc, block_kmers=B)
+                    got, st = ix.compute_mappability(p, chrom_cum_lengths=limits, return_stats=True)
+                    assert np.array_equal(got, want), (K, E, rc, B, st.jump_depth, np.nonzero(got != want)[0][:10])
+                    deepest = max(deepest, int(st.jump_depth))
+        assert deepest == 16, deepest
+        assert int(ix.refresh_info().jump_table_bytes) > (30 << 30)
+    finally:
+        _close(ix)
+
+
+@pytest.mark.parametrize("depth", [13, 14, 15, 16])
+def test_cuda_jump_tables_of_depth_13_to_16(gm, depth):
+    """Every table flavour (8-byte entries, + SA(T) array, 16-byte entries) at the depths the small-genome tests never
+    reach (tables have 4^d entries whatever the genome), E = 0, 1, 2, both alphabets."""
+    for with_n in (False, True):
+        seqs = T.repeat_rich(33 + depth, 2, 5000, with_n=with_n)
+        _, limits = T.concat(seqs)
+        ix, orc = gm.Index.build(seqs), T.Oracle(seqs)
+        ix.set_plan_text_size(4 ** depth - 1)  # the planner's idea of the text: picks entry depths up to `depth`
+        try:
+            for K, E in [(30, 0), (30, 1), (30, 2), (24, 2)]:
+                want = orc.map(K, E)
+                for B in (0, 1):
+                    got, st = ix.compute_mappability(gm.SearchParams(K, E, block_kmers=B), chrom_cum_lengths=limits, return_stats=True)
+                    assert np.array_equal(got, want), (depth, with_n, K, E, B, st.jump_depth)
+                    assert E != 0 or st.jump_depth == depth, (depth, st.jump_depth)
+            # a fixed depth instead of a planned one (E = 0 enters at exactly that depth)
+            ix.set_plan_text_size(0)
+            ix.set_jump_depth(depth)
+            got, st = ix.compute_mappability(gm.SearchParams(30, 0), chrom_cum_lengths=limits, return_stats=True)
+            assert np.array_equal(got, orc.map(30, 0)) and st.jump_depth == depth
+        finally:
+            _close(ix)
+
+
+def test_cuda_plan_cache_and_progress(gm):
+    """Cached plans (tables stay on the device between calls) give the same counts when configurations alternate,
+    and gmb_progress reports the finished call."""
+    seqs = gm.synth_genome(600_000, 3, 77)
+    ix = gm.Index.build(seqs)
+    assert ix.progress() == (0, 0)
+    first = {}
+    for rnd in range(3):
+        for K, E, bits in [(30, 0, 16), (30, 1, 16), (24, 2, 8), (30, 1, 8)]:
+            got = ix.compute_mappability(gm.SearchParams(K, E, value_bits=bits))
+            key = (K, E, bits)
+            if rnd == 0:
+                first[key] = got
+            else:
+                assert np.array_equal(got, first[key]), key
+            done, total = ix.progress()
+            assert done == total and 0 < total <= ix.n_text
+    assert np.array_equal(np.minimum(first[(30, 1, 16)], 255).astype(np.uint8), first[(30, 1, 8)])
+    _close(ix)
+
+
+def test_cuda_250mbp_whole_file_is_bit_exact_against_the_reference(gm):
+    """BASELINE config 2 as BASELINE.md §3 prescribes it: 250 Mbp, K = 30, E = 0, `cmp` of the whole .freq16 against
+    the unmodified reference binary; plus windows at E = 1 and E = 2 on the same index.  The reference reads an
+    index in its own format written from the GPU builder's BWT + SA (byte-identical to its own `index` output:
+    tests/test_seqan_index_writer.py, profiles/r02/writer_identity_40mbp.txt)."""
+    if not T.have_reference():
+        pytest.skip("oracle/_ref/genmap_ref not present")
+    import shutil, subprocess, tempfile
+    seqs = gm.synth_genome(250_000_000, 4, 46)
+    per = len(seqs[0])
+    ix = gm.Index.build(seqs, with_sa=True)
+    tmp = tempfile.mkdtemp(prefix="gmb_250_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        files = [("genome.fa", [("chr%d" % (i + 1), s) for i, s in enumerate(seqs)])]
+        d = T.write_seqan_index(os.path.join(tmp, "index"), files, ix.export_bwt(False), ix.export_bwt(True), ix.export_sa())
+        out = os.path.join(tmp, "out")
+        os.mkdir(out)
+        base = [T.REF_BIN, "map", "-I", d, "-O", out, "-K", "30", "-r", "-fl", "-T", str(os.cpu_count() or 1)]
+        subprocess.run(base + ["-E", "0"], check=True, stdout=subprocess.DEVNULL)
+        ref = np.fromfile(os.path.join(out, "genome.genmap.freq16"), dtype=np.uint16)
+        got = ix.compute_mappability(gm.SearchParams(30, 0))
+        assert len(ref) == len(got) == 4 * per
+        assert np.array_equal(got, ref), np.nonzero(got != ref)[0][:10]
+        assert int((got > 1).sum()) > 1_000_000  # the repeats are there
+        for E, n in ((1, 1_000_000), (2, 100_000)):
+            b = per + per // 3
+            with open(os.path.join(tmp, "w.bed"), "w") as f:
+                f.write("chr2\t%d\t%d\n" % (b - per, b - per + n))
+            subprocess.run(base + ["-E", str(E), "-S", os.path.join(tmp, "w.bed")], check=True, stdout=subprocess.DEVNULL)
+            ref = np.memmap(os.path.join(out, "genome.genmap.freq16"), dtype=np.uint16, mode="r")
+            got = ix.compute_mappability_range(gm.SearchParams(30, E), b, b + n)
+            assert np.array_equal(got, ref[b:b + n]), (E, np.nonzero(got != ref[b:b + n])[0][:10])
+            del ref
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+        _close(ix)
