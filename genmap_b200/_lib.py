@@ -34,7 +34,8 @@ class GmbMapStats(ctypes.Structure):
     _fields_ = [("kernel_ms", ctypes.c_double), ("positions", ctypes.c_uint64),
                 ("rank_block_fetches", ctypes.c_uint64), ("jump_table_reads", ctypes.c_uint64),
                 ("kernel_launches", ctypes.c_uint32), ("jump_depth", ctypes.c_uint32),
-                ("fetches_by_size", ctypes.c_uint64 * 8), ("thin_paths", ctypes.c_uint64), ("iterations", ctypes.c_uint64)]
+                ("fetches_by_size", ctypes.c_uint64 * 8), ("thin_paths", ctypes.c_uint64), ("iterations", ctypes.c_uint64),
+                ("located_entries", ctypes.c_uint64), ("text_reads", ctypes.c_uint64)]
 
 
 class GmbLocations(ctypes.Structure):

@@ -81,7 +81,7 @@ struct gmb_index {
     IndexHeader h{};
     std::vector<uint64_t> limits; // host copy
     // per-handle scratch, grown on demand
-    unsigned long long* d_counters = nullptr; // [0] work counter, [1..12] fetch counters (map_kernel.cuh), [14] run count
+    unsigned long long* d_counters = nullptr; // [0] work counter, [1..14] fetch counters (map_kernel.cuh), [15] finished pieces, [16] run count
     uint64_t* d_ranges = nullptr;
     size_t ranges_cap = 0;
     void* d_out = nullptr;
@@ -142,20 +142,31 @@ void fill_ctx(const gmb_index* ix, MapCtx& cx)
     cx.seq_to_file = nullptr;
     cx.n_seq = ix->h.n_seq; cx.own_file = 0; cx.all_files = 0;
     cx.loc_rows = nullptr;
+    cx.text = reinterpret_cast<const uint64_t*>(base + ix->h.off_text);
+    cx.n_text = ix->h.n_text;
+    cx.E = 0;
 }
 
 struct JumpNeeds { bool uni[17] = {}, lof[17] = {}, full[17] = {}; uint32_t top = 0; };
 
-// use_full: the blocked instantiation reads both intervals as one 16-byte entry; the one-k-mer instantiation keeps
-// 8-byte entries plus a separate array for the interval in SA(T)
-JumpNeeds jump_needs(const std::vector<JumpPlan>& plans, bool use_full)
+// GMB_LOCATE=0: tables without located entries (every search walks the index; for A/B measurements)
+bool locate_enabled()
+{
+    const char* env = std::getenv("GMB_LOCATE");
+    return !(env && env[0] == '0');
+}
+
+// use_full: the searches read 16-byte entries holding both intervals (the blocked instantiation, where SA(T) is needed
+// after the jump); all_full: every search does (Dna4 indices: the 16-byte entries of keys that occur once are LOCATED,
+// which ends most searches at the table read).  Otherwise 8-byte entries plus a separate array for the interval in SA(T).
+JumpNeeds jump_needs(const std::vector<JumpPlan>& plans, bool use_full, bool all_full)
 {
     JumpNeeds n;
     for (const JumpPlan& plan : plans)
         for (uint32_t s = 0; s < kMaxSearches; ++s) {
             const uint32_t d = plan.depth[s];
             if (!d) continue;
-            if (plan.need_lof[s] && use_full) n.full[d] = true;
+            if ((plan.need_lof[s] && use_full) || all_full) n.full[d] = true;
             else { n.uni[d] = true; if (plan.need_lof[s]) n.lof[d] = true; }
             n.top = std::max(n.top, d);
         }
@@ -245,6 +256,9 @@ int ensure_jump_tables(gmb_index* ix, const JumpNeeds& n, cudaStream_t stream)
             cudaError_t err = jt_alloc(ix, n, &ix->jt_full[d], e * sizeof(JtFull));
             if (err == cudaSuccess)
                 err = build_jump_level(cx, ix->h.sigma, d, ix->jt_uni[d - 1], ix->jt_lof[d - 1], nullptr, nullptr, ix->jt_full[d], stream);
+            if (err == cudaSuccess && ix->h.sigma == 4 && locate_enabled()) // keys that occur once: position + context instead of intervals
+                err = locate_jump_singletons(reinterpret_cast<const uint64_t*>(ix->d_blob + ix->h.off_text), ix->h.n_text, cx.seq_start,
+                                             ix->h.n_seq, d, ix->jt_full[d], stream);
             if (err != cudaSuccess) return cuda_fail(err, "jump table");
         }
     }
@@ -318,7 +332,8 @@ static int finish_open(gmb_index* ix, gmb_index** out)
     ix->sm_count = prop.multiProcessorCount;
     ix->limits.resize((size_t)ix->h.n_seq + 1);
     CU(cudaMemcpy(ix->limits.data(), ix->d_blob + ix->h.off_limits, ix->limits.size() * 8, cudaMemcpyDeviceToHost));
-    CU(cudaMalloc(&ix->d_counters, 16 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&ix->d_counters, 24 * sizeof(unsigned long long)));
+    CU(cudaMemset(ix->d_counters, 0, 24 * sizeof(unsigned long long)));
     CU(cudaEventCreate(&ix->ev0));
     CU(cudaEventCreate(&ix->ev1));
     CU(cudaStreamCreateWithFlags(&ix->s_progress, cudaStreamNonBlocking));
@@ -616,6 +631,7 @@ static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool l
     if (maxd > 16) maxd = 16;
     JumpNeeds needs;
     const bool use_full = tabs.B > 1 && !loc; // the blocked instantiation
+    const bool all_full = !loc && ix->h.sigma == 4 && locate_enabled();
     for (;;) {
         plan_depth = 0;
         for (uint32_t cnt = 0; cnt <= tabs.B; ++cnt) {
@@ -624,7 +640,7 @@ static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool l
             plan_jump_tables(tabs.infix[cnt], maxd, pl, p->E, model_n, ix->h.sigma, cnt, tabs.B > 1 && !loc);
             plan_depth = std::max(plan_depth, pl.max_depth);
         }
-        needs = jump_needs(plans, use_full);
+        needs = jump_needs(plans, use_full, all_full);
         if (want >= 0 || maxd <= 1) break; // a fixed depth is taken as it is
         // automatic depth: what is missing must fit comfortably in free HBM, if need be after dropping the cached
         // tables this configuration does not use
@@ -647,7 +663,7 @@ static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool l
             const uint32_t d = plans[cnt].depth[s2];
             SearchStart& S = starts[(size_t)cnt * kMaxSearches + s2];
             std::memset(&S, 0, sizeof(S));
-            const bool full = d && plans[cnt].need_lof[s2] && use_full;
+            const bool full = d && ((plans[cnt].need_lof[s2] && use_full) || all_full);
             S.uni = (d && !full) ? ix->jt_uni[d] : nullptr;
             S.lof = (d && !full && plans[cnt].need_lof[s2]) ? ix->jt_lof[d] : nullptr;
             S.full = full ? ix->jt_full[d] : nullptr;
@@ -753,7 +769,7 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
         CU(cudaMalloc(&ix->d_ranges, ix->ranges_cap * 8));
     }
     CU(cudaMemcpyAsync(ix->d_ranges, host_ranges.data(), host_ranges.size() * 8, cudaMemcpyHostToDevice, stream));
-    CU(cudaMemsetAsync(ix->d_counters, 0, (ix->prog_in_pipeline ? 15 : 16) * sizeof(unsigned long long), stream));
+    CU(cudaMemsetAsync(ix->d_counters, 0, (ix->prog_in_pipeline ? 15 : 16) * sizeof(unsigned long long), stream)); // [15]: see gmb_progress
     ix->prog_chunk.store(chunk);
     if (!ix->prog_in_pipeline) ix->prog_total.store(total);
 
@@ -769,6 +785,7 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
     L.chunk = (uint32_t)chunk;
     L.cx.K = p->K;
     L.cx.B = tabs.B;
+    L.cx.E = p->E;
     L.cx.n_search = tabs.n_search;
     L.cx.n_strands = p->revcompl ? 2u : 1u;
     L.cx.maxv = p->value_bits == 16 ? 65535u : 255u;
@@ -813,13 +830,15 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
         stats->kernel_launches = 1;
         stats->jump_depth = plan_depth;
         if (L.count_fetches) {
-            unsigned long long f[12] = {};
+            unsigned long long f[14] = {};
             CU(cudaMemcpy(f, ix->d_counters + 1, sizeof(f), cudaMemcpyDeviceToHost));
             stats->rank_block_fetches = f[0];
             stats->jump_table_reads = f[1];
             for (int k = 0; k < 8; ++k) stats->fetches_by_size[k] = f[2 + k];
             stats->thin_paths = f[10];
             stats->iterations = f[11];
+            stats->located_entries = f[12];
+            stats->text_reads = f[13];
         }
     }
     return GMB_OK;
@@ -1127,7 +1146,7 @@ int gmb_map_runs(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64
     DevBuf cum, temp, starts, values;
     CU(cum.alloc(((size_t)n_chrom + 1) * 8));
     CU(cudaMemcpyAsync(cum.p, chrom_cum, ((size_t)n_chrom + 1) * 8, cudaMemcpyHostToDevice, nullptr));
-    unsigned long long* d_count = ix->d_counters + 14;
+    unsigned long long* d_count = ix->d_counters + 16;
     CU(cudaEventRecord(ix->ev0, nullptr));
     size_t tb1 = 0, tb2 = 0;
     CU(rle_count(biased, p->value_bits, cum.as<uint64_t>(), n_chrom, pos_begin, pos_end, d_count, nullptr, tb1, nullptr));

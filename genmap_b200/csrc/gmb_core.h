@@ -1,4 +1,4 @@
-// gmb_core.h — rank arithmetic on the 64-byte blocks and the per-k-mer search state machine.
+// gmb_core.h — rank arithmetic on the 32-byte rank blocks and the per-k-mer search state machine.
 //
 // One "chain" (a CUDA thread in map_kernel.cu) owns one k-mer start at a time and walks the
 // bidirectional FM-index with the optimum-search-scheme bounds.  The recursion of the reference
@@ -389,6 +389,19 @@ GMB_HD void load_pattern(Pattern<KW, SIGMA>& p, const uint64_t* text, const uint
 // keys).  One table read replaces the walk through the dense top of the trie (JumpPlan, gmb_host.h).
 struct JtEntry { uint32_t lo_r, size; };
 struct JtFull { uint32_t lo_r, size, lo_f, pad; }; // both intervals in one 16-byte entry: one memory request
+// LOCATED entries (Dna4 tables, set by the text pass of jump_table.cu): a key that occurs exactly ONCE in the text
+// carries where — and what stands around it — instead of its two one-row intervals:
+//     lo_r = q, the text position of the occurrence (concatenated text, no sentinels)
+//     size = kLocated | 1
+//     lo_f = the kCtx characters right of the key window, text[q+d+i] in bits 2i
+//     pad  = the kCtx characters left of it,            text[q-kCtx+i] in bits 2i
+// A search entered through such an entry has ONE candidate alignment: it is finished by comparing the needle with
+// the text (verify_located) — from the 2*kCtx context characters when they cover the needle (no memory access at
+// all), else from one read of the packed text — instead of walking the index through one-row intervals, one
+// dependent rank-block fetch per character.  At 3 Gbp 69 % of the existing depth-16 entries are of this kind.
+constexpr uint32_t kLocated = 0x80000000u;
+constexpr uint32_t kCtx = 16;
+constexpr uint32_t kLocateMargin = 512; // keys this close to either end of the text are never located (> kMaxK + 16 + 32 * 9)
 struct SearchStart {
     const JtEntry* uni;   // [4^d] interval in SA(T') + size            (nullptr: no table, start at the root)
     const uint32_t* lof;  // [4^d] start of the interval in SA(T)       (nullptr when never needed again or `full` is set)
@@ -412,7 +425,7 @@ struct MapCtx {
     const uint32_t* p1_off;
     const uint32_t* fl_off;
     const SearchStart* starts; // [cnt * kMaxSearches + search]
-    uint32_t K, B, n_search, n_strands, maxv;
+    uint32_t K, B, E, n_search, n_strands, maxv;
     // --exclude-pseudo only (src/algo.hpp:351-361): locate every hit and count distinct FASTA files
     const uint32_t* sa;          // full suffix array of T
     const uint32_t* seq_start;   // n_seq + 1 sequence starts inside T
@@ -422,6 +435,9 @@ struct MapCtx {
     // locate instantiation only (csv output, src/algo.hpp:311-343): second pass writes the SA value of every
     // occurrence; nullptr in the first (counting) pass
     uint32_t* loc_rows;
+    // located table entries (verify_located): the packed text and its length
+    const uint64_t* text;
+    uint64_t n_text;
 };
 
 struct Node { uint32_t lo_f, lo_r, size; };
@@ -434,8 +450,10 @@ struct FetchStats {
     unsigned long long by_size[8];
     unsigned long long thin_paths;
     unsigned long long iterations; // passes through the state machine (expansions, table reads, window switches)
+    unsigned long long located;    // searches finished by verify_located (table entry of a key that occurs once)
+    unsigned long long text_reads; // ... of which needed a read of the packed text (the entry's context did not cover the needle)
 };
-constexpr int kFetchStatWords = 11;
+constexpr int kFetchStatWords = 13;
 GMB_HD uint32_t size_bucket(uint32_t n)
 {
     if (n <= 1u) return 0u;
@@ -543,7 +561,8 @@ struct Chain {
     uint32_t lvmask;           // error levels holding a frame with pending children
     uint32_t cnt, win, leaf_e; // k-mers in this block; window being completed (kNoWin: infix search); errors of the infix hit
     uint64_t files;            // B == 1, --exclude-pseudo: FASTA files seen so far (one bit each)
-    uint32_t pre_lo_f, pre_lo_r, pre_size; // jump-table entry of (reverse strand, search 0), fetched early
+    uint32_t pre_lo_f, pre_lo_r, pre_size, pre_ctx; // jump-table entry of (reverse strand, search 0), fetched early
+    uint32_t ctx_l;            // located entry (size & kLocated): its left context; lo_r = text position, lo_f = right context
     bool has_n;                // Dna5: the needle contains N (then no occurrence is error-free)
     // locate instantiation: occurrences found so far per strand (not saturated) and where this k-mer's two
     // lists start in cx.loc_rows
@@ -585,11 +604,11 @@ GMB_HD uint32_t frame_store_words(uint32_t E, uint32_t B, bool ep, int sigma, bo
     return E * frame_words(sigma) + kLeafWords + (blocked ? B * (ep ? 3u : 1u) : 0u);
 }
 
-GMB_HD void jump_lookup(const SearchStart& S, uint32_t key, uint32_t& lo_f, uint32_t& lo_r, uint32_t& size)
+GMB_HD void jump_lookup(const SearchStart& S, uint32_t key, uint32_t& lo_f, uint32_t& lo_r, uint32_t& size, uint32_t& pad)
 {
+    pad = 0u;
 #if defined(__CUDA_ARCH__)
     if (S.full) {
-        [[maybe_unused]] uint32_t pad;
         asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo_r), "=r"(size), "=r"(lo_f), "=r"(pad) : "l"(S.full + key));
         return;
     }
@@ -597,7 +616,7 @@ GMB_HD void jump_lookup(const SearchStart& S, uint32_t key, uint32_t& lo_f, uint
     lo_f = 0u;
     if (S.lof) asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(lo_f) : "l"(S.lof + key));
 #else
-    if (S.full) { lo_r = S.full[key].lo_r; size = S.full[key].size; lo_f = S.full[key].lo_f; return; }
+    if (S.full) { lo_r = S.full[key].lo_r; size = S.full[key].size; lo_f = S.full[key].lo_f; pad = S.full[key].pad; return; }
     lo_r = S.uni[key].lo_r; size = S.uni[key].size;
     lo_f = S.lof ? S.lof[key] : 0u;
 #endif
@@ -628,11 +647,12 @@ GMB_HD void chain_start(Chain<KW, SIGMA>& st, const MapCtx& cx, unsigned long lo
     if constexpr (!BLK) {
         const SearchStart& S = cx.starts[kMaxSearches + st.s];
         st.e = 0; st.lvmask = 0; st.win = kNoWin; st.leaf_e = 0; st.thin = false;
-        if (S.uni == nullptr) {
+        if (S.uni == nullptr && S.full == nullptr) {
             st.lo_f = 0; st.lo_r = 0; st.size = cx.n_bwt; st.t = 0;
         } else {
-            if (st.strand == 1 && st.s == 0) { st.lo_f = st.pre_lo_f; st.lo_r = st.pre_lo_r; st.size = st.pre_size; }
+            if (st.strand == 1 && st.s == 0) { st.lo_f = st.pre_lo_f; st.lo_r = st.pre_lo_r; st.size = st.pre_size; st.ctx_l = st.pre_ctx; }
             else if (S.set0 == kDeadVariant || (SIGMA == 5 && st.pat.has_n(S.a, S.d))) { st.lo_f = 0; st.lo_r = 0; st.size = 0; } // N never matches
+            else if (SIGMA == 4 && S.full) jump_lookup(S, st.pat.bits(S.a, S.d), st.lo_f, st.lo_r, st.size, st.ctx_l);
             else jump_lookup_lean(S, st.pat.bits(S.a, S.d), st.lo_f, st.lo_r, st.size);
             st.t = S.d;
             if (lut_reads) *lut_reads += 1;
@@ -649,7 +669,7 @@ GMB_HD void chain_start(Chain<KW, SIGMA>& st, const MapCtx& cx, unsigned long lo
 #else
         const uint32_t set = st.var == 0 ? S.set0 : S.var[st.var];
 #endif
-        if (st.strand == 1 && st.s == 0 && set == 0xffffffffu) { st.lo_f = st.pre_lo_f; st.lo_r = st.pre_lo_r; st.size = st.pre_size; st.nsub = 1; }
+        if (st.strand == 1 && st.s == 0 && set == 0xffffffffu) { st.lo_f = st.pre_lo_f; st.lo_r = st.pre_lo_r; st.size = st.pre_size; st.ctx_l = st.pre_ctx; st.nsub = 1; }
         else if (set == kDeadVariant || (SIGMA == 5 && st.pat.has_n(S.a, S.d))) { st.lo_f = 0; st.lo_r = 0; st.size = 0; st.nsub = 1; } // N never matches
         else {
             // substitute: offset p of the set gets one of the three other characters (XOR with 1..3), chosen by the
@@ -663,7 +683,7 @@ GMB_HD void chain_start(Chain<KW, SIGMA>& st, const MapCtx& cx, unsigned long lo
                     if (p != 0xffu) { key ^= (1u + q % 3u) << (2u * p); q /= 3u; n3 *= 3u; ++e; }
                 }
             }
-            jump_lookup(S, key, st.lo_f, st.lo_r, st.size);
+            jump_lookup(S, key, st.lo_f, st.lo_r, st.size, st.ctx_l);
             st.e = e; st.nsub = n3;
         }
         st.t = S.d;
@@ -686,11 +706,12 @@ GMB_HD void chain_begin_block(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx
     // the reverse strand's first jump-table entry does not depend on the forward search: request it now so
     // that its latency overlaps the forward strand instead of starting the reverse strand with a stall
     const SearchStart S0 = cx.starts[(BLK ? st.cnt : 1u) * kMaxSearches];
-    if (cx.n_strands > 1 && (S0.uni != nullptr || (BLK && S0.full != nullptr))) {
+    if (cx.n_strands > 1 && (S0.uni != nullptr || S0.full != nullptr)) {
         Pattern<KW, SIGMA> rc = st.pat;
         rc.reverse_complement(cx.K + (BLK ? st.cnt : 1u) - 1);
+        st.pre_ctx = 0;
         if (SIGMA == 5 && rc.has_n(S0.a, S0.d)) { st.pre_lo_f = 0; st.pre_lo_r = 0; st.pre_size = 0; }
-        else if (BLK) jump_lookup(S0, rc.bits(S0.a, S0.d), st.pre_lo_f, st.pre_lo_r, st.pre_size);
+        else if (BLK || (SIGMA == 4 && S0.full)) jump_lookup(S0, rc.bits(S0.a, S0.d), st.pre_lo_f, st.pre_lo_r, st.pre_size, st.pre_ctx);
         else jump_lookup_lean(S0, rc.bits(S0.a, S0.d), st.pre_lo_f, st.pre_lo_r, st.pre_size);
     }
     chain_start<KW, BLK, SIGMA>(st, cx, lut_reads);
@@ -759,6 +780,142 @@ GMB_HD void chain_count(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, uint
     }
 }
 
+// ---- located table entries: one candidate alignment, finished by comparison with the text ------------------------
+// mismatch bits of the needle against the text in 2-bit spacing (bit 2i of word k: character 32k + i differs)
+template <int KW>
+GMB_HD uint32_t count_mismatches(const uint64_t (&mm)[KW], uint32_t b, uint32_t e) // characters [b, e) of the needle
+{
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < KW; ++k) {
+        const uint32_t w0 = 32u * (uint32_t)k;
+        const uint32_t lo = b > w0 ? b - w0 : 0u, hi = e < w0 + 32u ? (e > w0 ? e - w0 : 0u) : 32u;
+        if (lo < hi) {
+            const uint64_t upto = hi == 32u ? ~0ull : ((1ull << (2u * hi)) - 1ull);
+            const uint64_t m = mm[k] & upto & ~((1ull << (2u * lo)) - 1ull);
+#if defined(__CUDA_ARCH__)
+            c += (uint32_t)__popcll(m);
+#else
+            c += (uint32_t)__builtin_popcountll(m);
+#endif
+        }
+    }
+    return c;
+}
+
+// mark FASTA file `file` for window w of the strand (--exclude-pseudo)
+template <int KW, bool BLK, int SIGMA, class Frames>
+GMB_HD void chain_mark_file(Chain<KW, SIGMA>& st, Frames& fr, uint32_t w, uint32_t file)
+{
+    const uint32_t widx = !BLK ? 0u : (st.strand ? st.cnt - 1u - w : w);
+    if (!BLK) { st.files |= 1ull << file; return; }
+    const uint32_t at = kLeafWords + st.cnt + 2 * widx;
+    if (file < 32u) fr.xset(at, fr.xget(at) | (1u << file));
+    else fr.xset(at + 1, fr.xget(at + 1) | (1u << (file - 32u)));
+}
+
+// The current search of the chain was entered through a LOCATED entry (see JtFull): the key of the entry occurs once
+// in the text, at position st.lo_r, so the search has one candidate alignment: needle[x] <-> text[q - a + x].  What the
+// index walk would find below this node is decided here by direct comparison:
+//   1. mismatch bits of the whole needle against the text — from the entry's 2 x kCtx context characters when they
+//      cover the needle (no memory access), else from one read of the packed text;
+//   2. more than E mismatches inside the infix: nothing (almost every chance hit ends here);
+//   3. the steps of the search over the infix with these mismatches, under the scheme's bounds (the same test per step
+//      as chain_step: an alignment is found by exactly one search of the scheme);
+//   4. every window whose K characters hold at most E mismatches and lie inside one sequence counts one occurrence
+//      (the index walk cannot leave a sequence: sentinels; here the sequence limits are checked).
+template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
+GMB_HD void verify_located(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, FetchStats* fetches)
+{
+    const uint32_t K = cx.K, cnt = BLK ? st.cnt : 1u;
+    const uint32_t Li = K - cnt + 1, NL = K + cnt - 1, E = cx.E;
+    const SearchStart& S = cx.starts[cnt * kMaxSearches + st.s];
+    const uint32_t q = st.lo_r, ctx_r = st.lo_f, ctx_l = st.ctx_l;
+    const uint32_t tab = (BLK ? cx.p1_off[cnt] : 0u) + st.s * Li;
+    if (fetches) ++fetches->located;
+    uint32_t set = 0xffffffffu;
+    if constexpr (BLK) {
+#if defined(__CUDA_ARCH__)
+        set = st.var == 0 ? S.set0 : __ldg(S.var + st.var);
+#else
+        set = st.var == 0 ? S.set0 : S.var[st.var];
+#endif
+    }
+    if (st.strand == 0 && set == 0xffffffffu) {
+        // the query's own window is an occurrence of its own key, and the key occurs once: this is the query itself
+        if (step_exact_ok(cx.steps[tab]))
+            for (uint32_t w = 0; w < cnt; ++w) chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, w, 0, 1, true);
+        return;
+    }
+    const uint64_t t0 = (uint64_t)q - S.a; // the table builder leaves keys near the ends of the text unlocated: no underflow
+    uint64_t mm[KW];
+    bool covered = false;
+    if constexpr (KW <= 2) covered = S.a <= kCtx && NL - S.a - S.d <= kCtx;
+    if (covered) {
+        // text[q - kCtx, q + d + kCtx) as one bit string T (character c in bits 2c), shifted so that character 0 is the needle's
+        uint32_t key = st.pat.bits(S.a, S.d);
+        if constexpr (BLK) {
+            if (set != 0xffffffffu) {
+                uint32_t sub = st.sub;
+#pragma unroll
+                for (uint32_t k = 0; k < kMaxE; ++k) {
+                    const uint32_t p = (set >> (8 * k)) & 0xffu;
+                    if (p != 0xffu) { key ^= (1u + sub % 3u) << (2u * p); sub /= 3u; }
+                }
+            }
+        }
+        const uint32_t sh = 32u + 2u * S.d; // 34..64
+        const uint64_t t_lo = (uint64_t)ctx_l | ((uint64_t)key << 32) | (sh < 64u ? (uint64_t)ctx_r << sh : 0ull);
+        const uint64_t t_hi = (uint64_t)ctx_r >> (64u - sh);
+        const uint32_t s2 = 2u * (kCtx - S.a); // 0..32
+        uint64_t tw[2];
+        tw[0] = s2 ? (t_lo >> s2) | (t_hi << (64u - s2)) : t_lo;
+        tw[1] = t_hi >> s2;
+#pragma unroll
+        for (int k = 0; k < KW; ++k) {
+            const uint64_t x = st.pat.w[k] ^ tw[k < 2 ? k : 1];
+            mm[k] = (x | (x >> 1)) & 0x5555555555555555ull;
+        }
+    } else {
+        if (fetches) ++fetches->text_reads;
+        Pattern<KW, SIGMA> tp;
+        load_pattern(tp, cx.text, nullptr, t0, NL);
+#pragma unroll
+        for (int k = 0; k < KW; ++k) {
+            const uint64_t x = st.pat.w[k] ^ tp.w[k];
+            mm[k] = (x | (x >> 1)) & 0x5555555555555555ull;
+        }
+    }
+    if (count_mismatches<KW>(mm, cnt - 1u, K) > E) return;
+    // the search's steps over the infix, with the text's mismatches (admissible child: e' <= ub and e' + rem >= lb)
+    uint32_t e = 0;
+    for (uint32_t t = 0; t < Li; ++t) {
+        const uint32_t ent = cx.steps[tab + t], x = step_pos(ent);
+        e += (uint32_t)(mm[KW == 1 ? 0 : (x >> 5)] >> (2u * (x & 31u))) & 1u;
+        if (e > step_ub(ent) || e + step_rem(ent) < step_lb(ent)) return;
+    }
+    // the sequence holding the occurrence (largest s with limits[s] <= q, limits[s] = seq_start[s] - s), looked up
+    // only when a window qualifies
+    uint32_t sq = 0xffffffffu;
+    uint64_t sb = 0, se = 0;
+    for (uint32_t w = 0; w < cnt; ++w) {
+        if (count_mismatches<KW>(mm, w, w + K) > E) continue;
+        if (sq == 0xffffffffu) {
+            uint32_t a = 0, b = cx.n_seq;
+            while (b - a > 1) {
+                const uint32_t mid = (a + b) >> 1;
+                if ((uint64_t)cx.seq_start[mid] - mid <= (uint64_t)q) a = mid; else b = mid;
+            }
+            sq = a;
+            sb = (uint64_t)cx.seq_start[a] - a;
+            se = (uint64_t)cx.seq_start[a + 1] - (a + 1);
+        }
+        if (t0 + w < sb || t0 + w + K > se) continue;
+        if constexpr (EP) chain_mark_file<KW, BLK, SIGMA>(st, fr, w, cx.seq_to_file[sq]);
+        else chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, w, 0, 1, false);
+    }
+}
+
 // One state-machine iteration.  Returns false when the block is finished (results via chain_result).
 // `fetches` counts rank-block reads (the roofline's algorithmic unit), when non-null.
 // LOC (locate instantiation, one k-mer per chain, EP tables): every occurrence is reported, not counted.
@@ -771,6 +928,12 @@ GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, Fetch
     const uint32_t K = cx.K, cnt = BLK ? st.cnt : 1u;
     const uint32_t Li = K - cnt + 1; // infix length
     if (fetches) ++fetches->iterations;
+
+    if constexpr (SIGMA == 4 && !LOC) {
+        // the search was entered through the table entry of a key that occurs once: one candidate alignment, finished
+        // by comparing needle and text; the node is done after that
+        if (st.size & kLocated) { verify_located<KW, EP, BLK, SIGMA>(st, fr, cx, fetches); st.size = 0; }
+    }
 
     if (BLK && st.win == kNoWin && st.t == Li) {
         // the whole infix is matched (only reached when cnt > 1): this node is an infix hit; complete it for
@@ -792,12 +955,16 @@ GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, Fetch
 
     if (st.size == 0) {
         // an empty node can only come out of a jump table: nothing to search here
-    } else if (!LOC && st.strand == 0 && st.e == 0 && st.size == 1 && step_exact_ok(ent) && !(SIGMA == 5 && st.has_n)) {
+    } else if (!LOC && st.strand == 0 && st.e == 0 && st.size == 1 && !(SIGMA == 5 && st.has_n)) {
         // Forward strand, no error so far, one occurrence left: it is the query's own position in the
         // indexed text, so the rest of the pattern matches it exactly and no mismatching extension
-        // exists.  The subtree contributes exactly one occurrence per window — no need to walk it.
-        if (in_flank) chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, st.win, 0, 1, true);
-        else for (uint32_t w = 0; w < cnt; ++w) chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, w, 0, 1, true);
+        // exists.  The subtree holds exactly one full-length node, the query itself without any error: one
+        // occurrence per window if the search admits an error-free completion, nothing if a later part of the
+        // scheme demands an error — no need to walk it either way.
+        if (step_exact_ok(ent)) {
+            if (in_flank) chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, st.win, 0, 1, true);
+            else for (uint32_t w = 0; w < cnt; ++w) chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, w, 0, 1, true);
+        }
     } else {
         // ---- expand the node: ranks at both interval ends of the active index -----------------------
         if (fetches) { // a run of one-row expansions starts here unless the parent was one already

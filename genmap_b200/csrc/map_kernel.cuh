@@ -26,7 +26,7 @@ struct MapLaunch {
     uint64_t n_chunks;
     uint64_t n_work;           // total k-mer starts to search (sizing only)
     unsigned long long* work_counter;  // device, zeroed before launch: next chunk id
-    unsigned long long* fetch_counter; // device, 12 words (count_fetches): [0] rank-block fetches, [1] jump-table reads,
+    unsigned long long* fetch_counter; // device, 14 words (count_fetches): [0] rank-block fetches, [1] jump-table reads,
                                        // [2..9] fetches by interval size, [10] thin paths, [11] state-machine iterations
     void* out;                 // device, value_bits/8 bytes per file-local position
     uint32_t value_bits;

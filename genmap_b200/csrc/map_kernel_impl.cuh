@@ -8,6 +8,7 @@ namespace gmb {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kCounterWords = 14; // instrumented instantiation: words of MapLaunch::fetch_counter
 #ifndef GMB_MIN_BLOCKS
 #define GMB_MIN_BLOCKS 4 // resident CTAs per SM the register allocation must allow
 #endif
@@ -145,12 +146,13 @@ __global__ void __launch_bounds__(kThreads, (SIGMA == 5 && BLK) ? GMB_MIN_BLOCKS
     }
     if (COUNT) {
         // fetch_counter: [0] rank-block fetches, [1] jump-table reads, [2..9] fetches by interval size, [10] thin paths,
-        // [11] state-machine iterations
-        unsigned long long v[2 + 10] = {fetches.total, lut_reads, fetches.by_size[0], fetches.by_size[1], fetches.by_size[2],
-                                        fetches.by_size[3], fetches.by_size[4], fetches.by_size[5], fetches.by_size[6],
-                                        fetches.by_size[7], fetches.thin_paths, fetches.iterations};
+        // [11] state-machine iterations, [12] located entries verified, [13] text reads of those
+        unsigned long long v[kCounterWords] = {fetches.total, lut_reads, fetches.by_size[0], fetches.by_size[1], fetches.by_size[2],
+                                               fetches.by_size[3], fetches.by_size[4], fetches.by_size[5], fetches.by_size[6],
+                                               fetches.by_size[7], fetches.thin_paths, fetches.iterations, fetches.located,
+                                               fetches.text_reads};
 #pragma unroll
-        for (int k = 0; k < 12; ++k) {
+        for (int k = 0; k < kCounterWords; ++k) {
             for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
             if (lane == 0 && v[k]) atomicAdd(L.fetch_counter + k, v[k]);
         }

@@ -456,7 +456,7 @@ class HostSim:
             pos_begin=0, pos_end=None, return_fetches=False, jump_depth=-1, exclude_pseudo=False, block_kmers=0):
         stf, tb, tl, cum, iv = _prep(self.limits, seq_to_file, file_no, intervals)
         out = np.zeros(tl, dtype=np.uint16 if value_bits == 16 else np.uint8)
-        f, lr = (ctypes.c_ulonglong * 11)(), ctypes.c_ulonglong(0)
+        f, lr = (ctypes.c_ulonglong * 13)(), ctypes.c_ulonglong(0)
         rc = self.L.hs_map(self.blob, K, E, int(revcompl), value_bits, tb, tl, _ptr(cum), len(cum) - 1, _ptr(iv),
                            0 if iv is None else len(iv), pos_begin, tl if pos_end is None else pos_end, _ptr(out),
                            f, jump_depth, ctypes.byref(lr), _ptr(stf) if exclude_pseudo else None, file_no,
@@ -464,7 +464,7 @@ class HostSim:
         if rc != 0:
             raise RuntimeError("hs_map failed: %d" % rc)
         self.last_lut_reads = lr.value
-        self.last_fetch_stats = list(f)  # total, by interval size [8], thin paths, iterations
+        self.last_fetch_stats = list(f)  # total, by interval size [8], thin paths, iterations, located entries, text reads
         return (out, f[0]) if return_fetches else out
 
     def locate(self, K, E, revcompl=True, seq_to_file=None, file_no=0, intervals=None, pos_begin=0, pos_end=None,

@@ -87,6 +87,30 @@ void build_host_jump_levels(const MapCtx& cx, uint32_t sigma, uint32_t max_depth
         }
     }
 }
+
+// the text pass of jump_table.cu (k_locate_singletons) on the host: keys that occur once become LOCATED entries
+void locate_host_singletons(const MapCtx& cx, uint32_t d, std::vector<JtFull>& full)
+{
+    const uint64_t n_text = cx.n_text;
+    if (n_text < 2ull * kLocateMargin + d + 1) return;
+    auto chars = [&](uint64_t p, uint32_t len) {
+        const uint64_t w = cx.text[p >> 5], w2 = cx.text[(p >> 5) + 1];
+        const uint32_t sh = 2u * (uint32_t)(p & 31u);
+        const uint64_t v = sh ? (w >> sh) | (w2 << (64u - sh)) : w;
+        return (uint32_t)(v & ((1ull << (2u * len)) - 1ull));
+    };
+    for (uint64_t q = kLocateMargin; q + d + kLocateMargin <= n_text; ++q) {
+        JtFull& e = full[chars(q, d)];
+        if (e.size != 1u) continue;
+        uint32_t a = 0, b = cx.n_seq;
+        while (b - a > 1) {
+            const uint32_t mid = (a + b) >> 1;
+            if ((uint64_t)cx.seq_start[mid] - mid <= q) a = mid; else b = mid;
+        }
+        if (q + d > (uint64_t)cx.seq_start[a + 1] - (a + 1)) continue;
+        e = JtFull{(uint32_t)q, kLocated | 1u, chars(q + d, kCtx), chars(q - kCtx, kCtx)};
+    }
+}
 } // namespace
 
 extern "C" {
@@ -151,7 +175,7 @@ int hs_step_tables(uint32_t K, uint32_t E, uint32_t* n_search, uint32_t* steps)
 }
 
 // jump_depth: -1 = default for the index size, 0 = no jump tables, else the maximum depth
-// fetches (optional): 11 words — total, by interval size [8], thin paths, iterations (gmb_core.h: FetchStats)
+// fetches (optional): 13 words — total, by interval size [8], thin paths, iterations, located entries, text reads (gmb_core.h: FetchStats)
 int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bits, uint64_t text_begin,
            uint64_t text_len, const uint64_t* chrom_cum, uint32_t n_chrom, const uint64_t* intervals,
            uint64_t n_intervals, uint64_t pos_begin, uint64_t pos_end, void* out, unsigned long long* fetches,
@@ -179,7 +203,7 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     cx.K = K; cx.B = B; cx.n_search = tabs.n_search; cx.n_strands = revcompl ? 2 : 1;
     cx.maxv = value_bits == 16 ? 65535u : 255u;
     cx.sa = nullptr; cx.seq_start = nullptr; cx.seq_to_file = nullptr; cx.n_seq = h.n_seq; cx.own_file = own_file; cx.all_files = 0;
-    cx.loc_rows = nullptr;
+    cx.loc_rows = nullptr; cx.text = nullptr; cx.n_text = 0; cx.E = E;
     if (ep) {
         if (!h.off_sa) return -3;
         cx.sa = reinterpret_cast<const uint32_t*>(base + h.off_sa);
@@ -200,18 +224,26 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     }
     std::vector<std::vector<JtFull>> full(max_depth + 1);
     build_host_jump_levels(cx, sigma, max_depth, full);
-    std::vector<std::vector<JtEntry>> uni(max_depth + 1);   // what the one-k-mer instantiation reads (B == 1)
+    std::vector<std::vector<JtEntry>> uni(max_depth + 1);   // what the one-k-mer instantiation reads on Dna5 indices
     std::vector<std::vector<uint32_t>> lof(max_depth + 1);
-    if (B == 1)
+    const char* loc_env = std::getenv("GMB_LOCATE");
+    const bool all_full = sigma == 4 && !(loc_env && loc_env[0] == '0'); // as capi.cu: Dna4 searches all read 16-byte entries
+    if (B == 1 && !all_full)
         for (uint32_t d = 1; d <= max_depth; ++d)
             for (const JtFull& q : full[d]) { uni[d].push_back(JtEntry{q.lo_r, q.size}); lof[d].push_back(q.lo_f); }
+    cx.seq_start = reinterpret_cast<const uint32_t*>(base + h.off_seq_start);
+    cx.text = reinterpret_cast<const uint64_t*>(base + h.off_text);
+    cx.n_text = h.n_text;
+    cx.E = E;
+    if (all_full)
+        for (uint32_t d = 1; d <= max_depth; ++d) locate_host_singletons(cx, d, full[d]);
     std::vector<SearchStart> starts((B + 1) * kMaxSearches);
     for (uint32_t cnt = 1; cnt <= B; ++cnt)
         for (uint32_t s = 0; s < kMaxSearches; ++s) {
             const uint32_t d = plans[cnt].depth[s];
             SearchStart& S = starts[cnt * kMaxSearches + s];
             std::memset(&S, 0, sizeof(S));
-            if (B == 1) { S.uni = d ? uni[d].data() : nullptr; S.lof = (d && plans[cnt].need_lof[s]) ? lof[d].data() : nullptr; }
+            if (B == 1 && !all_full) { S.uni = d ? uni[d].data() : nullptr; S.lof = (d && plans[cnt].need_lof[s]) ? lof[d].data() : nullptr; }
             else S.full = d ? full[d].data() : nullptr; // (the device uses 8-byte entries where SA(T) is not needed: same values)
             S.a = plans[cnt].a[s]; S.d = d;
             S.n_var = std::max(1u, plans[cnt].n_var[s]);
@@ -235,7 +267,7 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     else if (needle <= 64) RUN_KW(2);
     else if (needle <= 128) RUN_KW(4);
     else RUN_KW(9);
-    if (fetches) { fetches[0] = f.total; for (int k = 0; k < 8; ++k) fetches[1 + k] = f.by_size[k]; fetches[9] = f.thin_paths; fetches[10] = f.iterations; }
+    if (fetches) { fetches[0] = f.total; for (int k = 0; k < 8; ++k) fetches[1 + k] = f.by_size[k]; fetches[9] = f.thin_paths; fetches[10] = f.iterations; fetches[11] = f.located; fetches[12] = f.text_reads; }
     if (lut_reads_out) *lut_reads_out = lr;
     return 0;
 }
@@ -268,7 +300,7 @@ int hs_locate(const void* blob, uint32_t K, uint32_t E, int revcompl, uint64_t t
     cx.sa = reinterpret_cast<const uint32_t*>(base + h.off_sa);
     cx.seq_start = reinterpret_cast<const uint32_t*>(base + h.off_seq_start);
     cx.seq_to_file = nullptr; cx.n_seq = h.n_seq; cx.own_file = 0; cx.all_files = 0;
-    cx.loc_rows = nullptr;
+    cx.loc_rows = nullptr; cx.text = reinterpret_cast<const uint64_t*>(base + h.off_text); cx.n_text = h.n_text; cx.E = E;
     const uint32_t want_depth = jump_depth < 0 ? default_jump_depth(h.n_bwt) : (uint32_t)jump_depth;
     JumpPlan plan;
     plan_jump_tables(tabs.infix[1], want_depth, plan, E, h.n_bwt, sigma, 1, false);
