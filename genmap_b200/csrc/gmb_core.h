@@ -399,9 +399,7 @@ struct JtFull { uint32_t lo_r, size, lo_f, pad; }; // both intervals in one 16-b
 // the text (verify_located) — from the 2*kCtx context characters when they cover the needle (no memory access at
 // all), else from one read of the packed text — instead of walking the index through one-row intervals, one
 // dependent rank-block fetch per character.  At 3 Gbp 69 % of the existing depth-16 entries are of this kind.
-constexpr uint32_t kLocated = 0x80000000u;
-constexpr uint32_t kCtx = 16;
-constexpr uint32_t kLocateMargin = 512; // keys this close to either end of the text are never located (> kMaxK + 16 + 32 * 9)
+// (kLocated, kCtx, kLocateMargin: gmb_layout.h)
 struct SearchStart {
     const JtEntry* uni;   // [4^d] interval in SA(T') + size            (nullptr: no table, start at the root)
     const uint32_t* lof;  // [4^d] start of the interval in SA(T)       (nullptr when never needed again or `full` is set)
@@ -891,7 +889,8 @@ GMB_HD void verify_located(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, F
     uint32_t e = 0;
     for (uint32_t t = 0; t < Li; ++t) {
         const uint32_t ent = cx.steps[tab + t], x = step_pos(ent);
-        e += (uint32_t)(mm[KW == 1 ? 0 : (x >> 5)] >> (2u * (x & 31u))) & 1u;
+        const uint64_t word = KW == 1 ? mm[0] : (KW == 2 ? (x < 32u ? mm[0] : mm[KW - 1]) : mm[x >> 5]); // selects keep mm in registers
+        e += (uint32_t)(word >> (2u * (x & 31u))) & 1u;
         if (e > step_ub(ent) || e + step_rem(ent) < step_lb(ent)) return;
     }
     // the sequence holding the occurrence (largest s with limits[s] <= q, limits[s] = seq_start[s] - s), looked up

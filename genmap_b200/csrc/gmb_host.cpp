@@ -57,12 +57,16 @@ struct SearchProfile {
     double walk[2][kMaxK + 1];         // expected rank-block fetches of the nodes of depth t, strand 0 / 1
     double nstr[kMaxK + 2];            // strings of length t the scheme admits (error placements x 3^errors)
     double leaf[2];                    // window completions per infix hit
+    double N = 0;                      // text size the profile was made for
+    uint32_t needle = 0;               // characters of the block's needle (K + B - 1)
 };
 
 void profile_search(const uint32_t* ub, const uint32_t* lb, const uint32_t* rem, uint32_t Li, uint32_t E, double N, uint32_t B,
                     uint32_t block_bases, SearchProfile& P)
 {
     P.Li = Li;
+    P.N = N;
+    P.needle = Li + 2 * (B - 1);
     P.run = 0;
     while (P.run < Li && ub[P.run] == 0) ++P.run;
     std::vector<char> exact_ok(Li + 1);
@@ -107,22 +111,43 @@ void profile_search(const uint32_t* ub, const uint32_t* lb, const uint32_t* rem,
 // the key: one table read per string, both strands) instead of walking the dense top of the trie.  Returns the
 // depth that minimises expected table reads + expected fetches below it; *cost = that minimum (both strands).
 constexpr double kMaxVariantStrings = 3000.0;
-uint32_t best_jump_depth(const SearchProfile& P, uint32_t dmax, bool allow_variants, double* cost)
+// located: the tables hold LOCATED entries (gmb_core.h: JtFull) — a key that occurs once ends its search at the table
+// read (verify_located).  Of the occurrences of a random d-mer a fraction e^(-N/4^d) are alone, so what is walked
+// below an entry depth d shrinks by that fraction; a located entry whose context does not cover the needle costs one
+// read of the text instead.
+uint32_t best_jump_depth(const SearchProfile& P, uint32_t dmax, bool allow_variants, double* cost, bool located = false)
 {
     const uint32_t top = std::min(dmax, P.Li > 0 ? P.Li - 1 : 0u);
     const uint32_t first = std::min(P.run, top);
     std::vector<double> below(P.Li + 1, 0.0); // expected fetches of all depths >= t, both strands
     for (uint32_t t = P.Li; t-- > 0;) below[t] = below[t + 1] + P.walk[0][t] + P.walk[1][t];
+    auto entered_at = [&](uint32_t d, double strings) { // expected accesses of entering at depth d through `strings` keys per strand
+        if (d == 0) return below[0] + P.leaf[0] + P.leaf[1];
+        double walked = 1.0, text = 0.0;
+        if (located) {
+            const double lam = P.N / std::pow(4.0, (double)d);
+            const double alone = lam > 30 ? 0.0 : std::exp(-lam);
+            walked = 1.0 - alone;
+            if (P.needle > d + 2 * kCtx) text = (2.0 * strings - 1.0) * lam * alone; // (the query's own key needs no comparison)
+        }
+        return 2.0 * strings + text + walked * (below[d] + P.leaf[0] + P.leaf[1]);
+    };
     uint32_t best_d = first;
-    double best = (first > 0 ? 2.0 : 0.0) + below[first];
+    double best = entered_at(first, 1.0);
     if (allow_variants)
         for (uint32_t d = first + 1; d <= top; ++d) {
             if (P.nstr[d] > kMaxVariantStrings) break;
-            const double c = 2.0 * P.nstr[d] + below[d];
+            const double c = entered_at(d, P.nstr[d]);
             if (c < best) { best = c; best_d = d; }
         }
-    if (cost) *cost = best + P.leaf[0] + P.leaf[1];
+    if (cost) *cost = best;
     return best_d;
+}
+
+bool located_enabled(uint64_t n_bwt, uint32_t sigma)
+{
+    const char* env = std::getenv("GMB_LOCATE"); // "0": tables without located entries (every search walks the index)
+    return n_bwt != 0 && sigma == 4 && !(env && env[0] == '0');
 }
 
 bool variants_enabled(uint64_t n_bwt, uint32_t sigma)
@@ -132,7 +157,7 @@ bool variants_enabled(uint64_t n_bwt, uint32_t sigma)
 }
 
 double expected_fetches(const SchemeDef& sd, const uint32_t* len, uint32_t E, double N, uint32_t B, uint32_t jump_max, uint32_t block_bases,
-                        bool allow_variants)
+                        bool allow_variants, bool located)
 {
     const uint32_t nb = sd.n_blocks;
     uint32_t Li = 0;
@@ -148,7 +173,7 @@ double expected_fetches(const SchemeDef& sd, const uint32_t* len, uint32_t E, do
         }
         profile_search(ub.data(), lb.data(), rem.data(), Li, E, N, B, block_bases, P);
         double c = 0;
-        best_jump_depth(P, jump_max, allow_variants, &c);
+        best_jump_depth(P, jump_max, allow_variants, &c, located);
         total += c;
     }
     return total / B;
@@ -158,10 +183,11 @@ double expected_fetches(const SchemeDef& sd, const uint32_t* len, uint32_t E, do
 void choose_part_lengths(const SchemeDef& sd, uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t B, uint32_t block_bases, uint32_t* len)
 {
     const bool av = B > 1 && variants_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u); // (the one-k-mer kernel has none)
+    const bool loc = located_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u);
     const uint32_t nb = sd.n_blocks;
     if (nb < 2 || n_bwt == 0 || K < 2 * nb) return;
     const uint32_t jump_max = default_jump_depth(n_bwt);
-    double best = expected_fetches(sd, len, E, (double)n_bwt, B, jump_max, block_bases, av);
+    double best = expected_fetches(sd, len, E, (double)n_bwt, B, jump_max, block_bases, av, loc);
     for (int round = 0; round < 256; ++round) {
         int bi = -1, bj = -1;
         double bc = best * (1.0 - 1e-6);
@@ -169,7 +195,7 @@ void choose_part_lengths(const SchemeDef& sd, uint32_t K, uint32_t E, uint64_t n
             for (uint32_t j = 0; j < nb; ++j) {
                 if (i == j || len[i] <= 1) continue;
                 --len[i]; ++len[j];
-                const double c = expected_fetches(sd, len, E, (double)n_bwt, B, jump_max, block_bases, av);
+                const double c = expected_fetches(sd, len, E, (double)n_bwt, B, jump_max, block_bases, av, loc);
                 ++len[i]; --len[j];
                 if (c < bc) { bc = c; bi = (int)i; bj = (int)j; }
             }
@@ -282,7 +308,8 @@ uint32_t model_block_kmers(uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t bloc
         for (uint32_t b = 0; b < sd.n_blocks; ++b) len[b] = Li / sd.n_blocks + (b < Li % sd.n_blocks);
         choose_part_lengths(sd, Li, E, n_bwt, B, block_bases, len);
         cost[B] = expected_fetches(sd, len, E, (double)n_bwt, B, default_jump_depth(n_bwt), block_bases,
-                                   B > 1 && variants_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u));
+                                   B > 1 && variants_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u),
+                                   located_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u));
         // a Dna5 needle longer than 32 characters no longer fits one register word per plane: measured 1.55x slower per
         // fetch (profiles/r01/s25_sweep_dna5.txt vs s20_sweep_dna5.txt)
         if (block_bases == kBlockBases5 && K + B - 1 > 32 && K <= 32) cost[B] *= 1.5;
@@ -310,7 +337,9 @@ bool build_block_tables(uint32_t K, uint32_t E, uint32_t B, bool force_sync, Blo
     const char* e2 = std::getenv("GMB_PART_WEIGHTS");
     char buf[160];
     std::snprintf(buf, sizeof buf, "%u/%u/%u/%d/%llu/%u/", K, E, B, force_sync ? 1 : 0, (unsigned long long)n_bwt, block_bases);
-    const std::string key = std::string(buf) + (e1 ? e1 : "") + "/" + (e2 ? e2 : "");
+    const char* e3 = std::getenv("GMB_JUMP_VARIANTS");
+    const char* e4 = std::getenv("GMB_LOCATE");
+    const std::string key = std::string(buf) + (e1 ? e1 : "") + "/" + (e2 ? e2 : "") + "/" + (e3 ? e3 : "") + "/" + (e4 ? e4 : "");
     {
         std::lock_guard<std::mutex> lock(mu);
         for (const Entry& en : cache)
@@ -394,7 +423,7 @@ void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan
         for (uint32_t t = 0; t < K; ++t) { ub[t] = step_ub(st[t]); lb[t] = step_lb(st[t]); rem[t] = step_rem(st[t]); }
         profile_search(ub.data(), lb.data(), rem.data(), K, E, n_bwt ? (double)n_bwt : 1.0, block_kmers ? block_kmers : 1,
                        block_bases(sigma), P);
-        const uint32_t d = best_jump_depth(P, max_depth, allow, nullptr);
+        const uint32_t d = best_jump_depth(P, max_depth, allow, nullptr, located_enabled(n_bwt, sigma));
         plan.depth[s] = d;
         plan.var_off[s] = (uint32_t)plan.variants.size();
         if (d == 0) { plan.n_var[s] = 1; plan.variants.push_back(0xffffffffu); continue; }

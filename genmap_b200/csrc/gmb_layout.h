@@ -38,6 +38,9 @@ constexpr uint32_t kMaxK = 255;              // step tables keep pattern offsets
 constexpr uint32_t kMaxE = 4;                // src/mappability.hpp:187
 constexpr uint32_t kMaxSearches = 7;         // src/find2_index_approx.hpp:121-131
 constexpr uint32_t kMaxBlockKmers = 16;      // adjacent k-mers searched together through their common infix
+constexpr uint32_t kLocated = 0x80000000u;   // size flag of a LOCATED jump-table entry (gmb_core.h: JtFull)
+constexpr uint32_t kCtx = 16;                // context characters a located entry carries on either side of its key
+constexpr uint32_t kLocateMargin = 512;      // keys this close to either end of the text are never located (> kMaxK + 16 + 32 * 9)
 constexpr uint32_t kDeadVariant = 0xfffffffeu; // jump-table entry set of a search that admits no string of the key's length
 
 struct alignas(kBlockBytes) RankBlock {

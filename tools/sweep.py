@@ -18,6 +18,7 @@ ap.add_argument("--nchr", type=int, default=24)
 ap.add_argument("--seed", type=int, default=45)
 ap.add_argument("--configs", default="0:-1:256,0:0:256,0:13:256,0:14:256,0:16:256,1:-1:64,1:0:64,2:-1:8,2:0:8")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--kmer", type=int, default=30)
 ap.add_argument("--n-frac", type=float, default=0.0, help="fraction of every chromosome turned into runs of N (-> Dna5 index)")
 args = ap.parse_args()
 
@@ -44,7 +45,7 @@ for cfg in args.configs.split(","):
     blk = int(parts[3]) if len(parts) > 3 else 0
     batch = min(batch, n // 2)
     ix.set_jump_depth(depth)
-    p = gm.SearchParams(30, E, block_kmers=blk)
+    p = gm.SearchParams(args.kmer, E, block_kmers=blk)
     t1 = time.time()
     st = ix.compute_mappability_device(p, out.data_ptr(), pos_begin=0, pos_end=1 << 16, stream=stream)  # builds tables
     setup = time.time() - t1
@@ -60,6 +61,7 @@ for cfg in args.configs.split(","):
              st.jump_table_reads / st.positions, st.rank_block_fetches * ix.info.rank_block_bytes / st.positions * npos / np.median(ms) / 1e6,
              setup, torch.cuda.mem_get_info()[0] / 1e9), flush=True)
     tot = max(1, st.rank_block_fetches)
-    print("    fetches by interval size 1|2|3-4|5-8|9-16|17-32|33-64|65+ : %s   thin paths/pos=%.2f (%.1f fetches each)  iterations/pos=%.1f"
+    print("    fetches by interval size 1|2|3-4|5-8|9-16|17-32|33-64|65+ : %s   thin paths/pos=%.2f (%.1f fetches each)  iterations/pos=%.1f  located/pos=%.2f text reads/pos=%.3f"
           % (" ".join("%.1f%%" % (100.0 * x / tot) for x in st.fetches_by_size), st.thin_paths / st.positions,
-             st.fetches_by_size[0] / max(1, st.thin_paths), st.iterations / st.positions), flush=True)
+             st.fetches_by_size[0] / max(1, st.thin_paths), st.iterations / st.positions, st.located_entries / st.positions,
+             st.text_reads / st.positions), flush=True)
