@@ -125,14 +125,40 @@ bool read_fasta(const std::string& path, std::vector<uint8_t>& codes, std::vecto
     std::string line, cur_id;
     bool have = false;
     uint64_t cur_len = 0;
-    const bool fastq = false;
-    (void)fastq;
     auto flush = [&]() {
         if (have && cur_len > 0) { ids.push_back(cur_id); lens.push_back(cur_len); limits.push_back(codes.size()); }
         else if (have) { /* empty record: nothing was appended */ }
         cur_len = 0;
     };
-    while (std::getline(in, line)) {
+    // FASTQ (the reference's SeqFileIn detects the format from the first character; -FD accepts *.fastq): '@id',
+    // sequence lines up to the '+' line, then as many quality characters as the record has bases (ignored)
+    const int first = in.peek();
+    if (first == '@') {
+        while (std::getline(in, line)) {
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            if (line.empty()) continue;
+            if (line[0] != '@') return false; // malformed record
+            have = true;
+            cur_id = line.substr(1);
+            while (std::getline(in, line)) {
+                if (!line.empty() && line.back() == '\r') line.pop_back();
+                if (!line.empty() && line[0] == '+') break;
+                for (unsigned char ch : line) {
+                    if (ch == ' ' || ch == '\t') continue;
+                    codes.push_back((uint8_t)code_of(ch));
+                    ++cur_len;
+                }
+            }
+            uint64_t quals = 0;
+            while (quals < cur_len && std::getline(in, line)) {
+                if (!line.empty() && line.back() == '\r') line.pop_back();
+                quals += line.size();
+            }
+            flush();
+        }
+        have = false;
+    }
+    while (first != '@' && std::getline(in, line)) {
         if (!line.empty() && line.back() == '\r') line.pop_back();
         if (!line.empty() && line[0] == '>') {
             flush();

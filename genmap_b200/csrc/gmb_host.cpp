@@ -771,9 +771,19 @@ bool validate_header(const IndexHeader& h, uint64_t bytes, std::string& err)
     if (h.total_bytes > bytes) { err = "index blob truncated"; return false; }
     if (h.n_bwt != h.n_text + h.n_seq || h.n_blocks != h.n_bwt / block_bases(h.sigma) + 1) { err = "index header inconsistent"; return false; }
     if (h.sigma == 5 && !h.off_nmask) { err = "Dna5 index without N mask"; return false; }
-    const uint64_t offs[] = {h.off_fwd, h.off_rev, h.off_sent_fwd, h.off_sent_rev, h.off_text, h.off_limits, h.off_seq_start, h.off_sa, h.off_nmask};
-    for (uint64_t o : offs)
-        if (o >= h.total_bytes || (o % 256) != 0) { err = "index header offsets out of range"; return false; }
+    if (h.n_seq == 0 || h.n_seq > kMaxSeq || h.n_bwt >= 0xffffffffull) { err = "index header inconsistent (sizes)"; return false; }
+    // every section where the layout puts it for these sizes (so every section fits and none overlaps), and the
+    // cumulative counts consistent with the text size: a truncated or corrupt blob must not reach the kernels
+    const IndexHeader want = plan_blob(h.n_text, h.n_seq, h.off_sa != 0, h.sigma).h;
+    if (h.off_fwd != want.off_fwd || h.off_rev != want.off_rev || h.off_sent_fwd != want.off_sent_fwd || h.off_sent_rev != want.off_sent_rev ||
+        h.off_text != want.off_text || h.off_limits != want.off_limits || h.off_seq_start != want.off_seq_start || h.off_sa != want.off_sa ||
+        h.off_nmask != want.off_nmask || h.total_bytes != want.total_bytes) {
+        err = "index header offsets do not match the layout of an index of this size";
+        return false;
+    }
+    bool counts_ok = h.C[0] == h.n_seq && h.C[h.sigma] == h.n_bwt; // C[c] = symbols smaller than base c, sentinels first
+    for (uint32_t c = 0; c < h.sigma; ++c) counts_ok = counts_ok && h.C[c] <= h.C[c + 1];
+    if (!counts_ok) { err = "index header inconsistent (cumulative counts)"; return false; }
     return true;
 }
 

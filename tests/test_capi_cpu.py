@@ -82,3 +82,32 @@ def test_synth_generator_is_the_frozen_one():
     a = genmap_b200.synth_genome(100000, 2, 42)
     b = T.synth(100000, 2, 42)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_corrupt_or_truncated_blobs_are_rejected_before_they_reach_a_kernel(lib):
+    """section offsets, total size and cumulative counts are checked against the layout of an index of
+    the header's own sizes (validate_header), not just for being inside the blob."""
+    blob = genmap_b200.Index.build_blob(T.repeat_rich(5, 3, 2500), with_sa=True)
+    words = blob.view(np.uint64)
+
+    def rejected(b):
+        with pytest.raises(genmap_b200.GenmapError) as e:
+            genmap_b200.Index.from_blob(b)
+        return e.value.code == _lib.GMB_ERR_IO
+
+    assert rejected(blob[:len(blob) - 256].copy())                     # truncated
+    hdr_words = 256 // 8
+    hit = 0
+    for i in range(hdr_words):                                          # any changed size, count or offset
+        if words[i] == 0:
+            continue
+        bad = blob.copy()
+        bad.view(np.uint64)[i] += 256
+        with pytest.raises(genmap_b200.GenmapError) as e:
+            genmap_b200.Index.from_blob(bad)
+        hit += e.value.code == _lib.GMB_ERR_IO
+    assert hit >= 15
+    if lib.gmb_device_count() == 0:                                     # the intact blob gets as far as "no device" here
+        with pytest.raises(genmap_b200.GenmapError) as e:
+            genmap_b200.Index.from_blob(blob)
+        assert e.value.code == _lib.GMB_ERR_CUDA
