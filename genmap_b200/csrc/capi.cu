@@ -117,6 +117,8 @@ struct MapPlan {
     size_t start_off = 0;
     uint64_t jt_epoch = ~0ull;    // ix->jt_epoch the SearchStart entries were written for
     uint64_t last_use = 0;
+    const JtFull* e0_table = nullptr; // E = 0, one k-mer per chain, 16-byte entries: table and depth of its only search
+    uint32_t e0_depth = 0;
     ~MapPlan() { if (d_tables) cudaFree(d_tables); }
 };
 
@@ -699,6 +701,13 @@ static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool l
     CU(cudaStreamSynchronize(stream)); // pageable sources: staged before the vectors go out of scope
     plan->start_off = start_off;
     plan->plan_depth = plan_depth;
+    plan->e0_table = nullptr;
+    plan->e0_depth = 0;
+    {
+        const char* env = std::getenv("GMB_EXACT_KERNEL"); // "0": E = 0 through the general kernel (A/B measurements)
+        const SearchStart& S0 = starts[kMaxSearches];
+        if (p->E == 0 && tabs.B == 1 && !loc && S0.full && !(env && env[0] == '0')) { plan->e0_table = S0.full; plan->e0_depth = S0.d; }
+    }
     plan->jt_epoch = ix->jt_epoch;
     return GMB_OK;
 }
@@ -815,6 +824,8 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
         L.cx.all_files = n_files == 64 ? ~0ull : ((1ull << n_files) - 1ull);
     }
 
+    L.e0_table = plan->e0_table;
+    L.e0_depth = plan->e0_depth;
     L.cx.loc_rows = loc ? loc->rows : nullptr;
     L.loc_off = loc ? loc->off : nullptr;
     L.loc_pos0 = loc ? loc->pos0 : 0;

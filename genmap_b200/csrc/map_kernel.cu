@@ -58,6 +58,7 @@ size_t map_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool
 cudaError_t launch_map_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
     if (L.n_work == 0) return cudaSuccess;
+    if (exact_kernel_applies(L)) return launch_exact_kernel(L, sm_count, stream);
     const uint32_t needle = L.cx.K + L.cx.B - 1; // characters a chain keeps in registers
     if (needle <= 32) return launch_kw<1>(L, sm_count, stream);
     if (needle <= 64) return launch_kw<2>(L, sm_count, stream);

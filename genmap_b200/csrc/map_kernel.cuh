@@ -36,6 +36,10 @@ struct MapLaunch {
     // [loc_pos0, ...) in the counting pass; the fill pass (cx.loc_rows != nullptr) reads the list starts from loc_off
     const uint64_t* loc_off;
     uint64_t loc_pos0;
+    // E = 0 on a Dna4 index entered through 16-byte table entries: the straight-line kernel of exact_kernel.cu
+    // (nullptr: not applicable / switched off, the general kernel runs)
+    const JtFull* e0_table;
+    uint32_t e0_depth;
 };
 
 constexpr unsigned kChunk = 128; // positions handed out per global atomic (rounded down to a multiple of B)
@@ -46,6 +50,10 @@ size_t map_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool
 
 // Enqueue the kernel on `stream`.  Returns cudaSuccess or the launch error.
 cudaError_t launch_map_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream);
+
+// E = 0 (exact_kernel.cu): does the launch qualify, and the launcher launch_map_kernel forwards to when it does
+bool exact_kernel_applies(const MapLaunch& L);
+cudaError_t launch_exact_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream);
 
 // Locate variant (locate_kernel.cu): one k-mer per chain, every occurrence reported (csv output).
 cudaError_t launch_locate_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream);
