@@ -822,24 +822,17 @@ GMB_HD void chain_mark_file(Chain<KW, SIGMA>& st, Frames& fr, uint32_t w, uint32
 //      as chain_step: an alignment is found by exactly one search of the scheme);
 //   4. every window whose K characters hold at most E mismatches and lie inside one sequence counts one occurrence
 //      (the index walk cannot leave a sequence: sentinels; here the sequence limits are checked).
+// `key`: the table key the entry was read with (the needle's window with this entry's substitutions); own_key: it is
+// the needle's own window, nothing substituted; q / ctx_r / ctx_l: the entry.  st.s, st.strand, st.cnt, st.pat are read.
 template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
-GMB_HD void verify_located(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, FetchStats* fetches)
+GMB_HD void verify_located_key(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, FetchStats* fetches, const SearchStart& S,
+                               uint32_t key, bool own_key, uint32_t q, uint32_t ctx_r, uint32_t ctx_l)
 {
     const uint32_t K = cx.K, cnt = BLK ? st.cnt : 1u;
     const uint32_t Li = K - cnt + 1, NL = K + cnt - 1, E = cx.E;
-    const SearchStart& S = cx.starts[cnt * kMaxSearches + st.s];
-    const uint32_t q = st.lo_r, ctx_r = st.lo_f, ctx_l = st.ctx_l;
     const uint32_t tab = (BLK ? cx.p1_off[cnt] : 0u) + st.s * Li;
     if (fetches) ++fetches->located;
-    uint32_t set = 0xffffffffu;
-    if constexpr (BLK) {
-#if defined(__CUDA_ARCH__)
-        set = st.var == 0 ? S.set0 : __ldg(S.var + st.var);
-#else
-        set = st.var == 0 ? S.set0 : S.var[st.var];
-#endif
-    }
-    if (st.strand == 0 && set == 0xffffffffu) {
+    if (st.strand == 0 && own_key) {
         // the query's own window is an occurrence of its own key, and the key occurs once: this is the query itself
         if (step_exact_ok(cx.steps[tab]))
             for (uint32_t w = 0; w < cnt; ++w) chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, w, 0, 1, true);
@@ -851,17 +844,6 @@ GMB_HD void verify_located(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, F
     if constexpr (KW <= 2) covered = S.a <= kCtx && NL - S.a - S.d <= kCtx;
     if (covered) {
         // text[q - kCtx, q + d + kCtx) as one bit string T (character c in bits 2c), shifted so that character 0 is the needle's
-        uint32_t key = st.pat.bits(S.a, S.d);
-        if constexpr (BLK) {
-            if (set != 0xffffffffu) {
-                uint32_t sub = st.sub;
-#pragma unroll
-                for (uint32_t k = 0; k < kMaxE; ++k) {
-                    const uint32_t p = (set >> (8 * k)) & 0xffu;
-                    if (p != 0xffu) { key ^= (1u + sub % 3u) << (2u * p); sub /= 3u; }
-                }
-            }
-        }
         const uint32_t sh = 32u + 2u * S.d; // 34..64
         const uint64_t t_lo = (uint64_t)ctx_l | ((uint64_t)key << 32) | (sh < 64u ? (uint64_t)ctx_r << sh : 0ull);
         const uint64_t t_hi = (uint64_t)ctx_r >> (64u - sh);
@@ -915,10 +897,37 @@ GMB_HD void verify_located(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, F
     }
 }
 
+// the same for the search the chain is in (general kernel: the entry sits in st.lo_r / lo_f / ctx_l)
+template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
+GMB_HD void verify_located(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, FetchStats* fetches)
+{
+    const uint32_t cnt = BLK ? st.cnt : 1u;
+    const SearchStart& S = cx.starts[cnt * kMaxSearches + st.s];
+    uint32_t set = 0xffffffffu, key = st.pat.bits(S.a, S.d);
+    if constexpr (BLK) {
+#if defined(__CUDA_ARCH__)
+        set = st.var == 0 ? S.set0 : __ldg(S.var + st.var);
+#else
+        set = st.var == 0 ? S.set0 : S.var[st.var];
+#endif
+        if (set != 0xffffffffu) {
+            uint32_t sub = st.sub;
+#pragma unroll
+            for (uint32_t k = 0; k < kMaxE; ++k) {
+                const uint32_t p = (set >> (8 * k)) & 0xffu;
+                if (p != 0xffu) { key ^= (1u + sub % 3u) << (2u * p); sub /= 3u; }
+            }
+        }
+    }
+    verify_located_key<KW, EP, BLK, SIGMA>(st, fr, cx, fetches, S, key, set == 0xffffffffu, st.lo_r, st.lo_f, st.ctx_l);
+}
+
 // One state-machine iteration.  Returns false when the block is finished (results via chain_result).
 // `fetches` counts rank-block reads (the roofline's algorithmic unit), when non-null.
 // LOC (locate instantiation, one k-mer per chain, EP tables): every occurrence is reported, not counted.
-template <int KW, bool EP, bool BLK, int SIGMA, class Frames, bool LOC = false>
+// SUB (block_kernel.cu): the chain walks the subtree below ONE table entry; when that is exhausted the call returns
+// false instead of moving on to the search's next key (the caller enumerates the keys itself).
+template <int KW, bool EP, bool BLK, int SIGMA, class Frames, bool LOC = false, bool SUB = false>
 GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, FetchStats* fetches,
                        unsigned long long* lut_reads)
 {
@@ -1066,6 +1075,7 @@ GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, Fetch
             }
         }
         if (cand == 0) {
+            if constexpr (SUB) return false; // the subtree below this table entry is done
             // this entry into the search is exhausted: its next key, the next set of substituted offsets, ...
             if constexpr (BLK) {
                 if (++st.sub < st.nsub) { chain_start<KW, BLK, SIGMA>(st, cx, lut_reads); return true; }
