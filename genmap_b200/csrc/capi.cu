@@ -119,6 +119,8 @@ struct MapPlan {
     uint64_t last_use = 0;
     const JtFull* e0_table = nullptr; // E = 0, one k-mer per chain, 16-byte entries: table and depth of its only search
     uint32_t e0_depth = 0;
+    const uint2* d_keys = nullptr;    // E >= 1, block_kernel.cu: flat key lists by block size (inside d_tables)
+    uint32_t key_off[kMaxBlockKmers + 1] = {}, key_n[kMaxBlockKmers + 1] = {};
     ~MapPlan() { if (d_tables) cudaFree(d_tables); }
 };
 
@@ -681,10 +683,22 @@ static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool l
         variants.insert(variants.end(), plans[cnt].variants.begin(), plans[cnt].variants.end());
         if (plans[cnt].variants.empty()) variants.push_back(0xffffffffu);
     }
+    // block_kernel.cu: every key of every search of one strand as a flat list (the 3^m substitutions of a set of m offsets
+    // spelled out as XOR masks on the key window), when every search of every block size enters through 16-byte entries
+    KeyLists keylist;
+    bool block_ok = p->E >= 1 && !loc && all_full && p->K + tabs.B - 1 <= 64;
+    {
+        const char* env = std::getenv("GMB_BLOCK_KERNEL"); // "0": E >= 1 through the general kernel (A/B measurements)
+        if (env && env[0] == '0') block_ok = false;
+    }
+    if (block_ok) block_ok = build_key_lists(tabs, plans, keylist);
+    for (uint32_t cnt = 0; cnt <= kMaxBlockKmers; ++cnt) { plan->key_off[cnt] = block_ok ? keylist.off[cnt] : 0; plan->key_n[cnt] = block_ok ? keylist.n[cnt] : 0; }
+    if (!block_ok) keylist.xy.clear();
     const size_t step_bytes = tabs.steps.size() * sizeof(uint32_t);
     const size_t start_off = (step_bytes + 15) / 16 * 16;
     const size_t var_off = start_off + starts.size() * sizeof(SearchStart);
-    const size_t total = var_off + variants.size() * sizeof(uint32_t);
+    const size_t key_off_b = (var_off + variants.size() * sizeof(uint32_t) + 15) / 16 * 16;
+    const size_t total = key_off_b + keylist.xy.size() * sizeof(uint32_t);
     CU(cudaStreamSynchronize(stream)); // nothing in flight reads the old tables while they are replaced
     if (plan->d_tables) { cudaFree(plan->d_tables); plan->d_tables = nullptr; }
     CU(cudaMalloc(&plan->d_tables, total));
@@ -698,6 +712,8 @@ static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool l
     CU(cudaMemcpyAsync(dt, tabs.steps.data(), step_bytes, cudaMemcpyHostToDevice, stream));
     CU(cudaMemcpyAsync(dt + start_off, starts.data(), starts.size() * sizeof(SearchStart), cudaMemcpyHostToDevice, stream));
     CU(cudaMemcpyAsync(dt + var_off, variants.data(), variants.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    if (!keylist.xy.empty()) CU(cudaMemcpyAsync(dt + key_off_b, keylist.xy.data(), keylist.xy.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    plan->d_keys = keylist.xy.empty() ? nullptr : reinterpret_cast<const uint2*>(dt + key_off_b);
     CU(cudaStreamSynchronize(stream)); // pageable sources: staged before the vectors go out of scope
     plan->start_off = start_off;
     plan->plan_depth = plan_depth;
@@ -758,7 +774,9 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
     build_work_ranges(text_len, p->K, chrom_cum, n_chrom, reinterpret_cast<const uint64_t*>(intervals), n_intervals,
                       pos_begin, pos_end, ranges);
     const uint32_t nr = (uint32_t)ranges.size();
-    const uint64_t chunk = std::max<uint64_t>(tabs.B, kChunk / tabs.B * tabs.B); // whole blocks per work chunk
+    // whole blocks per work chunk; the two-phase kernel hands a warp one block per lane
+    const bool block_kernel = plan->d_keys != nullptr &&                               block_kernel_smem_bytes((uint32_t)tabs.steps.size(), p->E, tabs.B, p->exclude_pseudo != 0) <= (200u << 10);
+    const uint64_t chunk = block_kernel ? 32ull * tabs.B : std::max<uint64_t>(tabs.B, kChunk / tabs.B * tabs.B);
     std::vector<uint64_t> host_ranges(3 * (size_t)nr + 1); // begin[nr], end[nr], chunk_prefix[nr+1]
     uint64_t total = 0, chunks = 0;
     for (uint32_t i = 0; i < nr; ++i) {
@@ -826,6 +844,8 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
 
     L.e0_table = plan->e0_table;
     L.e0_depth = plan->e0_depth;
+    L.keylist = block_kernel ? plan->d_keys : nullptr;
+    for (uint32_t c2 = 0; c2 <= kMaxBlockKmers; ++c2) { L.key_off[c2] = plan->key_off[c2]; L.key_n[c2] = plan->key_n[c2]; }
     L.cx.loc_rows = loc ? loc->rows : nullptr;
     L.loc_off = loc ? loc->off : nullptr;
     L.loc_pos0 = loc ? loc->pos0 : 0;

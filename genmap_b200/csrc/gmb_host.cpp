@@ -445,6 +445,35 @@ void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan
 
 bool jump_variants_enabled(uint64_t n_bwt, uint32_t sigma) { return variants_enabled(n_bwt, sigma); }
 
+bool build_key_lists(const BlockTables& tabs, const std::vector<JumpPlan>& plans, KeyLists& out)
+{
+    out.xy.clear();
+    for (uint32_t cnt = 1; cnt <= tabs.B; ++cnt) {
+        out.off[cnt] = (uint32_t)(out.xy.size() / 2);
+        for (uint32_t s = 0; s < tabs.n_search; ++s) {
+            if (plans[cnt].depth[s] == 0) { out.xy.clear(); return false; } // a search that starts at the root
+            for (uint32_t v = 0; v < std::max(1u, plans[cnt].n_var[s]); ++v) {
+                const uint32_t set = plans[cnt].variants.empty() ? 0xffffffffu : plans[cnt].variants[plans[cnt].var_off[s] + v];
+                if (set == kDeadVariant) continue;
+                uint32_t m = 0, n3 = 1;
+                for (uint32_t k = 0; k < kMaxE; ++k)
+                    if (((set >> (8 * k)) & 0xffu) != 0xffu) { ++m; n3 *= 3; }
+                for (uint32_t sub = 0; sub < n3; ++sub) {
+                    uint32_t xr = 0, q = sub;
+                    for (uint32_t k = 0; k < kMaxE; ++k) {
+                        const uint32_t off = (set >> (8 * k)) & 0xffu;
+                        if (off != 0xffu) { xr ^= (1u + q % 3u) << (2u * off); q /= 3u; }
+                    }
+                    out.xy.push_back(xr);
+                    out.xy.push_back(s | (m << 4) | ((set == 0xffffffffu ? 1u : 0u) << 8));
+                }
+            }
+        }
+        out.n[cnt] = (uint32_t)(out.xy.size() / 2) - out.off[cnt];
+    }
+    return true;
+}
+
 uint32_t default_jump_depth(uint64_t n_bwt)
 {
     uint32_t d = 1; // ceil(log4(n_bwt)): the first depth at which a random d-mer is expected less than once

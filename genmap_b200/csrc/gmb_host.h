@@ -59,6 +59,16 @@ void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan
 // ceil(log4(n_bwt)) clamped to [1,16]: less than one expected occurrence per table entry
 uint32_t default_jump_depth(uint64_t n_bwt);
 
+// The table keys of one strand of a block as a flat list, per block size cnt = 1..B (block_kernel.cu): every search,
+// every admissible set of substituted offsets, the 3^m substitutions of a set of m offsets spelled out as an XOR mask
+// on the key window.  x = XOR mask, y = search | errors << 4 | (nothing substituted) << 8.  Returns false (and an empty
+// list) when some search starts at the root instead of a table.
+struct KeyLists {
+    std::vector<uint32_t> xy; // pairs (x, y)
+    uint32_t off[kMaxBlockKmers + 1] = {}, n[kMaxBlockKmers + 1] = {};
+};
+bool build_key_lists(const BlockTables& tabs, const std::vector<JumpPlan>& plans, KeyLists& out);
+
 // 256-byte aligned growable byte buffer for the index blob
 struct Blob {
     std::vector<uint64_t> storage;

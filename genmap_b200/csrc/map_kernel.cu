@@ -59,6 +59,7 @@ cudaError_t launch_map_kernel(const MapLaunch& L, int sm_count, cudaStream_t str
 {
     if (L.n_work == 0) return cudaSuccess;
     if (exact_kernel_applies(L)) return launch_exact_kernel(L, sm_count, stream);
+    if (block_kernel_applies(L)) return launch_block_kernel(L, sm_count, stream);
     const uint32_t needle = L.cx.K + L.cx.B - 1; // characters a chain keeps in registers
     if (needle <= 32) return launch_kw<1>(L, sm_count, stream);
     if (needle <= 64) return launch_kw<2>(L, sm_count, stream);

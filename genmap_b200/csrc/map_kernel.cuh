@@ -40,6 +40,12 @@ struct MapLaunch {
     // (nullptr: not applicable / switched off, the general kernel runs)
     const JtFull* e0_table;
     uint32_t e0_depth;
+    // E >= 1 on a Dna4 index with every search entered through 16-byte entries: the two-phase kernel of block_kernel.cu.
+    // keylist: for every block size cnt the flat list of table keys of one strand, key_n[cnt] entries from key_off[cnt]:
+    // x = XOR mask of the substituted characters on the key window, y = search | errors << 4 | (nothing substituted) << 8
+    // (nullptr: not applicable / switched off).  `chunk` is then 32 * B: one block per lane.
+    const uint2* keylist;
+    uint32_t key_off[kMaxBlockKmers + 1], key_n[kMaxBlockKmers + 1];
 };
 
 constexpr unsigned kChunk = 128; // positions handed out per global atomic (rounded down to a multiple of B)
@@ -54,6 +60,11 @@ cudaError_t launch_map_kernel(const MapLaunch& L, int sm_count, cudaStream_t str
 // E = 0 (exact_kernel.cu): does the launch qualify, and the launcher launch_map_kernel forwards to when it does
 bool exact_kernel_applies(const MapLaunch& L);
 cudaError_t launch_exact_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream);
+
+// E >= 1 (block_kernel.cu): the same
+bool block_kernel_applies(const MapLaunch& L);
+size_t block_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool ep);
+cudaError_t launch_block_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream);
 
 // Locate variant (locate_kernel.cu): one k-mer per chain, every occurrence reported (csv output).
 cudaError_t launch_locate_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream);

@@ -44,6 +44,49 @@ void run_ranges(const MapCtx& cx, const uint64_t* text, const uint64_t* nmask, u
             }
         }
 }
+// The driver of block_kernel.cu on the host, one block at a time: per strand the keys of the flat list, empty
+// entries skipped, located ones verified, the others walked in subtree mode (chain_step<..., SUB>).
+template <int KW, bool EP>
+void run_ranges_blockdriver(const MapCtx& cx, const KeyLists& kl, const uint64_t* text, uint64_t text_begin,
+                            const std::vector<WorkRange>& ranges, int value_bits, void* out, FetchStats* fetches,
+                            unsigned long long* lut_reads)
+{
+    for (const WorkRange& r : ranges)
+        for (uint64_t j0 = r.begin; j0 < r.end; j0 += cx.B) {
+            Chain<KW, 4> st;
+            HostFrames fr;
+            st.has_n = false; st.acc = 0; st.files = 0; st.var = 0; st.sub = 0; st.nsub = 1;
+            const uint32_t cnt = (uint32_t)std::min<uint64_t>(cx.B, r.end - j0), NL = cx.K + cnt - 1;
+            st.cnt = cnt;
+            load_pattern(st.pat, text, nullptr, text_begin + j0, NL);
+            for (uint32_t w = 0; w < cnt * (EP ? 3u : 1u); ++w) fr.xset(kLeafWords + w, 0u);
+            for (uint32_t strand = 0; strand < cx.n_strands; ++strand) {
+                st.strand = strand;
+                if (strand == 1) st.pat.reverse_complement(NL);
+                for (uint32_t g = 0; g < kl.n[cnt]; ++g) {
+                    const uint32_t x = kl.xy[2 * (kl.off[cnt] + g)], y = kl.xy[2 * (kl.off[cnt] + g) + 1];
+                    st.s = y & 7u;
+                    const SearchStart& S = cx.starts[cnt * kMaxSearches + st.s];
+                    const uint32_t key = st.pat.bits(S.a, S.d) ^ x;
+                    uint32_t pad;
+                    jump_lookup(S, key, st.lo_f, st.lo_r, st.size, pad);
+                    if (lut_reads) ++*lut_reads;
+                    if (st.size == 0) continue;
+                    if (st.size & kLocated) {
+                        verify_located_key<KW, EP, true, 4>(st, fr, cx, fetches, S, key, (y >> 8) & 1u, st.lo_r, st.lo_f, pad);
+                        continue;
+                    }
+                    st.e = (y >> 4) & 7u; st.t = S.d; st.lvmask = 0; st.win = kNoWin; st.leaf_e = 0; st.thin = false;
+                    while (chain_step<KW, EP, true, 4, HostFrames, false, true>(st, fr, cx, fetches, nullptr)) {}
+                }
+            }
+            for (uint32_t w = 0; w < cnt; ++w) {
+                const uint32_t v = chain_result<KW, EP, true, 4>(st, fr, cx, w);
+                if (value_bits == 16) static_cast<uint16_t*>(out)[j0 + w] = (uint16_t)v;
+                else static_cast<uint8_t*>(out)[j0 + w] = (uint8_t)v;
+            }
+        }
+}
 // the locate instantiation (csv lists): counting pass, prefix sums, filling pass, per-list sort — the
 // same sequence locate_kernel.cu / gmb_map_locations run on the device
 template <int KW, int SIGMA>
@@ -263,7 +306,17 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
 #define RUN_KB(KW, BLK) (sigma == 5 ? RUN_KS(KW, BLK, 5) : RUN_KS(KW, BLK, 4))
 #define RUN_KW(KW) (B > 1 ? RUN_KB(KW, true) : RUN_KB(KW, false))
     const uint32_t needle = K + B - 1; // characters a chain keeps in registers
-    if (needle <= 32) RUN_KW(1);
+    // the two-phase driver of block_kernel.cu, where the library would launch it (capi.cu: get_plan)
+    KeyLists kl;
+    const char* bk_env = std::getenv("GMB_BLOCK_KERNEL");
+    const bool block_driver = E >= 1 && all_full && needle <= 64 && !(bk_env && bk_env[0] == '0') && build_key_lists(tabs, plans, kl);
+    if (block_driver) {
+        if (needle <= 32) { if (ep) run_ranges_blockdriver<1, true>(cx, kl, text, text_begin, ranges, value_bits, out, &f, &lr);
+                            else run_ranges_blockdriver<1, false>(cx, kl, text, text_begin, ranges, value_bits, out, &f, &lr); }
+        else { if (ep) run_ranges_blockdriver<2, true>(cx, kl, text, text_begin, ranges, value_bits, out, &f, &lr);
+               else run_ranges_blockdriver<2, false>(cx, kl, text, text_begin, ranges, value_bits, out, &f, &lr); }
+    }
+    else if (needle <= 32) RUN_KW(1);
     else if (needle <= 64) RUN_KW(2);
     else if (needle <= 128) RUN_KW(4);
     else RUN_KW(9);
