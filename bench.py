@@ -43,6 +43,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="genome", choices=["genome", "pangenome"],
+                    help="genome: BASELINE configs 2-4 (one synthetic genome); pangenome: config 5 (10 x 300 Mbp files, K=50 E=2 -ep)")
+    ap.add_argument("--pan-files", type=int, default=10)
+    ap.add_argument("--pan-file-mbp", type=float, default=300.0)
+    ap.add_argument("--pan-cpu-mbp", type=float, default=3.0, help="per-file size of the scale model the reference binary is run on")
     ap.add_argument("--genome-mbp", type=float, default=3000.0)
     ap.add_argument("--nchr", type=int, default=24)
     ap.add_argument("--seed", type=int, default=45)
@@ -113,6 +118,32 @@ class _DeviceBytes:
 
     def __init__(self, ptr, nbytes):
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+NUMA_NOTE = "not bound"
+
+
+def bind_to_gpu_numa_node(local):
+    """Run this rank (and so its pinned-buffer allocations: first touch) on the CPUs of the GPU's own NUMA node."""
+    global NUMA_NOTE
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            NUMA_NOTE = "single node"
+            return
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            NUMA_NOTE = "rank bound to NUMA node %d of its GPU (%d CPUs)" % (node, len(cpus))
+    except Exception as ex:
+        NUMA_NOTE = "not bound (%s)" % type(ex).__name__
 
 
 def genome_limits(total, nchr):
@@ -272,9 +303,219 @@ def parity_check(arm, ix, K, E):
     return {"positions": int(e - b), "window": [int(b), int(e)], "equal": bool(len(diff) == 0), "mismatches": int(len(diff)),
             "against": arm.kind, "nonunique_in_window": int((ref > 1).sum()), "max_count": int(ref.max()) if len(ref) else 0}
 
+# --------------------------------------------------------------------------------------------------------
+# BASELINE config 5: multi-FASTA pan-genome, --exclude-pseudo (src/algo.hpp:351-361: distinct FASTA files with an
+# occurrence).  All files are indexed together (text + full suffix array in HBM, replicated); a step = one batch
+# of positions of one file per GPU, the files' positions range-partitioned over the ranks.
+# --------------------------------------------------------------------------------------------------------
+def pangenome_reference(args, K, E):
+    """The unmodified reference (`index -FD`, `map -ep`) on a scale model of the same construction, and the GPU on
+    the same model: -> (cpu_baseline dict, parity dict)."""
+    import shutil
+    import genmap_b200 as gm
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import gmtest as T
+    if not T.have_reference():
+        raise RuntimeError("oracle/_ref/genmap_ref is not present")
+    seqs, stf = gm.synth_pangenome(args.pan_cpu_mbp * 1e6, args.pan_files)
+    per = len(seqs) // args.pan_files
+    tmp = tempfile.mkdtemp(prefix="gmb_pan_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        fdir, odir = os.path.join(tmp, "fa"), os.path.join(tmp, "out")
+        os.mkdir(fdir); os.mkdir(odir)
+        for g in range(args.pan_files):
+            T.write_fasta(os.path.join(fdir, "g%02d.fa" % g), seqs[g * per:(g + 1) * per],
+                          names=["g%02d_chr%d" % (g, i + 1) for i in range(per)])
+        subprocess.run([T.REF_BIN, "index", "-FD", fdir, "-I", os.path.join(tmp, "index")], check=True, stdout=subprocess.DEVNULL)
+        cores = os.cpu_count() or 1
+        res = subprocess.run([T.REF_BIN, "map", "-I", os.path.join(tmp, "index"), "-O", odir, "-K", str(K), "-E", str(E), "-ep",
+                              "-r", "-fl", "-T", str(cores), "-v"], check=True, stdout=subprocess.PIPE, text=True)
+        secs = [float(l.split()[3]) for l in res.stdout.replace("\r", "\n").split("\n") if l.startswith("Mappability computed in")]
+        n_all = sum(len(s) for s in seqs)
+        lim = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        lim[1:] = np.cumsum([len(s) for s in seqs])
+        ix = gm.Index.build(seqs, with_sa=True, on_gpu=True, seq_to_file=stf)
+        mism, nonuni = 0, 0
+        for g in range(args.pan_files):
+            s0 = g * per
+            tb, tl = int(lim[s0]), int(lim[s0 + per] - lim[s0])
+            got = ix.compute_mappability(gm.SearchParams(K, E, True, True, 16), text_begin=tb, text_len=tl,
+                                         chrom_cum_lengths=np.ascontiguousarray(lim[s0:s0 + per + 1] - lim[s0]))
+            ref = np.fromfile(os.path.join(odir, "g%02d.genmap.freq16" % g), dtype=np.uint16)
+            mism += int((got != ref).sum()); nonuni += int((ref > 1).sum())
+        ix.close()
+        sample = ("`genmap_ref index -FD` + `map -ep` on a scale model of the same construction (%d files x %g Mbp), every "
+                  "position of every file, -T %d; time = the sum of its 'Mappability computed in' lines"
+                  % (args.pan_files, args.pan_cpu_mbp, cores))
+        return ({"value": n_all / sum(secs), "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+                {"positions": int(n_all), "equal": mism == 0, "mismatches": mism, "against": "reference (scale model, all files)",
+                 "values_above_1": nonuni})
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def main_pangenome(args):
+    import torch
+    import genmap_b200 as gm
+    from genmap_b200 import _lib, parallel
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    K, E = (50, 2) if (args.kmer, args.errors) == (30, 0) else (args.kmer, args.errors)
+    workload = "%d x %g Mbp synthetic pan-genome (file g = base + g %% substitutions), K=%d E=%d --exclude-pseudo, both strands, uint16" % (
+        args.pan_files, args.pan_file_mbp, K, E)
+    if _lib.lib().gmb_device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cpu, par = pangenome_reference(args, K, E)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
+                          "warmup": 0, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "u32", "data": "synthetic", "config": {"workload": workload, "K": K, "E": E}, "cpu_baseline": cpu,
+                          "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return 0
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        bind_to_gpu_numa_node(local)
+    nchr = 3
+    per_file = int(args.pan_file_mbp * 1e6) // nchr * nchr
+    limits = np.arange(args.pan_files * nchr + 1, dtype=np.uint64) * np.uint64(per_file // nchr)
+    stf = np.repeat(np.arange(args.pan_files, dtype=np.uint32), nchr)
+    t0 = time.time()
+    if rank == 0:
+        seqs, stf0 = gm.synth_pangenome(args.pan_file_mbp * 1e6, args.pan_files, nchr)
+        assert np.array_equal(stf0, stf)
+        log("pan-genome generated in %.1f s" % (time.time() - t0))
+        t0 = time.time()
+        ix = gm.Index.build(seqs, device=local, with_sa=True, on_gpu=True, seq_to_file=stf)
+        del seqs
+        log("index with suffix array built on GPU in %.1f s, blob %.2f GB" % (time.time() - t0, ix.info.blob_bytes / 1e9))
+    bcast_s = None
+    if dist is not None:
+        blob_t = torch.as_tensor(_DeviceBytes(int(ix.info.device_blob), int(ix.info.blob_bytes)), device=dev) if rank == 0 else None
+        dist.barrier()
+        t0 = time.time()
+        blob_t = parallel.broadcast_blob(blob_t, dist, dev)
+        torch.cuda.synchronize()
+        bcast_s = time.time() - t0
+        log("rank %d: index broadcast over NCCL in %.2f s" % (rank, bcast_s))
+        if rank != 0:
+            ix = gm.Index.adopt_device(blob_t.data_ptr(), blob_t.numel(), device=local, seq_to_file=stf)
+    ix.limits = limits
+    ix.set_jump_depth(args.jump_depth)
+    stream = torch.cuda.current_stream().cuda_stream
+    batch = int((args.batch_mpos or 8.0) * (1 << 20))
+    out_dev = torch.zeros(per_file, dtype=torch.int16, device=dev)
+
+    def file_args(g):
+        s0 = g * nchr
+        return dict(text_begin=int(limits[s0]), text_len=per_file, chrom_cum_lengths=np.ascontiguousarray(limits[s0:s0 + nchr + 1] - limits[s0]))
+
+    # every file's positions are split over the ranks; the steps walk through the files
+    sb, se = parallel.shard_range(per_file, rank, world)
+    b_ = max(1 << 14, min(batch, se - sb))
+    plan = []
+    for i in range(args.warmup + args.steps + 1):
+        g = i % args.pan_files
+        off = sb + ((i // args.pan_files) * b_) % max(1, se - sb - b_ + 1)
+        plan.append((g, off, off + b_))
+    p_ep, p_plain = gm.SearchParams(K, E, True, True, 16), gm.SearchParams(K, E, True, False, 16)
+
+    def run(g, b, e, p=p_ep, **kw):
+        return ix.compute_mappability_device(p, out_dev.data_ptr(), pos_begin=b, pos_end=e, stream=stream, **file_args(g), **kw)
+
+    for g, b, e in plan[:args.warmup]:
+        run(g, b, e, sync=False)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    timed = plan[args.warmup:args.warmup + args.steps]
+    for g, b, e in timed:
+        run(g, b, e, sync=False)
+    ev1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    npos = sum(e - b for _, b, e in timed)
+    if dist is not None:
+        ms = parallel.max_over_ranks(ms, dist, dev)
+        npos = parallel.sum_over_ranks(npos, dist, dev)
+    value = npos / (ms * 1e-3)
+    # end to end: the same batches through the host-buffer call (slice of c into pinned host memory)
+    host_t = torch.empty(b_, dtype=torch.int16).pin_memory()
+    host = host_t.numpy().view(np.uint16)
+    g, b, e = plan[-1]
+    ix.compute_mappability_range(p_ep, b, e, out=host, **file_args(g))
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for g, b, e in timed:
+        ix.compute_mappability_range(p_ep, b, e, out=host, **file_args(g))
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        dt = parallel.max_over_ranks(dt, dist, dev)
+    e2e = {"value": npos / dt, "unit": UNIT, "h2d_bytes_per_step": int(4 * 8 + 4 * len(stf)), "d2h_bytes_per_step": int(2 * b_), "numa": NUMA_NOTE}
+    roof = None
+    if rank == 0:
+        # kernel time per launch; rank-block fetches from the instrumented kernel on the same batches WITHOUT -ep (the same
+        # searches; the instrumented instantiation is not built for -ep, whose extra reads — one suffix-array entry per
+        # located occurrence — are therefore not in the figure)
+        k_ms, f_tot, lut_tot, searched, txt = [], 0, 0, 0, 0
+        for g, b, e in timed:
+            st = run(g, b, e)
+            k_ms.append(st.kernel_ms); searched += int(st.positions)
+        for g, b, e in timed:
+            st = run(g, b, e, p=p_plain, count_fetches=True)
+            f_tot += int(st.rank_block_fetches); lut_tot += int(st.jump_table_reads); txt += int(st.text_reads)
+        peak, peak_src = peak_hbm()
+        per_launch = f_tot * 32.0 / len(timed)
+        achieved = per_launch / (float(np.mean(k_ms)) * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "rank_block_bytes_per_position": f_tot * 32.0 / max(searched, 1),
+                "table_reads_per_position": lut_tot / max(searched, 1), "text_reads_per_position": txt / max(searched, 1),
+                "kernel_ms_per_launch": float(np.mean(k_ms)),
+                "note": "fetches counted on the same batches without -ep (same searches); -ep adds one suffix-array read per located occurrence"}
+    hbm = {"index_blob_with_sa": int(ix.info.blob_bytes), "jump_tables": int(ix.refresh_info().jump_table_bytes), "result_vector": int(2 * per_file)}
+    cpu, par = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            del out_dev
+            ix.close()
+            torch.cuda.empty_cache()
+            cpu, par = pangenome_reference(args, K, E)
+            log("reference on the scale model: %.3f M positions/s, parity %s" % (cpu["value"] / 1e6, par))
+        except Exception as ex:
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (ex,)}
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+                          "data": "synthetic",
+                          "config": {"workload": workload, "K": K, "E": E, "genome_bp": int(limits[-1]), "positions_per_step_per_gpu": b_,
+                                     "sharding": "every file's positions range-partitioned over %d GPU(s), index + suffix array replicated (NCCL broadcast%s)"
+                                                 % (world, "" if bcast_s is None else ": %.2f s" % bcast_s),
+                                     "cache": "inputs larger than L2: %.1f GB index vs 126 MB L2" % (hbm["index_blob_with_sa"] / 1e9),
+                                     "hbm_bytes": hbm},
+                          "parity": {"pangenome_K%d_E%d_ep" % (K, E): par} if par else None, "clocks": clocks, "e2e": e2e,
+                          "gpu_launches": args.steps, "roofline": roof, "cpu_baseline": cpu}), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
 
 def main():
     args = parse()
+    if args.config == "pangenome":
+        return main_pangenome(args)
     import torch
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -293,6 +534,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if args.impl == "ours" and world > 1:
+        bind_to_gpu_numa_node(local)
     dist = None
     if world > 1 and args.impl == "ours":
         import torch.distributed as dist
@@ -392,7 +635,8 @@ def main():
                 k_ms.append(st.kernel_ms); pos0 += int(st.positions)
             res.update(fetches=f_tot, kernel_ms=float(np.mean(k_ms)), searched=pos0, lut_reads=lut_tot, jump_depth=jd)
         if with_e2e:
-            host = torch.empty(batch, dtype=torch.int16).pin_memory().numpy().view(np.uint16)
+            host_t = torch.empty(batch, dtype=torch.int16).pin_memory()
+            host = host_t.numpy().view(np.uint16)
             bl2 = batches(E_, batch, 1 + steps)
             ix.compute_mappability_range(p, bl2[0][0], bl2[0][1], out=host)
             if dist is not None:
@@ -406,9 +650,27 @@ def main():
                 dt = parallel.max_over_ranks(dt, dist, dev)
                 npos2 = parallel.sum_over_ranks(npos2, dist, dev)
             # per step: work-range table + step table + counters go H2D, the slice of c comes back D2H
+            # what the host link alone allows: the same bytes device -> pinned host with no search at all, every rank at
+            # once (the e2e figure cannot exceed it; at E = 0 it is what bounds it)
+            src = out_dev[:batch]
+            host_t.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                host_t.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            dt_copy = time.perf_counter() - t0
+            if dist is not None:
+                dt_copy = parallel.max_over_ranks(dt_copy, dist, dev)
+            # per step: the work-range table goes H2D (search tables are cached in the handle), the slice of c comes back
             res["e2e"] = {"value": npos2 / dt, "unit": UNIT,
-                          "h2d_bytes_per_step": int(3 * 8 + 4 * K * {0: 1, 1: 2, 2: 3, 3: 4, 4: 7}[E_] + 16),
-                          "d2h_bytes_per_step": int(2 * batch)}
+                          "h2d_bytes_per_step": int(3 * 8 + 8),
+                          "d2h_bytes_per_step": int(2 * batch),
+                          "d2h_only_gb_per_s_per_gpu": 2.0 * batch * steps / dt_copy / 1e9,
+                          "d2h_only_positions_per_s": world * batch * steps / dt_copy,
+                          "numa": NUMA_NOTE}
         return res
 
     batch = int((args.batch_mpos or default_batch(E)) * (1 << 20))

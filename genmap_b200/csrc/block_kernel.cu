@@ -29,7 +29,13 @@ namespace {
 constexpr uint32_t kPendSlots = 8;      // entries a chain can put aside per round
 constexpr uint32_t kPendWords = 4;      // lo_r, size, lo_f, key index
 constexpr uint32_t kRound = 32;         // keys per round (one overflow bit each)
-constexpr uint32_t kKeyBatch = 4;       // table entries requested back to back
+#ifndef GMB_KEY_BATCH
+#define GMB_KEY_BATCH 4
+#endif
+#ifndef GMB_BLOCK_MINB
+#define GMB_BLOCK_MINB 3                // resident CTAs per SM the register allocation must allow (3: 80 registers)
+#endif
+constexpr uint32_t kKeyBatch = GMB_KEY_BATCH; // table entries requested back to back
 
 template <int KW, bool COUNT, typename OutT, bool EP, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L)
@@ -227,7 +233,9 @@ size_t block_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bo
 
 bool block_kernel_applies(const MapLaunch& L)
 {
-    return L.keylist != nullptr && L.sigma == 4 && L.E >= 1 && L.cx.K + L.cx.B - 1 <= 64 && L.cx.loc_rows == nullptr && L.loc_off == nullptr &&
+    // (E >= 3: walks dominate and the general kernel, whose lanes refill one by one, is still the faster of the two:
+    // profiles/r02/s4_sweep_{general,block}.txt)
+    return L.keylist != nullptr && L.sigma == 4 && L.E >= 1 && (L.E <= 2 || L.force_block_kernel) && L.cx.K + L.cx.B - 1 <= 64 && L.cx.loc_rows == nullptr && L.loc_off == nullptr &&
            !(L.exclude_pseudo && L.count_fetches);
 }
 
@@ -235,7 +243,7 @@ cudaError_t launch_block_kernel(const MapLaunch& L, int sm_count, cudaStream_t s
 {
     if (L.n_work == 0) return cudaSuccess;
     if (L.chunk != 32u * L.cx.B) return cudaErrorInvalidValue; // one block per lane
-    return L.cx.K + L.cx.B - 1 <= 32 ? launch_blk_kw<1, 3>(L, sm_count, stream) : launch_blk_kw<2, 3>(L, sm_count, stream);
+    return L.cx.K + L.cx.B - 1 <= 32 ? launch_blk_kw<1, GMB_BLOCK_MINB>(L, sm_count, stream) : launch_blk_kw<2, GMB_BLOCK_MINB>(L, sm_count, stream);
 }
 
 } // namespace gmb

@@ -24,6 +24,9 @@ namespace gmb {
 namespace {
 
 constexpr int kThreadsE0 = 256;
+#ifndef GMB_EXACT_MINB
+#define GMB_EXACT_MINB 4 // resident CTAs per SM the register allocation must allow
+#endif
 
 struct ExactCounters { unsigned long long fetches, lut, located, text_reads, steps; };
 
@@ -52,7 +55,7 @@ __device__ __forceinline__ uint32_t walk_exact(const Pattern<KW, 4>& P, uint32_t
 }
 
 template <int KW, bool COUNT, typename OutT>
-__global__ void __launch_bounds__(kThreadsE0, 4) exact_kernel(const MapLaunch L)
+__global__ void __launch_bounds__(kThreadsE0, GMB_EXACT_MINB) exact_kernel(const MapLaunch L)
 {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t K = L.cx.K, d = L.e0_depth, maxv = L.cx.maxv;

@@ -46,6 +46,7 @@ struct MapLaunch {
     // (nullptr: not applicable / switched off).  `chunk` is then 32 * B: one block per lane.
     const uint2* keylist;
     uint32_t key_off[kMaxBlockKmers + 1], key_n[kMaxBlockKmers + 1];
+    bool force_block_kernel;   // GMB_BLOCK_KERNEL=2: also for E >= 3 (measurements)
 };
 
 constexpr unsigned kChunk = 128; // positions handed out per global atomic (rounded down to a multiple of B)
