@@ -9,6 +9,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -505,13 +507,19 @@ int map_main(int argc, char const** argv)
     if (gmb_device_count() == 0) { std::cerr << "ERROR: no CUDA device found: the B200 build of `genmap map` has no CPU fallback.\n"; return 1; }
     if ((int)gpu > gmb_device_count()) { std::cerr << "ERROR: --gpus " << gpu << " requested but only " << gmb_device_count() << " CUDA device(s) found.\n"; return 1; }
     std::vector<gmb_index*> ixs(gpu, nullptr); // the index is replicated: one copy in the HBM of every GPU
+    const double t_open = wall();
     if (gmb_index_open(index_dir.c_str(), 0, &ixs[0]) != GMB_OK) { std::cerr << "ERROR: " << gmb_last_error() << "\n"; return 1; }
+    const double t_repl = wall();
     for (uint64_t g = 1; g < gpu; ++g) // read once, then GPU-to-GPU copies over NVLink
         if (gmb_index_replicate(ixs[0], (int)g, &ixs[g]) != GMB_OK) { std::cerr << "ERROR: " << gmb_last_error() << "\n"; return 1; }
+    const double t_loaded = wall();
     gmb_index_info iinfo;
     gmb_index_get_info(ixs[0], &iinfo);
     if (a.has("verbose")) {
         std::cout << "Index was loaded (" << (iinfo.alphabet_size == 5 ? "dna5" : "dna4") << " alphabet, " << iinfo.blob_bytes << " bytes in the HBM of " << gpu << " GPU(s)).\n";
+        std::cout << "- Index read and copied to GPU 0 in " << round2(t_repl - t_open) << " seconds";
+        if (gpu > 1) std::cout << ", replicated to " << (gpu - 1) << " more GPU(s) in " << round2(t_loaded - t_repl) << " seconds";
+        std::cout << "\n";
         std::cout << (directory ? "- Index was built on an entire directory.\n" : "- Index was built on a single fasta file.\n") << std::flush;
     }
 
@@ -575,6 +583,26 @@ int map_main(int argc, char const** argv)
             // positions are range-partitioned over the GPUs; every GPU fills its own slice of c
             std::vector<std::string> errors(gpu);
             std::vector<std::thread> workers;
+            const double t_search = wall();
+            // progress of the call in flight, as the reference prints it (src/common.hpp:94-131): polled from the devices
+            std::atomic<bool> searching{true};
+            std::thread progress([&] {
+                const double t0 = wall();
+                while (searching.load()) {
+                    std::this_thread::sleep_for(std::chrono::milliseconds(100));
+                    if (!searching.load() || wall() - t0 < 0.5) continue;
+                    uint64_t done = 0, total = 0;
+                    for (uint64_t g = 0; g < gpu; ++g) {
+                        uint64_t d = 0, t = 0;
+                        if (gmb_progress(ixs[g], &d, &t) == GMB_OK) { done += d; total += t; }
+                    }
+                    if (total == 0) continue;
+                    char buf[64];
+                    std::snprintf(buf, sizeof buf, "%.2f", 100.0 * (double)done / (double)total);
+                    if (total_files == 1) std::cout << "\rProgress: " << buf << "%\x1b[K" << std::flush;
+                    else std::cout << "\rFile " << file_no << " / " << total_files << ". Progress: " << buf << " %\x1b[K" << std::flush;
+                }
+            });
             for (uint64_t g = 0; want_freq && g < gpu; ++g)
                 workers.emplace_back([&, g] {
                     const uint64_t b = text_len * g / gpu, e = text_len * (g + 1) / gpu;
@@ -589,6 +617,9 @@ int map_main(int argc, char const** argv)
                         errors[g] = gmb_last_error();
                 });
             for (std::thread& w : workers) w.join();
+            searching.store(false);
+            progress.join();
+            const double t_searched = wall();
             for (const std::string& e : errors)
                 if (!e.empty()) { std::cerr << "ERROR: " << e << "\n"; return 1; }
             if (device_runs) { // a run that continues across a slice boundary is one run
@@ -608,6 +639,9 @@ int map_main(int argc, char const** argv)
                 std::cout << "\rFile " << file_no << " / " << total_files << ". Progress: 100.00 %\x1b[K" << std::flush;
                 if (a.has("verbose") || file_no == total_files) std::cout << '\n';
             }
+            if (a.has("verbose") && want_freq)
+                std::cout << "- Searched on " << gpu << " GPU(s) in " << round2(t_searched - t_search) << " seconds ("
+                          << (device_runs ? "runs" : "frequency vector") << " in host memory)\n";
             std::string prefix = out_path;
             if (!includes_filename) prefix += rows[i].file.substr(0, rows[i].file.find_last_of('.')) + ".genmap"; // :76-78
             gmbcli::Outputs o{raw, txt, wig, bg, bed, a.has("verbose"),
@@ -638,7 +672,7 @@ int render_main(int argc, char const** argv)
     std::vector<OptSpec> specs = {{"I", "ids", true}, {"C", "counts", true}, {"O", "output", true}, {"N", "file-no", true},
                                   {"fs", "frequency-small", false}, {"fl", "frequency-large", false}, {"r", "raw", false},
                                   {"t", "txt", false}, {"w", "wig", false}, {"bg", "bedgraph", false}, {"b", "bed", false},
-                                  {"xr", "via-runs", false}};
+                                  {"xr", "via-runs", false}, {"T", "threads", true}};
     Args a;
     int rc = parse_args("GenMap render", specs, argc, argv, a, "genmap render -I index.ids -C counts.freq16|.freq8 -N file_no -O prefix [-fs|-fl] -r -t -w -bg -b\n");
     if (rc) return rc == 2 ? 0 : 1;
@@ -662,7 +696,9 @@ int render_main(int argc, char const** argv)
     if (!in.read(reinterpret_cast<char*>(buf.data()), (std::streamsize)buf.size())) { std::cerr << "ERROR: short counts file\n"; return 1; }
     const gmbcli::OutputType otype = a.has("frequency-small") ? gmbcli::OutputType::frequency_small
                                    : a.has("frequency-large") ? gmbcli::OutputType::frequency_large : gmbcli::OutputType::mappability;
-    gmbcli::Outputs o{a.has("raw"), a.has("txt"), a.has("wig"), a.has("bedgraph"), a.has("bed"), false, 3u};
+    uint64_t n_threads = 3;
+    if (a.has("threads")) to_uint(a.val["threads"], n_threads);
+    gmbcli::Outputs o{a.has("raw"), a.has("txt"), a.has("wig"), a.has("bedgraph"), a.has("bed"), false, (unsigned)std::max<uint64_t>(1, n_threads)};
     if (a.has("via-runs")) { // the track writers fed from a run list shaped like gmb_map_runs' (a run starts at every sequence start)
         const std::vector<uint64_t> cum = gmbcli::cumulative(lens);
         std::vector<uint64_t> st;

@@ -2,7 +2,9 @@
 // .bedgraph, .bed.  Byte-identical to the reference's writers (src/output.hpp:10-187, dispatch and verbose
 // lines src/mappability.hpp:69-155); structured as one run-length pass feeding small format emitters.
 #pragma once
+#include <fcntl.h>
 #include <sys/time.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -181,18 +183,82 @@ inline std::vector<uint64_t> cumulative(const std::vector<uint64_t>& lens)
     return cum;
 }
 
+// src/output.hpp:10-31: the vector as it is (.freq8 / .freq16) or its inverses as floats (.map).  One file, written
+// by `threads` workers at their own offsets (pwrite): at 3 Gbp the raw file has 6-12 GB and a single buffered writer was
+// the longest step of a whole `genmap map` run.
 template <class T>
-void write_raw(const T* c, uint64_t n, const std::string& path, bool mappability)
+void write_raw(const T* c, uint64_t n, const std::string& path, bool mappability, unsigned threads = 1)
 {
-    Sink o(path);
-    if (!o.ok()) { std::cerr << "ERROR: cannot write " << path << "\n"; return; }
-    if (!mappability) { o.bytes(c, n * sizeof(T)); return; }
-    std::vector<float> buf(1 << 16);
-    for (uint64_t i = 0; i < n;) { // src/output.hpp:17-24
-        size_t m = 0;
-        for (; m < buf.size() && i < n; ++m, ++i) buf[m] = c[i] != 0 ? 1.0f / static_cast<float>(c[i]) : 0.0f;
-        o.bytes(buf.data(), m * sizeof(float));
+    const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) { std::cerr << "ERROR: cannot write " << path << "\n"; return; }
+    const size_t elem = mappability ? sizeof(float) : sizeof(T);
+    const uint64_t piece = 8u << 20; // values per piece
+    const uint64_t n_pieces = (n + piece - 1) / piece;
+    if (threads < 1) threads = 1;
+    if (threads > n_pieces) threads = (unsigned)std::max<uint64_t>(1, n_pieces);
+    std::vector<char> failed(threads, 0);
+    auto work = [&](unsigned t) {
+        std::vector<float> buf(mappability ? piece : 0);
+        for (uint64_t q = t; q < n_pieces; q += threads) {
+            const uint64_t b = q * piece, e = std::min(n, b + piece);
+            const char* src = reinterpret_cast<const char*>(c + b);
+            if (mappability) { // src/output.hpp:17-24
+                for (uint64_t i = b; i < e; ++i) buf[i - b] = c[i] != 0 ? 1.0f / static_cast<float>(c[i]) : 0.0f;
+                src = reinterpret_cast<const char*>(buf.data());
+            }
+            size_t left = (e - b) * elem;
+            off_t at = (off_t)(b * elem);
+            while (left) {
+                const ssize_t w = ::pwrite(fd, src, left, at);
+                if (w <= 0) { failed[t] = 1; return; }
+                src += w; at += w; left -= (size_t)w;
+            }
+        }
+    };
+    if (threads == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < threads; ++t) pool.emplace_back(work, t);
+        for (std::thread& w : pool) w.join();
     }
+    if (::close(fd) != 0 || std::count(failed.begin(), failed.end(), 1)) std::cerr << "ERROR: short write to " << path << "\n";
+}
+
+// The runs of a vector in host memory as a run list (what gmb_map_runs returns from the device), found by `threads`
+// workers on consecutive chunks; a run that continues across a chunk border is one run, and a new run starts at every
+// sequence start.  Lets the threaded run formatters serve the track formats also when the vector itself was asked for.
+template <class T>
+void runs_of_vector(const T* c, const std::vector<uint64_t>& cum, unsigned threads, std::vector<uint64_t>& start, std::vector<uint16_t>& value)
+{
+    const uint64_t n = cum.back();
+    if (threads < 1) threads = 1;
+    const uint64_t chunk = std::max<uint64_t>(1u << 20, (n + threads - 1) / threads);
+    const uint64_t n_chunks = n ? (n + chunk - 1) / chunk : 0;
+    std::vector<std::vector<uint64_t>> st(n_chunks);
+    std::vector<std::vector<uint16_t>> va(n_chunks);
+    auto work = [&](uint64_t q) {
+        const uint64_t b = q * chunk, e = std::min(n, b + chunk);
+        size_t s = std::upper_bound(cum.begin(), cum.end(), b) - cum.begin(); // next sequence start after b
+        for (uint64_t i = b; i < e; ++i) {
+            bool head = i == b || c[i] != c[i - 1];
+            while (s < cum.size() && cum[s] < i) ++s;
+            if (s < cum.size() && cum[s] == i) { head = true; ++s; }
+            if (head) { st[q].push_back(i); va[q].push_back((uint16_t)c[i]); }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (uint64_t q = 0; q < n_chunks; ++q) {
+        if (threads == 1) work(q);
+        else pool.emplace_back(work, q);
+    }
+    for (std::thread& w : pool) w.join();
+    start.clear(); value.clear();
+    for (uint64_t q = 0; q < n_chunks; ++q)
+        for (size_t r = 0; r < st[q].size(); ++r) {
+            const uint64_t at = st[q][r];
+            if (r == 0 && q != 0 && !value.empty() && value.back() == va[q][r] && !std::binary_search(cum.begin(), cum.end(), at)) continue;
+            start.push_back(at); value.push_back(va[q][r]);
+        }
 }
 
 // values [begin, end) of one sequence as text, separated by single spaces (no leading / trailing separator)
@@ -290,6 +356,9 @@ void write_bedgraph(const Source& src, const std::string& prefix, const std::vec
     }
 }
 
+inline void write_track_outputs(const ListRuns& src, const std::string& prefix, const std::vector<std::string>& names,
+                                const std::vector<uint64_t>& lens, OutputType type, const Outputs& o);
+
 template <class T>
 void write_outputs(const T* c, uint64_t n, const std::string& prefix, const std::vector<std::string>& names,
                    const std::vector<uint64_t>& lens, OutputType type, const Outputs& o)
@@ -301,14 +370,23 @@ void write_outputs(const T* c, uint64_t n, const std::string& prefix, const std:
         if (o.verbose) std::cout << "- " << what << " written in " << (std::round((now_s() - t0) * 100.0) / 100.0) << " seconds\n";
     };
     if (o.raw) timed("RAW file", [&] {
-        write_raw(c, n, prefix + (mapp ? ".map" : type == OutputType::frequency_small ? ".freq8" : ".freq16"), mapp);
+        write_raw(c, n, prefix + (mapp ? ".map" : type == OutputType::frequency_small ? ".freq8" : ".freq16"), mapp, o.threads);
     });
     if (o.txt) timed("TXT file", [&] { write_txt(c, prefix, names, lens, mapp, o.threads); });
+    if (!(o.wig || o.bedgraph || o.bed)) return;
     const std::vector<uint64_t> cum = cumulative(lens);
-    const VectorRuns<T> src{c, cum};
-    if (o.wig) timed("WIG file", [&] { write_wig(src, prefix, names, lens, mapp); });
-    if (o.bedgraph) timed("bedgraph file", [&] { write_bedgraph(src, prefix, names, lens, true, mapp); });
-    if (o.bed) timed("BED file", [&] { write_bedgraph(src, prefix, names, lens, false, mapp); });
+    if (o.threads <= 1) { // one scan per format, as the reference does it
+        const VectorRuns<T> src{c, cum};
+        if (o.wig) timed("WIG file", [&] { write_wig(src, prefix, names, lens, mapp); });
+        if (o.bedgraph) timed("bedgraph file", [&] { write_bedgraph(src, prefix, names, lens, true, mapp); });
+        if (o.bed) timed("BED file", [&] { write_bedgraph(src, prefix, names, lens, false, mapp); });
+        return;
+    }
+    // several host threads: the runs once (threaded scan), then the threaded run formatters
+    std::vector<uint64_t> run_start;
+    std::vector<uint16_t> run_value;
+    runs_of_vector(c, cum, o.threads, run_start, run_value);
+    write_track_outputs(ListRuns{run_start.data(), run_value.data(), run_start.size(), cum}, prefix, names, lens, type, o);
 }
 
 // run-list overloads: the same files, formatted by several host threads

@@ -153,12 +153,16 @@ def test_track_writers_from_run_lists_in_chunks_and_threads(genmap, tmp_path):
             f.write("g.fa;%d;s%d\n" % (n, i))
     for flags in (["-fl"], []):
         outs = []
-        for tag, extra in (("vec", []), ("runs", ["-xr"])):
+        for tag, extra in (("vec", []), ("runs", ["-xr"]), ("serial", ["-T", "1"]), ("many", ["-T", "7", "-r"])):
             out = tmp_path / ("o_%s_%d" % (tag, len(flags)))
             r = run(genmap, "render", "-I", tmp_path / "index.ids", "-C", tmp_path / "c.freq16", "-N", 0, "-O", out, "-w", "-bg", "-b",
                     *flags, *extra)
             assert r.returncode == 0, r.stderr
             outs.append(str(out))
         for ext in (".wig", ".bedgraph", ".bed", ".chrom.sizes"):
-            assert filecmp.cmp(outs[0] + ext, outs[1] + ext, shallow=False), (flags, ext)
+            for other in outs[1:]:  # threaded scan of the vector, run list, the serial scan, 7 threads: the same files
+                assert filecmp.cmp(outs[0] + ext, other + ext, shallow=False), (flags, ext, other)
+        raw = np.fromfile(outs[3] + (".freq16" if flags else ".map"), dtype=np.uint16 if flags else np.float32)  # threaded raw writer
+        want = c if flags else np.where(c != 0, np.float32(1.0) / np.maximum(c, 1).astype(np.float32), np.float32(0)).astype(np.float32)
+        assert np.array_equal(raw, want)
         assert os.path.getsize(outs[0] + ".wig") > 5_000_000
