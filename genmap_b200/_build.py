@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libgenmap_b200.so")
-SOURCES = ["capi.cu", "map_kernel.cu", "exact_kernel.cu", "block_kernel.cu", "locate_kernel.cu", "rle_kernel.cu", "jump_table.cu", "index_build_gpu.cu", "gmb_host.cpp"]
+SOURCES = ["capi.cu", "map_kernel.cu", "exact_kernel.cu", "block_kernel.cu", "locate_kernel.cu", "rle_kernel.cu", "jump_table.cu", "index_build_gpu.cu", "gmb_host.cpp", "seqan_export.cpp"]
 HEADERS = ["gmb_layout.h", "gmb_core.h", "gmb_host.h", "sais.hpp", "map_kernel.cuh", "map_kernel_impl.cuh", "locate.cuh", "rle.cuh", "jump_table.cuh", "index_build_gpu.cuh",
            os.path.join("..", "..", "include", "genmap_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

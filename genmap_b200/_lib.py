@@ -14,7 +14,7 @@ EXPORTS = ["gmb_last_error", "gmb_version", "gmb_device_count", "gmb_index_build
            "gmb_index_adopt_device", "gmb_index_close", "gmb_index_get_info", "gmb_map_frequencies",
            "gmb_map_frequencies_range", "gmb_map_frequencies_device", "gmb_index_export_bwt", "gmb_index_export_sa", "gmb_index_set_jump_depth",
            "gmb_index_import_reference", "gmb_map_locations", "gmb_locations_free", "gmb_map_runs", "gmb_runs_free", "gmb_index_replicate",
-           "gmb_index_set_plan_text_size", "gmb_progress"]
+           "gmb_index_set_plan_text_size", "gmb_progress", "gmb_blob_export_reference"]
 
 
 class GmbParams(ctypes.Structure):
@@ -102,6 +102,8 @@ def lib():
     L.gmb_index_set_plan_text_size.argtypes = [vp, u64]
     L.gmb_progress.restype = ci
     L.gmb_progress.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    L.gmb_blob_export_reference.restype = ci
+    L.gmb_blob_export_reference.argtypes = [vp, u64, ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), u32, ci, u32]
     L.gmb_index_import_reference.restype = ci
     L.gmb_index_import_reference.argtypes = [ctypes.c_char_p, pp, ctypes.POINTER(u64)]
     L.gmb_index_export_sa.restype = ci

@@ -71,6 +71,17 @@ class Index:
         _lib.lib().gmb_blob_free(blob)
         return out
 
+    @staticmethod
+    def export_reference_blob(blob, directory, ids, fasta_directory=False, sampling=10):
+        """Write a blob built with with_sa=True as an index directory in the reference's own format (what its `map`
+        opens).  ids: one "file;length;name" string per sequence."""
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        import os
+        os.makedirs(str(directory), exist_ok=True)
+        arr = (ctypes.c_char_p * len(ids))(*[s.encode() for s in ids])
+        check(_lib.lib().gmb_blob_export_reference(_ptr(blob), blob.nbytes, str(directory).encode(), arr, len(ids),
+                                                   int(fasta_directory), int(sampling)))
+
     @classmethod
     def build(cls, seqs, device=0, with_sa=False, on_gpu=True, seq_to_file=None):
         """Index the sequences (uint8 codes 0..3) and leave the index in HBM of `device`."""

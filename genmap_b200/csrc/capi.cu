@@ -449,6 +449,18 @@ int gmb_index_import_reference(const char* dir, void** blob_out, uint64_t* bytes
     return GMB_OK;
 }
 
+int gmb_blob_export_reference(const void* blob, uint64_t bytes, const char* dir, const char* const* ids, uint32_t n_ids,
+                              int fasta_directory, uint32_t sampling)
+{
+    if (!blob || !dir || (!ids && n_ids)) return fail(GMB_ERR_ARG, "gmb_blob_export_reference: NULL argument");
+    std::vector<std::string> lines;
+    for (uint32_t i = 0; i < n_ids; ++i) lines.emplace_back(ids[i] ? ids[i] : "");
+    std::string err;
+    if (!export_reference_index(static_cast<const uint8_t*>(blob), bytes, dir, lines, fasta_directory != 0, sampling, err))
+        return fail(err.find("write") != std::string::npos ? GMB_ERR_IO : GMB_ERR_UNSUPPORTED, err);
+    return GMB_OK;
+}
+
 int gmb_index_open(const char* dir, int device, gmb_index** out)
 {
     if (!dir || !out) return fail(GMB_ERR_ARG, "gmb_index_open: NULL argument");

@@ -216,6 +216,8 @@ const char* kIndexHelp =
     "  -S,  --sampling         accepted for compatibility: the index stores the FULL suffix array (4 bytes per\n"
     "                          base; used by --exclude-pseudo), unless --no-sa is given.\n"
     "  -xn, --no-sa            do not store the suffix array (smaller index; --exclude-pseudo unavailable).\n"
+    "  -xf, --reference-format also write the index in the reference's own on-disk format (SeqAn fibres, suffix array\n"
+    "                          sampled with -S, default 10): the directory then opens in the original genmap as well.\n"
     "  -v,  --verbose\n";
 
 int index_main(int argc, char const** argv)
@@ -223,7 +225,7 @@ int index_main(int argc, char const** argv)
     std::vector<OptSpec> specs = {{"F", "fasta-file", true}, {"FD", "fasta-directory", true}, {"I", "index", true},
                                   {"A", "algorithm", true}, {"S", "sampling", true}, {"v", "verbose", false},
                                   {"xa", "seqno", true}, {"xb", "seqpos", true}, {"xc", "bwtlen", true},
-                                  {"xn", "no-sa", false}, {"xh", "host-build", false}};
+                                  {"xn", "no-sa", false}, {"xh", "host-build", false}, {"xf", "reference-format", false}};
     Args a;
     int rc = parse_args("GenMap index", specs, argc, argv, a, kIndexHelp);
     if (rc == 2) return 0;
@@ -297,6 +299,16 @@ int index_main(int argc, char const** argv)
     std::string base = index_dir;
     if (base.back() != '/') base += '/';
     if (gmb_blob_save(blob, bytes, (base + "index.gmb").c_str()) != GMB_OK) { std::cerr << "ERROR: " << gmb_last_error() << "\n"; return 1; }
+    if (a.has("reference-format")) { // the same index as the fibres the original genmap opens (src/genmap_helper.hpp:71-127)
+        uint64_t sampling = 10;
+        if (a.has("sampling")) to_uint(a.val["sampling"], sampling);
+        std::vector<const char*> id_ptrs;
+        for (const std::string& l : ids_lines) id_ptrs.push_back(l.c_str());
+        if (gmb_blob_export_reference(blob, bytes, index_dir.c_str(), id_ptrs.data(), (uint32_t)id_ptrs.size(), fd ? 1 : 0, (uint32_t)sampling) != GMB_OK) {
+            std::cerr << "ERROR: " << gmb_last_error() << "\n";
+            return 1;
+        }
+    }
     gmb_blob_free(blob);
     {
         std::ofstream ids(base + "index.ids");

@@ -104,6 +104,11 @@ bool build_index_host(const uint8_t* codes, const uint64_t* limits, uint32_t n_s
 // class only; the sampled suffix array is not imported (no --exclude-pseudo on imported indices).
 bool import_reference_index(const std::string& dir, Blob& blob, std::string& err);
 
+// The reverse (seqan_export.cpp): the reference's own index directory from a blob that holds the suffix array.
+// ids: one "file;length;name" line per sequence (index.ids, src/indexing.hpp:399-401).
+bool export_reference_index(const uint8_t* blob, uint64_t bytes, const std::string& dir, const std::vector<std::string>& ids,
+                            bool fasta_directory, uint32_t sampling, std::string& err);
+
 // Positions whose k-mer is actually searched: inside a sequence with at least K bases left
 // (everything else stays 0: resetLimits, src/algo.hpp:10-22), inside a selection interval if any
 // (src/algo.hpp:441-476), inside [pos_begin, pos_end) (multi-GPU sharding).  Sorted, disjoint.

@@ -120,6 +120,13 @@ int gmb_index_open(const char *dir, int device, gmb_index **out);
  * blob (release with gmb_blob_free).  gmb_index_open does this automatically when <dir>/index.gmb is
  * absent but <dir>/index.lf.drv exists.  Dna4 and Dna5 indices of the default (16,32,32) width class. */
 int gmb_index_import_reference(const char *dir, void **blob_out, uint64_t *bytes_out);
+/* The reverse: write a host blob that holds the suffix array as an index directory in the reference's own format
+ * (<dir>/index.lf.drv, index.sa.val, ...: everything `genmap map` of the reference opens, src/genmap_helper.hpp:71-127),
+ * byte-identical to what the reference's `genmap index` writes for the same FASTA input.  ids: one
+ * "file;length;name" string per indexed sequence (index.ids, src/indexing.hpp:399-401); sampling: suffix-array
+ * sampling rate (the reference's -S, default 10).  Dna4 indices with at most 65535 sequences. */
+int gmb_blob_export_reference(const void *blob, uint64_t bytes, const char *dir, const char *const *ids, uint32_t n_ids,
+                              int fasta_directory, uint32_t sampling);
 int gmb_index_from_blob(const void *host_blob, uint64_t bytes, int device, gmb_index **out);
 int gmb_index_adopt_device(void *device_blob, uint64_t bytes, int device, gmb_index **out);
 /* Replicate an opened index into the HBM of another GPU of the same node with a peer-to-peer copy (NVLink /

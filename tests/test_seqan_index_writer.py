@@ -61,3 +61,39 @@ def test_importing_a_reference_built_index_gives_our_own_blob(tmp_path, seed, nc
     assert imported.tobytes() == ours.tobytes()
     with pytest.raises(genmap_b200.GenmapError):
         genmap_b200.Index.import_reference_blob(str(tmp_path / "nowhere"))
+
+
+@pytest.mark.parametrize("nfiles,sampling", [(1, 10), (3, 7)])
+def test_product_exporter_is_byte_identical_to_reference_index(tmp_path, nfiles, sampling):
+    """`genmap index --reference-format` / gmb_blob_export_reference (the product's writer, seqan_export.cpp) against
+    the reference's own `genmap index` on the same FASTA input: every fibre identical, and the reference maps on it."""
+    import genmap_b200
+    from genmap_b200 import _build
+    cli = _build.build_cli()
+    src = tmp_path / "fasta"
+    src.mkdir()
+    seqs_all = []
+    for f in range(nfiles):
+        seqs = T.repeat_rich(21 + f, 2 + f, 30000 + 777 * f)
+        seqs_all += seqs
+        T.write_fasta(str(src / ("g%02d.fa" % f if nfiles > 1 else "genome.fa")), seqs, names=["f%ds%d extra words" % (f, i) for i in range(len(seqs))])
+    flag = ["-FD", str(src)] if nfiles > 1 else ["-F", str(src / "genome.fa")]
+    ref_dir, our_dir = str(tmp_path / "ref_index"), str(tmp_path / "our_index")
+    subprocess.run([T.REF_BIN, "index"] + flag + ["-I", ref_dir, "-S", str(sampling)], check=True, stdout=subprocess.DEVNULL)
+    r = subprocess.run([cli, "index"] + flag + ["-I", our_dir, "-xh", "-xf", "-S", str(sampling)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    names = sorted(os.listdir(ref_dir))
+    assert set(names) <= set(os.listdir(our_dir))
+    match, mismatch, errors = filecmp.cmpfiles(ref_dir, our_dir, names, shallow=False)
+    assert not mismatch and not errors, (mismatch, errors)
+    out = tmp_path / "out"
+    out.mkdir()
+    subprocess.run([T.REF_BIN, "map", "-I", our_dir, "-O", str(out), "-K", "24", "-E", "1", "-r", "-fl"], check=True, stdout=subprocess.DEVNULL)
+    stf = np.array([f for f in range(nfiles) for _ in range(2 + f)], dtype=np.uint32)
+    orc = T.Oracle(seqs_all, seq_to_file=stf)
+    for f in range(nfiles):
+        got = np.fromfile(str(out / (("g%02d" % f if nfiles > 1 else "genome") + ".genmap.freq16")), dtype=np.uint16)
+        assert np.array_equal(got, orc.map(24, 1, file_no=f))
+    # what the exporter refuses
+    with pytest.raises(genmap_b200.GenmapError):
+        genmap_b200.Index.export_reference_blob(genmap_b200.Index.build_blob(seqs_all, with_sa=False), str(tmp_path / "x"), ["a;1;b"] * len(seqs_all))

@@ -13,5 +13,5 @@ for f in map_kernel locate_kernel exact_kernel block_kernel; do
 done
 wait
 nvcc $COMMON -shared -o genmap_b200/lib/variants/libgenmap_b200_$NAME.so build/variants/$NAME/map_kernel_cu.o build/variants/$NAME/locate_kernel_cu.o build/variants/$NAME/exact_kernel_cu.o build/variants/$NAME/block_kernel_cu.o \
-  build/obj/capi_cu.o build/obj/jump_table_cu.o build/obj/index_build_gpu_cu.o build/obj/gmb_host_cpp.o build/obj/rle_kernel_cu.o
+  build/obj/capi_cu.o build/obj/jump_table_cu.o build/obj/index_build_gpu_cu.o build/obj/gmb_host_cpp.o build/obj/rle_kernel_cu.o build/obj/seqan_export_cpp.o
 echo genmap_b200/lib/variants/libgenmap_b200_$NAME.so
