@@ -22,21 +22,26 @@ def synth_genome(total, nchr, seed, rep_frac=0.05, mut=0.02):
     return out
 
 
-def synth_pangenome(file_bp, n_files, nchr=3, seed=46):
+def synth_pangenome(file_bp, n_files, nchr=3, seed=46, threads=8):
     """BASELINE config 5: n_files FASTA files of nchr sequences; file g = the base genome (frozen generator, `seed`) with
-    g % substitutions.  -> (list of n_files * nchr code arrays in index order, seq_to_file uint32)."""
+    g % substitutions, every (file, sequence) from its own seeded stream so that the files can be made
+    side by side.  -> (list of n_files * nchr code arrays in index order, seq_to_file uint32)."""
+    from concurrent.futures import ThreadPoolExecutor
     base = synth_genome(int(file_bp), nchr, seed)
-    rng = np.random.default_rng(seed + 1)
-    seqs, stf = [], []
-    for g in range(n_files):
-        for s in base:
-            s = s.copy()
-            if g:
-                n_sub = int(len(s) * 0.01 * g)
-                idx = rng.choice(len(s), n_sub, replace=False) if len(s) < 5_000_000 else np.unique(rng.integers(0, len(s), n_sub))
-                s[idx] = (s[idx] + rng.integers(1, 4, len(idx), dtype=np.uint8)) & 3  # a substitution always changes the base
-            seqs.append(s); stf.append(g)
-    return seqs, np.asarray(stf, dtype=np.uint32)
+
+    def one(gc):
+        g, c = gc
+        s = base[c].copy()
+        if g:
+            rng = np.random.default_rng([seed + 1, g, c])
+            idx = rng.integers(0, len(s), int(len(s) * 0.01 * g))  # (a position drawn twice is substituted once)
+            s[idx] = (s[idx] + rng.integers(1, 4, len(idx), dtype=np.uint8)) & 3  # a substitution always changes the base
+        return s
+
+    jobs = [(g, c) for g in range(n_files) for c in range(nchr)]
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as pool:
+        seqs = list(pool.map(one, jobs))
+    return seqs, np.asarray([g for g, _ in jobs], dtype=np.uint32)
 
 
 def write_fasta(path, seqs, width=80):

@@ -23,18 +23,7 @@ import genmap_b200 as gm  # noqa: E402
 
 
 def pangenome(file_mbp, n_files, nchr=3, seed=46):
-    base = gm.synth_genome(int(file_mbp * 1e6), nchr, seed)
-    rng = np.random.default_rng(seed + 1)
-    seqs, stf = [], []
-    for g in range(n_files):
-        for s in base:
-            s = s.copy()
-            if g:
-                idx = rng.choice(len(s), int(len(s) * 0.01 * g), replace=False) if len(s) < 5_000_000 else \
-                    np.unique(rng.integers(0, len(s), int(len(s) * 0.01 * g)))
-                s[idx] = (s[idx] + rng.integers(1, 4, len(idx), dtype=np.uint8)) & 3  # a substitution always changes the base
-            seqs.append(s); stf.append(g)
-    return seqs, np.asarray(stf, dtype=np.uint32)
+    return gm.synth_pangenome(file_mbp * 1e6, n_files, nchr, seed)
 
 
 ap = argparse.ArgumentParser()
