@@ -681,16 +681,22 @@ bool decode_reference_bwt(const std::string& prefix, uint64_t n, uint32_t sigma,
 {
     std::vector<uint8_t> drv, drp;
     if (!slurp(prefix + ".drv", drv) || !slurp(prefix + ".drp", drp)) { err = "cannot read " + prefix + ".drv/.drp"; return false; }
-    const uint32_t bits = sigma == 5 ? 3 : 2, per_word = 64 / bits, entry = 8 + 2 * (sigma - 1);
-    if (drv.size() != (n + per_word - 1) / per_word * entry || drp.size() != (n + 63) / 64 * 10) {
-        err = "unsupported reference index: unexpected size of the rank dictionary (32-bit BWT dimensions expected)";
+    // the block counters behind every word are uint16 in the reference's 32-bit BWT classes and uint32 in its 64-bit
+    // ones (bwt_dimensions:64 — more than 65535 sequences, or a text beyond 2^32; src/indexing.hpp:151-170): entries of
+    // 14 / 20 bytes (Dna4), 16 / 24 bytes (Dna5); the sentinel bit vector's 10 / 12 bytes.  Only the words are read.
+    const uint32_t bits = sigma == 5 ? 3 : 2, per_word = 64 / bits;
+    const uint64_t n_words = (n + per_word - 1) / per_word, n_words2 = (n + 63) / 64;
+    const uint64_t entry = n_words ? drv.size() / n_words : 0, entry2 = n_words2 ? drp.size() / n_words2 : 0;
+    if (n_words == 0 || drv.size() != n_words * entry || drp.size() != n_words2 * entry2 ||
+        (entry != 8 + 2 * (sigma - 1) && entry != 8 + 4 * (sigma - 1)) || (entry2 != 10 && entry2 != 12)) {
+        err = "unsupported reference index: unexpected size of the rank dictionary";
         return false;
     }
     bwt.resize(n);
     for (uint64_t i = 0; i < n; ++i) {
         uint64_t w, s;
         std::memcpy(&w, drv.data() + (i / per_word) * entry, 8);
-        std::memcpy(&s, drp.data() + (i / 64) * 10, 8); // sentinel marker bits, bit k at 63-k
+        std::memcpy(&s, drp.data() + (i / 64) * entry2, 8); // sentinel marker bits, bit k at 63-k
         const uint32_t v = (uint32_t)(w >> ((per_word - 1 - i % per_word) * bits)) & ((1u << bits) - 1u);
         if (v >= sigma) { err = "corrupt rank dictionary in the reference index"; return false; }
         bwt[i] = ((s >> (63 - (i % 64))) & 1u) ? 1 : (uint8_t)(v + 2);
@@ -710,8 +716,11 @@ bool import_reference_index(const std::string& dir, Blob& blob, std::string& err
     const std::string info_s(info.begin(), info.end());
     const uint32_t sigma = info_s.find("alphabet_size:5") != std::string::npos ? 5u : 4u;
     if (sigma == 4 && info_s.find("alphabet_size:4") == std::string::npos) { err = "only Dna4 / Dna5 reference indices can be imported"; return false; }
-    if (info_s.find("bwt_dimensions:32") == std::string::npos || info_s.find("sa_dimensions_i1:16") == std::string::npos) {
-        err = "only the (16,32,32) reference index class can be imported";
+    // every width class of the reference (src/indexing.hpp:151-170: (16,32,32), (16,32,64), (32,16,64), (64,64,64)) as long
+    // as the text fits this layout's 32-bit rows (checked below); the classes differ in the counter widths of the rank
+    // dictionaries (decode_reference_bwt) and in the sampled suffix array, which is not imported
+    if (info_s.find("bwt_dimensions:") == std::string::npos || info_s.find("packed_text:true") == std::string::npos) {
+        err = "not an index written by genmap >= 1.3 (index.info lacks bwt_dimensions / packed_text:true)";
         return false;
     }
     if (!slurp(base + ".txt.limits", limits_raw) || limits_raw.size() < 16 || limits_raw.size() % 8) { err = "cannot read " + base + ".txt.limits"; return false; }

@@ -100,8 +100,9 @@ bool build_index_host(const uint8_t* codes, const uint64_t* limits, uint32_t n_s
 
 // Import an index written by the reference's own `genmap index` (SeqAn fibres index.lf.drv/.drp,
 // index.rev.lf.*, index.txt.*, index.lf.pst; src/genmap_helper.hpp:71-98 lists what `map` opens) into the
-// HBM blob layout, so that pre-built GenMap indices can be used as they are.  Dna4, (16,32,32) index
-// class only; the sampled suffix array is not imported (no --exclude-pseudo on imported indices).
+// HBM blob layout, so that pre-built GenMap indices can be used as they are.  Dna4 and Dna5, every width class of
+// the reference as long as the text has fewer than 2^32 - 1 rows; the sampled suffix array is not imported
+// (no --exclude-pseudo / csv on imported indices).
 bool import_reference_index(const std::string& dir, Blob& blob, std::string& err);
 
 // The reverse (seqan_export.cpp): the reference's own index directory from a blob that holds the suffix array.

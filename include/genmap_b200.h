@@ -118,7 +118,8 @@ int gmb_blob_save(const void *blob, uint64_t bytes, const char *path);
 int gmb_index_open(const char *dir, int device, gmb_index **out);
 /* Convert an index directory written by the reference's own `genmap index` (SeqAn fibres) into a host
  * blob (release with gmb_blob_free).  gmb_index_open does this automatically when <dir>/index.gmb is
- * absent but <dir>/index.lf.drv exists.  Dna4 and Dna5 indices of the default (16,32,32) width class. */
+ * absent but <dir>/index.lf.drv exists.  Dna4 and Dna5 indices of every width class of the reference
+ * (src/indexing.hpp:151-170) with fewer than 2^32 - 1 rows; the sampled suffix array is not imported. */
 int gmb_index_import_reference(const char *dir, void **blob_out, uint64_t *bytes_out);
 /* The reverse: write a host blob that holds the suffix array as an index directory in the reference's own format
  * (<dir>/index.lf.drv, index.sa.val, ...: everything `genmap map` of the reference opens, src/genmap_helper.hpp:71-127),

@@ -14,16 +14,16 @@ t = time.time(); seqs = gm.synth_genome(3_000_000_000, 24, 45); print("genome ge
 t = time.time(); synth.write_fasta("$W/genome.fa", seqs); print("FASTA written in %.1f s" % (time.time() - t), flush=True)
 PY
 ls -la $W/genome.fa
-t0=$(date +%s.%N)
+t0=$(date +%s%N)
 if [ -n "$REF" ]; then $G index -F $W/genome.fa -I $W/index -v -xf; else $G index -F $W/genome.fa -I $W/index -v -xn; fi
-t1=$(date +%s.%N); echo "== genmap index (B200 build): $(echo "$t1 - $t0" | bc) s wall"; ls -la $W/index | head -30
+t1=$(date +%s%N); echo "== genmap index (B200 build): $(( (t1 - t0) / 1000000 )) ms wall"; ls -la $W/index | head -30
 run() { # label, args...
   local label=$1; shift
   rm -rf $W/out; mkdir -p $W/out
-  local a=$(date +%s.%N)
+  local a=$(date +%s%N)
   "$@" | tr '\r' '\n' | grep -v "^Progress\|^File .* Progress" | sed 's/\x1b\[K//g'
-  local b=$(date +%s.%N)
-  echo "== $label: $(echo "$b - $a" | bc) s wall"; ls -la $W/out | tail -n +2 | awk '{print "   ", $5, $9}'
+  local b=$(date +%s%N)
+  echo "== $label: $(( (b - a) / 1000000 )) ms wall"; ls -la $W/out | tail -n +2 | awk '{print "   ", $5, $9}'
 }
 run "genmap map K=30 E=0 -r -fl -bg, $N GPU(s)" $G map -I $W/index -O $W/out -K 30 -E 0 -r -fl -bg -xg $N -v
 run "genmap map K=30 E=0 -bg -w (runs from the device), $N GPU(s)" $G map -I $W/index -O $W/out -K 30 -E 0 -bg -w -xg $N -v

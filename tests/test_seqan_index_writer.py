@@ -97,3 +97,25 @@ def test_product_exporter_is_byte_identical_to_reference_index(tmp_path, nfiles,
     # what the exporter refuses
     with pytest.raises(genmap_b200.GenmapError):
         genmap_b200.Index.export_reference_blob(genmap_b200.Index.build_blob(seqs_all, with_sa=False), str(tmp_path / "x"), ["a;1;b"] * len(seqs_all))
+
+
+@pytest.mark.parametrize("name,tail,with_n", [("32_16_64", 40, False), ("64_64_64", 70000, False), ("64_64_64_dna5", 70000, True)])
+def test_importing_the_reference_other_index_width_classes(tmp_path, name, tail, with_n):
+    """More than 65535 sequences put a reference index into its (32,16,64) or (64,64,64) class (src/indexing.hpp:151-170:
+    uint32 block counters, 64-bit superblocks, wider suffix-array pairs): they import into the same blob our own builder
+    makes, as long as the text has fewer than 2^32 - 1 rows."""
+    import genmap_b200
+    rng = np.random.default_rng(3)
+    seqs = [rng.integers(0, 4, n, dtype=np.uint8) for n in [40] * 69999 + [tail]]
+    if with_n:
+        seqs[5][7] = 4
+        seqs[-1][100:140] = 4
+    fa = str(tmp_path / "g.fa")
+    T.write_fasta(fa, seqs, names=["s%d" % i for i in range(len(seqs))])
+    ref_dir = str(tmp_path / "idx")
+    subprocess.run([T.REF_BIN, "index", "-F", fa, "-I", ref_dir], check=True, stdout=subprocess.DEVNULL)
+    info = open(os.path.join(ref_dir, "index.info.concat")).read()
+    assert "bwt_dimensions:64" in info and ("sa_dimensions_i1:32" in info or "sa_dimensions_i1:64" in info)
+    assert ("alphabet_size:5" in info) == with_n
+    imported = genmap_b200.Index.import_reference_blob(ref_dir)
+    assert imported.tobytes() == genmap_b200.Index.build_blob(seqs, with_sa=False).tobytes()
