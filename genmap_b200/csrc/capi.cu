@@ -2,6 +2,8 @@
 // reference-facing gmb_map_frequencies call.  Host logic only; the device work is map_kernel.cu and
 // index_build_gpu.cu.  No CPU fallback: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -11,6 +13,7 @@
 #include <atomic>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/genmap_b200.h"
@@ -484,22 +487,69 @@ int gmb_index_open(const char* dir, int device, gmb_index** out)
     }
     std::fseek(f, 0, SEEK_END);
     const long long sz = std::ftell(f);
-    std::fseek(f, 0, SEEK_SET);
-    void* host = nullptr;
-    if (sz <= 0 || cudaMallocHost(&host, (size_t)sz) != cudaSuccess) {
-        cudaGetLastError();
-        host = std::malloc(sz > 0 ? (size_t)sz : 1);
-        if (!host) { std::fclose(f); return fail(GMB_ERR_NOMEM, "out of host memory"); }
-        const size_t r = sz > 0 ? std::fread(host, 1, (size_t)sz, f) : 0;
-        std::fclose(f);
-        int rc = (long long)r == sz ? gmb_index_from_blob(host, (uint64_t)sz, device, out) : fail(GMB_ERR_IO, "short read from " + path);
-        std::free(host);
-        return rc;
-    }
-    const size_t r = std::fread(host, 1, (size_t)sz, f);
     std::fclose(f);
-    int rc = (long long)r == sz ? gmb_index_from_blob(host, (uint64_t)sz, device, out) : fail(GMB_ERR_IO, "short read from " + path);
-    cudaFreeHost(host);
+    if (sz < (long long)sizeof(IndexHeader)) return fail(GMB_ERR_IO, "index blob too small: " + path);
+    if (gmb_device_count() <= device || device < 0) return fail(GMB_ERR_CUDA, "no such CUDA device (the map path has no CPU fallback)");
+    // The blob goes file -> HBM through a small ring of pinned buffers filled by reader threads (pread) while earlier
+    // pieces are already on their way to the device: no pinned allocation of the blob's size (15.75 GB with the suffix
+    // array at 3 Gbp: the allocation alone took longer than the search), file reads and H2D copies overlap.
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return fail(GMB_ERR_IO, "cannot open " + path);
+    IndexHeader h;
+    if (::pread(fd, &h, sizeof h, 0) != (ssize_t)sizeof h) { ::close(fd); return fail(GMB_ERR_IO, "short read from " + path); }
+    std::string verr;
+    if (!validate_header(h, (uint64_t)sz, verr)) { ::close(fd); return fail(GMB_ERR_IO, verr); }
+    if (cudaError_t es = cudaSetDevice(device); es != cudaSuccess) { ::close(fd); return cuda_fail(es, "cudaSetDevice"); }
+    gmb_index* ix = new (std::nothrow) gmb_index;
+    if (!ix) { ::close(fd); return fail(GMB_ERR_NOMEM, "out of host memory"); }
+    ix->device = device;
+    ix->h = h;
+    cudaError_t e = cudaMalloc(&ix->d_blob, h.total_bytes);
+    if (e != cudaSuccess) { ::close(fd); delete ix; return cuda_fail(e, "cudaMalloc(index blob)"); }
+    ix->owns_blob = true;
+    constexpr size_t kPiece = 64u << 20;
+    constexpr int kSlots = 4;
+    uint8_t* ring = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t done[kSlots] = {};
+    e = cudaMallocHost(&ring, kPiece * kSlots);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    for (int k = 0; k < kSlots && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming);
+    const uint64_t total = h.total_bytes, n_pieces = (total + kPiece - 1) / kPiece;
+    bool io_error = false;
+    for (uint64_t q0 = 0; q0 < n_pieces && e == cudaSuccess && !io_error; q0 += kSlots) {
+        const int n = (int)std::min<uint64_t>(kSlots, n_pieces - q0);
+        std::vector<std::thread> readers;
+        std::vector<char> bad(n, 0);
+        for (int k = 0; k < n; ++k) {
+            if (q0) { e = cudaEventSynchronize(done[k]); if (e != cudaSuccess) break; } // the slot's previous copy has left it
+            readers.emplace_back([&, k] {
+                const uint64_t off = (q0 + k) * kPiece, len = std::min<uint64_t>(kPiece, total - off);
+                uint64_t got = 0;
+                while (got < len) {
+                    const ssize_t r = ::pread(fd, ring + k * kPiece + got, len - got, (off_t)(off + got));
+                    if (r <= 0) { bad[k] = 1; return; }
+                    got += (uint64_t)r;
+                }
+            });
+        }
+        for (int k = 0; k < (int)readers.size(); ++k) {
+            readers[k].join();
+            if (bad[k]) { io_error = true; continue; }
+            const uint64_t off = (q0 + k) * kPiece, len = std::min<uint64_t>(kPiece, total - off);
+            if (e == cudaSuccess && !io_error) e = cudaMemcpyAsync(ix->d_blob + off, ring + k * kPiece, len, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess && !io_error) e = cudaEventRecord(done[k], st);
+        }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    ::close(fd);
+    for (int k = 0; k < kSlots; ++k) if (done[k]) cudaEventDestroy(done[k]);
+    if (st) cudaStreamDestroy(st);
+    if (ring) cudaFreeHost(ring);
+    if (io_error) { gmb_index_close(ix); return fail(GMB_ERR_IO, "short read from " + path); }
+    if (e != cudaSuccess) { gmb_index_close(ix); return cuda_fail(e, "loading the index blob"); }
+    int rc = finish_open(ix, out);
+    if (rc != GMB_OK) gmb_index_close(ix);
     return rc;
 }
 
