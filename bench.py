@@ -554,14 +554,18 @@ def main():
         # timed index is the one `genmap index --no-sa` builds; the CPU arm builds its own afterwards (index_for_cpu_arm)
         ix = gm.Index.build(seqs, device=local, on_gpu=True, with_sa=args.impl == "reference")
         log("index built on GPU in %.1f s %s, blob %.2f GB" % (time.time() - t0, ix.build_timings_ms, ix.info.blob_bytes / 1e9))
+    bcast_s = 0.0
     if dist is not None:
         from genmap_b200 import parallel
         # the library-owned device blob, viewed as a tensor so NCCL can broadcast it in place
         blob_t = torch.as_tensor(_DeviceBytes(int(ix.info.device_blob), int(ix.info.blob_bytes)), device=dev) if rank == 0 else None
+        dist.barrier()  # (the other ranks have been waiting for rank 0's genome and index: not part of the broadcast)
+        torch.cuda.synchronize()
         t0 = time.time()
         blob_t = parallel.broadcast_blob(blob_t, dist, dev)
         torch.cuda.synchronize()
-        log("rank %d: index broadcast over NCCL in %.2f s" % (rank, time.time() - t0))
+        bcast_s = time.time() - t0
+        log("rank %d: index broadcast over NCCL in %.2f s" % (rank, bcast_s))
         if rank != 0:
             ix = gm.Index.adopt_device(blob_t.data_ptr(), blob_t.numel(), device=local)
     ix.limits = limits
@@ -764,7 +768,8 @@ def main():
                 "warmup": args.warmup, "ms_per_step": main_r["ms"] / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "config": {"workload": workload, "K": K, "E": E, "genome_bp": n_text, "positions_per_step_per_gpu": batch,
-                           "sharding": "positions range-partitioned over %d GPU(s), index replicated (NCCL broadcast)" % world,
+                           "sharding": "positions range-partitioned over %d GPU(s), index replicated (NCCL broadcast%s)"
+                                       % (world, ": %.2f s" % bcast_s if world > 1 else ""),
                            "cache": "inputs larger than L2: %.2f GB index vs 126 MB L2, every step searches different positions"
                                     % index_gb,
                            "hbm_bytes": hbm},

@@ -517,14 +517,23 @@ int map_main(int argc, char const** argv)
         }
     }
 
+    const double t_cuda = wall();
     if (gmb_device_count() == 0) { std::cerr << "ERROR: no CUDA device found: the B200 build of `genmap map` has no CPU fallback.\n"; return 1; }
+    if (a.has("verbose")) std::cout << "CUDA driver initialised in " << round2(wall() - t_cuda) << " seconds\n";
     if ((int)gpu > gmb_device_count()) { std::cerr << "ERROR: --gpus " << gpu << " requested but only " << gmb_device_count() << " CUDA device(s) found.\n"; return 1; }
     std::vector<gmb_index*> ixs(gpu, nullptr); // the index is replicated: one copy in the HBM of every GPU
     const double t_open = wall();
     if (gmb_index_open(index_dir.c_str(), 0, &ixs[0]) != GMB_OK) { std::cerr << "ERROR: " << gmb_last_error() << "\n"; return 1; }
     const double t_repl = wall();
-    for (uint64_t g = 1; g < gpu; ++g) // read once, then GPU-to-GPU copies over NVLink
-        if (gmb_index_replicate(ixs[0], (int)g, &ixs[g]) != GMB_OK) { std::cerr << "ERROR: " << gmb_last_error() << "\n"; return 1; }
+    { // read once, then GPU-to-GPU copies over NVLink, all at once (a CUDA context per device is created on the way)
+        std::vector<std::string> rep_err(gpu);
+        std::vector<std::thread> rep;
+        for (uint64_t g = 1; g < gpu; ++g)
+            rep.emplace_back([&, g] { if (gmb_index_replicate(ixs[0], (int)g, &ixs[g]) != GMB_OK) rep_err[g] = gmb_last_error(); });
+        for (std::thread& t : rep) t.join();
+        for (const std::string& e : rep_err)
+            if (!e.empty()) { std::cerr << "ERROR: " << e << "\n"; return 1; }
+    }
     const double t_loaded = wall();
     gmb_index_info iinfo;
     gmb_index_get_info(ixs[0], &iinfo);
@@ -689,8 +698,12 @@ int map_main(int argc, char const** argv)
         i = j;
     }
     if (a.has("verbose")) std::cout << "Mappability computed in " << round2(wall() - t_start) << " seconds\n";
-    for (gmb_index* ix : ixs) gmb_index_close(ix);
-    return 0;
+    // every output file is closed; the index replicas and their tables (tens of GB per GPU) are not freed one by one:
+    // the process ends here and the driver reclaims them
+    std::cout << std::flush;
+    std::cerr << std::flush;
+    std::fflush(nullptr);
+    std::_Exit(0);
 }
 
 // hidden developer command: render the text/track formats from a raw frequency file (lets the CPU-only
