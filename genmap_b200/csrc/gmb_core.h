@@ -592,7 +592,9 @@ GMB_HD void ep_mark_rows(uint64_t& mask, uint32_t lo, uint32_t n, const MapCtx& 
 //   then kLeafWords for the infix hit being completed (lo_f, lo_r, size),
 //   then, in the blocked instantiation, one counter per window (+ two words of file mask per window under
 //   --exclude-pseudo).
-// Accessors: set/get(level, word) for the mismatch frames, xset/xget(word) for the rest.
+// Accessors: set/get(level, word) for the mismatch frames, xset/xget(word) for the leaf frame; the per-window
+// counters go through cget / cset / cadd (saturating add) / cor, which a kernel may point at ANOTHER chain's store
+// and make atomic (block_kernel.cu: a lane walks a subtree for the chain that owns the block).
 constexpr int kFrameWords = 10;  // SIGMA == 4
 constexpr int kFrameWords5 = 12; // SIGMA == 5
 constexpr int kLeafWords = 3;
@@ -699,7 +701,7 @@ GMB_HD void chain_begin_block(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx
     st.has_n = st.pat.has_n();
     if (BLK) {
         const uint32_t per = EP ? 3u : 1u;
-        for (uint32_t w = 0; w < st.cnt * per; ++w) fr.xset(kLeafWords + w, 0u);
+        for (uint32_t w = 0; w < st.cnt * per; ++w) fr.cset(kLeafWords + w, 0u);
     }
     // the reverse strand's first jump-table entry does not depend on the forward search: request it now so
     // that its latency overlaps the forward strand instead of starting the reverse strand with a stall
@@ -720,8 +722,8 @@ template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
 GMB_HD uint32_t chain_result(const Chain<KW, SIGMA>& st, const Frames& fr, const MapCtx& cx, uint32_t w)
 {
     if (!BLK) return st.acc;
-    if (!EP) return fr.xget(kLeafWords + w);
-    const uint64_t m = (uint64_t)fr.xget(kLeafWords + st.cnt + 2 * w) | ((uint64_t)fr.xget(kLeafWords + st.cnt + 2 * w + 1) << 32);
+    if (!EP) { const uint32_t v = fr.cget(kLeafWords + w); return v < cx.maxv ? v : cx.maxv; }
+    const uint64_t m = (uint64_t)fr.cget(kLeafWords + st.cnt + 2 * w) | ((uint64_t)fr.cget(kLeafWords + st.cnt + 2 * w + 1) << 32);
 #if defined(__CUDA_ARCH__)
     return (uint32_t)__popcll(m);
 #else
@@ -764,17 +766,20 @@ GMB_HD void chain_count(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, uint
     }
     const uint32_t widx = !BLK ? 0u : (st.strand ? st.cnt - 1u - w : w); // reverse-strand windows run backwards (src/algo.hpp:304)
     if (EP) {
-        uint64_t m = !BLK ? st.files
-                          : (uint64_t)fr.xget(kLeafWords + st.cnt + 2 * widx) | ((uint64_t)fr.xget(kLeafWords + st.cnt + 2 * widx + 1) << 32);
+        const uint32_t at = kLeafWords + st.cnt + 2 * widx;
+        const uint64_t before = !BLK ? st.files : (uint64_t)fr.cget(at) | ((uint64_t)fr.cget(at + 1) << 32);
+        uint64_t m = before;
         if (own_only) m |= 1ull << cx.own_file;
         else ep_mark_rows(m, lo, n, cx);
         if (!BLK) st.files = m;
-        else { fr.xset(kLeafWords + st.cnt + 2 * widx, (uint32_t)m); fr.xset(kLeafWords + st.cnt + 2 * widx + 1, (uint32_t)(m >> 32)); }
+        else if (m != before) { fr.cor(at, (uint32_t)(m & ~before)); fr.cor(at + 1, (uint32_t)((m & ~before) >> 32)); }
     } else {
-        const uint32_t old = !BLK ? st.acc : fr.xget(kLeafWords + widx);
-        const uint64_t sum = (uint64_t)old + n;
-        const uint32_t v = sum < cx.maxv ? (uint32_t)sum : cx.maxv; // saturating (src/algo.hpp:48,191)
-        if (!BLK) st.acc = v; else fr.xset(kLeafWords + widx, v);
+        if (!BLK) {
+            const uint64_t sum = (uint64_t)st.acc + n;
+            st.acc = sum < cx.maxv ? (uint32_t)sum : cx.maxv; // saturating (src/algo.hpp:48,191)
+        } else {
+            fr.cadd(kLeafWords + widx, n, cx.maxv);
+        }
     }
 }
 
@@ -808,8 +813,8 @@ GMB_HD void chain_mark_file(Chain<KW, SIGMA>& st, Frames& fr, uint32_t w, uint32
     const uint32_t widx = !BLK ? 0u : (st.strand ? st.cnt - 1u - w : w);
     if (!BLK) { st.files |= 1ull << file; return; }
     const uint32_t at = kLeafWords + st.cnt + 2 * widx;
-    if (file < 32u) fr.xset(at, fr.xget(at) | (1u << file));
-    else fr.xset(at + 1, fr.xget(at + 1) | (1u << (file - 32u)));
+    if (file < 32u) fr.cor(at, 1u << file);
+    else fr.cor(at + 1, 1u << (file - 32u));
 }
 
 // The current search of the chain was entered through a LOCATED entry (see JtFull): the key of the entry occurs once

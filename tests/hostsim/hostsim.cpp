@@ -22,6 +22,10 @@ struct HostFrames {
     inline uint32_t get(uint32_t lv, uint32_t i) const { return w[lv][i]; }
     inline void xset(uint32_t i, uint32_t v) { x[i] = v; }
     inline uint32_t xget(uint32_t i) const { return x[i]; }
+    inline void cset(uint32_t i, uint32_t v) { x[i] = v; }
+    inline uint32_t cget(uint32_t i) const { return x[i]; }
+    inline void cadd(uint32_t i, uint32_t n, uint32_t maxv) { const uint64_t sum = (uint64_t)x[i] + n; x[i] = sum < maxv ? (uint32_t)sum : maxv; }
+    inline void cor(uint32_t i, uint32_t bits) { x[i] |= bits; }
 };
 
 template <int KW, bool EP, bool BLK, int SIGMA>
@@ -59,7 +63,7 @@ void run_ranges_blockdriver(const MapCtx& cx, const KeyLists& kl, const uint64_t
             const uint32_t cnt = (uint32_t)std::min<uint64_t>(cx.B, r.end - j0), NL = cx.K + cnt - 1;
             st.cnt = cnt;
             load_pattern(st.pat, text, nullptr, text_begin + j0, NL);
-            for (uint32_t w = 0; w < cnt * (EP ? 3u : 1u); ++w) fr.xset(kLeafWords + w, 0u);
+            for (uint32_t w = 0; w < cnt * (EP ? 3u : 1u); ++w) fr.cset(kLeafWords + w, 0u);
             for (uint32_t strand = 0; strand < cx.n_strands; ++strand) {
                 st.strand = strand;
                 if (strand == 1) st.pat.reverse_complement(NL);
