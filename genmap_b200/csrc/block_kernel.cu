@@ -16,12 +16,12 @@
 //               prepared (search, substituted characters as an XOR mask, errors): four entries requested back to back,
 //               then looked at — empty: nothing; located: compared on the spot; else: the entry is put aside
 //               (8 per chain in shared memory; beyond that a bit remembers the key and the entry is read again);
-//   walk phase  the entries the warp put aside are ONE task list (owner lane, slot) in shared memory, dealt out round
-//               robin: every lane walks the subtrees below its share with the state machine of gmb_core.h in subtree
-//               mode (chain_step<..., SUB>) — for the chain that owns the block: the owner's needle is read from
-//               shared memory, occurrences are added to the owner's window counters with shared-memory atomics —
-//               until no lane has a task left.  (Without the sharing a lane walked only its own entries: their number
-//               varies like a Poisson variable and 13 of 32 lanes were active.)
+//   walk phase  every lane walks the subtrees below the entries it put aside with the state machine of gmb_core.h
+//               in subtree mode (chain_step<..., SUB>), until no lane has one left.
+// (Tried and rejected: dealing the warp's put-aside entries out round robin, walking for the owning chain through a
+// shared-memory copy of its needle and atomic window counters — balanced task counts, but E = 1 17.7 -> 28.5 ms and
+// E = 2 22.2 -> 32.8 ms: profiles/r02/s8_sweep_shared_walk_rejected.txt; the frame store keeps the counter accessors
+// that experiment introduced.)
 // One chain = one block of up to B adjacent k-mer starts, as in the general kernel (same step tables, same frame
 // store); a warp takes 32 blocks per global atomic.
 #include "map_kernel_impl.cuh"
@@ -33,7 +33,6 @@ namespace {
 constexpr uint32_t kPendSlots = 8;      // entries a chain can put aside per round
 constexpr uint32_t kPendWords = 4;      // lo_r, size, lo_f, key index
 constexpr uint32_t kRound = 32;         // keys per round (one overflow bit each)
-constexpr uint32_t kPatWords = 5;       // needle of the current strand (2 x 64 bits) + k-mers in the block, per chain
 #ifndef GMB_KEY_BATCH
 #define GMB_KEY_BATCH 4
 #endif
@@ -53,8 +52,6 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
     uint32_t* offs_s = starts_s + align32(n_start_words);
     uint32_t* frames_s = offs_s + align32(2 * (kMaxBlockKmers + 1));
     uint32_t* pend_s = frames_s + frame_store_words(L.E, L.cx.B, EP, 4, true) * kThreads + threadIdx.x;
-    uint32_t* pat_s = pend_s - threadIdx.x + kPendSlots * kPendWords * kThreads;   // per chain: needle words of the strand, cnt
-    uint16_t* task_s = reinterpret_cast<uint16_t*>(pat_s + kPatWords * kThreads) + (threadIdx.x >> 5) * (32 * kPendSlots); // per warp
     for (uint32_t i = threadIdx.x; i < L.n_step_words; i += kThreads) steps_s[i] = L.cx.steps[i];
     for (uint32_t i = threadIdx.x; i < n_start_words; i += kThreads) starts_s[i] = reinterpret_cast<const uint32_t*>(L.cx.starts)[i];
     if (threadIdx.x == 0) {
@@ -71,9 +68,7 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
     cx.starts = reinterpret_cast<const SearchStart*>(starts_s);
     cx.p1_off = offs_s;
     cx.fl_off = offs_s + kMaxBlockKmers + 1;
-    SmemFrames<(int)frame_words(4), true> fr{frames_s + threadIdx.x, L.E * frame_words(4), frames_s + threadIdx.x};
-    uint32_t* const own_counters = frames_s + threadIdx.x;
-    const unsigned warp_col0 = threadIdx.x & ~31u; // column of lane 0 of this warp in the thread-strided stores
+    SmemFrames<(int)frame_words(4)> fr{frames_s + threadIdx.x, L.E * frame_words(4), frames_s + threadIdx.x};
     using Frames = decltype(fr);
 
     const unsigned lane = threadIdx.x & 31u;
@@ -116,15 +111,6 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
                 st.strand = strand;
                 if (strand == 1) st.pat.reverse_complement(NL);
             }
-            // the strand's needle where the other lanes of the warp can read it
-#pragma unroll
-            for (int k = 0; k < KW; ++k) {
-                pat_s[(2 * k) * kThreads + threadIdx.x] = (uint32_t)st.pat.w[k];
-                pat_s[(2 * k + 1) * kThreads + threadIdx.x] = (uint32_t)(st.pat.w[k] >> 32);
-            }
-            pat_s[4 * kThreads + threadIdx.x] = cnt;
-            st.strand = strand; // (idle lanes walk for others too)
-            __syncwarp();
             const uint32_t nk_max = __reduce_max_sync(0xffffffffu, nk);
             for (uint32_t g0 = 0; g0 < nk_max; g0 += kRound) {
                 // ---- key phase: the next kRound keys of every lane's block ----------------------------------------
@@ -162,68 +148,35 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
                         }
                     }
                 }
-                // ---- walk phase: the warp's entries as one task list, dealt out round robin -------------------------------
-                uint32_t incl = n_pend;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= (unsigned)o) incl += v;
-                }
-                const uint32_t n_tasks = __shfl_sync(0xffffffffu, incl, 31);
-                for (uint32_t k = 0; k < n_pend; ++k) task_s[incl - n_pend + k] = (uint16_t)(lane | (k << 5));
-                __syncwarp();
-                {
-                    uint32_t t = lane;
-                    bool walking = false;
-                    for (;;) {
-                        if (!walking && t < n_tasks) {
-                            const uint32_t task = task_s[t];
-                            t += 32;
-                            const unsigned col = warp_col0 + (task & 31u); // the owner's column
-                            const uint32_t* p = pend_s - threadIdx.x + col + (task >> 5) * kPendWords * kThreads;
-                            st.lo_r = p[0]; st.size = p[kThreads]; st.lo_f = p[2 * kThreads];
-                            const uint32_t gi = p[3 * kThreads];
-#pragma unroll
-                            for (int k = 0; k < KW; ++k)
-                                st.pat.w[k] = (uint64_t)pat_s[(2 * k) * kThreads + col] | ((uint64_t)pat_s[(2 * k + 1) * kThreads + col] << 32);
-                            st.cnt = pat_s[4 * kThreads + col];
-                            fr.cbase = frames_s + col;
-                            const uint2 ke = __ldg(keys + L.key_off[st.cnt] + gi);
+                // ---- walk phase: the subtrees below the entries put aside ------------------------------------------
+                bool walking = false;
+                for (;;) {
+                    if (!walking && (n_pend | over)) {
+                        uint32_t gi;
+                        if (n_pend) {
+                            --n_pend;
+                            const uint32_t* p = pend_s + n_pend * kPendWords * kThreads;
+                            st.lo_r = p[0]; st.size = p[kThreads]; st.lo_f = p[2 * kThreads]; gi = p[3 * kThreads];
+                            const uint2 ke = __ldg(keys + koff + gi);
                             st.s = ke.y & 7u; st.e = (ke.y >> 4) & 7u;
-                            st.t = cx.starts[st.cnt * kMaxSearches + st.s].d;
-                            st.lvmask = 0; st.win = kNoWin; st.leaf_e = 0; st.thin = false;
-                            walking = true;
+                            st.t = cx.starts[cnt * kMaxSearches + st.s].d;
+                        } else {
+                            gi = g0 + lowest_bit_index(over);
+                            over &= over - 1u;
+                            const uint2 ke = __ldg(keys + koff + gi);
+                            st.s = ke.y & 7u; st.e = (ke.y >> 4) & 7u;
+                            const SearchStart& S = cx.starts[cnt * kMaxSearches + st.s];
+                            uint32_t pad;
+                            jump_lookup(S, st.pat.bits(S.a, S.d) ^ ke.x, st.lo_f, st.lo_r, st.size, pad);
+                            st.t = S.d;
+                            if (COUNT) ++lut_reads;
                         }
-                        if (!__any_sync(0xffffffffu, walking)) break;
-                        if (walking)
-                            walking = chain_step<KW, EP, true, 4, Frames, false, true>(st, fr, cx, COUNT ? &fetches : nullptr, nullptr);
-                    }
-                }
-                __syncwarp();
-                // back to this lane's own block
-#pragma unroll
-                for (int k = 0; k < KW; ++k)
-                    st.pat.w[k] = (uint64_t)pat_s[(2 * k) * kThreads + threadIdx.x] | ((uint64_t)pat_s[(2 * k + 1) * kThreads + threadIdx.x] << 32);
-                st.cnt = cnt;
-                fr.cbase = own_counters;
-                // entries that did not fit (rare): read again and walked by their own lane
-                while (__any_sync(0xffffffffu, over != 0u)) {
-                    bool walking = false;
-                    if (over) {
-                        const uint32_t gi = g0 + lowest_bit_index(over);
-                        over &= over - 1u;
-                        const uint2 ke = __ldg(keys + koff + gi);
-                        st.s = ke.y & 7u; st.e = (ke.y >> 4) & 7u;
-                        const SearchStart& S = cx.starts[cnt * kMaxSearches + st.s];
-                        uint32_t pad;
-                        jump_lookup(S, st.pat.bits(S.a, S.d) ^ ke.x, st.lo_f, st.lo_r, st.size, pad);
-                        st.t = S.d;
-                        if (COUNT) ++lut_reads;
                         st.lvmask = 0; st.win = kNoWin; st.leaf_e = 0; st.thin = false;
                         walking = true;
                     }
-                    while (__any_sync(0xffffffffu, walking))
-                        if (walking) walking = chain_step<KW, EP, true, 4, Frames, false, true>(st, fr, cx, COUNT ? &fetches : nullptr, nullptr);
+                    if (!__any_sync(0xffffffffu, walking)) break;
+                    if (walking)
+                        walking = chain_step<KW, EP, true, 4, Frames, false, true>(st, fr, cx, COUNT ? &fetches : nullptr, nullptr);
                 }
             }
         }
@@ -279,8 +232,7 @@ cudaError_t launch_blk_kw(const MapLaunch& L, int sm_count, cudaStream_t stream)
 size_t block_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool ep)
 {
     const size_t tables = align32(n_step_words) + align32((B + 1) * kMaxSearches * kStartWords) + align32(2 * (kMaxBlockKmers + 1));
-    return (tables + ((size_t)frame_store_words(E, B, ep, 4, true) + kPendSlots * kPendWords + kPatWords) * kThreads) * sizeof(uint32_t) +
-           (kThreads / 32) * (32 * kPendSlots) * sizeof(uint16_t);
+    return (tables + ((size_t)frame_store_words(E, B, ep, 4, true) + kPendSlots * kPendWords) * kThreads) * sizeof(uint32_t);
 }
 
 bool block_kernel_applies(const MapLaunch& L)
