@@ -237,9 +237,9 @@ size_t block_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bo
 
 bool block_kernel_applies(const MapLaunch& L)
 {
-    // (E >= 3: walks dominate and the general kernel, whose lanes refill one by one, is still the faster of the two:
-    // profiles/r02/s4_sweep_{general,block}.txt)
-    return L.keylist != nullptr && L.sigma == 4 && L.E >= 1 && (L.E <= 2 || L.force_block_kernel) && L.cx.K + L.cx.B - 1 <= 64 && L.cx.loc_rows == nullptr && L.loc_off == nullptr &&
+    // (E = 3: walks dominate and the general kernel, whose lanes refill one by one, is still the faster of the two, 16.5 vs
+    // 18.7 ms; E = 4, with seven searches and 4000 keys per position, is 2.7x faster here: profiles/r02/s9_sweep_*.txt)
+    return L.keylist != nullptr && L.sigma == 4 && L.E >= 1 && (L.E != 3 || L.force_block_kernel) && L.cx.K + L.cx.B - 1 <= 64 && L.cx.loc_rows == nullptr && L.loc_off == nullptr &&
            !(L.exclude_pseudo && L.count_fetches);
 }
 

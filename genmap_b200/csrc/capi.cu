@@ -839,7 +839,7 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
     // whole blocks per work chunk; the two-phase kernel hands a warp one block per lane
     const char* blk_env = std::getenv("GMB_BLOCK_KERNEL"); // "0": never, "2": also for E >= 3 (measurements)
     const bool force_block = blk_env && blk_env[0] == '2';
-    const bool block_kernel = plan->d_keys != nullptr && (p->E <= 2 || force_block) &&
+    const bool block_kernel = plan->d_keys != nullptr && (p->E != 3 || force_block) &&
                               block_kernel_smem_bytes((uint32_t)tabs.steps.size(), p->E, tabs.B, p->exclude_pseudo != 0) <= (200u << 10);
     const uint64_t chunk = block_kernel ? 32ull * tabs.B : std::max<uint64_t>(tabs.B, kChunk / tabs.B * tabs.B);
     std::vector<uint64_t> host_ranges(3 * (size_t)nr + 1); // begin[nr], end[nr], chunk_prefix[nr+1]
