@@ -660,7 +660,10 @@ static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool l
     std::snprintf(buf, sizeof buf, "%u/%u/%u/%d/%d/%d/%llu/", p->K, p->E, want_b, sync_tables ? 1 : 0, loc ? 1 : 0, want,
                   (unsigned long long)model_n);
     const char* e4 = std::getenv("GMB_LOCATE");
-    const std::string key = std::string(buf) + (e1 ? e1 : "") + "/" + (e2 ? e2 : "") + "/" + (e3 ? e3 : "") + "/" + (e4 ? e4 : "");
+    const char* e5 = std::getenv("GMB_BLOCK_KERNEL");
+    const char* e6 = std::getenv("GMB_EXACT_KERNEL");
+    const std::string key = std::string(buf) + (e1 ? e1 : "") + "/" + (e2 ? e2 : "") + "/" + (e3 ? e3 : "") + "/" + (e4 ? e4 : "") + "/" +
+                            (e5 ? e5 : "") + "/" + (e6 ? e6 : "");
     MapPlan* plan = nullptr;
     for (auto& q : ix->plans)
         if (q->key == key) plan = q.get();

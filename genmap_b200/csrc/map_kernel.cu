@@ -1,12 +1,14 @@
-// map_kernel.cu — the (K,E)-frequency kernel for sm_100a.
+// map_kernel.cu — the GENERAL (K,E)-frequency kernel for sm_100a: every configuration the two specialised kernels do
+// not take (exact_kernel.cu: E = 0; block_kernel.cu: E = 1, 2, 4 — both Dna4, needle <= 64): E = 3, Dna5 indices, K > 64,
+// jump tables switched off; its locate instantiation serves the csv lists (locate_kernel.cu).
 //
 // Replaces the reference's per-position loop computeMappability -> computeMappabilitySingleBlock
 // (src/algo.hpp:221-483) and its search-scheme matcher (src/find2_index_approx.hpp:223-457).
 //
 // Mapping to the machine:
-//   * one CUDA thread = one "chain" = one k-mer start at a time; a chain is a strictly dependent series
-//     of random 64-byte rank-block reads, so throughput comes from the number of chains in flight
-//     (148 SMs x 1024 resident threads ~ 150 k independent 64-B requests), not from intra-chain width.
+//   * one CUDA thread = one "chain" = one block of k-mer starts at a time; a chain is a strictly dependent series
+//     of random 32-byte rank-block reads, so throughput comes from the number of chains in flight
+//     (148 SMs x 768-1024 resident threads), not from intra-chain width.
 //   * each loop iteration is one node expansion of gmb_core.h::chain_step — the same code for every
 //     chain whatever its depth, error level or search, so warps stay converged although every lane
 //     walks a different subtree.

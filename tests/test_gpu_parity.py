@@ -610,3 +610,33 @@ def test_cuda_250mbp_whole_file_is_bit_exact_against_the_reference(gm):
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
         _close(ix)
+
+
+@pytest.mark.parametrize("with_sa", [False, True], ids=["counts", "exclude_pseudo"])
+def test_cuda_three_kernels_and_table_flavours_agree(gm, monkeypatch, with_sa):
+    """The straight-line E = 0 kernel, the two-phase kernel and the general kernel, with and without located table
+    entries, give the same vector (and the oracle's) — also under --exclude-pseudo, with uint8 counts and -nc."""
+    seqs = gm.synth_genome(300_000, 3, 31)
+    seqs[1][5000:5600] = seqs[0][1000:1600]                      # a planted exact repeat
+    seqs[2][100:900] = (3 - seqs[0][2000:2800])[::-1]            # and a reverse-complemented one
+    stf = np.array([0, 1, 1], dtype=np.uint32) if with_sa else None
+    _, limits = T.concat(seqs)
+    ix = gm.Index.build(seqs, with_sa=with_sa, seq_to_file=stf)
+    ix.set_plan_text_size(3_000_000_024)  # deep tables, substituted keys: the plan of the bench genome
+    orc = T.Oracle(seqs, seq_to_file=stf)
+    knobs = [{}, {"GMB_LOCATE": "0"}, {"GMB_BLOCK_KERNEL": "0", "GMB_EXACT_KERNEL": "0"}, {"GMB_BLOCK_KERNEL": "0", "GMB_EXACT_KERNEL": "0", "GMB_LOCATE": "0"},
+             {"GMB_BLOCK_KERNEL": "2"}]
+    try:
+        for K, E, rc, bits in [(30, 0, True, 16), (30, 1, True, 16), (30, 2, True, 8), (24, 3, False, 16), (31, 1, False, 16), (40, 2, True, 16)]:
+            fi = 1 if with_sa else 0
+            stf_, tb, tl, cum, _ = T._prep(limits, stf, fi, None)
+            want = orc.map(K, E, revcompl=rc, exclude_pseudo=with_sa, value_bits=bits, file_no=fi)
+            for env in knobs:
+                for k in ("GMB_LOCATE", "GMB_BLOCK_KERNEL", "GMB_EXACT_KERNEL"):
+                    monkeypatch.delenv(k, raising=False)
+                for k, v in env.items():
+                    monkeypatch.setenv(k, v)
+                got = ix.compute_mappability(gm.SearchParams(K, E, rc, with_sa, bits), text_begin=tb, text_len=tl, chrom_cum_lengths=cum)
+                assert np.array_equal(got, want), (K, E, rc, bits, env, np.nonzero(got != want)[0][:10])
+    finally:
+        _close(ix)
