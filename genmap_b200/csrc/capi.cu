@@ -98,6 +98,7 @@ struct gmb_index {
     JtEntry* jt_uni[17] = {};
     uint32_t* jt_lof[17] = {};
     JtFull* jt_full[17] = {};    // both intervals per entry (searches that need the interval in SA(T) after the jump)
+    bool jt_full_located[17] = {}; // ... with the entries of keys that occur once rewritten as LOCATED entries
     uint64_t jt_epoch = 0;       // bumped whenever a jump table is freed: cached plans holding its address are re-made
     uint64_t plan_n = 0;         // plan the searches as if the text had this many symbols (0 = the index's own n_bwt)
     // search plans by configuration (tables on the device, ready to launch): a map call of a configuration seen
@@ -239,8 +240,13 @@ cudaError_t jt_alloc(gmb_index* ix, const JumpNeeds& n, T** p, size_t bytes)
 int ensure_jump_tables(gmb_index* ix, const JumpNeeds& n, cudaStream_t stream)
 {
     uint32_t top = 0;
-    for (uint32_t d = 1; d <= 16; ++d)
+    const bool want_located = ix->h.sigma == 4 && locate_enabled();
+    for (uint32_t d = 1; d <= 16; ++d) {
+        if (n.full[d] && ix->jt_full[d] && ix->jt_full_located[d] != want_located) { // built for the other setting of GMB_LOCATE
+            cudaFree(ix->jt_full[d]); ix->jt_full[d] = nullptr; ++ix->jt_epoch;
+        }
         if ((n.uni[d] && !ix->jt_uni[d]) || (n.lof[d] && !ix->jt_lof[d]) || (n.full[d] && !ix->jt_full[d])) top = d;
+    }
     if (top == 0) return GMB_OK; // everything this call needs is cached
     MapCtx cx;
     fill_ctx(ix, cx);
@@ -263,7 +269,8 @@ int ensure_jump_tables(gmb_index* ix, const JumpNeeds& n, cudaStream_t stream)
             cudaError_t err = jt_alloc(ix, n, &ix->jt_full[d], e * sizeof(JtFull));
             if (err == cudaSuccess)
                 err = build_jump_level(cx, ix->h.sigma, d, ix->jt_uni[d - 1], ix->jt_lof[d - 1], nullptr, nullptr, ix->jt_full[d], stream);
-            if (err == cudaSuccess && ix->h.sigma == 4 && locate_enabled()) // keys that occur once: position + context instead of intervals
+            ix->jt_full_located[d] = want_located;
+            if (err == cudaSuccess && want_located) // keys that occur once: position + context instead of intervals
                 err = locate_jump_singletons(reinterpret_cast<const uint64_t*>(ix->d_blob + ix->h.off_text), ix->h.n_text, cx.seq_start,
                                              ix->h.n_seq, d, ix->jt_full[d], stream);
             if (err != cudaSuccess) return cuda_fail(err, "jump table");
