@@ -33,13 +33,10 @@ namespace {
 #ifndef GMB_PEND_SLOTS
 #define GMB_PEND_SLOTS 8
 #endif
-#ifndef GMB_ROUND
-#define GMB_ROUND 32
-#endif
 constexpr uint32_t kPendSlots = GMB_PEND_SLOTS; // entries a chain can put aside per round
 constexpr uint32_t kPendWords = 4;      // lo_r, size, lo_f, key index
-constexpr uint32_t kRound = GMB_ROUND;  // keys per round (one overflow bit each): 32 or 64
-static_assert(kRound == 32 || kRound == 64, "one overflow bit per key of a round");
+constexpr uint32_t kRound = 32;         // keys per round (one overflow bit each; 64 with a 64-bit mask and 16 slots: slower,
+                                        // 22.6 vs 17.8 ms at E = 1 — profiles/r02/s11_sweep_round64.txt)
 #ifndef GMB_KEY_BATCH
 #define GMB_KEY_BATCH 4
 #endif
@@ -121,8 +118,7 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
             const uint32_t nk_max = __reduce_max_sync(0xffffffffu, nk);
             for (uint32_t g0 = 0; g0 < nk_max; g0 += kRound) {
                 // ---- key phase: the next kRound keys of every lane's block ----------------------------------------
-                uint32_t n_pend = 0;  // entries put aside
-                uint64_t over = 0;    // keys whose entry did not fit (read again below)
+                uint32_t n_pend = 0, over = 0; // entries put aside; keys whose entry did not fit (read again below)
                 const uint32_t g1 = g0 + kRound < nk ? g0 + kRound : nk;
                 for (uint32_t g = g0; g < g1; g += kKeyBatch) {
                     uint32_t e0[kKeyBatch], e1[kKeyBatch], e2[kKeyBatch], e3[kKeyBatch], key[kKeyBatch], meta[kKeyBatch];
@@ -152,14 +148,14 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
                             p[0] = e0[u]; p[kThreads] = e1[u]; p[2 * kThreads] = e2[u]; p[3 * kThreads] = g + u;
                             ++n_pend;
                         } else {
-                            over |= 1ull << (g + u - g0);
+                            over |= 1u << (g + u - g0);
                         }
                     }
                 }
                 // ---- walk phase: the subtrees below the entries put aside ------------------------------------------
                 bool walking = false;
                 for (;;) {
-                    if (!walking && (n_pend != 0u || over != 0ull)) {
+                    if (!walking && (n_pend | over)) {
                         uint32_t gi;
                         if (n_pend) {
                             --n_pend;
@@ -169,8 +165,8 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
                             st.s = ke.y & 7u; st.e = (ke.y >> 4) & 7u;
                             st.t = cx.starts[cnt * kMaxSearches + st.s].d;
                         } else {
-                            gi = g0 + (uint32_t)__ffsll((long long)over) - 1u;
-                            over &= over - 1ull;
+                            gi = g0 + lowest_bit_index(over);
+                            over &= over - 1u;
                             const uint2 ke = __ldg(keys + koff + gi);
                             st.s = ke.y & 7u; st.e = (ke.y >> 4) & 7u;
                             const SearchStart& S = cx.starts[cnt * kMaxSearches + st.s];

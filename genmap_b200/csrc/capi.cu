@@ -987,7 +987,7 @@ int gmb_map_frequencies_range(gmb_index* ix, const gmb_params* p, uint64_t text_
     void* biased = reinterpret_cast<void*>(reinterpret_cast<uintptr_t>(ix->d_out) - (uintptr_t)pos_begin * elem);
     gmb_map_stats local;
     std::memset(&local, 0, sizeof(local));
-    const uint64_t piece = 32ull << 20; // positions per pipeline stage
+    const uint64_t piece = 16ull << 20; // positions per pipeline stage (the copy of the last piece is not overlapped: keep it short)
     bool many_files = false; // --exclude-pseudo beyond 64 files runs unpipelined on the default stream (ep_many_files)
     if (p->exclude_pseudo && seq_to_file)
         for (uint32_t s2 = 0; s2 < n_seq && !many_files; ++s2) many_files = seq_to_file[s2] >= 64;
