@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
                             st.s = meta[u] & 7u;
                             const SearchStart& S = cx.starts[cnt * kMaxSearches + st.s];
                             verify_located_key<KW, EP, true, 4, Frames>(st, fr, cx, COUNT ? &fetches : nullptr, S, key[u],
-                                                                        (meta[u] >> 8) & 1u, e0[u], e1[u], e2[u], e3[u]);
+                                                                        (meta[u] >> 8) & 1u, e0[u], e2[u], e3[u]);
                         } else if (n_pend < kPendSlots) {
                             uint32_t* p = pend_s + n_pend * kPendWords * kThreads;
                             p[0] = e0[u]; p[kThreads] = e1[u]; p[2 * kThreads] = e2[u]; p[3 * kThreads] = g + u;

@@ -54,26 +54,6 @@ __device__ __forceinline__ uint32_t walk_exact(const Pattern<KW, 4>& P, uint32_t
     return size;
 }
 
-// does the text hold the K characters of P at position q, inside one sequence?  (one read of the packed text; the
-// index never matches across a sentinel, so the sequence limits are checked when the characters agree)
-template <int KW, bool COUNT>
-__device__ __forceinline__ uint32_t occurs_at(const Pattern<KW, 4>& P, uint32_t q, uint32_t K, const MapLaunch& L, ExactCounters& ctr)
-{
-    if (COUNT) ++ctr.text_reads;
-    Pattern<KW, 4> tp;
-    load_pattern(tp, L.cx.text, nullptr, (uint64_t)q, K);
-    bool same = true;
-#pragma unroll
-    for (int k = 0; k < KW; ++k) same = same && tp.w[k] == P.w[k];
-    if (!same) return 0u;
-    uint32_t a = 0, b = L.cx.n_seq;
-    while (b - a > 1) {
-        const uint32_t mid = (a + b) >> 1;
-        if ((uint64_t)__ldg(L.cx.seq_start + mid) - mid <= (uint64_t)q) a = mid; else b = mid;
-    }
-    return (uint64_t)q + K <= (uint64_t)__ldg(L.cx.seq_start + a + 1) - (a + 1) ? 1u : 0u;
-}
-
 template <int KW, bool COUNT, typename OutT>
 __global__ void __launch_bounds__(kThreadsE0, GMB_EXACT_MINB) exact_kernel(const MapLaunch L)
 {
@@ -121,40 +101,39 @@ __global__ void __launch_bounds__(kThreadsE0, GMB_EXACT_MINB) exact_kernel(const
             uint32_t count = 0;
             // ---- forward strand: the query occurs in the text, so its key does ---------------------------------
             if (f1 & kLocated) {
+                count = 1; // the key's only occurrence is the query itself
                 if (COUNT) ++ctr.located;
-                count = 1; // one occurrence of the key is the query itself
-                if (f1 != (kLocated | 1u)) { // the key occurs twice: the other occurrence is compared with the text
-                    const uint32_t own = (uint32_t)(L.text_begin + j);
-                    count += occurs_at<KW, COUNT>(pat, f0 == own ? f2 : f0, K, L, ctr);
-                }
             } else {
                 const uint32_t n = walk_exact<KW, COUNT>(pat, d, K, f0, f1, true, Brev, SPrev, C, ctr);
                 count = n; // 1 when the walk stopped at the query's own row
             }
             // ---- reverse strand ------------------------------------------------------------------------------------
             if (both && r1 != 0u) {
-                if (r1 == (kLocated | 1u)) {
+                if (r1 & kLocated) {
                     if (COUNT) ++ctr.located;
                     const uint32_t q = r0; // text position of the key's only occurrence
+                    bool same;
                     if (K - d <= kCtx) { // the entry's right context holds the rest of the k-mer
                         const uint32_t rest = K - d;
                         const uint32_t want = rest ? rc.bits(d, rest) : 0u;
                         const uint32_t have = rest == 16u ? r2 : (r2 & ((1u << (2u * rest)) - 1u));
-                        if (want == have) { // inside one sequence?  (the index never matches across a sentinel)
-                            uint32_t a = 0, b = L.cx.n_seq;
-                            while (b - a > 1) {
-                                const uint32_t mid = (a + b) >> 1;
-                                if ((uint64_t)__ldg(L.cx.seq_start + mid) - mid <= (uint64_t)q) a = mid; else b = mid;
-                            }
-                            if ((uint64_t)q + K <= (uint64_t)__ldg(L.cx.seq_start + a + 1) - (a + 1)) count += 1;
-                        }
+                        same = want == have;
                     } else {
-                        count += occurs_at<KW, COUNT>(rc, q, K, L, ctr);
+                        if (COUNT) ++ctr.text_reads;
+                        Pattern<KW, 4> tp;
+                        load_pattern(tp, L.cx.text, nullptr, (uint64_t)q, K);
+                        same = true;
+#pragma unroll
+                        for (int k = 0; k < KW; ++k) same = same && tp.w[k] == rc.w[k];
                     }
-                } else if (r1 & kLocated) { // the key occurs twice: both occurrences compared with the text
-                    if (COUNT) ++ctr.located;
-                    count += occurs_at<KW, COUNT>(rc, r0, K, L, ctr);
-                    count += occurs_at<KW, COUNT>(rc, r2, K, L, ctr);
+                    if (same) { // inside one sequence?  (the index never matches across a sentinel)
+                        uint32_t a = 0, b = L.cx.n_seq;
+                        while (b - a > 1) {
+                            const uint32_t mid = (a + b) >> 1;
+                            if ((uint64_t)__ldg(L.cx.seq_start + mid) - mid <= (uint64_t)q) a = mid; else b = mid;
+                        }
+                        if ((uint64_t)q + K <= (uint64_t)__ldg(L.cx.seq_start + a + 1) - (a + 1)) count += 1;
+                    }
                 } else {
                     count += walk_exact<KW, COUNT>(rc, d, K, r0, r1, false, Brev, SPrev, C, ctr);
                 }

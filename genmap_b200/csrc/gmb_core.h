@@ -395,8 +395,7 @@ struct JtFull { uint32_t lo_r, size, lo_f, pad; }; // both intervals in one 16-b
 //     size = kLocated | 1
 //     lo_f = the kCtx characters right of the key window, text[q+d+i] in bits 2i
 //     pad  = the kCtx characters left of it,            text[q-kCtx+i] in bits 2i
-// and a key that occurs exactly TWICE both positions: lo_r = q1, size = kLocated | 2, lo_f = q2 (no context).
-// A search entered through such an entry has ONE (two) candidate alignment(s): it is finished by comparing the needle with
+// A search entered through such an entry has ONE candidate alignment: it is finished by comparing the needle with
 // the text (verify_located) — from the 2*kCtx context characters when they cover the needle (no memory access at
 // all), else from one read of the packed text — instead of walking the index through one-row intervals, one
 // dependent rank-block fetch per character.  At 3 Gbp 69 % of the existing depth-16 entries are of this kind.
@@ -830,18 +829,24 @@ GMB_HD void chain_mark_file(Chain<KW, SIGMA>& st, Frames& fr, uint32_t w, uint32
 //      (the index walk cannot leave a sequence: sentinels; here the sequence limits are checked).
 // `key`: the table key the entry was read with (the needle's window with this entry's substitutions); own_key: it is
 // the needle's own window, nothing substituted; q / ctx_r / ctx_l: the entry.  st.s, st.strand, st.cnt, st.pat are read.
-// one candidate alignment: the key occurs at text position q; have_ctx: ctx_r / ctx_l hold the characters around it
 template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
-GMB_HD void verify_candidate(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, FetchStats* fetches, const SearchStart& S,
-                             uint32_t key, uint32_t q, bool have_ctx, uint32_t ctx_r, uint32_t ctx_l)
+GMB_HD void verify_located_key(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, FetchStats* fetches, const SearchStart& S,
+                               uint32_t key, bool own_key, uint32_t q, uint32_t ctx_r, uint32_t ctx_l)
 {
     const uint32_t K = cx.K, cnt = BLK ? st.cnt : 1u;
     const uint32_t Li = K - cnt + 1, NL = K + cnt - 1, E = cx.E;
     const uint32_t tab = (BLK ? cx.p1_off[cnt] : 0u) + st.s * Li;
+    if (fetches) ++fetches->located;
+    if (st.strand == 0 && own_key) {
+        // the query's own window is an occurrence of its own key, and the key occurs once: this is the query itself
+        if (step_exact_ok(cx.steps[tab]))
+            for (uint32_t w = 0; w < cnt; ++w) chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, w, 0, 1, true);
+        return;
+    }
     const uint64_t t0 = (uint64_t)q - S.a; // the table builder leaves keys near the ends of the text unlocated: no underflow
     uint64_t mm[KW];
     bool covered = false;
-    if constexpr (KW <= 2) covered = have_ctx && S.a <= kCtx && NL - S.a - S.d <= kCtx;
+    if constexpr (KW <= 2) covered = S.a <= kCtx && NL - S.a - S.d <= kCtx;
     if (covered) {
         // text[q - kCtx, q + d + kCtx) as one bit string T (character c in bits 2c), shifted so that character 0 is the needle's
         const uint32_t sh = 32u + 2u * S.d; // 34..64
@@ -897,31 +902,7 @@ GMB_HD void verify_candidate(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx,
     }
 }
 
-// A LOCATED entry as read from the table: (w0, size, w2, w3).  size = kLocated | 1: the key occurs once, at w0, with
-// context w2 (right) / w3 (left).  size = kLocated | 2: it occurs twice, at w0 and w2 (no context: each candidate is
-// compared with the packed text).  own_key: the key is the needle's own window with nothing substituted.
-template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
-GMB_HD void verify_located_key(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, FetchStats* fetches, const SearchStart& S,
-                               uint32_t key, bool own_key, uint32_t w0, uint32_t size, uint32_t w2, uint32_t w3)
-{
-    if (fetches) ++fetches->located;
-    if ((size & ~kLocated) == 1u) {
-        if (st.strand == 0 && own_key) {
-            // the query's own window is an occurrence of its own key, and the key occurs once: this is the query itself
-            const uint32_t cnt = BLK ? st.cnt : 1u;
-            const uint32_t tab = (BLK ? cx.p1_off[cnt] : 0u) + st.s * (cx.K - cnt + 1);
-            if (step_exact_ok(cx.steps[tab]))
-                for (uint32_t w = 0; w < cnt; ++w) chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, w, 0, 1, true);
-            return;
-        }
-        verify_candidate<KW, EP, BLK, SIGMA>(st, fr, cx, fetches, S, key, w0, true, w2, w3);
-    } else {
-        verify_candidate<KW, EP, BLK, SIGMA>(st, fr, cx, fetches, S, key, w0, false, 0u, 0u);
-        verify_candidate<KW, EP, BLK, SIGMA>(st, fr, cx, fetches, S, key, w2, false, 0u, 0u);
-    }
-}
-
-// the same for the search the chain is in (general kernel: the entry sits in st.lo_r / size / lo_f / ctx_l)
+// the same for the search the chain is in (general kernel: the entry sits in st.lo_r / lo_f / ctx_l)
 template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
 GMB_HD void verify_located(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, FetchStats* fetches)
 {
@@ -943,7 +924,7 @@ GMB_HD void verify_located(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, F
             }
         }
     }
-    verify_located_key<KW, EP, BLK, SIGMA>(st, fr, cx, fetches, S, key, set == 0xffffffffu, st.lo_r, st.size, st.lo_f, st.ctx_l);
+    verify_located_key<KW, EP, BLK, SIGMA>(st, fr, cx, fetches, S, key, set == 0xffffffffu, st.lo_r, st.lo_f, st.ctx_l);
 }
 
 // One state-machine iteration.  Returns false when the block is finished (results via chain_result).

@@ -112,9 +112,9 @@ void profile_search(const uint32_t* ub, const uint32_t* lb, const uint32_t* rem,
 // depth that minimises expected table reads + expected fetches below it; *cost = that minimum (both strands).
 constexpr double kMaxVariantStrings = 3000.0;
 // located: the tables hold LOCATED entries (gmb_core.h: JtFull) — a key that occurs once ends its search at the table
-// read (verify_located), a key that occurs twice at two reads of the text.  Of the occurrences of a random d-mer a
-// fraction e^(-lam) are alone and lam e^(-lam) have one companion (lam = N/4^d), so what is walked below an entry depth d
-// shrinks by those fractions; a located entry whose context does not cover the needle costs one read of the text.
+// read (verify_located).  Of the occurrences of a random d-mer a fraction e^(-N/4^d) are alone, so what is walked
+// below an entry depth d shrinks by that fraction; a located entry whose context does not cover the needle costs one
+// read of the text instead.
 uint32_t best_jump_depth(const SearchProfile& P, uint32_t dmax, bool allow_variants, double* cost, bool located = false)
 {
     const uint32_t top = std::min(dmax, P.Li > 0 ? P.Li - 1 : 0u);
@@ -126,11 +126,9 @@ uint32_t best_jump_depth(const SearchProfile& P, uint32_t dmax, bool allow_varia
         double walked = 1.0, text = 0.0;
         if (located) {
             const double lam = P.N / std::pow(4.0, (double)d);
-            const double alone = lam > 30 ? 0.0 : std::exp(-lam); // an occurrence of a key has no companion / exactly one
-            const double paired = lam * alone;
-            walked = 1.0 - alone - paired;
+            const double alone = lam > 30 ? 0.0 : std::exp(-lam);
+            walked = 1.0 - alone;
             if (P.needle > d + 2 * kCtx) text = (2.0 * strings - 1.0) * lam * alone; // (the query's own key needs no comparison)
-            text += 2.0 * strings * (0.5 * lam * lam * alone) * 2.0;               // keys that occur twice: two text reads each
         }
         return 2.0 * strings + text + walked * (below[d] + P.leaf[0] + P.leaf[1]);
     };

@@ -40,7 +40,7 @@ __global__ void k_jump_level(const MapCtx cx, uint32_t d, const JtEntry* __restr
 
 // Text pass over a finished level of 16-byte entries: the entry of every key that occurs exactly once is rewritten as
 // a LOCATED entry (gmb_core.h: JtFull) — text position and 2 x kCtx characters of context instead of two one-row
-// intervals; the entry of a key that occurs exactly twice gets both positions.  One thread per text position; a key with one occurrence has one writer.  Positions whose key window
+// intervals.  One thread per text position; a key with one occurrence has one writer.  Positions whose key window
 // leaves its sequence are not occurrences (the index never matches across a sentinel); keys within kLocateMargin of
 // either end of the text keep their intervals, so verify_located may read around the occurrence without range checks.
 __global__ void k_locate_singletons(const uint64_t* __restrict__ text, uint64_t n_text, const uint32_t* __restrict__ seq_start,
@@ -56,8 +56,7 @@ __global__ void k_locate_singletons(const uint64_t* __restrict__ text, uint64_t 
     };
     const uint32_t key = chars(q, d);
     JtFull* e = full + key;
-    const uint32_t size = e->size;
-    if (size != 1u && size != 2u) return;
+    if (e->size != 1u) return;
     uint32_t a = 0, b = n_seq; // largest s with limits[s] <= q (limits[s] = seq_start[s] - s)
     while (b - a > 1) {
         const uint32_t mid = (a + b) >> 1;
@@ -65,23 +64,10 @@ __global__ void k_locate_singletons(const uint64_t* __restrict__ text, uint64_t 
     }
     if (q + d > (uint64_t)seq_start[a + 1] - (a + 1)) return; // the window crosses into the next sequence
     JtFull o;
-    if (size == 1u) {
-        o.lo_r = (uint32_t)q;
-        o.size = kLocated | 1u;
-        o.lo_f = chars(q + d, kCtx);
-        o.pad = chars(q - kCtx, kCtx);
-        *e = o;
-        return;
-    }
-    // a key with two occurrences has two writers: the first leaves its position in the spare word, the second finds it
-    // there and completes the entry (if the other occurrence lies in the margin, the entry keeps its intervals)
-    const uint32_t prev = atomicCAS(&e->pad, 0u, (uint32_t)q + 1u);
-    if (prev == 0u) return;
-    const uint32_t other = prev - 1u;
-    o.lo_r = other < (uint32_t)q ? other : (uint32_t)q;
-    o.size = kLocated | 2u;
-    o.lo_f = other < (uint32_t)q ? (uint32_t)q : other;
-    o.pad = 0u;
+    o.lo_r = (uint32_t)q;
+    o.size = kLocated | 1u;
+    o.lo_f = chars(q + d, kCtx);
+    o.pad = chars(q - kCtx, kCtx);
     *e = o;
 }
 

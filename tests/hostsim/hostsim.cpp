@@ -77,7 +77,7 @@ void run_ranges_blockdriver(const MapCtx& cx, const KeyLists& kl, const uint64_t
                     if (lut_reads) ++*lut_reads;
                     if (st.size == 0) continue;
                     if (st.size & kLocated) {
-                        verify_located_key<KW, EP, true, 4>(st, fr, cx, fetches, S, key, (y >> 8) & 1u, st.lo_r, st.size, st.lo_f, pad);
+                        verify_located_key<KW, EP, true, 4>(st, fr, cx, fetches, S, key, (y >> 8) & 1u, st.lo_r, st.lo_f, pad);
                         continue;
                     }
                     st.e = (y >> 4) & 7u; st.t = S.d; st.lvmask = 0; st.win = kNoWin; st.leaf_e = 0; st.thin = false;
@@ -148,17 +148,14 @@ void locate_host_singletons(const MapCtx& cx, uint32_t d, std::vector<JtFull>& f
     };
     for (uint64_t q = kLocateMargin; q + d + kLocateMargin <= n_text; ++q) {
         JtFull& e = full[chars(q, d)];
-        if (e.size != 1u && e.size != 2u) continue;
+        if (e.size != 1u) continue;
         uint32_t a = 0, b = cx.n_seq;
         while (b - a > 1) {
             const uint32_t mid = (a + b) >> 1;
             if ((uint64_t)cx.seq_start[mid] - mid <= q) a = mid; else b = mid;
         }
         if (q + d > (uint64_t)cx.seq_start[a + 1] - (a + 1)) continue;
-        if (e.size == 1u) { e = JtFull{(uint32_t)q, kLocated | 1u, chars(q + d, kCtx), chars(q - kCtx, kCtx)}; continue; }
-        // two occurrences: the first one to come by leaves its position in the spare word, the second completes the entry
-        if (e.pad == 0u) e.pad = (uint32_t)q + 1u;
-        else e = JtFull{e.pad - 1u, kLocated | 2u, (uint32_t)q, 0u};
+        e = JtFull{(uint32_t)q, kLocated | 1u, chars(q + d, kCtx), chars(q - kCtx, kCtx)};
     }
 }
 } // namespace
