@@ -166,3 +166,34 @@ def test_track_writers_from_run_lists_in_chunks_and_threads(genmap, tmp_path):
         want = c if flags else np.where(c != 0, np.float32(1.0) / np.maximum(c, 1).astype(np.float32), np.float32(0)).astype(np.float32)
         assert np.array_equal(raw, want)
         assert os.path.getsize(outs[0] + ".wig") > 5_000_000
+
+
+def test_index_reads_fastq_and_awkward_fasta(genmap, tmp_path):
+    """-FD accepts .fastq like the reference's SeqFileIn; CRLF line ends, blank lines, lower case and
+    spaces inside FASTA sequence lines give the same index as the clean file."""
+    seqs = T.repeat_rich(4, 3, 700)
+    txt = ["".join("ACGT"[c] for c in s) for s in seqs]
+    d = tmp_path / "fq"
+    d.mkdir()
+    with open(d / "reads.fastq", "w") as f:
+        for i, t in enumerate(txt):
+            f.write("@r%d some comment\n%s\n%s\n+\n%s\n%s\n" % (i, t[:300], t[300:], "I" * 300, "@" * (len(t) - 300)))  # multi-line, '@' in the qualities
+    clean, messy = tmp_path / "clean.fa", tmp_path / "messy.fa"
+    with open(clean, "w") as f:
+        for i, t in enumerate(txt):
+            f.write(">r%d some comment\n%s\n" % (i, t))
+    with open(messy, "wb") as f:
+        f.write(b"\r\n")
+        for i, t in enumerate(txt):
+            f.write((">r%d some comment\r\n" % i).encode())
+            for k in range(0, len(t), 61):
+                f.write((t[k:k + 30].lower() + " " + t[k + 30:k + 61] + "\r\n\r\n").encode())
+    blobs = {}
+    for name, flag, src in (("fastq", "-FD", d), ("clean", "-F", clean), ("messy", "-F", messy)):
+        idx = tmp_path / ("idx_" + name)
+        r = run(genmap, "index", flag, src, "-I", idx, "-xh")
+        assert r.returncode == 0, r.stderr
+        blobs[name] = open(idx / "index.gmb", "rb").read()
+        ids = open(idx / "index.ids").read().split("\n")
+        assert ids[0].split(";")[1:] == ["700", "r0"], ids[0]
+    assert blobs["fastq"] == blobs["clean"] == blobs["messy"]
