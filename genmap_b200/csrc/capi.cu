@@ -987,7 +987,9 @@ int gmb_map_frequencies_range(gmb_index* ix, const gmb_params* p, uint64_t text_
     void* biased = reinterpret_cast<void*>(reinterpret_cast<uintptr_t>(ix->d_out) - (uintptr_t)pos_begin * elem);
     gmb_map_stats local;
     std::memset(&local, 0, sizeof(local));
-    const uint64_t piece = 16ull << 20; // positions per pipeline stage (the copy of the last piece is not overlapped: keep it short)
+    // host-output pipeline: pieces that halve towards the end — the copy of the LAST piece is the only one no search
+    // overlaps, and every piece costs a launch: half of what is left (at most 64 Mi, at least 2 Mi positions) per piece
+    const uint64_t piece = 4ull << 20, kMaxPiece = 64ull << 20, kMinPiece = 2ull << 20;
     bool many_files = false; // --exclude-pseudo beyond 64 files runs unpipelined on the default stream (ep_many_files)
     if (p->exclude_pseudo && seq_to_file)
         for (uint32_t s2 = 0; s2 < n_seq && !many_files; ++s2) many_files = seq_to_file[s2] >= 64;
@@ -1012,8 +1014,9 @@ int gmb_map_frequencies_range(gmb_index* ix, const gmb_params* p, uint64_t text_
         struct PipelineFlag { bool& f; ~PipelineFlag() { f = false; } } in_pipeline{ix->prog_in_pipeline};
         ix->prog_in_pipeline = true;
         uint32_t n_piece = 0;
-        for (uint64_t b = pos_begin; b < pos_end; b += piece, ++n_piece) {
-            const uint64_t e = std::min(b + piece, pos_end);
+        for (uint64_t b = pos_begin, e = pos_begin; b < pos_end; b = e, ++n_piece) {
+            const uint64_t left = pos_end - b;
+            e = b + (left <= kMinPiece ? left : std::min(kMaxPiece, std::max(kMinPiece, left / 2)));
             gmb_map_stats st;
             int rc = map_device_impl(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, seq_to_file,
                                      n_seq, b, e, biased, ix->s_compute, &st, false);
