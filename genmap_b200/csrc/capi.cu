@@ -989,7 +989,8 @@ int gmb_map_frequencies_range(gmb_index* ix, const gmb_params* p, uint64_t text_
     std::memset(&local, 0, sizeof(local));
     // host-output pipeline: pieces that halve towards the end — the copy of the LAST piece is the only one no search
     // overlaps, and every piece costs a launch: half of what is left (at most 64 Mi, at least 2 Mi positions) per piece
-    const uint64_t piece = 4ull << 20, kMaxPiece = 64ull << 20, kMinPiece = 2ull << 20;
+    // (ranges of up to 32 Mi positions are not worth a pipeline: one launch, one copy)
+    const uint64_t piece = 32ull << 20, kMaxPiece = 64ull << 20, kMinPiece = 2ull << 20;
     bool many_files = false; // --exclude-pseudo beyond 64 files runs unpipelined on the default stream (ep_many_files)
     if (p->exclude_pseudo && seq_to_file)
         for (uint32_t s2 = 0; s2 < n_seq && !many_files; ++s2) many_files = seq_to_file[s2] >= 64;
