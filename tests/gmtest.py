@@ -536,3 +536,26 @@ def write_seqan_index(directory, files, bwt_fwd, bwt_rev, sa, sampling=10):
     assert L.gmo_seqan_write_sa((base + ".sa").encode(), _ptr(sa), n, _ptr(seq_start), n_seq, sampling) == 0
     np.array([n], dtype="<u8").tofile(base + ".sa.len")
     return directory
+
+
+def fragmented_genome(seed, total=12000, with_n=False):
+    """Many short sequences (10 - 400 bases) with repeats shared between them and reverse-complemented copies: windows,
+    table-key contexts and candidate alignments cross sequence boundaries everywhere (what verify_located must reject)."""
+    rng = np.random.default_rng(seed)
+    pool = rng.integers(0, 4, 3000, dtype=np.uint8)
+    seqs, n = [], 0
+    while n < total:
+        L = int(rng.integers(10, 400))
+        if rng.random() < 0.5:
+            st = int(rng.integers(0, len(pool) - L))
+            s = pool[st:st + L].copy()
+            if rng.random() < 0.4:
+                s = (3 - s)[::-1].copy()
+            m = rng.random(L) < 0.02
+            s[m] = rng.integers(0, 4, int(m.sum()), dtype=np.uint8)
+        else:
+            s = rng.integers(0, 4, L, dtype=np.uint8)
+        if with_n and rng.random() < 0.1:
+            s[int(rng.integers(0, L))] = 4
+        seqs.append(s); n += L
+    return seqs

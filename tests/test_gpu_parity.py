@@ -640,3 +640,26 @@ def test_cuda_three_kernels_and_table_flavours_agree(gm, monkeypatch, with_sa):
                 assert np.array_equal(got, want), (K, E, rc, bits, env, np.nonzero(got != want)[0][:10])
     finally:
         _close(ix)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_cuda_located_entries_on_fragmented_genomes(gm, seed):
+    """The same on the device, through all three kernels: genomes of many short sequences, random (K, E, strand, block
+    size, value type, planner text size), against the oracle."""
+    rng = np.random.default_rng(100 + seed)
+    with_n = seed == 4
+    seqs = T.fragmented_genome(seed, 14000, with_n=with_n)
+    _, limits = T.concat(seqs)
+    orc, ix = T.Oracle(seqs), gm.Index.build(seqs)
+    try:
+        for _ in range(10):
+            E = int(rng.integers(0, 5)); K = int(rng.integers(max(E + 2, 8), 40))
+            if E == 4 and K > 20:
+                K = 20
+            rc, B, bits = bool(rng.random() < 0.7), int(rng.integers(0, 7)), int(rng.choice([8, 16]))
+            ix.set_plan_text_size(int(rng.choice([0, 4 ** 9, 4 ** 12 - 1])))
+            want = orc.map(K, E, revcompl=rc, value_bits=bits)
+            got = ix.compute_mappability(gm.SearchParams(K, E, rc, False, bits, block_kmers=B), chrom_cum_lengths=limits)
+            assert np.array_equal(got, want), dict(seed=seed, K=K, E=E, rc=rc, B=B, bits=bits, at=np.nonzero(got != want)[0][:8])
+    finally:
+        _close(ix)

@@ -363,3 +363,25 @@ def test_state_machine_fuzz_against_the_definition(seed, monkeypatch):
             want = T.brute(seqs, K, E, revcompl=rc, value_bits=bits, exclude_pseudo=ep, seq_to_file=stf, file_no=fi)
             got = hs.map(K, E, revcompl=rc, value_bits=bits, block_kmers=B, jump_depth=depth, exclude_pseudo=ep, seq_to_file=stf, file_no=fi)
             assert np.array_equal(got, want), dict(seed=seed, K=K, E=E, rc=rc, B=B, depth=depth, bits=bits, ep=ep, fi=fi)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_located_entries_on_fragmented_genomes(seed, monkeypatch):
+    """Located table entries on genomes made of many short sequences: candidate alignments, their windows and the
+    entries' context characters cross sequence boundaries all the time; the two-phase driver and the general state machine,
+    with and without located entries, against the oracle."""
+    rng = np.random.default_rng(seed)
+    seqs = T.fragmented_genome(seed, 9000)
+    orc, hs = T.Oracle(seqs), T.HostSim(seqs)
+    for _ in range(6):
+        E = int(rng.integers(0, 4)); K = int(rng.integers(max(E + 2, 8), 34))
+        rc, B, bits = bool(rng.random() < 0.7), int(rng.integers(0, 6)), int(rng.choice([8, 16]))
+        want = orc.map(K, E, revcompl=rc, value_bits=bits)
+        for env in ({}, {"GMB_LOCATE": "0"}, {"GMB_BLOCK_KERNEL": "0"}):
+            for k in ("GMB_LOCATE", "GMB_BLOCK_KERNEL"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            got = hs.map(K, E, revcompl=rc, value_bits=bits, block_kmers=B)
+            assert np.array_equal(got, want), dict(seed=seed, K=K, E=E, rc=rc, B=B, bits=bits, env=env, at=np.nonzero(got != want)[0][:8])
+        assert hs.last_fetch_stats[11] >= 0
