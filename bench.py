@@ -713,6 +713,10 @@ def main():
                 "random_request_rate_best_microbenchmark_per_s": 45.8e9,
                 # what the DRAM actually does: 64-byte accesses per second (ncu traffic / 64 B / kernel time)
                 "dram_64B_accesses_per_s": (traffic / 64.0 / (r["kernel_ms"] * 1e-3)) if traffic else None,
+                # ... and as a fraction of the copy peak: what the memory system is really asked to move (the north-star
+                # fraction above counts 32 useful bytes per rank block only, and falls when a change removes fetches)
+                "dram_gbs": (traffic / (r["kernel_ms"] * 1e-3) / 1e9) if traffic else None,
+                "dram_frac": (traffic / (r["kernel_ms"] * 1e-3) / 1e9 / peak) if traffic else None,
                 # the same fraction on the stricter figure (rank blocks + 16-byte jump-table entries)
                 "frac_with_table_reads": (r["fetches"] * blk + r["lut_reads"] * 16.0) / len(r["batches"]) / (r["kernel_ms"] * 1e-3) / 1e9 / peak,
                 "jump_table_depth": r["jump_depth"], "kernel_ms_per_launch": r["kernel_ms"]}
