@@ -19,12 +19,14 @@ ap.add_argument("--seed", type=int, default=45)
 ap.add_argument("--configs", default="0:-1:256,0:0:256,0:13:256,0:14:256,0:16:256,1:-1:64,1:0:64,2:-1:8,2:0:8")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--kmer", type=int, default=30)
+ap.add_argument("--rep-frac", type=float, default=0.05, help="fraction of every chromosome covered by planted repeat copies")
+ap.add_argument("--rep-mut", type=float, default=0.02, help="substitution rate of the planted copies")
 ap.add_argument("--n-frac", type=float, default=0.0, help="fraction of every chromosome turned into runs of N (-> Dna5 index)")
 args = ap.parse_args()
 
 total = int(args.genome_mbp * 1e6)
 t0 = time.time()
-seqs = gm.synth_genome(total, args.nchr, args.seed)
+seqs = gm.synth_genome(total, args.nchr, args.seed, rep_frac=args.rep_frac, mut=args.rep_mut)
 if args.n_frac > 0:  # assembly-gap model: one long run per chromosome (centromere) + a few short ones
     rng = np.random.default_rng(args.seed + 1)
     for s in seqs:
