@@ -663,3 +663,38 @@ def test_cuda_located_entries_on_fragmented_genomes(gm, seed):
             assert np.array_equal(got, want), dict(seed=seed, K=K, E=E, rc=rc, B=B, bits=bits, at=np.nonzero(got != want)[0][:8])
     finally:
         _close(ix)
+
+
+def test_cuda_jump_depth_shrinks_when_hbm_is_short(gm):
+    """The automatic table depth gives way when HBM is short (the shrink path had no test): with all but
+    ~12 GB of the device taken, the plan of a 3 Gbp genome (69 GB of tables at depth 16) is entered at a shallower depth
+    and the counts do not change; a cached deeper table is dropped first when another configuration needs the room."""
+    import torch
+    seqs = T.repeat_rich(41, 3, 5000)
+    _, limits = T.concat(seqs)
+    ix, orc = gm.Index.build(seqs), T.Oracle(seqs)
+    ix.set_plan_text_size(3_000_000_024)
+    hog = None
+    try:
+        got, st = ix.compute_mappability(gm.SearchParams(30, 0), chrom_cum_lengths=limits, return_stats=True)
+        assert st.jump_depth == 16 and np.array_equal(got, orc.map(30, 0))
+        torch.cuda.synchronize()
+        free, _total = torch.cuda.mem_get_info()
+        hog = torch.empty(max(0, free - (12 << 30)), dtype=torch.uint8, device="cuda")  # the depth-16 table stays, 12 GB are left
+        for K, E in ((30, 1), (30, 2), (50, 2)):
+            got, st = ix.compute_mappability(gm.SearchParams(K, E), chrom_cum_lengths=limits, return_stats=True)
+            assert np.array_equal(got, orc.map(K, E)), (K, E, st.jump_depth)
+            assert 1 <= st.jump_depth <= 16
+        del hog
+        hog = None
+        torch.cuda.empty_cache()
+        free, _total = torch.cuda.mem_get_info()
+        hog = torch.empty(max(0, free - (6 << 30)), dtype=torch.uint8, device="cuda")
+        ix2 = gm.Index.build(T.repeat_rich(42, 2, 4000))
+        ix2.set_plan_text_size(3_000_000_024)
+        got, st = ix2.compute_mappability(gm.SearchParams(24, 1), return_stats=True)
+        assert st.jump_depth < 16 and np.array_equal(got, T.Oracle(T.repeat_rich(42, 2, 4000)).map(24, 1)), st.jump_depth
+        ix2.close()
+    finally:
+        del hog
+        _close(ix)
