@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
     cx.starts = reinterpret_cast<const SearchStart*>(starts_s);
     cx.p1_off = offs_s;
     cx.fl_off = offs_s + kMaxBlockKmers + 1;
-    SmemFrames<(int)frame_words(4)> fr{frames_s + threadIdx.x, L.E * frame_words(4), frames_s + threadIdx.x};
+    SmemFrames<(int)frame_words(4)> fr{frames_s + threadIdx.x, L.E * frame_words(4)};
     using Frames = decltype(fr);
 
     const unsigned lane = threadIdx.x & 31u;

@@ -16,37 +16,25 @@ constexpr int kCounterWords = 14; // instrumented instantiation: words of MapLau
 #define GMB_MIN_BLOCKS5 3 // Dna5 indices, blocked instantiation (five-way children, 12-word frames): 3 CTAs / 80 registers
 #endif                    // measured best (profiles/r01/s15_sweep_dna5_*.txt); the one-k-mer instantiation fits 64 like Dna4
 
-// SHARED: the per-window counters may belong to ANOTHER chain of the warp (cbase is pointed at the owner's column) and
-// several lanes may count for the same owner at once: atomic accumulation (block_kernel.cu).
-template <int FW, bool SHARED = false> // FW: words per mismatch frame (10 for Dna4, 12 for Dna5)
+template <int FW> // FW: words per mismatch frame (10 for Dna4, 12 for Dna5)
 struct SmemFrames {
     uint32_t* base;  // + threadIdx.x; word i of this chain at base[i * kThreads] (conflict-free)
     uint32_t xoff;   // first word after the E mismatch frames
-    uint32_t* cbase; // counters: word i at cbase[(xoff + i) * kThreads]
     __device__ __forceinline__ void set(uint32_t lv, uint32_t i, uint32_t v) { base[(lv * FW + i) * kThreads] = v; }
     __device__ __forceinline__ uint32_t get(uint32_t lv, uint32_t i) const { return base[(lv * FW + i) * kThreads]; }
     __device__ __forceinline__ void xset(uint32_t i, uint32_t v) { base[(xoff + i) * kThreads] = v; }
     __device__ __forceinline__ uint32_t xget(uint32_t i) const { return base[(xoff + i) * kThreads]; }
-    __device__ __forceinline__ void cset(uint32_t i, uint32_t v) { cbase[(xoff + i) * kThreads] = v; }
-    __device__ __forceinline__ uint32_t cget(uint32_t i) const { return cbase[(xoff + i) * kThreads]; }
+    // the per-window counters (kept apart from xset / xget: a kernel that lets one lane count for another chain would
+    // redirect and atomise exactly these — tried in block_kernel.cu, see there)
+    __device__ __forceinline__ void cset(uint32_t i, uint32_t v) { base[(xoff + i) * kThreads] = v; }
+    __device__ __forceinline__ uint32_t cget(uint32_t i) const { return base[(xoff + i) * kThreads]; }
     __device__ __forceinline__ void cadd(uint32_t i, uint32_t n, uint32_t maxv)
     {
-        uint32_t* p = cbase + (xoff + i) * kThreads;
-        if constexpr (SHARED) {
-            // saturating: every addend is clamped, the sum is pulled back long before 32 bits overflow, results clamp again
-            const uint32_t old = atomicAdd(p, n < maxv ? n : maxv);
-            if (old > 0x3fffffffu) atomicMin(p, maxv);
-        } else {
-            const uint64_t sum = (uint64_t)*p + n;
-            *p = sum < maxv ? (uint32_t)sum : maxv; // saturating (src/algo.hpp:48,191)
-        }
+        uint32_t* p = base + (xoff + i) * kThreads;
+        const uint64_t sum = (uint64_t)*p + n;
+        *p = sum < maxv ? (uint32_t)sum : maxv; // saturating (src/algo.hpp:48,191)
     }
-    __device__ __forceinline__ void cor(uint32_t i, uint32_t bits)
-    {
-        if (bits == 0u) return;
-        if constexpr (SHARED) atomicOr(cbase + (xoff + i) * kThreads, bits);
-        else cbase[(xoff + i) * kThreads] |= bits;
-    }
+    __device__ __forceinline__ void cor(uint32_t i, uint32_t bits) { base[(xoff + i) * kThreads] |= bits; }
 };
 
 __host__ __device__ inline uint32_t align32(uint32_t x) { return (x + 31u) & ~31u; }
@@ -79,7 +67,7 @@ __global__ void __launch_bounds__(kThreads, (SIGMA == 5 && BLK) ? GMB_MIN_BLOCKS
     cx.starts = reinterpret_cast<const SearchStart*>(starts_s);
     cx.p1_off = offs_s;
     cx.fl_off = offs_s + kMaxBlockKmers + 1;
-    SmemFrames<(int)frame_words(SIGMA)> fr{frames_s + threadIdx.x, L.E * frame_words(SIGMA), frames_s + threadIdx.x};
+    SmemFrames<(int)frame_words(SIGMA)> fr{frames_s + threadIdx.x, L.E * frame_words(SIGMA)};
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
