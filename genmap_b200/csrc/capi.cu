@@ -681,6 +681,12 @@ static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool l
         np->key = key;
         BlockTables& tabs = np->tabs;
         if (!build_block_tables(p->K, p->E, want_b, sync_tables, tabs, err, model_n, block_bases(ix->h.sigma))) return fail(GMB_ERR_UNSUPPORTED, err);
+        // --exclude-pseudo is asked for on indices of several near-identical genomes: every infix hit then stands for about
+        // as many real occurrences as there are files, all of them completed window by window, and the planner's iid model
+        // (chance hits only) picks blocks that are too large: 10 x 300 Mbp, K = 50, E = 2: 531 M positions/s with its
+        // choice, 643 M with 4 k-mers per block, 197 M with 15 (profiles/r02/s19_pangenome_blocks.txt)
+        if (p->exclude_pseudo && want_b == 0 && tabs.B > 4 &&
+            !build_block_tables(p->K, p->E, 4, sync_tables, tabs, err, model_n, block_bases(ix->h.sigma))) return fail(GMB_ERR_UNSUPPORTED, err);
         // the tables and the per-chain frame store live in shared memory: shrink the block if they do not fit
         while (tabs.B > 1 && (map_kernel_smem_bytes((uint32_t)tabs.steps.size(), p->E, tabs.B, sync_tables, ix->h.sigma, true) > (200u << 10) ||
                               tabs.steps.size() * 4 + (tabs.B + 1) * kMaxSearches * sizeof(SearchStart) > kTableBytes))

@@ -33,6 +33,7 @@ ap.add_argument("-K", type=int, default=50)
 ap.add_argument("-E", type=int, default=2)
 ap.add_argument("--batch-mpos", type=float, default=4)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--blocks", default="0", help="comma-separated k-mers per block to try (0 = the planner's choice)")
 ap.add_argument("--cpu", action="store_true", help="also run the reference binary on a scale model and compare")
 ap.add_argument("--cpu-mbp", type=float, default=3.0, help="per-file size of the CPU scale model")
 args = ap.parse_args()
@@ -51,8 +52,9 @@ batch = int(args.batch_mpos * (1 << 20))
 per_file = len(seqs) // args.files
 out = torch.zeros(int(limits[per_file]), dtype=torch.int16, device="cuda")
 stream = torch.cuda.current_stream().cuda_stream
-for ep in (True, False):
-    p = gm.SearchParams(args.K, args.E, True, ep, 16)
+for ep, blk in [(e, int(b)) for b in args.blocks.split(",") for e in (True, False)]:
+    p = gm.SearchParams(args.K, args.E, True, ep, 16, block_kmers=blk)
+    print("-- k-mers per block: %s" % (blk or "planner"), flush=True)
     rates = []
     for fi in (0, args.files // 2, args.files - 1):
         s0 = fi * per_file
