@@ -473,6 +473,7 @@ def main_pangenome(args):
         for g, b, e in timed:
             st = run(g, b, e)
             k_ms.append(st.kernel_ms); searched += int(st.positions)
+        p_plain = gm.SearchParams(K, E, True, False, 16, block_kmers=int(st.block_kmers))  # the same blocks as the -ep plan
         for g, b, e in timed:
             st = run(g, b, e, p=p_plain, count_fetches=True)
             f_tot += int(st.rank_block_fetches); lut_tot += int(st.jump_table_reads); txt += int(st.text_reads)
@@ -482,7 +483,7 @@ def main_pangenome(args):
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "rank_block_bytes_per_position": f_tot * 32.0 / max(searched, 1),
                 "table_reads_per_position": lut_tot / max(searched, 1), "text_reads_per_position": txt / max(searched, 1),
-                "kernel_ms_per_launch": float(np.mean(k_ms)),
+                "kernel_ms_per_launch": float(np.mean(k_ms)), "block_kmers": int(p_plain.block_kmers),
                 "note": "fetches counted on the same batches without -ep (same searches); -ep adds one suffix-array read per located occurrence"}
     hbm = {"index_blob_with_sa": int(ix.info.blob_bytes), "jump_tables": int(ix.refresh_info().jump_table_bytes), "result_vector": int(2 * per_file)}
     cpu, par = None, None

@@ -35,7 +35,8 @@ class GmbMapStats(ctypes.Structure):
                 ("rank_block_fetches", ctypes.c_uint64), ("jump_table_reads", ctypes.c_uint64),
                 ("kernel_launches", ctypes.c_uint32), ("jump_depth", ctypes.c_uint32),
                 ("fetches_by_size", ctypes.c_uint64 * 8), ("thin_paths", ctypes.c_uint64), ("iterations", ctypes.c_uint64),
-                ("located_entries", ctypes.c_uint64), ("text_reads", ctypes.c_uint64)]
+                ("located_entries", ctypes.c_uint64), ("text_reads", ctypes.c_uint64),
+                ("block_kmers", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 class GmbLocations(ctypes.Structure):

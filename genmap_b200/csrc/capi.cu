@@ -932,7 +932,7 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
     L.loc_off = loc ? loc->off : nullptr;
     L.loc_pos0 = loc ? loc->pos0 : 0;
 
-    if (stats) { stats->jump_depth = plan_depth; stats->kernel_launches = 1; }
+    if (stats) { stats->jump_depth = plan_depth; stats->kernel_launches = 1; stats->block_kmers = tabs.B; }
     if (stats && timed) CU(cudaEventRecord(ix->ev0, stream));
     CU(loc ? launch_locate_kernel(L, ix->sm_count, stream) : launch_map_kernel(L, ix->sm_count, stream));
     if (stats && timed) {
@@ -943,6 +943,7 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
         stats->kernel_ms = ms;
         stats->kernel_launches = 1;
         stats->jump_depth = plan_depth;
+        stats->block_kmers = tabs.B;
         if (L.count_fetches) {
             unsigned long long f[14] = {};
             CU(cudaMemcpy(f, ix->d_counters + 1, sizeof(f), cudaMemcpyDeviceToHost));
@@ -1031,6 +1032,7 @@ int gmb_map_frequencies_range(gmb_index* ix, const gmb_params* p, uint64_t text_
             local.positions += st.positions;
             local.kernel_launches += st.kernel_launches;
             local.jump_depth = st.jump_depth;
+            local.block_kmers = st.block_kmers;
             const unsigned long long done_so_far = local.positions; // staged at once (pageable source)
             CU(cudaMemcpyAsync(ix->d_counters + 15, &done_so_far, sizeof(done_so_far), cudaMemcpyHostToDevice, ix->s_compute));
             CU(cudaEventRecord(ix->ev_piece[n_piece & 1], ix->s_compute));

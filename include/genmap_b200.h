@@ -90,6 +90,8 @@ typedef struct gmb_map_stats {
     uint64_t iterations;         /* only with count_fetches: passes of all chains through the search state machine */
     uint64_t located_entries;    /* only with count_fetches: searches finished at a table entry whose key occurs once */
     uint64_t text_reads;         /* only with count_fetches: ... of which had to read the packed text (<= 32 bytes each) */
+    uint32_t block_kmers;        /* adjacent k-mers searched together by this call (the planner's choice when params.block_kmers == 0) */
+    uint32_t reserved;
 } gmb_map_stats;
 
 /* flags for gmb_index_build */

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.GmbParams) == 32
     assert ctypes.sizeof(_lib.GmbIndexInfo) == 64
-    assert ctypes.sizeof(_lib.GmbMapStats) == 136
+    assert ctypes.sizeof(_lib.GmbMapStats) == 144
 
 
 def test_host_builder_blob_is_deterministic_and_matches_hostsim(lib):
