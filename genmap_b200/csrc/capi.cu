@@ -151,6 +151,7 @@ void fill_ctx(const gmb_index* ix, MapCtx& cx)
     cx.n_seq = ix->h.n_seq; cx.own_file = 0; cx.all_files = 0;
     cx.loc_rows = nullptr;
     cx.text = reinterpret_cast<const uint64_t*>(base + ix->h.off_text);
+    cx.nmask = ix->h.sigma == 5 ? reinterpret_cast<const uint64_t*>(base + ix->h.off_nmask) : nullptr;
     cx.n_text = ix->h.n_text;
     cx.E = 0;
 }
@@ -165,7 +166,7 @@ bool locate_enabled()
 }
 
 // use_full: the searches read 16-byte entries holding both intervals (the blocked instantiation, where SA(T) is needed
-// after the jump); all_full: every search does (Dna4 indices: the 16-byte entries of keys that occur once are LOCATED,
+// after the jump); all_full: every search does (the 16-byte entries of keys that occur once are LOCATED,
 // which ends most searches at the table read).  Otherwise 8-byte entries plus a separate array for the interval in SA(T).
 JumpNeeds jump_needs(const std::vector<JumpPlan>& plans, bool use_full, bool all_full)
 {
@@ -240,7 +241,7 @@ cudaError_t jt_alloc(gmb_index* ix, const JumpNeeds& n, T** p, size_t bytes)
 int ensure_jump_tables(gmb_index* ix, const JumpNeeds& n, cudaStream_t stream)
 {
     uint32_t top = 0;
-    const bool want_located = ix->h.sigma == 4 && locate_enabled();
+    const bool want_located = locate_enabled();
     for (uint32_t d = 1; d <= 16; ++d) {
         if (n.full[d] && ix->jt_full[d] && ix->jt_full_located[d] != want_located) { // built for the other setting of GMB_LOCATE
             cudaFree(ix->jt_full[d]); ix->jt_full[d] = nullptr; ++ix->jt_epoch;
@@ -271,8 +272,9 @@ int ensure_jump_tables(gmb_index* ix, const JumpNeeds& n, cudaStream_t stream)
                 err = build_jump_level(cx, ix->h.sigma, d, ix->jt_uni[d - 1], ix->jt_lof[d - 1], nullptr, nullptr, ix->jt_full[d], stream);
             ix->jt_full_located[d] = want_located;
             if (err == cudaSuccess && want_located) // keys that occur once: position + context instead of intervals
-                err = locate_jump_singletons(reinterpret_cast<const uint64_t*>(ix->d_blob + ix->h.off_text), ix->h.n_text, cx.seq_start,
-                                             ix->h.n_seq, d, ix->jt_full[d], stream);
+                err = locate_jump_singletons(reinterpret_cast<const uint64_t*>(ix->d_blob + ix->h.off_text),
+                                             ix->h.sigma == 5 ? reinterpret_cast<const uint64_t*>(ix->d_blob + ix->h.off_nmask) : nullptr,
+                                             ix->h.n_text, cx.seq_start, ix->h.n_seq, d, ix->jt_full[d], stream);
             if (err != cudaSuccess) return cuda_fail(err, "jump table");
         }
     }
@@ -714,7 +716,7 @@ static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool l
     if (maxd > 16) maxd = 16;
     JumpNeeds needs;
     const bool use_full = tabs.B > 1 && !loc; // the blocked instantiation
-    const bool all_full = !loc && ix->h.sigma == 4 && locate_enabled();
+    const bool all_full = !loc && locate_enabled();
     for (;;) {
         plan_depth = 0;
         for (uint32_t cnt = 0; cnt <= tabs.B; ++cnt) {
@@ -764,7 +766,7 @@ static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool l
     // block_kernel.cu: every key of every search of one strand as a flat list (the 3^m substitutions of a set of m offsets
     // spelled out as XOR masks on the key window), when every search of every block size enters through 16-byte entries
     KeyLists keylist;
-    bool block_ok = p->E >= 1 && !loc && all_full && p->K + tabs.B - 1 <= 64;
+    bool block_ok = p->E >= 1 && !loc && all_full && ix->h.sigma == 4 && p->K + tabs.B - 1 <= 64;
     {
         const char* env = std::getenv("GMB_BLOCK_KERNEL"); // "0": E >= 1 through the general kernel (A/B measurements)
         if (env && env[0] == '0') block_ok = false;

@@ -1,4 +1,5 @@
-// exact_kernel.cu — the (K, 0)-frequency kernel: E = 0 on a Dna4 index, entered through 16-byte jump-table entries.
+// exact_kernel.cu — the (K, 0)-frequency kernel: E = 0, entered through 16-byte jump-table entries (Dna4 and Dna5 indices;
+// in a Dna5 index a k-mer with an N has no occurrence at E = 0, on either strand: src/algo.hpp:111-112).
 //
 // Replaces, for E = 0, the same reference path as map_kernel.cu (computeMappability<0> -> ... -> the exact search of
 // src/find2_index_approx.hpp:303-369 for a single block, both strands).  Why a kernel of its own: without errors a
@@ -32,35 +33,48 @@ struct ExactCounters { unsigned long long fetches, lut, located, text_reads, ste
 
 // rows [lo, lo + size) of SA(T') after matching P[t], t = from .. K-1, rightwards; stop_at_one: the forward strand may
 // stop as soon as one row is left (it is the query's own)
-template <int KW, bool COUNT>
-__device__ __forceinline__ uint32_t walk_exact(const Pattern<KW, 4>& P, uint32_t from, uint32_t K, uint32_t lo, uint32_t size,
-                                               bool stop_at_one, const RankBlock* __restrict__ B, const uint32_t* __restrict__ SP,
+template <int KW, bool COUNT, int SIGMA>
+__device__ __forceinline__ uint32_t walk_exact(const Pattern<KW, SIGMA>& P, uint32_t from, uint32_t K, uint32_t lo, uint32_t size,
+                                               bool stop_at_one, const void* __restrict__ blocks, const uint32_t* __restrict__ SP,
                                                const uint32_t (&C)[5], ExactCounters& ctr)
 {
     for (uint32_t t = from; t < K && size != 0u; ++t) {
         if (stop_at_one && size == 1u) break;
-        const uint32_t c = P.at(t);
+        const uint32_t c = P.at(t); // (no N here: k-mers with an N never get this far)
         const uint32_t x = lo, y = lo + size;
-        const uint32_t bx = x / kBlockBases, by = y / kBlockBases;
-        if (COUNT) { ctr.fetches += 1u + (by != bx); ++ctr.steps; }
-        const BlockRegs rbx = load_block(B + bx);
-        BlockRegs rby = rbx;
-        load_block_if(rby, B + by, by != bx);
-        const uint32_t r0 = block_rank_one(rbx, x - bx * kBlockBases, x, c, SP);
-        const uint32_t r1 = block_rank_one(rby, y - by * kBlockBases, y, c, SP);
+        uint32_t r0, r1;
+        if constexpr (SIGMA == 4) {
+            const RankBlock* B = static_cast<const RankBlock*>(blocks);
+            const uint32_t bx = x / kBlockBases, by = y / kBlockBases;
+            if (COUNT) { ctr.fetches += 1u + (by != bx); ++ctr.steps; }
+            const BlockRegs rbx = load_block(B + bx);
+            BlockRegs rby = rbx;
+            load_block_if(rby, B + by, by != bx);
+            r0 = block_rank_one(rbx, x - bx * kBlockBases, x, c, SP);
+            r1 = block_rank_one(rby, y - by * kBlockBases, y, c, SP);
+        } else {
+            const RankBlock5* B = static_cast<const RankBlock5*>(blocks);
+            const uint32_t bx = x / kBlockBases5, by = y / kBlockBases5;
+            if (COUNT) { ctr.fetches += 1u + (by != bx); ++ctr.steps; }
+            const BlockRegs5 rbx = load_block5(B + bx);
+            BlockRegs5 rby = rbx;
+            load_block5_if(rby, B + by, by != bx);
+            r0 = block_rank5_one(rbx, x - bx * kBlockBases5, x, c, SP);
+            r1 = block_rank5_one(rby, y - by * kBlockBases5, y, c, SP);
+        }
         size = r1 - r0;
         lo = (c == 0 ? C[0] : (c == 1 ? C[1] : (c == 2 ? C[2] : C[3]))) + r0;
     }
     return size;
 }
 
-template <int KW, bool COUNT, typename OutT>
+template <int KW, bool COUNT, typename OutT, int SIGMA>
 __global__ void __launch_bounds__(kThreadsE0, GMB_EXACT_MINB) exact_kernel(const MapLaunch L)
 {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t K = L.cx.K, d = L.e0_depth, maxv = L.cx.maxv;
     const JtFull* __restrict__ table = L.e0_table;
-    const RankBlock* __restrict__ Brev = static_cast<const RankBlock*>(L.cx.blk[1]);
+    const void* __restrict__ Brev = L.cx.blk[1];
     const uint32_t* __restrict__ SPrev = L.cx.sent[1];
     const uint32_t C[5] = {L.cx.C[0], L.cx.C[1], L.cx.C[2], L.cx.C[3], L.cx.C[4]};
     OutT* __restrict__ out = static_cast<OutT*>(L.out);
@@ -83,8 +97,13 @@ __global__ void __launch_bounds__(kThreadsE0, GMB_EXACT_MINB) exact_kernel(const
         if (ne > re) ne = re;
 
         for (unsigned long long j = nb + lane; j < ne; j += 32) {
-            Pattern<KW, 4> pat, rc;
-            load_pattern(pat, L.text, nullptr, L.text_begin + j, K);
+            Pattern<KW, SIGMA> pat, rc;
+            load_pattern(pat, L.text, L.nmask, L.text_begin + j, K);
+            if (SIGMA == 5 && pat.has_n()) { // an N never matches: no occurrence on either strand
+                if (COUNT) ctr.lut += both ? 2u : 1u; // (counted like the general kernel counts its dead entries)
+                out[j] = (OutT)0;
+                continue;
+            }
             rc = pat;
             rc.reverse_complement(K);
             // both table entries requested before either is used
@@ -104,7 +123,7 @@ __global__ void __launch_bounds__(kThreadsE0, GMB_EXACT_MINB) exact_kernel(const
                 count = 1; // the key's only occurrence is the query itself
                 if (COUNT) ++ctr.located;
             } else {
-                const uint32_t n = walk_exact<KW, COUNT>(pat, d, K, f0, f1, true, Brev, SPrev, C, ctr);
+                const uint32_t n = walk_exact<KW, COUNT, SIGMA>(pat, d, K, f0, f1, true, Brev, SPrev, C, ctr);
                 count = n; // 1 when the walk stopped at the query's own row
             }
             // ---- reverse strand ------------------------------------------------------------------------------------
@@ -120,9 +139,9 @@ __global__ void __launch_bounds__(kThreadsE0, GMB_EXACT_MINB) exact_kernel(const
                         same = want == have;
                     } else {
                         if (COUNT) ++ctr.text_reads;
-                        Pattern<KW, 4> tp;
-                        load_pattern(tp, L.cx.text, nullptr, (uint64_t)q, K);
-                        same = true;
+                        Pattern<KW, SIGMA> tp;
+                        load_pattern(tp, L.cx.text, L.cx.nmask, (uint64_t)q, K);
+                        same = !tp.has_n(); // (Dna5: a text N matches nothing)
 #pragma unroll
                         for (int k = 0; k < KW; ++k) same = same && tp.w[k] == rc.w[k];
                     }
@@ -135,7 +154,7 @@ __global__ void __launch_bounds__(kThreadsE0, GMB_EXACT_MINB) exact_kernel(const
                         if ((uint64_t)q + K <= (uint64_t)__ldg(L.cx.seq_start + a + 1) - (a + 1)) count += 1;
                     }
                 } else {
-                    count += walk_exact<KW, COUNT>(rc, d, K, r0, r1, false, Brev, SPrev, C, ctr);
+                    count += walk_exact<KW, COUNT, SIGMA>(rc, d, K, r0, r1, false, Brev, SPrev, C, ctr);
                 }
             }
             out[j] = (OutT)(count < maxv ? count : maxv);
@@ -154,10 +173,10 @@ __global__ void __launch_bounds__(kThreadsE0, GMB_EXACT_MINB) exact_kernel(const
     }
 }
 
-template <int KW, bool COUNT, typename OutT>
+template <int KW, bool COUNT, typename OutT, int SIGMA>
 cudaError_t launch_e0(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
-    auto kern = exact_kernel<KW, COUNT, OutT>;
+    auto kern = exact_kernel<KW, COUNT, OutT, SIGMA>;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreadsE0, 0);
     if (e != cudaSuccess) return e;
@@ -169,26 +188,27 @@ cudaError_t launch_e0(const MapLaunch& L, int sm_count, cudaStream_t stream)
     return cudaGetLastError();
 }
 
-template <int KW>
+template <int KW, int SIGMA>
 cudaError_t launch_e0_kw(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
     if (L.value_bits == 16)
-        return L.count_fetches ? launch_e0<KW, true, uint16_t>(L, sm_count, stream) : launch_e0<KW, false, uint16_t>(L, sm_count, stream);
-    return L.count_fetches ? launch_e0<KW, true, uint8_t>(L, sm_count, stream) : launch_e0<KW, false, uint8_t>(L, sm_count, stream);
+        return L.count_fetches ? launch_e0<KW, true, uint16_t, SIGMA>(L, sm_count, stream) : launch_e0<KW, false, uint16_t, SIGMA>(L, sm_count, stream);
+    return L.count_fetches ? launch_e0<KW, true, uint8_t, SIGMA>(L, sm_count, stream) : launch_e0<KW, false, uint8_t, SIGMA>(L, sm_count, stream);
 }
 
 } // namespace
 
 bool exact_kernel_applies(const MapLaunch& L)
 {
-    return L.E == 0 && L.sigma == 4 && !L.exclude_pseudo && L.cx.B == 1 && L.e0_table != nullptr && L.e0_depth >= 1 &&
+    return L.E == 0 && (L.sigma == 4 || L.sigma == 5) && !L.exclude_pseudo && L.cx.B == 1 && L.e0_table != nullptr && L.e0_depth >= 1 &&
            L.e0_depth < L.cx.K && L.cx.K <= 64 && L.cx.loc_rows == nullptr && L.loc_off == nullptr;
 }
 
 cudaError_t launch_exact_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
     if (L.n_work == 0) return cudaSuccess;
-    return L.cx.K <= 32 ? launch_e0_kw<1>(L, sm_count, stream) : launch_e0_kw<2>(L, sm_count, stream);
+    if (L.sigma == 5) return L.cx.K <= 32 ? launch_e0_kw<1, 5>(L, sm_count, stream) : launch_e0_kw<2, 5>(L, sm_count, stream);
+    return L.cx.K <= 32 ? launch_e0_kw<1, 4>(L, sm_count, stream) : launch_e0_kw<2, 4>(L, sm_count, stream);
 }
 
 } // namespace gmb

@@ -221,6 +221,19 @@ GMB_HD Ranks5 block_rank5(const BlockRegs5& b, uint32_t r, uint32_t i, const uin
     return R;
 }
 
+// rank of ONE of A, C, G, T at BWT position i = blk*32 + r of a Dna5 block (exact-match steps)
+GMB_HD uint32_t block_rank5_one(const BlockRegs5& b, uint32_t r, uint32_t i, uint32_t sym, const uint32_t* sent_pos)
+{
+    const uint32_t m = piece_mask(r, 0);
+    const uint32_t k0 = (sym & 1u) ? b.p0 : ~b.p0, k1 = (sym & 2u) ? b.p1 : ~b.p1;
+    uint32_t n = popc32(k0 & k1 & ~b.p2 & m);
+    if (sym == 0u) { // sentinel rows are stored as code 0
+        const uint32_t s_before = b.h[4] >> 8, s_in = b.h[4] & 0xffu;
+        for (uint32_t k = 0; k < s_in; ++k) n -= sent_pos[s_before + k] < i;
+    }
+    return (sym == 0u ? b.h[0] : (sym == 1u ? b.h[1] : (sym == 2u ? b.h[2] : b.h[3]))) + n;
+}
+
 // ---- pattern -----------------------------------------------------------------------------------------
 GMB_HD uint64_t reverse_groups64(uint64_t x) // reverse the order of the 32 two-bit groups
 {
@@ -389,8 +402,9 @@ GMB_HD void load_pattern(Pattern<KW, SIGMA>& p, const uint64_t* text, const uint
 // keys).  One table read replaces the walk through the dense top of the trie (JumpPlan, gmb_host.h).
 struct JtEntry { uint32_t lo_r, size; };
 struct JtFull { uint32_t lo_r, size, lo_f, pad; }; // both intervals in one 16-byte entry: one memory request
-// LOCATED entries (Dna4 tables, set by the text pass of jump_table.cu): a key that occurs exactly ONCE in the text
-// carries where — and what stands around it — instead of its two one-row intervals:
+// LOCATED entries (set by the text pass of jump_table.cu; in a Dna5 index only keys without an N in window or context):
+// a key that occurs exactly ONCE in the text carries where — and what stands around it — instead of its two one-row
+// intervals:
 //     lo_r = q, the text position of the occurrence (concatenated text, no sentinels)
 //     size = kLocated | 1
 //     lo_f = the kCtx characters right of the key window, text[q+d+i] in bits 2i
@@ -433,8 +447,9 @@ struct MapCtx {
     // locate instantiation only (csv output, src/algo.hpp:311-343): second pass writes the SA value of every
     // occurrence; nullptr in the first (counting) pass
     uint32_t* loc_rows;
-    // located table entries (verify_located): the packed text and its length
+    // located table entries (verify_located): the packed text, its N mask (Dna5 indices) and its length
     const uint64_t* text;
+    const uint64_t* nmask;
     uint64_t n_text;
 };
 
@@ -651,8 +666,8 @@ GMB_HD void chain_start(Chain<KW, SIGMA>& st, const MapCtx& cx, unsigned long lo
             st.lo_f = 0; st.lo_r = 0; st.size = cx.n_bwt; st.t = 0;
         } else {
             if (st.strand == 1 && st.s == 0) { st.lo_f = st.pre_lo_f; st.lo_r = st.pre_lo_r; st.size = st.pre_size; st.ctx_l = st.pre_ctx; }
-            else if (S.set0 == kDeadVariant || (SIGMA == 5 && st.pat.has_n(S.a, S.d))) { st.lo_f = 0; st.lo_r = 0; st.size = 0; } // N never matches
-            else if (SIGMA == 4 && S.full) jump_lookup(S, st.pat.bits(S.a, S.d), st.lo_f, st.lo_r, st.size, st.ctx_l);
+            else if (S.set0 == kDeadVariant || (SIGMA == 5 && (st.pat.has_n(S.a, S.d) || (cx.E == 0 && st.has_n)))) { st.lo_f = 0; st.lo_r = 0; st.size = 0; } // N never matches (E = 0: anywhere in the k-mer)
+            else if (S.full) jump_lookup(S, st.pat.bits(S.a, S.d), st.lo_f, st.lo_r, st.size, st.ctx_l);
             else jump_lookup_lean(S, st.pat.bits(S.a, S.d), st.lo_f, st.lo_r, st.size);
             st.t = S.d;
             if (lut_reads) *lut_reads += 1;
@@ -710,8 +725,8 @@ GMB_HD void chain_begin_block(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx
         Pattern<KW, SIGMA> rc = st.pat;
         rc.reverse_complement(cx.K + (BLK ? st.cnt : 1u) - 1);
         st.pre_ctx = 0;
-        if (SIGMA == 5 && rc.has_n(S0.a, S0.d)) { st.pre_lo_f = 0; st.pre_lo_r = 0; st.pre_size = 0; }
-        else if (BLK || (SIGMA == 4 && S0.full)) jump_lookup(S0, rc.bits(S0.a, S0.d), st.pre_lo_f, st.pre_lo_r, st.pre_size, st.pre_ctx);
+        if (SIGMA == 5 && (rc.has_n(S0.a, S0.d) || (!BLK && cx.E == 0 && st.has_n))) { st.pre_lo_f = 0; st.pre_lo_r = 0; st.pre_size = 0; }
+        else if (BLK || S0.full) jump_lookup(S0, rc.bits(S0.a, S0.d), st.pre_lo_f, st.pre_lo_r, st.pre_size, st.pre_ctx);
         else jump_lookup_lean(S0, rc.bits(S0.a, S0.d), st.pre_lo_f, st.pre_lo_r, st.pre_size);
     }
     chain_start<KW, BLK, SIGMA>(st, cx, lut_reads);
@@ -817,6 +832,18 @@ GMB_HD void chain_mark_file(Chain<KW, SIGMA>& st, Frames& fr, uint32_t w, uint32
     else fr.cor(at + 1, 1u << (file - 32u));
 }
 
+// bit i of a 32-bit mask -> bit 2i of a 64-bit word (the spacing of the mismatch bits)
+GMB_HD uint64_t spread_bits(uint32_t m)
+{
+    uint64_t x = m;
+    x = (x | (x << 16)) & 0x0000ffff0000ffffull;
+    x = (x | (x << 8)) & 0x00ff00ff00ff00ffull;
+    x = (x | (x << 4)) & 0x0f0f0f0f0f0f0f0full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & 0x5555555555555555ull;
+    return x;
+}
+
 // The current search of the chain was entered through a LOCATED entry (see JtFull): the key of the entry occurs once
 // in the text, at position st.lo_r, so the search has one candidate alignment: needle[x] <-> text[q - a + x].  What the
 // index walk would find below this node is decided here by direct comparison:
@@ -829,6 +856,9 @@ GMB_HD void chain_mark_file(Chain<KW, SIGMA>& st, Frames& fr, uint32_t w, uint32
 //      (the index walk cannot leave a sequence: sentinels; here the sequence limits are checked).
 // `key`: the table key the entry was read with (the needle's window with this entry's substitutions); own_key: it is
 // the needle's own window, nothing substituted; q / ctx_r / ctx_l: the entry.  st.s, st.strand, st.cnt, st.pat are read.
+// Dna5 indices: a pattern N never matches and a text N matches nothing (src/algo.hpp:111-112) — both are mismatch bits;
+// the table builder locates a key only if neither its window nor its context holds an N, so the context path needs no
+// text mask.
 template <int KW, bool EP, bool BLK, int SIGMA, class Frames>
 GMB_HD void verify_located_key(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, FetchStats* fetches, const SearchStart& S,
                                uint32_t key, bool own_key, uint32_t q, uint32_t ctx_r, uint32_t ctx_l)
@@ -837,8 +867,9 @@ GMB_HD void verify_located_key(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& c
     const uint32_t Li = K - cnt + 1, NL = K + cnt - 1, E = cx.E;
     const uint32_t tab = (BLK ? cx.p1_off[cnt] : 0u) + st.s * Li;
     if (fetches) ++fetches->located;
-    if (st.strand == 0 && own_key) {
+    if (st.strand == 0 && own_key && !(SIGMA == 5 && st.has_n)) {
         // the query's own window is an occurrence of its own key, and the key occurs once: this is the query itself
+        // (a needle with an N outside the key window is compared like any other candidate: its N never matches)
         if (step_exact_ok(cx.steps[tab]))
             for (uint32_t w = 0; w < cnt; ++w) chain_count<KW, EP, BLK, SIGMA>(st, fr, cx, w, 0, 1, true);
         return;
@@ -860,15 +891,17 @@ GMB_HD void verify_located_key(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& c
         for (int k = 0; k < KW; ++k) {
             const uint64_t x = st.pat.w[k] ^ tw[k < 2 ? k : 1];
             mm[k] = (x | (x >> 1)) & 0x5555555555555555ull;
+            if constexpr (SIGMA == 5) mm[k] |= spread_bits(st.pat.nm[k]);
         }
     } else {
         if (fetches) ++fetches->text_reads;
         Pattern<KW, SIGMA> tp;
-        load_pattern(tp, cx.text, nullptr, t0, NL);
+        load_pattern(tp, cx.text, cx.nmask, t0, NL);
 #pragma unroll
         for (int k = 0; k < KW; ++k) {
             const uint64_t x = st.pat.w[k] ^ tp.w[k];
             mm[k] = (x | (x >> 1)) & 0x5555555555555555ull;
+            if constexpr (SIGMA == 5) mm[k] |= spread_bits(st.pat.nm[k] | tp.nm[k]);
         }
     }
     if (count_mismatches<KW>(mm, cnt - 1u, K) > E) return;
@@ -942,7 +975,7 @@ GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, Fetch
     const uint32_t Li = K - cnt + 1; // infix length
     if (fetches) ++fetches->iterations;
 
-    if constexpr (SIGMA == 4 && !LOC) {
+    if constexpr (!LOC) {
         // the search was entered through the table entry of a key that occurs once: one candidate alignment, finished
         // by comparing needle and text; the node is done after that
         if (st.size & kLocated) { verify_located<KW, EP, BLK, SIGMA>(st, fr, cx, fetches); st.size = 0; }

@@ -147,7 +147,7 @@ uint32_t best_jump_depth(const SearchProfile& P, uint32_t dmax, bool allow_varia
 bool located_enabled(uint64_t n_bwt, uint32_t sigma)
 {
     const char* env = std::getenv("GMB_LOCATE"); // "0": tables without located entries (every search walks the index)
-    return n_bwt != 0 && sigma == 4 && !(env && env[0] == '0');
+    return n_bwt != 0 && (sigma == 4 || sigma == 5) && !(env && env[0] == '0');
 }
 
 bool variants_enabled(uint64_t n_bwt, uint32_t sigma)

@@ -43,11 +43,18 @@ __global__ void k_jump_level(const MapCtx cx, uint32_t d, const JtEntry* __restr
 // intervals.  One thread per text position; a key with one occurrence has one writer.  Positions whose key window
 // leaves its sequence are not occurrences (the index never matches across a sentinel); keys within kLocateMargin of
 // either end of the text keep their intervals, so verify_located may read around the occurrence without range checks.
-__global__ void k_locate_singletons(const uint64_t* __restrict__ text, uint64_t n_text, const uint32_t* __restrict__ seq_start,
-                                    uint32_t n_seq, uint32_t d, JtFull* __restrict__ full)
+__global__ void k_locate_singletons(const uint64_t* __restrict__ text, const uint64_t* __restrict__ nmask, uint64_t n_text,
+                                    const uint32_t* __restrict__ seq_start, uint32_t n_seq, uint32_t d, JtFull* __restrict__ full)
 {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + kLocateMargin;
     if (q + d + kLocateMargin > n_text) return;
+    if (nmask) { // Dna5: a window with an N is no key, and a key is only located if its context holds no N either
+        const uint64_t b = q - kCtx, len = d + 2 * kCtx; // <= 48 positions: at most two mask words
+        const uint64_t w0 = nmask[b >> 6], w1 = nmask[(b >> 6) + 1];
+        const uint32_t sh = (uint32_t)(b & 63u);
+        const uint64_t bits = sh ? (w0 >> sh) | (w1 << (64u - sh)) : w0;
+        if (bits & ((1ull << len) - 1ull)) return;
+    }
     auto chars = [&](uint64_t p, uint32_t len) { // len <= 16 characters starting at text position p
         const uint64_t w = text[p >> 5], w2 = text[(p >> 5) + 1];
         const uint32_t sh = 2u * (uint32_t)(p & 31u);
@@ -73,13 +80,13 @@ __global__ void k_locate_singletons(const uint64_t* __restrict__ text, uint64_t 
 
 } // namespace
 
-cudaError_t locate_jump_singletons(const uint64_t* text, uint64_t n_text, const uint32_t* seq_start, uint32_t n_seq, uint32_t d,
-                                   JtFull* full, cudaStream_t stream)
+cudaError_t locate_jump_singletons(const uint64_t* text, const uint64_t* nmask, uint64_t n_text, const uint32_t* seq_start, uint32_t n_seq,
+                                   uint32_t d, JtFull* full, cudaStream_t stream)
 {
     if (n_text < 2ull * kLocateMargin + d + 1) return cudaSuccess; // too small a text: nothing gets located
     const uint64_t n = n_text - 2ull * kLocateMargin - d + 1;
     const unsigned threads = 256;
-    k_locate_singletons<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(text, n_text, seq_start, n_seq, d, full);
+    k_locate_singletons<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(text, nmask, n_text, seq_start, n_seq, d, full);
     return cudaGetLastError();
 }
 

@@ -12,9 +12,10 @@ namespace gmb {
 cudaError_t build_jump_level(const MapCtx& cx, uint32_t sigma, uint32_t d, const JtEntry* prev_uni, const uint32_t* prev_lof,
                              JtEntry* out_uni, uint32_t* out_lof, JtFull* out_full, cudaStream_t stream);
 
-// Rewrite the entries of a finished Dna4 level of 16-byte entries whose key occurs exactly once as LOCATED entries
-// (text position + context characters, gmb_core.h: JtFull); one pass over the packed text.
-cudaError_t locate_jump_singletons(const uint64_t* text, uint64_t n_text, const uint32_t* seq_start, uint32_t n_seq, uint32_t d,
-                                   JtFull* full, cudaStream_t stream);
+// Rewrite the entries of a finished level of 16-byte entries whose key occurs exactly once as LOCATED entries
+// (text position + context characters, gmb_core.h: JtFull); one pass over the packed text.  nmask: the N mask of a
+// Dna5 index (nullptr for Dna4): keys whose window or context holds an N keep their intervals.
+cudaError_t locate_jump_singletons(const uint64_t* text, const uint64_t* nmask, uint64_t n_text, const uint32_t* seq_start, uint32_t n_seq,
+                                   uint32_t d, JtFull* full, cudaStream_t stream);
 
 } // namespace gmb

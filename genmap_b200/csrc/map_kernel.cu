@@ -1,5 +1,5 @@
 // map_kernel.cu — the GENERAL (K,E)-frequency kernel for sm_100a: every configuration the two specialised kernels do
-// not take (exact_kernel.cu: E = 0; block_kernel.cu: E = 1, 2, 4 — both Dna4, needle <= 64): E = 3, Dna5 indices, K > 64,
+// not take (exact_kernel.cu: E = 0, K <= 64; block_kernel.cu: E = 1, 2, 4 on Dna4, needle <= 64): E = 3, Dna5 indices at E >= 1, K > 64,
 // jump tables switched off; its locate instantiation serves the csv lists (locate_kernel.cu).
 //
 // Replaces the reference's per-position loop computeMappability -> computeMappabilitySingleBlock

@@ -147,6 +147,11 @@ void locate_host_singletons(const MapCtx& cx, uint32_t d, std::vector<JtFull>& f
         return (uint32_t)(v & ((1ull << (2u * len)) - 1ull));
     };
     for (uint64_t q = kLocateMargin; q + d + kLocateMargin <= n_text; ++q) {
+        if (cx.nmask) { // Dna5: no N in the key window or its context
+            bool any = false;
+            for (uint64_t i = q - kCtx; i < q + d + kCtx; ++i) any = any || ((cx.nmask[i >> 6] >> (i & 63)) & 1ull);
+            if (any) continue;
+        }
         JtFull& e = full[chars(q, d)];
         if (e.size != 1u) continue;
         uint32_t a = 0, b = cx.n_seq;
@@ -250,7 +255,7 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     cx.K = K; cx.B = B; cx.n_search = tabs.n_search; cx.n_strands = revcompl ? 2 : 1;
     cx.maxv = value_bits == 16 ? 65535u : 255u;
     cx.sa = nullptr; cx.seq_start = nullptr; cx.seq_to_file = nullptr; cx.n_seq = h.n_seq; cx.own_file = own_file; cx.all_files = 0;
-    cx.loc_rows = nullptr; cx.text = nullptr; cx.n_text = 0; cx.E = E;
+    cx.loc_rows = nullptr; cx.text = nullptr; cx.nmask = nullptr; cx.n_text = 0; cx.E = E;
     if (ep) {
         if (!h.off_sa) return -3;
         cx.sa = reinterpret_cast<const uint32_t*>(base + h.off_sa);
@@ -274,12 +279,13 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     std::vector<std::vector<JtEntry>> uni(max_depth + 1);   // what the one-k-mer instantiation reads on Dna5 indices
     std::vector<std::vector<uint32_t>> lof(max_depth + 1);
     const char* loc_env = std::getenv("GMB_LOCATE");
-    const bool all_full = sigma == 4 && !(loc_env && loc_env[0] == '0'); // as capi.cu: Dna4 searches all read 16-byte entries
+    const bool all_full = !(loc_env && loc_env[0] == '0'); // as capi.cu: every search reads 16-byte entries
     if (B == 1 && !all_full)
         for (uint32_t d = 1; d <= max_depth; ++d)
             for (const JtFull& q : full[d]) { uni[d].push_back(JtEntry{q.lo_r, q.size}); lof[d].push_back(q.lo_f); }
     cx.seq_start = reinterpret_cast<const uint32_t*>(base + h.off_seq_start);
     cx.text = reinterpret_cast<const uint64_t*>(base + h.off_text);
+    cx.nmask = sigma == 5 ? reinterpret_cast<const uint64_t*>(base + h.off_nmask) : nullptr;
     cx.n_text = h.n_text;
     cx.E = E;
     if (all_full)
@@ -313,7 +319,7 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     // the two-phase driver of block_kernel.cu, where the library would launch it (capi.cu: get_plan)
     KeyLists kl;
     const char* bk_env = std::getenv("GMB_BLOCK_KERNEL");
-    const bool block_driver = E >= 1 && all_full && needle <= 64 && !(bk_env && bk_env[0] == '0') && build_key_lists(tabs, plans, kl);
+    const bool block_driver = E >= 1 && all_full && sigma == 4 && needle <= 64 && !(bk_env && bk_env[0] == '0') && build_key_lists(tabs, plans, kl);
     if (block_driver) {
         if (needle <= 32) { if (ep) run_ranges_blockdriver<1, true>(cx, kl, text, text_begin, ranges, value_bits, out, &f, &lr);
                             else run_ranges_blockdriver<1, false>(cx, kl, text, text_begin, ranges, value_bits, out, &f, &lr); }
@@ -357,7 +363,7 @@ int hs_locate(const void* blob, uint32_t K, uint32_t E, int revcompl, uint64_t t
     cx.sa = reinterpret_cast<const uint32_t*>(base + h.off_sa);
     cx.seq_start = reinterpret_cast<const uint32_t*>(base + h.off_seq_start);
     cx.seq_to_file = nullptr; cx.n_seq = h.n_seq; cx.own_file = 0; cx.all_files = 0;
-    cx.loc_rows = nullptr; cx.text = reinterpret_cast<const uint64_t*>(base + h.off_text); cx.n_text = h.n_text; cx.E = E;
+    cx.loc_rows = nullptr; cx.text = reinterpret_cast<const uint64_t*>(base + h.off_text); cx.nmask = nullptr; cx.n_text = h.n_text; cx.E = E;
     const uint32_t want_depth = jump_depth < 0 ? default_jump_depth(h.n_bwt) : (uint32_t)jump_depth;
     JumpPlan plan;
     plan_jump_tables(tabs.infix[1], want_depth, plan, E, h.n_bwt, sigma, 1, false);

@@ -239,6 +239,32 @@ def test_cuda_fetch_counter_matches_cpu_restatement(gm):
         assert np.array_equal(out, want) and st.rank_block_fetches == f and st.jump_depth == min(depth, 9)
 
 
+@pytest.mark.parametrize("with_n", [False, True], ids=["dna4", "dna5"])
+def test_cuda_located_entries_are_used_like_in_the_host_mirror(gm, with_n, monkeypatch):
+    """Located table entries on Dna4 and Dna5 indices, general kernel: the device verifies exactly the
+    entries the host mirror verifies (same rank-block fetches, table reads, located entries, text reads) — a table
+    whose text pass located nothing would still give the right counts, only slower."""
+    monkeypatch.setenv("GMB_BLOCK_KERNEL", "0")  # the two-phase kernel keeps its own counters
+    seqs = T.repeat_rich(23, 2, 60000, rep_frac=0.05, with_n=with_n)
+    _, limits = T.concat(seqs)
+    ix, hs = gm.Index.build(seqs), T.HostSim(seqs)
+    try:
+        bad = []
+        for K, E, B, depth in [(30, 1, 1, -1), (30, 1, 3, -1), (30, 1, 3, 7), (24, 2, 4, -1), (30, 0, 1, -1)]:
+            ix.set_jump_depth(depth)
+            p = gm.SearchParams(K, E, block_kmers=B)
+            out, st = ix.compute_mappability(p, chrom_cum_lengths=limits, count_fetches=True, return_stats=True)
+            want = hs.map(K, E, jump_depth=depth, block_kmers=B)
+            f = hs.last_fetch_stats
+            got = (st.rank_block_fetches, st.jump_table_reads, st.located_entries, st.text_reads)
+            host = (f[0], hs.last_lut_reads, f[11], f[12])
+            if not np.array_equal(out, want) or got != host or st.located_entries == 0:
+                bad.append(dict(K=K, E=E, B=B, depth=depth, equal=bool(np.array_equal(out, want)), device=got, host=host))
+        assert not bad, bad
+    finally:
+        _close(ix)
+
+
 # ---- 1 Mbp of the frozen synthetic generator: md5 pins measured with the reference (BASELINE.md §2) --
 PINS = {0: "15a50bb1184e42daacd5569323356621", 1: "27e5f62a996ee570ba5e600972303903", 2: "4445ff36c72e8ff1a45f3ab08685d0c4"}
 
