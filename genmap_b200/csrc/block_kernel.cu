@@ -1,5 +1,6 @@
-// block_kernel.cu — the (K,E)-frequency kernel for E >= 1 on Dna4 indices: blocks of adjacent k-mers, every search
-// entered through the 16-byte jump-table entries of all the strings it admits.
+// block_kernel.cu — the (K,E)-frequency kernel for E >= 1: blocks of adjacent k-mers, every search entered through the
+// 16-byte jump-table entries of all the strings it admits.  Dna4 indices, and Dna5 indices in calls whose searches skip
+// the text's N (MapCtx::skip_n: the alignments to text windows with an N are counted by the N pass of capi.cu).
 //
 // Replaces the same reference path as map_kernel.cu (computeMappabilitySingleBlock over the optimum search scheme,
 // src/algo.hpp:221-403, src/find2_index_approx.hpp:223-457); the counts are the same by construction: it runs the
@@ -45,7 +46,7 @@ constexpr uint32_t kRound = 32;         // keys per round (one overflow bit each
 #endif
 constexpr uint32_t kKeyBatch = GMB_KEY_BATCH; // table entries requested back to back
 
-template <int KW, bool COUNT, typename OutT, bool EP, int MINB>
+template <int KW, bool COUNT, typename OutT, bool EP, int MINB, int SIGMA>
 __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L)
 {
     // shared memory: step tables | jump-table starts | offsets | per-chain frame store | per-chain entries put aside
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
     uint32_t* starts_s = steps_s + align32(L.n_step_words);
     uint32_t* offs_s = starts_s + align32(n_start_words);
     uint32_t* frames_s = offs_s + align32(2 * (kMaxBlockKmers + 1));
-    uint32_t* pend_s = frames_s + frame_store_words(L.E, L.cx.B, EP, 4, true) * kThreads + threadIdx.x;
+    uint32_t* pend_s = frames_s + frame_store_words(L.E, L.cx.B, EP, SIGMA, true) * kThreads + threadIdx.x;
     for (uint32_t i = threadIdx.x; i < L.n_step_words; i += kThreads) steps_s[i] = L.cx.steps[i];
     for (uint32_t i = threadIdx.x; i < n_start_words; i += kThreads) starts_s[i] = reinterpret_cast<const uint32_t*>(L.cx.starts)[i];
     if (threadIdx.x == 0) {
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
     cx.starts = reinterpret_cast<const SearchStart*>(starts_s);
     cx.p1_off = offs_s;
     cx.fl_off = offs_s + kMaxBlockKmers + 1;
-    SmemFrames<(int)frame_words(4)> fr{frames_s + threadIdx.x, L.E * frame_words(4)};
+    SmemFrames<(int)frame_words(SIGMA)> fr{frames_s + threadIdx.x, L.E * frame_words(SIGMA)};
     using Frames = decltype(fr);
 
     const unsigned lane = threadIdx.x & 31u;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
     const uint2* __restrict__ keys = L.keylist;
     FetchStats fetches{};
     unsigned long long lut_reads = 0;
-    Chain<KW, 4> st;
+    Chain<KW, SIGMA> st;
     st.has_n = false; st.acc = 0; st.files = 0; st.var = 0; st.sub = 0; st.nsub = 1;
 
     for (;;) {
@@ -102,12 +103,19 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
         const unsigned long long j = nb + (unsigned long long)lane * B; // first position of this lane's block
         const uint32_t cnt = j < ne ? (uint32_t)(ne - j < B ? ne - j : B) : 0u;
         const uint32_t NL = K + cnt - 1;
-        const uint32_t nk = cnt ? L.key_n[cnt] : 0u, koff = cnt ? L.key_off[cnt] : 0u;
+        uint32_t nk = cnt ? L.key_n[cnt] : 0u;
+        const uint32_t koff = cnt ? L.key_off[cnt] : 0u;
         if (cnt) {
             st.cnt = cnt;
-            load_pattern(st.pat, L.text, nullptr, L.text_begin + j, NL);
+            load_pattern(st.pat, L.text, L.nmask, L.text_begin + j, NL);
             const uint32_t per = EP ? 3u : 1u;
             for (uint32_t w = 0; w < cnt * per; ++w) fr.cset(kLeafWords + w, 0u);
+            if constexpr (SIGMA == 5) {
+                // an N in the common infix is an N in every window of the block: nothing to search (windows with 1..E N
+                // get their counts from the N pass, the others have none)
+                st.has_n = st.pat.has_n();
+                if (st.has_n && st.pat.has_n(cnt - 1u, K - cnt + 1u)) nk = 0u;
+            }
         }
 
         for (uint32_t strand = 0; strand < cx.n_strands; ++strand) {
@@ -141,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
                         if (e1[u] & kLocated) {
                             st.s = meta[u] & 7u;
                             const SearchStart& S = cx.starts[cnt * kMaxSearches + st.s];
-                            verify_located_key<KW, EP, true, 4, Frames>(st, fr, cx, COUNT ? &fetches : nullptr, S, key[u],
+                            verify_located_key<KW, EP, true, SIGMA, Frames>(st, fr, cx, COUNT ? &fetches : nullptr, S, key[u],
                                                                         (meta[u] >> 8) & 1u, e0[u], e2[u], e3[u]);
                         } else if (n_pend < kPendSlots) {
                             uint32_t* p = pend_s + n_pend * kPendWords * kThreads;
@@ -180,12 +188,12 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
                     }
                     if (!__any_sync(0xffffffffu, walking)) break;
                     if (walking)
-                        walking = chain_step<KW, EP, true, 4, Frames, false, true>(st, fr, cx, COUNT ? &fetches : nullptr, nullptr);
+                        walking = chain_step<KW, EP, true, SIGMA, Frames, false, true>(st, fr, cx, COUNT ? &fetches : nullptr, nullptr);
                 }
             }
         }
         if (cnt)
-            for (uint32_t w = 0; w < cnt; ++w) out[j + w] = (OutT)chain_result<KW, EP, true, 4>(st, fr, cx, w);
+            for (uint32_t w = 0; w < cnt; ++w) out[j + w] = (OutT)chain_result<KW, EP, true, SIGMA>(st, fr, cx, w);
     }
     if (COUNT) {
         unsigned long long v[kCounterWords] = {fetches.total, lut_reads, fetches.by_size[0], fetches.by_size[1], fetches.by_size[2],
@@ -200,11 +208,11 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
     }
 }
 
-template <int KW, bool COUNT, typename OutT, bool EP, int MINB>
+template <int KW, bool COUNT, typename OutT, bool EP, int MINB, int SIGMA = 4>
 cudaError_t launch_blk(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
-    auto kern = block_kernel<KW, COUNT, OutT, EP, MINB>;
-    const size_t smem = block_kernel_smem_bytes(L.n_step_words, L.E, L.cx.B, EP);
+    auto kern = block_kernel<KW, COUNT, OutT, EP, MINB, SIGMA>;
+    const size_t smem = block_kernel_smem_bytes(L.n_step_words, L.E, L.cx.B, EP, SIGMA);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -221,6 +229,13 @@ cudaError_t launch_blk(const MapLaunch& L, int sm_count, cudaStream_t stream)
 template <int KW, int MINB>
 cudaError_t launch_blk_kw(const MapLaunch& L, int sm_count, cudaStream_t stream)
 {
+    if (L.sigma == 5) { // (never with --exclude-pseudo: block_kernel_applies)
+        if (L.value_bits == 16)
+            return L.count_fetches ? launch_blk<KW, true, uint16_t, false, MINB, 5>(L, sm_count, stream)
+                                   : launch_blk<KW, false, uint16_t, false, MINB, 5>(L, sm_count, stream);
+        return L.count_fetches ? launch_blk<KW, true, uint8_t, false, MINB, 5>(L, sm_count, stream)
+                               : launch_blk<KW, false, uint8_t, false, MINB, 5>(L, sm_count, stream);
+    }
     if (L.exclude_pseudo) // (the counting instantiation is not built for --exclude-pseudo, as in map_kernel.cu)
         return L.value_bits == 16 ? launch_blk<KW, false, uint16_t, true, MINB>(L, sm_count, stream)
                                   : launch_blk<KW, false, uint8_t, true, MINB>(L, sm_count, stream);
@@ -233,17 +248,17 @@ cudaError_t launch_blk_kw(const MapLaunch& L, int sm_count, cudaStream_t stream)
 
 } // namespace
 
-size_t block_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool ep)
+size_t block_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool ep, uint32_t sigma)
 {
     const size_t tables = align32(n_step_words) + align32((B + 1) * kMaxSearches * kStartWords) + align32(2 * (kMaxBlockKmers + 1));
-    return (tables + ((size_t)frame_store_words(E, B, ep, 4, true) + kPendSlots * kPendWords) * kThreads) * sizeof(uint32_t);
+    return (tables + ((size_t)frame_store_words(E, B, ep, (int)sigma, true) + kPendSlots * kPendWords) * kThreads) * sizeof(uint32_t);
 }
 
 bool block_kernel_applies(const MapLaunch& L)
 {
     // (E = 3: walks dominate and the general kernel, whose lanes refill one by one, is still the faster of the two, 16.5 vs
     // 18.7 ms; E = 4, with seven searches and 4000 keys per position, is 2.7x faster here: profiles/r02/s9_sweep_*.txt)
-    return L.keylist != nullptr && L.sigma == 4 && L.E >= 1 && (L.E != 3 || L.force_block_kernel) && L.cx.K + L.cx.B - 1 <= 64 && L.cx.loc_rows == nullptr && L.loc_off == nullptr &&
+    return L.keylist != nullptr && (L.sigma == 4 || (L.sigma == 5 && L.cx.skip_n && !L.exclude_pseudo)) && L.E >= 1 && (L.E != 3 || L.force_block_kernel) && L.cx.K + L.cx.B - 1 <= 64 && L.cx.loc_rows == nullptr && L.loc_off == nullptr &&
            !(L.exclude_pseudo && L.count_fetches);
 }
 

@@ -105,6 +105,10 @@ struct gmb_index {
     // before uploads nothing but its work ranges
     std::vector<std::unique_ptr<struct MapPlan>> plans;
     uint64_t plan_clock = 0;
+    // Dna5 indices: the N pass of calls whose searches skip the text's N, by (K, E, strands); nfix_off: this index has
+    // too many windows with N for it (every call then walks the N children as before)
+    std::vector<std::unique_ptr<struct NFix>> nfix;
+    bool nfix_off = false;
     // progress of the call in flight (gmb_progress): positions of finished pieces + chunks the kernel has handed out
     // d_counters[15] = positions of the pieces already finished (written in stream order by the host-output pipeline)
     std::atomic<uint64_t> prog_total{0}, prog_chunk{0};
@@ -126,6 +130,25 @@ struct MapPlan {
     const uint2* d_keys = nullptr;    // E >= 1, block_kernel.cu: flat key lists by block size (inside d_tables)
     uint32_t key_off[kMaxBlockKmers + 1] = {}, key_n[kMaxBlockKmers + 1] = {};
     ~MapPlan() { if (d_tables) cudaFree(d_tables); }
+};
+
+// What a Dna5 call whose searches skip the text's N (MapCtx::skip_n) adds afterwards: the text windows with 1..E N
+// (n_win of them, found by one pass over the N mask) were located through the index like csv queries, which gives
+//   win_count[i]  the whole count of window win_pos[i] as a query (it overwrites what the search left there), and
+//   hits          one entry per (N window, strand, occurrence) whose own window holds no N: by the symmetry of the
+//                 Hamming distance (N mismatching everything on either side) these are exactly the alignments of the
+//                 N-free queries to text windows with N — the ones the searches skipped; + 1 each.
+// Positions in the concatenated text.  Built once per (K, E, strands) and handle, applied after every search kernel
+// to the positions of its work ranges.
+struct NFix {
+    uint32_t K = 0, E = 0;
+    bool revcompl = false;
+    uint64_t n_win = 0, n_hits = 0;
+    uint32_t* d_win_pos = nullptr;
+    uint32_t* d_win_count = nullptr;
+    uint32_t* d_hits = nullptr;
+    double build_ms = 0;
+    ~NFix() { if (d_win_pos) cudaFree(d_win_pos); if (d_win_count) cudaFree(d_win_count); if (d_hits) cudaFree(d_hits); }
 };
 
 namespace {
@@ -154,6 +177,7 @@ void fill_ctx(const gmb_index* ix, MapCtx& cx)
     cx.nmask = ix->h.sigma == 5 ? reinterpret_cast<const uint64_t*>(base + ix->h.off_nmask) : nullptr;
     cx.n_text = ix->h.n_text;
     cx.E = 0;
+    cx.skip_n = 0;
 }
 
 struct JumpNeeds { bool uni[17] = {}, lof[17] = {}, full[17] = {}; uint32_t top = 0; };
@@ -573,6 +597,7 @@ int gmb_index_close(gmb_index* ix)
     if (ix->d_seq_to_file) cudaFree(ix->d_seq_to_file);
     for (int d = 0; d < 17; ++d) { if (ix->jt_uni[d]) cudaFree(ix->jt_uni[d]); if (ix->jt_lof[d]) cudaFree(ix->jt_lof[d]); if (ix->jt_full[d]) cudaFree(ix->jt_full[d]); }
     ix->plans.clear();
+    ix->nfix.clear();
     if (ix->s_progress) cudaStreamDestroy(ix->s_progress);
     if (ix->s_compute) cudaStreamDestroy(ix->s_compute);
     if (ix->s_copy) cudaStreamDestroy(ix->s_copy);
@@ -641,6 +666,8 @@ namespace {
 int ep_many_files(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len, const uint64_t* chrom_cum,
                   uint32_t n_chrom, const uint64_t (*intervals)[2], uint64_t n_intervals, const uint32_t* seq_to_file,
                   uint32_t n_seq, uint64_t pos_begin, uint64_t pos_end, void* out_device, gmb_map_stats* stats);
+bool dna5_nfree(const gmb_index* ix, const gmb_params* p);
+int ensure_nfix(gmb_index* ix, const gmb_params* p, const NFix** out);
 }
 
 // One pass of the locate path (gmb_map_locations): counting (rows == nullptr: out_device receives two uint32 list
@@ -649,12 +676,14 @@ struct LocPass {
     const uint64_t* off;
     uint32_t* rows;
     uint64_t pos0;
+    const uint32_t* pos_list = nullptr; // position j stands for text position pos_list[j] (MapLaunch::loc_list)
 };
 
 // The search plan of a configuration: step tables, block size, how every search enters through the jump tables —
 // built once per handle and configuration, with its tables left on the device.  (Round 1 rebuilt and re-uploaded all
 // of it on every call, i.e. once per 32 Mi-position piece of the host-output pipeline.)
-static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool loc, cudaStream_t stream, MapPlan** out)
+// nfree: Dna5 index, the searches skip the text's N (dna5_nfree below)
+static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool loc, bool nfree, cudaStream_t stream, MapPlan** out)
 {
     uint32_t want_b = p->block_kmers;
     if (want_b == 0) { const char* env = std::getenv("GMB_BLOCK_KMERS"); if (env && *env) want_b = (uint32_t)std::atoi(env); }
@@ -666,7 +695,7 @@ static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool l
     const char* e2 = std::getenv("GMB_PART_WEIGHTS");
     const char* e3 = std::getenv("GMB_JUMP_VARIANTS");
     char buf[200];
-    std::snprintf(buf, sizeof buf, "%u/%u/%u/%d/%d/%d/%llu/", p->K, p->E, want_b, sync_tables ? 1 : 0, loc ? 1 : 0, want,
+    std::snprintf(buf, sizeof buf, "%u/%u/%u/%d/%d/%d/%d/%llu/", p->K, p->E, want_b, sync_tables ? 1 : 0, loc ? 1 : 0, nfree ? 1 : 0, want,
                   (unsigned long long)model_n);
     const char* e4 = std::getenv("GMB_LOCATE");
     const char* e5 = std::getenv("GMB_BLOCK_KERNEL");
@@ -682,17 +711,17 @@ static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool l
         if (!np) return fail(GMB_ERR_NOMEM, "out of host memory");
         np->key = key;
         BlockTables& tabs = np->tabs;
-        if (!build_block_tables(p->K, p->E, want_b, sync_tables, tabs, err, model_n, block_bases(ix->h.sigma))) return fail(GMB_ERR_UNSUPPORTED, err);
+        if (!build_block_tables(p->K, p->E, want_b, sync_tables, tabs, err, model_n, block_bases(ix->h.sigma), nfree)) return fail(GMB_ERR_UNSUPPORTED, err);
         // --exclude-pseudo is asked for on indices of several near-identical genomes: every infix hit then stands for about
         // as many real occurrences as there are files, all of them completed window by window, and the planner's iid model
         // (chance hits only) picks blocks that are too large: 10 x 300 Mbp, K = 50, E = 2: 531 M positions/s with its
         // choice, 643 M with 4 k-mers per block, 197 M with 15 (profiles/r02/s19_pangenome_blocks.txt)
         if (p->exclude_pseudo && want_b == 0 && tabs.B > 4 &&
-            !build_block_tables(p->K, p->E, 4, sync_tables, tabs, err, model_n, block_bases(ix->h.sigma))) return fail(GMB_ERR_UNSUPPORTED, err);
+            !build_block_tables(p->K, p->E, 4, sync_tables, tabs, err, model_n, block_bases(ix->h.sigma), nfree)) return fail(GMB_ERR_UNSUPPORTED, err);
         // the tables and the per-chain frame store live in shared memory: shrink the block if they do not fit
         while (tabs.B > 1 && (map_kernel_smem_bytes((uint32_t)tabs.steps.size(), p->E, tabs.B, sync_tables, ix->h.sigma, true) > (200u << 10) ||
                               tabs.steps.size() * 4 + (tabs.B + 1) * kMaxSearches * sizeof(SearchStart) > kTableBytes))
-            if (!build_block_tables(p->K, p->E, tabs.B - 1, sync_tables, tabs, err, model_n, block_bases(ix->h.sigma))) return fail(GMB_ERR_UNSUPPORTED, err);
+            if (!build_block_tables(p->K, p->E, tabs.B - 1, sync_tables, tabs, err, model_n, block_bases(ix->h.sigma), nfree)) return fail(GMB_ERR_UNSUPPORTED, err);
         if (ix->plans.size() >= 12) { // drop the least recently used plan
             size_t lru = 0;
             for (size_t i = 1; i < ix->plans.size(); ++i) if (ix->plans[i]->last_use < ix->plans[lru]->last_use) lru = i;
@@ -722,7 +751,7 @@ static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool l
         for (uint32_t cnt = 0; cnt <= tabs.B; ++cnt) {
             JumpPlan& pl = plans[cnt];
             if (cnt == 0) { pl = JumpPlan(); std::memset(pl.depth, 0, sizeof(pl.depth)); pl.max_depth = 0; continue; }
-            plan_jump_tables(tabs.infix[cnt], maxd, pl, p->E, model_n, ix->h.sigma, cnt, tabs.B > 1 && !loc);
+            plan_jump_tables(tabs.infix[cnt], maxd, pl, p->E, model_n, ix->h.sigma, cnt, tabs.B > 1 && !loc, nfree);
             plan_depth = std::max(plan_depth, pl.max_depth);
         }
         needs = jump_needs(plans, use_full, all_full);
@@ -766,7 +795,7 @@ static int get_plan(gmb_index* ix, const gmb_params* p, bool sync_tables, bool l
     // block_kernel.cu: every key of every search of one strand as a flat list (the 3^m substitutions of a set of m offsets
     // spelled out as XOR masks on the key window), when every search of every block size enters through 16-byte entries
     KeyLists keylist;
-    bool block_ok = p->E >= 1 && !loc && all_full && ix->h.sigma == 4 && p->K + tabs.B - 1 <= 64;
+    bool block_ok = p->E >= 1 && !loc && all_full && (ix->h.sigma == 4 || nfree) && p->K + tabs.B - 1 <= 64;
     {
         const char* env = std::getenv("GMB_BLOCK_KERNEL"); // "0": E >= 1 through the general kernel (A/B measurements)
         if (env && env[0] == '0') block_ok = false;
@@ -843,9 +872,17 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
     if (n_intervals && !intervals) return fail(GMB_ERR_ARG, "intervals is NULL");
     CU(cudaSetDevice(ix->device));
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    // Dna5: with the suffix array in HBM the searches of an E >= 1 call skip the text's N and enter through substituted
+    // keys like on a Dna4 index; the alignments to the text windows with N come from the N pass (NFix)
+    const NFix* nfix = nullptr;
+    if (!loc && dna5_nfree(ix, p)) {
+        int rcn = ensure_nfix(ix, p, &nfix);
+        if (rcn != GMB_OK) return rcn;
+    }
+    const bool nfree = nfix != nullptr;
     MapPlan* plan = nullptr;
     {
-        int rcp = get_plan(ix, p, sync_tables, loc != nullptr, stream, &plan);
+        int rcp = get_plan(ix, p, sync_tables, loc != nullptr, nfree, stream, &plan);
         if (rcp != GMB_OK) return rcp;
     }
     const BlockTables& tabs = plan->tabs;
@@ -858,7 +895,7 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
     const char* blk_env = std::getenv("GMB_BLOCK_KERNEL"); // "0": never, "2": also for E >= 3 (measurements)
     const bool force_block = blk_env && blk_env[0] == '2';
     const bool block_kernel = plan->d_keys != nullptr && (p->E != 3 || force_block) &&
-                              block_kernel_smem_bytes((uint32_t)tabs.steps.size(), p->E, tabs.B, p->exclude_pseudo != 0) <= (200u << 10);
+                              block_kernel_smem_bytes((uint32_t)tabs.steps.size(), p->E, tabs.B, p->exclude_pseudo != 0, ix->h.sigma) <= (200u << 10);
     const uint64_t chunk = block_kernel ? 32ull * tabs.B : std::max<uint64_t>(tabs.B, kChunk / tabs.B * tabs.B);
     std::vector<uint64_t> host_ranges(3 * (size_t)nr + 1); // begin[nr], end[nr], chunk_prefix[nr+1]
     uint64_t total = 0, chunks = 0;
@@ -900,6 +937,7 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
     L.cx.n_search = tabs.n_search;
     L.cx.n_strands = p->revcompl ? 2u : 1u;
     L.cx.maxv = p->value_bits == 16 ? 65535u : 255u;
+    L.cx.skip_n = nfree ? 1u : 0u;
     L.E = p->E;
     L.sigma = ix->h.sigma;
     L.text = reinterpret_cast<const uint64_t*>(base + ix->h.off_text);
@@ -933,17 +971,23 @@ static int map_device_impl(gmb_index* ix, const gmb_params* p_in, uint64_t text_
     L.cx.loc_rows = loc ? loc->rows : nullptr;
     L.loc_off = loc ? loc->off : nullptr;
     L.loc_pos0 = loc ? loc->pos0 : 0;
+    L.loc_list = loc ? loc->pos_list : nullptr;
 
     if (stats) { stats->jump_depth = plan_depth; stats->kernel_launches = 1; stats->block_kmers = tabs.B; }
     if (stats && timed) CU(cudaEventRecord(ix->ev0, stream));
     CU(loc ? launch_locate_kernel(L, ix->sm_count, stream) : launch_map_kernel(L, ix->sm_count, stream));
+    if (nfix) { // the N pass: whole counts of the windows with N, then + 1 per alignment to one of them
+        CU(nfix_apply(nfix->d_win_pos, nfix->d_win_count, nfix->n_win, text_begin, L.range_begin, L.range_end, nr, out_device, p->value_bits, stream));
+        CU(nfix_apply(nfix->d_hits, nullptr, nfix->n_hits, text_begin, L.range_begin, L.range_end, nr, out_device, p->value_bits, stream));
+        if (stats) stats->kernel_launches = 3;
+    }
     if (stats && timed) {
         CU(cudaEventRecord(ix->ev1, stream));
         CU(cudaEventSynchronize(ix->ev1));
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
         stats->kernel_ms = ms;
-        stats->kernel_launches = 1;
+        stats->kernel_launches = nfix ? 3 : 1;
         stats->jump_depth = plan_depth;
         stats->block_kmers = tabs.B;
         if (L.count_fetches) {
@@ -1101,7 +1145,7 @@ struct LocatePiece {
 
 int locate_piece(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64_t text_len, const uint64_t* chrom_cum,
                  uint32_t n_chrom, const uint64_t (*intervals)[2], uint64_t n_intervals, uint64_t pos_begin,
-                 uint64_t pos_end, uint64_t max_locations, LocatePiece& P)
+                 uint64_t pos_end, uint64_t max_locations, LocatePiece& P, const uint32_t* pos_list = nullptr)
 {
     const uint64_t kMaxPositions = 4ull << 20, kMaxRows = 1ull << 30;
     if (pos_end - pos_begin > kMaxPositions) pos_end = pos_begin + kMaxPositions;
@@ -1117,7 +1161,7 @@ int locate_piece(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64
     CU(cudaMemsetAsync(P.counts.p, 0, (n_lists + 1) * 4, nullptr));
     gmb_map_stats st1, st2;
     std::memset(&st2, 0, sizeof(st2));
-    LocPass pass1{nullptr, nullptr, pos_begin};
+    LocPass pass1{nullptr, nullptr, pos_begin, pos_list};
     int rc = map_device_impl(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, nullptr, 0, pos_begin,
                              pos_end, P.counts.p, nullptr, &st1, true, &pass1);
     if (rc != GMB_OK) return rc;
@@ -1147,7 +1191,7 @@ int locate_piece(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint64
         DevBuf temp2;
         CU(P.rows.alloc(P.n_rows * 4));
         CU(P.sorted.alloc(P.n_rows * 4));
-        LocPass pass2{P.offs.as<uint64_t>(), P.rows.as<uint32_t>(), pos_begin};
+        LocPass pass2{P.offs.as<uint64_t>(), P.rows.as<uint32_t>(), pos_begin, pos_list};
         rc = map_device_impl(ix, p, text_begin, text_len, chrom_cum, n_chrom, intervals, n_intervals, nullptr, 0, pos_begin,
                              pos_begin + m, P.counts.p, nullptr, &st2, true, &pass2);
         if (rc != GMB_OK) return rc;
@@ -1188,6 +1232,92 @@ int ep_many_files(gmb_index* ix, const gmb_params* p, uint64_t text_begin, uint6
         b += P.m;
     }
     if (stats) stats->positions = pos_end - pos_begin;
+    return GMB_OK;
+}
+
+// Does this call run with searches that skip the text's N (plus the N pass)?  Dna5 index, E >= 1, plain counts, the
+// suffix array in HBM (the N pass locates).  GMB_DNA5_NFREE=0: never (A/B measurements).
+bool dna5_nfree(const gmb_index* ix, const gmb_params* p)
+{
+    const char* env = std::getenv("GMB_DNA5_NFREE");
+    return ix->h.sigma == 5 && p->E >= 1 && !p->exclude_pseudo && ix->h.off_sa != 0 && !ix->nfix_off && !(env && env[0] == '0');
+}
+
+// The N pass of (K, E, strands), built on first use: *out stays nullptr when the index has too many windows with N
+// for it to pay (the call then runs as before, N children walked).
+int ensure_nfix(gmb_index* ix, const gmb_params* p, const NFix** out)
+{
+    *out = nullptr;
+    const bool rc = p->revcompl != 0;
+    for (auto& q : ix->nfix)
+        if (q->K == p->K && q->E == p->E && q->revcompl == rc) { *out = q.get(); return GMB_OK; }
+    CU(cudaSetDevice(ix->device));
+    CU(cudaDeviceSynchronize()); // the locate passes below use the handle's scratch on the default stream
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    CU(cudaEventCreate(&t0)); CU(cudaEventCreate(&t1));
+    CU(cudaEventRecord(t0, nullptr));
+    std::unique_ptr<NFix> nf(new (std::nothrow) NFix);
+    if (!nf) return fail(GMB_ERR_NOMEM, "out of host memory");
+    nf->K = p->K; nf->E = p->E; nf->revcompl = rc;
+    const uint64_t n_text = ix->h.n_text;
+    // 1. the windows: at most 1/64 of the text (an assembly has a few hundred gaps; every gap edge gives 2 E windows)
+    const uint64_t cap = std::max<uint64_t>(1024, std::min<uint64_t>(n_text / 64, 32ull << 20));
+    DevBuf win, counter;
+    CU(win.alloc(cap * 4));
+    CU(counter.alloc(8));
+    CU(cudaMemsetAsync(counter.p, 0, 8, nullptr));
+    const uint8_t* base = ix->d_blob;
+    const uint64_t* nmask = reinterpret_cast<const uint64_t*>(base + ix->h.off_nmask);
+    const uint32_t* seq_start = reinterpret_cast<const uint32_t*>(base + ix->h.off_seq_start);
+    CU(nfix_collect_windows(nmask, n_text, seq_start, ix->h.n_seq, p->K, p->E, win.as<uint32_t>(), counter.as<unsigned long long>(), cap, nullptr));
+    unsigned long long n_win = 0;
+    CU(cudaMemcpy(&n_win, counter.p, 8, cudaMemcpyDeviceToHost));
+    if (n_win > cap || n_win + p->K - 1 > n_text) { ix->nfix_off = true; cudaEventDestroy(t0); cudaEventDestroy(t1); return GMB_OK; }
+    nf->n_win = n_win;
+    std::vector<uint32_t> hits_host;
+    if (n_win) {
+        CU(cudaMalloc(&nf->d_win_pos, n_win * 4));
+        CU(cudaMemcpy(nf->d_win_pos, win.p, n_win * 4, cudaMemcpyDeviceToDevice));
+        CU(cudaMalloc(&nf->d_win_count, n_win * 4));
+        // 2. locate them like csv queries: "positions" are list indices (LocPass::pos_list), one pseudo chromosome
+        gmb_params q = *p;
+        q.exclude_pseudo = 0; q.count_fetches = 0;
+        const uint64_t list_len = n_win + p->K - 1, cum[2] = {0, list_len};
+        const uint64_t kMaxHits = 256ull << 20;
+        for (uint64_t b = 0; b < n_win;) {
+            LocatePiece P;
+            int rcl = locate_piece(ix, &q, 0, list_len, cum, 1, nullptr, 0, b, n_win, 0, P, nf->d_win_pos);
+            if (rcl != GMB_OK) return rcl;
+            DevBuf hits;
+            CU(hits.alloc(P.n_rows * 4));
+            CU(cudaMemsetAsync(counter.p, 0, 8, nullptr));
+            CU(nfix_collect_hits(P.sorted.as<uint32_t>(), P.offs.as<uint64_t>(), P.m, P.n_rows, seq_start, ix->h.n_seq, nmask, p->K,
+                                 nf->d_win_count + b, hits.as<uint32_t>(), counter.as<unsigned long long>(), nullptr));
+            unsigned long long n_h = 0;
+            CU(cudaMemcpy(&n_h, counter.p, 8, cudaMemcpyDeviceToHost));
+            if (hits_host.size() + n_h > kMaxHits) { ix->nfix_off = true; cudaEventDestroy(t0); cudaEventDestroy(t1); return GMB_OK; }
+            const size_t at = hits_host.size();
+            hits_host.resize(at + n_h);
+            if (n_h) CU(cudaMemcpy(hits_host.data() + at, hits.p, n_h * 4, cudaMemcpyDeviceToHost));
+            b += P.m;
+        }
+    }
+    nf->n_hits = hits_host.size();
+    if (nf->n_hits) {
+        CU(cudaMalloc(&nf->d_hits, nf->n_hits * 4));
+        CU(cudaMemcpy(nf->d_hits, hits_host.data(), nf->n_hits * 4, cudaMemcpyHostToDevice));
+    }
+    CU(cudaEventRecord(t1, nullptr));
+    CU(cudaEventSynchronize(t1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    nf->build_ms = ms;
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    if (const char* v = std::getenv("GMB_VERBOSE"); v && v[0] == '1')
+        std::fprintf(stderr, "[gmb] N pass of (K=%u, E=%u): %llu windows with N, %llu alignments to them, built in %.1f ms\n", p->K, p->E,
+                     (unsigned long long)nf->n_win, (unsigned long long)nf->n_hits, ms);
+    *out = nf.get();
+    ix->nfix.push_back(std::move(nf));
     return GMB_OK;
 }
 } // namespace

@@ -451,6 +451,10 @@ struct MapCtx {
     const uint64_t* text;
     const uint64_t* nmask;
     uint64_t n_text;
+    // Dna5 indices: the searches never match a text N — the call counts the alignments to text windows WITHOUT an N,
+    // which lets every search enter through substituted keys as on a Dna4 index; the alignments to the (few) text
+    // windows with 1..E N are added afterwards by a pass of their own (capi.cu: NFix)
+    uint32_t skip_n;
 };
 
 struct Node { uint32_t lo_f, lo_r, size; };
@@ -867,6 +871,7 @@ GMB_HD void verify_located_key(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& c
     const uint32_t Li = K - cnt + 1, NL = K + cnt - 1, E = cx.E;
     const uint32_t tab = (BLK ? cx.p1_off[cnt] : 0u) + st.s * Li;
     if (fetches) ++fetches->located;
+    [[maybe_unused]] uint64_t tn[KW] = {}; // Dna5, skip_n: the text's N (a window holding one is not counted)
     if (st.strand == 0 && own_key && !(SIGMA == 5 && st.has_n)) {
         // the query's own window is an occurrence of its own key, and the key occurs once: this is the query itself
         // (a needle with an N outside the key window is compared like any other candidate: its N never matches)
@@ -901,7 +906,7 @@ GMB_HD void verify_located_key(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& c
         for (int k = 0; k < KW; ++k) {
             const uint64_t x = st.pat.w[k] ^ tp.w[k];
             mm[k] = (x | (x >> 1)) & 0x5555555555555555ull;
-            if constexpr (SIGMA == 5) mm[k] |= spread_bits(st.pat.nm[k] | tp.nm[k]);
+            if constexpr (SIGMA == 5) { mm[k] |= spread_bits(st.pat.nm[k] | tp.nm[k]); tn[k] = spread_bits(tp.nm[k]); }
         }
     }
     if (count_mismatches<KW>(mm, cnt - 1u, K) > E) return;
@@ -919,6 +924,7 @@ GMB_HD void verify_located_key(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& c
     uint64_t sb = 0, se = 0;
     for (uint32_t w = 0; w < cnt; ++w) {
         if (count_mismatches<KW>(mm, w, w + K) > E) continue;
+        if constexpr (SIGMA == 5) { if (cx.skip_n && count_mismatches<KW>(tn, w, w + K) != 0u) continue; }
         if (sq == 0xffffffffu) {
             uint32_t a = 0, b = cx.n_seq;
             while (b - a > 1) {
@@ -1055,6 +1061,7 @@ GMB_HD bool chain_step(Chain<KW, SIGMA>& st, Frames& fr, const MapCtx& cx, Fetch
 #pragma unroll
         for (int k = 0; k < SIGMA; ++k)
             if (ch.n[k] && (p == (uint32_t)k ? hit_ok : mis_ok)) ok |= 1u << k;
+        if (SIGMA == 5 && cx.skip_n) ok &= 0xfu; // the N child: text windows with an N are not this pass's
         const uint32_t hit_bit = p == kNone ? 0u : (1u << p);
 
         if (st.t + 1 == T && (in_flank || cnt == 1)) {

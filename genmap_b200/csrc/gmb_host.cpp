@@ -150,10 +150,12 @@ bool located_enabled(uint64_t n_bwt, uint32_t sigma)
     return n_bwt != 0 && (sigma == 4 || sigma == 5) && !(env && env[0] == '0');
 }
 
-bool variants_enabled(uint64_t n_bwt, uint32_t sigma)
+// nfree: the searches of this call never match a text N (gmb_core.h: MapCtx::skip_n; the alignments to text windows with
+// an N are counted by a pass of their own, capi.cu), so a Dna5 index is entered through substituted keys like a Dna4 one
+bool variants_enabled(uint64_t n_bwt, uint32_t sigma, bool nfree)
 {
     const char* env = std::getenv("GMB_JUMP_VARIANTS"); // "0": enter every search through its error-free prefix only
-    return n_bwt != 0 && sigma == 4 && !(env && env[0] == '0');
+    return n_bwt != 0 && (sigma == 4 || (sigma == 5 && nfree)) && !(env && env[0] == '0');
 }
 
 double expected_fetches(const SchemeDef& sd, const uint32_t* len, uint32_t E, double N, uint32_t B, uint32_t jump_max, uint32_t block_bases,
@@ -180,9 +182,10 @@ double expected_fetches(const SchemeDef& sd, const uint32_t* len, uint32_t E, do
 }
 
 // steepest descent over single-character moves between parts, from the reference's equal split
-void choose_part_lengths(const SchemeDef& sd, uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t B, uint32_t block_bases, uint32_t* len)
+void choose_part_lengths(const SchemeDef& sd, uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t B, uint32_t block_bases, uint32_t* len,
+                         bool nfree)
 {
-    const bool av = B > 1 && variants_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u); // (the one-k-mer kernel has none)
+    const bool av = B > 1 && variants_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u, nfree); // (the one-k-mer kernel has none)
     const bool loc = located_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u);
     const uint32_t nb = sd.n_blocks;
     if (nb < 2 || n_bwt == 0 || K < 2 * nb) return;
@@ -207,7 +210,7 @@ void choose_part_lengths(const SchemeDef& sd, uint32_t K, uint32_t E, uint64_t n
 } // namespace
 
 bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err, bool force_sync, uint64_t n_bwt, uint32_t block_kmers,
-                       uint32_t block_bases)
+                       uint32_t block_bases, bool nfree)
 {
     if (E > kMaxE) { err = "E > 4 not yet supported."; return false; } // src/mappability.hpp:187
     if (K < E + 2) { err = "K must be at least E + 2."; return false; } // undefined in the reference (rc 139)
@@ -218,7 +221,7 @@ bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err
     uint32_t len[6], begin[6];
     for (uint32_t b = 0; b < nb; ++b) len[b] = K / nb + (b < K % nb);
     const char* model_env = std::getenv("GMB_PART_MODEL"); // "0": keep the reference's equal split
-    if (n_bwt != 0 && !(model_env && model_env[0] == '0')) choose_part_lengths(sd, K, E, n_bwt, block_kmers ? block_kmers : 1, block_bases, len);
+    if (n_bwt != 0 && !(model_env && model_env[0] == '0')) choose_part_lengths(sd, K, E, n_bwt, block_kmers ? block_kmers : 1, block_bases, len, nfree);
     // Tuning knob (results never depend on it: any split into nb non-empty parts keeps the scheme exhaustive and
     // non-redundant, only the size of the search tree changes): relative part lengths, e.g. GMB_PART_WEIGHTS=5,5,8,8
     if (const char* env = std::getenv("GMB_PART_WEIGHTS")) {
@@ -294,7 +297,7 @@ uint32_t default_block_kmers(uint32_t K, uint32_t E)
 // Block size by the same model: expected fetches per position of the best split for every B; the largest B within
 // 3 % of the minimum (equal fetch counts favour the larger block: fewer chain start-ups).  Measured at 3 Gbp, K = 30
 // (profiles/r01/s19_sweep_model1.txt): the model is 4 % above the counted fetches for B = 3..8 and ranks them alike.
-uint32_t model_block_kmers(uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t block_bases)
+uint32_t model_block_kmers(uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t block_bases, bool nfree)
 {
     if (E == 0 || n_bwt == 0) return default_block_kmers(K, E);
     const SchemeDef& sd = kSchemes[E];
@@ -306,9 +309,9 @@ uint32_t model_block_kmers(uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t bloc
         const uint32_t Li = K - B + 1;
         uint32_t len[6];
         for (uint32_t b = 0; b < sd.n_blocks; ++b) len[b] = Li / sd.n_blocks + (b < Li % sd.n_blocks);
-        choose_part_lengths(sd, Li, E, n_bwt, B, block_bases, len);
+        choose_part_lengths(sd, Li, E, n_bwt, B, block_bases, len, nfree);
         cost[B] = expected_fetches(sd, len, E, (double)n_bwt, B, default_jump_depth(n_bwt), block_bases,
-                                   B > 1 && variants_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u),
+                                   B > 1 && variants_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u, nfree),
                                    located_enabled(n_bwt, block_bases == kBlockBases5 ? 5u : 4u));
         // a Dna5 needle longer than 32 characters no longer fits one register word per plane: measured 1.55x slower per
         // fetch (profiles/r01/s25_sweep_dna5.txt vs s20_sweep_dna5.txt)
@@ -324,11 +327,11 @@ uint32_t model_block_kmers(uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t bloc
 }
 
 static bool build_block_tables_uncached(uint32_t K, uint32_t E, uint32_t B, bool force_sync, BlockTables& out, std::string& err,
-                                        uint64_t n_bwt, uint32_t block_bases);
+                                        uint64_t n_bwt, uint32_t block_bases, bool nfree);
 
 // The tables of one (K, E, B, text size) are asked for by every map call (every pipeline piece): keep the last few.
 bool build_block_tables(uint32_t K, uint32_t E, uint32_t B, bool force_sync, BlockTables& out, std::string& err, uint64_t n_bwt,
-                        uint32_t block_bases)
+                        uint32_t block_bases, bool nfree)
 {
     struct Entry { std::string key; BlockTables tabs; };
     static std::mutex mu;
@@ -336,7 +339,7 @@ bool build_block_tables(uint32_t K, uint32_t E, uint32_t B, bool force_sync, Blo
     const char* e1 = std::getenv("GMB_PART_MODEL");
     const char* e2 = std::getenv("GMB_PART_WEIGHTS");
     char buf[160];
-    std::snprintf(buf, sizeof buf, "%u/%u/%u/%d/%llu/%u/", K, E, B, force_sync ? 1 : 0, (unsigned long long)n_bwt, block_bases);
+    std::snprintf(buf, sizeof buf, "%u/%u/%u/%d/%llu/%u/%d/", K, E, B, force_sync ? 1 : 0, (unsigned long long)n_bwt, block_bases, nfree ? 1 : 0);
     const char* e3 = std::getenv("GMB_JUMP_VARIANTS");
     const char* e4 = std::getenv("GMB_LOCATE");
     const std::string key = std::string(buf) + (e1 ? e1 : "") + "/" + (e2 ? e2 : "") + "/" + (e3 ? e3 : "") + "/" + (e4 ? e4 : "");
@@ -345,7 +348,7 @@ bool build_block_tables(uint32_t K, uint32_t E, uint32_t B, bool force_sync, Blo
         for (const Entry& en : cache)
             if (en.key == key) { out = en.tabs; return true; }
     }
-    if (!build_block_tables_uncached(K, E, B, force_sync, out, err, n_bwt, block_bases)) return false;
+    if (!build_block_tables_uncached(K, E, B, force_sync, out, err, n_bwt, block_bases, nfree)) return false;
     std::lock_guard<std::mutex> lock(mu);
     if (cache.size() >= 8) cache.erase(cache.begin());
     cache.push_back(Entry{key, out});
@@ -353,13 +356,13 @@ bool build_block_tables(uint32_t K, uint32_t E, uint32_t B, bool force_sync, Blo
 }
 
 static bool build_block_tables_uncached(uint32_t K, uint32_t E, uint32_t B, bool force_sync, BlockTables& out, std::string& err,
-                                        uint64_t n_bwt, uint32_t block_bases)
+                                        uint64_t n_bwt, uint32_t block_bases, bool nfree)
 {
     if (E > kMaxE) { err = "E > 4 not yet supported."; return false; }
     if (K < E + 2) { err = "K must be at least E + 2."; return false; }
     if (B == 0) {
         const char* model_env = std::getenv("GMB_PART_MODEL");
-        B = (n_bwt != 0 && !(model_env && model_env[0] == '0')) ? model_block_kmers(K, E, n_bwt, block_bases) : default_block_kmers(K, E);
+        B = (n_bwt != 0 && !(model_env && model_env[0] == '0')) ? model_block_kmers(K, E, n_bwt, block_bases, nfree) : default_block_kmers(K, E);
     }
     if (B > kMaxBlockKmers) B = kMaxBlockKmers;
     while (B > 1 && (B + E + 1 > K || K + B - 2 > 255)) --B; // the infix keeps >= E + 2 characters; offsets fit 8 bits
@@ -370,7 +373,7 @@ static bool build_block_tables_uncached(uint32_t K, uint32_t E, uint32_t B, bool
     for (uint32_t cnt = 1; cnt <= B; ++cnt) {
         const uint32_t Li = K - cnt + 1;
         StepTables& t = out.infix[cnt];
-        if (!build_step_tables(Li, E, t, err, force_sync || cnt > 1, n_bwt, cnt, block_bases)) return false; // flanks need both intervals
+        if (!build_step_tables(Li, E, t, err, force_sync || cnt > 1, n_bwt, cnt, block_bases, nfree)) return false; // flanks need both intervals
         out.n_search = t.n_search;
         out.p1_off[cnt] = (uint32_t)out.steps.size();
         for (uint32_t i = 0; i < t.n_search * Li; ++i) {
@@ -408,13 +411,13 @@ void enumerate_variants(const uint32_t* st, uint32_t d, uint32_t E, uint32_t a, 
 } // namespace
 
 void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan, uint32_t E, uint64_t n_bwt, uint32_t sigma,
-                      uint32_t block_kmers, bool allow_variants)
+                      uint32_t block_kmers, bool allow_variants, bool nfree)
 {
     plan.max_depth = 0;
     plan.variants.clear();
     for (uint32_t s = 0; s < kMaxSearches; ++s) { plan.depth[s] = 0; plan.a[s] = 0; plan.need_lof[s] = false; plan.var_off[s] = 0; plan.n_var[s] = 0; }
     const uint32_t K = tabs.K;
-    const bool allow = allow_variants && variants_enabled(n_bwt, sigma);
+    const bool allow = allow_variants && variants_enabled(n_bwt, sigma, nfree);
     if (max_depth > 16) max_depth = 16;
     std::vector<uint32_t> ub(K), lb(K), rem(K);
     SearchProfile P;
@@ -443,7 +446,6 @@ void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan
     }
 }
 
-bool jump_variants_enabled(uint64_t n_bwt, uint32_t sigma) { return variants_enabled(n_bwt, sigma); }
 
 bool build_key_lists(const BlockTables& tabs, const std::vector<JumpPlan>& plans, KeyLists& out)
 {

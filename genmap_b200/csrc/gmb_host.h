@@ -17,7 +17,7 @@ namespace gmb {
 // n_bwt != 0: the part lengths are chosen for a text of n_bwt symbols (see choose_part_lengths in gmb_host.cpp);
 // n_bwt == 0: the reference's equal split.  Results never depend on the split.
 bool build_step_tables(uint32_t K, uint32_t E, StepTables& out, std::string& err, bool force_sync = false, uint64_t n_bwt = 0,
-                       uint32_t block_kmers = 1, uint32_t block_bases = 64);
+                       uint32_t block_kmers = 1, uint32_t block_bases = 64, bool nfree = false);
 
 // Search tables of a (K,E) configuration for blocks of up to B adjacent k-mers (see Chain in gmb_core.h):
 // for every block size cnt = 1..B the scheme's step table over the common infix (K - cnt + 1 characters,
@@ -30,12 +30,13 @@ struct BlockTables {
     std::vector<uint32_t> steps;
     std::vector<StepTables> infix; // [cnt] the per-cnt infix tables (index 0 unused), kept for jump-table planning
 };
-// B == 0 picks the default for (K,E).  force_sync: see build_step_tables.
+// B == 0 picks the default for (K,E).  force_sync: see build_step_tables.  nfree (Dna5 indices): plan for searches that
+// never match a text N and are therefore entered through substituted keys like on a Dna4 index (MapCtx::skip_n).
 bool build_block_tables(uint32_t K, uint32_t E, uint32_t B, bool force_sync, BlockTables& out, std::string& err, uint64_t n_bwt = 0,
-                        uint32_t block_bases = 64);
+                        uint32_t block_bases = 64, bool nfree = false);
 uint32_t default_block_kmers(uint32_t K, uint32_t E);
 // B for a text of n_bwt symbols by the expected-fetch model (gmb_host.cpp); falls back to default_block_kmers
-uint32_t model_block_kmers(uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t block_bases);
+uint32_t model_block_kmers(uint32_t K, uint32_t E, uint64_t n_bwt, uint32_t block_bases, bool nfree = false);
 
 // How every search of a (K,E) configuration is entered through the jump tables.  depth[s]: length of the key
 // (0 = no table: start at the root); a[s]: pattern offset of the key window [a, a + depth) (the region the first
@@ -55,7 +56,7 @@ struct JumpPlan {
 // allow_variants: the launch uses the blocked instantiation of the kernel (the one-k-mer instantiation enters every
 // search through its error-free prefix only)
 void plan_jump_tables(const StepTables& tabs, uint32_t max_depth, JumpPlan& plan, uint32_t E = 0, uint64_t n_bwt = 0, uint32_t sigma = 4,
-                      uint32_t block_kmers = 1, bool allow_variants = false);
+                      uint32_t block_kmers = 1, bool allow_variants = false, bool nfree = false);
 // ceil(log4(n_bwt)) clamped to [1,16]: less than one expected occurrence per table entry
 uint32_t default_jump_depth(uint64_t n_bwt);
 

@@ -36,11 +36,14 @@ struct MapLaunch {
     // [loc_pos0, ...) in the counting pass; the fill pass (cx.loc_rows != nullptr) reads the list starts from loc_off
     const uint64_t* loc_off;
     uint64_t loc_pos0;
+    // locate instantiation, optional: "position" j stands for the text position loc_list[j] (the N pass of capi.cu
+    // locates a list of scattered windows; the work ranges then cover list indices)
+    const uint32_t* loc_list;
     // E = 0 on a Dna4 index entered through 16-byte table entries: the straight-line kernel of exact_kernel.cu
     // (nullptr: not applicable / switched off, the general kernel runs)
     const JtFull* e0_table;
     uint32_t e0_depth;
-    // E >= 1 on a Dna4 index with every search entered through 16-byte entries: the two-phase kernel of block_kernel.cu.
+    // E >= 1 with every search entered through 16-byte entries (Dna4; Dna5 with cx.skip_n): the two-phase kernel of block_kernel.cu.
     // keylist: for every block size cnt the flat list of table keys of one strand, key_n[cnt] entries from key_off[cnt]:
     // x = XOR mask of the substituted characters on the key window, y = search | errors << 4 | (nothing substituted) << 8
     // (nullptr: not applicable / switched off).  `chunk` is then 32 * B: one block per lane.
@@ -64,7 +67,7 @@ cudaError_t launch_exact_kernel(const MapLaunch& L, int sm_count, cudaStream_t s
 
 // E >= 1 (block_kernel.cu): the same
 bool block_kernel_applies(const MapLaunch& L);
-size_t block_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool ep);
+size_t block_kernel_smem_bytes(uint32_t n_step_words, uint32_t E, uint32_t B, bool ep, uint32_t sigma = 4);
 cudaError_t launch_block_kernel(const MapLaunch& L, int sm_count, cudaStream_t stream);
 
 // Locate variant (locate_kernel.cu): one k-mer per chain, every occurrence reported (csv output).

@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(kThreads, (SIGMA == 5 && BLK) ? GMB_MIN_BLOCKS
             if (need) {
                 if (got) {
                     st.cnt = (uint32_t)(jend - j < B ? jend - j : B);
-                    load_pattern(st.pat, L.text, L.nmask, L.text_begin + j, cx.K + st.cnt - 1);
+                    uint64_t at = L.text_begin + j;
+                    if constexpr (LOC) { if (L.loc_list) at = __ldg(L.loc_list + j); }
+                    load_pattern(st.pat, L.text, L.nmask, at, cx.K + st.cnt - 1);
                     chain_begin_block<KW, EP, BLK, SIGMA>(st, fr, cx, COUNT ? &lut_reads : nullptr);
                     if (LOC && cx.loc_rows) { // second pass: where this k-mer's two lists start
                         st.loc_at_fwd = L.loc_off[2 * (j - L.loc_pos0)];

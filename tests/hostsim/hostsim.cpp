@@ -50,21 +50,25 @@ void run_ranges(const MapCtx& cx, const uint64_t* text, const uint64_t* nmask, u
 }
 // The driver of block_kernel.cu on the host, one block at a time: per strand the keys of the flat list, empty
 // entries skipped, located ones verified, the others walked in subtree mode (chain_step<..., SUB>).
-template <int KW, bool EP>
-void run_ranges_blockdriver(const MapCtx& cx, const KeyLists& kl, const uint64_t* text, uint64_t text_begin,
+template <int KW, bool EP, int SIGMA>
+void run_ranges_blockdriver(const MapCtx& cx, const KeyLists& kl, const uint64_t* text, const uint64_t* nmask, uint64_t text_begin,
                             const std::vector<WorkRange>& ranges, int value_bits, void* out, FetchStats* fetches,
                             unsigned long long* lut_reads)
 {
     for (const WorkRange& r : ranges)
         for (uint64_t j0 = r.begin; j0 < r.end; j0 += cx.B) {
-            Chain<KW, 4> st;
+            Chain<KW, SIGMA> st;
             HostFrames fr;
             st.has_n = false; st.acc = 0; st.files = 0; st.var = 0; st.sub = 0; st.nsub = 1;
             const uint32_t cnt = (uint32_t)std::min<uint64_t>(cx.B, r.end - j0), NL = cx.K + cnt - 1;
             st.cnt = cnt;
-            load_pattern(st.pat, text, nullptr, text_begin + j0, NL);
+            load_pattern(st.pat, text, nmask, text_begin + j0, NL);
+            if (SIGMA == 5) st.has_n = st.pat.has_n();
             for (uint32_t w = 0; w < cnt * (EP ? 3u : 1u); ++w) fr.cset(kLeafWords + w, 0u);
-            for (uint32_t strand = 0; strand < cx.n_strands; ++strand) {
+            // Dna5: an N in the common infix is an N in every window of the block — nothing to search (the windows with
+            // 1..E N get their counts from the N pass, the others have none)
+            const bool dead = SIGMA == 5 && st.pat.has_n(cnt - 1, cx.K - cnt + 1);
+            for (uint32_t strand = 0; strand < (dead ? 0u : cx.n_strands); ++strand) {
                 st.strand = strand;
                 if (strand == 1) st.pat.reverse_complement(NL);
                 for (uint32_t g = 0; g < kl.n[cnt]; ++g) {
@@ -77,18 +81,71 @@ void run_ranges_blockdriver(const MapCtx& cx, const KeyLists& kl, const uint64_t
                     if (lut_reads) ++*lut_reads;
                     if (st.size == 0) continue;
                     if (st.size & kLocated) {
-                        verify_located_key<KW, EP, true, 4>(st, fr, cx, fetches, S, key, (y >> 8) & 1u, st.lo_r, st.lo_f, pad);
+                        verify_located_key<KW, EP, true, SIGMA>(st, fr, cx, fetches, S, key, (y >> 8) & 1u, st.lo_r, st.lo_f, pad);
                         continue;
                     }
                     st.e = (y >> 4) & 7u; st.t = S.d; st.lvmask = 0; st.win = kNoWin; st.leaf_e = 0; st.thin = false;
-                    while (chain_step<KW, EP, true, 4, HostFrames, false, true>(st, fr, cx, fetches, nullptr)) {}
+                    while (chain_step<KW, EP, true, SIGMA, HostFrames, false, true>(st, fr, cx, fetches, nullptr)) {}
                 }
             }
             for (uint32_t w = 0; w < cnt; ++w) {
-                const uint32_t v = chain_result<KW, EP, true, 4>(st, fr, cx, w);
+                const uint32_t v = chain_result<KW, EP, true, SIGMA>(st, fr, cx, w);
                 if (value_bits == 16) static_cast<uint16_t*>(out)[j0 + w] = (uint16_t)v;
                 else static_cast<uint8_t*>(out)[j0 + w] = (uint8_t)v;
             }
+        }
+}
+
+// The N pass of a Dna5 call whose searches skip the text's N (MapCtx::skip_n), by brute force: the product locates the
+// text windows with 1..E N through the index (capi.cu: NFix) — here every such window is compared with every query.
+//   * a query window with 1..E N: its whole count (every text window, N mismatching everything), overwriting;
+//   * a query window without N: + 1 per text window with 1..E N it matches with <= E mismatches, per strand.
+void nfix_bruteforce(const IndexHeader& h, const uint8_t* base, uint32_t K, uint32_t E, bool revcompl, uint64_t text_begin,
+                     const std::vector<WorkRange>& ranges, int value_bits, void* out)
+{
+    const uint64_t* text = reinterpret_cast<const uint64_t*>(base + h.off_text);
+    const uint64_t* nmask = reinterpret_cast<const uint64_t*>(base + h.off_nmask);
+    const uint32_t* seq_start = reinterpret_cast<const uint32_t*>(base + h.off_seq_start);
+    const uint64_t n = h.n_text;
+    std::vector<uint8_t> c(n);
+    for (uint64_t i = 0; i < n; ++i)
+        c[i] = ((nmask[i >> 6] >> (i & 63)) & 1ull) ? 4 : (uint8_t)((text[i >> 5] >> (2 * (i & 31))) & 3ull);
+    std::vector<uint32_t> nn(n + 1, 0); // prefix counts of N
+    for (uint64_t i = 0; i < n; ++i) nn[i + 1] = nn[i] + (c[i] == 4);
+    std::vector<uint64_t> starts; // every window start inside one sequence
+    std::vector<uint64_t> nwin;   // ... whose window holds 1..E N
+    for (uint32_t q = 0; q < h.n_seq; ++q) {
+        const uint64_t b = (uint64_t)seq_start[q] - q, e = (uint64_t)seq_start[q + 1] - (q + 1);
+        for (uint64_t t = b; t + K <= e; ++t) {
+            starts.push_back(t);
+            const uint32_t k = nn[t + K] - nn[t];
+            if (k >= 1 && k <= E) nwin.push_back(t);
+        }
+    }
+    const uint32_t maxv = value_bits == 16 ? 65535u : 255u;
+    auto matches = [&](uint64_t j, uint64_t t, bool rc) { // query window j (its reverse complement) against text window t
+        uint32_t e = 0;
+        for (uint32_t i = 0; i < K && e <= E; ++i) {
+            const uint8_t a = rc ? c[j + K - 1 - i] : c[j + i], b = c[t + i];
+            e += a == 4 || b == 4 || (rc ? 3 - a : a) != b;
+        }
+        return e <= E;
+    };
+    for (const WorkRange& r : ranges)
+        for (uint64_t j0 = r.begin; j0 < r.end; ++j0) {
+            const uint64_t j = text_begin + j0;
+            const uint32_t k = nn[j + K] - nn[j];
+            if (k > E) continue;
+            uint64_t v = 0;
+            if (k >= 1) {
+                for (uint64_t t : starts) v += matches(j, t, false) + (revcompl && matches(j, t, true));
+            } else {
+                v = value_bits == 16 ? static_cast<uint16_t*>(out)[j0] : static_cast<uint8_t*>(out)[j0];
+                for (uint64_t t : nwin) v += matches(j, t, false) + (revcompl && matches(j, t, true));
+            }
+            if (v > maxv) v = maxv;
+            if (value_bits == 16) static_cast<uint16_t*>(out)[j0] = (uint16_t)v;
+            else static_cast<uint8_t*>(out)[j0] = (uint8_t)v;
         }
 }
 // the locate instantiation (csv lists): counting pass, prefix sums, filling pass, per-list sort — the
@@ -239,9 +296,13 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     std::string err;
     const IndexHeader& h = *reinterpret_cast<const IndexHeader*>(base);
     BlockTables tabs;
-    if (!build_block_tables(K, E, block_kmers, ep, tabs, err, h.n_bwt, block_bases(h.sigma))) return -2;
+    // as capi.cu (dna5_nfree): on a Dna5 index with the suffix array the searches of an E >= 1 call skip the text's N
+    const char* nf_env = std::getenv("GMB_DNA5_NFREE");
+    const bool nfree = h.sigma == 5 && E >= 1 && !ep && h.off_sa != 0 && !(nf_env && nf_env[0] == '0');
+    if (!build_block_tables(K, E, block_kmers, ep, tabs, err, h.n_bwt, block_bases(h.sigma), nfree)) return -2;
     const uint32_t B = tabs.B;
     MapCtx cx;
+    cx.skip_n = nfree ? 1u : 0u;
     cx.blk[0] = base + h.off_fwd;
     cx.blk[1] = base + h.off_rev;
     cx.sent[0] = reinterpret_cast<const uint32_t*>(base + h.off_sent_fwd);
@@ -271,7 +332,7 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     std::vector<JumpPlan> plans(B + 1);
     uint32_t max_depth = 0;
     for (uint32_t cnt = 1; cnt <= B; ++cnt) {
-        plan_jump_tables(tabs.infix[cnt], want_depth, plans[cnt], E, h.n_bwt, sigma, cnt, B > 1);
+        plan_jump_tables(tabs.infix[cnt], want_depth, plans[cnt], E, h.n_bwt, sigma, cnt, B > 1, nfree);
         max_depth = std::max(max_depth, plans[cnt].max_depth);
     }
     std::vector<std::vector<JtFull>> full(max_depth + 1);
@@ -319,17 +380,21 @@ int hs_map(const void* blob, uint32_t K, uint32_t E, int revcompl, int value_bit
     // the two-phase driver of block_kernel.cu, where the library would launch it (capi.cu: get_plan)
     KeyLists kl;
     const char* bk_env = std::getenv("GMB_BLOCK_KERNEL");
-    const bool block_driver = E >= 1 && all_full && sigma == 4 && needle <= 64 && !(bk_env && bk_env[0] == '0') && build_key_lists(tabs, plans, kl);
-    if (block_driver) {
-        if (needle <= 32) { if (ep) run_ranges_blockdriver<1, true>(cx, kl, text, text_begin, ranges, value_bits, out, &f, &lr);
-                            else run_ranges_blockdriver<1, false>(cx, kl, text, text_begin, ranges, value_bits, out, &f, &lr); }
-        else { if (ep) run_ranges_blockdriver<2, true>(cx, kl, text, text_begin, ranges, value_bits, out, &f, &lr);
-               else run_ranges_blockdriver<2, false>(cx, kl, text, text_begin, ranges, value_bits, out, &f, &lr); }
+    const bool block_driver = E >= 1 && all_full && (sigma == 4 || nfree) && needle <= 64 && !(bk_env && bk_env[0] == '0') && build_key_lists(tabs, plans, kl);
+    if (block_driver && sigma == 5) {
+        if (needle <= 32) run_ranges_blockdriver<1, false, 5>(cx, kl, text, nmask, text_begin, ranges, value_bits, out, &f, &lr);
+        else run_ranges_blockdriver<2, false, 5>(cx, kl, text, nmask, text_begin, ranges, value_bits, out, &f, &lr);
+    } else if (block_driver) {
+        if (needle <= 32) { if (ep) run_ranges_blockdriver<1, true, 4>(cx, kl, text, nullptr, text_begin, ranges, value_bits, out, &f, &lr);
+                            else run_ranges_blockdriver<1, false, 4>(cx, kl, text, nullptr, text_begin, ranges, value_bits, out, &f, &lr); }
+        else { if (ep) run_ranges_blockdriver<2, true, 4>(cx, kl, text, nullptr, text_begin, ranges, value_bits, out, &f, &lr);
+               else run_ranges_blockdriver<2, false, 4>(cx, kl, text, nullptr, text_begin, ranges, value_bits, out, &f, &lr); }
     }
     else if (needle <= 32) RUN_KW(1);
     else if (needle <= 64) RUN_KW(2);
     else if (needle <= 128) RUN_KW(4);
     else RUN_KW(9);
+    if (nfree) nfix_bruteforce(h, base, K, E, revcompl != 0, text_begin, ranges, value_bits, out);
     if (fetches) { fetches[0] = f.total; for (int k = 0; k < 8; ++k) fetches[1 + k] = f.by_size[k]; fetches[9] = f.thin_paths; fetches[10] = f.iterations; fetches[11] = f.located; fetches[12] = f.text_reads; }
     if (lut_reads_out) *lut_reads_out = lr;
     return 0;
@@ -364,6 +429,7 @@ int hs_locate(const void* blob, uint32_t K, uint32_t E, int revcompl, uint64_t t
     cx.seq_start = reinterpret_cast<const uint32_t*>(base + h.off_seq_start);
     cx.seq_to_file = nullptr; cx.n_seq = h.n_seq; cx.own_file = 0; cx.all_files = 0;
     cx.loc_rows = nullptr; cx.text = reinterpret_cast<const uint64_t*>(base + h.off_text); cx.nmask = nullptr; cx.n_text = h.n_text; cx.E = E;
+    cx.skip_n = 0;
     const uint32_t want_depth = jump_depth < 0 ? default_jump_depth(h.n_bwt) : (uint32_t)jump_depth;
     JumpPlan plan;
     plan_jump_tables(tabs.infix[1], want_depth, plan, E, h.n_bwt, sigma, 1, false);

@@ -119,6 +119,129 @@ def test_cuda_dna5_matches_oracle(gm, K, E):
                 assert np.array_equal(got, want), (K, E, rc, B, depth, np.nonzero(got != want)[0][:10])
 
 
+def _dna5_genome_with_gaps():
+    seqs = T.repeat_rich(51, 3, 2500, with_n=True)
+    seqs[1][100:160] = 4
+    seqs[1][300:302] = 4
+    seqs[2][-5:] = 4
+    seqs[0][[7, 500, 501, 1200, 1230]] = 4
+    return seqs
+
+
+@pytest.mark.parametrize("K,E", [(20, 1), (20, 2), (14, 3), (9, 4), (30, 2), (40, 1), (33, 2), (70, 2), (130, 1)])
+def test_cuda_dna5_searches_that_skip_the_text_n_plus_the_n_pass(gm, K, E, monkeypatch):
+    """Dna5 index WITH the suffix array, E >= 1: the searches never match a text N, so they enter through
+    substituted keys and run in the two-phase kernel like on a Dna4 index; the N pass then locates the text windows with
+    1..E N through the index and adds the alignments to them.  Gap edges, a short run, isolated N, N at a sequence end,
+    both strands, every kernel, 8-bit saturation, selection intervals, position slices — against the oracle."""
+    seqs = _dna5_genome_with_gaps()
+    _, limits = T.concat(seqs)
+    orc, ix = T.Oracle(seqs), gm.Index.build(seqs, with_sa=True)
+    try:
+        for env in ({}, {"GMB_BLOCK_KERNEL": "0"}):
+            monkeypatch.delenv("GMB_BLOCK_KERNEL", raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            for rc in (True, False):
+                want = orc.map(K, E, revcompl=rc)
+                for B in (1, 3, 0):
+                    for depth in (0, 5, -1):
+                        ix.set_jump_depth(depth)
+                        p = gm.SearchParams(K, E, rev_compl=rc, block_kmers=B)
+                        got = ix.compute_mappability(p, chrom_cum_lengths=limits)
+                        assert np.array_equal(got, want), (K, E, rc, B, depth, env, np.nonzero(got != want)[0][:10])
+        monkeypatch.delenv("GMB_BLOCK_KERNEL", raising=False)
+        ix.set_jump_depth(-1)
+        iv = np.array([[90, 400], [2400, 2600], [5100, 7400]], dtype=np.uint64)
+        p8 = gm.SearchParams(K, E, True, False, 8)
+        assert np.array_equal(ix.compute_mappability(p8, chrom_cum_lengths=limits, intervals=iv), orc.map(K, E, value_bits=8, intervals=iv))
+        want = orc.map(K, E)
+        for a, b in ((0, 97), (97, 1201), (1201, 7500)):
+            got = ix.compute_mappability_range(gm.SearchParams(K, E), a, b, chrom_cum_lengths=limits)
+            assert np.array_equal(got, want[a:b]), (K, E, a, b)
+        start, value = ix.compute_runs(gm.SearchParams(K, E), chrom_cum_lengths=limits)
+        ends = np.append(start[1:], len(want)).astype(np.int64)
+        assert np.array_equal(np.repeat(value, ends - start.astype(np.int64)), want)
+    finally:
+        _close(ix)
+
+
+def test_cuda_dna5_n_pass_on_several_files_and_fragmented_genomes(gm):
+    """The N pass is built once for the whole index and applied per FASTA file (text_begin > 0); sequences of a few
+    dozen bases with N anywhere (windows and located contexts crossing sequence ends)."""
+    base = _dna5_genome_with_gaps()
+    rng = np.random.default_rng(9)
+    seqs, stf = [], []
+    for g in range(3):
+        for b in base:
+            b = b.copy()
+            m = (rng.random(len(b)) < 0.02 * g) & (b < 4)
+            b[m] = rng.integers(0, 4, int(m.sum()), dtype=np.uint8)
+            seqs.append(b); stf.append(g)
+    stf = np.array(stf, dtype=np.uint32)
+    _, limits = T.concat(seqs)
+    orc, ix = T.Oracle(seqs, seq_to_file=stf), gm.Index.build(seqs, with_sa=True, seq_to_file=stf)
+    try:
+        for K, E in ((24, 2), (30, 1)):
+            for f in (0, 1, 2):
+                got = _map(gm, ix, K, E, limits=limits, stf=stf, file_no=f)
+                assert np.array_equal(got, orc.map(K, E, file_no=f)), (K, E, f)
+    finally:
+        _close(ix)
+    seqs = T.fragmented_genome(4, 14000, with_n=True)
+    _, limits = T.concat(seqs)
+    orc, ix = T.Oracle(seqs), gm.Index.build(seqs, with_sa=True)
+    try:
+        for _ in range(12):
+            E = int(rng.integers(1, 5)); K = int(rng.integers(max(E + 2, 8), 40))
+            if E == 4 and K > 20:
+                K = 20
+            rc, B, bits = bool(rng.random() < 0.7), int(rng.integers(0, 7)), int(rng.choice([8, 16]))
+            ix.set_plan_text_size(int(rng.choice([0, 4 ** 9, 4 ** 12 - 1])))
+            want = orc.map(K, E, revcompl=rc, value_bits=bits)
+            got = ix.compute_mappability(gm.SearchParams(K, E, rc, False, bits, block_kmers=B), chrom_cum_lengths=limits)
+            assert np.array_equal(got, want), dict(K=K, E=E, rc=rc, B=B, bits=bits, at=np.nonzero(got != want)[0][:8])
+    finally:
+        _close(ix)
+
+
+def test_cuda_dna5_n_pass_at_2mbp_equals_the_walked_n_children_and_the_host_mirror(gm, monkeypatch):
+    """At a size where the substituted keys are really in use (depth 11): the two ways of treating the text's N give the
+    same counts on a 2 Mbp genome with assembly gaps, and the device reads what the host mirror reads."""
+    seqs = gm.synth_genome(2_000_000, 4, 77)
+    rng = np.random.default_rng(3)
+    for s in seqs:
+        a = int(rng.integers(0, len(s) - 60000))
+        s[a:a + 50000] = 4
+        for a in rng.integers(0, len(s) - 100, 12):
+            s[int(a):int(a) + int(rng.integers(1, 40))] = 4
+    _, limits = T.concat(seqs)
+    ix = gm.Index.build(seqs, with_sa=True)
+    try:
+        for K, E in ((30, 1), (30, 2), (50, 2)):
+            monkeypatch.setenv("GMB_DNA5_NFREE", "0")
+            walked, st0 = ix.compute_mappability(gm.SearchParams(K, E), chrom_cum_lengths=limits, count_fetches=True, return_stats=True)
+            monkeypatch.delenv("GMB_DNA5_NFREE")
+            got, st1 = ix.compute_mappability(gm.SearchParams(K, E), chrom_cum_lengths=limits, count_fetches=True, return_stats=True)
+            assert np.array_equal(got, walked), (K, E, np.nonzero(got != walked)[0][:10])
+            assert st1.rank_block_fetches < 0.8 * st0.rank_block_fetches, (K, E, st0.rank_block_fetches, st1.rank_block_fetches)
+    finally:
+        _close(ix)
+    small = _dna5_genome_with_gaps()
+    _, limits = T.concat(small)
+    ix, hs = gm.Index.build(small, with_sa=True), T.HostSim(small, with_sa=True)
+    try:
+        for K, E, B in ((20, 2, 4), (20, 1, 3), (33, 2, 3)):
+            ix.set_jump_depth(5)
+            out, st = ix.compute_mappability(gm.SearchParams(K, E, block_kmers=B), chrom_cum_lengths=limits, count_fetches=True, return_stats=True)
+            want = hs.map(K, E, jump_depth=5, block_kmers=B)
+            assert np.array_equal(out, want)
+            # (the two-phase kernel reads an entry again when a round puts more than eight aside: >= for the table reads)
+            assert st.rank_block_fetches == hs.last_fetch_stats[0] and st.jump_table_reads >= hs.last_lut_reads, (K, E, B)
+    finally:
+        _close(ix)
+
+
 def test_cuda_dna5_exclude_pseudo_bwt_export_and_fetch_counter(gm):
     base = T.repeat_rich(13, 2, 900, with_n=True)
     rng = np.random.default_rng(5)

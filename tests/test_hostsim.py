@@ -221,6 +221,38 @@ def test_dna5_matches_oracle(K, E):
                 assert np.array_equal(got, want), (K, E, rc, B, depth, np.nonzero(got != want)[0][:10])
 
 
+@pytest.mark.parametrize("K,E,B,depth", [(20, 1, 0, -1), (20, 1, 1, -1), (20, 2, 4, 5), (14, 3, 0, -1), (9, 4, 2, -1), (33, 2, 3, -1), (40, 1, 0, -1)])
+def test_dna5_searches_that_skip_the_text_n_plus_the_n_pass(K, E, B, depth, monkeypatch):
+    """Dna5 index WITH the suffix array, E >= 1: the searches never descend into an N child (so they enter through
+    substituted keys like on a Dna4 index; two-phase driver and general state machine), and the alignments to the text
+    windows with 1..E N are added by the N pass — here its brute-force mirror.  Gap edges, a short run, isolated N, N at
+    a sequence end; both strands, selection intervals, 8-bit saturation; against the oracle."""
+    seqs = T.repeat_rich(51, 3, 2500, with_n=True)
+    seqs[1][100:160] = 4
+    seqs[1][300:302] = 4
+    seqs[2][-5:] = 4
+    seqs[0][[7, 500, 501, 1200, 1230]] = 4
+    orc, hs = T.Oracle(seqs), T.HostSim(seqs, with_sa=True)
+    walked = T.HostSim(seqs)  # no suffix array: the N children are walked, no substituted keys
+    for env in ({}, {"GMB_BLOCK_KERNEL": "0"}):
+        monkeypatch.delenv("GMB_BLOCK_KERNEL", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for rc in (True, False):
+            want = orc.map(K, E, revcompl=rc)
+            got = hs.map(K, E, revcompl=rc, block_kmers=B, jump_depth=depth)
+            assert np.array_equal(got, want), (K, E, B, depth, rc, env, np.nonzero(got != want)[0][:10])
+    if (K, E, B, depth) == (20, 2, 4, 5):
+        keys = hs.last_lut_reads
+        walked.map(K, E, revcompl=False, block_kmers=B, jump_depth=depth)
+        assert keys > walked.last_lut_reads  # the substituted keys were in use
+    iv = np.array([[90, 400], [2400, 2600], [5100, 7400]], dtype=np.uint64)
+    want = orc.map(K, E, value_bits=8, intervals=iv)
+    assert np.array_equal(hs.map(K, E, value_bits=8, intervals=iv, block_kmers=B, jump_depth=depth), want)
+    monkeypatch.setenv("GMB_DNA5_NFREE", "0")
+    assert np.array_equal(hs.map(K, E, block_kmers=B, jump_depth=depth), orc.map(K, E))
+
+
 def test_dna5_exclude_pseudo_and_reference_fixtures():
     import test_ref_fixtures as RF
     for line in [c for c in RF.CASES if c.startswith("dna5")]:

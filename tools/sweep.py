@@ -21,6 +21,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--kmer", type=int, default=30)
 ap.add_argument("--rep-frac", type=float, default=0.05, help="fraction of every chromosome covered by planted repeat copies")
 ap.add_argument("--rep-mut", type=float, default=0.02, help="substitution rate of the planted copies")
+ap.add_argument("--with-sa", action="store_true", help="keep the suffix array in the index (Dna5: enables the searches that skip the text's N + the N pass)")
 ap.add_argument("--n-frac", type=float, default=0.0, help="fraction of every chromosome turned into runs of N (-> Dna5 index)")
 args = ap.parse_args()
 
@@ -36,7 +37,7 @@ if args.n_frac > 0:  # assembly-gap model: one long run per chromosome (centrome
         small = max(1, int(len(s) * args.n_frac * 0.1) // 20)
         for a in rng.integers(0, len(s) - small, 20):
             s[int(a):int(a) + small] = 4
-ix = gm.Index.build(seqs, on_gpu=True)
+ix = gm.Index.build(seqs, on_gpu=True, with_sa=args.with_sa)
 print("genome+index %.1f s, build %s" % (time.time() - t0, ix.build_timings_ms), flush=True)
 n = ix.n_text
 out = torch.zeros(n, dtype=torch.int16, device="cuda")
