@@ -72,7 +72,8 @@ typedef struct gmb_index_info {
     uint64_t rank_block_bytes; /* one 32-byte sector: 64 symbols (Dna4) or 32 symbols (Dna5) per block */
     void *device_blob;    /* device address of the blob (for broadcast / diagnostics) */
     int32_t device;
-    int32_t alphabet_size; /* 4 = Dna4; 5 = Dna5, chosen when the text contains N (src/indexing.hpp:459-473) */
+    int32_t alphabet_size; /* 4 = Dna4; 5 = Dna5, chosen when the text contains N (src/indexing.hpp:459-473).  A Dna5 index
+                            * that holds the suffix array is searched faster at E >= 1: same results */
     uint64_t jump_table_bytes; /* HBM currently held by the handle's jump tables (built lazily by the map calls) */
 } gmb_index_info;
 
