@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, MINB) block_kernel(const MapLaunch L
                 // an N in the common infix is an N in every window of the block: nothing to search (windows with 1..E N
                 // get their counts from the N pass, the others have none)
                 st.has_n = st.pat.has_n();
-                if (st.has_n && st.pat.has_n(cnt - 1u, K - cnt + 1u)) nk = 0u;
+                if (st.has_n && st.pat.has_n_in(cnt - 1u, K - cnt + 1u)) nk = 0u;
             }
         }
 

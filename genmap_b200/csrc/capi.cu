@@ -11,6 +11,7 @@
 #include <new>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <memory>
 #include <string>
 #include <thread>
@@ -1253,9 +1254,7 @@ int ensure_nfix(gmb_index* ix, const gmb_params* p, const NFix** out)
         if (q->K == p->K && q->E == p->E && q->revcompl == rc) { *out = q.get(); return GMB_OK; }
     CU(cudaSetDevice(ix->device));
     CU(cudaDeviceSynchronize()); // the locate passes below use the handle's scratch on the default stream
-    cudaEvent_t t0 = nullptr, t1 = nullptr;
-    CU(cudaEventCreate(&t0)); CU(cudaEventCreate(&t1));
-    CU(cudaEventRecord(t0, nullptr));
+    const auto t0 = std::chrono::steady_clock::now(); // (every step below ends in a synchronous copy)
     std::unique_ptr<NFix> nf(new (std::nothrow) NFix);
     if (!nf) return fail(GMB_ERR_NOMEM, "out of host memory");
     nf->K = p->K; nf->E = p->E; nf->revcompl = rc;
@@ -1272,7 +1271,7 @@ int ensure_nfix(gmb_index* ix, const gmb_params* p, const NFix** out)
     CU(nfix_collect_windows(nmask, n_text, seq_start, ix->h.n_seq, p->K, p->E, win.as<uint32_t>(), counter.as<unsigned long long>(), cap, nullptr));
     unsigned long long n_win = 0;
     CU(cudaMemcpy(&n_win, counter.p, 8, cudaMemcpyDeviceToHost));
-    if (n_win > cap || n_win + p->K - 1 > n_text) { ix->nfix_off = true; cudaEventDestroy(t0); cudaEventDestroy(t1); return GMB_OK; }
+    if (n_win > cap || n_win + p->K - 1 > n_text) { ix->nfix_off = true; return GMB_OK; }
     nf->n_win = n_win;
     std::vector<uint32_t> hits_host;
     if (n_win) {
@@ -1295,7 +1294,7 @@ int ensure_nfix(gmb_index* ix, const gmb_params* p, const NFix** out)
                                  nf->d_win_count + b, hits.as<uint32_t>(), counter.as<unsigned long long>(), nullptr));
             unsigned long long n_h = 0;
             CU(cudaMemcpy(&n_h, counter.p, 8, cudaMemcpyDeviceToHost));
-            if (hits_host.size() + n_h > kMaxHits) { ix->nfix_off = true; cudaEventDestroy(t0); cudaEventDestroy(t1); return GMB_OK; }
+            if (hits_host.size() + n_h > kMaxHits) { ix->nfix_off = true; return GMB_OK; }
             const size_t at = hits_host.size();
             hits_host.resize(at + n_h);
             if (n_h) CU(cudaMemcpy(hits_host.data() + at, hits.p, n_h * 4, cudaMemcpyDeviceToHost));
@@ -1307,12 +1306,9 @@ int ensure_nfix(gmb_index* ix, const gmb_params* p, const NFix** out)
         CU(cudaMalloc(&nf->d_hits, nf->n_hits * 4));
         CU(cudaMemcpy(nf->d_hits, hits_host.data(), nf->n_hits * 4, cudaMemcpyHostToDevice));
     }
-    CU(cudaEventRecord(t1, nullptr));
-    CU(cudaEventSynchronize(t1));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, t0, t1);
+    CU(cudaDeviceSynchronize());
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     nf->build_ms = ms;
-    cudaEventDestroy(t0); cudaEventDestroy(t1);
     if (const char* v = std::getenv("GMB_VERBOSE"); v && v[0] == '1')
         std::fprintf(stderr, "[gmb] N pass of (K=%u, E=%u): %llu windows with N, %llu alignments to them, built in %.1f ms\n", p->K, p->E,
                      (unsigned long long)nf->n_win, (unsigned long long)nf->n_hits, ms);

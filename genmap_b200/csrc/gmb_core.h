@@ -288,6 +288,22 @@ struct Pattern {
         }
         return false;
     }
+    // does any of the characters [a, a + d) equal N?  (any d)
+    GMB_HD bool has_n_in(uint32_t a, uint32_t d) const
+    {
+        if constexpr (SIGMA == 5) {
+#pragma unroll
+            for (int k = 0; k < KW; ++k) {
+                const uint32_t lo = 32u * (uint32_t)k, hi = lo + 32u; // the characters of word k
+                const uint32_t b = a > lo ? a : lo, e = a + d < hi ? a + d : hi;
+                if (b < e) {
+                    const uint32_t len = e - b, m = (len == 32u ? ~0u : ((1u << len) - 1u)) << (b - lo);
+                    if (nm[k] & m) return true;
+                }
+            }
+        }
+        return false;
+    }
     GMB_HD bool has_n() const
     {
         uint32_t any = 0;

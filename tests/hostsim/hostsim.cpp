@@ -67,7 +67,7 @@ void run_ranges_blockdriver(const MapCtx& cx, const KeyLists& kl, const uint64_t
             for (uint32_t w = 0; w < cnt * (EP ? 3u : 1u); ++w) fr.cset(kLeafWords + w, 0u);
             // Dna5: an N in the common infix is an N in every window of the block — nothing to search (the windows with
             // 1..E N get their counts from the N pass, the others have none)
-            const bool dead = SIGMA == 5 && st.pat.has_n(cnt - 1, cx.K - cnt + 1);
+            const bool dead = SIGMA == 5 && st.pat.has_n_in(cnt - 1, cx.K - cnt + 1);
             for (uint32_t strand = 0; strand < (dead ? 0u : cx.n_strands); ++strand) {
                 st.strand = strand;
                 if (strand == 1) st.pat.reverse_complement(NL);

@@ -248,7 +248,7 @@ def test_cuda_dna5_n_pass_at_2mbp_equals_the_walked_n_children_and_the_host_mirr
     _, limits = T.concat(small)
     ix, hs = gm.Index.build(small, with_sa=True), T.HostSim(small, with_sa=True)
     try:
-        for K, E, B in ((20, 2, 4), (20, 1, 3), (33, 2, 3)):
+        for K, E, B in ((20, 2, 4), (20, 1, 3), (33, 2, 3), (33, 2, 1), (40, 2, 3)):
             ix.set_jump_depth(5)
             out, st = ix.compute_mappability(gm.SearchParams(K, E, block_kmers=B), chrom_cum_lengths=limits, count_fetches=True, return_stats=True)
             want = hs.map(K, E, jump_depth=5, block_kmers=B)
@@ -271,7 +271,7 @@ def test_cuda_dna5_exclude_pseudo_bwt_export_and_fetch_counter(gm):
             ms.append(s); stf.append(g)
     stf = np.array(stf, dtype=np.uint32)
     _, limits = T.concat(ms)
-    mo, ix, hs = T.Oracle(ms, seq_to_file=stf), gm.Index.build(ms, with_sa=True, seq_to_file=stf), T.HostSim(ms)
+    mo, ix, hs = T.Oracle(ms, seq_to_file=stf), gm.Index.build(ms, with_sa=True, seq_to_file=stf), T.HostSim(ms, with_sa=True)
     for rev in (False, True):
         assert np.array_equal(ix.export_bwt(rev), mo.bwt(rev))
     assert np.array_equal(ix.export_sa(), mo.sa().astype(np.uint32))
