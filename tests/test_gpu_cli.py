@@ -4,6 +4,7 @@ import filecmp
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 import gmtest as T
@@ -128,13 +129,19 @@ def test_cli_maps_on_an_index_written_by_the_reference(genmap, tmp_path):
             assert not mismatch and not errors, (case, sub, mismatch, errors)
 
 
-def test_cli_multi_gpu_sharding_gives_identical_files(genmap, tmp_path):
+@pytest.mark.parametrize("with_n", [False, True], ids=["dna4", "dna5"])
+def test_cli_multi_gpu_sharding_gives_identical_files(genmap, tmp_path, with_n):
     from genmap_b200 import _lib
     if _lib.lib().gmb_device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import genmap_b200 as gm
     fa = str(tmp_path / "g.fa")
-    T.write_fasta(fa, gm.synth_genome(600_000, 3, 3))
+    seqs = gm.synth_genome(600_000, 3, 3)
+    if with_n:  # assembly gaps, one of them across the middle of the text where the two GPUs' slices meet: every GPU
+        seqs[0][50_000:60_000] = 4  # builds the N pass for the whole index and applies it to its own positions
+        seqs[1][95_000:105_000] = 4
+        seqs[2][1000:1003] = 4
+    T.write_fasta(fa, seqs)
     idx = str(tmp_path / "index")
     assert subprocess.run([genmap, "index", "-F", fa, "-I", idx]).returncode == 0
     outs = []
@@ -154,6 +161,7 @@ def test_cli_multi_gpu_sharding_gives_identical_files(genmap, tmp_path):
         assert filecmp.cmp(str(out / "g.genmap.bedgraph"), str(out2 / "g.genmap.bedgraph"), shallow=False)
     for name in os.listdir(str(outs[0])):
         assert filecmp.cmp(str(outs[0] / name), str(outs[1] / name), shallow=False), name
+    assert np.array_equal(np.fromfile(str(outs[1] / "g.genmap.freq16"), dtype=np.uint16), T.Oracle(seqs).map(30, 1))
 
 
 def test_cli_csv_matches_the_reference_binary(genmap, tmp_path):
