@@ -411,6 +411,8 @@ def hostsim_lib():
         L.hs_export_bwt.argtypes = [vp, ci, vp]
         L.hs_export_sa.restype = ci
         L.hs_export_sa.argtypes = [vp, vp]
+        L.hs_has_n_selftest.restype = ci
+        L.hs_has_n_selftest.argtypes = [u64]
         L.hs_step_tables.restype = ci
         L.hs_step_tables.argtypes = [u32, u32, ctypes.POINTER(u32), vp]
         L.hs_map.restype = ci

@@ -222,6 +222,35 @@ void locate_host_singletons(const MapCtx& cx, uint32_t d, std::vector<JtFull>& f
 }
 } // namespace
 
+// Pattern<KW, 5>::has_n_in / has_n against a per-character loop, for every (offset, length) of random N masks
+// (block_kernel.cu asks it about common infixes of 32 and more characters); returns the number of disagreements
+template <int KW>
+static int has_n_selftest(uint64_t seed)
+{
+    int bad = 0;
+    for (int round = 0; round < 64; ++round) {
+        Pattern<KW, 5> p;
+        for (int k = 0; k < KW; ++k) {
+            seed = seed * 6364136223846793005ull + 1442695040888963407ull;
+            p.w[k] = seed;
+            // sparse masks (and a few empty / full ones): single bits are what a wrong shift loses
+            p.nm[k] = round % 8 == 0 ? 0u : (round % 8 == 1 ? ~0u : (1u << ((seed >> 40) & 31u)) | ((seed >> 13) & 1u ? 1u << ((seed >> 20) & 31u) : 0u));
+        }
+        const uint32_t n = 32u * KW;
+        for (uint32_t a = 0; a < n; ++a)
+            for (uint32_t d = 0; a + d <= n; ++d) {
+                bool want = false;
+                for (uint32_t i = a; i < a + d; ++i) want = want || ((p.nm[i >> 5] >> (i & 31u)) & 1u);
+                bad += p.has_n_in(a, d) != want;
+                if (d >= 1 && d <= 16) bad += p.has_n(a, d) != want; // the table-key form (d <= 16)
+            }
+        bool any = false;
+        for (uint32_t i = 0; i < n; ++i) any = any || ((p.nm[i >> 5] >> (i & 31u)) & 1u);
+        bad += p.has_n() != any;
+    }
+    return bad;
+}
+
 extern "C" {
 
 int hs_build(const uint8_t* codes, const uint64_t* limits, uint32_t n_seq, int with_sa, void** blob_out, uint64_t* bytes)
@@ -471,5 +500,7 @@ int hs_locate(const void* blob, uint32_t K, uint32_t E, int revcompl, uint64_t t
     *rows_out = r;
     return 0;
 }
+
+int hs_has_n_selftest(uint64_t seed) { return has_n_selftest<1>(seed) + has_n_selftest<2>(seed + 1) + has_n_selftest<4>(seed + 2) + has_n_selftest<9>(seed + 3); }
 
 } // extern "C"

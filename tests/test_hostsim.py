@@ -253,6 +253,12 @@ def test_dna5_searches_that_skip_the_text_n_plus_the_n_pass(K, E, B, depth, monk
     assert np.array_equal(hs.map(K, E, block_kmers=B, jump_depth=depth), orc.map(K, E))
 
 
+def test_pattern_n_mask_queries_for_every_offset_and_length():
+    """Pattern<KW, 5>::has_n_in (any length: the common infix of a block), has_n(a, d <= 16) (table keys) and has_n()
+    against a per-character loop — a shift by 32 or more is where x86 and the GPU part ways (profiles/r02 s28)."""
+    assert T.hostsim_lib().hs_has_n_selftest(12345) == 0
+
+
 def test_dna5_exclude_pseudo_and_reference_fixtures():
     import test_ref_fixtures as RF
     for line in [c for c in RF.CASES if c.startswith("dna5")]:
